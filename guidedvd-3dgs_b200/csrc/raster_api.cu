@@ -1,0 +1,271 @@
+// raster_api.cu -- C-ABI entry points (include/gvd_raster.h): buffer carving, stage sequencing,
+// CUB scan + radix sort. Mirrors the control flow of DGR/cuda_rasterizer/rasterizer_impl.cu:197-447
+// on an explicit stream; no torch types, no allocation.
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/gvd_raster.h"
+#include "raster_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* what, cudaError_t e) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+}
+int fail_msg(const std::string& s) {
+    g_err = s;
+    return 2;
+}
+
+#define GVD_CHECK(expr, what)                         \
+    do {                                              \
+        cudaError_t _e = (expr);                      \
+        if (_e != cudaSuccess) return fail(what, _e); \
+    } while (0)
+
+// after a launch: always catch launch-config errors; in debug mode also sync (auxiliary.h:166-173)
+#define GVD_STAGE(what)                                                   \
+    do {                                                                  \
+        cudaError_t _e = cudaGetLastError();                              \
+        if (_e != cudaSuccess) return fail(what, _e);                     \
+        if (debug) {                                                      \
+            _e = cudaStreamSynchronize(stream);                           \
+            if (_e != cudaSuccess) return fail(what " (debug sync)", _e); \
+        }                                                                 \
+    } while (0)
+
+template <typename T>
+void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128) {
+    size_t offset = (reinterpret_cast<uintptr_t>(chunk) + alignment - 1) & ~(alignment - 1);
+    ptr = reinterpret_cast<T*>(offset);
+    chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+// The three carve_* functions define the scratch layouts; calling them on a null base yields sizes
+// (same trick as CudaRasterizer::required<T>, rasterizer_impl.h:63-69).
+RasterGeomPtrs carve_geom(char*& chunk, size_t P) {
+    RasterGeomPtrs g;
+    obtain(chunk, g.splat, P);
+    obtain(chunk, g.clamped, P);
+    obtain(chunk, g.tiles_touched, P);
+    obtain(chunk, g.point_offsets, P);
+    g.scan_temp_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, (int)P);
+    obtain(chunk, g.scan_temp, g.scan_temp_bytes);
+    return g;
+}
+
+RasterBinPtrs carve_binning(char*& chunk, size_t R) {
+    RasterBinPtrs b;
+    obtain(chunk, b.point_list, R);
+    obtain(chunk, b.point_list_unsorted, R);
+    obtain(chunk, b.keys, R);
+    obtain(chunk, b.keys_unsorted, R);
+    b.sort_temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b.sort_temp_bytes, b.keys_unsorted, b.keys, b.point_list_unsorted,
+                                    b.point_list, (int)R);
+    obtain(chunk, b.sort_temp, b.sort_temp_bytes);
+    obtain(chunk, b.packed, R);
+    return b;
+}
+
+RasterImgPtrs carve_img(char*& chunk, size_t tiles, size_t pixels) {
+    RasterImgPtrs im;
+    obtain(chunk, im.ranges, tiles);
+    obtain(chunk, im.n_contrib, pixels);
+    return im;
+}
+
+// rasterizer_impl.cu:35-50
+uint32_t higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb)
+            msb += step;
+        else
+            msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+inline dim3 tile_grid(int width, int height) {
+    return dim3((width + GVD_TILE_X - 1) / GVD_TILE_X, (height + GVD_TILE_Y - 1) / GVD_TILE_Y, 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvd_raster_abi_version(void) { return GVD_RASTER_ABI_VERSION; }
+const char* gvd_last_error(void) { return g_err.c_str(); }
+
+size_t gvd_raster_geom_bytes(int P) {
+    char* p = nullptr;
+    carve_geom(p, (size_t)P);
+    return (size_t)p + 128;
+}
+size_t gvd_raster_binning_bytes(int R) {
+    char* p = nullptr;
+    carve_binning(p, (size_t)R);
+    return (size_t)p + 128;
+}
+size_t gvd_raster_img_bytes(int width, int height) {
+    char* p = nullptr;
+    dim3 g = tile_grid(width, height);
+    carve_img(p, (size_t)g.x * g.y, (size_t)width * height);
+    return (size_t)p + 128;
+}
+size_t gvd_raster_backward_scratch_bytes(int P) { return (size_t)P * GVD_ACC_STRIDE * sizeof(float) + 128; }
+
+int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out) {
+    if (!out) return fail_msg("gvd_raster_layout: null out");
+    char* p = nullptr;
+    RasterGeomPtrs g = carve_geom(p, (size_t)P);
+    out->geom_splat = (size_t)g.splat;
+    out->geom_clamped = (size_t)g.clamped;
+    out->geom_tiles_touched = (size_t)g.tiles_touched;
+    out->geom_point_offsets = (size_t)g.point_offsets;
+    p = nullptr;
+    RasterBinPtrs b = carve_binning(p, (size_t)R);
+    out->bin_point_list = (size_t)b.point_list;
+    out->bin_point_list_keys = (size_t)b.keys;
+    out->bin_point_list_unsorted = (size_t)b.point_list_unsorted;
+    out->bin_keys_unsorted = (size_t)b.keys_unsorted;
+    out->bin_packed = (size_t)b.packed;
+    p = nullptr;
+    dim3 tg = tile_grid(width, height);
+    RasterImgPtrs im = carve_img(p, (size_t)tg.x * tg.y, (size_t)width * height);
+    out->img_ranges = (size_t)im.ranges;
+    out->img_n_contrib = (size_t)im.n_contrib;
+    return 0;
+}
+
+int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a) return fail_msg("gvd_raster_forward: null args");
+    const bool debug = a->debug != 0;
+    a->num_rendered = 0;
+    if (a->P <= 0) return 0;
+    if (a->width <= 0 || a->height <= 0) return fail_msg("gvd_raster_forward: bad image size");
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
+        return fail_msg("Please provide excatly one of either SHs or precomputed colors!");
+    if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
+        ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
+        return fail_msg("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    if (!a->geom_alloc || !a->binning_alloc || !a->img_alloc) return fail_msg("gvd_raster_forward: null allocator");
+    if (a->shs && (a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
+        return fail_msg("gvd_raster_forward: SH degree / coefficient count mismatch");
+
+    const int P = a->P;
+    const float focal_y = a->height / (2.0f * a->tan_fovy);
+    const float focal_x = a->width / (2.0f * a->tan_fovx);
+    const dim3 grid = tile_grid(a->width, a->height);
+    if (grid.x > 0xffff || grid.y > 0xffff) return fail_msg("gvd_raster_forward: image too large");
+    const size_t tiles = (size_t)grid.x * grid.y;
+
+    char* gp = (char*)a->geom_alloc(a->alloc_user, gvd_raster_geom_bytes(P));
+    if (!gp) return fail_msg("gvd_raster_forward: geometry allocator returned null");
+    RasterGeomPtrs g = carve_geom(gp, (size_t)P);
+    char* ip = (char*)a->img_alloc(a->alloc_user, gvd_raster_img_bytes(a->width, a->height));
+    if (!ip) return fail_msg("gvd_raster_forward: image allocator returned null");
+    RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
+
+    gvd_launch_preprocess(*a, g, focal_x, focal_y, grid, stream);
+    GVD_STAGE("preprocess");
+
+    GVD_CHECK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, P,
+                                            stream),
+              "InclusiveSum");
+    GVD_STAGE("scan");
+
+    // Size of the instance list. Like the reference (rasterizer_impl.cu:281-282) this is the one
+    // host round trip of the forward: the binning buffer is caller-owned and sized from R.
+    int num_rendered = 0;
+    GVD_CHECK(cudaMemcpyAsync(&num_rendered, g.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, stream),
+              "copy num_rendered");
+    GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
+    a->num_rendered = num_rendered;
+
+    char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered));
+    if (!bp) return fail_msg("gvd_raster_forward: binning allocator returned null");
+    RasterBinPtrs b = carve_binning(bp, (size_t)num_rendered);
+
+    GVD_CHECK(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), stream), "memset ranges");
+    if (num_rendered > 0) {
+        gvd_launch_emit_keys(P, g, b, grid, stream);
+        GVD_STAGE("emit_keys");
+
+        const int bit = (int)higher_msb((uint32_t)tiles);
+        GVD_CHECK(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys,
+                                                  b.point_list_unsorted, b.point_list, num_rendered, 0, 32 + bit,
+                                                  stream),
+                  "SortPairs");
+        GVD_STAGE("sort");
+
+        gvd_launch_pack(num_rendered, g, b, im, grid, stream);
+        GVD_STAGE("pack");
+    }
+    gvd_launch_render_forward(*a, b, im, grid, stream);
+    GVD_STAGE("render_forward");
+    return 0;
+}
+
+int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a) return fail_msg("gvd_raster_backward: null args");
+    const bool debug = a->debug != 0;
+    if (a->P <= 0) return 0;
+    if (!a->geom_buffer || !a->img_buffer || !a->scratch) return fail_msg("gvd_raster_backward: null scratch buffer");
+    if (a->R > 0 && !a->binning_buffer) return fail_msg("gvd_raster_backward: null binning buffer");
+    if (!a->dL_dmeans2D || !a->dL_dmeans3D || !a->dL_dopacity) return fail_msg("gvd_raster_backward: null output");
+    if (a->shs && !a->dL_dsh) return fail_msg("gvd_raster_backward: shs given but dL_dsh is null");
+    if (a->scales && (!a->dL_dscales || !a->dL_drotations || !a->rotations))
+        return fail_msg("gvd_raster_backward: scales given but dL_dscales/dL_drotations is null");
+    if (!a->scales && !a->cov3D_precomp) return fail_msg("gvd_raster_backward: neither scales nor cov3D_precomp");
+
+    const int P = a->P;
+    const float focal_y = a->height / (2.0f * a->tan_fovy);
+    const float focal_x = a->width / (2.0f * a->tan_fovx);
+    const dim3 grid = tile_grid(a->width, a->height);
+    const size_t tiles = (size_t)grid.x * grid.y;
+
+    char* gp = (char*)a->geom_buffer;
+    RasterGeomPtrs g = carve_geom(gp, (size_t)P);
+    char* bp = (char*)a->binning_buffer;
+    RasterBinPtrs b = carve_binning(bp, (size_t)a->R);
+    char* ip = (char*)a->img_buffer;
+    RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
+
+    float* acc = reinterpret_cast<float*>(((uintptr_t)a->scratch + 127) & ~(uintptr_t)127);
+    GVD_CHECK(cudaMemsetAsync(acc, 0, (size_t)P * GVD_ACC_STRIDE * sizeof(float), stream), "memset acc");
+
+    if (a->R > 0) {
+        gvd_launch_render_backward(*a, b, im, acc, grid, stream);
+        GVD_STAGE("render_backward");
+    }
+    gvd_launch_gaussian_backward(*a, g, acc, focal_x, focal_y, stream);
+    GVD_STAGE("gaussian_backward");
+    return 0;
+}
+
+int gvd_raster_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                            uint8_t* present, gvd_stream_t stream_) {
+    (void)projmatrix;  // the reference passes it but only the view-space z test is live (auxiliary.h:154)
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (P <= 0) return 0;
+    if (!means3D || !viewmatrix || !present) return fail_msg("gvd_raster_mark_visible: null pointer");
+    gvd_launch_mark_visible(P, means3D, viewmatrix, present, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("mark_visible", e);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// raster_common.cuh -- shared definitions for the B200-native Gaussian rasterizer.
+//
+// Data layout in HBM (all caller-owned scratch, see include/gvd_raster.h):
+//   geom   : SplatRec[P]  (48 B per Gaussian, written by preprocess, gathered by pack)
+//            uint8 clamped[P], uint32 tiles_touched[P], uint32 point_offsets[P], scan temp
+//   binning: uint32 point_list[R], uint64 keys[R], unsorted copies, sort temp,
+//            SplatRec packed[R] -- per (Gaussian,tile) instance, in sorted order, so one tile's
+//            list is ONE contiguous byte range that the render kernels stage with TMA bulk copies.
+//   img    : uint2 ranges[T], uint32 n_contrib[H*W]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GVD_TILE_X 16
+#define GVD_TILE_Y 16
+#define GVD_BLOCK 256      // threads per render CTA = pixels per tile
+#define GVD_BATCH 256      // tile-list entries staged per TMA bulk copy
+#define GVD_ACC_STRIDE 12  // floats per Gaussian in the backward accumulator
+
+// 48-byte record. Per-Gaussian (geom) and per-instance (packed) flavours share a.. and c.xy:
+//   a = {mean2D.x, mean2D.y, conic.x, conic.y}
+//   b = {conic.z, opacity, rgb.r, rgb.g}
+//   c = {rgb.b, depth, w0, w1}
+//       geom  : w0 = rect_min.x | rect_min.y<<16 ; w1 = rect_max.x | rect_max.y<<16 (tile units)
+//       packed: w0 = Gaussian id                 ; w1 = 8-bit sub-tile mask (bit w = warp w's 8x4 pixels)
+struct __align__(16) SplatRec {
+    float4 a, b, c;
+};
+
+struct RasterGeomPtrs {
+    SplatRec* splat;
+    uint8_t* clamped;
+    uint32_t* tiles_touched;
+    uint32_t* point_offsets;
+    char* scan_temp;
+    size_t scan_temp_bytes;
+};
+
+struct RasterBinPtrs {
+    uint32_t* point_list;
+    uint32_t* point_list_unsorted;
+    uint64_t* keys;
+    uint64_t* keys_unsorted;
+    char* sort_temp;
+    size_t sort_temp_bytes;
+    SplatRec* packed;
+};
+
+struct RasterImgPtrs {
+    uint2* ranges;
+    uint32_t* n_contrib;
+};
+
+// ---- launchers implemented in the .cu files -------------------------------------------
+struct GvdRasterForwardArgs;
+struct GvdRasterBackwardArgs;
+
+void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, float focal_x, float focal_y,
+                           dim3 grid, cudaStream_t s);
+void gvd_launch_emit_keys(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, dim3 grid, cudaStream_t s);
+void gvd_launch_pack(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im, dim3 grid,
+                     cudaStream_t s);
+void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                               dim3 grid, cudaStream_t s);
+void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                                float* acc, dim3 grid, cudaStream_t s);
+void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
+                                  float focal_x, float focal_y, cudaStream_t s);
+void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                             cudaStream_t s);
+
+// ---- small device helpers ----------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Column-major 3x3 with the exact operation order of the math library the reference uses
+// (glm::mat3: m[col][row]; operator* and transpose written out term by term), so that the
+// compiler sees the same expression trees as in DGR/cuda_rasterizer/forward.cu:74-152.
+struct M3 {
+    float m[3][3];
+};
+
+__device__ __forceinline__ M3 m3_make(float x0, float y0, float z0, float x1, float y1, float z1, float x2,
+                                      float y2, float z2) {
+    M3 r;
+    r.m[0][0] = x0; r.m[0][1] = y0; r.m[0][2] = z0;
+    r.m[1][0] = x1; r.m[1][1] = y1; r.m[1][2] = z1;
+    r.m[2][0] = x2; r.m[2][1] = y2; r.m[2][2] = z2;
+    return r;
+}
+
+__device__ __forceinline__ M3 m3_mul(const M3& p, const M3& q) {
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int w = 0; w < 3; ++w)
+            r.m[c][w] = p.m[0][w] * q.m[c][0] + p.m[1][w] * q.m[c][1] + p.m[2][w] * q.m[c][2];
+    return r;
+}
+
+__device__ __forceinline__ M3 m3_transpose(const M3& p) {
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int w = 0; w < 3; ++w) r.m[c][w] = p.m[w][c];
+    return r;
+}
+
+// auxiliary.h:58-77 (matrices arrive transposed; index as column-major)
+__device__ __forceinline__ float3 xform_point_4x3(const float3& p, const float* __restrict__ m) {
+    float3 t = {
+        m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+        m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+        m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+    };
+    return t;
+}
+
+__device__ __forceinline__ float4 xform_point_4x4(const float3& p, const float* __restrict__ m) {
+    float4 t = {
+        m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+        m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+        m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+        m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15],
+    };
+    return t;
+}
+
+// auxiliary.h:41-44 -- evaluated in DOUBLE (the literals 1.0 / 0.5 promote), then narrowed.
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// forward.cu:118-152. Quaternion used as given (not normalised). Sigma = (S R)^T (S R).
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot,
+                                                     float* cov3D) {
+    // S is diagonal; the reference multiplies the full matrices (zeros included) -- the extra
+    // "+ 0*x" terms are exact, so M[c][r] = fl(s_r * R[c][r]).
+    const float sx = mod * scale.x, sy = mod * scale.y, sz = mod * scale.z;
+    const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+    M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                   2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                   2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    M3 M;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        M.m[c][0] = sx * R.m[c][0];
+        M.m[c][1] = sy * R.m[c][1];
+        M.m[c][2] = sz * R.m[c][2];
+    }
+    M3 Sigma = m3_mul(m3_transpose(M), M);
+    cov3D[0] = Sigma.m[0][0];
+    cov3D[1] = Sigma.m[0][1];
+    cov3D[2] = Sigma.m[0][2];
+    cov3D[3] = Sigma.m[1][1];
+    cov3D[4] = Sigma.m[1][2];
+    cov3D[5] = Sigma.m[2][2];
+}
+
+// SH basis constants, auxiliary.h:21-39
+#define GVD_SH_C0 0.28209479177387814f
+#define GVD_SH_C1 0.4886025119029199f
+#define GVD_SH_C2_0 1.0925484305920792f
+#define GVD_SH_C2_1 -1.0925484305920792f
+#define GVD_SH_C2_2 0.31539156525252005f
+#define GVD_SH_C2_3 -1.0925484305920792f
+#define GVD_SH_C2_4 0.5462742152960396f
+#define GVD_SH_C3_0 -0.5900435899266435f
+#define GVD_SH_C3_1 2.890611442640554f
+#define GVD_SH_C3_2 -0.4570457994644658f
+#define GVD_SH_C3_3 0.3731763325901154f
+#define GVD_SH_C3_4 -0.4570457994644658f
+#define GVD_SH_C3_5 1.445305721320277f
+#define GVD_SH_C3_6 -0.5900435899266435f
+
+__device__ __forceinline__ float3 f3_add(float3 a, float3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ float3 f3_sub(float3 a, float3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float3 f3_scale(float s, float3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float f3_dot(float3 a, float3 b) {
+    float tx = a.x * b.x, ty = a.y * b.y, tz = a.z * b.z;
+    return tx + ty + tz;
+}
+
+// ---- mbarrier / TMA bulk-copy wrappers (sm_90+; SASS: UBLKCP + SYNCS) ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk async copy, completion signalled on an mbarrier (bytes % 16 == 0).
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,134 @@
+"""B200-native drop-in for the reference package `diff_gaussian_rasterization`
+(DGR/diff_gaussian_rasterization/__init__.py).  Same public names, signatures and semantics:
+
+    GaussianRasterizationSettings(image_height, image_width, tanfovx, tanfovy, bg, scale_modifier,
+                                  viewmatrix, projmatrix, sh_degree, campos, prefiltered, debug, confidence)
+    GaussianRasterizer(raster_settings)(means3D, means2D, opacities, shs=None, colors_precomp=None,
+                                        scales=None, rotations=None, cov3D_precomp=None)
+        -> (color[3,H,W], radii[P] int32, depth[1,H,W], alpha[1,H,W])
+    GaussianRasterizer.markVisible(positions) -> bool[P]
+    rasterize_gaussians(...)  (functional form)
+
+so `gaussian_renderer.render()` (gaussian_renderer/__init__.py:14,42-101) runs unchanged when this
+directory's parent is put on sys.path ahead of the reference submodule.  The compute is the sm_100a
+library behind include/gvd_raster.h; there is no fallback path.
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _C
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    """Host snapshot of a call's arguments, written to snapshot_{fw,bw}.dump when debug=True fails."""
+    return tuple(x.detach().cpu().clone() if torch.is_tensor(x) else x for x in input_tuple)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
+                rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)  # copy before they can be corrupted
+            try:
+                out = _C.rasterize_gaussians(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            out = _C.rasterize_gaussians(*args)
+        num_rendered, color, depth, alpha, radii, geomBuffer, binningBuffer, imgBuffer = out
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+                              binningBuffer, imgBuffer, alpha)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
+         imgBuffer, alpha) = ctx.saved_tensors
+        conf = rs.confidence
+        if conf is not None and conf.numel() != means3D.size(0):
+            raise RuntimeError("confidence must hold one value per Gaussian")
+        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_color, grad_depth, grad_alpha, sh,
+                rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, alpha, rs.debug)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                out = _C.rasterize_gaussians_backward(*args, confidence=conf)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            out = _C.rasterize_gaussians_backward(*args, confidence=conf)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
+         grad_scales, grad_rotations) = out
+        # confidence is already applied in-kernel to everything except grad_means2D
+        # (reference: diff_gaussian_rasterization/__init__.py:147-157)
+        return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
+                grad_rotations, grad_cov3Ds_precomp, None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    confidence: torch.Tensor
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            rs = self.raster_settings
+            visible = _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+        return visible
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        # argument contract of the reference module (DGR/diff_gaussian_rasterization/__init__.py:192-212):
+        # exactly one colour source and exactly one covariance source; messages kept verbatim because
+        # callers/tests match on them.
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        pair_given = scales is not None or rotations is not None
+        pair_complete = scales is not None and rotations is not None
+        if (cov3D_precomp is None and not pair_complete) or (cov3D_precomp is not None and pair_given):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        absent = torch.Tensor([])  # empty CPU tensor == "not provided" (NULL at the C ABI)
+        opt = [absent if t is None else t for t in (shs, colors_precomp, scales, rotations, cov3D_precomp)]
+        return rasterize_gaussians(means3D, means2D, opt[0], opt[1], opacities, opt[2], opt[3], opt[4],
+                                   self.raster_settings)

@@ -1,0 +1,103 @@
+"""ctypes binding of the C-ABI libraries in ./lib (built from ./csrc for sm_100a).
+
+This is the only place the product loads native code.  There is NO fallback: if the
+library is missing the import raises, and every op raises RuntimeError with
+gvd_last_error() when a call fails.  Signatures mirror include/gvd_raster.h.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_DIR = os.path.join(_HERE, "lib")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class RasterForwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("width", C.c_int), ("height", C.c_int),
+        ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p),
+        ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
+        ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
+        ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("prefiltered", C.c_int), ("debug", C.c_int),
+        ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
+        ("geom_alloc", ALLOC_FN), ("binning_alloc", ALLOC_FN), ("img_alloc", ALLOC_FN),
+        ("alloc_user", C.c_void_p),
+        ("num_rendered", C.c_int),
+    ]
+
+
+class RasterBackwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int), ("width", C.c_int), ("height", C.c_int),
+        ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p),
+        ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+        ("campos", C.c_void_p),
+        ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("radii", C.c_void_p), ("alphas", C.c_void_p),
+        ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("img_buffer", C.c_void_p),
+        ("dL_dpix", C.c_void_p), ("dL_ddepth_pix", C.c_void_p), ("dL_dalpha_pix", C.c_void_p),
+        ("confidence", C.c_void_p),
+        ("scratch", C.c_void_p),
+        ("dL_dmeans2D", C.c_void_p), ("dL_dmeans3D", C.c_void_p), ("dL_dopacity", C.c_void_p),
+        ("dL_dcolors", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
+        ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
+        ("debug", C.c_int),
+    ]
+
+
+class RasterLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "geom_splat", "geom_clamped", "geom_tiles_touched", "geom_point_offsets",
+        "bin_point_list", "bin_point_list_keys", "bin_point_list_unsorted", "bin_keys_unsorted", "bin_packed",
+        "img_ranges", "img_n_contrib")]
+
+
+RASTER_SYMBOLS = (
+    "gvd_raster_abi_version", "gvd_last_error", "gvd_raster_geom_bytes", "gvd_raster_binning_bytes",
+    "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes", "gvd_raster_layout",
+    "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible",
+)
+
+_raster = None
+
+
+def lib_path(name="libgvd_raster.so"):
+    return os.path.join(_LIB_DIR, name)
+
+
+def raster():
+    """Load libgvd_raster.so once; raise loudly when it is absent (no CPU/torch fallback exists)."""
+    global _raster
+    if _raster is not None:
+        return _raster
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C guidedvd-3dgs_b200/csrc`). The rasterizer has no fallback path.")
+    lib = C.CDLL(path)
+    lib.gvd_last_error.restype = C.c_char_p
+    lib.gvd_raster_abi_version.restype = C.c_int
+    for n in ("gvd_raster_geom_bytes", "gvd_raster_binning_bytes", "gvd_raster_backward_scratch_bytes"):
+        getattr(lib, n).restype = C.c_size_t
+        getattr(lib, n).argtypes = [C.c_int]
+    lib.gvd_raster_img_bytes.restype = C.c_size_t
+    lib.gvd_raster_img_bytes.argtypes = [C.c_int, C.c_int]
+    lib.gvd_raster_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RasterLayout)]
+    lib.gvd_raster_forward.argtypes = [C.POINTER(RasterForwardArgs), C.c_void_p]
+    lib.gvd_raster_backward.argtypes = [C.POINTER(RasterBackwardArgs), C.c_void_p]
+    lib.gvd_raster_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for n in ("gvd_raster_layout", "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible"):
+        getattr(lib, n).restype = C.c_int
+    if lib.gvd_raster_abi_version() != 3:
+        raise RuntimeError("libgvd_raster.so ABI version mismatch; rebuild")
+    _raster = lib
+    return lib
+
+
+def last_error(lib):
+    return (lib.gvd_last_error() or b"").decode("utf-8", "replace")

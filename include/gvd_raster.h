@@ -1,0 +1,170 @@
+/*
+ * gvd_raster.h -- C ABI of the B200-native differentiable Gaussian rasterizer.
+ *
+ * Drop-in boundary for the reference's native extension
+ *   submodules/diff-gaussian-rasterization-confidence  (abbrev. DGR below).
+ * Each entry point names the reference interface it replaces.  All pointers
+ * named "dev" are CUDA device pointers; NULL means "argument absent" (the
+ * reference passes empty tensors, DGR/diff_gaussian_rasterization/__init__.py:202-212,
+ * which its C++ sees as nullptr).  Nothing here allocates device memory: every
+ * buffer, including scratch, is owned by the caller (DGR/rasterize_points.cu:73-80
+ * uses resize callbacks on torch tensors; we keep that contract with plain C
+ * callbacks).  Functions return 0 on success, non-zero on error; the message is
+ * available from gvd_last_error().  Nothing throws across the ABI.
+ *
+ * All launches go to the cudaStream_t passed in (the reference uses the legacy
+ * default stream).  The library keeps no global state besides the per-thread
+ * error string and cached function attributes.
+ */
+#ifndef GVD_RASTER_H_
+#define GVD_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GVD_API __attribute__((visibility("default")))
+#else
+#define GVD_API
+#endif
+
+typedef struct CUstream_st* gvd_stream_t; /* == cudaStream_t */
+
+/* Resize callback: must return a device pointer to at least `bytes` bytes,
+ * 128-byte aligned, valid until the matching backward has run.
+ * Replaces std::function<char*(size_t)> of DGR/cuda_rasterizer/rasterizer.h:31-34. */
+typedef void* (*gvd_alloc_fn)(void* user, size_t bytes);
+
+/* Layout/version of the scratch buffers (bumped when the packed layouts change). */
+#define GVD_RASTER_ABI_VERSION 3
+
+typedef struct GvdRasterForwardArgs {
+    /* sizes -- DGR/cuda_rasterizer/rasterizer_impl.cu:197-224 */
+    int P;            /* number of Gaussians                       */
+    int D;            /* active SH degree 0..3                      */
+    int M;            /* SH coefficients stored per Gaussian (16)   */
+    int width, height;
+    /* inputs (dev) */
+    const float* background;     /* [3]                                   */
+    const float* means3D;        /* [P,3]                                 */
+    const float* shs;            /* [P,M,3] or NULL                       */
+    const float* colors_precomp; /* [P,3]   or NULL                       */
+    const float* opacities;      /* [P]                                   */
+    const float* scales;         /* [P,3]   or NULL                       */
+    const float* rotations;      /* [P,4]   or NULL (used un-normalised)  */
+    const float* cov3D_precomp;  /* [P,6]   or NULL                       */
+    const float* viewmatrix;     /* [16], transposed (row-vector) layout  */
+    const float* projmatrix;     /* [16], transposed                      */
+    const float* campos;         /* [3]                                   */
+    float scale_modifier;
+    float tan_fovx, tan_fovy;
+    int prefiltered;
+    int debug;                   /* sync + check after every stage        */
+    /* outputs (dev) */
+    float* out_color;            /* [3,H,W]  */
+    float* out_depth;            /* [1,H,W]  sum depth*alpha*T (un-normalised) */
+    float* out_alpha;            /* [1,H,W]  sum alpha*T                       */
+    int*   radii;                /* [P]      */
+    /* scratch (caller-owned, via callbacks like the reference) */
+    gvd_alloc_fn geom_alloc;     /* called once with gvd_raster_geom_bytes(P)        */
+    gvd_alloc_fn binning_alloc;  /* called once with gvd_raster_binning_bytes(R)     */
+    gvd_alloc_fn img_alloc;      /* called once with gvd_raster_img_bytes(W,H)       */
+    void* alloc_user;
+    /* result */
+    int num_rendered;            /* out: R = number of (Gaussian,tile) instances     */
+} GvdRasterForwardArgs;
+
+typedef struct GvdRasterBackwardArgs {
+    int P, D, M, R;
+    int width, height;
+    /* forward inputs again (dev) -- DGR/rasterize_points.cu:121-146 */
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float scale_modifier;
+    float tan_fovx, tan_fovy;
+    const int*   radii;          /* [P]     from forward                          */
+    const float* alphas;         /* [1,H,W] out_alpha from forward                */
+    /* forward scratch (dev) */
+    const void* geom_buffer;
+    const void* binning_buffer;
+    const void* img_buffer;
+    /* incoming cotangents (dev) */
+    const float* dL_dpix;        /* [3,H,W] */
+    const float* dL_ddepth_pix;  /* [1,H,W] */
+    const float* dL_dalpha_pix;  /* [1,H,W] */
+    /* per-Gaussian confidence, fused: DGR/diff_gaussian_rasterization/__init__.py:147-157
+     * multiplies every returned gradient except dL_dmeans2D by confidence[P,1]. NULL = ones. */
+    const float* confidence;     /* [P] or NULL */
+    /* scratch: zero-filled by this call; gvd_raster_backward_scratch_bytes(P) bytes */
+    void* scratch;
+    /* outputs (dev); all fully written by this call (no pre-zeroing needed).      */
+    float* dL_dmeans2D;          /* [P,3]  (z = 0), NOT confidence-scaled          */
+    float* dL_dmeans3D;          /* [P,3]                                          */
+    float* dL_dopacity;          /* [P]                                            */
+    float* dL_dcolors;           /* [P,3]   or NULL (needed iff colors_precomp)    */
+    float* dL_dcov3D;            /* [P,6]   or NULL (needed iff cov3D_precomp)     */
+    float* dL_dsh;               /* [P,M,3] or NULL (needed iff shs)               */
+    float* dL_dscales;           /* [P,3]   or NULL (needed iff scales)            */
+    float* dL_drotations;        /* [P,4]   or NULL (needed iff rotations)         */
+    int debug;
+} GvdRasterBackwardArgs;
+
+/* sizes of the caller-owned scratch buffers; replaces
+ * CudaRasterizer::required<GeometryState|BinningState|ImageState>
+ * (DGR/cuda_rasterizer/rasterizer_impl.h:63-69). */
+GVD_API size_t gvd_raster_geom_bytes(int P);
+GVD_API size_t gvd_raster_binning_bytes(int R);
+GVD_API size_t gvd_raster_img_bytes(int width, int height);
+GVD_API size_t gvd_raster_backward_scratch_bytes(int P);
+
+/* Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer_impl.cu:197-339)
+ * as reached from RasterizeGaussiansCUDA (DGR/rasterize_points.cu:35-119). */
+GVD_API int gvd_raster_forward(GvdRasterForwardArgs* args, gvd_stream_t stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:343-447) as reached
+ * from RasterizeGaussiansBackwardCUDA (rasterize_points.cu:121-208), plus the Python-side
+ * confidence scaling (diff_gaussian_rasterization/__init__.py:147-157). */
+GVD_API int gvd_raster_backward(const GvdRasterBackwardArgs* args, gvd_stream_t stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer_impl.cu:141-153):
+ * present[i] = (view-space z of means3D[i] > 0.2).  present: dev uint8[P]. */
+GVD_API int gvd_raster_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                            const float* projmatrix, uint8_t* present, gvd_stream_t stream);
+
+/* Introspection for parity tests: byte offsets of the bit-exact-comparable arrays inside
+ * the scratch buffers of THIS library (the reference's own layout is
+ * rasterizer_impl.cu:155-195). */
+typedef struct GvdRasterLayout {
+    size_t geom_splat;          /* float4[3P]: {x,y,conA,conB},{conC,opac,r,g},{b,depth,rect_lo,rect_hi} */
+    size_t geom_clamped;        /* uint8[P]: bit c set = channel c was clamped at 0                       */
+    size_t geom_tiles_touched;  /* uint32[P]                                                              */
+    size_t geom_point_offsets;  /* uint32[P] inclusive scan of tiles_touched                              */
+    size_t bin_point_list;          /* uint32[R] sorted Gaussian ids                                      */
+    size_t bin_point_list_keys;     /* uint64[R] sorted keys (tile<<32 | depth bits)                      */
+    size_t bin_point_list_unsorted; /* uint32[R]                                                          */
+    size_t bin_keys_unsorted;       /* uint64[R]                                                          */
+    size_t bin_packed;              /* float4[3R] packed per-instance records (TMA source)                */
+    size_t img_ranges;          /* uint2[T]   */
+    size_t img_n_contrib;       /* uint32[H*W]*/
+} GvdRasterLayout;
+GVD_API int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out);
+
+GVD_API int gvd_raster_abi_version(void);
+GVD_API const char* gvd_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVD_RASTER_H_ */

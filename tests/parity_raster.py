@@ -1,0 +1,163 @@
+"""Run the B200-native rasterizer and the compiled reference on the same seeded inputs and
+compare (test infrastructure; used by tests/test_raster_gpu.py and runnable standalone)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "guidedvd-3dgs_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import refload  # noqa: E402
+import synth  # noqa: E402
+
+
+def make_inputs(P, W, H, seed, sh_degree=3, device="cuda", fovx_deg=90.0):
+    sc = synth.synth_scene(P, seed, device=device)
+    cam = synth.synth_camera(seed + 1, W, H, fovx_deg=fovx_deg, device=device)
+    g = torch.Generator().manual_seed(seed + 2)
+    cot = dict(color=torch.randn(3, H, W, generator=g).to(device), depth=torch.randn(1, H, W, generator=g).to(device),
+               alpha=torch.randn(1, H, W, generator=g).to(device))
+    bg = torch.tensor([0.1, 0.2, 0.3], device=device)
+    return sc, cam, cot, bg, sh_degree
+
+
+def run(pkg, sc, cam, cot, bg, sh_degree, use_conf=True, precomp=False, debug=False, backward=True):
+    """One forward(+backward) through the package's public API. Returns dict of outputs/grads/buffers."""
+    dev = sc["means3D"].device
+    conf = sc["confidence"] if use_conf else torch.ones_like(sc["confidence"])
+    settings = pkg.GaussianRasterizationSettings(
+        image_height=cam["height"], image_width=cam["width"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+        bg=bg, scale_modifier=1.0, viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"],
+        sh_degree=sh_degree, campos=cam["campos"], prefiltered=False, debug=debug, confidence=conf)
+    rast = pkg.GaussianRasterizer(raster_settings=settings)
+    leaf = {k: sc[k].detach().clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    kw = dict(means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"])
+    if precomp:
+        # exercise colors_precomp + cov3D_precomp inputs
+        colors = (torch.sigmoid(sc["shs"][:, 0, :])).detach().clone().requires_grad_(True)
+        L = torch.diag_embed(sc["scales"]) @ _quat_to_rot(sc["rotations"])
+        Sigma = L.transpose(1, 2) @ L
+        cov = torch.stack([Sigma[:, 0, 0], Sigma[:, 0, 1], Sigma[:, 0, 2], Sigma[:, 1, 1], Sigma[:, 1, 2],
+                           Sigma[:, 2, 2]], 1).detach().clone().requires_grad_(True)
+        leaf["colors_precomp"], leaf["cov3D_precomp"] = colors, cov
+        kw.update(colors_precomp=colors, cov3D_precomp=cov)
+    else:
+        kw.update(shs=leaf["shs"], scales=leaf["scales"], rotations=leaf["rotations"])
+    color, radii, depth, alpha = rast(**kw)
+    out = dict(color=color.detach(), radii=radii.detach(), depth=depth.detach(), alpha=alpha.detach())
+    fn = color.grad_fn
+    saved = getattr(fn, "saved_tensors", None)
+    if saved is not None:
+        out["geom"], out["binning"], out["img"] = saved[7], saved[8], saved[9]
+    out["num_rendered"] = getattr(fn, "num_rendered", None)
+    if backward:
+        loss = (color * cot["color"]).sum() + (depth * cot["depth"]).sum() + (alpha * cot["alpha"]).sum()
+        loss.backward()
+        out["grads"] = {k: (v.grad.detach() if v.grad is not None else None) for k, v in leaf.items()}
+        out["grads"]["means2D"] = means2D.grad.detach() if means2D.grad is not None else None
+    return out
+
+
+def _quat_to_rot(q):
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(-1, 3, 3)
+    return R
+
+
+def ours_views(out, P, W, H):
+    """Views of the bit-exact-comparable arrays inside OUR scratch buffers."""
+    import gvd_native
+
+    lib = gvd_native.raster()
+    R = out["num_rendered"]
+    L = gvd_native.RasterLayout()
+    lib.gvd_raster_layout(P, R, W, H, C.byref(L))
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    b, g, im = out["binning"], out["geom"], out["img"]
+    v = {}
+    v["point_list"] = b[L.bin_point_list:L.bin_point_list + 4 * R].view(torch.int32)
+    v["point_list_keys"] = b[L.bin_point_list_keys:L.bin_point_list_keys + 8 * R].view(torch.int64)
+    v["tiles_touched"] = g[L.geom_tiles_touched:L.geom_tiles_touched + 4 * P].view(torch.int32)
+    v["splat"] = g[L.geom_splat:L.geom_splat + 48 * P].view(torch.float32).view(P, 12)
+    v["clamped"] = g[L.geom_clamped:L.geom_clamped + P]
+    v["ranges"] = im[L.img_ranges:L.img_ranges + 8 * tiles].view(torch.int32).view(tiles, 2)
+    v["n_contrib"] = im[L.img_n_contrib:L.img_n_contrib + 4 * W * H].view(torch.int32)
+    return v
+
+
+def relerr(a, b, floor_frac=1e-3):
+    """max |a-b| / (|b| + floor) with floor = floor_frac * rms(b): 'relative error with an absolute
+    floor' so exact zeros / cancellations do not divide by ~0."""
+    a, b = a.double().flatten(), b.double().flatten()
+    if b.numel() == 0:
+        return 0.0, 0.0
+    floor = floor_frac * b.pow(2).mean().sqrt().clamp_min(1e-30)
+    e = (a - b).abs() / (b.abs() + floor)
+    return e.max().item(), e.mean().item()
+
+
+def compare(P, W, H, seed, sh_degree=3, use_conf=True, precomp=False, verbose=True):
+    import diff_gaussian_rasterization as ours
+
+    ref = refload.ref_dgr()
+    assert ref is not None, "oracle/_ref not built (python oracle/build_ref.py)"
+    sc, cam, cot, bg, D = make_inputs(P, W, H, seed, sh_degree)
+    o = run(ours, sc, cam, cot, bg, D, use_conf, precomp)
+    r = run(ref, sc, cam, cot, bg, D, use_conf, precomp)
+    r2 = run(ref, sc, cam, cot, bg, D, use_conf, precomp)  # the reference's own atomic-order jitter
+    res = {"P": P, "W": W, "H": H, "R_ours": o["num_rendered"], "R_ref": r["num_rendered"],
+           "visible": int((r["radii"] > 0).sum())}
+    res["radii_mismatch"] = int((o["radii"] != r["radii"]).sum())
+    ov = ours_views(o, P, W, H)
+    R = r["num_rendered"]
+    rb = refload.ref_binning_views(r["binning"], R)
+    rg = refload.ref_geom_views(r["geom"], P)
+    ri = refload.ref_img_views(r["img"], W, H)
+    if o["num_rendered"] == R:
+        res["point_list_mismatch"] = int((ov["point_list"] != rb["point_list"]).sum())
+        res["keys_mismatch"] = int((ov["point_list_keys"] != rb["point_list_keys"]).sum())
+    else:
+        res["point_list_mismatch"] = res["keys_mismatch"] = -1
+    res["tiles_touched_mismatch"] = int((ov["tiles_touched"] != rg["tiles_touched"]).sum())
+    res["ranges_mismatch"] = int((ov["ranges"] != ri["ranges"]).sum())
+    res["n_contrib_mismatch"] = int((ov["n_contrib"] != ri["n_contrib"]).sum())
+    vis = r["radii"] > 0
+    res["means2D_bits_mismatch"] = int((ov["splat"][vis][:, 0:2].view(torch.int32) != rg["means2D"][vis].view(torch.int32)).sum())
+    res["depth_bits_mismatch"] = int((ov["splat"][vis][:, 9].view(torch.int32) != rg["depths"][vis].view(torch.int32)).sum())
+    conic_o = torch.cat([ov["splat"][vis][:, 2:4], ov["splat"][vis][:, 4:6]], 1)
+    res["conic_bits_mismatch"] = int((conic_o.view(torch.int32) != rg["conic_opacity"][vis].view(torch.int32)).sum())
+    if not precomp:
+        rgb_o = torch.cat([ov["splat"][vis][:, 6:8], ov["splat"][vis][:, 8:9]], 1)
+        res["rgb_bits_mismatch"] = int((rgb_o.view(torch.int32) != rg["rgb"][vis].view(torch.int32)).sum())
+    for k in ("color", "depth", "alpha"):
+        res[f"{k}_relerr"] = relerr(o[k], r[k])
+        res[f"{k}_bits_mismatch"] = int((o[k].view(torch.int32) != r[k].view(torch.int32)).sum())
+    for k, gr in r["grads"].items():
+        go = o["grads"].get(k)
+        if gr is None or go is None:
+            res[f"grad_{k}"] = None if (gr is None and go is None) else "presence mismatch"
+            continue
+        res[f"grad_{k}_relerr"] = relerr(go, gr)
+        res[f"grad_{k}_ref_jitter"] = relerr(r2["grads"][k], gr)
+    if verbose:
+        for k, v in res.items():
+            print(f"  {k}: {v}")
+    return res
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["tiny", "small"]
+    for n in names:
+        P, W, H, seed = synth.CONFIGS[n]
+        for D in (3, 0):
+            print(f"== {n} P={P} {W}x{H} seed={seed} D={D}")
+            compare(P, W, H, seed, sh_degree=D)
+        print(f"== {n} precomp colours + cov3D")
+        compare(P, W, H, seed, sh_degree=0, precomp=True)
