@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- views/s of the differentiable Gaussian rasterizer (fwd+bwd) on B200.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            our sm_100a path
+  python bench.py --impl reference --gpus N ...            the unmodified reference (oracle/_ref)
+One JSON line on rank 0.  A "step" is one view: rasterizer forward + backward through the
+`GaussianRasterizer` autograd boundary with fixed random cotangents.
+N>1: one process per GPU (torchrun), each rank renders its own view of the replicated scene
+(weak scaling) and the per-Gaussian gradients are summed with one NCCL all-reduce per step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "guidedvd-3dgs_b200")
+for p in (PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    # name: (P, W, H, seed, sh_degree, description)
+    "C2": (500_000, 640, 480, 20260002, 3,
+           "BASELINE.json configs[1]: Replica office_3-like synthetic scene, 500k Gaussians, 640x480, SH deg 3, "
+           "rasterizer fwd+bwd only"),
+    "C4": (800_000, 1600, 1066, 20260004, 3, "ScanNet++-like 800k Gaussians 1600x1066"),
+    "C5": (2_000_000, 640, 480, 20260005, 3, "Replica room_0-like 2M Gaussians, 640x480 (one view per rank)"),
+    "small": (50_000, 320, 240, 20260001, 3, "smoke-size"),
+}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons of this rank's GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def load_impl(impl):
+    if impl == "ours":
+        import diff_gaussian_rasterization as pkg
+        import gvd_native
+        gvd_native.raster()  # fail loudly if the CUDA library is missing
+        return pkg
+    import refload
+    pkg = refload.ref_dgr()
+    return pkg
+
+
+def make_step(pkg, sc, cam, bg, D):
+    """Returns step(cot) -> (color, leaves) running fwd+bwd through the public API."""
+    leaves = {k: sc[k].detach().clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    conf = sc["confidence"]
+
+    def step(cot, viewmatrix, projmatrix, campos):
+        settings = pkg.GaussianRasterizationSettings(
+            image_height=cam["height"], image_width=cam["width"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+            bg=bg, scale_modifier=1.0, viewmatrix=viewmatrix, projmatrix=projmatrix, sh_degree=D, campos=campos,
+            prefiltered=False, debug=False, confidence=conf)
+        rast = pkg.GaussianRasterizer(raster_settings=settings)
+        for v in leaves.values():
+            v.grad = None
+        means2D.grad = None
+        color, radii, depth, alpha = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                                          shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        torch.autograd.backward([color, depth, alpha], [cot[0:3], cot[3:4], cot[4:5]])
+        return color, radii
+
+    return step, leaves, means2D
+
+
+def grad_flat(leaves):
+    return [v.grad for v in leaves.values() if v.grad is not None]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="gpu", choices=["gpu", "cpu"],
+                    help="reference arm: compiled reference CUDA on the GPU (default) or the C oracle port on host cores")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    K, Wm = args.steps, max(args.warmup, 3)
+    P, W, H, seed, D, desc = WORKLOADS[args.workload]
+
+    if args.impl == "reference" and args.ref_device == "cpu":
+        if rank == 0:
+            print(json.dumps(cpu_reference_line(args, P, W, H, seed, D, desc, K, Wm)))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = load_impl(args.impl)
+    if pkg is None:
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (python oracle/build_ref.py)"}))
+        return
+
+    import synth
+    sc = synth.synth_scene(P, seed, device=dev)
+    cam = synth.synth_camera(seed + 1 + rank, W, H, device=dev)
+    bg = torch.zeros(3, device=dev)
+    g = torch.Generator().manual_seed(seed + 2 + rank)
+    cot_host = torch.randn(5, H, W, generator=g).pin_memory()
+    cam_host = torch.cat([cam["viewmatrix"].flatten(), cam["projmatrix"].flatten(), cam["campos"].flatten()]).cpu().pin_memory()
+    cot_dev = cot_host.to(dev)
+    step, leaves, means2D = make_step(pkg, sc, cam, bg, D)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def resident_step():
+        step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
+        if world > 1:
+            flat = torch.cat([t.reshape(-1) for t in grad_flat(leaves)])
+            dist.all_reduce(flat)
+
+    def e2e_step():
+        cm = cam_host.to(dev, non_blocking=True)
+        cot = cot_host.to(dev, non_blocking=True)
+        color, radii = step(cot, cm[0:16].view(4, 4), cm[16:32].view(4, 4), cm[32:35])
+        if world > 1:
+            flat = torch.cat([t.reshape(-1) for t in grad_flat(leaves)])
+            dist.all_reduce(flat)
+        # the step's result: the scalar a trainer reads back every iteration (train_baseline.py:88)
+        return float((color * cot[0:3]).sum().item())
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), wall
+
+    for _ in range(Wm):
+        resident_step()
+        e2e_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, wall_res = timed(resident_step, K)
+    ms_e2e, wall_e2e = timed(e2e_step, K)
+    clocks = sampler.stop()
+
+    # workload facts (same for both arms): R, visible count
+    color, radii = step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
+    fn = color.grad_fn
+    R = int(getattr(fn, "num_rendered", 0) or 0)
+    visible = int((radii > 0).sum().item())
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    HWp = H * W
+
+    roofline = None
+    stage_ms = None
+    if args.impl == "ours":
+        import gvd_native
+        lib = gvd_native.raster()
+        lib.gvd_raster_profile_enable(1)
+        nprof = min(K, 50)
+        for _ in range(nprof):
+            step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
+        torch.cuda.synchronize()
+        st = gvd_native.RasterStageTimes()
+        lib.gvd_raster_profile_read(C.byref(st))
+        lib.gvd_raster_profile_enable(0)
+        stage_ms = {n: (st.ms[i] / st.calls[i] if st.calls[i] else 0.0) for i, n in enumerate(gvd_native.STAGE_NAMES)}
+        # algorithmic bytes per launch, SURVEY.md section 8(d)
+        nbits = 32 + max(1, (tiles - 1).bit_length())
+        passes = (nbits + 7) // 8
+        alg = {
+            "preprocess": P * (12 + 12 + 16 + 4 + 12 * (D + 1) ** 2) + P * 8 + visible * (8 + 4 + 24 + 12 + 16 + 3),
+            "scan": 8 * P, "emit": 12 * R, "sort": 12 * R * 2 * passes, "pack": 8 * R + 8 * tiles + 2 * 44 * R,
+            "render_fwd": 44 * R + 24 * HWp + 8 * tiles,
+            "render_bwd": 44 * R + 28 * HWp + 8 * tiles + 80 * R,
+            "gaussian_bwd": visible * (12 + 4 + 24 + 16 + 12 * (D + 1) ** 2 + 3 + 16 + 12 + 4) + visible * (12 + 24 + 12 * 16 + 12 + 16),
+        }
+        top = max(stage_ms, key=lambda k: stage_ms[k])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = alg[top] / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "algorithmic_bytes": alg[top],
+                    "note": "render kernels are fp32-ALU/SFU/atomic bound, not HBM bound (SURVEY.md 0.5); see DESIGN.md",
+                    "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+                    "stage_gbs": {k: round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None for k, v in stage_ms.items()}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    views_per_s = world * K / (ms_res * 1e-3)
+    e2e_views_per_s = world * K / (ms_e2e * 1e-3)
+    h2d = cot_host.numel() * 4 + cam_host.numel() * 4
+    ws_mb = (P * 236 + P * 248 + R * (12 * 2 + 48 + 12) + HWp * 48) / 1e6
+    line = {
+        "metric": "3DGS train-step views/sec (rasterizer fwd+bwd)", "value": round(views_per_s, 2), "unit": "views/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_res / K, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": args.impl,
+        "config": {"workload": args.workload, "description": desc, "P": P, "width": W, "height": H, "sh_degree": D,
+                   "num_rendered": R, "visible": visible, "tiles": tiles,
+                   "l2_policy": f"inputs larger than L2: per-step working set ~{ws_mb:.0f} MB > 126 MB",
+                   "parallelism": f"view-parallel dp{world}" + (" + NCCL all-reduce of 62 floats/Gaussian per step" if world > 1 else "")},
+        "e2e": {"value": round(e2e_views_per_s, 2), "unit": "views/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4), "wall_ms_per_step": round(wall_e2e / K * 1e3, 4)},
+        "gpu_launches": (6 * K * 2) if args.impl == "ours" else 0,
+        "gpu_launches_note": "own kernels in the two timed regions: preprocess, emit_keys, pack, render_fwd, render_bwd, "
+                             "gaussian_bwd per step (+ CUB scan/radix-sort library kernels, not counted)",
+        "clocks": clocks,
+    }
+    if roofline:
+        line["roofline"] = roofline
+    if args.impl == "reference":
+        line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": "reference",
+                                "sample": "the reference has no CPU rasterizer: this arm is its own CUDA code "
+                                          "(oracle/_ref, compiled unmodified for sm_100a) on the same B200, full workload"}
+    elif world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(P, W, H, seed, D)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(P, W, H, seed, D, budget_s=20.0):
+    """Times the C restatement (oracle/) on the host: a bounded sample of the same workload."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import raster_oracle
+        return raster_oracle.timed_sample(P, W, H, seed, D, budget_s=budget_s)
+    except Exception as ex:  # the baseline is a reported number, never the product path
+        return {"value": None, "unit": "views/s", "cores": 1, "kind": "port", "sample": f"unavailable: {ex!r}"}
+
+
+def cpu_reference_line(args, P, W, H, seed, D, desc, K, Wm):
+    cb = cpu_baseline(P, W, H, seed, D, budget_s=60.0)
+    return {"metric": "3DGS train-step views/sec (rasterizer fwd+bwd)", "value": cb.get("value"), "unit": "views/s",
+            "n_gpus": 1, "steps": K, "warmup": Wm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "description": desc}, "cpu_baseline": cb,
+            "e2e": {"value": cb.get("value"), "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,50 @@ int fail_msg(const std::string& s) {
         }                                                                 \
     } while (0)
 
+// ---- optional per-stage timing -------------------------------------------------------------
+struct StageProfiler {
+    bool on = false;
+    static const int kMax = 4096;
+    cudaEvent_t beg[kMax], end[kMax];
+    int stage[kMax];
+    int used = 0, created = 0;
+    GvdRasterStageTimes acc{};
+    void flush() {
+        for (int i = 0; i < used; ++i) {
+            if (cudaEventSynchronize(end[i]) != cudaSuccess) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, beg[i], end[i]) == cudaSuccess) {
+                acc.ms[stage[i]] += ms;
+                acc.calls[stage[i]] += 1;
+            }
+        }
+        used = 0;
+    }
+    int begin(int st, cudaStream_t s) {
+        if (!on) return -1;
+        if (used == kMax) flush();
+        if (used == created) {
+            cudaEventCreate(&beg[created]);
+            cudaEventCreate(&end[created]);
+            ++created;
+        }
+        stage[used] = st;
+        cudaEventRecord(beg[used], s);
+        return used++;
+    }
+    void finish(int h, cudaStream_t s) {
+        if (h >= 0) cudaEventRecord(end[h], s);
+    }
+};
+StageProfiler g_prof;
+
+struct StageScope {
+    int h;
+    cudaStream_t s;
+    StageScope(int st, cudaStream_t s_) : h(g_prof.begin(st, s_)), s(s_) {}
+    ~StageScope() { g_prof.finish(h, s); }
+};
+
 template <typename T>
 void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128) {
     size_t offset = (reinterpret_cast<uintptr_t>(chunk) + alignment - 1) & ~(alignment - 1);
@@ -105,6 +149,19 @@ inline dim3 tile_grid(int width, int height) {
 extern "C" {
 
 int gvd_raster_abi_version(void) { return GVD_RASTER_ABI_VERSION; }
+
+int gvd_raster_profile_enable(int on) {
+    g_prof.flush();
+    g_prof.acc = GvdRasterStageTimes{};
+    g_prof.on = on != 0;
+    return 0;
+}
+int gvd_raster_profile_read(GvdRasterStageTimes* out) {
+    if (!out) return fail_msg("gvd_raster_profile_read: null out");
+    g_prof.flush();
+    *out = g_prof.acc;
+    return 0;
+}
 const char* gvd_last_error(void) { return g_err.c_str(); }
 
 size_t gvd_raster_geom_bytes(int P) {
@@ -178,12 +235,17 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     if (!ip) return fail_msg("gvd_raster_forward: image allocator returned null");
     RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
 
-    gvd_launch_preprocess(*a, g, focal_x, focal_y, grid, stream);
+    {
+        StageScope t(GVD_STAGE_PREPROCESS, stream);
+        gvd_launch_preprocess(*a, g, focal_x, focal_y, grid, stream);
+    }
     GVD_STAGE("preprocess");
-
-    GVD_CHECK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, P,
-                                            stream),
-              "InclusiveSum");
+    {
+        StageScope t(GVD_STAGE_SCAN, stream);
+        GVD_CHECK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, P,
+                                                stream),
+                  "InclusiveSum");
+    }
     GVD_STAGE("scan");
 
     // Size of the instance list. Like the reference (rasterizer_impl.cu:281-282) this is the one
@@ -200,20 +262,31 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
 
     GVD_CHECK(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), stream), "memset ranges");
     if (num_rendered > 0) {
-        gvd_launch_emit_keys(P, g, b, grid, stream);
+        {
+            StageScope t(GVD_STAGE_EMIT, stream);
+            gvd_launch_emit_keys(P, g, b, grid, stream);
+        }
         GVD_STAGE("emit_keys");
 
         const int bit = (int)higher_msb((uint32_t)tiles);
-        GVD_CHECK(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys,
-                                                  b.point_list_unsorted, b.point_list, num_rendered, 0, 32 + bit,
-                                                  stream),
-                  "SortPairs");
+        {
+            StageScope t(GVD_STAGE_SORT, stream);
+            GVD_CHECK(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys,
+                                                      b.point_list_unsorted, b.point_list, num_rendered, 0, 32 + bit,
+                                                      stream),
+                      "SortPairs");
+        }
         GVD_STAGE("sort");
-
-        gvd_launch_pack(num_rendered, g, b, im, grid, stream);
+        {
+            StageScope t(GVD_STAGE_PACK, stream);
+            gvd_launch_pack(num_rendered, g, b, im, grid, stream);
+        }
         GVD_STAGE("pack");
     }
-    gvd_launch_render_forward(*a, b, im, grid, stream);
+    {
+        StageScope t(GVD_STAGE_RENDER_FWD, stream);
+        gvd_launch_render_forward(*a, b, im, grid, stream);
+    }
     GVD_STAGE("render_forward");
     return 0;
 }
@@ -248,10 +321,16 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     GVD_CHECK(cudaMemsetAsync(acc, 0, (size_t)P * GVD_ACC_STRIDE * sizeof(float), stream), "memset acc");
 
     if (a->R > 0) {
-        gvd_launch_render_backward(*a, b, im, acc, grid, stream);
+        {
+            StageScope t(GVD_STAGE_RENDER_BWD, stream);
+            gvd_launch_render_backward(*a, b, im, acc, grid, stream);
+        }
         GVD_STAGE("render_backward");
     }
-    gvd_launch_gaussian_backward(*a, g, acc, focal_x, focal_y, stream);
+    {
+        StageScope t(GVD_STAGE_GAUSSIAN_BWD, stream);
+        gvd_launch_gaussian_backward(*a, g, acc, focal_x, focal_y, stream);
+    }
     GVD_STAGE("gaussian_backward");
     return 0;
 }

@@ -56,7 +56,15 @@ class RasterLayout(C.Structure):
         "img_ranges", "img_n_contrib")]
 
 
+STAGE_NAMES = ("preprocess", "scan", "emit", "sort", "pack", "render_fwd", "render_bwd", "gaussian_bwd")
+
+
+class RasterStageTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * len(STAGE_NAMES)), ("calls", C.c_int * len(STAGE_NAMES))]
+
+
 RASTER_SYMBOLS = (
+    "gvd_raster_profile_enable", "gvd_raster_profile_read",
     "gvd_raster_abi_version", "gvd_last_error", "gvd_raster_geom_bytes", "gvd_raster_binning_bytes",
     "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes", "gvd_raster_layout",
     "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible",
@@ -93,6 +101,8 @@ def raster():
     lib.gvd_raster_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for n in ("gvd_raster_layout", "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible"):
         getattr(lib, n).restype = C.c_int
+    lib.gvd_raster_profile_enable.argtypes = [C.c_int]
+    lib.gvd_raster_profile_read.argtypes = [C.POINTER(RasterStageTimes)]
     if lib.gvd_raster_abi_version() != 3:
         raise RuntimeError("libgvd_raster.so ABI version mismatch; rebuild")
     _raster = lib

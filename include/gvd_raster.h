@@ -161,6 +161,19 @@ typedef struct GvdRasterLayout {
 } GvdRasterLayout;
 GVD_API int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out);
 
+/* Optional per-stage device timing (CUDA events recorded on the caller's stream around each stage).
+ * Off by default; used by bench.py for the live roofline numbers. Not thread-safe; single stream. */
+enum {
+    GVD_STAGE_PREPROCESS = 0, GVD_STAGE_SCAN, GVD_STAGE_EMIT, GVD_STAGE_SORT, GVD_STAGE_PACK,
+    GVD_STAGE_RENDER_FWD, GVD_STAGE_RENDER_BWD, GVD_STAGE_GAUSSIAN_BWD, GVD_STAGE_COUNT
+};
+typedef struct GvdRasterStageTimes {
+    double ms[GVD_STAGE_COUNT];   /* accumulated device milliseconds per stage        */
+    int    calls[GVD_STAGE_COUNT];/* number of timed launches accumulated per stage   */
+} GvdRasterStageTimes;
+GVD_API int gvd_raster_profile_enable(int on);                   /* resets the accumulators   */
+GVD_API int gvd_raster_profile_read(GvdRasterStageTimes* out);   /* syncs pending events      */
+
 GVD_API int gvd_raster_abi_version(void);
 GVD_API const char* gvd_last_error(void);
 
