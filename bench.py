@@ -39,35 +39,56 @@ WORKLOADS = {
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons of this rank's GPU while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons of this rank's GPU (NVML, in-process) while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
 
     def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, int(r)))
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        self.join(timeout=2)
+        if self.h is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, b in names.items() if bits & b)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(self.samples)}
 
 
 def load_impl(impl):
@@ -193,6 +214,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), wall
 
+    # untimed: let the caching allocator reach its steady state, then the W warm-up steps proper
+    for _ in range(20):
+        resident_step()
     for _ in range(Wm):
         resident_step()
         e2e_step()
@@ -223,16 +247,21 @@ def main():
         st = gvd_native.RasterStageTimes()
         lib.gvd_raster_profile_read(C.byref(st))
         lib.gvd_raster_profile_enable(0)
-        stage_ms = {n: (st.ms[i] / st.calls[i] if st.calls[i] else 0.0) for i, n in enumerate(gvd_native.STAGE_NAMES)}
-        # algorithmic bytes per launch, SURVEY.md section 8(d)
-        nbits = 32 + max(1, (tiles - 1).bit_length())
-        passes = (nbits + 7) // 8
+        stage_ms = {n: st.ms[i] / nprof for i, n in enumerate(gvd_native.STAGE_NAMES)}  # per step
+        # algorithmic bytes per stage, SURVEY.md section 8(d). The reference's scan + duplicateWithKeys + 64-bit
+        # radix sort + identifyTileRanges (8P + 12R + 12R*2*passes + 8R+8T) are replaced here by a depth sort of the
+        # Gaussians and a counting sort on the tile id; the figures below are the bytes THESE stages must move.
+        chunks = (P + 255) // 256
+        vchunks = (visible + 255) // 256
         alg = {
-            "preprocess": P * (12 + 12 + 16 + 4 + 12 * (D + 1) ** 2) + P * 8 + visible * (8 + 4 + 24 + 12 + 16 + 3),
-            "scan": 8 * P, "emit": 12 * R, "sort": 12 * R * 2 * passes, "pack": 8 * R + 8 * tiles + 2 * 44 * R,
+            "preprocess": P * (12 + 12 + 16 + 4 + 12 * (D + 1) ** 2) + P * 16 + visible * 64,
+            "depth_sort": P * 8 * 2 * 4,
+            "bin_count": visible * 16 + vchunks * tiles * 4 * 3 + tiles * 12,
+            "bin_fill": visible * 16 + vchunks * tiles * 4 + 4 * R,
+            "export_keys": 0,
             "render_fwd": 44 * R + 24 * HWp + 8 * tiles,
             "render_bwd": 44 * R + 28 * HWp + 8 * tiles + 80 * R,
-            "gaussian_bwd": visible * (12 + 4 + 24 + 16 + 12 * (D + 1) ** 2 + 3 + 16 + 12 + 4) + visible * (12 + 24 + 12 * 16 + 12 + 16),
+            "gaussian_bwd": visible * (12 + 4 + 24 + 16 + 12 * (D + 1) ** 2 + 3 + 16 + 12 + 4) + P * (12 + 12 + 4 + 12 * 16 + 12 + 16),
         }
         top = max(stage_ms, key=lambda k: stage_ms[k])
         peaks = {}
@@ -248,7 +277,9 @@ def main():
                     "algorithmic_bytes": alg[top],
                     "note": "render kernels are fp32-ALU/SFU/atomic bound, not HBM bound (SURVEY.md 0.5); see DESIGN.md",
                     "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-                    "stage_gbs": {k: round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None for k, v in stage_ms.items()}}
+                    "stage_gbs": {k: round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None for k, v in stage_ms.items()},
+                    "traversed_note": "render_* GB/s use SURVEY 8d's whole-list byte count (44 B x R); tiles stop early and "
+                                      "actually walk only a few % of their lists"}
 
     if rank != 0:
         if world > 1:
@@ -270,9 +301,10 @@ def main():
                    "parallelism": f"view-parallel dp{world}" + (" + NCCL all-reduce of 62 floats/Gaussian per step" if world > 1 else "")},
         "e2e": {"value": round(e2e_views_per_s, 2), "unit": "views/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4), "wall_ms_per_step": round(wall_e2e / K * 1e3, 4)},
-        "gpu_launches": (6 * K * 2) if args.impl == "ours" else 0,
-        "gpu_launches_note": "own kernels in the two timed regions: preprocess, emit_keys, pack, render_fwd, render_bwd, "
-                             "gaussian_bwd per step (+ CUB scan/radix-sort library kernels, not counted)",
+        "gpu_launches": (8 * K * 2) if args.impl == "ours" else 0,
+        "gpu_launches_note": "own kernels in the two timed regions: preprocess, bin_count, bin_prefix, bin_ranges, bin_fill, "
+                             "render_fwd, render_bwd, gaussian_bwd per step (+ CUB radix-sort library kernels for the "
+                             "depth sort, not counted)",
         "clocks": clocks,
     }
     if roofline:

@@ -92,29 +92,31 @@ void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128) {
 
 // The three carve_* functions define the scratch layouts; calling them on a null base yields sizes
 // (same trick as CudaRasterizer::required<T>, rasterizer_impl.h:63-69).
-RasterGeomPtrs carve_geom(char*& chunk, size_t P) {
+RasterGeomPtrs carve_geom(char*& chunk, size_t P, size_t T) {
     RasterGeomPtrs g;
     obtain(chunk, g.splat, P);
     obtain(chunk, g.clamped, P);
     obtain(chunk, g.tiles_touched, P);
-    obtain(chunk, g.point_offsets, P);
-    g.scan_temp_bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, (int)P);
-    obtain(chunk, g.scan_temp, g.scan_temp_bytes);
+    obtain(chunk, g.depth_key, P);
+    obtain(chunk, g.gidx, P);
+    obtain(chunk, g.depth_sorted, P);
+    obtain(chunk, g.order, P);
+    g.sort_temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, g.sort_temp_bytes, g.depth_key, g.depth_sorted, g.gidx, g.order, (int)P);
+    obtain(chunk, g.sort_temp, g.sort_temp_bytes);
+    g.chunks = (P + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK;
+    obtain(chunk, g.chunk_flags, g.chunks);
+    obtain(chunk, g.hist, g.chunks * T);
+    obtain(chunk, g.tile_total, T);
+    obtain(chunk, g.num_rendered, 1);
     return g;
 }
 
-RasterBinPtrs carve_binning(char*& chunk, size_t R) {
+RasterBinPtrs carve_binning(char*& chunk, size_t R, bool with_keys) {
     RasterBinPtrs b;
-    obtain(chunk, b.point_list, R);
-    obtain(chunk, b.point_list_unsorted, R);
-    obtain(chunk, b.keys, R);
-    obtain(chunk, b.keys_unsorted, R);
-    b.sort_temp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b.sort_temp_bytes, b.keys_unsorted, b.keys, b.point_list_unsorted,
-                                    b.point_list, (int)R);
-    obtain(chunk, b.sort_temp, b.sort_temp_bytes);
-    obtain(chunk, b.packed, R);
+    obtain(chunk, b.point_list, R + 4);  // +4: the TMA id copies round their length up to 16 bytes
+    b.keys = nullptr;
+    if (with_keys) obtain(chunk, b.keys, R);
     return b;
 }
 
@@ -164,14 +166,15 @@ int gvd_raster_profile_read(GvdRasterStageTimes* out) {
 }
 const char* gvd_last_error(void) { return g_err.c_str(); }
 
-size_t gvd_raster_geom_bytes(int P) {
+size_t gvd_raster_geom_bytes(int P, int width, int height) {
     char* p = nullptr;
-    carve_geom(p, (size_t)P);
+    dim3 g = tile_grid(width, height);
+    carve_geom(p, (size_t)P, (size_t)g.x * g.y);
     return (size_t)p + 128;
 }
-size_t gvd_raster_binning_bytes(int R) {
+size_t gvd_raster_binning_bytes(int R, int export_keys) {
     char* p = nullptr;
-    carve_binning(p, (size_t)R);
+    carve_binning(p, (size_t)R, export_keys != 0);
     return (size_t)p + 128;
 }
 size_t gvd_raster_img_bytes(int width, int height) {
@@ -184,21 +187,18 @@ size_t gvd_raster_backward_scratch_bytes(int P) { return (size_t)P * GVD_ACC_STR
 
 int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out) {
     if (!out) return fail_msg("gvd_raster_layout: null out");
+    dim3 tg = tile_grid(width, height);
     char* p = nullptr;
-    RasterGeomPtrs g = carve_geom(p, (size_t)P);
+    RasterGeomPtrs g = carve_geom(p, (size_t)P, (size_t)tg.x * tg.y);
     out->geom_splat = (size_t)g.splat;
     out->geom_clamped = (size_t)g.clamped;
     out->geom_tiles_touched = (size_t)g.tiles_touched;
-    out->geom_point_offsets = (size_t)g.point_offsets;
+    out->geom_order = (size_t)g.order;
     p = nullptr;
-    RasterBinPtrs b = carve_binning(p, (size_t)R);
+    RasterBinPtrs b = carve_binning(p, (size_t)R, true);
     out->bin_point_list = (size_t)b.point_list;
     out->bin_point_list_keys = (size_t)b.keys;
-    out->bin_point_list_unsorted = (size_t)b.point_list_unsorted;
-    out->bin_keys_unsorted = (size_t)b.keys_unsorted;
-    out->bin_packed = (size_t)b.packed;
     p = nullptr;
-    dim3 tg = tile_grid(width, height);
     RasterImgPtrs im = carve_img(p, (size_t)tg.x * tg.y, (size_t)width * height);
     out->img_ranges = (size_t)im.ranges;
     out->img_n_contrib = (size_t)im.n_contrib;
@@ -225,12 +225,13 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     const float focal_y = a->height / (2.0f * a->tan_fovy);
     const float focal_x = a->width / (2.0f * a->tan_fovx);
     const dim3 grid = tile_grid(a->width, a->height);
-    if (grid.x > 0xffff || grid.y > 0xffff) return fail_msg("gvd_raster_forward: image too large");
     const size_t tiles = (size_t)grid.x * grid.y;
+    if (grid.x > 0xffff || grid.y > 0xffff || tiles > GVD_MAX_TILES)
+        return fail_msg("gvd_raster_forward: image too large (more than 49152 tiles of 16x16)");
 
-    char* gp = (char*)a->geom_alloc(a->alloc_user, gvd_raster_geom_bytes(P));
+    char* gp = (char*)a->geom_alloc(a->alloc_user, gvd_raster_geom_bytes(P, a->width, a->height));
     if (!gp) return fail_msg("gvd_raster_forward: geometry allocator returned null");
-    RasterGeomPtrs g = carve_geom(gp, (size_t)P);
+    RasterGeomPtrs g = carve_geom(gp, (size_t)P, tiles);
     char* ip = (char*)a->img_alloc(a->alloc_user, gvd_raster_img_bytes(a->width, a->height));
     if (!ip) return fail_msg("gvd_raster_forward: image allocator returned null");
     RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
@@ -241,51 +242,48 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     }
     GVD_STAGE("preprocess");
     {
-        StageScope t(GVD_STAGE_SCAN, stream);
-        GVD_CHECK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, P,
-                                                stream),
-                  "InclusiveSum");
+        // level 1: Gaussians by depth (stable; ties keep id order). Culled ones carry key 0xFFFFFFFF.
+        StageScope t(GVD_STAGE_SORT, stream);
+        GVD_CHECK(cub::DeviceRadixSort::SortPairs(g.sort_temp, g.sort_temp_bytes, g.depth_key, g.depth_sorted, g.gidx,
+                                                  g.order, P, 0, 32, stream),
+                  "SortPairs(depth)");
     }
-    GVD_STAGE("scan");
+    GVD_STAGE("depth sort");
+    {
+        // level 2a: per-chunk tile histograms -> per-tile prefixes -> ranges and R
+        StageScope t(GVD_STAGE_SCAN, stream);
+        GVD_CHECK(gvd_launch_bin_count(P, g, im, grid, stream), "bin_count");
+    }
+    GVD_STAGE("bin_count");
 
     // Size of the instance list. Like the reference (rasterizer_impl.cu:281-282) this is the one
     // host round trip of the forward: the binning buffer is caller-owned and sized from R.
     int num_rendered = 0;
-    GVD_CHECK(cudaMemcpyAsync(&num_rendered, g.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, stream),
+    GVD_CHECK(cudaMemcpyAsync(&num_rendered, g.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, stream),
               "copy num_rendered");
     GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
     a->num_rendered = num_rendered;
 
-    char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered));
+    char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered, a->export_keys));
     if (!bp) return fail_msg("gvd_raster_forward: binning allocator returned null");
-    RasterBinPtrs b = carve_binning(bp, (size_t)num_rendered);
+    RasterBinPtrs b = carve_binning(bp, (size_t)num_rendered, a->export_keys != 0);
 
-    GVD_CHECK(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), stream), "memset ranges");
     if (num_rendered > 0) {
         {
+            // level 2b: stable scatter of the Gaussian ids into the tile lists
             StageScope t(GVD_STAGE_EMIT, stream);
-            gvd_launch_emit_keys(P, g, b, grid, stream);
+            GVD_CHECK(gvd_launch_bin_fill(P, g, b, im, grid, stream), "bin_fill");
         }
-        GVD_STAGE("emit_keys");
-
-        const int bit = (int)higher_msb((uint32_t)tiles);
-        {
-            StageScope t(GVD_STAGE_SORT, stream);
-            GVD_CHECK(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys,
-                                                      b.point_list_unsorted, b.point_list, num_rendered, 0, 32 + bit,
-                                                      stream),
-                      "SortPairs");
-        }
-        GVD_STAGE("sort");
-        {
+        GVD_STAGE("bin_fill");
+        if (a->export_keys) {
             StageScope t(GVD_STAGE_PACK, stream);
-            gvd_launch_pack(num_rendered, g, b, im, grid, stream);
+            gvd_launch_export_keys(num_rendered, g, b, im, grid, stream);
         }
-        GVD_STAGE("pack");
+        GVD_STAGE("export_keys");
     }
     {
         StageScope t(GVD_STAGE_RENDER_FWD, stream);
-        gvd_launch_render_forward(*a, b, im, grid, stream);
+        gvd_launch_render_forward(*a, g, b, im, grid, stream);
     }
     GVD_STAGE("render_forward");
     return 0;
@@ -311,9 +309,9 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     const size_t tiles = (size_t)grid.x * grid.y;
 
     char* gp = (char*)a->geom_buffer;
-    RasterGeomPtrs g = carve_geom(gp, (size_t)P);
+    RasterGeomPtrs g = carve_geom(gp, (size_t)P, tiles);
     char* bp = (char*)a->binning_buffer;
-    RasterBinPtrs b = carve_binning(bp, (size_t)a->R);
+    RasterBinPtrs b = carve_binning(bp, (size_t)a->R, false);
     char* ip = (char*)a->img_buffer;
     RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
 
@@ -323,7 +321,7 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     if (a->R > 0) {
         {
             StageScope t(GVD_STAGE_RENDER_BWD, stream);
-            gvd_launch_render_backward(*a, b, im, acc, grid, stream);
+            gvd_launch_render_backward(*a, g, b, im, acc, grid, stream);
         }
         GVD_STAGE("render_backward");
     }

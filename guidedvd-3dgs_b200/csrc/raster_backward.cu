@@ -1,7 +1,8 @@
 // raster_backward.cu -- backward kernels of the B200-native Gaussian rasterizer (sm_100a).
 //
 //   render_backward_kernel   per tile, back-to-front replay (DGR/cuda_rasterizer/backward.cu:415-601).
-//                            Same TMA-staged packed list and sub-tile masks as the forward. The ten
+//                            Same staging as the forward (ids by TMA bulk copy, records gathered from the
+//                            L2-resident per-Gaussian array one batch ahead, sub-tile culling). The ten
 //                            per-(pixel,Gaussian) partial gradients are summed across the warp with a
 //                            transposing butterfly (12 shuffles instead of 50) and leave the SM as ONE
 //                            predicated RED.ADD.F32 instruction per (warp, instance) into a packed
@@ -76,22 +77,24 @@ __device__ __forceinline__ int warp_reduce10(float (&v)[10], uint32_t lane, floa
 }
 
 __global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
-    const uint2* __restrict__ ranges, const SplatRec* __restrict__ packed, int W, int H, uint32_t tiles_x,
-    const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
-    const float* __restrict__ dL_dalphas, float* __restrict__ acc) {
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
+    int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, const float* __restrict__ alphas,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas, float* __restrict__ acc) {
     __shared__ __align__(128) float4 buf[2][GVD_BATCH * 3];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(128) IdSlot ids[3];
+    __shared__ __align__(8) uint64_t bar[3];
     __shared__ uint32_t warp_max[GVD_BLOCK / 32];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tile = blockIdx.x;
     const uint32_t tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const uint32_t px = tile_x * GVD_TILE_X + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = tile_y * GVD_TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t sub_x = tile_x * GVD_TILE_X + (warp & 1) * 8, sub_y = tile_y * GVD_TILE_Y + (warp >> 1) * 4;
+    const uint32_t px = sub_x + (lane & 7), py = sub_y + (lane >> 3);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = W * py + px;
     const float2 pixf = {(float)px, (float)py};
+    const float sxf = (float)sub_x, syf = (float)sub_y;
 
     const uint2 range = ranges[tile];
     const int n_all = (int)(range.y - range.x);
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
         mbar_fence_init();
     }
     if (lane == 0) warp_max[warp] = warp_last;
@@ -112,13 +116,23 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
     // Entries at positions >= block_last are skipped by every pixel: never stage them.
     const int n = min(n_all, (int)block_last);
     const int rounds = (n + GVD_BATCH - 1) / GVD_BATCH;
-    const SplatRec* list = packed + range.x;
+    const uint32_t* list = point_list + range.x;
+    // batch i (counted from the back) covers list positions [bstart(i), bstart(i) + bcnt(i))
+    auto bstart = [n](int i) { return max(0, n - (i + 1) * GVD_BATCH); };
+    auto bcnt = [n, &bstart](int i) { return (n - i * GVD_BATCH) - bstart(i); };
 
-    if (tid == 0 && rounds > 0) {
-        const int start = max(0, n - GVD_BATCH);
-        const uint32_t bytes = (uint32_t)(n - start) * (uint32_t)sizeof(SplatRec);
-        mbar_arrive_expect_tx(&bar[0], bytes);
-        tma_bulk_g2s(&buf[0][0], list + start, bytes, &bar[0]);
+    if (tid == 0) {
+        if (rounds > 0) issue_id_copy(&ids[0], &bar[0], list + bstart(0), bcnt(0));
+        if (rounds > 1) issue_id_copy(&ids[1], &bar[1], list + bstart(1), bcnt(1));
+    }
+    if (rounds > 0) {
+        mbar_wait(&bar[0], 0);
+        if ((int)tid < bcnt(0)) {
+            const float4* src = reinterpret_cast<const float4*>(splat + ids[0].v[id_lead(list + bstart(0)) + tid]);
+            buf[0][tid * 3 + 0] = __ldg(src);
+            buf[0][tid * 3 + 1] = __ldg(src + 1);
+            buf[0][tid * 3 + 2] = __ldg(src + 2);
+        }
     }
 
     const size_t HW = (size_t)H * W;
@@ -142,96 +156,109 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
     bg_dot_dpixel += bg_color[2] * dL_dpixel2;
 
     for (int i = 0; i < rounds; ++i) {
-        __syncthreads();  // everyone is done with buf[(i+1)&1]
+        __syncthreads();  // publishes buf[i&1]; everyone is done with buf[(i+1)&1] and ids[(i+2)%3]
         const int cur = i & 1;
-        const int hi = n - i * GVD_BATCH;            // exclusive end position of this batch
-        const int start = max(0, hi - GVD_BATCH);    // first position of this batch
-        const int cnt = hi - start;
-        if (tid == 0 && i + 1 < rounds) {
-            const int nhi = n - (i + 1) * GVD_BATCH;
-            const int nstart = max(0, nhi - GVD_BATCH);
-            const uint32_t bytes = (uint32_t)(nhi - nstart) * (uint32_t)sizeof(SplatRec);
-            mbar_arrive_expect_tx(&bar[cur ^ 1], bytes);
-            tma_bulk_g2s(&buf[cur ^ 1][0], list + nstart, bytes, &bar[cur ^ 1]);
+        const int start = bstart(i);
+        const int cnt = bcnt(i);
+        float4 pa, pb, pc;
+        const bool have_next = (i + 1 < rounds) && ((int)tid < bcnt(i + 1));
+        if (i + 1 < rounds) {
+            mbar_wait(&bar[(i + 1) % 3], (uint32_t)(((i + 1) / 3) & 1));
+            if (have_next) {
+                const float4* src = reinterpret_cast<const float4*>(
+                    splat + ids[(i + 1) % 3].v[id_lead(list + bstart(i + 1)) + tid]);
+                pa = __ldg(src);
+                pb = __ldg(src + 1);
+                pc = __ldg(src + 2);
+            }
+            if (tid == 0 && i + 2 < rounds)
+                issue_id_copy(&ids[(i + 2) % 3], &bar[(i + 2) % 3], list + bstart(i + 2), bcnt(i + 2));
         }
-        mbar_wait(&bar[cur], (uint32_t)((i >> 1) & 1));
-        if ((uint32_t)start >= warp_last) continue;  // warp-uniform: nothing in this batch for us
 
-        const float4* rec = buf[cur];
-        for (int chunk = (cnt - 1) / 32; chunk >= 0; --chunk) {
-            const int e = chunk * 32 + (int)lane;
-            const uint32_t mk = (e < cnt) ? __float_as_uint(rec[e * 3 + 2].w) : 0u;
-            unsigned m = __ballot_sync(0xffffffffu, ((mk >> warp) & 1u) && (uint32_t)(start + e) < warp_last);
-            while (m) {
-                const int bsel = 31 - __clz(m);
-                m &= ~(1u << bsel);
-                const int j = chunk * 32 + bsel;
-                const uint32_t pos = (uint32_t)(start + j);
-                const float4 ra = rec[j * 3], rb = rec[j * 3 + 1], rc = rec[j * 3 + 2];
-
-                // backward.cu:509-528
-                const float2 d = {ra.x - pixf.x, ra.y - pixf.y};
-                const float power = -0.5f * (ra.z * d.x * d.x + rb.x * d.y * d.y) - ra.w * d.x * d.y;
-                const float G = expf(power);
-                const float alpha = fminf(0.99f, rb.y * G);
-                const bool contrib = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                if (!__any_sync(0xffffffffu, contrib)) continue;
-
-                float g[10];
-#pragma unroll
-                for (int k = 0; k < 10; ++k) g[k] = 0.0f;
-                if (contrib) {
-                    T = T / (1.f - alpha);
-                    const float dchannel_dcolor = alpha * T;
-                    const float dpixel_depth_ddepth = alpha * T;
-                    float dL_dopa = 0.0f;
-                    // colours (backward.cu:538-551)
-                    accum_rec0 = last_alpha * last_color0 + (1.f - last_alpha) * accum_rec0;
-                    last_color0 = rb.z;
-                    dL_dopa += (rb.z - accum_rec0) * dL_dpixel0;
-                    g[6] = dchannel_dcolor * dL_dpixel0;
-                    accum_rec1 = last_alpha * last_color1 + (1.f - last_alpha) * accum_rec1;
-                    last_color1 = rb.w;
-                    dL_dopa += (rb.w - accum_rec1) * dL_dpixel1;
-                    g[7] = dchannel_dcolor * dL_dpixel1;
-                    accum_rec2 = last_alpha * last_color2 + (1.f - last_alpha) * accum_rec2;
-                    last_color2 = rc.x;
-                    dL_dopa += (rc.x - accum_rec2) * dL_dpixel2;
-                    g[8] = dchannel_dcolor * dL_dpixel2;
-                    // depth (backward.cu:553-563)
-                    const float c_d = rc.y;
-                    accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                    last_depth = c_d;
-                    dL_dopa += (c_d - accum_depth_rec) * dL_dpixel_depth;
-                    g[9] = dpixel_depth_ddepth * dL_dpixel_depth;
-                    // alpha (backward.cu:565-567)
-                    accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-                    dL_dopa += (1 - accum_alpha_rec) * dL_dalpha;
-
-                    dL_dopa *= T;
-                    last_alpha = alpha;
-                    // background (backward.cu:573-578)
-                    dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-
-                    const float dL_dG = rb.y * dL_dopa;
-                    const float gdx = G * d.x;
-                    const float gdy = G * d.y;
-                    const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-                    const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-                    g[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    g[1] = dL_dG * dG_ddely * ddely_dy;
-                    g[2] = -0.5f * gdx * d.x * dL_dG;
-                    g[3] = -0.5f * gdx * d.y * dL_dG;
-                    g[4] = -0.5f * gdy * d.y * dL_dG;
-                    g[5] = G * dL_dopa;
+        if ((uint32_t)start < warp_last) {  // warp-uniform: otherwise nothing in this batch for us
+            const float4* rec = buf[cur];
+            const uint32_t* idv = ids[i % 3].v + id_lead(list + start);
+            for (int chunk = (cnt - 1) / 32; chunk >= 0; --chunk) {
+                const int e = chunk * 32 + (int)lane;
+                bool hit = false;
+                if (e < cnt && (uint32_t)(start + e) < warp_last) {
+                    const float4 ea = rec[e * 3], ec = rec[e * 3 + 2];
+                    hit = subtile_hit(ea.x, ea.y, ec.z, ec.w, sxf, syf);
                 }
-                float total;
-                const int slot = warp_reduce10(g, lane, total);
-                if (slot >= 0) {
-                    const uint32_t gid = __float_as_uint(rc.z);
-                    atomicAdd(acc + (size_t)gid * GVD_ACC_STRIDE + slot, total);
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int bsel = 31 - __clz(m);
+                    m &= ~(1u << bsel);
+                    const int j = chunk * 32 + bsel;
+                    const uint32_t pos = (uint32_t)(start + j);
+                    const float4 ra = rec[j * 3], rb = rec[j * 3 + 1], rc = rec[j * 3 + 2];
+
+                    // backward.cu:509-528
+                    const float2 d = {ra.x - pixf.x, ra.y - pixf.y};
+                    const float power = -0.5f * (ra.z * d.x * d.x + rb.x * d.y * d.y) - ra.w * d.x * d.y;
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, rb.y * G);
+                    const bool contrib = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    if (!__any_sync(0xffffffffu, contrib)) continue;
+
+                    float g[10];
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) g[k] = 0.0f;
+                    if (contrib) {
+                        T = T / (1.f - alpha);
+                        const float dchannel_dcolor = alpha * T;
+                        const float dpixel_depth_ddepth = alpha * T;
+                        float dL_dopa = 0.0f;
+                        // colours (backward.cu:538-551)
+                        accum_rec0 = last_alpha * last_color0 + (1.f - last_alpha) * accum_rec0;
+                        last_color0 = rb.z;
+                        dL_dopa += (rb.z - accum_rec0) * dL_dpixel0;
+                        g[6] = dchannel_dcolor * dL_dpixel0;
+                        accum_rec1 = last_alpha * last_color1 + (1.f - last_alpha) * accum_rec1;
+                        last_color1 = rb.w;
+                        dL_dopa += (rb.w - accum_rec1) * dL_dpixel1;
+                        g[7] = dchannel_dcolor * dL_dpixel1;
+                        accum_rec2 = last_alpha * last_color2 + (1.f - last_alpha) * accum_rec2;
+                        last_color2 = rc.x;
+                        dL_dopa += (rc.x - accum_rec2) * dL_dpixel2;
+                        g[8] = dchannel_dcolor * dL_dpixel2;
+                        // depth (backward.cu:553-563)
+                        const float c_d = rc.y;
+                        accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+                        last_depth = c_d;
+                        dL_dopa += (c_d - accum_depth_rec) * dL_dpixel_depth;
+                        g[9] = dpixel_depth_ddepth * dL_dpixel_depth;
+                        // alpha (backward.cu:565-567)
+                        accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
+                        dL_dopa += (1 - accum_alpha_rec) * dL_dalpha;
+
+                        dL_dopa *= T;
+                        last_alpha = alpha;
+                        // background (backward.cu:573-578)
+                        dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                        const float dL_dG = rb.y * dL_dopa;
+                        const float gdx = G * d.x;
+                        const float gdy = G * d.y;
+                        const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
+                        const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                        g[0] = dL_dG * dG_ddelx * ddelx_dx;
+                        g[1] = dL_dG * dG_ddely * ddely_dy;
+                        g[2] = -0.5f * gdx * d.x * dL_dG;
+                        g[3] = -0.5f * gdx * d.y * dL_dG;
+                        g[4] = -0.5f * gdy * d.y * dL_dG;
+                        g[5] = G * dL_dopa;
+                    }
+                    float total;
+                    const int slot = warp_reduce10(g, lane, total);
+                    if (slot >= 0) atomicAdd(acc + (size_t)idv[j] * GVD_ACC_STRIDE + slot, total);
                 }
             }
+        }
+        if (have_next) {
+            buf[cur ^ 1][tid * 3 + 0] = pa;
+            buf[cur ^ 1][tid * 3 + 1] = pb;
+            buf[cur ^ 1][tid * 3 + 2] = pc;
         }
     }
 }
@@ -248,11 +275,33 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
     return r;
 }
 
-__device__ __forceinline__ void store3(float* p, float3 v, float s) {
-    p[0] = v.x * s;
-    p[1] = v.y * s;
-    p[2] = v.z * s;
+// Block-cooperative store of one [P,3] tensor: each thread parks its 3 floats in shared memory
+// (stride 3 is conflict-free), then the block writes the 768 floats back with unit-stride stores.
+__device__ __forceinline__ void store_p3_coalesced(float* __restrict__ dst, float* stage, int block_first, int P,
+                                                   float x, float y, float z) {
+    const int t = threadIdx.x;
+    stage[3 * t] = x;
+    stage[3 * t + 1] = y;
+    stage[3 * t + 2] = z;
+    __syncthreads();
+    const int n = 3 * min(256, P - block_first);
+    float* base = dst + 3 * (size_t)block_first;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = t + 256 * k;
+        if (i < n) base[i] = stage[i];
+    }
+    __syncthreads();
 }
+
+#define SH(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
+#define OUT(k, val)                                 \
+    {                                               \
+        const float3 _t = f3_scale((val), dL_dRGB); \
+        o_sh[3 * (k)] = _t.x * conf;                \
+        o_sh[3 * (k) + 1] = _t.y * conf;            \
+        o_sh[3 * (k) + 2] = _t.z * conf;            \
+    }
 
 __global__ void __launch_bounds__(256) gaussian_backward_kernel(
     int P, int D, int M, const float3* __restrict__ means, const int* __restrict__ radii,
@@ -263,295 +312,313 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(
     const float* __restrict__ confidence, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dmeans3D,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dcov3D,
     float* __restrict__ dL_dsh, float* __restrict__ dL_dscales, float* __restrict__ dL_drots) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    __shared__ float stage[3 * 256];
+    const int block_first = blockIdx.x * blockDim.x;
+    const int idx = block_first + threadIdx.x;
+    const bool valid = idx < P;
+    const bool visible = valid && (radii[idx] > 0);
 
-    if (!(radii[idx] > 0)) {
-        // the reference returns torch::zeros for Gaussians it never touched (rasterize_points.cu:158-167)
-        store3(dL_dmeans2D + 3 * (size_t)idx, {0, 0, 0}, 1.f);
-        store3(dL_dmeans3D + 3 * (size_t)idx, {0, 0, 0}, 1.f);
-        dL_dopacity[idx] = 0.f;
-        if (dL_dcolors) store3(dL_dcolors + 3 * (size_t)idx, {0, 0, 0}, 1.f);
-        if (dL_dcov3D)
-            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = 0.f;
-        if (dL_dsh)
-            for (int k = 0; k < 3 * M; ++k) dL_dsh[(size_t)idx * 3 * M + k] = 0.f;
-        if (dL_dscales) store3(dL_dscales + 3 * (size_t)idx, {0, 0, 0}, 1.f);
-        if (dL_drots) {
-            float4* o = reinterpret_cast<float4*>(dL_drots) + idx;
-            *o = make_float4(0, 0, 0, 0);
-        }
-        return;
-    }
-
-    const float conf = confidence ? confidence[idx] : 1.0f;
-    const float4* ap = reinterpret_cast<const float4*>(acc + (size_t)idx * GVD_ACC_STRIDE);
-    const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
-    const float2 dL_dmean2D = {a0.x, a0.y};
-    const float3 dL_dconic = {a0.z, a0.w, a1.x};
-    const float dL_dopac = a1.y;
-    const float3 dL_dcolor = {a1.z, a1.w, a2.x};
-    const float dL_ddepth = a2.y;
-
-    // ---------------- computeCov2DCUDA (backward.cu:144-274) ----------------
-    float cov3D_local[6];
-    const float* cov3D;
-    if (cov3D_precomp != nullptr)
-        cov3D = cov3D_precomp + 6 * (size_t)idx;
-    else {
-        cov3d_from_scale_rot(scales[idx], scale_modifier, rotations[idx], cov3D_local);
-        cov3D = cov3D_local;
-    }
-    const float3 mean = means[idx];
-    float3 t = xform_point_4x3(mean, view);
-    const float limx = 1.3f * tan_fovx;
-    const float limy = 1.3f * tan_fovy;
-    const float txtz = t.x / t.z;
-    const float tytz = t.y / t.z;
-    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
-    const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
-    const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
-
-    M3 J = m3_make(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z), 0, 0, 0);
-    M3 Wm = m3_make(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
-    M3 Vrk = m3_make(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
-    M3 Tm = m3_mul(Wm, J);
-    M3 cov2D = m3_mul(m3_mul(m3_transpose(Tm), m3_transpose(Vrk)), Tm);
-
-    const float a = cov2D.m[0][0] += 0.3f;
-    const float b = cov2D.m[0][1];
-    const float c = cov2D.m[1][1] += 0.3f;
-    const float denom = a * c - b * b;
-    float dL_da = 0, dL_db = 0, dL_dc = 0;
-    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    float dcov[6];
-    if (denom2inv != 0) {
-        dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
-        dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
-        dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
-
-        dcov[0] = (Tm.m[0][0] * Tm.m[0][0] * dL_da + Tm.m[0][0] * Tm.m[1][0] * dL_db + Tm.m[1][0] * Tm.m[1][0] * dL_dc);
-        dcov[3] = (Tm.m[0][1] * Tm.m[0][1] * dL_da + Tm.m[0][1] * Tm.m[1][1] * dL_db + Tm.m[1][1] * Tm.m[1][1] * dL_dc);
-        dcov[5] = (Tm.m[0][2] * Tm.m[0][2] * dL_da + Tm.m[0][2] * Tm.m[1][2] * dL_db + Tm.m[1][2] * Tm.m[1][2] * dL_dc);
-        dcov[1] = 2 * Tm.m[0][0] * Tm.m[0][1] * dL_da + (Tm.m[0][0] * Tm.m[1][1] + Tm.m[0][1] * Tm.m[1][0]) * dL_db +
-                  2 * Tm.m[1][0] * Tm.m[1][1] * dL_dc;
-        dcov[2] = 2 * Tm.m[0][0] * Tm.m[0][2] * dL_da + (Tm.m[0][0] * Tm.m[1][2] + Tm.m[0][2] * Tm.m[1][0]) * dL_db +
-                  2 * Tm.m[1][0] * Tm.m[1][2] * dL_dc;
-        dcov[4] = 2 * Tm.m[0][2] * Tm.m[0][1] * dL_da + (Tm.m[0][1] * Tm.m[1][2] + Tm.m[0][2] * Tm.m[1][1]) * dL_db +
-                  2 * Tm.m[1][1] * Tm.m[1][2] * dL_dc;
-    } else {
+    // Everything the reference leaves at torch::zeros for untouched Gaussians (rasterize_points.cu:158-167)
+    // is produced here as explicit zeros, so no separate zero-fill pass over the outputs is needed.
+    float2 o_m2 = {0.f, 0.f};
+    float3 o_m3 = {0.f, 0.f, 0.f}, o_sc = {0.f, 0.f, 0.f}, o_col = {0.f, 0.f, 0.f};
+    float4 o_rot = {0.f, 0.f, 0.f, 0.f};
+    float o_op = 0.f;
+    float o_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float o_sh[48];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dcov[k] = 0;
-    }
+    for (int k = 0; k < 48; ++k) o_sh[k] = 0.f;
 
-    const float dL_dT00 = 2 * (Tm.m[0][0] * Vrk.m[0][0] + Tm.m[0][1] * Vrk.m[0][1] + Tm.m[0][2] * Vrk.m[0][2]) * dL_da +
-                          (Tm.m[1][0] * Vrk.m[0][0] + Tm.m[1][1] * Vrk.m[0][1] + Tm.m[1][2] * Vrk.m[0][2]) * dL_db;
-    const float dL_dT01 = 2 * (Tm.m[0][0] * Vrk.m[1][0] + Tm.m[0][1] * Vrk.m[1][1] + Tm.m[0][2] * Vrk.m[1][2]) * dL_da +
-                          (Tm.m[1][0] * Vrk.m[1][0] + Tm.m[1][1] * Vrk.m[1][1] + Tm.m[1][2] * Vrk.m[1][2]) * dL_db;
-    const float dL_dT02 = 2 * (Tm.m[0][0] * Vrk.m[2][0] + Tm.m[0][1] * Vrk.m[2][1] + Tm.m[0][2] * Vrk.m[2][2]) * dL_da +
-                          (Tm.m[1][0] * Vrk.m[2][0] + Tm.m[1][1] * Vrk.m[2][1] + Tm.m[1][2] * Vrk.m[2][2]) * dL_db;
-    const float dL_dT10 = 2 * (Tm.m[1][0] * Vrk.m[0][0] + Tm.m[1][1] * Vrk.m[0][1] + Tm.m[1][2] * Vrk.m[0][2]) * dL_dc +
-                          (Tm.m[0][0] * Vrk.m[0][0] + Tm.m[0][1] * Vrk.m[0][1] + Tm.m[0][2] * Vrk.m[0][2]) * dL_db;
-    const float dL_dT11 = 2 * (Tm.m[1][0] * Vrk.m[1][0] + Tm.m[1][1] * Vrk.m[1][1] + Tm.m[1][2] * Vrk.m[1][2]) * dL_dc +
-                          (Tm.m[0][0] * Vrk.m[1][0] + Tm.m[0][1] * Vrk.m[1][1] + Tm.m[0][2] * Vrk.m[1][2]) * dL_db;
-    const float dL_dT12 = 2 * (Tm.m[1][0] * Vrk.m[2][0] + Tm.m[1][1] * Vrk.m[2][1] + Tm.m[1][2] * Vrk.m[2][2]) * dL_dc +
-                          (Tm.m[0][0] * Vrk.m[2][0] + Tm.m[0][1] * Vrk.m[2][1] + Tm.m[0][2] * Vrk.m[2][2]) * dL_db;
+    if (visible) {
+        const float conf = confidence ? confidence[idx] : 1.0f;
+        const float4* ap = reinterpret_cast<const float4*>(acc + (size_t)idx * GVD_ACC_STRIDE);
+        const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
+        const float2 dL_dmean2D = {a0.x, a0.y};
+        const float3 dL_dconic = {a0.z, a0.w, a1.x};
+        const float dL_dopac = a1.y;
+        const float3 dL_dcolor = {a1.z, a1.w, a2.x};
+        const float dL_ddepth = a2.y;
 
-    const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
-    const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
-    const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
-    const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
+        // ---------------- computeCov2DCUDA (backward.cu:144-274) ----------------
+        float cov3D_local[6];
+        const float* cov3D;
+        if (cov3D_precomp != nullptr)
+            cov3D = cov3D_precomp + 6 * (size_t)idx;
+        else {
+            cov3d_from_scale_rot(scales[idx], scale_modifier, rotations[idx], cov3D_local);
+            cov3D = cov3D_local;
+        }
+        const float3 mean = means[idx];
+        float3 t = xform_point_4x3(mean, view);
+        const float limx = 1.3f * tan_fovx;
+        const float limy = 1.3f * tan_fovy;
+        const float txtz = t.x / t.z;
+        const float tytz = t.y / t.z;
+        t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+        t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+        const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+        const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
 
-    const float tz = 1.f / t.z;
-    const float tz2 = tz * tz;
-    const float tz3 = tz2 * tz;
-    const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
-    const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
-    const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
-                         (2 * h_y * t.y) * tz3 * dL_dJ12;
-    // auxiliary.h:89-97 (transformVec4x3Transpose)
-    float3 dL_dmean = {view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz,
-                       view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
-                       view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz};
+        M3 J = m3_make(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z), 0, 0, 0);
+        M3 Wm = m3_make(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
+        M3 Vrk = m3_make(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+        M3 Tm = m3_mul(Wm, J);
+        M3 cov2D = m3_mul(m3_mul(m3_transpose(Tm), m3_transpose(Vrk)), Tm);
 
-    // ---------------- preprocessCUDA backward (backward.cu:346-412) ----------------
-    const float3 m = mean;
-    const float4 m_hom = xform_point_4x4(m, proj);
-    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-    const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
-    const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
-    float3 dm;
-    dm.x = (proj[0] * m_w - proj[3] * mul1) * dL_dmean2D.x + (proj[1] * m_w - proj[3] * mul2) * dL_dmean2D.y;
-    dm.y = (proj[4] * m_w - proj[7] * mul1) * dL_dmean2D.x + (proj[5] * m_w - proj[7] * mul2) * dL_dmean2D.y;
-    dm.z = (proj[8] * m_w - proj[11] * mul1) * dL_dmean2D.x + (proj[9] * m_w - proj[11] * mul2) * dL_dmean2D.y;
-    dL_dmean = f3_add(dL_dmean, dm);
+        const float a = cov2D.m[0][0] += 0.3f;
+        const float b = cov2D.m[0][1];
+        const float c = cov2D.m[1][1] += 0.3f;
+        const float denom = a * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        float dcov[6];
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+            dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
 
-    // depth -> mean (backward.cu:391-403)
-    const float mul3 = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
-    float3 dm2;
-    dm2.x = (view[2] - view[3] * mul3) * dL_ddepth;
-    dm2.y = (view[6] - view[7] * mul3) * dL_ddepth;
-    dm2.z = (view[10] - view[11] * mul3) * dL_ddepth;
-    dL_dmean = f3_add(dL_dmean, dm2);
+            dcov[0] = (Tm.m[0][0] * Tm.m[0][0] * dL_da + Tm.m[0][0] * Tm.m[1][0] * dL_db + Tm.m[1][0] * Tm.m[1][0] * dL_dc);
+            dcov[3] = (Tm.m[0][1] * Tm.m[0][1] * dL_da + Tm.m[0][1] * Tm.m[1][1] * dL_db + Tm.m[1][1] * Tm.m[1][1] * dL_dc);
+            dcov[5] = (Tm.m[0][2] * Tm.m[0][2] * dL_da + Tm.m[0][2] * Tm.m[1][2] * dL_db + Tm.m[1][2] * Tm.m[1][2] * dL_dc);
+            dcov[1] = 2 * Tm.m[0][0] * Tm.m[0][1] * dL_da + (Tm.m[0][0] * Tm.m[1][1] + Tm.m[0][1] * Tm.m[1][0]) * dL_db +
+                      2 * Tm.m[1][0] * Tm.m[1][1] * dL_dc;
+            dcov[2] = 2 * Tm.m[0][0] * Tm.m[0][2] * dL_da + (Tm.m[0][0] * Tm.m[1][2] + Tm.m[0][2] * Tm.m[1][0]) * dL_db +
+                      2 * Tm.m[1][0] * Tm.m[1][2] * dL_dc;
+            dcov[4] = 2 * Tm.m[0][2] * Tm.m[0][1] * dL_da + (Tm.m[0][1] * Tm.m[1][2] + Tm.m[0][2] * Tm.m[1][1]) * dL_db +
+                      2 * Tm.m[1][1] * Tm.m[1][2] * dL_dc;
+        } else {
+    #pragma unroll
+            for (int k = 0; k < 6; ++k) dcov[k] = 0;
+        }
 
-    // ---------------- SH backward (backward.cu:20-139) ----------------
-    if (shs) {
-        const float3 cp = *campos;
-        const float3 dir_orig = f3_sub(m, cp);
-        const float len = sqrtf(f3_dot(dir_orig, dir_orig));
-        const float3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
-        const float3* sh = reinterpret_cast<const float3*>(shs) + (size_t)idx * M;
-        const uint8_t cl = clamped[idx];
-        float3 dL_dRGB = dL_dcolor;
-        dL_dRGB.x *= (cl & 1) ? 0 : 1;
-        dL_dRGB.y *= (cl & 2) ? 0 : 1;
-        dL_dRGB.z *= (cl & 4) ? 0 : 1;
-        float3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
-        const float x = dir.x, y = dir.y, z = dir.z;
-        float* out = dL_dsh + (size_t)idx * 3 * M;
-        int written = 1;
-        store3(out + 0, f3_scale(GVD_SH_C0, dL_dRGB), conf);
-        if (D > 0) {
-            written = 4;
-            store3(out + 3, f3_scale(-GVD_SH_C1 * y, dL_dRGB), conf);
-            store3(out + 6, f3_scale(GVD_SH_C1 * z, dL_dRGB), conf);
-            store3(out + 9, f3_scale(-GVD_SH_C1 * x, dL_dRGB), conf);
-            dRGBdx = f3_scale(-GVD_SH_C1, sh[3]);
-            dRGBdy = f3_scale(-GVD_SH_C1, sh[1]);
-            dRGBdz = f3_scale(GVD_SH_C1, sh[2]);
-            if (D > 1) {
-                written = 9;
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                store3(out + 12, f3_scale(GVD_SH_C2_0 * xy, dL_dRGB), conf);
-                store3(out + 15, f3_scale(GVD_SH_C2_1 * yz, dL_dRGB), conf);
-                store3(out + 18, f3_scale(GVD_SH_C2_2 * (2.f * zz - xx - yy), dL_dRGB), conf);
-                store3(out + 21, f3_scale(GVD_SH_C2_3 * xz, dL_dRGB), conf);
-                store3(out + 24, f3_scale(GVD_SH_C2_4 * (xx - yy), dL_dRGB), conf);
+        const float dL_dT00 = 2 * (Tm.m[0][0] * Vrk.m[0][0] + Tm.m[0][1] * Vrk.m[0][1] + Tm.m[0][2] * Vrk.m[0][2]) * dL_da +
+                              (Tm.m[1][0] * Vrk.m[0][0] + Tm.m[1][1] * Vrk.m[0][1] + Tm.m[1][2] * Vrk.m[0][2]) * dL_db;
+        const float dL_dT01 = 2 * (Tm.m[0][0] * Vrk.m[1][0] + Tm.m[0][1] * Vrk.m[1][1] + Tm.m[0][2] * Vrk.m[1][2]) * dL_da +
+                              (Tm.m[1][0] * Vrk.m[1][0] + Tm.m[1][1] * Vrk.m[1][1] + Tm.m[1][2] * Vrk.m[1][2]) * dL_db;
+        const float dL_dT02 = 2 * (Tm.m[0][0] * Vrk.m[2][0] + Tm.m[0][1] * Vrk.m[2][1] + Tm.m[0][2] * Vrk.m[2][2]) * dL_da +
+                              (Tm.m[1][0] * Vrk.m[2][0] + Tm.m[1][1] * Vrk.m[2][1] + Tm.m[1][2] * Vrk.m[2][2]) * dL_db;
+        const float dL_dT10 = 2 * (Tm.m[1][0] * Vrk.m[0][0] + Tm.m[1][1] * Vrk.m[0][1] + Tm.m[1][2] * Vrk.m[0][2]) * dL_dc +
+                              (Tm.m[0][0] * Vrk.m[0][0] + Tm.m[0][1] * Vrk.m[0][1] + Tm.m[0][2] * Vrk.m[0][2]) * dL_db;
+        const float dL_dT11 = 2 * (Tm.m[1][0] * Vrk.m[1][0] + Tm.m[1][1] * Vrk.m[1][1] + Tm.m[1][2] * Vrk.m[1][2]) * dL_dc +
+                              (Tm.m[0][0] * Vrk.m[1][0] + Tm.m[0][1] * Vrk.m[1][1] + Tm.m[0][2] * Vrk.m[1][2]) * dL_db;
+        const float dL_dT12 = 2 * (Tm.m[1][0] * Vrk.m[2][0] + Tm.m[1][1] * Vrk.m[2][1] + Tm.m[1][2] * Vrk.m[2][2]) * dL_dc +
+                              (Tm.m[0][0] * Vrk.m[2][0] + Tm.m[0][1] * Vrk.m[2][1] + Tm.m[0][2] * Vrk.m[2][2]) * dL_db;
 
-                dRGBdx = f3_add(dRGBdx, f3_add(f3_add(f3_add(f3_scale(GVD_SH_C2_0 * y, sh[4]),
-                                                             f3_scale(GVD_SH_C2_2 * 2.f * -x, sh[6])),
-                                                      f3_scale(GVD_SH_C2_3 * z, sh[7])),
-                                               f3_scale(GVD_SH_C2_4 * 2.f * x, sh[8])));
-                dRGBdy = f3_add(dRGBdy, f3_add(f3_add(f3_add(f3_scale(GVD_SH_C2_0 * x, sh[4]),
-                                                             f3_scale(GVD_SH_C2_1 * z, sh[5])),
-                                                      f3_scale(GVD_SH_C2_2 * 2.f * -y, sh[6])),
-                                               f3_scale(GVD_SH_C2_4 * 2.f * -y, sh[8])));
-                dRGBdz = f3_add(dRGBdz, f3_add(f3_add(f3_scale(GVD_SH_C2_1 * y, sh[5]),
-                                                      f3_scale(GVD_SH_C2_2 * 2.f * 2.f * z, sh[6])),
-                                               f3_scale(GVD_SH_C2_3 * x, sh[7])));
-                if (D > 2) {
-                    written = 16;
-                    store3(out + 27, f3_scale(GVD_SH_C3_0 * y * (3.f * xx - yy), dL_dRGB), conf);
-                    store3(out + 30, f3_scale(GVD_SH_C3_1 * xy * z, dL_dRGB), conf);
-                    store3(out + 33, f3_scale(GVD_SH_C3_2 * y * (4.f * zz - xx - yy), dL_dRGB), conf);
-                    store3(out + 36, f3_scale(GVD_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy), dL_dRGB), conf);
-                    store3(out + 39, f3_scale(GVD_SH_C3_4 * x * (4.f * zz - xx - yy), dL_dRGB), conf);
-                    store3(out + 42, f3_scale(GVD_SH_C3_5 * z * (xx - yy), dL_dRGB), conf);
-                    store3(out + 45, f3_scale(GVD_SH_C3_6 * x * (xx - 3.f * yy), dL_dRGB), conf);
+        const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
+        const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
+        const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
+        const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
 
-                    float3 ax = f3_scale(GVD_SH_C3_0 * 3.f * 2.f * xy, sh[9]);
-                    ax = f3_add(ax, f3_scale(GVD_SH_C3_1 * yz, sh[10]));
-                    ax = f3_add(ax, f3_scale(GVD_SH_C3_2 * -2.f * xy, sh[11]));
-                    ax = f3_add(ax, f3_scale(GVD_SH_C3_3 * -3.f * 2.f * xz, sh[12]));
-                    ax = f3_add(ax, f3_scale(GVD_SH_C3_4 * (-3.f * xx + 4.f * zz - yy), sh[13]));
-                    ax = f3_add(ax, f3_scale(GVD_SH_C3_5 * 2.f * xz, sh[14]));
-                    ax = f3_add(ax, f3_scale(GVD_SH_C3_6 * 3.f * (xx - yy), sh[15]));
-                    dRGBdx = f3_add(dRGBdx, ax);
+        const float tz = 1.f / t.z;
+        const float tz2 = tz * tz;
+        const float tz3 = tz2 * tz;
+        const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+        const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+        const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+                             (2 * h_y * t.y) * tz3 * dL_dJ12;
+        // auxiliary.h:89-97 (transformVec4x3Transpose)
+        float3 dL_dmean = {view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz,
+                           view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
+                           view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz};
 
-                    float3 ay = f3_scale(GVD_SH_C3_0 * 3.f * (xx - yy), sh[9]);
-                    ay = f3_add(ay, f3_scale(GVD_SH_C3_1 * xz, sh[10]));
-                    ay = f3_add(ay, f3_scale(GVD_SH_C3_2 * (-3.f * yy + 4.f * zz - xx), sh[11]));
-                    ay = f3_add(ay, f3_scale(GVD_SH_C3_3 * -3.f * 2.f * yz, sh[12]));
-                    ay = f3_add(ay, f3_scale(GVD_SH_C3_4 * -2.f * xy, sh[13]));
-                    ay = f3_add(ay, f3_scale(GVD_SH_C3_5 * -2.f * yz, sh[14]));
-                    ay = f3_add(ay, f3_scale(GVD_SH_C3_6 * -3.f * 2.f * xy, sh[15]));
-                    dRGBdy = f3_add(dRGBdy, ay);
+        // ---------------- preprocessCUDA backward (backward.cu:346-412) ----------------
+        const float3 m = mean;
+        const float4 m_hom = xform_point_4x4(m, proj);
+        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
+        float3 dm;
+        dm.x = (proj[0] * m_w - proj[3] * mul1) * dL_dmean2D.x + (proj[1] * m_w - proj[3] * mul2) * dL_dmean2D.y;
+        dm.y = (proj[4] * m_w - proj[7] * mul1) * dL_dmean2D.x + (proj[5] * m_w - proj[7] * mul2) * dL_dmean2D.y;
+        dm.z = (proj[8] * m_w - proj[11] * mul1) * dL_dmean2D.x + (proj[9] * m_w - proj[11] * mul2) * dL_dmean2D.y;
+        dL_dmean = f3_add(dL_dmean, dm);
 
-                    float3 az = f3_scale(GVD_SH_C3_1 * xy, sh[10]);
-                    az = f3_add(az, f3_scale(GVD_SH_C3_2 * 4.f * 2.f * yz, sh[11]));
-                    az = f3_add(az, f3_scale(GVD_SH_C3_3 * 3.f * (2.f * zz - xx - yy), sh[12]));
-                    az = f3_add(az, f3_scale(GVD_SH_C3_4 * 4.f * 2.f * xz, sh[13]));
-                    az = f3_add(az, f3_scale(GVD_SH_C3_5 * (xx - yy), sh[14]));
-                    dRGBdz = f3_add(dRGBdz, az);
+        // depth -> mean (backward.cu:391-403)
+        const float mul3 = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
+        float3 dm2;
+        dm2.x = (view[2] - view[3] * mul3) * dL_ddepth;
+        dm2.y = (view[6] - view[7] * mul3) * dL_ddepth;
+        dm2.z = (view[10] - view[11] * mul3) * dL_ddepth;
+        dL_dmean = f3_add(dL_dmean, dm2);
+
+        // ---------------- SH backward (backward.cu:20-139) ----------------
+        if (shs) {
+            const float3 cp = *campos;
+            const float3 dir_orig = f3_sub(m, cp);
+            const float len = sqrtf(f3_dot(dir_orig, dir_orig));
+            const float3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
+            float v[48];
+            load_sh(shs, idx, D, M, v);
+            const uint8_t cl = clamped[idx];
+            float3 dL_dRGB = dL_dcolor;
+            dL_dRGB.x *= (cl & 1) ? 0 : 1;
+            dL_dRGB.y *= (cl & 2) ? 0 : 1;
+            dL_dRGB.z *= (cl & 4) ? 0 : 1;
+            float3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+            const float x = dir.x, y = dir.y, z = dir.z;
+            OUT(0, GVD_SH_C0);
+            if (D > 0) {
+                OUT(1, -GVD_SH_C1 * y);
+                OUT(2, GVD_SH_C1 * z);
+                OUT(3, -GVD_SH_C1 * x);
+                dRGBdx = f3_scale(-GVD_SH_C1, SH(3));
+                dRGBdy = f3_scale(-GVD_SH_C1, SH(1));
+                dRGBdz = f3_scale(GVD_SH_C1, SH(2));
+                if (D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z;
+                    const float xy = x * y, yz = y * z, xz = x * z;
+                    OUT(4, GVD_SH_C2_0 * xy);
+                    OUT(5, GVD_SH_C2_1 * yz);
+                    OUT(6, GVD_SH_C2_2 * (2.f * zz - xx - yy));
+                    OUT(7, GVD_SH_C2_3 * xz);
+                    OUT(8, GVD_SH_C2_4 * (xx - yy));
+
+                    dRGBdx = f3_add(dRGBdx, f3_add(f3_add(f3_add(f3_scale(GVD_SH_C2_0 * y, SH(4)),
+                                                                 f3_scale(GVD_SH_C2_2 * 2.f * -x, SH(6))),
+                                                          f3_scale(GVD_SH_C2_3 * z, SH(7))),
+                                                   f3_scale(GVD_SH_C2_4 * 2.f * x, SH(8))));
+                    dRGBdy = f3_add(dRGBdy, f3_add(f3_add(f3_add(f3_scale(GVD_SH_C2_0 * x, SH(4)),
+                                                                 f3_scale(GVD_SH_C2_1 * z, SH(5))),
+                                                          f3_scale(GVD_SH_C2_2 * 2.f * -y, SH(6))),
+                                                   f3_scale(GVD_SH_C2_4 * 2.f * -y, SH(8))));
+                    dRGBdz = f3_add(dRGBdz, f3_add(f3_add(f3_scale(GVD_SH_C2_1 * y, SH(5)),
+                                                          f3_scale(GVD_SH_C2_2 * 2.f * 2.f * z, SH(6))),
+                                                   f3_scale(GVD_SH_C2_3 * x, SH(7))));
+                    if (D > 2) {
+                        OUT(9, GVD_SH_C3_0 * y * (3.f * xx - yy));
+                        OUT(10, GVD_SH_C3_1 * xy * z);
+                        OUT(11, GVD_SH_C3_2 * y * (4.f * zz - xx - yy));
+                        OUT(12, GVD_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                        OUT(13, GVD_SH_C3_4 * x * (4.f * zz - xx - yy));
+                        OUT(14, GVD_SH_C3_5 * z * (xx - yy));
+                        OUT(15, GVD_SH_C3_6 * x * (xx - 3.f * yy));
+
+                        float3 ax = f3_scale(GVD_SH_C3_0 * 3.f * 2.f * xy, SH(9));
+                        ax = f3_add(ax, f3_scale(GVD_SH_C3_1 * yz, SH(10)));
+                        ax = f3_add(ax, f3_scale(GVD_SH_C3_2 * -2.f * xy, SH(11)));
+                        ax = f3_add(ax, f3_scale(GVD_SH_C3_3 * -3.f * 2.f * xz, SH(12)));
+                        ax = f3_add(ax, f3_scale(GVD_SH_C3_4 * (-3.f * xx + 4.f * zz - yy), SH(13)));
+                        ax = f3_add(ax, f3_scale(GVD_SH_C3_5 * 2.f * xz, SH(14)));
+                        ax = f3_add(ax, f3_scale(GVD_SH_C3_6 * 3.f * (xx - yy), SH(15)));
+                        dRGBdx = f3_add(dRGBdx, ax);
+
+                        float3 ay = f3_scale(GVD_SH_C3_0 * 3.f * (xx - yy), SH(9));
+                        ay = f3_add(ay, f3_scale(GVD_SH_C3_1 * xz, SH(10)));
+                        ay = f3_add(ay, f3_scale(GVD_SH_C3_2 * (-3.f * yy + 4.f * zz - xx), SH(11)));
+                        ay = f3_add(ay, f3_scale(GVD_SH_C3_3 * -3.f * 2.f * yz, SH(12)));
+                        ay = f3_add(ay, f3_scale(GVD_SH_C3_4 * -2.f * xy, SH(13)));
+                        ay = f3_add(ay, f3_scale(GVD_SH_C3_5 * -2.f * yz, SH(14)));
+                        ay = f3_add(ay, f3_scale(GVD_SH_C3_6 * -3.f * 2.f * xy, SH(15)));
+                        dRGBdy = f3_add(dRGBdy, ay);
+
+                        float3 az = f3_scale(GVD_SH_C3_1 * xy, SH(10));
+                        az = f3_add(az, f3_scale(GVD_SH_C3_2 * 4.f * 2.f * yz, SH(11)));
+                        az = f3_add(az, f3_scale(GVD_SH_C3_3 * 3.f * (2.f * zz - xx - yy), SH(12)));
+                        az = f3_add(az, f3_scale(GVD_SH_C3_4 * 4.f * 2.f * xz, SH(13)));
+                        az = f3_add(az, f3_scale(GVD_SH_C3_5 * (xx - yy), SH(14)));
+                        dRGBdz = f3_add(dRGBdz, az);
+                    }
                 }
             }
-        }
-        // coefficients above the active degree get zero gradient (torch::zeros in the reference)
-        for (int k = written * 3; k < 3 * M; ++k) out[k] = 0.f;
 
-        const float3 dL_ddir = {f3_dot(dRGBdx, dL_dRGB), f3_dot(dRGBdy, dL_dRGB), f3_dot(dRGBdz, dL_dRGB)};
-        dL_dmean = f3_add(dL_dmean, dnormvdv3(dir_orig, dL_ddir));
+            const float3 dL_ddir = {f3_dot(dRGBdx, dL_dRGB), f3_dot(dRGBdy, dL_dRGB), f3_dot(dRGBdz, dL_dRGB)};
+            dL_dmean = f3_add(dL_dmean, dnormvdv3(dir_orig, dL_ddir));
+        }
+
+        // ---------------- cov3D backward (backward.cu:278-341) ----------------
+        if (scales) {
+            const float4 q = rotations[idx];
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                           2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                           2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+            const float3 sc = scales[idx];
+            const float3 s = {scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z};
+            M3 Mm;
+    #pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                Mm.m[cc][0] = s.x * R.m[cc][0];
+                Mm.m[cc][1] = s.y * R.m[cc][1];
+                Mm.m[cc][2] = s.z * R.m[cc][2];
+            }
+            M3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
+                                   0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
+            // dL_dM = 2 * M * dL_dSigma   (scalar*matrix first, then product, as written in the reference)
+            M3 M2;
+    #pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+    #pragma unroll
+                for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = Mm.m[cc][rr] * 2.0f;
+            M3 dL_dM = m3_mul(M2, dL_dSigma);
+            M3 Rt = m3_transpose(R);
+            M3 dL_dMt = m3_transpose(dL_dM);
+
+            float3 dscale;
+            dscale.x = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
+            dscale.y = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
+            dscale.z = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
+            o_sc = {dscale.x * conf, dscale.y * conf, dscale.z * conf};
+
+    #pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                dL_dMt.m[0][rr] *= s.x;
+                dL_dMt.m[1][rr] *= s.y;
+                dL_dMt.m[2][rr] *= s.z;
+            }
+            float4 dq;
+            dq.x = 2 * z * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * y * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) +
+                   2 * x * (dL_dMt.m[1][2] - dL_dMt.m[2][1]);
+            dq.y = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
+                   2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
+            dq.z = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) +
+                   2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
+            dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
+                   2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
+            o_rot = make_float4(dq.x * conf, dq.y * conf, dq.z * conf, dq.w * conf);
+        }
+
+
+        o_m2 = dL_dmean2D;  // not confidence-scaled (diff_gaussian_rasterization/__init__.py:149)
+        o_m3 = {dL_dmean.x * conf, dL_dmean.y * conf, dL_dmean.z * conf};
+        o_op = dL_dopac * conf;
+        o_col = {dL_dcolor.x * conf, dL_dcolor.y * conf, dL_dcolor.z * conf};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o_cov[k] = dcov[k] * conf;
     }
 
-    // ---------------- cov3D backward (backward.cu:278-341) ----------------
-    if (scales) {
-        const float4 q = rotations[idx];
-        const float r = q.x, x = q.y, y = q.z, z = q.w;
-        M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                       2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                       2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-        const float3 sc = scales[idx];
-        const float3 s = {scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z};
-        M3 Mm;
+    // ---------------- stores: every output element written exactly once ----------------
+    store_p3_coalesced(dL_dmeans2D, stage, block_first, P, o_m2.x, o_m2.y, 0.f);
+    store_p3_coalesced(dL_dmeans3D, stage, block_first, P, o_m3.x, o_m3.y, o_m3.z);
+    if (dL_dscales) store_p3_coalesced(dL_dscales, stage, block_first, P, o_sc.x, o_sc.y, o_sc.z);
+    if (dL_dcolors) store_p3_coalesced(dL_dcolors, stage, block_first, P, o_col.x, o_col.y, o_col.z);
+    if (!valid) return;
+    dL_dopacity[idx] = o_op;
+    if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
+    if (dL_dcov3D) {
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-            Mm.m[cc][0] = s.x * R.m[cc][0];
-            Mm.m[cc][1] = s.y * R.m[cc][1];
-            Mm.m[cc][2] = s.z * R.m[cc][2];
-        }
-        M3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
-                               0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
-        // dL_dM = 2 * M * dL_dSigma   (scalar*matrix first, then product, as written in the reference)
-        M3 M2;
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-#pragma unroll
-            for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = Mm.m[cc][rr] * 2.0f;
-        M3 dL_dM = m3_mul(M2, dL_dSigma);
-        M3 Rt = m3_transpose(R);
-        M3 dL_dMt = m3_transpose(dL_dM);
-
-        float3 dscale;
-        dscale.x = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
-        dscale.y = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
-        dscale.z = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
-        store3(dL_dscales + 3 * (size_t)idx, dscale, conf);
-
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
-            dL_dMt.m[0][rr] *= s.x;
-            dL_dMt.m[1][rr] *= s.y;
-            dL_dMt.m[2][rr] *= s.z;
-        }
-        float4 dq;
-        dq.x = 2 * z * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * y * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) +
-               2 * x * (dL_dMt.m[1][2] - dL_dMt.m[2][1]);
-        dq.y = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
-               2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
-        dq.z = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) +
-               2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
-        dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
-               2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
-        float4* o = reinterpret_cast<float4*>(dL_drots) + idx;
-        *o = make_float4(dq.x * conf, dq.y * conf, dq.z * conf, dq.w * conf);
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = o_cov[k];
     }
-
-    // ---------------- epilogue ----------------
-    store3(dL_dmeans2D + 3 * (size_t)idx, {dL_dmean2D.x, dL_dmean2D.y, 0.f}, 1.f);  // not confidence-scaled
-    store3(dL_dmeans3D + 3 * (size_t)idx, dL_dmean, conf);
-    dL_dopacity[idx] = dL_dopac * conf;
-    if (dL_dcolors) store3(dL_dcolors + 3 * (size_t)idx, dL_dcolor, conf);
-    if (dL_dcov3D)
-        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = dcov[k] * conf;
+    if (dL_dsh) {
+        float* row = dL_dsh + (size_t)idx * 3 * M;
+        if (M == 16 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+            float4* r4 = reinterpret_cast<float4*>(row);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) r4[k] = make_float4(o_sh[4 * k], o_sh[4 * k + 1], o_sh[4 * k + 2], o_sh[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 48; ++k)
+                if (k < 3 * M) row[k] = o_sh[k];
+        }
+    }
 }
+#undef SH
+#undef OUT
 
 }  // namespace
 
-void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                                float* acc, dim3 grid, cudaStream_t s) {
-    render_backward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.packed, a.width, a.height, grid.x,
+void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                                const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
+    render_backward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height, grid.x,
                                                                   a.background, a.alphas, im.n_contrib, a.dL_dpix,
                                                                   a.dL_ddepth_pix, a.dL_dalpha_pix, acc);
 }

@@ -1,11 +1,12 @@
 // raster_common.cuh -- shared definitions for the B200-native Gaussian rasterizer.
 //
 // Data layout in HBM (all caller-owned scratch, see include/gvd_raster.h):
-//   geom   : SplatRec[P]  (48 B per Gaussian, written by preprocess, gathered by pack)
-//            uint8 clamped[P], uint32 tiles_touched[P], uint32 point_offsets[P], scan temp
-//   binning: uint32 point_list[R], uint64 keys[R], unsorted copies, sort temp,
-//            SplatRec packed[R] -- per (Gaussian,tile) instance, in sorted order, so one tile's
-//            list is ONE contiguous byte range that the render kernels stage with TMA bulk copies.
+//   geom   : SplatRec[P] (64 B per Gaussian, written by preprocess, gathered on demand by the render
+//            kernels -- the visible set is a few MB and lives in the 126 MB L2), clamped[P],
+//            tiles_touched[P], depth keys / order[P] (depth sort), per-chunk tile histogram matrix
+//            [ceil(P/256)][T] (binning), tile totals.
+//   binning: uint32 point_list[R] -- Gaussian ids, tile-major, depth-sorted inside a tile (identical to
+//            the reference's sorted value array); optional uint64 keys[R] for parity checks.
 //   img    : uint2 ranges[T], uint32 n_contrib[H*W]
 #pragma once
 #include <cuda_runtime.h>
@@ -14,36 +15,47 @@
 #define GVD_TILE_X 16
 #define GVD_TILE_Y 16
 #define GVD_BLOCK 256      // threads per render CTA = pixels per tile
-#define GVD_BATCH 256      // tile-list entries staged per TMA bulk copy
+#define GVD_BATCH 256      // tile-list entries staged per round
 #define GVD_ACC_STRIDE 12  // floats per Gaussian in the backward accumulator
+#define GVD_BIN_CHUNK 256  // Gaussians (in depth order) per binning chunk
+#define GVD_MAX_TILES 49152  // per-CTA shared-memory tile counters (4 B each) must fit in 227 KB
 
-// 48-byte record. Per-Gaussian (geom) and per-instance (packed) flavours share a.. and c.xy:
+// 64-byte per-Gaussian record:
 //   a = {mean2D.x, mean2D.y, conic.x, conic.y}
 //   b = {conic.z, opacity, rgb.r, rgb.g}
-//   c = {rgb.b, depth, w0, w1}
-//       geom  : w0 = rect_min.x | rect_min.y<<16 ; w1 = rect_max.x | rect_max.y<<16 (tile units)
-//       packed: w0 = Gaussian id                 ; w1 = 8-bit sub-tile mask (bit w = warp w's 8x4 pixels)
+//   c = {rgb.b, depth, hx, hy}   hx,hy = half extents (pixels, with slack) of the axis-aligned bound of the
+//                                 region where alpha can reach 1/255; -1e30 = never, +1e30 = unbounded
+//   d = {rect_min.x | rect_min.y<<16, rect_max.x | rect_max.y<<16, 0, 0}  (tile units, as uint bits)
+// The render kernels read a,b,c (48 B); the binning kernels read d.
 struct __align__(16) SplatRec {
-    float4 a, b, c;
+    float4 a, b, c, d;
 };
 
 struct RasterGeomPtrs {
     SplatRec* splat;
     uint8_t* clamped;
-    uint32_t* tiles_touched;
-    uint32_t* point_offsets;
-    char* scan_temp;
-    size_t scan_temp_bytes;
-};
-
-struct RasterBinPtrs {
-    uint32_t* point_list;
-    uint32_t* point_list_unsorted;
-    uint64_t* keys;
-    uint64_t* keys_unsorted;
+    uint32_t* tiles_touched;   // per Gaussian id
+    uint32_t* depth_key;       // per Gaussian id: depth bits, 0xFFFFFFFF when culled
+    uint32_t* gidx;            // iota (values fed to the depth sort)
+    uint32_t* depth_sorted;    // sorted depth keys (sort output, otherwise unused)
+    uint32_t* order;           // Gaussian ids in (depth, id) order; culled ones last
     char* sort_temp;
     size_t sort_temp_bytes;
-    SplatRec* packed;
+    uint32_t* chunk_flags;     // [chunks] 1 = chunk holds at least one visible Gaussian
+    uint32_t* hist;            // [chunks][T] per-chunk tile counts, turned into exclusive prefixes in place
+    uint32_t* tile_total;      // [T]
+    uint32_t* num_rendered;    // [1] device copy of R
+    size_t chunks;
+};
+
+// Binning = depth sort of the Gaussians (P 32-bit keys) followed by a rect-aware STABLE counting sort on
+// the tile id: chunks of 256 depth-consecutive Gaussians histogram their tile rects, a column prefix over
+// chunks gives every chunk its starting rank in every tile, and each chunk then writes its Gaussians'
+// ids tile by tile in depth order. The result equals the reference's single stable radix sort on
+// (tile<<32 | depth bits): same tile -> by depth -> ties by Gaussian id (rasterizer_impl.cu:70-111,304-309).
+struct RasterBinPtrs {
+    uint32_t* point_list;
+    uint64_t* keys;            // optional (export_keys): (tile<<32 | depth bits) per sorted instance
 };
 
 struct RasterImgPtrs {
@@ -57,13 +69,15 @@ struct GvdRasterBackwardArgs;
 
 void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, float focal_x, float focal_y,
                            dim3 grid, cudaStream_t s);
-void gvd_launch_emit_keys(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, dim3 grid, cudaStream_t s);
-void gvd_launch_pack(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im, dim3 grid,
-                     cudaStream_t s);
-void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                               dim3 grid, cudaStream_t s);
-void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                                float* acc, dim3 grid, cudaStream_t s);
+cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, cudaStream_t s);
+cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                                dim3 grid, cudaStream_t s);
+void gvd_launch_export_keys(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                            dim3 grid, cudaStream_t s);
+void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                               const RasterImgPtrs& im, dim3 grid, cudaStream_t s);
+void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                                const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s);
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
                                   float focal_x, float focal_y, cudaStream_t s);
 void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
@@ -180,6 +194,27 @@ __device__ __forceinline__ float f3_dot(float3 a, float3 b) {
     return tx + ty + tz;
 }
 
+// Loads one Gaussian's SH coefficients into registers: 12 x LDG.128 when the row is 16-byte aligned
+// (M == 16: 192 B per Gaussian), scalar otherwise. Only the (deg+1)^2 active coefficients are read.
+__device__ __forceinline__ void load_sh(const float* __restrict__ shs, int idx, int deg, int max_coeffs, float (&v)[48]) {
+    const float* row = shs + (size_t)idx * max_coeffs * 3;
+    const int nfl = 3 * (deg + 1) * (deg + 1);
+    if (max_coeffs == 16 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            if (4 * k < nfl) {
+                const float4 t = __ldg(r4 + k);
+                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 48; ++k)
+            if (k < nfl) v[k] = row[k];
+    }
+}
+
 // ---- mbarrier / TMA bulk-copy wrappers (sm_90+; SASS: UBLKCP + SYNCS) ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -213,6 +248,31 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// ---- tile-list staging shared by the forward and backward render kernels --------------------------
+// Ids of one batch of a tile's list are fetched with ONE TMA bulk copy (the list is contiguous); the copy
+// starts at the 16-byte boundary below the first id, `lead` is the number of leading pad elements.
+struct IdSlot {
+    uint32_t v[GVD_BATCH + 8];
+};
+
+__device__ __forceinline__ uint32_t issue_id_copy(IdSlot* slot, uint64_t* bar, const uint32_t* first, int cnt) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(first);
+    const uint32_t lead = (uint32_t)((addr & 15) >> 2);
+    const uint32_t bytes = (((lead + (uint32_t)cnt) * 4u) + 15u) & ~15u;
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_bulk_g2s(slot->v, reinterpret_cast<const void*>(addr & ~(uintptr_t)15), bytes, bar);
+    return lead;
+}
+__device__ __forceinline__ uint32_t id_lead(const uint32_t* first) {
+    return (uint32_t)((reinterpret_cast<uintptr_t>(first) & 15) >> 2);
+}
+
+// Can this Gaussian reach alpha >= 1/255 on some pixel of the 8x4 block whose top-left pixel is (sx, sy)?
+// Conservative; written with negated comparisons so that NaNs count as "yes".
+__device__ __forceinline__ bool subtile_hit(float x, float y, float hx, float hy, float sx, float sy) {
+    return !(x - hx > sx + 7.0f) && !(x + hx < sx) && !(y - hy > sy + 3.0f) && !(y + hy < sy);
 }
 
 #endif  // __CUDACC__

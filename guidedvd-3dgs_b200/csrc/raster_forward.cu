@@ -2,15 +2,18 @@
 //
 //   preprocess_kernel     per Gaussian: cull, project, EWA cov2D, conic, radius, tile rect, SH->RGB
 //                         (follows DGR/cuda_rasterizer/forward.cu:155-256 arithmetic exactly so that
-//                         radii / tile rects / depth bits are bit-identical to the reference)
-//   emit_keys_kernel      per Gaussian: (tile<<32 | depth bits, id) per covered tile
-//                         (rasterizer_impl.cu:70-111; large rects are spread over the warp)
-//   pack_kernel           per sorted instance: tile ranges (rasterizer_impl.cu:116-138) + gather the
-//                         48-B splat record into sorted order + per-instance 8x4 sub-tile mask
-//   render_forward_kernel per tile: TMA bulk (cp.async.bulk + mbarrier) double-buffered staging of the
-//                         contiguous packed list; each warp owns an 8x4 pixel sub-tile and visits only
-//                         the instances whose mask bit is set (forward.cu:261-381 semantics preserved:
-//                         skipped instances are exactly those every pixel of the warp would `continue` on).
+//                         radii / tile rects / depth bits are bit-identical to the reference), plus the
+//                         alpha>=1/255 extent used for sub-tile culling
+//   bin_count / bin_prefix / bin_ranges / bin_fill
+//                         rect-aware stable counting sort of the (Gaussian, tile) instances on the tile id,
+//                         run over the depth-sorted Gaussians; produces point_list + ranges exactly as the
+//                         reference's duplicateWithKeys + 64-bit radix sort + identifyTileRanges
+//                         (rasterizer_impl.cu:70-138,304-319) without materialising keys
+//   render_forward_kernel per tile: ids staged by TMA bulk copy (cp.async.bulk + mbarrier), records gathered
+//                         from the L2-resident per-Gaussian array one batch ahead; each warp owns an 8x4
+//                         pixel sub-tile and visits only the instances that can touch it
+//                         (forward.cu:261-381 semantics preserved: skipped instances are exactly those every
+//                         pixel of the warp would `continue` on).
 #include <cstdio>
 #include "raster_common.cuh"
 #include "../../include/gvd_raster.h"
@@ -25,32 +28,35 @@ __device__ __forceinline__ float3 sh_to_rgb(int idx, int deg, int max_coeffs, co
     float len = sqrtf(f3_dot(dir, dir));
     dir = {dir.x / len, dir.y / len, dir.z / len};
 
-    const float3* sh = reinterpret_cast<const float3*>(shs) + (size_t)idx * max_coeffs;
-    float3 result = f3_scale(GVD_SH_C0, sh[0]);
+    float v[48];
+    load_sh(shs, idx, deg, max_coeffs, v);
+#define SH(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
+    float3 result = f3_scale(GVD_SH_C0, SH(0));
     if (deg > 0) {
         float x = dir.x, y = dir.y, z = dir.z;
-        result = f3_sub(f3_add(f3_sub(result, f3_scale(GVD_SH_C1 * y, sh[1])), f3_scale(GVD_SH_C1 * z, sh[2])),
-                        f3_scale(GVD_SH_C1 * x, sh[3]));
+        result = f3_sub(f3_add(f3_sub(result, f3_scale(GVD_SH_C1 * y, SH(1))), f3_scale(GVD_SH_C1 * z, SH(2))),
+                        f3_scale(GVD_SH_C1 * x, SH(3)));
         if (deg > 1) {
             float xx = x * x, yy = y * y, zz = z * z;
             float xy = x * y, yz = y * z, xz = x * z;
             result = f3_add(
-                f3_add(f3_add(f3_add(f3_add(result, f3_scale(GVD_SH_C2_0 * xy, sh[4])), f3_scale(GVD_SH_C2_1 * yz, sh[5])),
-                              f3_scale(GVD_SH_C2_2 * (2.0f * zz - xx - yy), sh[6])),
-                       f3_scale(GVD_SH_C2_3 * xz, sh[7])),
-                f3_scale(GVD_SH_C2_4 * (xx - yy), sh[8]));
+                f3_add(f3_add(f3_add(f3_add(result, f3_scale(GVD_SH_C2_0 * xy, SH(4))), f3_scale(GVD_SH_C2_1 * yz, SH(5))),
+                              f3_scale(GVD_SH_C2_2 * (2.0f * zz - xx - yy), SH(6))),
+                       f3_scale(GVD_SH_C2_3 * xz, SH(7))),
+                f3_scale(GVD_SH_C2_4 * (xx - yy), SH(8)));
             if (deg > 2) {
                 result = f3_add(
-                    f3_add(f3_add(f3_add(f3_add(f3_add(f3_add(result, f3_scale(GVD_SH_C3_0 * y * (3.0f * xx - yy), sh[9])),
-                                                       f3_scale(GVD_SH_C3_1 * xy * z, sh[10])),
-                                                f3_scale(GVD_SH_C3_2 * y * (4.0f * zz - xx - yy), sh[11])),
-                                         f3_scale(GVD_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), sh[12])),
-                                  f3_scale(GVD_SH_C3_4 * x * (4.0f * zz - xx - yy), sh[13])),
-                           f3_scale(GVD_SH_C3_5 * z * (xx - yy), sh[14])),
-                    f3_scale(GVD_SH_C3_6 * x * (xx - 3.0f * yy), sh[15]));
+                    f3_add(f3_add(f3_add(f3_add(f3_add(f3_add(result, f3_scale(GVD_SH_C3_0 * y * (3.0f * xx - yy), SH(9))),
+                                                       f3_scale(GVD_SH_C3_1 * xy * z, SH(10))),
+                                                f3_scale(GVD_SH_C3_2 * y * (4.0f * zz - xx - yy), SH(11))),
+                                         f3_scale(GVD_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), SH(12))),
+                                  f3_scale(GVD_SH_C3_4 * x * (4.0f * zz - xx - yy), SH(13))),
+                           f3_scale(GVD_SH_C3_5 * z * (xx - yy), SH(14))),
+                    f3_scale(GVD_SH_C3_6 * x * (xx - 3.0f * yy), SH(15)));
             }
         }
     }
+#undef SH
     result.x += 0.5f;
     result.y += 0.5f;
     result.z += 0.5f;
@@ -90,6 +96,26 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
                 min(grid.y, max((int)0, (int)((p.y + max_radius + GVD_TILE_Y - 1) / GVD_TILE_Y)))};
 }
 
+// Half extents of the axis-aligned bound of { d : opac * exp(power(d)) >= 1/255 } (power = -q(d)/2 with the
+// conic as quadratic form), inflated by a slack that dwarfs any rounding in the per-pixel evaluation.
+// -1e30: can never contribute (opac < 1/255: alpha <= opac).  +1e30: no usable bound.
+__device__ __forceinline__ void alpha_extent(const float3 conic, float opac, float& hx, float& hy) {
+    hx = hy = 1e30f;
+    if (opac * 255.0f < 0.999f) {
+        hx = hy = -1e30f;
+        return;
+    }
+    const float A = conic.x, B = conic.y, C = conic.z;
+    const float t = 2.0f * logf(opac * 255.0f) * 1.0005f + 1e-3f;  // q(d) <= t  <=>  power >= -t/2
+    const float det = A * C - B * B;
+    if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f) || !(t >= 0.0f)) return;
+    const float ex = sqrtf(t * C / det) * 1.0005f + 0.02f;
+    const float ey = sqrtf(t * A / det) * 1.0005f + 0.02f;
+    if (!(ex < 1e9f) || !(ey < 1e9f)) return;
+    hx = ex;
+    hy = ey;
+}
+
 __global__ void __launch_bounds__(256) preprocess_kernel(
     int P, int D, int M, const float* __restrict__ orig_points, const float3* __restrict__ scales,
     const float scale_modifier, const float4* __restrict__ rotations, const float* __restrict__ opacities,
@@ -97,12 +123,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
     const float* __restrict__ projmatrix, const float3* __restrict__ cam_pos, const int W, int H,
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
-    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched, int prefiltered) {
+    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched,
+    uint32_t* __restrict__ depth_key, uint32_t* __restrict__ gidx, int prefiltered) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
 
     radii[idx] = 0;
     tiles_touched[idx] = 0;
+    depth_key[idx] = 0xFFFFFFFFu;  // culled Gaussians sort behind every visible one
+    gidx[idx] = idx;
 
     // near cull (auxiliary.h:139-164): only p_view.z <= 0.2 rejects.
     const float3 p_orig = {orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]};
@@ -155,163 +184,311 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
 
     radii[idx] = (int)my_radius;
     tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+    depth_key[idx] = __float_as_uint(p_view.z);
 
     SplatRec rec;
     rec.a = make_float4(point_image.x, point_image.y, conic.x, conic.y);
     rec.b = make_float4(conic.z, opacities[idx], rgb.x, rgb.y);
-    rec.c = make_float4(rgb.z, p_view.z, __uint_as_float(rect_min.x | (rect_min.y << 16)),
-                        __uint_as_float(rect_max.x | (rect_max.y << 16)));
+    float hx, hy;
+    alpha_extent(conic, opacities[idx], hx, hy);
+    rec.c = make_float4(rgb.z, p_view.z, hx, hy);
+    rec.d = make_float4(__uint_as_float(rect_min.x | (rect_min.y << 16)), __uint_as_float(rect_max.x | (rect_max.y << 16)),
+                        0.f, 0.f);
     splat[idx] = rec;
 }
 
 // ------------------------------------------------------------------------------------------
-// Key emission. One thread per Gaussian for small rects; rects with more than EMIT_SERIAL_MAX
-// tiles are handed to the whole warp (the reference's serial per-thread loop leaves 31 lanes
-// idle behind one screen-filling Gaussian).
-#define EMIT_SERIAL_MAX 16
-__global__ void __launch_bounds__(256) emit_keys_kernel(int P, const SplatRec* __restrict__ splat,
-                                                        const uint32_t* __restrict__ tiles_touched,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        uint64_t* __restrict__ keys_unsorted,
-                                                        uint32_t* __restrict__ values_unsorted, dim3 grid) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t n = 0, off = 0, w0 = 0, w1 = 0, depth_bits = 0;
-    if (idx < P) {
-        n = tiles_touched[idx];
-        if (n > 0) {
-            off = (idx == 0) ? 0 : offsets[idx - 1];
-            const float4 c = splat[idx].c;
-            depth_bits = __float_as_uint(c.y);
-            w0 = __float_as_uint(c.z);
-            w1 = __float_as_uint(c.w);
-        }
-    }
-    const uint32_t x0 = w0 & 0xffff, y0 = w0 >> 16, x1 = w1 & 0xffff, y1 = w1 >> 16;
-    if (n > 0 && n <= EMIT_SERIAL_MAX) {
-        for (uint32_t y = y0; y < y1; y++)
-            for (uint32_t x = x0; x < x1; x++) {
-                uint64_t key = y * grid.x + x;
-                key <<= 32;
-                key |= depth_bits;
-                keys_unsorted[off] = key;
-                values_unsorted[off] = idx;
-                off++;
-            }
-    }
-    unsigned big = __ballot_sync(0xffffffffu, n > EMIT_SERIAL_MAX);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t bn = __shfl_sync(0xffffffffu, n, src);
-        const uint32_t boff = __shfl_sync(0xffffffffu, off, src);
-        const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src);
-        const uint32_t by0 = __shfl_sync(0xffffffffu, y0, src);
-        const uint32_t bx1 = __shfl_sync(0xffffffffu, x1, src);
-        const uint32_t bdepth = __shfl_sync(0xffffffffu, depth_bits, src);
-        const uint32_t bidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
-        const uint32_t bw = bx1 - bx0;
-        for (uint32_t k = lane; k < bn; k += 32) {
-            const uint32_t y = by0 + k / bw, x = bx0 + k % bw;  // y-major then x, as the reference
-            uint64_t key = y * grid.x + x;
-            key <<= 32;
-            key |= bdepth;
-            keys_unsorted[boff + k] = key;
-            values_unsorted[boff + k] = bidx;
-        }
-    }
+// ---- binning: rect-aware stable counting sort on the tile id -------------------------------------
+// Instance order required (and produced by the reference's stable sort on tile<<32|depth): tile-major;
+// inside a tile by depth, ties by Gaussian id. `order` already lists the Gaussians by (depth, id).
+
+__device__ __forceinline__ void unpack_rect(const float4 d, uint32_t& x0, uint32_t& y0, uint32_t& x1, uint32_t& y1) {
+    const uint32_t w0 = __float_as_uint(d.x), w1 = __float_as_uint(d.y);
+    x0 = w0 & 0xffff; y0 = w0 >> 16; x1 = w1 & 0xffff; y1 = w1 >> 16;
 }
 
-// ------------------------------------------------------------------------------------------
-// Sub-tile mask: bit w set iff the instance can reach alpha >= 1/255 on some pixel of warp w's
-// 8x4 block (sx = w&1, sy = w>>1). Conservative (axis-aligned bound of the level-set ellipse
-// plus slack), so skipping a cleared bit never changes a pixel: on those pixels the reference
-// takes `continue` at forward.cu:348.
-__device__ __forceinline__ uint32_t subtile_mask(const float4 a, const float4 b, uint32_t tile_x, uint32_t tile_y) {
-    const float opac = b.y;
-    const float A = a.z, B = a.w, C = b.x;
-    // alpha = min(.99, opac*exp(power)) with power <= 0, so opac < 1/255 can never pass.
-    if (opac * 255.0f < 0.999f) return 0u;
-    const float t = 2.0f * logf(opac * 255.0f) * 1.0005f + 1e-3f;  // q(d) <= t  <=>  power >= -t/2
-    const float det = A * C - B * B;
-    if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f)) return 0xffu;
-    const float hx = sqrtf(t * C / det) * 1.0005f + 0.02f;
-    const float hy = sqrtf(t * A / det) * 1.0005f + 0.02f;
-    if (!(hx < 1e9f) || !(hy < 1e9f)) return 0xffu;
-    const float ox = (float)(tile_x * GVD_TILE_X), oy = (float)(tile_y * GVD_TILE_Y);
-    const float xmin = a.x - hx - ox, xmax = a.x + hx - ox;  // tile-local
-    const float ymin = a.y - hy - oy, ymax = a.y + hy - oy;
-    uint32_t colmask = 0, m = 0;
-    if (xmin <= 7.0f && xmax >= 0.0f) colmask |= 1u;
-    if (xmin <= 15.0f && xmax >= 8.0f) colmask |= 2u;
+// Pass 1: chunk c = Gaussians order[256c .. 256c+255]. hist[c][t] = how many of them cover tile t.
+// A rect adds +1/-1 at its four corners of a (gy+1) x (gx+1) difference grid; a 2-D prefix sum then yields
+// the per-tile counts. Cost per chunk is O(256 + T) whatever the rect sizes (no per-instance atomics).
+__global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(int P, uint32_t gx, uint32_t gy,
+                                                                 const SplatRec* __restrict__ splat,
+                                                                 const uint32_t* __restrict__ order,
+                                                                 const uint32_t* __restrict__ tiles_touched,
+                                                                 uint32_t* __restrict__ chunk_flags,
+                                                                 uint32_t* __restrict__ hist) {
+    extern __shared__ int diff[];  // (gy+1) rows of stride ld
+    const int ld = (int)(gx + 1) | 1;  // odd stride: column walks are bank-conflict free
+    const int rows = (int)gy + 1, cols = (int)gx + 1;
+    const int i = blockIdx.x * GVD_BIN_CHUNK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t n = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (i < P) {
+        const uint32_t id = order[i];
+        n = tiles_touched[id];
+        if (n > 0) unpack_rect(splat[id].d, x0, y0, x1, y1);
+    }
+    const int any = __syncthreads_or(n > 0);
+    if (threadIdx.x == 0) chunk_flags[blockIdx.x] = any ? 1u : 0u;
+    if (!any) return;  // culled Gaussians sort last: this and all later chunks are empty
+    for (int t = threadIdx.x; t < rows * ld; t += GVD_BIN_CHUNK) diff[t] = 0;
+    __syncthreads();
+    if (n > 0) {
+        atomicAdd(&diff[y0 * ld + x0], 1);
+        atomicAdd(&diff[y0 * ld + x1], -1);
+        atomicAdd(&diff[y1 * ld + x0], -1);
+        atomicAdd(&diff[y1 * ld + x1], 1);
+    }
+    __syncthreads();
+    // prefix along x: one warp per row
+    for (int y = warp; y < rows; y += GVD_BIN_CHUNK / 32) {
+        int carry = 0;
+        for (int xb = 0; xb < cols; xb += 32) {
+            const int x = xb + lane;
+            int v = (x < cols) ? diff[y * ld + x] : 0;
 #pragma unroll
-    for (int sy = 0; sy < 4; ++sy)
-        if (ymin <= (float)(sy * 4 + 3) && ymax >= (float)(sy * 4)) m |= colmask << (2 * sy);
-    return m;
-}
-
-__global__ void __launch_bounds__(256) pack_kernel(int R, const uint64_t* __restrict__ keys,
-                                                   const uint32_t* __restrict__ point_list,
-                                                   const SplatRec* __restrict__ splat, SplatRec* __restrict__ packed,
-                                                   uint2* __restrict__ ranges, uint32_t tiles_x) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R) return;
-    const uint64_t key = keys[idx];
-    const uint32_t currtile = key >> 32;
-    if (idx == 0)
-        ranges[currtile].x = 0;
-    else {
-        const uint32_t prevtile = keys[idx - 1] >> 32;
-        if (currtile != prevtile) {
-            ranges[prevtile].y = idx;
-            ranges[currtile].x = idx;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            v += carry;
+            if (x < cols) diff[y * ld + x] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
         }
     }
-    if (idx == R - 1) ranges[currtile].y = R;
+    __syncthreads();
+    // prefix along y: one thread per column
+    for (int x = threadIdx.x; x < cols; x += GVD_BIN_CHUNK) {
+        int run = 0;
+        for (int y = 0; y < rows; ++y) {
+            run += diff[y * ld + x];
+            diff[y * ld + x] = run;
+        }
+    }
+    __syncthreads();
+    uint32_t* row = hist + (size_t)blockIdx.x * (gx * gy);
+    for (uint32_t t = threadIdx.x; t < gx * gy; t += GVD_BIN_CHUNK) row[t] = (uint32_t)diff[(t / gx) * ld + (t % gx)];
+}
 
-    const uint32_t id = point_list[idx];
-    const float4* src = reinterpret_cast<const float4*>(splat + id);
-    float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-    c.z = __uint_as_float(id);
-    c.w = __uint_as_float(subtile_mask(a, b, currtile % tiles_x, currtile / tiles_x));
-    float4* dst = reinterpret_cast<float4*>(packed + idx);
-    dst[0] = a;
-    dst[1] = b;
-    dst[2] = c;
+// Pass 2: per tile, exclusive prefix over the (valid) chunks, in place, and the tile's total.
+// CTA = 32 tiles x 32 chunk segments: every thread sums its segment, the segment sums are scanned through
+// shared memory, then every thread rewrites its segment as running prefixes.
+__global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int chunks, const uint32_t* __restrict__ chunk_flags,
+                                                          uint32_t* hist, uint32_t* __restrict__ tile_total) {
+    __shared__ uint32_t seg_sum[32][33];
+    __shared__ int s_valid;
+    const int tx = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    {   // valid chunks form a prefix of the chunk array: count them
+        int c = 0;
+        for (int k = threadIdx.x; k < chunks; k += 1024) c += chunk_flags[k] ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (tx == 0 && c) atomicAdd(&s_valid, c);
+    }
+    __syncthreads();
+    const int nv = s_valid;
+    const int per = (nv + 31) / 32;
+    const int c0 = seg * per, c1 = min(nv, c0 + per);
+    const int t = blockIdx.x * 32 + tx;
+    uint32_t sum = 0;
+    if (t < T)
+        for (int c = c0; c < c1; ++c) sum += hist[(size_t)c * T + t];
+    seg_sum[seg][tx] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int k = 0; k < seg; ++k) run += seg_sum[k][tx];
+    if (t < T) {
+        for (int c = c0; c < c1; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (c + k < c1) ? hist[(size_t)(c + k) * T + t] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c + k < c1) {
+                    hist[(size_t)(c + k) * T + t] = run;
+                    run += v[k];
+                }
+        }
+        if (seg == 31) {
+            uint32_t tot = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) tot += seg_sum[k][tx];
+            tile_total[t] = tot;
+        }
+    }
+}
+
+// Pass 3: exclusive scan over the tiles -> ranges (rasterizer_impl.cu:116-138 semantics: empty tiles (0,0))
+// and R. One CTA; T <= GVD_MAX_TILES.
+__global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t* __restrict__ tile_total,
+                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ num_rendered) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        const uint32_t v = (t < T) ? tile_total[t] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_sums[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t start = carry + (warp ? warp_sums[warp - 1] : 0u) + incl - v;
+        if (t < T) ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (tid == 0) *num_rendered = carry_s;
+}
+
+// Pass 4: chunk c writes its Gaussians' ids into the tile lists in depth order. cnt[t] = next free slot of
+// tile t. Two strategies, chosen per chunk:
+//   dense  (many large rects): one thread per tile walks the chunk's 256 rects in order -- no barriers, and
+//          most tests succeed;
+//   sparse (small rects): Gaussians one after the other, threads sharing the tiles of the current rect.
+__global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, uint32_t tiles_x,
+                                                                const SplatRec* __restrict__ splat,
+                                                                const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ tiles_touched,
+                                                                const uint32_t* __restrict__ chunk_flags,
+                                                                const uint32_t* __restrict__ hist,
+                                                                const uint2* __restrict__ ranges,
+                                                                uint32_t* __restrict__ point_list) {
+    extern __shared__ uint32_t cnt[];
+    __shared__ uint32_t s_id[GVD_BIN_CHUNK], s_n[GVD_BIN_CHUNK], s_r0[GVD_BIN_CHUNK], s_r1[GVD_BIN_CHUNK];
+    __shared__ uint32_t s_total;
+    if (!chunk_flags[blockIdx.x]) return;
+    const int tid = threadIdx.x;
+    const uint32_t* row = hist + (size_t)blockIdx.x * T;
+    if (tid == 0) s_total = 0;
+    {
+        const int i = blockIdx.x * GVD_BIN_CHUNK + tid;
+        uint32_t id = 0, n = 0, r0 = 0, r1 = 0;
+        if (i < P) {
+            id = order[i];
+            n = tiles_touched[id];
+            if (n > 0) {
+                const float4 d = splat[id].d;
+                r0 = __float_as_uint(d.x);
+                r1 = __float_as_uint(d.y);
+            }
+        }
+        s_id[tid] = id; s_n[tid] = n; s_r0[tid] = r0; s_r1[tid] = r1;
+        __syncthreads();
+        uint32_t w = n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if ((tid & 31) == 0 && w) atomicAdd(&s_total, w);
+    }
+    __syncthreads();
+    const bool dense = (uint64_t)s_total * 4u > (uint64_t)T * GVD_BIN_CHUNK;  // > 25 % of the rect tests succeed
+    if (dense) {
+        for (int t = tid; t < T; t += GVD_BIN_CHUNK) {
+            const uint32_t tx = (uint32_t)t % tiles_x, ty = (uint32_t)t / tiles_x;
+            uint32_t slot = ranges[t].x + row[t];
+            for (int g = 0; g < GVD_BIN_CHUNK; ++g) {
+                const uint32_t r0 = s_r0[g], r1 = s_r1[g];
+                // empty rects have r0 == r1 == 0 and fail the test
+                if (tx >= (r0 & 0xffff) && tx < (r1 & 0xffff) && ty >= (r0 >> 16) && ty < (r1 >> 16))
+                    point_list[slot++] = s_id[g];
+            }
+        }
+        return;
+    }
+    for (int t = tid; t < T; t += GVD_BIN_CHUNK) cnt[t] = ranges[t].x + row[t];
+    bool prev_big = true;
+    for (int g = 0; g < GVD_BIN_CHUNK; ++g) {
+        const uint32_t n = s_n[g];
+        if (n == 0) continue;
+        const bool big = n > 32;
+        // rects of <= 32 tiles are handled by warp 0 alone: consecutive small ones only need warp-level ordering
+        if (big || prev_big) __syncthreads(); else __syncwarp();
+        prev_big = big;
+        if (!big && tid >= 32) continue;
+        const uint32_t id = s_id[g], r0 = s_r0[g], r1 = s_r1[g];
+        const uint32_t x0 = r0 & 0xffff, y0 = r0 >> 16, bw = (r1 & 0xffff) - x0;
+        for (uint32_t k = tid; k < n; k += GVD_BIN_CHUNK) {
+            const uint32_t t = (y0 + k / bw) * tiles_x + x0 + k % bw;
+            const uint32_t slot = cnt[t];
+            cnt[t] = slot + 1;
+            point_list[slot] = id;
+        }
+    }
+}
+
+// Optional (export_keys): rebuild the reference's sorted 64-bit keys for parity checks.
+__global__ void __launch_bounds__(256) export_keys_kernel(int R, int T, const uint2* __restrict__ ranges,
+                                                          const uint32_t* __restrict__ point_list,
+                                                          const uint32_t* __restrict__ depth_key,
+                                                          uint64_t* __restrict__ keys) {
+    const int tile = blockIdx.x;
+    const uint2 r = ranges[tile];
+    for (uint32_t k = r.x + threadIdx.x; k < r.y; k += blockDim.x)
+        keys[k] = ((uint64_t)tile << 32) | depth_key[point_list[k]];
 }
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GVD_BLOCK) render_forward_kernel(
-    const uint2* __restrict__ ranges, const SplatRec* __restrict__ packed, int W, int H, uint32_t tiles_x,
-    const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_depth,
-    float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib) {
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
+    int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, float* __restrict__ out_color,
+    float* __restrict__ out_depth, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib) {
     __shared__ __align__(128) float4 buf[2][GVD_BATCH * 3];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(128) IdSlot ids[3];
+    __shared__ __align__(8) uint64_t bar[3];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tile = blockIdx.x;
     const uint32_t tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const uint32_t px = tile_x * GVD_TILE_X + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = tile_y * GVD_TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t sub_x = tile_x * GVD_TILE_X + (warp & 1) * 8, sub_y = tile_y * GVD_TILE_Y + (warp >> 1) * 4;
+    const uint32_t px = sub_x + (lane & 7), py = sub_y + (lane >> 3);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = W * py + px;
     const float2 pixf = {(float)px, (float)py};
+    const float sxf = (float)sub_x, syf = (float)sub_y;
 
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
     const int rounds = (n + GVD_BATCH - 1) / GVD_BATCH;
-    const SplatRec* list = packed + range.x;
+    const uint32_t* list = point_list + range.x;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0 && rounds > 0) {
-        const uint32_t bytes = (uint32_t)min(GVD_BATCH, n) * (uint32_t)sizeof(SplatRec);
-        mbar_arrive_expect_tx(&bar[0], bytes);
-        tma_bulk_g2s(&buf[0][0], list, bytes, &bar[0]);
+    if (tid == 0) {
+        if (rounds > 0) issue_id_copy(&ids[0], &bar[0], list, min(GVD_BATCH, n));
+        if (rounds > 1) issue_id_copy(&ids[1], &bar[1], list + GVD_BATCH, min(GVD_BATCH, n - GVD_BATCH));
+    }
+    // batch 0 -> buf[0]
+    if (rounds > 0) {
+        mbar_wait(&bar[0], 0);
+        if ((int)tid < min(GVD_BATCH, n)) {
+            const float4* src = reinterpret_cast<const float4*>(splat + ids[0].v[id_lead(list) + tid]);
+            buf[0][tid * 3 + 0] = __ldg(src);
+            buf[0][tid * 3 + 1] = __ldg(src + 1);
+            buf[0][tid * 3 + 2] = __ldg(src + 2);
+        }
     }
 
     bool done = !inside;
@@ -320,29 +497,44 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_forward_kernel(
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, weight = 0.f, Dsum = 0.f;
 
     for (int i = 0; i < rounds; ++i) {
-        // whole tile saturated? (forward.cu:310-313). Also frees buf[(i+1)&1] for the prefetch.
+        // whole tile saturated? (forward.cu:310-313). Also publishes buf[i&1] and retires buf[(i+1)&1].
         const int num_done = __syncthreads_count(done);
         if (num_done == GVD_BLOCK) {
-            // batch i is already in flight: a CTA must not exit under a pending bulk copy.
-            mbar_wait(&bar[i & 1], (uint32_t)((i >> 1) & 1));
+            // a CTA must not exit under a pending bulk copy: batch i+1's ids may still be in flight
+            if (i + 1 < rounds) mbar_wait(&bar[(i + 1) % 3], (uint32_t)(((i + 1) / 3) & 1));
             break;
         }
         const int cur = i & 1;
         const int cnt = min(GVD_BATCH, n - i * GVD_BATCH);
-        if (tid == 0 && i + 1 < rounds) {
-            const uint32_t bytes = (uint32_t)min(GVD_BATCH, n - (i + 1) * GVD_BATCH) * (uint32_t)sizeof(SplatRec);
-            mbar_arrive_expect_tx(&bar[cur ^ 1], bytes);
-            tma_bulk_g2s(&buf[cur ^ 1][0], list + (size_t)(i + 1) * GVD_BATCH, bytes, &bar[cur ^ 1]);
+        // prefetch: records of batch i+1 into registers (ids landed a round ago), ids of batch i+2 by TMA
+        float4 pa, pb, pc;
+        const int ncnt = min(GVD_BATCH, n - (i + 1) * GVD_BATCH);
+        const bool have_next = (i + 1 < rounds) && ((int)tid < ncnt);
+        if (i + 1 < rounds) {
+            mbar_wait(&bar[(i + 1) % 3], (uint32_t)(((i + 1) / 3) & 1));
+            if (have_next) {
+                const uint32_t* first = list + (size_t)(i + 1) * GVD_BATCH;
+                const float4* src = reinterpret_cast<const float4*>(splat + ids[(i + 1) % 3].v[id_lead(first) + tid]);
+                pa = __ldg(src);
+                pb = __ldg(src + 1);
+                pc = __ldg(src + 2);
+            }
+            if (tid == 0 && i + 2 < rounds)
+                issue_id_copy(&ids[(i + 2) % 3], &bar[(i + 2) % 3], list + (size_t)(i + 2) * GVD_BATCH,
+                              min(GVD_BATCH, n - (i + 2) * GVD_BATCH));
         }
-        mbar_wait(&bar[cur], (uint32_t)((i >> 1) & 1));
 
         const float4* rec = buf[cur];
         const uint32_t base = (uint32_t)i * GVD_BATCH;
         for (int chunk = 0; chunk * 32 < cnt; ++chunk) {
             if (__all_sync(0xffffffffu, done)) break;
             const int e = chunk * 32 + (int)lane;
-            const uint32_t mk = (e < cnt) ? __float_as_uint(rec[e * 3 + 2].w) : 0u;
-            unsigned m = __ballot_sync(0xffffffffu, (mk >> warp) & 1u);
+            bool hit = false;
+            if (e < cnt) {
+                const float4 ea = rec[e * 3], ec = rec[e * 3 + 2];
+                hit = subtile_hit(ea.x, ea.y, ec.z, ec.w, sxf, syf);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = chunk * 32 + __ffs(m) - 1;
                 m &= m - 1;
@@ -367,6 +559,11 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_forward_kernel(
                 T = test_T;
                 last_contributor = base + (uint32_t)j + 1u;
             }
+        }
+        if (have_next) {
+            buf[cur ^ 1][tid * 3 + 0] = pa;
+            buf[cur ^ 1][tid * 3 + 1] = pb;
+            buf[cur ^ 1][tid * 3 + 2] = pc;
         }
     }
 
@@ -399,25 +596,49 @@ void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& 
         a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
         a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
         (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
-        g.tiles_touched, a.prefiltered);
+        g.tiles_touched, g.depth_key, g.gidx, a.prefiltered);
 }
 
-void gvd_launch_emit_keys(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, dim3 grid, cudaStream_t s) {
-    emit_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.splat, g.tiles_touched, g.point_offsets, b.keys_unsorted,
-                                                     b.point_list_unsorted, grid);
+static cudaError_t ensure_smem(const void* fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-void gvd_launch_pack(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im, dim3 grid,
-                     cudaStream_t s) {
-    if (R > 0)
-        pack_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, b.keys, b.point_list, g.splat, b.packed, im.ranges, grid.x);
+cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, cudaStream_t s) {
+    const int T = (int)(grid.x * grid.y);
+    const size_t smem = (size_t)(grid.y + 1) * ((grid.x + 1) | 1) * sizeof(int);
+    cudaError_t e = ensure_smem((const void*)bin_count_kernel, smem);
+    if (e != cudaSuccess) return e;
+    bin_count_kernel<<<(unsigned)g.chunks, GVD_BIN_CHUNK, smem, s>>>(P, grid.x, grid.y, g.splat, g.order,
+                                                                    g.tiles_touched, g.chunk_flags, g.hist);
+    bin_prefix_kernel<<<(T + 31) / 32, 1024, 0, s>>>(T, (int)g.chunks, g.chunk_flags, g.hist, g.tile_total);
+    bin_ranges_kernel<<<1, 1024, 0, s>>>(T, g.tile_total, im.ranges, g.num_rendered);
+    return cudaGetLastError();
 }
 
-void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                               dim3 grid, cudaStream_t s) {
-    render_forward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.packed, a.width, a.height, grid.x,
-                                                                 a.background, a.out_color, a.out_depth, a.out_alpha,
-                                                                 im.n_contrib);
+cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                                dim3 grid, cudaStream_t s) {
+    const int T = (int)(grid.x * grid.y);
+    const size_t smem = (size_t)T * sizeof(uint32_t);
+    cudaError_t e = ensure_smem((const void*)bin_fill_kernel, smem);
+    if (e != cudaSuccess) return e;
+    bin_fill_kernel<<<(unsigned)g.chunks, GVD_BIN_CHUNK, smem, s>>>(P, T, grid.x, g.splat, g.order, g.tiles_touched,
+                                                                   g.chunk_flags, g.hist, im.ranges, b.point_list);
+    return cudaGetLastError();
+}
+
+void gvd_launch_export_keys(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                            dim3 grid, cudaStream_t s) {
+    if (R <= 0 || !b.keys) return;
+    const int T = (int)(grid.x * grid.y);
+    export_keys_kernel<<<T, 256, 0, s>>>(R, T, im.ranges, b.point_list, g.depth_key, b.keys);
+}
+
+void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                               const RasterImgPtrs& im, dim3 grid, cudaStream_t s) {
+    render_forward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height,
+                                                                 grid.x, a.background, a.out_color, a.out_depth,
+                                                                 a.out_alpha, im.n_contrib);
 }
 
 void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,

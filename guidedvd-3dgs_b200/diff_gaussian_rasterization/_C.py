@@ -32,6 +32,10 @@ def _f32c(t, name):
     return t.contiguous()
 
 
+# Tests flip this to also get the sorted 64-bit keys (tile<<32 | depth bits) written next to point_list.
+EXPORT_KEYS = False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -51,6 +55,14 @@ class _Allocs:
         t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         setattr(self, which, t)
         return t.data_ptr()
+
+    def take(self):
+        """Hand the buffers over and drop the callback closures: they reference `self`, and a reference
+        cycle would keep ~100 MB of scratch alive until the cyclic GC runs."""
+        out = (self.geom, self.binning, self.img)
+        self.geom = self.binning = self.img = None
+        self.cb_geom = self.cb_binning = self.cb_img = None
+        return out
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
@@ -103,14 +115,17 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     a.campos = _ptr(campos)
     a.scale_modifier, a.tan_fovx, a.tan_fovy = float(scale_modifier), float(tan_fovx), float(tan_fovy)
     a.prefiltered, a.debug = int(bool(prefiltered)), int(bool(debug))
+    a.export_keys = int(bool(EXPORT_KEYS))
     a.out_color, a.out_depth, a.out_alpha, a.radii = (out_color.data_ptr(), out_depth.data_ptr(),
                                                         out_alpha.data_ptr(), radii.data_ptr())
     a.geom_alloc, a.binning_alloc, a.img_alloc = allocs.cb_geom, allocs.cb_binning, allocs.cb_img
     with torch.cuda.device(dev):
         rc = lib.gvd_raster_forward(C.byref(a), _stream())
+    a.geom_alloc = a.binning_alloc = a.img_alloc = _n.ALLOC_FN(0)
+    geom, binning, img = allocs.take()
     if rc != 0:
         raise RuntimeError("gvd_raster_forward failed: " + _n.last_error(lib))
-    return (int(a.num_rendered), out_color, out_depth, out_alpha, radii, allocs.geom, allocs.binning, allocs.img)
+    return (int(a.num_rendered), out_color, out_depth, out_alpha, radii, geom, binning, img)
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,

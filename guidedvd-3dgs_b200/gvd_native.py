@@ -21,7 +21,7 @@ class RasterForwardArgs(C.Structure):
         ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
         ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
         ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
-        ("prefiltered", C.c_int), ("debug", C.c_int),
+        ("prefiltered", C.c_int), ("debug", C.c_int), ("export_keys", C.c_int),
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
         ("geom_alloc", ALLOC_FN), ("binning_alloc", ALLOC_FN), ("img_alloc", ALLOC_FN),
         ("alloc_user", C.c_void_p),
@@ -51,12 +51,12 @@ class RasterBackwardArgs(C.Structure):
 
 class RasterLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "geom_splat", "geom_clamped", "geom_tiles_touched", "geom_point_offsets",
-        "bin_point_list", "bin_point_list_keys", "bin_point_list_unsorted", "bin_keys_unsorted", "bin_packed",
+        "geom_splat", "geom_clamped", "geom_tiles_touched", "geom_order",
+        "bin_point_list", "bin_point_list_keys",
         "img_ranges", "img_n_contrib")]
 
 
-STAGE_NAMES = ("preprocess", "scan", "emit", "sort", "pack", "render_fwd", "render_bwd", "gaussian_bwd")
+STAGE_NAMES = ("preprocess", "bin_count", "bin_fill", "depth_sort", "export_keys", "render_fwd", "render_bwd", "gaussian_bwd")
 
 
 class RasterStageTimes(C.Structure):
@@ -71,6 +71,7 @@ RASTER_SYMBOLS = (
 )
 
 _raster = None
+ABI_VERSION = 5
 
 
 def lib_path(name="libgvd_raster.so"):
@@ -90,9 +91,12 @@ def raster():
     lib = C.CDLL(path)
     lib.gvd_last_error.restype = C.c_char_p
     lib.gvd_raster_abi_version.restype = C.c_int
-    for n in ("gvd_raster_geom_bytes", "gvd_raster_binning_bytes", "gvd_raster_backward_scratch_bytes"):
-        getattr(lib, n).restype = C.c_size_t
-        getattr(lib, n).argtypes = [C.c_int]
+    lib.gvd_raster_geom_bytes.restype = C.c_size_t
+    lib.gvd_raster_geom_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.gvd_raster_binning_bytes.restype = C.c_size_t
+    lib.gvd_raster_binning_bytes.argtypes = [C.c_int, C.c_int]
+    lib.gvd_raster_backward_scratch_bytes.restype = C.c_size_t
+    lib.gvd_raster_backward_scratch_bytes.argtypes = [C.c_int]
     lib.gvd_raster_img_bytes.restype = C.c_size_t
     lib.gvd_raster_img_bytes.argtypes = [C.c_int, C.c_int]
     lib.gvd_raster_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RasterLayout)]
@@ -103,7 +107,7 @@ def raster():
         getattr(lib, n).restype = C.c_int
     lib.gvd_raster_profile_enable.argtypes = [C.c_int]
     lib.gvd_raster_profile_read.argtypes = [C.POINTER(RasterStageTimes)]
-    if lib.gvd_raster_abi_version() != 3:
+    if lib.gvd_raster_abi_version() != ABI_VERSION:
         raise RuntimeError("libgvd_raster.so ABI version mismatch; rebuild")
     _raster = lib
     return lib

@@ -40,7 +40,7 @@ typedef struct CUstream_st* gvd_stream_t; /* == cudaStream_t */
 typedef void* (*gvd_alloc_fn)(void* user, size_t bytes);
 
 /* Layout/version of the scratch buffers (bumped when the packed layouts change). */
-#define GVD_RASTER_ABI_VERSION 3
+#define GVD_RASTER_ABI_VERSION 5
 
 typedef struct GvdRasterForwardArgs {
     /* sizes -- DGR/cuda_rasterizer/rasterizer_impl.cu:197-224 */
@@ -64,14 +64,15 @@ typedef struct GvdRasterForwardArgs {
     float tan_fovx, tan_fovy;
     int prefiltered;
     int debug;                   /* sync + check after every stage        */
+    int export_keys;             /* also write the sorted 64-bit keys (tile<<32|depth bits) for parity checks */
     /* outputs (dev) */
     float* out_color;            /* [3,H,W]  */
     float* out_depth;            /* [1,H,W]  sum depth*alpha*T (un-normalised) */
     float* out_alpha;            /* [1,H,W]  sum alpha*T                       */
     int*   radii;                /* [P]      */
     /* scratch (caller-owned, via callbacks like the reference) */
-    gvd_alloc_fn geom_alloc;     /* called once with gvd_raster_geom_bytes(P)        */
-    gvd_alloc_fn binning_alloc;  /* called once with gvd_raster_binning_bytes(R)     */
+    gvd_alloc_fn geom_alloc;     /* called once with gvd_raster_geom_bytes(P,W,H)    */
+    gvd_alloc_fn binning_alloc;  /* called once with gvd_raster_binning_bytes(R,export_keys) */
     gvd_alloc_fn img_alloc;      /* called once with gvd_raster_img_bytes(W,H)       */
     void* alloc_user;
     /* result */
@@ -124,8 +125,8 @@ typedef struct GvdRasterBackwardArgs {
 /* sizes of the caller-owned scratch buffers; replaces
  * CudaRasterizer::required<GeometryState|BinningState|ImageState>
  * (DGR/cuda_rasterizer/rasterizer_impl.h:63-69). */
-GVD_API size_t gvd_raster_geom_bytes(int P);
-GVD_API size_t gvd_raster_binning_bytes(int R);
+GVD_API size_t gvd_raster_geom_bytes(int P, int width, int height);
+GVD_API size_t gvd_raster_binning_bytes(int R, int export_keys);
 GVD_API size_t gvd_raster_img_bytes(int width, int height);
 GVD_API size_t gvd_raster_backward_scratch_bytes(int P);
 
@@ -147,24 +148,22 @@ GVD_API int gvd_raster_mark_visible(int P, const float* means3D, const float* vi
  * the scratch buffers of THIS library (the reference's own layout is
  * rasterizer_impl.cu:155-195). */
 typedef struct GvdRasterLayout {
-    size_t geom_splat;          /* float4[3P]: {x,y,conA,conB},{conC,opac,r,g},{b,depth,rect_lo,rect_hi} */
-    size_t geom_clamped;        /* uint8[P]: bit c set = channel c was clamped at 0                       */
-    size_t geom_tiles_touched;  /* uint32[P]                                                              */
-    size_t geom_point_offsets;  /* uint32[P] inclusive scan of tiles_touched                              */
-    size_t bin_point_list;          /* uint32[R] sorted Gaussian ids                                      */
-    size_t bin_point_list_keys;     /* uint64[R] sorted keys (tile<<32 | depth bits)                      */
-    size_t bin_point_list_unsorted; /* uint32[R]                                                          */
-    size_t bin_keys_unsorted;       /* uint64[R]                                                          */
-    size_t bin_packed;              /* float4[3R] packed per-instance records (TMA source)                */
-    size_t img_ranges;          /* uint2[T]   */
-    size_t img_n_contrib;       /* uint32[H*W]*/
+    size_t geom_splat;          /* float4[4P]: {x,y,conA,conB},{conC,opac,r,g},{b,depth,hx,hy},{rect_lo,rect_hi,0,0} */
+    size_t geom_clamped;        /* uint8[P]: bit c set = channel c was clamped at 0                          */
+    size_t geom_tiles_touched;  /* uint32[P]                                                                 */
+    size_t geom_order;          /* uint32[P] Gaussian ids sorted by (depth bits, id); culled ones last       */
+    size_t bin_point_list;      /* uint32[R] sorted Gaussian ids (tile-major, depth order inside a tile)     */
+    size_t bin_point_list_keys; /* uint64[R] sorted keys (tile<<32 | depth bits); only with export_keys      */
+    size_t img_ranges;          /* uint2[T]                                                                  */
+    size_t img_n_contrib;       /* uint32[H*W]                                                               */
 } GvdRasterLayout;
 GVD_API int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out);
 
 /* Optional per-stage device timing (CUDA events recorded on the caller's stream around each stage).
  * Off by default; used by bench.py for the live roofline numbers. Not thread-safe; single stream. */
 enum {
-    GVD_STAGE_PREPROCESS = 0, GVD_STAGE_SCAN, GVD_STAGE_EMIT, GVD_STAGE_SORT, GVD_STAGE_PACK,
+    GVD_STAGE_PREPROCESS = 0, GVD_STAGE_SCAN /* bin count+prefix+ranges */, GVD_STAGE_EMIT /* bin fill */,
+    GVD_STAGE_SORT /* depth sort */, GVD_STAGE_PACK /* export_keys (tests only) */,
     GVD_STAGE_RENDER_FWD, GVD_STAGE_RENDER_BWD, GVD_STAGE_GAUSSIAN_BWD, GVD_STAGE_COUNT
 };
 typedef struct GvdRasterStageTimes {

@@ -27,6 +27,8 @@ def make_inputs(P, W, H, seed, sh_degree=3, device="cuda", fovx_deg=90.0):
 
 def run(pkg, sc, cam, cot, bg, sh_degree, use_conf=True, precomp=False, debug=False, backward=True):
     """One forward(+backward) through the package's public API. Returns dict of outputs/grads/buffers."""
+    if hasattr(pkg, "_C") and hasattr(pkg._C, "EXPORT_KEYS"):
+        pkg._C.EXPORT_KEYS = True  # ours: also materialise the sorted 64-bit keys for comparison
     dev = sc["means3D"].device
     conf = sc["confidence"] if use_conf else torch.ones_like(sc["confidence"])
     settings = pkg.GaussianRasterizationSettings(
@@ -85,11 +87,20 @@ def ours_views(out, P, W, H):
     v["point_list"] = b[L.bin_point_list:L.bin_point_list + 4 * R].view(torch.int32)
     v["point_list_keys"] = b[L.bin_point_list_keys:L.bin_point_list_keys + 8 * R].view(torch.int64)
     v["tiles_touched"] = g[L.geom_tiles_touched:L.geom_tiles_touched + 4 * P].view(torch.int32)
-    v["splat"] = g[L.geom_splat:L.geom_splat + 48 * P].view(torch.float32).view(P, 12)
+    v["splat"] = g[L.geom_splat:L.geom_splat + 64 * P].view(torch.float32).view(P, 16)
     v["clamped"] = g[L.geom_clamped:L.geom_clamped + P]
     v["ranges"] = im[L.img_ranges:L.img_ranges + 8 * tiles].view(torch.int32).view(tiles, 2)
     v["n_contrib"] = im[L.img_n_contrib:L.img_n_contrib + 4 * W * H].view(torch.int32)
     return v
+
+
+def scale_err(a, b):
+    """(max |a-b| / rms(b), ||a-b|| / ||b||): error relative to the tensor's scale."""
+    a, b = a.double().flatten(), b.double().flatten()
+    if b.numel() == 0:
+        return 0.0, 0.0
+    rms = b.pow(2).mean().sqrt().clamp_min(1e-30)
+    return ((a - b).abs().max() / rms).item(), ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
 def relerr(a, b, floor_frac=1e-3):
@@ -146,6 +157,8 @@ def compare(P, W, H, seed, sh_degree=3, use_conf=True, precomp=False, verbose=Tr
             continue
         res[f"grad_{k}_relerr"] = relerr(go, gr)
         res[f"grad_{k}_ref_jitter"] = relerr(r2["grads"][k], gr)
+        res[f"grad_{k}_scale_err"] = scale_err(go, gr)
+        res[f"grad_{k}_ref_scale_jitter"] = scale_err(r2["grads"][k], gr)
     if verbose:
         for k, v in res.items():
             print(f"  {k}: {v}")

@@ -22,25 +22,24 @@ def test_header_symbols_exported():
     for s in declared:
         assert hasattr(lib, s), f"libgvd_raster.so does not export {s}"
     assert set(declared) == set(gvd_native.RASTER_SYMBOLS)
-    assert lib.gvd_raster_abi_version() == 3
+    assert lib.gvd_raster_abi_version() == gvd_native.ABI_VERSION
 
 
 def test_sizes_and_layout_monotone():
     import gvd_native
 
     lib = gvd_native.raster()
-    assert lib.gvd_raster_geom_bytes(0) >= 128
-    g1, g2 = lib.gvd_raster_geom_bytes(1000), lib.gvd_raster_geom_bytes(2000)
-    assert g2 > g1 >= 1000 * 48
-    b1 = lib.gvd_raster_binning_bytes(10000)
-    assert b1 >= 10000 * (48 + 4 + 4)
+    assert lib.gvd_raster_geom_bytes(0, 64, 64) >= 128
+    g1, g2 = lib.gvd_raster_geom_bytes(1000, 640, 480), lib.gvd_raster_geom_bytes(2000, 640, 480)
+    assert g2 > g1 >= 1000 * 64
+    b1 = lib.gvd_raster_binning_bytes(10000, 0)
+    assert b1 >= 10000 * 4 and lib.gvd_raster_binning_bytes(10000, 1) >= b1 + 10000 * 8
     assert lib.gvd_raster_img_bytes(640, 480) >= 640 * 480 * 4 + 1200 * 8
     assert lib.gvd_raster_backward_scratch_bytes(1000) >= 1000 * 48
     L = gvd_native.RasterLayout()
     assert lib.gvd_raster_layout(1000, 5000, 640, 480, C.byref(L)) == 0
     offs = [getattr(L, n) for n, _ in L._fields_]
     assert all(o % 128 == 0 for o in offs)
-    assert L.bin_packed % 16 == 0  # TMA bulk copies need 16-byte aligned sources
 
 
 def test_struct_sizes_match_header():

