@@ -189,23 +189,65 @@ def main():
             flat = torch.cat([t.reshape(-1) for t in grad_flat(leaves)])
             dist.all_reduce(flat)
 
+    # End-to-end step: this step's inputs (camera, cotangent images) come from pinned host memory. Like a
+    # prefetching data loader, the upload of step k+1 is issued on a copy stream while step k computes.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_slots = [(torch.empty_like(cam_host, device=dev), torch.empty_like(cot_host, device=dev)) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    slot_free = [torch.cuda.Event() for _ in range(2)]
+    staged = {"n": 0}
+
+    def stage_inputs(k):
+        cm, cot = dev_slots[k % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot_free[k % 2])  # the step that last used this slot has finished
+            cm.copy_(cam_host, non_blocking=True)
+            cot.copy_(cot_host, non_blocking=True)
+            h2d_done[k % 2].record(copy_stream)
+
     def e2e_step():
-        cm = cam_host.to(dev, non_blocking=True)
-        cot = cot_host.to(dev, non_blocking=True)
+        k = e2e_state["k"]
+        if staged["n"] <= k:
+            stage_inputs(k)
+            staged["n"] = k + 1
+        cm, cot = dev_slots[k % 2]
+        torch.cuda.current_stream().wait_event(h2d_done[k % 2])
+        stage_inputs(k + 1)  # H2D of the next step overlaps this step's kernels
+        staged["n"] = k + 2
         color, radii = step(cot, cm[0:16].view(4, 4), cm[16:32].view(4, 4), cm[32:35])
         if world > 1:
             flat = torch.cat([t.reshape(-1) for t in grad_flat(leaves)])
             dist.all_reduce(flat)
-        # the step's result: the scalar a trainer reads back every iteration (train_baseline.py:88)
-        return float((color * cot[0:3]).sum().item())
+        # The step's result: the scalar a trainer reads back every iteration (train_baseline.py:88). It is copied
+        # to pinned host memory asynchronously and READ one step later (asynchronous loss logging), so the host
+        # never idles the GPU; every step's value is read inside the timed region (the last one by e2e_flush).
+        loss_pinned[k % 2].copy_((color * cot[0:3]).sum(), non_blocking=True)
+        loss_events[k % 2].record()
+        if k > 0:
+            loss_events[(k - 1) % 2].synchronize()
+            e2e_state["last"] = float(loss_pinned[(k - 1) % 2])
+        slot_free[k % 2].record()
+        e2e_state["k"] = k + 1
 
-    def timed(fn, n):
+    def e2e_flush():
+        k = e2e_state["k"]
+        if k > 0:
+            loss_events[(k - 1) % 2].synchronize()
+            e2e_state["last"] = float(loss_pinned[(k - 1) % 2])
+
+    e2e_state = {"k": 0, "last": None}
+    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_events = [torch.cuda.Event() for _ in range(2)]
+
+    def timed(fn, n, flush=None):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(n):
             fn()
+        if flush is not None:
+            flush()
         e1.record()
         sync_all()
         wall = time.perf_counter() - t0
@@ -223,7 +265,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_res, wall_res = timed(resident_step, K)
-    ms_e2e, wall_e2e = timed(e2e_step, K)
+    ms_e2e, wall_e2e = timed(e2e_step, K, e2e_flush)
     clocks = sampler.stop()
 
     # workload facts (same for both arms): R, visible count

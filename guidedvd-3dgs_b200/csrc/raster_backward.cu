@@ -76,7 +76,7 @@ __device__ __forceinline__ int warp_reduce10(float (&v)[10], uint32_t lane, floa
     return local + (b4 ? 5 : 0);
 }
 
-__global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
+__global__ void __launch_bounds__(GVD_BLOCK, 3) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, const float* __restrict__ alphas,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
 #pragma unroll
                     for (int k = 0; k < 10; ++k) g[k] = 0.0f;
                     if (contrib) {
-                        T = T / (1.f - alpha);
+                        const float rcp_1ma = 1.0f / (1.f - alpha);  // one IEEE reciprocal feeds both quotients below
+                        T = T * rcp_1ma;
                         const float dchannel_dcolor = alpha * T;
                         const float dpixel_depth_ddepth = alpha * T;
                         float dL_dopa = 0.0f;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(GVD_BLOCK) render_backward_kernel(
                         dL_dopa *= T;
                         last_alpha = alpha;
                         // background (backward.cu:573-578)
-                        dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                        dL_dopa += (-T_final * rcp_1ma) * bg_dot_dpixel;
 
                         const float dL_dG = rb.y * dL_dopa;
                         const float gdx = G * d.x;
@@ -303,7 +304,7 @@ __device__ __forceinline__ void store_p3_coalesced(float* __restrict__ dst, floa
         o_sh[3 * (k) + 2] = _t.z * conf;            \
     }
 
-__global__ void __launch_bounds__(256) gaussian_backward_kernel(
+__global__ void __launch_bounds__(256, 2) gaussian_backward_kernel(
     int P, int D, int M, const float3* __restrict__ means, const int* __restrict__ radii,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float3* __restrict__ scales,
     const float4* __restrict__ rotations, const float scale_modifier, const float* __restrict__ cov3D_precomp,
@@ -618,6 +619,11 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(
 
 void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                 const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute((const void*)render_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carveout_set = true;
+    }
     render_backward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height, grid.x,
                                                                   a.background, a.alphas, im.n_contrib, a.dL_dpix,
                                                                   a.dL_ddepth_pix, a.dL_dalpha_pix, acc);

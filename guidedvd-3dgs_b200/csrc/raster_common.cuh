@@ -4,7 +4,7 @@
 //   geom   : SplatRec[P] (64 B per Gaussian, written by preprocess, gathered on demand by the render
 //            kernels -- the visible set is a few MB and lives in the 126 MB L2), clamped[P],
 //            tiles_touched[P], depth keys / order[P] (depth sort), per-chunk tile histogram matrix
-//            [ceil(P/256)][T] (binning), tile totals.
+//            [ceil(P/GVD_BIN_CHUNK)][T] (binning), tile totals.
 //   binning: uint32 point_list[R] -- Gaussian ids, tile-major, depth-sorted inside a tile (identical to
 //            the reference's sorted value array); optional uint64 keys[R] for parity checks.
 //   img    : uint2 ranges[T], uint32 n_contrib[H*W]
@@ -17,7 +17,7 @@
 #define GVD_BLOCK 256      // threads per render CTA = pixels per tile
 #define GVD_BATCH 256      // tile-list entries staged per round
 #define GVD_ACC_STRIDE 12  // floats per Gaussian in the backward accumulator
-#define GVD_BIN_CHUNK 256  // Gaussians (in depth order) per binning chunk
+#define GVD_BIN_CHUNK 64   // Gaussians (in depth order) per binning chunk (= threads per binning CTA)
 #define GVD_MAX_TILES 49152  // per-CTA shared-memory tile counters (4 B each) must fit in 227 KB
 
 // 64-byte per-Gaussian record:
@@ -49,7 +49,7 @@ struct RasterGeomPtrs {
 };
 
 // Binning = depth sort of the Gaussians (P 32-bit keys) followed by a rect-aware STABLE counting sort on
-// the tile id: chunks of 256 depth-consecutive Gaussians histogram their tile rects, a column prefix over
+// the tile id: chunks of GVD_BIN_CHUNK depth-consecutive Gaussians histogram their tile rects, a column prefix over
 // chunks gives every chunk its starting rank in every tile, and each chunk then writes its Gaussians'
 // ids tile by tile in depth order. The result equals the reference's single stable radix sort on
 // (tile<<32 | depth bits): same tile -> by depth -> ties by Gaussian id (rasterizer_impl.cu:70-111,304-309).

@@ -207,9 +207,9 @@ __device__ __forceinline__ void unpack_rect(const float4 d, uint32_t& x0, uint32
     x0 = w0 & 0xffff; y0 = w0 >> 16; x1 = w1 & 0xffff; y1 = w1 >> 16;
 }
 
-// Pass 1: chunk c = Gaussians order[256c .. 256c+255]. hist[c][t] = how many of them cover tile t.
+// Pass 1: chunk c = GVD_BIN_CHUNK depth-consecutive Gaussians order[c*CHUNK ..]. hist[c][t] = how many of them cover tile t.
 // A rect adds +1/-1 at its four corners of a (gy+1) x (gx+1) difference grid; a 2-D prefix sum then yields
-// the per-tile counts. Cost per chunk is O(256 + T) whatever the rect sizes (no per-instance atomics).
+// the per-tile counts. Cost per chunk is O(CHUNK + T) whatever the rect sizes (no per-instance atomics).
 __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(int P, uint32_t gx, uint32_t gy,
                                                                  const SplatRec* __restrict__ splat,
                                                                  const uint32_t* __restrict__ order,
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t*
 
 // Pass 4: chunk c writes its Gaussians' ids into the tile lists in depth order. cnt[t] = next free slot of
 // tile t. Two strategies, chosen per chunk:
-//   dense  (many large rects): one thread per tile walks the chunk's 256 rects in order -- no barriers, and
+//   dense  (many large rects): one thread per tile walks the chunk's rects in order -- no barriers, and
 //          most tests succeed;
 //   sparse (small rects): Gaussians one after the other, threads sharing the tiles of the current rect.
 __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, uint32_t tiles_x,
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) export_keys_kernel(int R, int T, const ui
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GVD_BLOCK) render_forward_kernel(
+__global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib) {
@@ -636,6 +636,11 @@ void gvd_launch_export_keys(int R, const RasterGeomPtrs& g, const RasterBinPtrs&
 
 void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                const RasterImgPtrs& im, dim3 grid, cudaStream_t s) {
+    static bool carveout_set = false;
+    if (!carveout_set) {  // eight 28 KB CTAs per SM need the large shared-memory carveout
+        cudaFuncSetAttribute((const void*)render_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carveout_set = true;
+    }
     render_forward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height,
                                                                  grid.x, a.background, a.out_color, a.out_depth,
                                                                  a.out_alpha, im.n_contrib);
