@@ -115,3 +115,26 @@ def raster():
 
 def last_error(lib):
     return (lib.gvd_last_error() or b"").decode("utf-8", "replace")
+
+
+# ---- libgvd_knn.so (include/gvd_knn.h) -----------------------------------------------------------------
+KNN_SYMBOLS = ("gvd_knn3_tmp_bytes", "gvd_knn3", "gvd_knn_last_error")
+_knn = None
+
+
+def knn():
+    """Load libgvd_knn.so once; raise loudly when it is absent (there is no fallback)."""
+    global _knn
+    if _knn is not None:
+        return _knn
+    path = lib_path("libgvd_knn.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `make -C guidedvd-3dgs_b200/csrc`. No fallback path exists.")
+    lib = C.CDLL(path)
+    lib.gvd_knn_last_error.restype = C.c_char_p
+    lib.gvd_knn3_tmp_bytes.restype = C.c_size_t
+    lib.gvd_knn3_tmp_bytes.argtypes = [C.c_int]
+    lib.gvd_knn3.restype = C.c_int
+    lib.gvd_knn3.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    _knn = lib
+    return lib
