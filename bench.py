@@ -27,6 +27,8 @@ for p in (PKG, os.path.join(ROOT, "tests")):
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+import view_parallel  # noqa: E402
+
 WORKLOADS = {
     # name: (P, W, H, seed, sh_degree, description)
     "C2": (500_000, 640, 480, 20260002, 3,
@@ -186,8 +188,7 @@ def main():
     def resident_step():
         step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
         if world > 1:
-            flat = torch.cat([t.reshape(-1) for t in grad_flat(leaves)])
-            dist.all_reduce(flat)
+            view_parallel.allreduce_gradients(grad_flat(leaves))
 
     # End-to-end step: this step's inputs (camera, cotangent images) come from pinned host memory. Like a
     # prefetching data loader, the upload of step k+1 is issued on a copy stream while step k computes.
@@ -216,8 +217,7 @@ def main():
         staged["n"] = k + 2
         color, radii = step(cot, cm[0:16].view(4, 4), cm[16:32].view(4, 4), cm[32:35])
         if world > 1:
-            flat = torch.cat([t.reshape(-1) for t in grad_flat(leaves)])
-            dist.all_reduce(flat)
+            view_parallel.allreduce_gradients(grad_flat(leaves))
         # The step's result: the scalar a trainer reads back every iteration (train_baseline.py:88). It is copied
         # to pinned host memory asynchronously and READ one step later (asynchronous loss logging), so the host
         # never idles the GPU; every step's value is read inside the timed region (the last one by e2e_flush).
