@@ -1,0 +1,256 @@
+// gemm_tc.cu -- strided-batched bf16 GEMM on Blackwell tensor cores (include/gvd_nn.h::gvd_gemm_bf16).
+//
+// One CTA computes a 128x128 tile of C:
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor (4-D tensor maps, 128-byte swizzle) into a 3-stage smem ring
+//   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32 in TMEM),
+//                                tcgen05.commit releases smem stages / signals the epilogue; also owns TMEM alloc
+//   warps 2-5: epilogue       -- tcgen05.ld (32 lanes x 16 columns), alpha / bias / activation / residual, bf16 or
+//                                fp32 stores straight to the (strided) destination
+// Two CTAs fit per SM (96 KB of stages each, 128 TMEM columns each), so one CTA's epilogue overlaps the other's
+// main loop.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the epilogue.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <string>
+
+#include "../../include/gvd_nn.h"
+#include "tc_common.cuh"
+
+namespace {
+
+thread_local std::string g_nn_err;
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+
+struct EpiParams {
+    void* C;
+    long long ldc, c_stride_h, c_stride_b;
+    const float* bias;
+    const void* residual;
+    float alpha;
+    int act, out_fp32;
+    int M, N, K, batch_h;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == GVD_ACT_SILU) return x / (1.0f + __expf(-x));
+    if (act == GVD_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    return x;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint64_t* full = bars;               // [STAGES]
+    uint64_t* empty = bars + STAGES;     // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int bh = blockIdx.z % p.batch_h, bb = blockIdx.z / p.batch_h;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, BN);  // 128 fp32 columns
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
+                tc::mbar_wait(&empty[s], ph ^ 1u);
+                tc::mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
+                tc::tma_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full[s], kb * BK, m0, bh, bb);
+                tc::tma_load_4d(smem_b + s * B_STAGE_BYTES, &tmap_b, &full[s], kb * BK, n0, bh, bb);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
+                tc::mbar_wait(&full[s], ph);
+                tc::fence_after_sync();
+                const uint32_t a_addr = tc::smem_u32(smem_a + s * A_STAGE_BYTES);
+                const uint32_t b_addr = tc::smem_u32(smem_b + s * B_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t adesc = tc::make_desc_kmajor_sw128(a_addr + k * 32);
+                    const uint64_t bdesc = tc::make_desc_kmajor_sw128(b_addr + k * 32);
+                    tc::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+                }
+                tc::umma_commit(&empty[s]);  // frees this smem stage once the MMAs above have read it
+            }
+            tc::umma_commit(tmem_full);      // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
+        const int q = warp & 3;
+        tc::mbar_wait(tmem_full, 0);
+        tc::fence_after_sync();
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
+        const long long row_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h + (long long)m * p.ldc;
+        const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_stride_h & 7) == 0) && ((p.c_stride_b & 7) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            if (n0 + c >= p.N) break;  // warp-uniform
+            uint32_t v[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            tc::tmem_ld_wait();
+            if (!row_ok) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(v[j]) * p.alpha;
+                const int n = n0 + c + j;
+                if (p.bias != nullptr && n < p.N) x += p.bias[n];
+                f[j] = apply_act(x, p.act);
+            }
+            const int n_first = n0 + c;
+            const bool full16 = (n_first + 16 <= p.N);
+            if (p.out_fp32) {
+                float* dst = reinterpret_cast<float*>(p.C) + row_off + n_first;
+                const float* res = p.residual ? reinterpret_cast<const float*>(p.residual) + row_off + n_first : nullptr;
+                if (full16 && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        if (res) {
+                            const float4 r = *reinterpret_cast<const float4*>(res + j);
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+                    for (int j = 0; j < 16 && n_first + j < p.N; ++j) dst[j] = f[j] + (res ? res[j] : 0.f);
+                }
+            } else {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + row_off + n_first;
+                const __nv_bfloat16* res =
+                    p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + row_off + n_first : nullptr;
+                if (full16 && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        float r8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        if (res) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(res + j);
+                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 rf = __bfloat1622float2(rp[t]);
+                                r8[2 * t] = rf.x;
+                                r8[2 * t + 1] = rf.y;
+                            }
+                        }
+                        uint4 ov;
+                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            op[t] = __floats2bfloat162_rn(f[j + 2 * t] + r8[2 * t], f[j + 2 * t + 1] + r8[2 * t + 1]);
+                        *reinterpret_cast<uint4*>(dst + j) = ov;
+                    }
+                } else {
+                    for (int j = 0; j < 16 && n_first + j < p.N; ++j)
+                        dst[j] = __float2bfloat16(f[j] + (res ? __bfloat162float(res[j]) : 0.f));
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+// ---- host side: tensor maps ----
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 4-D bf16 view: (K contiguous, rows with stride ld, h with stride sh, b with stride sb), all in elements
+bool make_tmap(CUtensorMap* map, const void* base, long long K, long long rows, long long H, long long Bn, long long ld,
+               long long sh, long long sb, int box_rows) {
+    auto enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)H, (cuuint64_t)Bn};
+    // strides of a size-1 dimension are never used to form an address but must still be valid (multiple of 16 bytes)
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(H > 1 ? sh : ld) * 2, (cuuint64_t)(Bn > 1 ? sb : ld) * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gvd_nn_last_error(void) { return g_nn_err.c_str(); }
+
+int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->A || !a->B || !a->C) { g_nn_err = "gvd_gemm_bf16: null pointer"; return 2; }
+    if (a->M <= 0 || a->N <= 0 || a->batch_h <= 0 || a->batch_b <= 0) return 0;
+    if (a->K <= 0) { g_nn_err = "gvd_gemm_bf16: K must be positive"; return 2; }
+    auto bad = [](long long v) { return (v & 7) != 0; };
+    if (bad(a->lda) || bad(a->ldb) || (a->batch_h > 1 && (bad(a->a_stride_h) || bad(a->b_stride_h))) ||
+        (a->batch_b > 1 && (bad(a->a_stride_b) || bad(a->b_stride_b))) ||
+        (reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) {
+        g_nn_err = "gvd_gemm_bf16: operand strides must be multiples of 8 elements and bases 16-byte aligned";
+        return 2;
+    }
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
+        !make_tmap(&tb, a->B, a->K, a->N, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b, BN)) {
+        g_nn_err = "gvd_gemm_bf16: cuTensorMapEncodeTiled failed";
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 attr: ") + cudaGetErrorString(e); return 1; }
+        attr_set = true;
+    }
+    EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->residual, a->alpha, a->act, a->out_fp32,
+                a->M, a->N, a->K, a->batch_h};
+    dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM, a->batch_h * a->batch_b);
+    gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 launch: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+}  // extern "C"

@@ -138,3 +138,34 @@ def knn():
     lib.gvd_knn3.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     _knn = lib
     return lib
+
+
+# ---- libgvd_nn.so (include/gvd_nn.h) --------------------------------------------------------------------
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch_h", C.c_int), ("batch_b", C.c_int),
+        ("A", C.c_void_p), ("lda", C.c_longlong), ("a_stride_h", C.c_longlong), ("a_stride_b", C.c_longlong),
+        ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_stride_h", C.c_longlong), ("b_stride_b", C.c_longlong),
+        ("C", C.c_void_p), ("ldc", C.c_longlong), ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("alpha", C.c_float), ("act", C.c_int), ("out_fp32", C.c_int),
+    ]
+
+
+NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error")
+_nn = None
+
+
+def nn():
+    """Load libgvd_nn.so once; raise loudly when it is absent (there is no fallback)."""
+    global _nn
+    if _nn is not None:
+        return _nn
+    path = lib_path("libgvd_nn.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `make -C guidedvd-3dgs_b200/csrc`. No fallback path exists.")
+    lib = C.CDLL(path)
+    lib.gvd_nn_last_error.restype = C.c_char_p
+    lib.gvd_gemm_bf16.restype = C.c_int
+    lib.gvd_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    _nn = lib
+    return lib

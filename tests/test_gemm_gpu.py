@@ -1,0 +1,56 @@
+"""GPU numerics: the tcgen05 bf16 GEMM (include/gvd_nn.h::gvd_gemm_bf16) against a plain PyTorch fp32 reference of
+the same op on the same bf16 inputs.  Tolerance: bf16 output rounding (2^-8 relative) plus fp32 accumulation noise."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, bias, res, alpha, act):
+    y = alpha * (A.float() @ B.float().transpose(-1, -2))
+    if bias is not None:
+        y = y + bias
+    if act == "silu":
+        y = torch.nn.functional.silu(y)
+    elif act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    if res is not None:
+        y = y + res.float()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 320), (1000, 320, 2880), (130, 72, 72), (77, 1280, 1024),
+                                   (4096, 2560, 320), (300, 8, 2880), (64, 4, 320), (513, 640, 8)])
+@pytest.mark.parametrize("opts", [dict(), dict(bias=True, act="silu"), dict(bias=True, res=True), dict(fp32=True, bias=True, act="gelu", alpha=0.125)])
+def test_linear_shapes(M, N, K, opts):
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) if opts.get("bias") else None
+    out_dtype = torch.float32 if opts.get("fp32") else torch.bfloat16
+    res = torch.randn(M, N, device="cuda", generator=g).to(out_dtype) if opts.get("res") else None
+    alpha, act = opts.get("alpha", 1.0), opts.get("act", "none")
+    y = ops.linear(A, B, bias=bias, act=act, residual=res, out_dtype=out_dtype, alpha=alpha)
+    ref = _ref(A, B, bias, res, alpha, act)
+    tol = 2e-5 if out_dtype == torch.float32 else 1.0 / 128
+    err = (y.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * scale + 1e-4, (err, scale)
+
+
+def test_batched_strided_heads():
+    """The q/k layout of CrossAttention: [b, n, h*64] viewed per head without a copy (attention.py:98-103)."""
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Bn, H, Nq, Nk, D = 3, 5, 200, 77, 64
+    q = torch.randn(Bn, Nq, H * D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(Bn, Nk, H * D, device="cuda", generator=g).bfloat16()
+    sim = torch.empty(Bn, H, Nq, Nk + 3, device="cuda", dtype=torch.float32)[..., :Nk]  # padded rows: ldc = Nk+3 -> scalar path
+    sim = torch.empty(Bn, H, Nq, 80, device="cuda", dtype=torch.float32)
+    ops.gemm_raw(q, k, sim, Nq, Nk, D, H * D, H * D, 80, batch_h=H, batch_b=Bn, a_strides=(D, Nq * H * D),
+                 b_strides=(D, Nk * H * D), c_strides=(Nq * 80, H * Nq * 80), alpha=D ** -0.5)
+    ref = torch.einsum("bihd,bjhd->bhij", q.float().view(Bn, Nq, H, D), k.float().view(Bn, Nk, H, D)) * D ** -0.5
+    assert (sim[..., :Nk] - ref).abs().max().item() < 1e-3
