@@ -15,9 +15,11 @@
 #include "../../include/gvd_nn.h"
 #include "tc_common.cuh"
 
+thread_local std::string g_nn_err_ext;
+#define g_nn_err g_nn_err_ext
+
 namespace {
 
-thread_local std::string g_nn_err;
 
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
@@ -28,11 +30,14 @@ struct EpiParams {
     void* C;
     long long ldc, c_stride_h, c_stride_b;
     const float* bias;
+    const float* bias2;
     const void* residual;
     float alpha;
     int act, out_fp32;
     int M, N, K, batch_h;
 };
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == GVD_ACT_SILU) return x / (1.0f + __expf(-x));
@@ -125,10 +130,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]) * p.alpha;
+                float x = __uint_as_float(v[j]);
                 const int n = n0 + c + j;
-                if (p.bias != nullptr && n < p.N) x += p.bias[n];
-                f[j] = apply_act(x, p.act);
+                if (p.act == GVD_ACT_ROUND_SCALE) {
+                    x = bf16r(bf16r(x) * p.alpha);  // einsum output rounded to bf16, then "* scale" in bf16 (attention.py:103)
+                } else {
+                    x *= p.alpha;
+                    if (p.bias != nullptr && n < p.N) x += p.bias[n];
+                    x = apply_act(x, p.act);
+                }
+                if (!p.out_fp32) {
+                    // the reference materialises the layer output in bf16 before any following add: keep those rounding points
+                    if (p.bias2 != nullptr && n < p.N) x = bf16r(x) + p.bias2[n];
+                    if (p.residual != nullptr) x = bf16r(x);
+                }
+                f[j] = x;
             }
             const int n_first = n0 + c;
             const bool full16 = (n_first + 16 <= p.N);
@@ -244,7 +260,7 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 attr: ") + cudaGetErrorString(e); return 1; }
         attr_set = true;
     }
-    EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->residual, a->alpha, a->act, a->out_fp32,
+    EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,
                 a->M, a->N, a->K, a->batch_h};
     dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM, a->batch_h * a->batch_b);
     gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);

@@ -1,0 +1,461 @@
+// nn_kernels.cu -- memory-bound layers of the U-Net denoiser on channels-last bf16 activations, and the fused
+// DDIM update (include/gvd_nn.h).  Activations live in HBM as [frames, pixels, channels] bf16 (channels contiguous =
+// K-major for the tensor-core GEMMs); statistics and softmax are computed in fp32 like the reference under autocast
+// (GroupNormSpecific casts to float, lvdm/basics.py:76-78; softmax/LayerNorm are autocast-to-fp32 ops).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/gvd_nn.h"
+
+extern thread_local std::string g_nn_err_ext;
+
+namespace {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------- GroupNorm (channels-last) ----------------
+// x [F, S, C]; group g = channels [g*cpg, (g+1)*cpg); statistics over S x cpg per (frame, group).
+// Pass 1: grid (chunks, F); each CTA sums a slab of rows; partial (sum, sumsq) per (frame, chunk, group).
+__global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int groups,
+                                                         int rows_per_chunk, float* __restrict__ partial) {
+    extern __shared__ float sh[];  // [groups*2]
+    const int f = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int cpg = C / groups;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int r0 = chunk * rows_per_chunk, r1 = min(S, r0 + rows_per_chunk);
+    const int pairs = C / 2;  // C is even
+    // thread -> fixed channel pair(s), loops over rows: coalesced along C
+    for (int cp = threadIdx.x; cp < pairs; cp += blockDim.x) {
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        const __nv_bfloat162* base = reinterpret_cast<const __nv_bfloat162*>(x + ((size_t)f * S + r0) * C) + cp;
+        for (int r = r0; r < r1; ++r) {
+            const float2 v = __bfloat1622float2(*base);
+            base += pairs;
+            s0 += v.x; q0 += v.x * v.x;
+            s1 += v.y; q1 += v.y * v.y;
+        }
+        const int g0 = (2 * cp) / cpg, g1 = (2 * cp + 1) / cpg;
+        atomicAdd(&sh[2 * g0], s0); atomicAdd(&sh[2 * g0 + 1], q0);
+        atomicAdd(&sh[2 * g1], s1); atomicAdd(&sh[2 * g1 + 1], q1);
+    }
+    __syncthreads();
+    float* out = partial + ((size_t)f * nchunks + chunk) * groups * 2;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = sh[i];
+}
+
+// Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ partial, int S, int C, int groups,
+                                                       int nchunks, int rows_per_cta, float eps, int do_silu) {
+    extern __shared__ float sh[];  // mean[groups], rstd[groups]
+    const int f = blockIdx.y;
+    const int cpg = C / groups;
+    if (threadIdx.x < groups) {
+        double s = 0.0, q = 0.0;
+        for (int c = 0; c < nchunks; ++c) {
+            const float* p = partial + ((size_t)f * nchunks + c) * groups * 2 + 2 * threadIdx.x;
+            s += p[0];
+            q += p[1];
+        }
+        const double n = (double)S * cpg;
+        const double mean = s / n;
+        const double var = fmax(q / n - mean * mean, 0.0);
+        sh[threadIdx.x] = (float)mean;
+        sh[groups + threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
+    const int pairs = C / 2;
+    const size_t total = (size_t)(r1 - r0) * pairs;
+    const __nv_bfloat162* xin = reinterpret_cast<const __nv_bfloat162*>(x + ((size_t)f * S + r0) * C);
+    __nv_bfloat162* yout = reinterpret_cast<__nv_bfloat162*>(y + ((size_t)f * S + r0) * C);
+    for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const int cp = (int)(i % pairs);
+        const int c0 = 2 * cp, c1 = c0 + 1;
+        const int g0 = c0 / cpg, g1 = c1 / cpg;
+        const float2 v = __bfloat1622float2(xin[i]);
+        float a = (v.x - sh[g0]) * sh[groups + g0] * gamma[c0] + beta[c0];
+        float b = (v.y - sh[g1]) * sh[groups + g1] * gamma[c1] + beta[c1];
+        if (do_silu == 1) {  // GroupNormSpecific casts its output to bf16 before nn.SiLU sees it (basics.py:76-78)
+            a = silu(__bfloat162float(__float2bfloat16(a)));
+            b = silu(__bfloat162float(__float2bfloat16(b)));
+        } else if (do_silu == 2) {  // plain nn.GroupNorm returns fp32 under autocast: SiLU in fp32, one rounding at the end
+            a = silu(a);
+            b = silu(b);
+        }
+        yout[i] = __floats2bfloat162_rn(a, b);
+    }
+}
+
+// ---------------- LayerNorm over the last dim (one warp per row) ----------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long long rows, int C, float eps) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const __nv_bfloat162* xin = reinterpret_cast<const __nv_bfloat162*>(x + row * C);
+    const int pairs = C / 2;
+    float s = 0.f;
+    for (int i = lane; i < pairs; i += 32) {
+        const float2 v = __bfloat1622float2(xin[i]);
+        s += v.x + v.y;
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int i = lane; i < pairs; i += 32) {
+        const float2 v = __bfloat1622float2(xin[i]);
+        q += (v.x - mean) * (v.x - mean) + (v.y - mean) * (v.y - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    __nv_bfloat162* yout = reinterpret_cast<__nv_bfloat162*>(y + row * C);
+    for (int i = lane; i < pairs; i += 32) {
+        const float2 v = __bfloat1622float2(xin[i]);
+        yout[i] = __floats2bfloat162_rn((v.x - mean) * rstd * gamma[2 * i] + beta[2 * i],
+                                        (v.y - mean) * rstd * gamma[2 * i + 1] + beta[2 * i + 1]);
+    }
+}
+
+// ---------------- GEGLU: out[r, j] = h[r, j] * gelu(h[r, D + j]) ----------------
+__global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out,
+                                                    long long rows, int D) {
+    const long long pairs = rows * (D / 2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (D / 2);
+        const int j = (int)(i % (D / 2));
+        const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * D);
+        const float2 a = __bfloat1622float2(row[j]);
+        const float2 g = __bfloat1622float2(row[D / 2 + j]);
+        // F.gelu(gate) is materialised in bf16 before the product (attention.py:422-423)
+        const float gx = __bfloat162float(__float2bfloat16(gelu(g.x))), gy = __bfloat162float(__float2bfloat16(gelu(g.y)));
+        reinterpret_cast<__nv_bfloat162*>(out + r * D)[j] = __floats2bfloat162_rn(a.x * gx, a.y * gy);
+    }
+}
+
+// ---------------- row softmax: fp32 scores -> bf16 probabilities (one warp per row) ----------------
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const TIn* __restrict__ x, long long ldx,
+                                                           __nv_bfloat16* __restrict__ y, long long ldy, long long rows,
+                                                           int cols) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const TIn* xr = x + row * ldx;
+    float m = -INFINITY;
+    for (int i = lane; i < cols; i += 32) m = fmaxf(m, ldf(xr + i));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < cols; i += 32) s += __expf(ldf(xr + i) - m);
+    const float inv = 1.0f / warp_sum(s);
+    __nv_bfloat16* yr = y + row * ldy;
+    for (int i = lane; i < cols; i += 32) yr[i] = __float2bfloat16(__expf(ldf(xr + i) - m) * inv);
+    for (int i = cols + lane; i < ldy; i += 32) yr[i] = __float2bfloat16(0.f);  // zero the K padding
+}
+
+// ---------------- im2col for 3x3 convs on [F, H, W, C]; K order = (ky, kx, c) ----------------
+// stride 1|2, pad 1; up=1 reads a nearest-neighbour 2x upsampled view of x (Upsample + conv fused).
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col,
+                                                        int F, int H, int W, int C, int Ho, int Wo, int stride, int up) {
+    const int vec = C / 8;  // 16-byte vectors per pixel
+    const long long total = (long long)F * Ho * Wo * 9 * vec;
+    const int Hin = up ? 2 * H : H, Win = up ? 2 * W : W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec);
+        long long t = i / vec;
+        const int tap = (int)(t % 9);
+        t /= 9;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int f = (int)(t / Ho);
+        int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+            if (up) { iy >>= 1; ix >>= 1; }
+            val = reinterpret_cast<const uint4*>(x + (((size_t)f * H + iy) * W + ix) * C)[v];
+        }
+        reinterpret_cast<uint4*>(col)[i] = val;
+    }
+}
+
+// ---------------- im2col for (3,1,1) temporal convs on [B, T, S, C]; K order = (kt, c) ----------------
+__global__ void __launch_bounds__(256) im2col_t3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col,
+                                                        int B, int T, long long S, int C) {
+    const int vec = C / 8;
+    const long long total = (long long)B * T * S * 3 * vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec);
+        long long t = i / vec;
+        const int tap = (int)(t % 3);
+        t /= 3;
+        const long long s = t % S;
+        t /= S;
+        const int tt = (int)(t % T);
+        const int b = (int)(t / T);
+        const int it = tt + tap - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (it >= 0 && it < T) val = reinterpret_cast<const uint4*>(x + (((size_t)b * T + it) * S + s) * C)[v];
+        reinterpret_cast<uint4*>(col)[i] = val;
+    }
+}
+
+// ---------------- temporal self-attention: sequences of T <= 32 frames per (pixel, head), d = 64 ----------------
+// q,k,v,out: [B, T, S, H*64] bf16. One warp per (b, s, h): lane j owns key/value frame j; queries are broadcast.
+__global__ void __launch_bounds__(256) temporal_attn_kernel(const __nv_bfloat16* __restrict__ q,
+                                                            const __nv_bfloat16* __restrict__ k,
+                                                            const __nv_bfloat16* __restrict__ v,
+                                                            __nv_bfloat16* __restrict__ out, int B, int T, long long S,
+                                                            int H, float scale) {
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long total = (long long)B * S * H;
+    if (w >= total) return;
+    const int lane = threadIdx.x & 31;
+    const int h = (int)(w % H);
+    const long long s = (w / H) % S;
+    const int b = (int)(w / (H * S));
+    const long long tstride = S * H * 64;
+    const size_t base = ((size_t)b * T * S + s) * H * 64 + (size_t)h * 64;
+    // lane j keeps k_j and v_j (64 values each) in registers
+    float kj[64], vj[64];
+    if (lane < T) {
+        const uint4* kp = reinterpret_cast<const uint4*>(k + base + lane * tstride);
+        const uint4* vp = reinterpret_cast<const uint4*>(v + base + lane * tstride);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 kk = kp[c], vv = vp[c];
+            const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
+            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 a = __bfloat1622float2(k2[e]), bb = __bfloat1622float2(v2[e]);
+                kj[c * 8 + 2 * e] = a.x; kj[c * 8 + 2 * e + 1] = a.y;
+                vj[c * 8 + 2 * e] = bb.x; vj[c * 8 + 2 * e + 1] = bb.y;
+            }
+        }
+    }
+    for (int i = 0; i < T; ++i) {
+        // query frame i: lanes 0..31 load two channels each, then broadcast by shuffle
+        const __nv_bfloat162 q2 = reinterpret_cast<const __nv_bfloat162*>(q + base + i * tstride)[lane];
+        const float2 qf = __bfloat1622float2(q2);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float qx = __shfl_sync(0xffffffffu, qf.x, c), qy = __shfl_sync(0xffffffffu, qf.y, c);
+            dot += qx * kj[2 * c] + qy * kj[2 * c + 1];
+        }
+        // the reference rounds sim to the autocast dtype before softmax (einsum output): keep that rounding point
+        float sc = (lane < T) ? __bfloat162float(__float2bfloat16(__bfloat162float(__float2bfloat16(dot)) * scale)) : -INFINITY;
+        const float m = warp_max(sc);
+        const float e = (lane < T) ? __expf(sc - m) : 0.f;
+        const float p = __bfloat162float(__float2bfloat16(e / warp_sum(e)));  // softmax output cast to bf16 for the PV product
+        // out_i[c] = sum_j p_j v_j[c]: lane c' gathers channels 2c', 2c'+1
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float a0 = warp_sum(p * vj[2 * c]), a1 = warp_sum(p * vj[2 * c + 1]);
+            if (lane == c) { o0 = a0; o1 = a1; }
+        }
+        reinterpret_cast<__nv_bfloat162*>(out + base + i * tstride)[lane] = __floats2bfloat162_rn(o0, o1);
+    }
+}
+
+// ---------------- fused DDIM step (ddim.py:206-280, v-prediction, CFG + rescale, dynamic rescale) ----------------
+// pass 1: model_output = e_u + s (e_c - e_u); accumulate sum / sumsq of e_c and of model_output (for the two stds)
+__global__ void __launch_bounds__(256) ddim_cfg_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u,
+                                                       float* __restrict__ mo, long long n, float cfg,
+                                                       double* __restrict__ stats) {
+    double s_c = 0, q_c = 0, s_m = 0, q_m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float c = e_c[i], u = e_u[i];
+        const float m = u + cfg * (c - u);
+        mo[i] = m;
+        s_c += c; q_c += (double)c * c;
+        s_m += m; q_m += (double)m * m;
+    }
+    __shared__ double sh[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_c += __shfl_xor_sync(0xffffffffu, s_c, o); q_c += __shfl_xor_sync(0xffffffffu, q_c, o);
+        s_m += __shfl_xor_sync(0xffffffffu, s_m, o); q_m += __shfl_xor_sync(0xffffffffu, q_m, o);
+    }
+    if (lane == 0) { sh[0][warp] = s_c; sh[1][warp] = q_c; sh[2][warp] = s_m; sh[3][warp] = q_m; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w2 = 0; w2 < 8; ++w2) t += sh[threadIdx.x][w2];
+        atomicAdd(&stats[threadIdx.x], t);
+    }
+}
+
+struct DdimCoef {
+    float guidance_rescale, sqrt_ac, sqrt_1mac, a_prev_sqrt, dir_coef, sigma, scale_ratio;
+    int use_rescale;
+};
+
+__global__ void __launch_bounds__(256) ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ mo,
+                                                          const float* __restrict__ noise, float* __restrict__ x_prev,
+                                                          float* __restrict__ pred_x0, long long n, DdimCoef c,
+                                                          const double* __restrict__ stats) {
+    float factor = 1.0f;
+    if (c.guidance_rescale > 0.f) {
+        // torch.std default: unbiased (N-1)
+        const double nn = (double)n;
+        const double var_c = (stats[1] - stats[0] * stats[0] / nn) / (nn - 1.0);
+        const double var_m = (stats[3] - stats[2] * stats[2] / nn) / (nn - 1.0);
+        const float ratio = (float)sqrt(var_c) / (float)sqrt(var_m);
+        factor = c.guidance_rescale * ratio + (1.0f - c.guidance_rescale);  // gr*(m*ratio) + (1-gr)*m
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float xt = x[i];
+        float v = mo[i];
+        if (c.guidance_rescale > 0.f) {
+            const float r = v * (factor - (1.0f - c.guidance_rescale)) / c.guidance_rescale;  // v * ratio
+            v = c.guidance_rescale * r + (1.0f - c.guidance_rescale) * v;
+        }
+        const float e_t = c.sqrt_ac * v + c.sqrt_1mac * xt;        // predict_eps_from_z_and_v (ddpm3d.py:247-251)
+        float p0 = c.sqrt_ac * xt - c.sqrt_1mac * v;                // predict_start_from_z_and_v (ddpm3d.py:239-245)
+        if (c.use_rescale) p0 *= c.scale_ratio;
+        pred_x0[i] = p0;
+        x_prev[i] = c.a_prev_sqrt * p0 + c.dir_coef * e_t + c.sigma * noise[i];
+    }
+}
+
+int grid_for(long long n, int block = 256, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* beta, int F, long long S, int C, int groups,
+                     float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (F <= 0 || S <= 0) return 0;
+    if (C % groups != 0 || C % 2 != 0 || groups > 256) { g_nn_err_ext = "gvd_groupnorm_cl: bad channel/group count"; return 2; }
+    int nchunks = (int)((S + 1023) / 1024);
+    if (nchunks > 512) nchunks = 512;
+    const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
+    nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
+    if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
+    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(float), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
+                                                                                 rows_per_chunk, tmp);
+    const int rows_per_cta = 64;
+    gn_apply_kernel<<<dim3((unsigned)((S + rows_per_cta - 1) / rows_per_cta), F), 256, groups * 2 * sizeof(float), s>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups, nchunks, rows_per_cta, eps, do_silu);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+size_t gvd_groupnorm_tmp_floats(int F, long long S, int groups) {
+    int nchunks = (int)((S + 1023) / 1024);
+    if (nchunks > 512) nchunks = 512;
+    return (size_t)F * (nchunks + 1) * groups * 2;
+}
+
+int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
+                  gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (rows <= 0) return 0;
+    if (C % 2) { g_nn_err_ext = "gvd_layernorm: C must be even"; return 2; }
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, rows, C, eps);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_geglu(const void* h, void* out, long long rows, int D, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (rows <= 0) return 0;
+    if (D % 2) { g_nn_err_ext = "gvd_geglu: D must be even"; return 2; }
+    geglu_kernel<<<grid_for(rows * (D / 2)), 256, 0, s>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)out, rows, D);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_softmax_rows(const void* x, int x_is_bf16, long long ldx, void* y, long long ldy, long long rows, int cols,
+                     gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (rows <= 0) return 0;
+    if (x_is_bf16)
+        softmax_rows_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, rows, cols);
+    else
+        softmax_rows_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const float*)x, ldx, (__nv_bfloat16*)y, ldy, rows, cols);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_im2col3x3_cl(const void* x, void* col, int F, int H, int W, int C, int stride, int upsample, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (C % 8) { g_nn_err_ext = "gvd_im2col3x3_cl: C must be a multiple of 8"; return 2; }
+    const int Hin = upsample ? 2 * H : H, Win = upsample ? 2 * W : W;
+    const int Ho = (Hin + 2 - 3) / stride + 1, Wo = (Win + 2 - 3) / stride + 1;
+    const long long total = (long long)F * Ho * Wo * 9 * (C / 8);
+    if (total <= 0) return 0;
+    im2col3x3_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, F, H, W, C, Ho, Wo, stride, upsample);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long long S, int C, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (C % 8) { g_nn_err_ext = "gvd_im2col_t3_cl: C must be a multiple of 8"; return 2; }
+    const long long total = (long long)B * T * S * 3 * (C / 8);
+    if (total <= 0) return 0;
+    im2col_t3_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, B, T, S, C);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S, int H,
+                           float scale, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (T > 32 || T <= 0) { g_nn_err_ext = "gvd_temporal_attention: needs 1 <= T <= 32"; return 2; }
+    const long long warps = (long long)B * S * H;
+    if (warps <= 0) return 0;
+    temporal_attn_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                                    (const __nv_bfloat16*)v, (__nv_bfloat16*)out, B, T, S, H, scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_ddim_step(const GvdDdimArgs* a, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->x || !a->e_cond || !a->x_prev || !a->pred_x0 || !a->noise || !a->scratch) { g_nn_err_ext = "gvd_ddim_step: null pointer"; return 2; }
+    const long long n = a->n;
+    if (n <= 0) return 0;
+    double* stats = reinterpret_cast<double*>(a->scratch);
+    float* mo = reinterpret_cast<float*>(stats + 4);
+    cudaMemsetAsync(stats, 0, 4 * sizeof(double), s);
+    const float* e_u = a->e_uncond ? a->e_uncond : a->e_cond;
+    const float cfg = a->e_uncond ? a->cfg_scale : 1.0f;
+    ddim_cfg_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(a->e_cond, e_u, mo, n, cfg, stats);
+    DdimCoef c;
+    c.guidance_rescale = a->e_uncond ? a->guidance_rescale : 0.f;
+    c.sqrt_ac = a->sqrt_alphas_cumprod_t;
+    c.sqrt_1mac = a->sqrt_one_minus_alphas_cumprod_t;
+    c.a_prev_sqrt = sqrtf(a->ddim_alpha_prev);
+    c.dir_coef = sqrtf(1.0f - a->ddim_alpha_prev - a->ddim_sigma * a->ddim_sigma);
+    c.sigma = a->ddim_sigma * a->temperature;
+    c.scale_ratio = a->scale_prev / a->scale_t;
+    c.use_rescale = a->use_dynamic_rescale;
+    ddim_update_kernel<<<grid_for(n), 256, 0, s>>>(a->x, mo, a->noise, a->x_prev, a->pred_x0, n, c, stats);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // extern "C"

@@ -147,11 +147,25 @@ class GemmArgs(C.Structure):
         ("A", C.c_void_p), ("lda", C.c_longlong), ("a_stride_h", C.c_longlong), ("a_stride_b", C.c_longlong),
         ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_stride_h", C.c_longlong), ("b_stride_b", C.c_longlong),
         ("C", C.c_void_p), ("ldc", C.c_longlong), ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
-        ("bias", C.c_void_p), ("residual", C.c_void_p), ("alpha", C.c_float), ("act", C.c_int), ("out_fp32", C.c_int),
+        ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("alpha", C.c_float), ("act", C.c_int),
+        ("out_fp32", C.c_int),
     ]
 
 
-NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error")
+class DdimArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_longlong), ("x", C.c_void_p), ("e_cond", C.c_void_p), ("e_uncond", C.c_void_p), ("noise", C.c_void_p),
+        ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p), ("scratch", C.c_void_p),
+        ("cfg_scale", C.c_float), ("guidance_rescale", C.c_float),
+        ("sqrt_alphas_cumprod_t", C.c_float), ("sqrt_one_minus_alphas_cumprod_t", C.c_float),
+        ("ddim_alpha_prev", C.c_float), ("ddim_sigma", C.c_float), ("temperature", C.c_float),
+        ("scale_t", C.c_float), ("scale_prev", C.c_float), ("use_dynamic_rescale", C.c_int),
+    ]
+
+
+NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", "gvd_groupnorm_cl", "gvd_layernorm",
+              "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention",
+              "gvd_ddim_step")
 _nn = None
 
 
@@ -167,5 +181,19 @@ def nn():
     lib.gvd_nn_last_error.restype = C.c_char_p
     lib.gvd_gemm_bf16.restype = C.c_int
     lib.gvd_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+    lib.gvd_groupnorm_tmp_floats.restype = C.c_size_t
+    lib.gvd_groupnorm_tmp_floats.argtypes = [i32, ll, i32]
+    lib.gvd_groupnorm_cl.argtypes = [vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    lib.gvd_layernorm.argtypes = [vp, vp, vp, vp, ll, i32, f32, vp]
+    lib.gvd_geglu.argtypes = [vp, vp, ll, i32, vp]
+    lib.gvd_softmax_rows.argtypes = [vp, i32, ll, vp, ll, ll, i32, vp]
+    lib.gvd_im2col3x3_cl.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.gvd_im2col_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
+    lib.gvd_temporal_attention.argtypes = [vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
+    lib.gvd_ddim_step.argtypes = [C.POINTER(DdimArgs), vp]
+    for n in ("gvd_groupnorm_cl", "gvd_layernorm", "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl",
+              "gvd_temporal_attention", "gvd_ddim_step"):
+        getattr(lib, n).restype = C.c_int
     _nn = lib
     return lib

@@ -1,4 +1,12 @@
-"""Operator-level Python bindings of include/gvd_nn.h (torch is used only for memory and streams)."""
+"""Operator-level Python bindings of include/gvd_nn.h.
+
+torch is used for device memory, streams and pure layout plumbing (views, one head-transpose of V); every
+arithmetic operator of the denoiser goes through the sm_100a library.  There is no fallback path: a missing
+library raises in gvd_native.nn().
+
+Activation layout: channels-last bf16, x[F, S, C] with F = batch*frames, S = h*w pixels, C channels (the K-major
+operand layout of the tensor-core GEMM).
+"""
 import ctypes as C
 import os
 import sys
@@ -10,7 +18,8 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 import gvd_native as _n  # noqa: E402
 
-ACT = {"none": 0, "silu": 1, "gelu": 2}
+ACT = {"none": 0, "silu": 1, "gelu": 2, "round_scale": 3}
+BF16 = torch.bfloat16
 
 
 def _stream():
@@ -22,25 +31,28 @@ def _check(rc, lib, what):
         raise RuntimeError(f"{what} failed: " + (lib.gvd_nn_last_error() or b"").decode())
 
 
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
 def gemm_raw(A, B, Cout, M, N, K, lda, ldb, ldc, batch_h=1, batch_b=1, a_strides=(0, 0), b_strides=(0, 0),
-             c_strides=(0, 0), bias=None, residual=None, alpha=1.0, act="none"):
-    """C[b,h,m,n] = act(alpha * sum_k A[b,h,m,k] B[b,h,n,k] + bias[n]) + residual; strides in elements."""
+             c_strides=(0, 0), bias=None, bias2=None, residual=None, alpha=1.0, act="none"):
+    """C[b,h,m,n] = act(alpha * sum_k A[b,h,m,k] B[b,h,n,k] + bias[n]) (+ bias2[n]) + residual; strides in elements."""
     lib = _n.nn()
     a = _n.GemmArgs()
     a.M, a.N, a.K, a.batch_h, a.batch_b = int(M), int(N), int(K), int(batch_h), int(batch_b)
     a.A, a.lda, a.a_stride_h, a.a_stride_b = A.data_ptr(), int(lda), int(a_strides[0]), int(a_strides[1])
     a.B, a.ldb, a.b_stride_h, a.b_stride_b = B.data_ptr(), int(ldb), int(b_strides[0]), int(b_strides[1])
     a.C, a.ldc, a.c_stride_h, a.c_stride_b = Cout.data_ptr(), int(ldc), int(c_strides[0]), int(c_strides[1])
-    a.bias = bias.data_ptr() if bias is not None else None
-    a.residual = residual.data_ptr() if residual is not None else None
+    a.bias, a.bias2, a.residual = _p(bias), _p(bias2), _p(residual)
     a.alpha, a.act, a.out_fp32 = float(alpha), ACT[act], int(Cout.dtype == torch.float32)
     with torch.cuda.device(A.device):
         _check(lib.gvd_gemm_bf16(C.byref(a), _stream()), lib, "gvd_gemm_bf16")
     return Cout
 
 
-def linear(x, weight, bias=None, act="none", residual=None, out_dtype=torch.bfloat16, alpha=1.0):
-    """y = act(x @ weight^T + bias) + residual.  x [..., K] bf16 contiguous, weight [N, K] bf16, bias fp32 [N]."""
+def linear(x, weight, bias=None, act="none", residual=None, out_dtype=BF16, alpha=1.0, bias2=None):
+    """y = act(x @ weight^T + bias) (+ bias2) + residual.  x [..., K] bf16, weight [N, K] bf16, biases fp32 [N]."""
     K = x.shape[-1]
     N = weight.shape[0]
     x2 = x.reshape(-1, K)
@@ -49,5 +61,144 @@ def linear(x, weight, bias=None, act="none", residual=None, out_dtype=torch.bflo
     M = x2.shape[0]
     out = torch.empty(M, N, dtype=out_dtype, device=x.device)
     res2 = residual.reshape(M, N) if residual is not None else None
-    gemm_raw(x2, weight, out, M, N, K, K, K, N, bias=bias, residual=res2, alpha=alpha, act=act)
+    gemm_raw(x2, weight, out, M, N, K, K, K, N, bias=bias, bias2=bias2, residual=res2, alpha=alpha, act=act)
     return out.reshape(*x.shape[:-1], N)
+
+
+_gn_tmp = {}
+
+
+def groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
+    """x viewed as [F, S, C] channels-last bf16; statistics over S x (C/groups)."""
+    lib = _n.nn()
+    Cc = x.shape[-1]
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    nfl = int(lib.gvd_groupnorm_tmp_floats(int(F), int(S), int(groups)))
+    key = (x.device, nfl)
+    tmp = _gn_tmp.get(key)
+    if tmp is None:
+        tmp = _gn_tmp[key] = torch.empty(nfl, dtype=torch.float32, device=x.device)
+    _check(lib.gvd_groupnorm_cl(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(F), int(S), int(Cc),
+                                int(groups), float(eps), int(silu), tmp.data_ptr(), nfl, _stream()), lib, "gvd_groupnorm_cl")
+    return y
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    lib = _n.nn()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    Cc = x.shape[-1]
+    _check(lib.gvd_layernorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), x.numel() // Cc, int(Cc),
+                             float(eps), _stream()), lib, "gvd_layernorm")
+    return y
+
+
+def geglu(h):
+    lib = _n.nn()
+    D = h.shape[-1] // 2
+    h = h.contiguous()
+    out = torch.empty(*h.shape[:-1], D, dtype=BF16, device=h.device)
+    _check(lib.gvd_geglu(h.data_ptr(), out.data_ptr(), h.numel() // (2 * D), int(D), _stream()), lib, "gvd_geglu")
+    return out
+
+
+def softmax_rows(scores, cols, ldy):
+    """scores [rows, ld] (bf16 or fp32, contiguous) -> bf16 probabilities [rows, ldy] (columns >= cols zeroed)."""
+    lib = _n.nn()
+    rows = scores.numel() // scores.shape[-1]
+    out = torch.empty(*scores.shape[:-1], ldy, dtype=BF16, device=scores.device)
+    _check(lib.gvd_softmax_rows(scores.data_ptr(), int(scores.dtype == BF16), int(scores.shape[-1]), out.data_ptr(), int(ldy),
+                                int(rows), int(cols), _stream()), lib, "gvd_softmax_rows")
+    return out
+
+
+def conv3x3(x, F, H, W, weight, bias=None, stride=1, upsample=False, bias2=None, residual=None, act="none"):
+    """3x3 / pad 1 convolution of channels-last x[F, H*W, Cin] with weight [Cout, 9*Cin] (K order ky, kx, cin)."""
+    lib = _n.nn()
+    Cin = x.shape[-1]
+    Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
+    Ho, Wo = (Hin + 2 - 3) // stride + 1, (Win + 2 - 3) // stride + 1
+    col = torch.empty(F * Ho * Wo, 9 * Cin, dtype=BF16, device=x.device)
+    _check(lib.gvd_im2col3x3_cl(x.data_ptr(), col.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),
+                                _stream()), lib, "gvd_im2col3x3_cl")
+    y = linear(col, weight, bias=bias, bias2=bias2, residual=residual, act=act)
+    return y.view(F, Ho * Wo, -1), Ho, Wo
+
+
+def conv_t3(x, B, T, S, weight, bias=None, residual=None):
+    """(3,1,1) / pad (1,0,0) temporal convolution of x[B*T, S, C] with weight [Cout, 3*Cin] (K order kt, cin)."""
+    lib = _n.nn()
+    Cin = x.shape[-1]
+    col = torch.empty(B * T * S, 3 * Cin, dtype=BF16, device=x.device)
+    _check(lib.gvd_im2col_t3_cl(x.data_ptr(), col.data_ptr(), int(B), int(T), int(S), int(Cin), _stream()), lib,
+           "gvd_im2col_t3_cl")
+    return linear(col, weight, bias=bias, residual=residual).view(B * T, S, -1)
+
+
+def temporal_attention(q, k, v, B, T, S, H, scale):
+    lib = _n.nn()
+    out = torch.empty_like(q)
+    _check(lib.gvd_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), int(B), int(T), int(S), int(H),
+                                      float(scale), _stream()), lib, "gvd_temporal_attention")
+    return out
+
+
+def attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False, max_score_bytes=6 << 30):
+    """softmax(q k^T * scale) v with head dim 64.
+    q [Bq, Nq, H*64]; k, v [Bq, Nk, H*64] (or [1, Nk, H*64] when shared_kv: the same keys for every batch item, then
+    the batch is folded into the query rows).  Scores are materialised in bf16 (rounded exactly where the reference
+    rounds them) one chunk of batch items at a time, probabilities feed the PV product as bf16."""
+    D = 64
+    HD = H * D
+    dev = q.device
+    out = torch.empty(Bq, Nq, HD, dtype=BF16, device=dev)
+    Nkp = (Nk + 7) // 8 * 8
+    if shared_kv:
+        # V^T per head, zero-padded along the key axis: [H, 64, Nkp]
+        vt = torch.zeros(H, D, Nkp, dtype=BF16, device=dev)
+        vt[:, :, :Nk] = v.view(Nk, H, D).permute(1, 2, 0)
+        rows_total = Bq * Nq
+        rows_chunk = max(128, min(rows_total, max_score_bytes // (H * Nkp * 2) // 128 * 128))
+        q2 = q.view(rows_total, HD)
+        o2 = out.view(rows_total, HD)
+        for r0 in range(0, rows_total, rows_chunk):
+            m = min(rows_chunk, rows_total - r0)
+            sim = torch.empty(H, m, Nkp, dtype=BF16, device=dev)
+            gemm_raw(q2[r0:], k, sim, m, Nk, D, HD, HD, Nkp, batch_h=H, a_strides=(D, 0), b_strides=(D, 0),
+                     c_strides=(m * Nkp, 0), alpha=scale, act="round_scale")
+            p = softmax_rows(sim, Nk, Nkp)
+            gemm_raw(p, vt, o2[r0:], m, D, Nkp, Nkp, Nkp, HD, batch_h=H, a_strides=(m * Nkp, 0), b_strides=(D * Nkp, 0),
+                     c_strides=(D, 0))
+        return out
+    bchunk = max(1, min(Bq, max_score_bytes // (H * Nq * Nkp * 2)))
+    for b0 in range(0, Bq, bchunk):
+        nb = min(bchunk, Bq - b0)
+        vt = torch.zeros(nb, H, D, Nkp, dtype=BF16, device=dev)
+        vt[..., :Nk] = v[b0:b0 + nb].view(nb, Nk, H, D).permute(0, 2, 3, 1)
+        sim = torch.empty(nb, H, Nq, Nkp, dtype=BF16, device=dev)
+        gemm_raw(q[b0:], k[b0:], sim, Nq, Nk, D, HD, HD, Nkp, batch_h=H, batch_b=nb, a_strides=(D, Nq * HD),
+                 b_strides=(D, Nk * HD), c_strides=(Nq * Nkp, H * Nq * Nkp), alpha=scale, act="round_scale")
+        p = softmax_rows(sim, Nk, Nkp)
+        gemm_raw(p, vt, out[b0:], Nq, D, Nkp, Nkp, Nkp, HD, batch_h=H, batch_b=nb, a_strides=(Nq * Nkp, H * Nq * Nkp),
+                 b_strides=(D * Nkp, H * D * Nkp), c_strides=(D, Nq * HD))
+    return out
+
+
+def ddim_step(x, e_cond, e_uncond, noise, coef):
+    """Fused DDIM update; all tensors fp32, same shape. coef: dict from vc_b200.sampler. Returns (x_prev, pred_x0)."""
+    lib = _n.nn()
+    n = x.numel()
+    x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+    scratch = torch.empty(32 + 4 * n, dtype=torch.uint8, device=x.device)
+    a = _n.DdimArgs()
+    a.n = n
+    a.x, a.e_cond, a.e_uncond, a.noise = x.data_ptr(), e_cond.data_ptr(), _p(e_uncond), noise.data_ptr()
+    a.x_prev, a.pred_x0, a.scratch = x_prev.data_ptr(), pred_x0.data_ptr(), scratch.data_ptr()
+    for k in ("cfg_scale", "guidance_rescale", "sqrt_alphas_cumprod_t", "sqrt_one_minus_alphas_cumprod_t", "ddim_alpha_prev",
+              "ddim_sigma", "temperature", "scale_t", "scale_prev"):
+        setattr(a, k, float(coef[k]))
+    a.use_dynamic_rescale = int(coef["use_dynamic_rescale"])
+    with torch.cuda.device(x.device):
+        _check(lib.gvd_ddim_step(C.byref(a), _stream()), lib, "gvd_ddim_step")
+    return x_prev, pred_x0

@@ -25,10 +25,13 @@ extern "C" {
 
 typedef struct CUstream_st* gvd_nn_stream_t; /* == cudaStream_t */
 
-enum { GVD_ACT_NONE = 0, GVD_ACT_SILU = 1, GVD_ACT_GELU = 2 };
+enum {
+    GVD_ACT_NONE = 0, GVD_ACT_SILU = 1, GVD_ACT_GELU = 2,
+    GVD_ACT_ROUND_SCALE = 3 /* C = bf16(bf16(acc) * alpha): the rounding points of `einsum(q,k) * scale` under autocast */
+};
 
 /* Strided-batched bf16 GEMM on tcgen05 tensor cores (fp32 accumulation in TMEM):
- *     C[b,h,m,n] = act( alpha * sum_k A[b,h,m,k] * B[b,h,n,k] + bias[n] ) + residual[b,h,m,n]
+ *     C[b,h,m,n] = act( alpha * sum_k A[b,h,m,k] * B[b,h,n,k] + bias[n] ) (+ bias2[n]) + residual[b,h,m,n]
  * A and B are K-major (k contiguous); every row/batch stride is in ELEMENTS and must be a multiple of 8.
  * Serves nn.Linear / 1x1 conv / im2col'ed 3x3 and (3,1,1) convs (openaimodel3d.py:155-236,255-279), the
  * q/k/v/out projections, GEGLU/FF linears and the QK^T / PV products of CrossAttention (attention.py:81-144). */
@@ -39,12 +42,72 @@ typedef struct GvdGemmArgs {
     const void* B; long long ldb, b_stride_h, b_stride_b;   /* bf16 */
     void* C;       long long ldc, c_stride_h, c_stride_b;   /* bf16, or fp32 when out_fp32 */
     const float* bias;                 /* [N] fp32 or NULL */
-    const void* residual;              /* same layout/dtype as C, or NULL */
+    const float* bias2;                /* [N] fp32 or NULL: added AFTER the bf16 rounding of the layer output
+                                          (ResBlock `h + emb_out`, openaimodel3d.py:228) */
+    const void* residual;              /* same layout/dtype as C, or NULL; added after bf16 rounding as well */
     float alpha;
     int act;                           /* GVD_ACT_* applied before the residual add */
     int out_fp32;
 } GvdGemmArgs;
 GVD_NN_API int gvd_gemm_bf16(const GvdGemmArgs* args, gvd_nn_stream_t stream);
+
+/* GroupNorm(groups) [+ SiLU] on channels-last activations x[F, S, C] (bf16 in/out, fp32 statistics over S x C/groups
+ * per (frame, group)).  Serves normalization()/nn.GroupNorm(32) in ResBlock.in_layers/out_layers
+ * (openaimodel3d.py:155-181; per frame: F = b*t, S = h*w), TemporalConvBlock (openaimodel3d.py:255-266; statistics
+ * span t*h*w: F = b, S = t*h*w) and the Spatial/TemporalTransformer input norms (attention.py:268,331).
+ * do_silu: 0 = none, 1 = SiLU applied to the bf16-rounded norm output (GroupNormSpecific semantics),
+ *          2 = SiLU in fp32 before the single bf16 rounding (plain nn.GroupNorm under autocast).
+ * tmp: gvd_groupnorm_tmp_floats(F, S, groups) floats of scratch. */
+GVD_NN_API size_t gvd_groupnorm_tmp_floats(int F, long long S, int groups);
+GVD_NN_API int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* beta, int F, long long S, int C,
+                                int groups, float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream);
+
+/* LayerNorm over the last dimension of x[rows, C] (bf16 in/out) -- BasicTransformerBlock.norm1/2/3 (attention.py:236-238). */
+GVD_NN_API int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
+                             gvd_nn_stream_t stream);
+
+/* GEGLU gate: out[r, j] = h[r, j] * gelu(h[r, D + j]), h[rows, 2D] bf16 (attention.py:415-423). */
+GVD_NN_API int gvd_geglu(const void* h, void* out, long long rows, int D, gvd_nn_stream_t stream);
+
+/* Row softmax of fp32 or bf16 scores x[rows, ldx] (first `cols` columns) into bf16 probabilities y[rows, ldy]; columns
+ * cols..ldy-1 of y are zeroed so y can feed the PV GEMM with K = ldy (attention.py:118,138). */
+GVD_NN_API int gvd_softmax_rows(const void* x, int x_is_bf16, long long ldx, void* y, long long ldy, long long rows,
+                                int cols, gvd_nn_stream_t stream);
+
+/* im2col for 3x3 / pad 1 convolutions on x[F, H, W, C] bf16 -> col[F, Ho, Wo, 9*C] with K order (ky, kx, c).
+ * stride 1 or 2 (Downsample, openaimodel3d.py:61-75); upsample=1 convolves the nearest-neighbour 2x upsampling of x
+ * without materialising it (Upsample, openaimodel3d.py:88-103). */
+GVD_NN_API int gvd_im2col3x3_cl(const void* x, void* col, int F, int H, int W, int C, int stride, int upsample,
+                                gvd_nn_stream_t stream);
+
+/* im2col for the (3,1,1) / pad (1,0,0) temporal convolutions on x[B, T, S, C] -> col[B, T, S, 3*C], K order (kt, c)
+ * (TemporalConvBlock, openaimodel3d.py:246-266). */
+GVD_NN_API int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long long S, int C, gvd_nn_stream_t stream);
+
+/* Temporal self-attention over T <= 32 frames per (pixel, head), head dim 64: q,k,v,out [B, T, S, H*64] bf16
+ * (CrossAttention inside TemporalTransformer, attention.py:365-412 with '(b h w) t c' sequences). */
+GVD_NN_API int gvd_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S,
+                                      int H, float scale, gvd_nn_stream_t stream);
+
+/* One DDIM update, fused (lvdm/models/samplers/ddim.py:206-280 with v-prediction, classifier-free guidance,
+ * rescale_noise_cfg (utils_diffusion.py:147-158) and dynamic rescale).  All tensors fp32 with n elements (one batch
+ * item); e_uncond may be NULL (no guidance).  scratch: 32 + 4*n bytes. */
+typedef struct GvdDdimArgs {
+    long long n;
+    const float* x;          /* x_t                                       */
+    const float* e_cond;     /* model output with conditioning             */
+    const float* e_uncond;   /* model output with unconditional cond, or NULL */
+    const float* noise;      /* N(0,1) noise for this step                 */
+    float* x_prev;           /* out                                        */
+    float* pred_x0;          /* out                                        */
+    void* scratch;
+    float cfg_scale, guidance_rescale;
+    float sqrt_alphas_cumprod_t, sqrt_one_minus_alphas_cumprod_t;   /* model schedule at timestep t */
+    float ddim_alpha_prev, ddim_sigma, temperature;                 /* DDIM schedule at this index  */
+    float scale_t, scale_prev;
+    int use_dynamic_rescale;
+} GvdDdimArgs;
+GVD_NN_API int gvd_ddim_step(const GvdDdimArgs* args, gvd_nn_stream_t stream);
 
 GVD_NN_API const char* gvd_nn_last_error(void);
 

@@ -96,8 +96,32 @@ def build_knn():
     return True
 
 
+def build_vc():
+    """Install (copy) the pure-python ViewCrafter denoiser/sampler modules the parity tests import on the GPU box:
+    lvdm/{basics,common}.py, lvdm/modules/{attention.py,networks/openaimodel3d.py},
+    lvdm/models/{utils_diffusion.py,samplers/*.py}, utils_vc/diffusion_utils.py.  They need torch, einops, cv2, tqdm."""
+    src = os.path.join(REF, "third_party", "ViewCrafter")
+    if not os.path.isdir(src):
+        print("reference not present, skip vc")
+        return False
+    dst = os.path.join(OUT, "ViewCrafter")
+    # utils_vc/diffusion_utils.py is pulled in by lvdm/basics.py (instantiate_from_config) and itself imports the
+    # three sampler modules
+    for rel in ("lvdm/basics.py", "lvdm/common.py", "lvdm/modules/attention.py", "lvdm/modules/networks/openaimodel3d.py",
+                "lvdm/models/utils_diffusion.py", "lvdm/models/samplers/ddim.py", "lvdm/models/samplers/ddim_guidance.py",
+                "lvdm/models/samplers/ddim_multiplecond.py", "utils_vc/diffusion_utils.py"):
+        d = os.path.join(dst, rel)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        if os.path.exists(d):
+            os.chmod(d, 0o644)
+        shutil.copyfile(os.path.join(src, rel), d)
+        os.chmod(d, 0o644)
+    print("installed", dst)
+    return True
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dgr", "knn"]
+    which = sys.argv[1:] or ["dgr", "knn", "vc"]
     if len(which) > 1:
         # one process per extension: torch's JIT loader renames a second "_C" built in the
         # same process to "_C_v1", which the packages' `from . import _C` would not find.
@@ -109,3 +133,5 @@ if __name__ == "__main__":
         build_dgr()
     elif which[0] == "knn":
         build_knn()
+    elif which[0] == "vc":
+        build_vc()
