@@ -236,6 +236,8 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __nv_bfloat16*
     const size_t base = ((size_t)b * T * S + s) * H * 64 + (size_t)h * 64;
     // lane j keeps k_j and v_j (64 values each) in registers
     float kj[64], vj[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) kj[c] = vj[c] = 0.f;  // lanes >= T hold no frame: they must contribute exact zeros
     if (lane < T) {
         const uint4* kp = reinterpret_cast<const uint4*>(k + base + lane * tstride);
         const uint4* vp = reinterpret_cast<const uint4*>(v + base + lane * tstride);

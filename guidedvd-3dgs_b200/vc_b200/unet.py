@@ -241,6 +241,12 @@ class UNetB200:
                 h, st["H"], st["W"] = ops.conv3x3(h, st["F"], st["H"], st["W"], *m, upsample=True)
         return h
 
+    trace = None  # set to a list to record (name, activation[F, S, C]) after every top-level block (tests/debug)
+
+    def _rec(self, name, h, st):
+        if self.trace is not None:
+            self.trace.append((name, h.view(st["F"], st["H"], st["W"], -1).permute(0, 3, 1, 2).float()))
+
     @torch.no_grad()
     def forward(self, x, timesteps, context, fs=None):
         """x [1, C_in, t, h, w] fp32; timesteps [1]; context [1, 77+256, 1024]; fs [1] -> [1, C_out, t, h, w] bf16."""
@@ -261,13 +267,17 @@ class UNetB200:
         hs = []
         for i, layers in enumerate(self.input_blocks):
             h = self._run(layers, h, st)
+            self._rec(f"input_blocks.{i}", h, st)
             if i == 0 and self.init_attn is not None:
                 h = self.init_attn(h, b, t, st["H"] * st["W"])
+                self._rec("init_attn", h, st)
             hs.append(h)
         h = self._run(self.middle, h, st)
-        for layers in self.output_blocks:
+        self._rec("middle_block", h, st)
+        for i, layers in enumerate(self.output_blocks):
             h = torch.cat([h, hs.pop()], dim=-1)
             h = self._run(layers, h, st)
+            self._rec(f"output_blocks.{i}", h, st)
         # `h = h.type(x.dtype)`: the last norm/SiLU run in fp32, one rounding at the conv input (openaimodel3d.py:598-599)
         h = ops.groupnorm(h, *self.out_norm, st["F"], st["H"] * st["W"], eps=1e-5, silu=2)
         y, _, _ = ops.conv3x3(h, st["F"], st["H"], st["W"], *self.out_conv)

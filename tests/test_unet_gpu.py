@@ -1,10 +1,12 @@
 """GPU parity of the B200-native denoiser against the reference UNetModel run on the same GPU under
 torch.autocast(bfloat16) with identical seeded weights and inputs.
 
-Bar: <= 1e-3 relative on the denoiser output is the north-star; in bf16 two implementations that round at the same
-points but accumulate in different orders (tcgen05 vs cuBLAS/cuDNN) differ by a few bf16 ulps per layer, so the test
-states what is measured: relative L2 error of the output <= 1e-2, and it must not exceed 2x the reference's own
-sensitivity to accumulation order (reference with TF32-free fp32 matmuls vs the autocast run)."""
+The north-star asks for <= 1e-3 relative on latents.  That bar is below the bf16 noise floor of the network itself:
+the REFERENCE run under bf16 autocast differs from the REFERENCE run in fp32 by ~2e-2 relative L2 on these inputs
+(measured below, printed by the test), because ~150 layers each round to 8 mantissa bits and cuDNN/cuBLAS pick
+Winograd/split-K algorithms with their own rounding.  The test therefore states and enforces what can be true:
+  (1) ours is at least as close to the fp32 ground truth as the reference's own bf16 run (<= 1.15x + 1e-3), and
+  (2) ours vs the reference bf16 run stays within the combined noise of the two (<= 1.5 * hypot of the two errors)."""
 import pytest
 import torch
 
@@ -38,5 +40,5 @@ def test_unet_small_vs_reference(mc, t, h, w):
     e_ours, e_ref = _rel(y, y_fp32), _rel(y_ref, y_fp32)
     e_pair = _rel(y, y_ref)
     print(f"rel L2: ours vs fp32 {e_ours:.3e}, ref-bf16 vs fp32 {e_ref:.3e}, ours vs ref-bf16 {e_pair:.3e}")
-    assert e_pair <= 1e-2
-    assert e_ours <= 2.0 * e_ref + 1e-3
+    assert e_ours <= 1.15 * e_ref + 1e-3
+    assert e_pair <= 1.5 * (e_ours ** 2 + e_ref ** 2) ** 0.5
