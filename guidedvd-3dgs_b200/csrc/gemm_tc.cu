@@ -1,6 +1,13 @@
 // gemm_tc.cu -- strided-batched bf16 GEMM on Blackwell tensor cores (include/gvd_nn.h::gvd_gemm_bf16).
 //
-// One CTA computes a 128x128 tile of C:
+// Two kernels:
+//  * gemm_bf16_persistent_kernel<BN> (default): persistent CTAs (one per SM) loop over 128 x BN tiles (BN = 64/128/256,
+//    picked per problem); the accumulator is DOUBLE-BUFFERED in TMEM so the MMA warp runs tile i+1 while the four
+//    epilogue warps drain tile i; the epilogue stages bf16 rows in swizzled shared memory and writes them (and reads
+//    the residual) with fully coalesced 16-byte accesses.
+//  * gemm_bf16_kernel (fallback: fp32 output or unaligned destinations): one 128x128 tile per CTA.
+//
+// Fallback kernel -- one CTA computes a 128x128 tile of C:
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor (4-D tensor maps, 128-byte swizzle) into a 3-stage smem ring
 //   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32 in TMEM),
 //                                tcgen05.commit releases smem stages / signals the epilogue; also owns TMEM alloc
@@ -201,6 +208,249 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
 }
 
+
+// ====================================================================================================================
+// Persistent kernel
+// ====================================================================================================================
+constexpr int P_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+
+template <int BN_> struct PCfg {
+    static constexpr int STAGES_ = BN_ == 256 ? 3 : (BN_ == 128 ? 4 : 6);
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_ * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int HALF = BN_ / 2;                           // columns handled by one epilogue warp
+    static constexpr int EPI_WARP_BYTES = 32 * HALF * 2;          // one warp's 32 rows x BN/2 bf16
+    static constexpr int BAR_OFF = STAGES_ * STAGE_BYTES + 8 * EPI_WARP_BYTES;
+    static constexpr int SMEM = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 2 * BN_ <= 128 ? 128 : (2 * BN_ <= 256 ? 256 : 512);
+};
+
+// 32 accumulator columns of one row -> alpha / bias / activation / bias2 with the reference's bf16 rounding points -> bf16
+template <int MODE>  // 0: plain (alpha, optional bias), 1: general
+__device__ __forceinline__ void epi_convert32(const uint32_t (&v)[32], uint32_t (&packed)[16], const EpiParams& p, int n_first) {
+    if (MODE == 0) {
+        float b[32];
+        if (p.bias != nullptr) {
+            if (n_first + 32 <= p.N && ((n_first & 3) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n_first + j));
+                    b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) b[j] = (n_first + j < p.N) ? p.bias[n_first + j] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) b[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[j]), p.alpha, b[j]),
+                                                      fmaf(__uint_as_float(v[j + 1]), p.alpha, b[j + 1]));
+            packed[j / 2] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float x2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float x = __uint_as_float(v[j + e]);
+                const int n = n_first + j + e;
+                if (p.act == GVD_ACT_ROUND_SCALE) {
+                    x = bf16r(bf16r(x) * p.alpha);
+                } else {
+                    x *= p.alpha;
+                    if (p.bias != nullptr && n < p.N) x += p.bias[n];
+                    x = apply_act(x, p.act);
+                }
+                if (p.bias2 != nullptr && n < p.N) x = bf16r(x) + p.bias2[n];
+                x2[e] = x;
+            }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(x2[0], x2[1]);
+            packed[j / 2] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+    }
+}
+
+template <int BN_>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                            EpiParams p, int tiles_m, int tiles_n, int total_tiles) {
+    using Cfg = PCfg<BN_>;
+    constexpr int ST = Cfg::STAGES_;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_epi = smem + ST * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* full = bars;                   // [ST]   TMA -> MMA
+    uint64_t* empty = bars + ST;             // [ST]   MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * ST;     // [2]    MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * ST + 2;  // [2]  epilogue -> MMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < ST; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&tmem_full[b], 1);
+            tc::mbar_init(&tmem_empty[b], 8);  // one arrival per epilogue warp
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int tiles_mn = tiles_m * tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int kc = 0;  // running k-block counter across tiles -> stage / phase
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_mn, r = tile - z * tiles_mn;
+                const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_;
+                const int bh = z % p.batch_h, bb = z / p.batch_h;
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const int s = kc % ST;
+                    const uint32_t ph = (uint32_t)((kc / ST) & 1);
+                    tc::mbar_wait(&empty[s], ph ^ 1u);
+                    tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                    tc::tma_load_4d(sa, &tmap_a, &full[s], kb * BK, m0, bh, bb);
+                    tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kb * BK, n0, bh, bb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(BM, BN_);
+            int kc = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                tc::mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));  // epilogue has drained this buffer
+                tc::fence_after_sync();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN_);
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const int s = kc % ST;
+                    const uint32_t ph = (uint32_t)((kc / ST) & 1);
+                    tc::mbar_wait(&full[s], ph);
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc::umma_bf16(tmem_d, tc::make_desc_kmajor_sw128(a_addr + k * 32),
+                                      tc::make_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    tc::umma_commit(&empty[s]);
+                }
+                tc::umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int q = warp & 3;      // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
+        const int half = ew >> 2;    // which half of the tile's columns
+        constexpr int HALF = Cfg::HALF;
+        uint8_t* stage = smem_epi + ew * Cfg::EPI_WARP_BYTES;
+        constexpr int ROW_BYTES = HALF * 2, CHUNKS = ROW_BYTES / 16;   // 16-byte chunks per staged row: 4 / 8 / 16
+        constexpr int ROWS_PER_PASS = 32 / CHUNKS;
+        constexpr int SWZ = CHUNKS >= 8 ? 7 : CHUNKS - 1;
+        const bool plain = (p.act == GVD_ACT_NONE) && (p.bias2 == nullptr);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int z = tile / tiles_mn, r = tile - z * tiles_mn;
+            const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_ + half * HALF;
+            const int bh = z % p.batch_h, bb = z / p.batch_h;
+            const int buf = it & 1;
+            tc::mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            tc::fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + half * HALF);
+            // ---- phase 1: TMEM -> registers -> bf16 -> swizzled smem row `lane` ----
+#pragma unroll 1
+            for (int c = 0; c < HALF; c += 32) {
+                if (n0 + c >= p.N) break;
+                uint32_t v[32], packed[16];
+                tc::tmem_ld32(taddr + (uint32_t)c, v);
+                tc::tmem_ld_wait();
+                if (plain) epi_convert32<0>(v, packed, p, n0 + c);
+                else epi_convert32<1>(v, packed, p, n0 + c);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ch = c / 8 + k;
+                    *reinterpret_cast<uint4*>(stage + lane * ROW_BYTES + ((ch ^ (lane & SWZ)) << 4)) =
+                        make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                }
+            }
+            // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+            // ---- phase 2: coalesced write-out (+ residual), ROWS_PER_PASS rows per warp instruction ----
+            const long long base_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h;
+            const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
+            const int n = n0 + chunk * 8;
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += ROWS_PER_PASS) {
+                const int rr = r0 + rsub;
+                const int m = m0 + q * 32 + rr;
+                if (m < p.M && n < p.N) {
+                    uint4 val = *reinterpret_cast<const uint4*>(stage + rr * ROW_BYTES + ((chunk ^ (rr & SWZ)) << 4));
+                    const long long off = base_off + (long long)m * p.ldc + n;
+                    if (p.residual != nullptr) {
+                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + off));
+                        __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&val);
+                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 af = __bfloat1622float2(a2[e]), rf = __bfloat1622float2(r2[e]);
+                            a2[e] = __floats2bfloat162_rn(af.x + rf.x, af.y + rf.y);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = val;
+                }
+            }
+            __syncwarp();  // the staging rows are rewritten by the next tile
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN_>
+cudaError_t launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int batch, cudaStream_t s) {
+    using Cfg = PCfg<BN_>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_persistent_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN_ - 1) / BN_;
+    const long long total = (long long)tiles_m * tiles_n * batch;
+    const int grid = (int)(total < num_sms ? total : num_sms);
+    gemm_bf16_persistent_kernel<BN_><<<grid, P_THREADS, Cfg::SMEM, s>>>(ta, tb, p, tiles_m, tiles_n, (int)total);
+    return cudaGetLastError();
+}
+
 // ---- host side: tensor maps ----
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -249,6 +499,31 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         return 2;
     }
     CUtensorMap ta, tb;
+    EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,
+                a->M, a->N, a->K, a->batch_h};
+    const bool aligned_out = !a->out_fp32 && (a->N % 8 == 0) && (a->ldc % 8 == 0) &&
+                             (a->batch_h == 1 || a->c_stride_h % 8 == 0) && (a->batch_b == 1 || a->c_stride_b % 8 == 0) &&
+                             (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) &&
+                             (a->residual == nullptr || reinterpret_cast<uintptr_t>(a->residual) % 16 == 0);
+    const long long total_tiles128 = (long long)((a->M + BM - 1) / BM) * ((a->N + 127) / 128) * a->batch_h * a->batch_b;
+    if (aligned_out && total_tiles128 < (1ll << 30)) {
+        // tile width: least padding of N, ties to the wider tile (fewer A re-reads); 64 only for narrow outputs
+        auto padded = [&](int bn) { return (long long)((a->N + bn - 1) / bn) * bn; };
+        int bn = 128;
+        if (a->N <= 64) bn = 64;
+        else if (padded(256) <= padded(128)) bn = 256;
+        if (!make_tmap(&ta, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
+            !make_tmap(&tb, a->B, a->K, a->N, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b, bn)) {
+            g_nn_err = "gvd_gemm_bf16: cuTensorMapEncodeTiled failed";
+            return 1;
+        }
+        const int batch = a->batch_h * a->batch_b;
+        cudaError_t e = bn == 256 ? launch_persistent<256>(ta, tb, p, batch, s)
+                      : bn == 128 ? launch_persistent<128>(ta, tb, p, batch, s)
+                                  : launch_persistent<64>(ta, tb, p, batch, s);
+        if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 persistent launch: ") + cudaGetErrorString(e); return 1; }
+        return 0;
+    }
     if (!make_tmap(&ta, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
         !make_tmap(&tb, a->B, a->K, a->N, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b, BN)) {
         g_nn_err = "gvd_gemm_bf16: cuTensorMapEncodeTiled failed";
@@ -260,8 +535,6 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 attr: ") + cudaGetErrorString(e); return 1; }
         attr_set = true;
     }
-    EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,
-                a->M, a->N, a->K, a->batch_h};
     dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM, a->batch_h * a->batch_b);
     gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
