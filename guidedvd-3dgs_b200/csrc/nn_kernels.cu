@@ -29,29 +29,43 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---------------- GroupNorm (channels-last) ----------------
 // x [F, S, C]; group g = channels [g*cpg, (g+1)*cpg); statistics over S x cpg per (frame, group).
-// Pass 1: grid (chunks, F); each CTA sums a slab of rows; partial (sum, sumsq) per (frame, chunk, group).
+// Thread layout: a thread owns one 16-byte vector of 8 channels and walks rows; the CTA covers
+// (256 / (C/8)) rows per step, so every load is a full coalesced 16-byte access.
+// Pass 1: grid (chunks, F): partial (sum, sumsq) per (frame, chunk, group).
 __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int groups,
                                                          int rows_per_chunk, float* __restrict__ partial) {
     extern __shared__ float sh[];  // [groups*2]
     const int f = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-    const int cpg = C / groups;
+    const int cpg = C / groups, vecs = C / 8;
     for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
     const int r0 = chunk * rows_per_chunk, r1 = min(S, r0 + rows_per_chunk);
-    const int pairs = C / 2;  // C is even
-    // thread -> fixed channel pair(s), loops over rows: coalesced along C
-    for (int cp = threadIdx.x; cp < pairs; cp += blockDim.x) {
-        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-        const __nv_bfloat162* base = reinterpret_cast<const __nv_bfloat162*>(x + ((size_t)f * S + r0) * C) + cp;
-        for (int r = r0; r < r1; ++r) {
-            const float2 v = __bfloat1622float2(*base);
-            base += pairs;
-            s0 += v.x; q0 += v.x * v.x;
-            s1 += v.y; q1 += v.y * v.y;
+    // vecs <= 256: 256/vecs rows in flight per step; wider rows: one row per step, threads stride over the vectors
+    const int vper = vecs <= 256 ? vecs : 256;
+    const int rows_par = vecs <= 256 ? 256 / vecs : 1;
+    const int rsub = threadIdx.x / vper;
+    if (rsub < rows_par)
+    for (int v = threadIdx.x % vper; v < vecs; v += vper) {
+        float sm[8], sq[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sm[e] = sq[e] = 0.f;
+        const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
+        for (int r = r0 + rsub; r < r1; r += rows_par) {
+            const uint4 u = __ldg(base + (size_t)r * vecs);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(h2[e]);
+                sm[2 * e] += t.x; sq[2 * e] += t.x * t.x;
+                sm[2 * e + 1] += t.y; sq[2 * e + 1] += t.y * t.y;
+            }
         }
-        const int g0 = (2 * cp) / cpg, g1 = (2 * cp + 1) / cpg;
-        atomicAdd(&sh[2 * g0], s0); atomicAdd(&sh[2 * g0 + 1], q0);
-        atomicAdd(&sh[2 * g1], s1); atomicAdd(&sh[2 * g1 + 1], q1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (8 * v + e) / cpg;
+            atomicAdd(&sh[2 * g], sm[e]);
+            atomicAdd(&sh[2 * g + 1], sq[e]);
+        }
     }
     __syncthreads();
     float* out = partial + ((size_t)f * nchunks + chunk) * groups * 2;
@@ -65,7 +79,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                                                        int nchunks, int rows_per_cta, float eps, int do_silu) {
     extern __shared__ float sh[];  // mean[groups], rstd[groups]
     const int f = blockIdx.y;
-    const int cpg = C / groups;
+    const int cpg = C / groups, vecs = C / 8;
     if (threadIdx.x < groups) {
         double s = 0.0, q = 0.0;
         for (int c = 0; c < nchunks; ++c) {
@@ -80,26 +94,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
         sh[groups + threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
+    const int vper = vecs <= 256 ? vecs : 256;
+    const int rows_par = vecs <= 256 ? 256 / vecs : 1;
+    const int rsub = threadIdx.x / vper;
+    if (rsub >= rows_par) return;
+    for (int v = threadIdx.x % vper; v < vecs; v += vper) {
+    // per-thread constants for its 8 channels: scale = rstd*gamma, shift = beta - mean*rstd*gamma
+    float sc[8], sf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = 8 * v + e, g = c / cpg;
+        sc[e] = sh[groups + g] * gamma[c];
+        sf[e] = beta[c] - sh[g] * sc[e];
+    }
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
-    const int pairs = C / 2;
-    const size_t total = (size_t)(r1 - r0) * pairs;
-    const __nv_bfloat162* xin = reinterpret_cast<const __nv_bfloat162*>(x + ((size_t)f * S + r0) * C);
-    __nv_bfloat162* yout = reinterpret_cast<__nv_bfloat162*>(y + ((size_t)f * S + r0) * C);
-    for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
-        const int cp = (int)(i % pairs);
-        const int c0 = 2 * cp, c1 = c0 + 1;
-        const int g0 = c0 / cpg, g1 = c1 / cpg;
-        const float2 v = __bfloat1622float2(xin[i]);
-        float a = (v.x - sh[g0]) * sh[groups + g0] * gamma[c0] + beta[c0];
-        float b = (v.y - sh[g1]) * sh[groups + g1] * gamma[c1] + beta[c1];
-        if (do_silu == 1) {  // GroupNormSpecific casts its output to bf16 before nn.SiLU sees it (basics.py:76-78)
-            a = silu(__bfloat162float(__float2bfloat16(a)));
-            b = silu(__bfloat162float(__float2bfloat16(b)));
-        } else if (do_silu == 2) {  // plain nn.GroupNorm returns fp32 under autocast: SiLU in fp32, one rounding at the end
-            a = silu(a);
-            b = silu(b);
+    const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
+    uint4* yout = reinterpret_cast<uint4*>(y + (size_t)f * S * C) + v;
+    for (int r = r0 + rsub; r < r1; r += rows_par) {
+        uint4 u = __ldg(xin + (size_t)r * vecs);
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 t = __bfloat1622float2(h2[e]);
+            float a = fmaf(t.x, sc[2 * e], sf[2 * e]), b = fmaf(t.y, sc[2 * e + 1], sf[2 * e + 1]);
+            if (do_silu == 1) {  // GroupNormSpecific casts its output to bf16 before nn.SiLU sees it (basics.py:76-78)
+                a = silu(__bfloat162float(__float2bfloat16(a)));
+                b = silu(__bfloat162float(__float2bfloat16(b)));
+            } else if (do_silu == 2) {  // plain nn.GroupNorm returns fp32 under autocast: SiLU in fp32, one rounding at the end
+                a = silu(a);
+                b = silu(b);
+            }
+            h2[e] = __floats2bfloat162_rn(a, b);
         }
-        yout[i] = __floats2bfloat162_rn(a, b);
+        yout[(size_t)r * vecs] = u;
+    }
     }
 }
 
@@ -219,64 +247,105 @@ __global__ void __launch_bounds__(256) im2col_t3_kernel(const __nv_bfloat16* __r
 }
 
 // ---------------- temporal self-attention: sequences of T <= 32 frames per (pixel, head), d = 64 ----------------
-// q,k,v,out: [B, T, S, H*64] bf16. One warp per (b, s, h): lane j owns key/value frame j; queries are broadcast.
-__global__ void __launch_bounds__(256) temporal_attn_kernel(const __nv_bfloat16* __restrict__ q,
-                                                            const __nv_bfloat16* __restrict__ k,
-                                                            const __nv_bfloat16* __restrict__ v,
-                                                            __nv_bfloat16* __restrict__ out, int B, int T, long long S,
-                                                            int H, float scale) {
-    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// q,k,v,out: [B, T, S, H*64] bf16. One warp per (b, s, h): K and V of the sequence (T x 64 each) are staged in shared
+// memory with coalesced 128-byte row loads; lane i < T owns query frame i: its q row and output row live in registers,
+// K/V rows are read as warp-wide broadcasts.
+#define TA_WARPS 4
+__global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv_bfloat16* __restrict__ q,
+                                                                      const __nv_bfloat16* __restrict__ k,
+                                                                      const __nv_bfloat16* __restrict__ v,
+                                                                      __nv_bfloat16* __restrict__ out, int B, int T,
+                                                                      long long S, int H, float scale) {
+    __shared__ __align__(16) __nv_bfloat16 sk[TA_WARPS][32 * 64];
+    __shared__ __align__(16) __nv_bfloat16 sv[TA_WARPS][32 * 64];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * TA_WARPS + wib;
     const long long total = (long long)B * S * H;
     if (w >= total) return;
-    const int lane = threadIdx.x & 31;
     const int h = (int)(w % H);
     const long long s = (w / H) % S;
     const int b = (int)(w / (H * S));
     const long long tstride = S * H * 64;
     const size_t base = ((size_t)b * T * S + s) * H * 64 + (size_t)h * 64;
-    // lane j keeps k_j and v_j (64 values each) in registers
-    float kj[64], vj[64];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) kj[c] = vj[c] = 0.f;  // lanes >= T hold no frame: they must contribute exact zeros
-    if (lane < T) {
-        const uint4* kp = reinterpret_cast<const uint4*>(k + base + lane * tstride);
-        const uint4* vp = reinterpret_cast<const uint4*>(v + base + lane * tstride);
+    // stage K, V: 8 lanes x 16 B cover one 128-byte row; 4 rows per pass
+    for (int r = lane >> 3; r < T; r += 4) {
+        const int c = lane & 7;
+        reinterpret_cast<uint4*>(&sk[wib][r * 64])[c] = __ldg(reinterpret_cast<const uint4*>(k + base + r * tstride) + c);
+        reinterpret_cast<uint4*>(&sv[wib][r * 64])[c] = __ldg(reinterpret_cast<const uint4*>(v + base + r * tstride) + c);
+    }
+    __syncwarp();
+    if (lane >= T) return;
+    float qf[64];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(q + base + lane * tstride);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 kk = kp[c], vv = vp[c];
-            const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
-            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+            const uint4 u = __ldg(qp + c);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float2 a = __bfloat1622float2(k2[e]), bb = __bfloat1622float2(v2[e]);
-                kj[c * 8 + 2 * e] = a.x; kj[c * 8 + 2 * e + 1] = a.y;
-                vj[c * 8 + 2 * e] = bb.x; vj[c * 8 + 2 * e + 1] = bb.y;
+                const float2 t = __bfloat1622float2(h2[e]);
+                qf[c * 8 + 2 * e] = t.x;
+                qf[c * 8 + 2 * e + 1] = t.y;
             }
         }
     }
-    for (int i = 0; i < T; ++i) {
-        // query frame i: lanes 0..31 load two channels each, then broadcast by shuffle
-        const __nv_bfloat162 q2 = reinterpret_cast<const __nv_bfloat162*>(q + base + i * tstride)[lane];
-        const float2 qf = __bfloat1622float2(q2);
+    float sc[32];
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+        const uint4* kp = reinterpret_cast<const uint4*>(&sk[wib][j * 64]);
         float dot = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float qx = __shfl_sync(0xffffffffu, qf.x, c), qy = __shfl_sync(0xffffffffu, qf.y, c);
-            dot += qx * kj[2 * c] + qy * kj[2 * c + 1];
-        }
-        // the reference rounds sim to the autocast dtype before softmax (einsum output): keep that rounding point
-        float sc = (lane < T) ? __bfloat162float(__float2bfloat16(__bfloat162float(__float2bfloat16(dot)) * scale)) : -INFINITY;
-        const float m = warp_max(sc);
-        const float e = (lane < T) ? __expf(sc - m) : 0.f;
-        const float p = __bfloat162float(__float2bfloat16(e / warp_sum(e)));  // softmax output cast to bf16 for the PV product
-        // out_i[c] = sum_j p_j v_j[c]: lane c' gathers channels 2c', 2c'+1
-        float o0 = 0.f, o1 = 0.f;
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = kp[c];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float a0 = warp_sum(p * vj[2 * c]), a1 = warp_sum(p * vj[2 * c + 1]);
-            if (lane == c) { o0 = a0; o1 = a1; }
+            for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(h2[e]);
+                dot = fmaf(qf[c * 8 + 2 * e], t.x, dot);
+                dot = fmaf(qf[c * 8 + 2 * e + 1], t.y, dot);
+            }
         }
-        reinterpret_cast<__nv_bfloat162*>(out + base + i * tstride)[lane] = __floats2bfloat162_rn(o0, o1);
+        // the reference rounds the einsum output to bf16 and scales in bf16 before the fp32 softmax (attention.py:103)
+        const float x = __bfloat162float(__float2bfloat16(__bfloat162float(__float2bfloat16(dot)) * scale));
+        sc[j] = x;
+        m = fmaxf(m, x);
+    }
+    float l = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+        sc[j] = __expf(sc[j] - m);
+        l += sc[j];
+    }
+    const float inv = 1.0f / l;
+    float o[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) o[c] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+        const float p = __bfloat162float(__float2bfloat16(sc[j] * inv));  // softmax output enters the PV einsum as bf16
+        const uint4* vp = reinterpret_cast<const uint4*>(&sv[wib][j * 64]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = vp[c];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(h2[e]);
+                o[c * 8 + 2 * e] = fmaf(p, t.x, o[c * 8 + 2 * e]);
+                o[c * 8 + 2 * e + 1] = fmaf(p, t.y, o[c * 8 + 2 * e + 1]);
+            }
+        }
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + base + lane * tstride);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o[c * 8 + 2 * e], o[c * 8 + 2 * e + 1]);
+        op[c] = u;
     }
 }
 
@@ -355,7 +424,10 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
                      float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (F <= 0 || S <= 0) return 0;
-    if (C % groups != 0 || C % 2 != 0 || groups > 256) { g_nn_err_ext = "gvd_groupnorm_cl: bad channel/group count"; return 2; }
+    if (C % groups != 0 || C % 8 != 0 || groups > 128) {
+        g_nn_err_ext = "gvd_groupnorm_cl: needs C % groups == 0, C % 8 == 0, groups <= 128";
+        return 2;
+    }
     int nchunks = (int)((S + 1023) / 1024);
     if (nchunks > 512) nchunks = 512;
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
@@ -363,7 +435,7 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
     if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
     gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(float), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
                                                                                  rows_per_chunk, tmp);
-    const int rows_per_cta = 64;
+    const int rows_per_cta = 128;
     gn_apply_kernel<<<dim3((unsigned)((S + rows_per_cta - 1) / rows_per_cta), F), 256, groups * 2 * sizeof(float), s>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups, nchunks, rows_per_cta, eps, do_silu);
     cudaError_t e = cudaGetLastError();
@@ -431,7 +503,7 @@ int gvd_temporal_attention(const void* q, const void* k, const void* v, void* ou
     if (T > 32 || T <= 0) { g_nn_err_ext = "gvd_temporal_attention: needs 1 <= T <= 32"; return 2; }
     const long long warps = (long long)B * S * H;
     if (warps <= 0) return 0;
-    temporal_attn_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+    temporal_attn_kernel<<<(unsigned)((warps + TA_WARPS - 1) / TA_WARPS), TA_WARPS * 32, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                     (const __nv_bfloat16*)v, (__nv_bfloat16*)out, B, T, S, H, scale);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -1,0 +1,109 @@
+"""GPU numerics of the memory-bound U-Net layers (include/gvd_nn.h) against plain PyTorch fp32 references of the same
+ops on the same bf16 inputs (tolerance: one bf16 rounding of the output, 2^-8 relative, plus fp32 reduction noise)."""
+import pytest
+import torch
+import torch.nn.functional as Fn
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _close(a, b, tol=1.0 / 128):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    assert err <= tol * b.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("F,S,C,silu", [(5, 256, 320, 1), (2, 1000, 64, 0), (1, 5 * 64, 2560, 2), (3, 77, 1920, 1), (25, 144, 1280, 2)])
+def test_groupnorm(F, S, C, silu):
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(C + S)
+    x = (torch.randn(F, S, C, device="cuda", generator=g) * 2 + 0.5).to(BF)
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    y = ops.groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=silu)
+    ref = Fn.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
+    if silu == 1:
+        ref = Fn.silu(ref.to(BF).float())
+    elif silu == 2:
+        ref = Fn.silu(ref)
+    _close(y, ref)
+
+
+def test_layernorm_geglu_softmax():
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(1000, 640, device="cuda", generator=g).to(BF)
+    gamma, beta = 1 + 0.1 * torch.randn(640, device="cuda", generator=g), 0.1 * torch.randn(640, device="cuda", generator=g)
+    _close(ops.layernorm(x, gamma, beta), Fn.layer_norm(x.float(), (640,), gamma, beta))
+    h = torch.randn(777, 2 * 1280, device="cuda", generator=g).to(BF)
+    a, gate = h.float().chunk(2, -1)
+    _close(ops.geglu(h), a * Fn.gelu(gate).to(BF).float())
+    for dt in (BF, torch.float32):
+        sc = (4 * torch.randn(300, 80, device="cuda", generator=g)).to(dt)
+        p = ops.softmax_rows(sc, 77, 80)
+        _close(p[:, :77], torch.softmax(sc[:, :77].float(), -1))
+        assert float(p[:, 77:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("F,H,W,C,stride,up", [(3, 16, 24, 64, 1, False), (2, 16, 16, 320, 2, False), (2, 8, 12, 128, 1, True), (1, 9, 7, 8, 1, False)])
+def test_conv3x3(F, H, W, C, stride, up):
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(H * W + C)
+    Cout = 96
+    x = torch.randn(F, C, H, W, device="cuda", generator=g).to(BF)
+    w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (3 * C ** 0.5)).to(BF)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    xin = Fn.interpolate(x.float(), scale_factor=2, mode="nearest") if up else x.float()
+    ref = Fn.conv2d(xin, w.float(), b, stride=stride, padding=1)
+    x_cl = x.permute(0, 2, 3, 1).reshape(F, H * W, C).contiguous()
+    w_cl = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    y, Ho, Wo = ops.conv3x3(x_cl, F, H, W, w_cl, b, stride=stride, upsample=up)
+    assert (Ho, Wo) == tuple(ref.shape[2:])
+    _close(y.view(F, Ho, Wo, Cout).permute(0, 3, 1, 2), ref)
+
+
+def test_conv_t3_and_temporal_attention():
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, T, S, C, Cout = 1, 7, 50, 64, 128
+    x = torch.randn(B, C, T, S, 1, device="cuda", generator=g).to(BF)
+    w = (torch.randn(Cout, C, 3, 1, 1, device="cuda", generator=g) / (3 * C) ** 0.5).to(BF)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    ref = Fn.conv3d(x.float(), w.float(), b, padding=(1, 0, 0))[..., 0]           # [B, Cout, T, S]
+    x_cl = x[..., 0].permute(0, 2, 3, 1).reshape(B * T, S, C).contiguous()
+    w_cl = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(Cout, -1).contiguous()
+    y = ops.conv_t3(x_cl, B, T, S, w_cl, b)
+    _close(y.view(B, T, S, Cout).permute(0, 3, 1, 2), ref)
+    for T in (1, 5, 25, 32):
+        H, S = 5, 37
+        q, k, v = (torch.randn(2, T, S, H * 64, device="cuda", generator=g).to(BF) for _ in range(3))
+        o = ops.temporal_attention(q, k, v, 2, T, S, H, 0.125)
+        qh, kh, vh = (t.float().view(2, T, S, H, 64).permute(0, 2, 3, 1, 4) for t in (q, k, v))  # [B,S,H,T,64]
+        sim = ((qh @ kh.transpose(-1, -2)).to(BF).float() * 0.125).to(BF).float()
+        ref = (torch.softmax(sim, -1).to(BF).float() @ vh).permute(0, 3, 1, 2, 4).reshape(2, T, S, H * 64)
+        _close(o, ref)
+
+
+def test_attention_paths():
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Bq, Nq, H = 3, 200, 5
+    q = torch.randn(Bq, Nq, H * 64, device="cuda", generator=g).to(BF)
+
+    def ref(q, k, v):
+        qh = q.float().view(q.shape[0], -1, H, 64).transpose(1, 2)
+        kh = k.float().view(k.shape[0], -1, H, 64).transpose(1, 2)
+        vh = v.float().view(v.shape[0], -1, H, 64).transpose(1, 2)
+        sim = ((qh @ kh.transpose(-1, -2)).to(BF).float() * 0.125).to(BF).float()
+        return (torch.softmax(sim, -1).to(BF).float() @ vh).transpose(1, 2).reshape(q.shape[0], -1, H * 64)
+
+    k, v = (torch.randn(Bq, Nq, H * 64, device="cuda", generator=g).to(BF) for _ in range(2))
+    _close(ops.attention(q, k, v, Bq, Nq, Nq, H, 0.125), ref(q, k, v), tol=1.0 / 64)
+    ks, vs = (torch.randn(1, 77, H * 64, device="cuda", generator=g).to(BF) for _ in range(2))
+    _close(ops.attention(q, ks, vs, Bq, Nq, 77, H, 0.125, shared_kv=True), ref(q, ks.expand(Bq, -1, -1), vs.expand(Bq, -1, -1)), tol=1.0 / 64)
