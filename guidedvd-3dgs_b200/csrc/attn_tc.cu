@@ -1,0 +1,290 @@
+// attn_tc.cu -- fused softmax(Q K^T * scale) V on Blackwell tensor cores, head dim 64 (include/gvd_nn.h::gvd_flash_attention).
+//
+// Never materialises the score matrix (the reference's einsum path writes [b*h, N, N] scores: 21 GB per layer at
+// 576x1024, attention.py:103,118).  One CTA = 128 query rows of one (batch, head); key/value blocks of 128 stream through
+// a 2-stage TMA ring:
+//   warp 0    : TMA producer  (Q once, then K_j / V_j tiles, 128-byte swizzle)
+//   warp 1    : MMA issuer    S = Q K_j^T        (SS: both operands in smem, accumulator S in TMEM, 128 fp32 columns)
+//                             O_j = P_j V_j      (TS: A = P_j read from TMEM as packed bf16, B = V_j smem tile, MN-major)
+//   warps 2-5 : softmax       thread = query row. Two passes over its S row in TMEM (row max, then exp -> bf16 P written
+//                             back to TMEM with tcgen05.st), running max / sum / output row (64 fp32) in registers;
+//                             O_j is read from TMEM and folded in with the usual exp(m_old - m_new) correction.
+// TMEM: S [0,128) | P [128,192) | O_j [192,256)  -> 256 columns, two CTAs per SM.
+// Logits are rounded exactly where the reference rounds them under autocast: bf16(bf16(q.k) * scale).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <string>
+
+#include "../../include/gvd_nn.h"
+#include "tc_common.cuh"
+
+extern thread_local std::string g_nn_err_ext;
+
+namespace {
+
+constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64;
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K_j or V_j tile
+constexpr int FA_STAGES = 2;
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 1024 + 256;
+constexpr int FA_THREADS = 192;
+constexpr uint32_t FA_TMEM_COLS = 256, FA_S_COL = 0, FA_P_COL = 128, FA_O_COL = 192;
+
+__device__ __forceinline__ float bf16r_(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+// MN-major B operand tile (V_j: 128 keys x 64 d, rows of 128 bytes, 128-byte swizzle): same geometry as the K-major
+// tile (8-row atoms of 1024 bytes); the "major" bit lives in the instruction descriptor.
+__device__ __forceinline__ uint32_t make_idesc_pv() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(FA_D >> 3) << 17) |
+           ((uint32_t)(FA_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct FaParams {
+    __nv_bfloat16* out;
+    long long ldo, o_stride_h, o_stride_b;
+    int Nq, Nk, H;
+    float scale;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                  const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sq = smem;
+    uint8_t* sk = smem + FA_TILE_BYTES;
+    uint8_t* sv = smem + FA_TILE_BYTES * (1 + FA_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;              // [2]
+    uint64_t* kv_empty = bars + 3;             // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.Nk + FA_BN - 1) / FA_BN;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_q);
+        tc::prefetch_tmap(&tmap_k);
+        tc::prefetch_tmap(&tmap_v);
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < FA_STAGES; ++s) {
+            tc::mbar_init(&kv_full[s], 1);
+            tc::mbar_init(&kv_empty[s], 1);
+        }
+        tc::mbar_init(s_full, 1);
+        tc::mbar_init(p_full, 4);  // one arrival per softmax warp
+        tc::mbar_init(o_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(q_full, FA_TILE_BYTES);
+            tc::tma_load_4d(sq, &tmap_q, q_full, 0, m0, h, b);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA_STAGES) & 1) ^ 1));
+                tc::mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+                tc::tma_load_4d(sk + s * FA_TILE_BYTES, &tmap_k, &kv_full[s], 0, j * FA_BN, h, b);
+                tc::tma_load_4d(sv + s * FA_TILE_BYTES, &tmap_v, &kv_full[s], 0, j * FA_BN, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = tc::make_idesc_bf16(FA_BM, FA_BN);
+            const uint32_t idesc_pv = make_idesc_pv();
+            const uint32_t q_addr = tc::smem_u32(sq);
+            tc::mbar_wait(q_full, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_full[s], (uint32_t)((j / FA_STAGES) & 1));
+                // S_j may overwrite S_{j-1} only after the softmax warps have read it: p_full(j-1) was waited on below
+                tc::fence_after_sync();
+                const uint32_t k_addr = tc::smem_u32(sk + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k)
+                    tc::umma_bf16(tmem_base + FA_S_COL, tc::make_desc_kmajor_sw128(q_addr + k * 32),
+                                  tc::make_desc_kmajor_sw128(k_addr + k * 32), idesc_qk, k != 0);
+                tc::umma_commit(s_full);
+                // O_j = P_j V_j once the softmax warps have written P_j
+                tc::mbar_wait(p_full, (uint32_t)(j & 1));
+                tc::fence_after_sync();
+                const uint32_t v_addr = tc::smem_u32(sv + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < FA_BN / 16; ++k)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 smem rows of V
+                    umma_bf16_ts(tmem_base + FA_O_COL, tmem_base + FA_P_COL + k * 8,
+                                 tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, k != 0);
+                tc::umma_commit(o_full);
+                tc::umma_commit(&kv_empty[s]);
+            }
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quadrant of this warp
+        const int row = m0 + q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float L2E = 1.4426950408889634f;
+        float m_run = -INFINITY, l_run = 0.f;
+        float o[FA_D];
+#pragma unroll
+        for (int c = 0; c < FA_D; ++c) o[c] = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            tc::mbar_wait(s_full, (uint32_t)(j & 1));
+            tc::fence_after_sync();
+            const int key0 = j * FA_BN;
+            // ---- pass 1: row max of the rounded logits ----
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < FA_BN; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + lane_off + FA_S_COL + c, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = bf16r_(bf16r_(__uint_as_float(v[e])) * p.scale);
+                    mx = fmaxf(mx, (key0 + c + e < p.Nk) ? x : -INFINITY);
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * L2E);
+            const float mneg = -m_new * L2E;
+            // ---- pass 2: P = exp(x - m_new) -> bf16 pairs -> TMEM ----
+            float l_blk = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < FA_BN; c += 32) {
+                uint32_t v[32], pk[16];
+                tc::tmem_ld32(tmem_base + lane_off + FA_S_COL + c, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float pe[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float x = bf16r_(bf16r_(__uint_as_float(v[e + u])) * p.scale);
+                        pe[u] = (key0 + c + e + u < p.Nk) ? exp2f(fmaf(x, L2E, mneg)) : 0.f;
+                        l_blk += pe[u];
+                    }
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(pe[0], pe[1]);
+                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st16(tmem_base + lane_off + FA_P_COL + c / 2, pk);
+            }
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(p_full);
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+            // ---- fold in O_j ----
+            tc::mbar_wait(o_full, (uint32_t)(j & 1));
+            tc::fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < FA_D; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + lane_off + FA_O_COL + c, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[c + e] = fmaf(o[c + e], alpha, __uint_as_float(v[e]));
+            }
+        }
+        if (row < p.Nq) {
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
+#pragma unroll
+            for (int c = 0; c < FA_D; c += 8) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o[c + 2 * e] * inv, o[c + 2 * e + 1] * inv);
+                *reinterpret_cast<uint4*>(dst + c) = u;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// [B, N, H*64] bf16 viewed as (d=64, rows=N with stride ld, heads with stride 64, batch with stride sb)
+bool fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long H, long long B, long long ld, long long sb) {
+    auto enc = fa_get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {64, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, 64 * 2, (cuuint64_t)(B > 1 ? sb : ld) * 2};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, void* out, int B, int Nq, int Nk, int H,
+                                   long long q_batch_stride, long long kv_batch_stride, float scale,
+                                   gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (!q || !k || !v || !out) { g_nn_err_ext = "gvd_flash_attention: null pointer"; return 2; }
+    if (B <= 0 || Nq <= 0 || H <= 0) return 0;
+    if (Nk <= 0) { g_nn_err_ext = "gvd_flash_attention: Nk must be positive"; return 2; }
+    const long long ld = (long long)H * 64;
+    if ((q_batch_stride & 7) || (kv_batch_stride & 7)) { g_nn_err_ext = "gvd_flash_attention: batch strides must be multiples of 8"; return 2; }
+    CUtensorMap tq, tk, tv;
+    if (!fa_make_tmap(&tq, q, Nq, H, B, ld, q_batch_stride) || !fa_make_tmap(&tk, k, Nk, H, B, ld, kv_batch_stride) ||
+        !fa_make_tmap(&tv, v, Nk, H, B, ld, kv_batch_stride)) {
+        g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+        if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
+        attr_set = true;
+    }
+    FaParams p{reinterpret_cast<__nv_bfloat16*>(out), ld, 64, q_batch_stride, Nq, Nk, H, scale};
+    dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
+    flash_attn_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}

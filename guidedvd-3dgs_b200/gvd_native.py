@@ -165,7 +165,7 @@ class DdimArgs(C.Structure):
 
 NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", "gvd_groupnorm_cl", "gvd_layernorm",
               "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention",
-              "gvd_ddim_step")
+              "gvd_ddim_step", "gvd_flash_attention")
 _nn = None
 
 
@@ -192,6 +192,8 @@ def nn():
     lib.gvd_im2col_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
     lib.gvd_temporal_attention.argtypes = [vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
     lib.gvd_ddim_step.argtypes = [C.POINTER(DdimArgs), vp]
+    lib.gvd_flash_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]
+    lib.gvd_flash_attention.restype = C.c_int
     for n in ("gvd_groupnorm_cl", "gvd_layernorm", "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl",
               "gvd_temporal_attention", "gvd_ddim_step"):
         getattr(lib, n).restype = C.c_int

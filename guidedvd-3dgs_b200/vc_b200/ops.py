@@ -144,6 +144,21 @@ def temporal_attention(q, k, v, B, T, S, H, scale):
     return out
 
 
+def flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False):
+    """Fused softmax(q k^T * scale) v (gvd_flash_attention). Same arguments/layouts as `attention` below."""
+    lib = _n.nn()
+    HD = H * 64
+    out = torch.empty(Bq, Nq, HD, dtype=BF16, device=q.device)
+    if shared_kv:
+        B, nq, qs, ks = 1, Bq * Nq, Bq * Nq * HD, Nk * HD
+    else:
+        B, nq, qs, ks = Bq, Nq, Nq * HD, Nk * HD
+    with torch.cuda.device(q.device):
+        _check(lib.gvd_flash_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), int(B), int(nq), int(Nk), int(H),
+                                       int(qs), int(ks), float(scale), _stream()), lib, "gvd_flash_attention")
+    return out
+
+
 def attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False, max_score_bytes=6 << 30):
     """softmax(q k^T * scale) v with head dim 64.
     q [Bq, Nq, H*64]; k, v [Bq, Nk, H*64] (or [1, Nk, H*64] when shared_kv: the same keys for every batch item, then

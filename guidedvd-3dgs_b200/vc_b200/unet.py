@@ -138,16 +138,16 @@ class SpatialTransformer:
         # self attention, per frame
         a = ops.layernorm(h, *b.n1)
         at = b.attn1
-        o = ops.attention(ops.linear(a, at.q), ops.linear(a, at.k), ops.linear(a, at.v), F, S, S, at.heads, at.scale)
+        o = ops.flash_attention(ops.linear(a, at.q), ops.linear(a, at.k), ops.linear(a, at.v), F, S, S, at.heads, at.scale)
         h = ops.linear(o, *at.o, residual=h)
         # cross attention: 77 text tokens + 256 image tokens, identical for every frame (openaimodel3d.py:555-562)
         a = ops.layernorm(h, *b.n2)
         at = b.attn2
         q = ops.linear(a, at.q)
-        o = ops.attention(q, ops.linear(ctx_text, at.k), ops.linear(ctx_text, at.v), F, S, ctx_text.shape[1], at.heads, at.scale,
+        o = ops.flash_attention(q, ops.linear(ctx_text, at.k), ops.linear(ctx_text, at.v), F, S, ctx_text.shape[1], at.heads, at.scale,
                           shared_kv=True)
         if at.k_ip is not None:
-            o_ip = ops.attention(q, ops.linear(ctx_img, at.k_ip), ops.linear(ctx_img, at.v_ip), F, S, ctx_img.shape[1], at.heads,
+            o_ip = ops.flash_attention(q, ops.linear(ctx_img, at.k_ip), ops.linear(ctx_img, at.v_ip), F, S, ctx_img.shape[1], at.heads,
                                  at.scale, shared_kv=True)
             o = o + o_ip  # image_cross_attention_scale = 1.0, not learnable (attention.py:141-142)
         h = ops.linear(o, *at.o, residual=h)

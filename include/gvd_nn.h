@@ -89,6 +89,13 @@ GVD_NN_API int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long lon
 GVD_NN_API int gvd_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S,
                                       int H, float scale, gvd_nn_stream_t stream);
 
+/* Fused attention, head dim 64: out = softmax(bf16(bf16(q k^T) * scale)) v without materialising the scores
+ * (CrossAttention.forward, attention.py:81-144; the reference's einsum path writes the full [b*h, Nq, Nk] matrix).
+ * q, out: [B, Nq, H*64] bf16 (batch stride q_batch_stride elements); k, v: [B, Nk, H*64] bf16 (kv_batch_stride).
+ * Shared keys for all batch items (text / image cross-attention): pass B = 1 and Nq = batch * tokens. */
+GVD_NN_API int gvd_flash_attention(const void* q, const void* k, const void* v, void* out, int B, int Nq, int Nk, int H,
+                                   long long q_batch_stride, long long kv_batch_stride, float scale, gvd_nn_stream_t stream);
+
 /* One DDIM update, fused (lvdm/models/samplers/ddim.py:206-280 with v-prediction, classifier-free guidance,
  * rescale_noise_cfg (utils_diffusion.py:147-158) and dynamic rescale).  All tensors fp32 with n elements (one batch
  * item); e_uncond may be NULL (no guidance).  scratch: 32 + 4*n bytes. */

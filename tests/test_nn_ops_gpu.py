@@ -89,8 +89,11 @@ def test_conv_t3_and_temporal_attention():
         _close(o, ref)
 
 
-def test_attention_paths():
+@pytest.mark.parametrize("fn", ["attention", "flash_attention"])
+def test_attention_paths(fn):
     from vc_b200 import ops
+
+    attn = getattr(ops, fn)
 
     g = torch.Generator(device="cuda").manual_seed(11)
     Bq, Nq, H = 3, 200, 5
@@ -104,6 +107,10 @@ def test_attention_paths():
         return (torch.softmax(sim, -1).to(BF).float() @ vh).transpose(1, 2).reshape(q.shape[0], -1, H * 64)
 
     k, v = (torch.randn(Bq, Nq, H * 64, device="cuda", generator=g).to(BF) for _ in range(2))
-    _close(ops.attention(q, k, v, Bq, Nq, Nq, H, 0.125), ref(q, k, v), tol=1.0 / 64)
+    _close(attn(q, k, v, Bq, Nq, Nq, H, 0.125), ref(q, k, v), tol=1.0 / 64)
     ks, vs = (torch.randn(1, 77, H * 64, device="cuda", generator=g).to(BF) for _ in range(2))
-    _close(ops.attention(q, ks, vs, Bq, Nq, 77, H, 0.125, shared_kv=True), ref(q, ks.expand(Bq, -1, -1), vs.expand(Bq, -1, -1)), tol=1.0 / 64)
+    _close(attn(q, ks, vs, Bq, Nq, 77, H, 0.125, shared_kv=True), ref(q, ks.expand(Bq, -1, -1), vs.expand(Bq, -1, -1)), tol=1.0 / 64)
+    # longer sequences: several key blocks, ragged tails on both axes
+    q2 = torch.randn(2, 700, H * 64, device="cuda", generator=g).to(BF)
+    k2, v2 = (torch.randn(2, 700, H * 64, device="cuda", generator=g).to(BF) for _ in range(2))
+    _close(attn(q2, k2, v2, 2, 700, 700, H, 0.125), ref(q2, k2, v2), tol=1.0 / 64)
