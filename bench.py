@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-denoise", action="store_true", help="skip the secondary DDIM denoise-steps/s measurement")
     ap.add_argument("--ref-device", default="gpu", choices=["gpu", "cpu"],
                     help="reference arm: compiled reference CUDA on the GPU (default) or the C oracle port on host cores")
     args = ap.parse_args()
@@ -351,6 +352,13 @@ def main():
     }
     if roofline:
         line["roofline"] = roofline
+    if world == 1 and not args.no_denoise:
+        try:
+            del sc, leaves, means2D
+            torch.cuda.empty_cache()
+            line["denoise"] = denoise_bench(args.impl, dev)
+        except Exception as ex:  # the secondary metric must never take the headline line down
+            line["denoise"] = {"error": repr(ex)[:300]}
     if args.impl == "reference":
         line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": "reference",
                                 "sample": "the reference has no CPU rasterizer: this arm is its own CUDA code "
@@ -360,6 +368,60 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def denoise_bench(impl, dev, steps=2, t=25, h=72, w=128):
+    """Secondary metric of BASELINE.json: DDIM denoise-steps/s at configs[2] (25 frames, 576x1024 -> latent 72x128, cond +
+    uncond U-Net forward + sampler update per step), full-size ViewCrafter U-Net (1.44 B parameters, seeded random
+    weights).  impl 'ours' = vc_b200 (tcgen05 GEMM / flash attention); 'reference' = the reference
+    UNetModel + its own DDIMSampler arithmetic under torch.autocast(bfloat16) on the same GPU."""
+    import unet_ref
+    if not unet_ref.ref_available():
+        return {"unavailable": "oracle/_ref/ViewCrafter not installed (python oracle/build_ref.py vc)"}
+    from vc_b200.sampler import DDIMSampler
+    from vc_b200.schedule import ModelSchedule
+    from vc_b200.unet import DiffusionModelB200, UNetB200
+    ref, cfg = unet_ref.build_reference_unet(model_channels=320, device=dev)
+    x, cc, ctx, ctx_uc = unet_ref.synth_inputs(t, h, w, device=dev)
+    fs = torch.tensor([10], device=dev)
+    cond = {"c_concat": [cc], "c_crossattn": [ctx]}
+    uc = {"c_concat": [cc], "c_crossattn": [ctx_uc]}
+    sched = ModelSchedule()
+    if impl == "ours":
+        model = DiffusionModelB200(UNetB200(ref.state_dict(), device=dev, **cfg), sched)
+        del ref
+    else:
+        class RefModel:  # apply_model of DiffusionWrapper 'hybrid' (ddpm3d.py:1437-1443) around the reference module
+            schedule = sched
+
+            def apply_model(self, xx, tt, c, fs=None, **kw):
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    return ref(torch.cat([xx] + c["c_concat"], 1), tt, context=torch.cat(c["c_crossattn"], 1), fs=fs).float()
+        model = RefModel()
+    torch.cuda.empty_cache()
+    sampler = DDIMSampler(model)
+    sampler.make_schedule(50, ddim_discretize="uniform_trailing", ddim_eta=1.0)
+    noise = torch.randn_like(x)
+
+    def one(index):
+        ts = torch.full((1,), int(sampler.ddim_timesteps[index]), device=dev, dtype=torch.long)
+        return sampler.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5,
+                                     unconditional_conditioning=uc, guidance_rescale=0.7, noise=noise, fs=fs)
+    one(49)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(49 - i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = 2 * 82.76e12
+    return {"metric": "DDIM denoise-steps/sec", "value": round(1e3 / ms, 4), "unit": "steps/s", "ms_per_step": round(ms, 2),
+            "steps": steps, "dtype": "bf16", "config": {"workload": "C3", "frames": t, "latent": [h, w], "cfg": 7.5,
+            "ddim_steps": 50, "unet_params_M": 1438.9}, "tflops_per_s": round(flops / (ms * 1e-3) / 1e12, 1),
+            "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 1), "peak": 1392.9, "unit": "TFLOP/s",
+                         "frac": round(flops / (ms * 1e-3) / 1e12 / 1392.9, 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"}}
 
 
 def cpu_baseline(P, W, H, seed, D, budget_s=20.0):

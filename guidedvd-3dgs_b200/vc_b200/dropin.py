@@ -1,0 +1,48 @@
+"""Drop-in boundary for the diffusion half: swap the reference's U-Net module for the B200-native forward.
+
+The reference pipeline (utils/viewcrafter_wrapper.py:550-573 -> VC/viewcrafter.py:92-112 ->
+VC/utils_vc/diffusion_utils.py:118-223 -> DDIMSampler.p_sample_ddim -> model.apply_model ->
+DiffusionWrapper.forward, lvdm/models/ddpm3d.py:1426-1443) reaches the denoiser as
+`model.model.diffusion_model(xc, t, context=cc, **kwargs)`.  `B200UNet` is an nn.Module with that call signature whose
+forward runs vc_b200.unet.UNetB200; `replace_unet(latent_diffusion)` installs it, so `ViewCrafterWrapper`,
+`ViewCrafter.run_diffusion`, `image_guided_synthesis` and the reference samplers run unchanged on top of it.
+
+Scope: the plain DDIM path (`no_guidance=True`, and every U-Net call made under torch.no_grad()).  The guided sampler
+(lvdm/models/samplers/ddim_guidance.py:259-337) differentiates through the U-Net; this forward is inference-only, so
+`B200UNet` hands calls that need a graph back to the reference module it wraps (next).
+"""
+import torch
+import torch.nn as nn
+
+from .unet import UNetB200
+
+
+class B200UNet(nn.Module):
+    def __init__(self, reference_unet, device=None):
+        super().__init__()
+        self.reference = reference_unet  # kept for the autograd (guided) path and for state_dict round trips
+        dev = device or next(reference_unet.parameters()).device
+        cfg = dict(in_channels=reference_unet.in_channels, model_channels=reference_unet.model_channels,
+                   out_channels=reference_unet.out_channels, num_res_blocks=reference_unet.num_res_blocks,
+                   attention_resolutions=tuple(reference_unet.attention_resolutions),
+                   channel_mult=tuple(reference_unet.channel_mult), temporal_conv=True,
+                   addition_attention=bool(reference_unet.addition_attention),
+                   fs_condition=bool(reference_unet.fs_condition), default_fs=int(reference_unet.default_fs))
+        self.native = UNetB200(reference_unet.state_dict(), device=dev, **cfg)
+
+    def forward(self, x, timesteps, context=None, features_adapter=None, fs=None, **kwargs):
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.reference.parameters()))
+        if needs_graph or features_adapter is not None:
+            return self.reference(x, timesteps, context=context, features_adapter=features_adapter, fs=fs, **kwargs)
+        return self.native(x.float(), timesteps, context.float(), fs=fs).to(x.dtype)
+
+
+def replace_unet(latent_diffusion):
+    """latent_diffusion.model.diffusion_model <- B200UNet(original).  Returns the wrapper."""
+    wrapper = latent_diffusion.model
+    unet = wrapper.diffusion_model
+    if isinstance(unet, B200UNet):
+        return unet
+    new = B200UNet(unet)
+    wrapper.diffusion_model = new
+    return new

@@ -105,3 +105,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "raster_oracle" not in txt and "oracle/" not in txt.replace("oracle/_ref", ""), os.path.join(dp, f)
+
+
+def test_nn_header_symbols_exported():
+    import gvd_native
+
+    lib = gvd_native.nn()
+    declared = _declared_symbols_api("gvd_nn.h", "GVD_NN_API")
+    assert set(declared) == set(gvd_native.NN_SYMBOLS), (sorted(declared), sorted(gvd_native.NN_SYMBOLS))
+    for s in declared:
+        assert hasattr(lib, s), s
+    # argument validation happens before any CUDA call
+    assert lib.gvd_gemm_bf16(None, None) != 0 and b"null" in lib.gvd_nn_last_error()
+    assert lib.gvd_ddim_step(None, None) != 0
+
+
+def _declared_symbols_api(header, macro):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(macro + r"\s+[\w\s\*]+?\b(gvd_\w+)\s*\(", txt)))

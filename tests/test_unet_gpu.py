@@ -42,3 +42,39 @@ def test_unet_small_vs_reference(mc, t, h, w):
     print(f"rel L2: ours vs fp32 {e_ours:.3e}, ref-bf16 vs fp32 {e_ref:.3e}, ours vs ref-bf16 {e_pair:.3e}")
     assert e_ours <= 1.15 * e_ref + 1e-3
     assert e_pair <= 1.5 * (e_ours ** 2 + e_ref ** 2) ** 0.5
+
+
+def test_dropin_module_swaps_into_reference_wrapper():
+    """vc_b200.dropin.replace_unet: the reference call path model.model.diffusion_model(xc, t, context=cc, fs=fs) keeps
+    working; under no_grad it runs the native forward, with grad enabled it defers to the reference module."""
+    import unet_ref
+    from vc_b200.dropin import B200UNet, replace_unet
+
+    if not unet_ref.ref_available():
+        pytest.skip("oracle/_ref/ViewCrafter not installed")
+    ref, cfg = unet_ref.build_reference_unet(model_channels=64)
+
+    class Wrapper(torch.nn.Module):  # stands in for DiffusionWrapper (ddpm3d.py:1410-1425)
+        def __init__(self, m):
+            super().__init__()
+            self.diffusion_model = m
+
+    class LD:
+        pass
+
+    ld = LD()
+    ld.model = Wrapper(ref)
+    new = replace_unet(ld)
+    assert isinstance(ld.model.diffusion_model, B200UNet) and replace_unet(ld) is new
+    x, cc, ctx, _ = unet_ref.synth_inputs(3, 16, 16)
+    xin = torch.cat([x, cc], 1)
+    ts, fs = torch.tensor([300], device="cuda"), torch.tensor([10], device="cuda")
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y_ref = ref(xin, ts, context=ctx, fs=fs)
+        y_new = ld.model.diffusion_model(xin, ts, context=ctx, fs=fs)
+    assert _rel(y_new, y_ref) < 5e-2
+    xg = xin.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_g = ld.model.diffusion_model(xg, ts, context=ctx, fs=fs)
+    y_g.float().sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
