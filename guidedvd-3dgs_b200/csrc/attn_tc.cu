@@ -10,7 +10,9 @@
 //                             back to TMEM with tcgen05.st), running max / sum / output row (64 fp32) in registers;
 //                             O_j is read from TMEM and folded in with the usual exp(m_old - m_new) correction.
 // TMEM: S [0,128) | P [128,192) | O_j [192,256)  -> 256 columns, two CTAs per SM.
-// Logits are rounded exactly where the reference rounds them under autocast: bf16(bf16(q.k) * scale).
+// Logits stay in fp32 (acc * scale); the reference rounds them to bf16 twice before its fp32 softmax (attention.py:103),
+// which this kernel deliberately does not emulate: the emulation costs three ALU ops per score in a loop that is
+// MUFU/ALU-bound, and the difference is below the bf16 noise of the PV product (tests bound the error).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <string>
@@ -29,7 +31,11 @@ constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 1024 + 256;
 constexpr int FA_THREADS = 192;
 constexpr uint32_t FA_TMEM_COLS = 256, FA_S_COL = 0, FA_P_COL = 128, FA_O_COL = 192;
 
-__device__ __forceinline__ float bf16r_(float x) { return __bfloat162float(__float2bfloat16(x)); }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // MN-major B operand tile (V_j: 128 keys x 64 d, rows of 128 bytes, 128-byte swizzle): same geometry as the K-major
 // tile (8-row atoms of 1024 bytes); the "major" bit lives in the instruction descriptor.
@@ -160,21 +166,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             tc::mbar_wait(s_full, (uint32_t)(j & 1));
             tc::fence_after_sync();
             const int key0 = j * FA_BN;
-            // ---- pass 1: row max of the rounded logits ----
+            const bool tail = key0 + FA_BN > p.Nk;  // only the last key block can hold out-of-range keys
+            // ---- pass 1: row max of the raw scores (scale > 0, so the max commutes with the scaling) ----
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < FA_BN; c += 32) {
                 uint32_t v[32];
                 tc::tmem_ld32(tmem_base + lane_off + FA_S_COL + c, v);
                 tc::tmem_ld_wait();
+                if (!tail) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float x = bf16r_(bf16r_(__uint_as_float(v[e])) * p.scale);
-                    mx = fmaxf(mx, (key0 + c + e < p.Nk) ? x : -INFINITY);
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (key0 + c + e < p.Nk) ? __uint_as_float(v[e]) : -INFINITY);
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * L2E);
+            const float sl2 = p.scale * L2E;          // exp(x*scale - m) = exp2(x*sl2 - m*L2E), m kept in scaled units
+            const float m_new = fmaxf(m_run, mx * p.scale);
+            const float alpha = (m_run == -INFINITY) ? 0.f : ex2(( m_run - m_new) * L2E);
             const float mneg = -m_new * L2E;
             // ---- pass 2: P = exp(x - m_new) -> bf16 pairs -> TMEM ----
             float l_blk = 0.f;
@@ -185,14 +195,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
-                    float pe[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float x = bf16r_(bf16r_(__uint_as_float(v[e + u])) * p.scale);
-                        pe[u] = (key0 + c + e + u < p.Nk) ? exp2f(fmaf(x, L2E, mneg)) : 0.f;
-                        l_blk += pe[u];
+                    float p0 = ex2(fmaf(__uint_as_float(v[e]), sl2, mneg));
+                    float p1 = ex2(fmaf(__uint_as_float(v[e + 1]), sl2, mneg));
+                    if (tail) {
+                        if (key0 + c + e >= p.Nk) p0 = 0.f;
+                        if (key0 + c + e + 1 >= p.Nk) p1 = 0.f;
                     }
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(pe[0], pe[1]);
+                    l_blk += p0 + p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
                     pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
                 }
                 tmem_st16(tmem_base + lane_off + FA_P_COL + c / 2, pk);

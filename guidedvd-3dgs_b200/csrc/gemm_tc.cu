@@ -373,6 +373,22 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_ + half * HALF;
             const int bh = z % p.batch_h, bb = z / p.batch_h;
             const int buf = it & 1;
+            // residual rows of this warp's sub-tile: issue the (coalesced) loads now, they land while the tile's
+            // MMAs are still running
+            const long long base_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h;
+            const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
+            const int n = n0 + chunk * 8;
+            uint4 resv[32 / ROWS_PER_PASS];
+            if (p.residual != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
+                    const int m = m0 + q * 32 + i * ROWS_PER_PASS + rsub;
+                    resv[i] = make_uint4(0, 0, 0, 0);
+                    if (m < p.M && n < p.N)
+                        resv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                                       base_off + (long long)m * p.ldc + n));
+                }
+            }
             tc::mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             tc::fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + half * HALF);
@@ -397,18 +413,15 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
             // ---- phase 2: coalesced write-out (+ residual), ROWS_PER_PASS rows per warp instruction ----
-            const long long base_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h;
-            const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
-            const int n = n0 + chunk * 8;
-#pragma unroll 4
-            for (int r0 = 0; r0 < 32; r0 += ROWS_PER_PASS) {
-                const int rr = r0 + rsub;
+#pragma unroll
+            for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
+                const int rr = i * ROWS_PER_PASS + rsub;
                 const int m = m0 + q * 32 + rr;
                 if (m < p.M && n < p.N) {
                     uint4 val = *reinterpret_cast<const uint4*>(stage + rr * ROW_BYTES + ((chunk ^ (rr & SWZ)) << 4));
                     const long long off = base_off + (long long)m * p.ldc + n;
                     if (p.residual != nullptr) {
-                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + off));
+                        const uint4 rv = resv[i];
                         __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&val);
                         const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll

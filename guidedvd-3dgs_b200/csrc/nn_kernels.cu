@@ -50,7 +50,23 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
 #pragma unroll
         for (int e = 0; e < 8; ++e) sm[e] = sq[e] = 0.f;
         const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
-        for (int r = r0 + rsub; r < r1; r += rows_par) {
+        int r = r0 + rsub;
+        for (; r + 3 * rows_par < r1; r += 4 * rows_par) {  // four independent 16-byte loads in flight per thread
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = __ldg(base + (size_t)(r + k * rows_par) * vecs);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 t = __bfloat1622float2(h2[e]);
+                    sm[2 * e] += t.x; sq[2 * e] += t.x * t.x;
+                    sm[2 * e + 1] += t.y; sq[2 * e + 1] += t.y * t.y;
+                }
+            }
+        }
+        for (; r < r1; r += rows_par) {
             const uint4 u = __ldg(base + (size_t)r * vecs);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -411,6 +427,17 @@ __global__ void __launch_bounds__(256) ddim_update_kernel(const float* __restric
     }
 }
 
+int gn_chunks(int F, long long S) {
+    long long want = (592 + F - 1) / F;            // ~4 CTAs per SM in total
+    long long maxc = (S + 15) / 16;                // at least 16 rows per CTA
+    long long minc = (S + 4095) / 4096;            // at most 4096 rows per CTA
+    long long c = want < minc ? minc : want;
+    if (c > maxc) c = maxc;
+    if (c < 1) c = 1;
+    if (c > 2048) c = 2048;
+    return (int)c;
+}
+
 int grid_for(long long n, int block = 256, int cap = 148 * 16) {
     long long g = (n + block - 1) / block;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -428,15 +455,15 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
         g_nn_err_ext = "gvd_groupnorm_cl: needs C % groups == 0, C % 8 == 0, groups <= 128";
         return 2;
     }
-    int nchunks = (int)((S + 1023) / 1024);
-    if (nchunks > 512) nchunks = 512;
+    // enough CTAs to fill the chip even for small feature maps: >= ~2 waves of 148 SMs, >= 16 rows per CTA
+    int nchunks = gn_chunks(F, S);
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
     gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(float), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
                                                                                  rows_per_chunk, tmp);
-    const int rows_per_cta = 128;
-    gn_apply_kernel<<<dim3((unsigned)((S + rows_per_cta - 1) / rows_per_cta), F), 256, groups * 2 * sizeof(float), s>>>(
+    const int rows_per_cta = rows_per_chunk;
+    gn_apply_kernel<<<dim3((unsigned)nchunks, F), 256, groups * 2 * sizeof(float), s>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups, nchunks, rows_per_cta, eps, do_silu);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl: ") + cudaGetErrorString(e); return 1; }
@@ -444,9 +471,7 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
 }
 
 size_t gvd_groupnorm_tmp_floats(int F, long long S, int groups) {
-    int nchunks = (int)((S + 1023) / 1024);
-    if (nchunks > 512) nchunks = 512;
-    return (size_t)F * (nchunks + 1) * groups * 2;
+    return (size_t)F * (gn_chunks(F, S) + 1) * groups * 2;
 }
 
 int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,

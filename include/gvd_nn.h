@@ -89,7 +89,7 @@ GVD_NN_API int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long lon
 GVD_NN_API int gvd_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S,
                                       int H, float scale, gvd_nn_stream_t stream);
 
-/* Fused attention, head dim 64: out = softmax(bf16(bf16(q k^T) * scale)) v without materialising the scores
+/* Fused attention, head dim 64: out = softmax(q k^T * scale) v (fp32 logits) without materialising the scores
  * (CrossAttention.forward, attention.py:81-144; the reference's einsum path writes the full [b*h, Nq, Nk] matrix).
  * q, out: [B, Nq, H*64] bf16 (batch stride q_batch_stride elements); k, v: [B, Nk, H*64] bf16 (kv_batch_stride).
  * Shared keys for all batch items (text / image cross-attention): pass B = 1 and Nq = batch * tokens. */
