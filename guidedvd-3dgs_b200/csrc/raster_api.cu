@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 
 #include "../../include/gvd_raster.h"
@@ -256,34 +257,53 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     }
     GVD_STAGE("bin_count");
 
-    // Size of the instance list. Like the reference (rasterizer_impl.cu:281-282) this is the one
-    // host round trip of the forward: the binning buffer is caller-owned and sized from R.
-    int num_rendered = 0;
-    GVD_CHECK(cudaMemcpyAsync(&num_rendered, g.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, stream),
-              "copy num_rendered");
-    GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
-    a->num_rendered = num_rendered;
+    RasterBinPtrs b;
+    uint32_t capacity = 0xffffffffu;  // instance slots available in the binning buffer
+    bool have_instances = true;
+    if (a->spec_binning_buffer != nullptr && !debug) {
+        // speculative path: no host round trip; the caller validates R afterwards
+        if (!a->num_rendered_pinned) return fail_msg("gvd_raster_forward: speculative path needs num_rendered_pinned");
+        GVD_CHECK(cudaMemcpyAsync(a->num_rendered_pinned, g.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, stream),
+                  "copy num_rendered (async)");
+        if (a->r_ready_event) GVD_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->r_ready_event), stream), "record R event");
+        a->num_rendered = -1;
+        // largest R whose layout fits the caller's buffer
+        const size_t per = sizeof(uint32_t) + (a->export_keys ? sizeof(uint64_t) : 0);
+        const size_t fixed = gvd_raster_binning_bytes(0, a->export_keys);
+        const size_t room = a->spec_binning_bytes > fixed + 256 ? a->spec_binning_bytes - fixed - 256 : 0;
+        capacity = (uint32_t)std::min<size_t>(room / per, 0x7fffffffu);
+        char* bp = (char*)a->spec_binning_buffer;
+        b = carve_binning(bp, (size_t)capacity, a->export_keys != 0);
+    } else {
+        // Size of the instance list. Like the reference (rasterizer_impl.cu:281-282) this is the one
+        // host round trip of the forward: the binning buffer is caller-owned and sized from R.
+        int num_rendered = 0;
+        GVD_CHECK(cudaMemcpyAsync(&num_rendered, g.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, stream),
+                  "copy num_rendered");
+        GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
+        a->num_rendered = num_rendered;
+        char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered, a->export_keys));
+        if (!bp) return fail_msg("gvd_raster_forward: binning allocator returned null");
+        b = carve_binning(bp, (size_t)num_rendered, a->export_keys != 0);
+        have_instances = num_rendered > 0;
+    }
 
-    char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered, a->export_keys));
-    if (!bp) return fail_msg("gvd_raster_forward: binning allocator returned null");
-    RasterBinPtrs b = carve_binning(bp, (size_t)num_rendered, a->export_keys != 0);
-
-    if (num_rendered > 0) {
+    if (have_instances) {
         {
             // level 2b: stable scatter of the Gaussian ids into the tile lists
             StageScope t(GVD_STAGE_EMIT, stream);
-            GVD_CHECK(gvd_launch_bin_fill(P, g, b, im, grid, stream), "bin_fill");
+            GVD_CHECK(gvd_launch_bin_fill(P, g, b, im, grid, capacity, stream), "bin_fill");
         }
         GVD_STAGE("bin_fill");
         if (a->export_keys) {
             StageScope t(GVD_STAGE_PACK, stream);
-            gvd_launch_export_keys(num_rendered, g, b, im, grid, stream);
+            gvd_launch_export_keys(capacity, g, b, im, grid, stream);
         }
         GVD_STAGE("export_keys");
     }
     {
         StageScope t(GVD_STAGE_RENDER_FWD, stream);
-        gvd_launch_render_forward(*a, g, b, im, grid, stream);
+        gvd_launch_render_forward(*a, g, b, im, grid, capacity, stream);
     }
     GVD_STAGE("render_forward");
     return 0;

@@ -71,11 +71,11 @@ void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& 
                            dim3 grid, cudaStream_t s);
 cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, cudaStream_t s);
 cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                                dim3 grid, cudaStream_t s);
-void gvd_launch_export_keys(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+                                dim3 grid, uint32_t capacity, cudaStream_t s);
+void gvd_launch_export_keys(uint32_t capacity, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
                             dim3 grid, cudaStream_t s);
 void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
-                               const RasterImgPtrs& im, dim3 grid, cudaStream_t s);
+                               const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s);
 void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                 const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s);
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,

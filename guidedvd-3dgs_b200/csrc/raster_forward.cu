@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, u
                                                                 const uint32_t* __restrict__ chunk_flags,
                                                                 const uint32_t* __restrict__ hist,
                                                                 const uint2* __restrict__ ranges,
-                                                                uint32_t* __restrict__ point_list) {
+                                                                uint32_t* __restrict__ point_list, uint32_t capacity) {
     extern __shared__ uint32_t cnt[];
     __shared__ uint32_t s_id[GVD_BIN_CHUNK], s_n[GVD_BIN_CHUNK], s_r0[GVD_BIN_CHUNK], s_r1[GVD_BIN_CHUNK];
     __shared__ uint32_t s_total;
@@ -407,8 +407,10 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, u
             for (int g = 0; g < GVD_BIN_CHUNK; ++g) {
                 const uint32_t r0 = s_r0[g], r1 = s_r1[g];
                 // empty rects have r0 == r1 == 0 and fail the test
-                if (tx >= (r0 & 0xffff) && tx < (r1 & 0xffff) && ty >= (r0 >> 16) && ty < (r1 >> 16))
-                    point_list[slot++] = s_id[g];
+                if (tx >= (r0 & 0xffff) && tx < (r1 & 0xffff) && ty >= (r0 >> 16) && ty < (r1 >> 16)) {
+                    if (slot < capacity) point_list[slot] = s_id[g];  // capacity: speculative buffers may be too small
+                    ++slot;
+                }
             }
         }
         return;
@@ -429,19 +431,19 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, u
             const uint32_t t = (y0 + k / bw) * tiles_x + x0 + k % bw;
             const uint32_t slot = cnt[t];
             cnt[t] = slot + 1;
-            point_list[slot] = id;
+            if (slot < capacity) point_list[slot] = id;
         }
     }
 }
 
 // Optional (export_keys): rebuild the reference's sorted 64-bit keys for parity checks.
-__global__ void __launch_bounds__(256) export_keys_kernel(int R, int T, const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(256) export_keys_kernel(uint32_t capacity, int T, const uint2* __restrict__ ranges,
                                                           const uint32_t* __restrict__ point_list,
                                                           const uint32_t* __restrict__ depth_key,
                                                           uint64_t* __restrict__ keys) {
     const int tile = blockIdx.x;
     const uint2 r = ranges[tile];
-    for (uint32_t k = r.x + threadIdx.x; k < r.y; k += blockDim.x)
+    for (uint32_t k = r.x + threadIdx.x; k < r.y && k < capacity; k += blockDim.x)
         keys[k] = ((uint64_t)tile << 32) | depth_key[point_list[k]];
 }
 
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(256) export_keys_kernel(int R, int T, const ui
 __global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, float* __restrict__ out_color,
-    float* __restrict__ out_depth, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib) {
+    float* __restrict__ out_depth, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, uint32_t capacity) {
     __shared__ __align__(128) float4 buf[2][GVD_BATCH * 3];
     __shared__ __align__(128) IdSlot ids[3];
     __shared__ __align__(8) uint64_t bar[3];
@@ -464,7 +466,10 @@ __global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
     const float2 pixf = {(float)px, (float)py};
     const float sxf = (float)sub_x, syf = (float)sub_y;
 
-    const uint2 range = ranges[tile];
+    uint2 range = ranges[tile];
+    // a speculative instance buffer may be smaller than R: never read past it (the caller discards such a frame)
+    range.x = min(range.x, capacity);
+    range.y = min(range.y, capacity);
     const int n = (int)(range.y - range.x);
     const int rounds = (n + GVD_BATCH - 1) / GVD_BATCH;
     const uint32_t* list = point_list + range.x;
@@ -617,25 +622,25 @@ cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImg
 }
 
 cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                                dim3 grid, cudaStream_t s) {
+                                dim3 grid, uint32_t capacity, cudaStream_t s) {
     const int T = (int)(grid.x * grid.y);
     const size_t smem = (size_t)T * sizeof(uint32_t);
     cudaError_t e = ensure_smem((const void*)bin_fill_kernel, smem);
     if (e != cudaSuccess) return e;
     bin_fill_kernel<<<(unsigned)g.chunks, GVD_BIN_CHUNK, smem, s>>>(P, T, grid.x, g.splat, g.order, g.tiles_touched,
-                                                                   g.chunk_flags, g.hist, im.ranges, b.point_list);
+                                                                   g.chunk_flags, g.hist, im.ranges, b.point_list, capacity);
     return cudaGetLastError();
 }
 
-void gvd_launch_export_keys(int R, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+void gvd_launch_export_keys(uint32_t capacity, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
                             dim3 grid, cudaStream_t s) {
-    if (R <= 0 || !b.keys) return;
+    if (capacity == 0 || !b.keys) return;
     const int T = (int)(grid.x * grid.y);
-    export_keys_kernel<<<T, 256, 0, s>>>(R, T, im.ranges, b.point_list, g.depth_key, b.keys);
+    export_keys_kernel<<<T, 256, 0, s>>>(capacity, T, im.ranges, b.point_list, g.depth_key, b.keys);
 }
 
 void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
-                               const RasterImgPtrs& im, dim3 grid, cudaStream_t s) {
+                               const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s) {
     static bool carveout_set = false;
     if (!carveout_set) {  // eight 28 KB CTAs per SM need the large shared-memory carveout
         cudaFuncSetAttribute((const void*)render_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -643,7 +648,7 @@ void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPt
     }
     render_forward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height,
                                                                  grid.x, a.background, a.out_color, a.out_depth,
-                                                                 a.out_alpha, im.n_contrib);
+                                                                 a.out_alpha, im.n_contrib, capacity);
 }
 
 void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,

@@ -36,6 +36,23 @@ def _f32c(t, name):
 EXPORT_KEYS = False
 
 
+# Speculative sizing of the instance buffer: after the first frame on a device the shim allocates the buffer from the
+# previous frame's R (+25 %) and lets the library queue every stage without the host round trip the reference makes
+# (rasterizer_impl.cu:281-282); R arrives through pinned memory and is validated here, falling back to the exact,
+# synchronous path when a frame outgrows the guess.
+SPECULATE = os.environ.get("GVD_SPECULATE", "1") != "0"
+_spec_state = {}
+
+
+def _spec(dev):
+    st = _spec_state.get(dev)
+    if st is None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))  # forces creation of the underlying cudaEvent_t
+        st = _spec_state[dev] = {"last_R": None, "pinned": torch.zeros(1, dtype=torch.int32).pin_memory(), "event": ev}
+    return st
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -119,12 +136,32 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     a.out_color, a.out_depth, a.out_alpha, a.radii = (out_color.data_ptr(), out_depth.data_ptr(),
                                                         out_alpha.data_ptr(), radii.data_ptr())
     a.geom_alloc, a.binning_alloc, a.img_alloc = allocs.cb_geom, allocs.cb_binning, allocs.cb_img
+    st = _spec(dev) if (SPECULATE and not debug and not EXPORT_KEYS) else None
+    spec_buf = None
     with torch.cuda.device(dev):
+        if st is not None and st["last_R"] is not None:
+            nbytes = int(lib.gvd_raster_binning_bytes(int(st["last_R"] * 1.25) + 65536, 0))
+            spec_buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            a.spec_binning_buffer, a.spec_binning_bytes = spec_buf.data_ptr(), nbytes
+            a.num_rendered_pinned, a.r_ready_event = st["pinned"].data_ptr(), st["event"].cuda_event
         rc = lib.gvd_raster_forward(C.byref(a), _stream())
+        if rc == 0 and spec_buf is not None:
+            st["event"].synchronize()  # waits for the scan, not for the render kernels queued behind it
+            R = int(st["pinned"][0])
+            if int(lib.gvd_raster_binning_bytes(R, 0)) > a.spec_binning_bytes:
+                # the guess was too small: redo this frame on the exact path
+                a.spec_binning_buffer, a.spec_binning_bytes, spec_buf = None, 0, None
+                rc = lib.gvd_raster_forward(C.byref(a), _stream())
+            else:
+                a.num_rendered = R
     a.geom_alloc = a.binning_alloc = a.img_alloc = _n.ALLOC_FN(0)
     geom, binning, img = allocs.take()
+    if spec_buf is not None:
+        binning = spec_buf
     if rc != 0:
         raise RuntimeError("gvd_raster_forward failed: " + _n.last_error(lib))
+    if st is not None:
+        st["last_R"] = int(a.num_rendered)
     return (int(a.num_rendered), out_color, out_depth, out_alpha, radii, geom, binning, img)
 
 
@@ -152,14 +189,30 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
         return z(0, 3), z(0, 3), z(0, 1), z(0, 3), z(0, 6), z(0, M, 3), z(0, 3), z(0, 4)
 
-    e = lambda *s: torch.empty(*s, **f32)  # noqa: E731
-    dL_dmeans2D, dL_dmeans3D, dL_dopacity = e(P, 3), e(P, 3), e(P, 1)
-    # gradients of absent inputs are never consumed; return zeros-shaped views like the reference
-    dL_dcolors = e(P, 3) if has_colors else None
-    dL_dcov3D = e(P, 6) if has_cov else None
-    dL_dsh = e(P, M, 3) if has_sh else None
-    dL_dscales = e(P, 3) if has_scales else None
-    dL_drotations = e(P, 4) if has_scales else None
+    # All gradients are views of ONE flat allocation (16-byte aligned slices), so a data-parallel caller can sum them
+    # across ranks with a single collective on `grad.untyped_storage()` / `._base` without packing copies.
+    widths = [("means3D", 3), ("sh", 3 * M if has_sh else 0), ("opacity", 1), ("scales", 3 if has_scales else 0),
+              ("rot", 4 if has_scales else 0), ("colors", 3 if has_colors else 0), ("cov", 6 if has_cov else 0),
+              ("means2D", 3)]
+    offs, total = {}, 0
+    for name, w in widths:
+        offs[name] = total
+        total += (P * w + 3) // 4 * 4
+    flat = torch.empty(total, **f32)
+
+    def view(name, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        return flat[offs[name]:offs[name] + n].view(*shape)
+
+    dL_dmeans2D, dL_dmeans3D, dL_dopacity = view("means2D", P, 3), view("means3D", P, 3), view("opacity", P, 1)
+    # gradients of absent inputs are never consumed: None instead of the reference's unused zero tensors
+    dL_dcolors = view("colors", P, 3) if has_colors else None
+    dL_dcov3D = view("cov", P, 6) if has_cov else None
+    dL_dsh = view("sh", P, M, 3) if has_sh else None
+    dL_dscales = view("scales", P, 3) if has_scales else None
+    dL_drotations = view("rot", P, 4) if has_scales else None
     scratch = torch.empty(int(lib.gvd_raster_backward_scratch_bytes(P)), dtype=torch.uint8, device=dev)
 
     keep = [_f32c(t, n) for t, n in ((background, "background"), (means3D, "means3D"), (colors, "colors_precomp"),

@@ -25,6 +25,8 @@ class RasterForwardArgs(C.Structure):
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
         ("geom_alloc", ALLOC_FN), ("binning_alloc", ALLOC_FN), ("img_alloc", ALLOC_FN),
         ("alloc_user", C.c_void_p),
+        ("spec_binning_buffer", C.c_void_p), ("spec_binning_bytes", C.c_size_t),
+        ("num_rendered_pinned", C.c_void_p), ("r_ready_event", C.c_void_p),
         ("num_rendered", C.c_int),
     ]
 
@@ -71,7 +73,7 @@ RASTER_SYMBOLS = (
 )
 
 _raster = None
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 def lib_path(name="libgvd_raster.so"):

@@ -26,6 +26,16 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool
     grads = [g for g in grads if g is not None]
     if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
+    # Fast path: the rasterizer hands out all its gradients as views of one flat buffer -> reduce it in place.
+    base = grads[0]._base
+    if base is not None and base.dim() == 1 and all(g._base is base for g in grads):
+        lo = min(g.storage_offset() for g in grads)
+        hi = max(g.storage_offset() + g.numel() for g in grads)
+        seg = base[lo - base.storage_offset():hi - base.storage_offset()]
+        dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            seg /= dist.get_world_size(group)
+        return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:

@@ -40,7 +40,7 @@ typedef struct CUstream_st* gvd_stream_t; /* == cudaStream_t */
 typedef void* (*gvd_alloc_fn)(void* user, size_t bytes);
 
 /* Layout/version of the scratch buffers (bumped when the packed layouts change). */
-#define GVD_RASTER_ABI_VERSION 5
+#define GVD_RASTER_ABI_VERSION 6
 
 typedef struct GvdRasterForwardArgs {
     /* sizes -- DGR/cuda_rasterizer/rasterizer_impl.cu:197-224 */
@@ -75,6 +75,17 @@ typedef struct GvdRasterForwardArgs {
     gvd_alloc_fn binning_alloc;  /* called once with gvd_raster_binning_bytes(R,export_keys) */
     gvd_alloc_fn img_alloc;      /* called once with gvd_raster_img_bytes(W,H)       */
     void* alloc_user;
+    /* Optional speculative instance buffer (no host round trip).  When spec_binning_buffer != NULL the library does NOT
+     * synchronise to learn R: it copies R asynchronously to *num_rendered_pinned (pinned host memory), records
+     * r_ready_event (a cudaEvent_t) right after that copy, and queues the remaining stages against the caller's buffer
+     * of spec_binning_bytes bytes (writes and reads are clamped to it).  The caller waits on the event, reads R, and if
+     * gvd_raster_binning_bytes(R, export_keys) > spec_binning_bytes the outputs are invalid and the call must be
+     * repeated with a larger buffer (or with spec_binning_buffer = NULL, the synchronous path of the reference,
+     * rasterizer_impl.cu:281-286).  num_rendered is set to -1 on this path. */
+    void* spec_binning_buffer;
+    size_t spec_binning_bytes;
+    int* num_rendered_pinned;
+    void* r_ready_event;
     /* result */
     int num_rendered;            /* out: R = number of (Gaussian,tile) instances     */
 } GvdRasterForwardArgs;
