@@ -88,11 +88,24 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
     for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = sh[i];
 }
 
+// Fold the per-chunk partials of one frame into (sum, sumsq) per group: the exchange unit when the rows of a group are
+// spread over several GPUs.
+__global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks,
+                                                      int groups) {
+    const int f = blockIdx.x;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+        double a = 0.0;
+        for (int c = 0; c < nchunks; ++c) a += partial[((size_t)f * nchunks + c) * groups * 2 + i];
+        stats[(size_t)f * groups * 2 + i] = (float)a;
+    }
+}
+
 // Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ partial, int S, int C, int groups,
-                                                       int nchunks, int rows_per_cta, float eps, int do_silu) {
+                                                       int nchunks, int rows_per_cta, float eps, int do_silu,
+                                                       long long stat_rows) {
     extern __shared__ float sh[];  // mean[groups], rstd[groups]
     const int f = blockIdx.y;
     const int cpg = C / groups, vecs = C / 8;
@@ -103,7 +116,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
             s += p[0];
             q += p[1];
         }
-        const double n = (double)S * cpg;
+        const double n = (double)stat_rows * cpg;  // rows behind the sums (> S when the sums were added up across shards)
         const double mean = s / n;
         const double var = fmax(q / n - mean * mean, 0.0);
         sh[threadIdx.x] = (float)mean;
@@ -464,9 +477,48 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
                                                                                  rows_per_chunk, tmp);
     const int rows_per_cta = rows_per_chunk;
     gn_apply_kernel<<<dim3((unsigned)nchunks, F), 256, groups * 2 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups, nchunks, rows_per_cta, eps, do_silu);
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups, nchunks, rows_per_cta, eps, do_silu, S);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+int gvd_groupnorm_cl_stats(const void* x, float* stats, int F, long long S, int C, int groups, float* tmp, size_t tmp_floats,
+                           gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (F <= 0) return 0;
+    if (C % groups != 0 || C % 8 != 0 || groups > 128) {
+        g_nn_err_ext = "gvd_groupnorm_cl_stats: needs C % groups == 0, C % 8 == 0, groups <= 128";
+        return 2;
+    }
+    if (S <= 0) return cudaMemsetAsync(stats, 0, sizeof(float) * F * groups * 2, s) == cudaSuccess ? 0 : 1;
+    int nchunks = gn_chunks(F, S);
+    const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
+    nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
+    if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl_stats: scratch too small"; return 2; }
+    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(float), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
+                                                                                 rows_per_chunk, tmp);
+    gn_fold_kernel<<<F, 256, 0, s>>>(tmp, stats, nchunks, groups);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_stats: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+int gvd_groupnorm_cl_apply(const void* x, void* y, const float* gamma, const float* beta, const float* stats, int F, long long S,
+                           long long stat_rows, int C, int groups, float eps, int do_silu, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (F <= 0 || S <= 0) return 0;
+    if (C % groups != 0 || C % 8 != 0 || groups > 128 || stat_rows < S) {
+        g_nn_err_ext = "gvd_groupnorm_cl_apply: needs C % groups == 0, C % 8 == 0, groups <= 128, stat_rows >= S";
+        return 2;
+    }
+    int nchunks = gn_chunks(F, S);
+    const int rows_per_cta = (int)((S + nchunks - 1) / nchunks);
+    nchunks = (int)((S + rows_per_cta - 1) / rows_per_cta);
+    gn_apply_kernel<<<dim3((unsigned)nchunks, F), 256, groups * 2 * sizeof(float), s>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, (int)S, C, groups, 1, rows_per_cta, eps, do_silu, stat_rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_apply: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
 

@@ -167,7 +167,7 @@ class DdimArgs(C.Structure):
 
 NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", "gvd_groupnorm_cl", "gvd_layernorm",
               "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention",
-              "gvd_ddim_step", "gvd_flash_attention")
+              "gvd_ddim_step", "gvd_flash_attention", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply")
 _nn = None
 
 
@@ -187,6 +187,8 @@ def nn():
     lib.gvd_groupnorm_tmp_floats.restype = C.c_size_t
     lib.gvd_groupnorm_tmp_floats.argtypes = [i32, ll, i32]
     lib.gvd_groupnorm_cl.argtypes = [vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    lib.gvd_groupnorm_cl_stats.argtypes = [vp, vp, i32, ll, i32, i32, vp, C.c_size_t, vp]
+    lib.gvd_groupnorm_cl_apply.argtypes = [vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]
     lib.gvd_layernorm.argtypes = [vp, vp, vp, vp, ll, i32, f32, vp]
     lib.gvd_geglu.argtypes = [vp, vp, ll, i32, vp]
     lib.gvd_softmax_rows.argtypes = [vp, i32, ll, vp, ll, ll, i32, vp]
@@ -196,7 +198,7 @@ def nn():
     lib.gvd_ddim_step.argtypes = [C.POINTER(DdimArgs), vp]
     lib.gvd_flash_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]
     lib.gvd_flash_attention.restype = C.c_int
-    for n in ("gvd_groupnorm_cl", "gvd_layernorm", "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl",
+    for n in ("gvd_groupnorm_cl", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply", "gvd_layernorm", "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl",
               "gvd_temporal_attention", "gvd_ddim_step"):
         getattr(lib, n).restype = C.c_int
     _nn = lib

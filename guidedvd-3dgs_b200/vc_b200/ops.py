@@ -84,6 +84,28 @@ def groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
     return y
 
 
+def groupnorm_sharded(x, gamma, beta, F, S_local, S_total, part, groups=32, eps=1e-5, silu=False):
+    """GroupNorm whose rows are spread over the ranks of `part` (vc_b200.frame_parallel.FramePartition): local
+    (sum, sumsq) -> one all-reduce of F*groups*2 floats -> local normalisation with the global statistics."""
+    lib = _n.nn()
+    Cc = x.shape[-1]
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    nfl = int(lib.gvd_groupnorm_tmp_floats(int(F), int(max(S_local, 1)), int(groups)))
+    key = (x.device, nfl)
+    tmp = _gn_tmp.get(key)
+    if tmp is None:
+        tmp = _gn_tmp[key] = torch.empty(nfl, dtype=torch.float32, device=x.device)
+    stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
+    _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S_local), int(Cc), int(groups), tmp.data_ptr(),
+                                      nfl, _stream()), lib, "gvd_groupnorm_cl_stats")
+    part.sum_stats(stats)
+    _check(lib.gvd_groupnorm_cl_apply(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), int(F),
+                                      int(S_local), int(S_total), int(Cc), int(groups), float(eps), int(silu), _stream()), lib,
+           "gvd_groupnorm_cl_apply")
+    return y
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     lib = _n.nn()
     x = x.contiguous()

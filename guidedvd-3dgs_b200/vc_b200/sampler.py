@@ -16,6 +16,15 @@ from . import ops
 from .schedule import DdimSchedule
 
 
+def _randn(model, shape, device):
+    """Fresh Gaussian noise; under a multi-GPU plan rank 0 draws it and broadcasts, so every rank steps the same latent."""
+    z = torch.randn(shape, device=device)
+    plan = getattr(model, "plan", None)
+    if plan is not None and plan.world > 1:
+        torch.distributed.broadcast(z, src=0)
+    return z
+
+
 class DDIMSampler:
     def __init__(self, model, schedule="linear", **kwargs):
         self.model = model
@@ -33,7 +42,7 @@ class DDIMSampler:
                temperature=1., noises=None, device="cuda", **kwargs):
         self.make_schedule(S, ddim_discretize=timestep_spacing, ddim_eta=eta, verbose=verbose)
         size = (batch_size, *shape)
-        img = torch.randn(size, device=device) if x_T is None else x_T
+        img = _randn(self.model, size, device) if x_T is None else x_T
         steps = self.ddim_timesteps.shape[0]
         inter = {"x_inter": [img], "pred_x0": [img]}
         for i, step in enumerate(np.flip(self.ddim_timesteps)):
@@ -58,12 +67,17 @@ class DDIMSampler:
                                        _index_cond(unconditional_conditioning, i), guidance_rescale, temperature,
                                        None if noise is None else noise[i:i + 1], **kwargs) for i in range(x.shape[0])]
             return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
-        e_c = self.model.apply_model(x, t, c, **kwargs)
         e_u = None
         if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
-            e_u = self.model.apply_model(x, t, unconditional_conditioning, **kwargs)
+            if hasattr(self.model, "apply_model_cfg"):  # lets a multi-GPU plan run the two forwards on different ranks
+                e_c, e_u = self.model.apply_model_cfg(x, t, c, unconditional_conditioning, **kwargs)
+            else:
+                e_c = self.model.apply_model(x, t, c, **kwargs)
+                e_u = self.model.apply_model(x, t, unconditional_conditioning, **kwargs)
+        else:
+            e_c = self.model.apply_model(x, t, c, **kwargs)
         if noise is None:
-            noise = torch.randn(x.shape, device=x.device)
+            noise = _randn(self.model, x.shape, x.device)
         coef = self.ddim.coefficients(index, unconditional_guidance_scale, guidance_rescale, temperature)
         return ops.ddim_step(x.float().contiguous(), e_c.float().contiguous(),
                              None if e_u is None else e_u.float().contiguous(), noise.float().contiguous(), coef)

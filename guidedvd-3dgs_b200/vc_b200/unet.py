@@ -75,7 +75,7 @@ class ResBlock:
             t = pre + ".temopral_conv"
             self.tconv = [(p.norm(f"{t}.conv{i}.0"), p.conv_t3(f"{t}.conv{i}.{2 if i == 1 else 3}")) for i in (1, 2, 3, 4)]
 
-    def __call__(self, x, F, H, W, emb_silu, B):
+    def __call__(self, x, F, H, W, emb_silu, B, T=None, part=None):
         S = H * W
         h = ops.groupnorm(x, *self.gn1, F, S, eps=1e-5, silu=1)
         emb_out = ops.linear(emb_silu, *self.emb).float().reshape(-1).contiguous()  # [Cout], bf16-rounded values
@@ -84,12 +84,21 @@ class ResBlock:
         skip = x if self.skip is None else ops.linear(x, *self.skip)
         h, _, _ = ops.conv3x3(h, F, H, W, *self.conv2, residual=skip)
         if self.tconv is not None:
-            T = F // B
+            T = F // B if T is None else T
+            sharded = part is not None and part.active
+            if sharded:  # frames -> pixels: every pixel of this rank's slice sees all T frames
+                h = part.to_pixels(h)
+            Sl = h.shape[1]
             ident = h
             for i, (gn, conv) in enumerate(self.tconv):
                 # plain nn.GroupNorm: fp32 out under autocast, SiLU in fp32, one rounding at the conv input
-                g = ops.groupnorm(h, *gn, B, T * S, eps=1e-5, silu=2)
-                h = ops.conv_t3(g, B, T, S, *conv, residual=ident if i == 3 else None)
+                if sharded:
+                    g = ops.groupnorm_sharded(h, *gn, B, T * Sl, T * S, part, eps=1e-5, silu=2)
+                else:
+                    g = ops.groupnorm(h, *gn, B, T * S, eps=1e-5, silu=2)
+                h = ops.conv_t3(g, B, T, Sl, *conv, residual=ident if i == 3 else None)
+            if sharded:
+                h = part.to_frames(h, S)
         return h
 
 
@@ -164,15 +173,24 @@ class TemporalTransformer:
         self.blk = _TBlock(p, pre + ".transformer_blocks.0", False)
         self.proj_out = p.lin(pre + ".proj_out")
 
-    def __call__(self, x, B, T, S):
+    def __call__(self, x, B, T, S, part=None):
         b = self.blk
-        h = ops.linear(ops.groupnorm(x, *self.norm, B, T * S, eps=1e-6, silu=0), *self.proj_in)
+        sharded = part is not None and part.active
+        if sharded:  # the whole block runs pixel-sharded: attention over t needs every frame of a pixel
+            x = part.to_pixels(x)
+            Sl = x.shape[1]
+            n = ops.groupnorm_sharded(x, *self.norm, B, T * Sl, T * S, part, eps=1e-6, silu=0)
+        else:
+            Sl = S
+            n = ops.groupnorm(x, *self.norm, B, T * S, eps=1e-6, silu=0)
+        h = ops.linear(n, *self.proj_in)
         for at, n in ((b.attn1, b.n1), (b.attn2, b.n2)):
             a = ops.layernorm(h, *n)
-            o = ops.temporal_attention(ops.linear(a, at.q), ops.linear(a, at.k), ops.linear(a, at.v), B, T, S, at.heads, at.scale)
+            o = ops.temporal_attention(ops.linear(a, at.q), ops.linear(a, at.k), ops.linear(a, at.v), B, T, Sl, at.heads, at.scale)
             h = ops.linear(o, *at.o, residual=h)
         h = b.ff(h)
-        return ops.linear(h, *self.proj_out, residual=x)
+        y = ops.linear(h, *self.proj_out, residual=x)
+        return part.to_frames(y, S) if sharded else y
 
 
 class UNetB200:
@@ -228,11 +246,11 @@ class UNetB200:
     def _run(self, layers, h, st):
         for kind, m in layers:
             if kind == "res":
-                h = m(h, st["F"], st["H"], st["W"], st["emb_silu"], st["B"])
+                h = m(h, st["F"], st["H"], st["W"], st["emb_silu"], st["B"], st["T"], st["part"])
             elif kind == "st":
                 h = m(h, st["F"], st["H"] * st["W"], st["ctx_text"], st["ctx_img"])
             elif kind == "tt":
-                h = m(h, st["B"], st["F"] // st["B"], st["H"] * st["W"])
+                h = m(h, st["B"], st["T"], st["H"] * st["W"], st["part"])
             elif kind == "conv":
                 h, _, _ = ops.conv3x3(h, st["F"], st["H"], st["W"], *m)
             elif kind == "down":
@@ -241,6 +259,7 @@ class UNetB200:
                 h, st["H"], st["W"] = ops.conv3x3(h, st["F"], st["H"], st["W"], *m, upsample=True)
         return h
 
+    part = None   # vc_b200.frame_parallel.FramePartition: this rank's frame slice (None / inactive = all frames here)
     trace = None  # set to a list to record (name, activation[F, S, C]) after every top-level block (tests/debug)
 
     def _rec(self, name, h, st):
@@ -249,7 +268,9 @@ class UNetB200:
 
     @torch.no_grad()
     def forward(self, x, timesteps, context, fs=None):
-        """x [1, C_in, t, h, w] fp32; timesteps [1]; context [1, 77+256, 1024]; fs [1] -> [1, C_out, t, h, w] bf16."""
+        """x [1, C_in, t, h, w] fp32; timesteps [1]; context [1, 77+256, 1024]; fs [1] -> [1, C_out, t, h, w] bf16.
+        With an active `self.part` the input is still the full clip; the result holds this rank's frames only
+        ([1, C_out, F_r, h, w]); DiffusionModelB200 gathers them."""
         b, cin, t, hh, ww = x.shape
         if b != 1:
             return torch.cat([self.forward(x[i:i + 1], timesteps[i:i + 1], context[i:i + 1], None if fs is None else fs[i:i + 1])
@@ -261,15 +282,20 @@ class UNetB200:
             emb = emb + self._mlp(timestep_embedding(fs, self.model_channels), self.fps_embedding)
         emb_silu = torch.nn.functional.silu(emb)  # [1, 4*mc] bf16: the input of every ResBlock's emb_layers
         ctx = context.to(BF16)
-        st = dict(B=b, F=b * t, H=hh, W=ww, emb_silu=emb_silu, ctx_text=ctx[:, :77].contiguous(),
-                  ctx_img=ctx[:, 77:].contiguous())
-        h = x.permute(0, 2, 3, 4, 1).reshape(b * t, hh * ww, cin).to(BF16).contiguous()
+        part = self.part if (self.part is not None and self.part.active) else None
+        if part is not None:
+            assert part.T == t, "frame partition was built for a different clip length"
+            x = x[:, :, part.frame_slice()]
+        fl = x.shape[2]
+        st = dict(B=b, F=b * fl, T=t, H=hh, W=ww, emb_silu=emb_silu, ctx_text=ctx[:, :77].contiguous(),
+                  ctx_img=ctx[:, 77:].contiguous(), part=part)
+        h = x.permute(0, 2, 3, 4, 1).reshape(b * fl, hh * ww, cin).to(BF16).contiguous()
         hs = []
         for i, layers in enumerate(self.input_blocks):
             h = self._run(layers, h, st)
             self._rec(f"input_blocks.{i}", h, st)
             if i == 0 and self.init_attn is not None:
-                h = self.init_attn(h, b, t, st["H"] * st["W"])
+                h = self.init_attn(h, b, t, st["H"] * st["W"], part)
                 self._rec("init_attn", h, st)
             hs.append(h)
         h = self._run(self.middle, h, st)
@@ -281,7 +307,7 @@ class UNetB200:
         # `h = h.type(x.dtype)`: the last norm/SiLU run in fp32, one rounding at the conv input (openaimodel3d.py:598-599)
         h = ops.groupnorm(h, *self.out_norm, st["F"], st["H"] * st["W"], eps=1e-5, silu=2)
         y, _, _ = ops.conv3x3(h, st["F"], st["H"], st["W"], *self.out_conv)
-        return y.view(b, t, st["H"], st["W"], -1).permute(0, 4, 1, 2, 3).contiguous()
+        return y.view(b, fl, st["H"], st["W"], -1).permute(0, 4, 1, 2, 3).contiguous()
 
     __call__ = forward
 
@@ -291,10 +317,32 @@ class DiffusionModelB200:
     conditioning of DiffusionWrapper.forward (lvdm/models/ddpm3d.py:1426-1443): channel-concat c_concat, cross-attend
     to cat(c_crossattn)."""
 
-    def __init__(self, unet, schedule):
-        self.unet, self.schedule = unet, schedule
+    def __init__(self, unet, schedule, plan=None):
+        """plan: vc_b200.frame_parallel.DenoisePlan (one process per GPU) or None for a single GPU."""
+        self.unet, self.schedule, self.plan = unet, schedule, plan
+        if plan is not None:
+            unet.part = plan.part
 
-    def apply_model(self, x, t, cond, fs=None, **kwargs):
+    def _local(self, x, t, cond, fs):
         xc = torch.cat([x] + list(cond["c_concat"]), dim=1)
         cc = torch.cat(list(cond["c_crossattn"]), dim=1)
         return self.unet(xc, t, cc, fs=fs).float()
+
+    def apply_model(self, x, t, cond, fs=None, **kwargs):
+        y = self._local(x, t, cond, fs)
+        if self.plan is None or self.plan.world == 1:
+            return y
+        if self.plan.cfg_ways == 1:
+            return self.plan.gather_outputs(y)[0]
+        raise RuntimeError("CFG-split plan: call apply_model_cfg (each rank evaluates one of cond / uncond)")
+
+    def apply_model_cfg(self, x, t, cond, uncond, fs=None, **kwargs):
+        """Both forwards of a classifier-free-guidance step (ddim.py:222-223) -> (e_cond, e_uncond), full clips on every
+        rank.  Under a CFG-split plan each rank runs one of them on its frame slice."""
+        plan = self.plan
+        if plan is None or plan.world == 1:
+            return self._local(x, t, cond, fs), self._local(x, t, uncond, fs)
+        if plan.cfg_ways == 1:
+            return plan.gather_outputs(self._local(x, t, cond, fs))[0], plan.gather_outputs(self._local(x, t, uncond, fs))[0]
+        e_c, e_u = plan.gather_outputs(self._local(x, t, cond if plan.cfg_index == 0 else uncond, fs))
+        return e_c, e_u

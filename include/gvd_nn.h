@@ -62,6 +62,16 @@ GVD_NN_API size_t gvd_groupnorm_tmp_floats(int F, long long S, int groups);
 GVD_NN_API int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* beta, int F, long long S, int C,
                                 int groups, float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream);
 
+/* The same normalisation split at its reduction, for a group whose rows are sharded across GPUs (frame- or
+ * pixel-sharded TemporalConvBlock / TemporalTransformer norms): `_stats` writes (sum, sum of squares)
+ * per (frame, group) of the LOCAL rows into stats[F, groups, 2]; the caller adds the shards' stats (one all-reduce of
+ * 2*F*groups floats) and `_apply` normalises the local rows with them, stat_rows = total rows behind the sums. */
+GVD_NN_API int gvd_groupnorm_cl_stats(const void* x, float* stats, int F, long long S, int C, int groups, float* tmp,
+                                      size_t tmp_floats, gvd_nn_stream_t stream);
+GVD_NN_API int gvd_groupnorm_cl_apply(const void* x, void* y, const float* gamma, const float* beta, const float* stats, int F,
+                                      long long S, long long stat_rows, int C, int groups, float eps, int do_silu,
+                                      gvd_nn_stream_t stream);
+
 /* LayerNorm over the last dimension of x[rows, C] (bf16 in/out) -- BasicTransformerBlock.norm1/2/3 (attention.py:236-238). */
 GVD_NN_API int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
                              gvd_nn_stream_t stream);

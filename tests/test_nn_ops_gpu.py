@@ -31,6 +31,42 @@ def test_groupnorm(F, S, C, silu):
     _close(y, ref)
 
 
+@pytest.mark.parametrize("S,C,cut,silu", [(25 * 144, 1280, 25 * 36, 2), (1000, 320, 333, 0)])
+def test_groupnorm_sharded_rows(S, C, cut, silu):
+    """Statistics added up across two row shards (what two ranks exchange) reproduce the unsharded norm."""
+    from vc_b200 import ops
+
+    class TwoShards:  # stands in for FramePartition.sum_stats: adds the other shard's (sum, sumsq)
+        def __init__(self):
+            self.seen, self.other = [], None
+
+        def sum_stats(self, st):
+            if self.other is None:
+                self.seen.append(st.clone())
+            else:
+                st += self.other
+            return st
+
+    g = torch.Generator(device="cuda").manual_seed(C + S)
+    x = (torch.randn(1, S, C, device="cuda", generator=g) * 2 + 0.5).to(BF)
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    full = ops.groupnorm(x, gamma, beta, 1, S, groups=32, eps=1e-6, silu=silu)
+    halves = [x[:, :cut].contiguous(), x[:, cut:].contiguous()]
+    probe = TwoShards()
+    for hx in halves:  # first pass only records each shard's local statistics
+        ops.groupnorm_sharded(hx, gamma, beta, 1, hx.shape[1], S, probe, groups=32, eps=1e-6, silu=silu)
+    outs = []
+    for i, hx in enumerate(halves):
+        part = TwoShards()
+        part.other = probe.seen[1 - i]
+        outs.append(ops.groupnorm_sharded(hx, gamma, beta, 1, hx.shape[1], S, part, groups=32, eps=1e-6, silu=silu))
+    got = torch.cat(outs, dim=1)
+    # identical up to the fp32 summation order of the statistics: at most one bf16 ulp on isolated elements
+    d = (got.float() - full.float()).abs()
+    assert float(d.max()) <= 2 ** -6 * float(full.float().abs().max()) and float((d > 0).float().mean()) < 0.01
+
+
 def test_layernorm_geglu_softmax():
     from vc_b200 import ops
 
