@@ -186,10 +186,18 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # N > 1: the backward writes its gradients straight into this rank's peer-mapped exchange buffer and the sum over
+    # ranks is one launch of the library's NVLink peer-memory kernel (include/gvd_exchange.h); the reference arm, which
+    # has no such hook, sums its gradients with NCCL.
+    exchange = None
+    if world > 1 and args.impl == "ours":
+        exchange = view_parallel.GradientExchange(pkg.gradient_buffer_floats(P), dev)
+        pkg.set_gradient_buffer(exchange.buffer)
+
     def resident_step():
         step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
         if world > 1:
-            view_parallel.allreduce_gradients(grad_flat(leaves))
+            view_parallel.allreduce_gradients(grad_flat(leaves), exchange=exchange)
 
     # End-to-end step: this step's inputs (camera, cotangent images) come from pinned host memory. Like a
     # prefetching data loader, the upload of step k+1 is issued on a copy stream while step k computes.
@@ -218,7 +226,7 @@ def main():
         staged["n"] = k + 2
         color, radii = step(cot, cm[0:16].view(4, 4), cm[16:32].view(4, 4), cm[32:35])
         if world > 1:
-            view_parallel.allreduce_gradients(grad_flat(leaves))
+            view_parallel.allreduce_gradients(grad_flat(leaves), exchange=exchange)
         # The step's result: the scalar a trainer reads back every iteration (train_baseline.py:88). It is copied
         # to pinned host memory asynchronously and READ one step later (asynchronous loss logging), so the host
         # never idles the GPU; every step's value is read inside the timed region (the last one by e2e_flush).
@@ -324,6 +332,9 @@ def main():
                     "traversed_note": "render_* GB/s use SURVEY 8d's whole-list byte count (44 B x R); tiles stop early and "
                                       "actually walk only a few % of their lists"}
 
+    if exchange is not None:
+        pkg.set_gradient_buffer(None)
+        exchange.close()
     denoise_result = None
     if not args.no_denoise and (world == 1 or args.impl == "ours"):
         # every rank takes part: at N > 1 the DDIM step is CFG-split x frame-sharded (vc_b200/frame_parallel.py)
@@ -351,13 +362,14 @@ def main():
         "config": {"workload": args.workload, "description": desc, "P": P, "width": W, "height": H, "sh_degree": D,
                    "num_rendered": R, "visible": visible, "tiles": tiles,
                    "l2_policy": f"inputs larger than L2: per-step working set ~{ws_mb:.0f} MB > 126 MB",
-                   "parallelism": f"view-parallel dp{world}" + (" + NCCL all-reduce of 62 floats/Gaussian per step" if world > 1 else "")},
+                   "parallelism": f"view-parallel dp{world}" + ((" + gradient sum of 59 floats/Gaussian per step: " + ("one NVLink peer-memory kernel (gvd_exchange_allreduce_sum)"
+                                   if args.impl == "ours" else "NCCL all-reduce")) if world > 1 else "")},
         "e2e": {"value": round(e2e_views_per_s, 2), "unit": "views/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4), "wall_ms_per_step": round(wall_e2e / K * 1e3, 4)},
-        "gpu_launches": (8 * K * 2) if args.impl == "ours" else 0,
+        "gpu_launches": ((8 + (1 if world > 1 else 0)) * K * 2) if args.impl == "ours" else 0,
         "gpu_launches_note": "own kernels in the two timed regions: preprocess, bin_count, bin_prefix, bin_ranges, bin_fill, "
-                             "render_fwd, render_bwd, gaussian_bwd per step (+ CUB radix-sort library kernels for the "
-                             "depth sort, not counted)",
+                             "render_fwd, render_bwd, gaussian_bwd per step, + grad_allreduce_kernel at N > 1 (+ CUB radix-sort "
+                             "library kernels for the depth sort, not counted)",
         "clocks": clocks,
     }
     if roofline:

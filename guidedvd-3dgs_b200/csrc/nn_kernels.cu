@@ -34,10 +34,13 @@ __device__ __forceinline__ float warp_max(float v) {
 // Pass 1: grid (chunks, F): partial (sum, sumsq) per (frame, chunk, group).
 __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int groups,
                                                          int rows_per_chunk, float* __restrict__ partial) {
-    extern __shared__ float sh[];  // [groups*2]
+    // Per-thread fp32 sums are merged in 2^-20 fixed point: integer adds commute, so the statistics (and with them the
+    // whole denoiser) are bit-reproducible run to run, whatever order the atomics land in.
+    extern __shared__ unsigned long long sh_fix[];  // [groups*2]
+    unsigned long long* sh = sh_fix;
     const int f = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int cpg = C / groups, vecs = C / 8;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0ull;
     __syncthreads();
     const int r0 = chunk * rows_per_chunk, r1 = min(S, r0 + rows_per_chunk);
     // vecs <= 256: 256/vecs rows in flight per step; wider rows: one row per step, threads stride over the vectors
@@ -79,13 +82,13 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int g = (8 * v + e) / cpg;
-            atomicAdd(&sh[2 * g], sm[e]);
-            atomicAdd(&sh[2 * g + 1], sq[e]);
+            atomicAdd(&sh[2 * g], (unsigned long long)__double2ll_rn((double)sm[e] * 1048576.0));
+            atomicAdd(&sh[2 * g + 1], (unsigned long long)__double2ll_rn((double)sq[e] * 1048576.0));
         }
     }
     __syncthreads();
     float* out = partial + ((size_t)f * nchunks + chunk) * groups * 2;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = sh[i];
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = (float)((double)(long long)sh[i] * (1.0 / 1048576.0));
 }
 
 // Fold the per-chunk partials of one frame into (sum, sumsq) per group: the exchange unit when the rows of a group are
@@ -473,7 +476,7 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
-    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(float), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
+    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(unsigned long long), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
                                                                                  rows_per_chunk, tmp);
     const int rows_per_cta = rows_per_chunk;
     gn_apply_kernel<<<dim3((unsigned)nchunks, F), 256, groups * 2 * sizeof(float), s>>>(
@@ -496,7 +499,7 @@ int gvd_groupnorm_cl_stats(const void* x, float* stats, int F, long long S, int 
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl_stats: scratch too small"; return 2; }
-    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(float), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
+    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(unsigned long long), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
                                                                                  rows_per_chunk, tmp);
     gn_fold_kernel<<<F, 256, 0, s>>>(tmp, stats, nchunks, groups);
     cudaError_t e = cudaGetLastError();

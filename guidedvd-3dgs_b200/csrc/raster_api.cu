@@ -10,9 +10,10 @@
 #include "../../include/gvd_raster.h"
 #include "raster_common.cuh"
 
-namespace {
+thread_local std::string g_raster_err;  // shared with grad_exchange.cu; hidden visibility keeps it out of the ABI
+#define g_err g_raster_err
 
-thread_local std::string g_err;
+namespace {
 
 int fail(const char* what, cudaError_t e) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);

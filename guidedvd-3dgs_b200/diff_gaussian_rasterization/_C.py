@@ -53,6 +53,25 @@ def _spec(dev):
     return st
 
 
+# Optional caller-owned gradient storage per device (set_gradient_buffer): the backward then writes its gradients there
+# instead of into fresh memory, e.g. into the peer-mapped exchange buffer of view_parallel.GradientExchange so the
+# cross-GPU sum needs no packing copy.  The gradients of two backward calls then alias: consume them in between.
+_grad_buffer = {}
+
+
+def gradient_buffer_floats(P, M=16):
+    """Floats a gradient buffer must hold for P Gaussians with M SH coefficients (every optional gradient present)."""
+    return sum((P * w + 3) // 4 * 4 for w in (3, 3 * M, 1, 3, 4, 3, 6, 3))
+
+
+def set_gradient_buffer(buf):
+    """buf: 1-D float32 CUDA tensor (>= 62 floats per Gaussian + padding) or None to restore fresh allocations."""
+    if buf is None:
+        _grad_buffer.clear()
+    else:
+        _grad_buffer[buf.device] = buf
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -198,7 +217,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     for name, w in widths:
         offs[name] = total
         total += (P * w + 3) // 4 * 4
-    flat = torch.empty(total, **f32)
+    ext = _grad_buffer.get(dev)
+    flat = ext[:total] if (ext is not None and ext.numel() >= total) else torch.empty(total, **f32)
 
     def view(name, *shape):
         n = 1

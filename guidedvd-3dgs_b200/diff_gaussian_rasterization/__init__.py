@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _C
+from ._C import gradient_buffer_floats, set_gradient_buffer  # noqa: F401  (B200 extension: caller-owned gradient storage)
 
 
 def cpu_deep_copy_tuple(input_tuple):

@@ -70,7 +70,17 @@ RASTER_SYMBOLS = (
     "gvd_raster_abi_version", "gvd_last_error", "gvd_raster_geom_bytes", "gvd_raster_binning_bytes",
     "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes", "gvd_raster_layout",
     "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible",
+    "gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum",
 )
+
+EXCHANGE_MAX_RANKS = 8
+EXCHANGE_HANDLE_BYTES = 64
+
+
+class ExchangeArgs(C.Structure):
+    """include/gvd_exchange.h::GvdExchangeArgs"""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("bufs", C.c_void_p * EXCHANGE_MAX_RANKS),
+                ("payload_bytes", C.c_size_t), ("n_floats", C.c_size_t), ("epoch", C.c_uint32)]
 
 _raster = None
 ABI_VERSION = 6
@@ -106,6 +116,13 @@ def raster():
     lib.gvd_raster_backward.argtypes = [C.POINTER(RasterBackwardArgs), C.c_void_p]
     lib.gvd_raster_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for n in ("gvd_raster_layout", "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible"):
+        getattr(lib, n).restype = C.c_int
+    lib.gvd_exchange_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.gvd_exchange_free.argtypes = [C.c_void_p]
+    lib.gvd_exchange_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.gvd_exchange_close.argtypes = [C.c_void_p]
+    lib.gvd_exchange_allreduce_sum.argtypes = [C.POINTER(ExchangeArgs), C.c_void_p]
+    for n in ("gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum"):
         getattr(lib, n).restype = C.c_int
     lib.gvd_raster_profile_enable.argtypes = [C.c_int]
     lib.gvd_raster_profile_read.argtypes = [C.POINTER(RasterStageTimes)]

@@ -6,6 +6,7 @@ step with a single all-reduce over one flat buffer (62 floats per Gaussian: mean
 scale 3, rotation 4, plus means2D 3).  One process per GPU, `torch.distributed` (NCCL over NVLink on the
 GPU box; gloo in the CPU tests).
 """
+import ctypes as C
 from typing import Iterable, List, Sequence
 
 import torch
@@ -21,10 +22,95 @@ def shard_views(num_views: int, world_size: int, rank: int) -> List[int]:
     return list(range(start, start + base + (1 if rank < extra else 0)))
 
 
-def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool = False) -> None:
-    """In-place sum (or mean) of a list of gradient tensors over the ranks, as ONE collective."""
+class _RawCuda:
+    """Exposes a raw device allocation to torch (zero-copy) through the CUDA array interface."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class GradientExchange:
+    """The gradient sum of the view-parallel step as ONE hand-written kernel over NVLink peer memory
+    (include/gvd_exchange.h): each rank owns an exchange buffer the rasterizer backward writes its gradients into
+    (diff_gaussian_rasterization.set_gradient_buffer); `allreduce()` sums it in place across the ranks of the world.
+    torch.distributed only carries the 64-byte IPC handles at set-up.  CUDA only (there is no CPU path)."""
+
+    def __init__(self, n_floats: int, device):
+        import gvd_native as _n
+
+        self.lib = _n.raster()
+        self._n = _n
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if not (2 <= self.world <= _n.EXCHANGE_MAX_RANKS):
+            raise ValueError("GradientExchange needs 2..8 ranks")
+        self.device = torch.device(device)
+        self.n_floats = (int(n_floats) + 3) // 4 * 4
+        self.payload = self.n_floats * 4
+        ptr, handle = C.c_void_p(), C.create_string_buffer(_n.EXCHANGE_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gvd_exchange_alloc(self.payload, C.byref(ptr), handle), "gvd_exchange_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw)
+            self.ptrs = []
+            for q, h in enumerate(handles):
+                if q == self.rank:
+                    self.ptrs.append(ptr.value)
+                else:
+                    pp = C.c_void_p()
+                    self._check(self.lib.gvd_exchange_open(h, C.byref(pp)), "gvd_exchange_open")
+                    self.ptrs.append(pp.value)
+        self.buffer = torch.as_tensor(_RawCuda(ptr.value, self.n_floats), device=self.device)
+        self.epoch = 0
+        dist.barrier()  # every mapping exists before anybody launches
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: " + self._n.last_error(self.lib))
+
+    def owns(self, t: torch.Tensor) -> bool:
+        lo = self.buffer.data_ptr()
+        return t.is_cuda and lo <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= lo + self.payload
+
+    def allreduce(self, n_floats: int = None) -> torch.Tensor:
+        """Sums the first n_floats (default: all) of every rank's buffer in place; stream-ordered on the current stream."""
+        a = self._n.ExchangeArgs()
+        a.world, a.rank = self.world, self.rank
+        for q, pq in enumerate(self.ptrs):
+            a.bufs[q] = pq
+        a.payload_bytes = self.payload
+        a.n_floats = self.n_floats if n_floats is None else (int(n_floats) + 3) // 4 * 4
+        self.epoch += 1
+        a.epoch = self.epoch
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gvd_exchange_allreduce_sum(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                        "gvd_exchange_allreduce_sum")
+        return self.buffer
+
+    def close(self):
+        if getattr(self, "ptrs", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        for q, pq in enumerate(self.ptrs):
+            if q != self.rank:
+                self.lib.gvd_exchange_close(pq)
+        dist.barrier()
+        self.buffer = None
+        self.lib.gvd_exchange_free(self.ptrs[self.rank])
+        self.ptrs = None
+
+
+def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool = False, exchange: GradientExchange = None) -> None:
+    """In-place sum (or mean) of a list of gradient tensors over the ranks, as ONE collective.  With `exchange`, and the
+    gradients living in its buffer (set_gradient_buffer), the collective is the peer-memory kernel; otherwise NCCL/gloo."""
     grads = [g for g in grads if g is not None]
     if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    if exchange is not None and all(exchange.owns(g) for g in grads):
+        hi = max(g.data_ptr() + g.numel() * 4 for g in grads) - exchange.buffer.data_ptr()
+        exchange.allreduce(hi // 4)
+        if average:
+            exchange.buffer[:hi // 4] /= exchange.world
         return
     # Fast path: the rasterizer hands out all its gradients as views of one flat buffer -> reduce it in place.
     base = grads[0]._base

@@ -17,8 +17,8 @@ def test_header_symbols_exported():
     import gvd_native
 
     lib = gvd_native.raster()
-    declared = _declared_symbols("gvd_raster.h")
-    assert len(declared) >= 12
+    declared = _declared_symbols("gvd_raster.h") + _declared_symbols("gvd_exchange.h")
+    assert len(declared) >= 17
     for s in declared:
         assert hasattr(lib, s), f"libgvd_raster.so does not export {s}"
     assert set(declared) == set(gvd_native.RASTER_SYMBOLS)
@@ -49,8 +49,9 @@ def test_struct_sizes_match_header():
 
     import gvd_native
 
-    src = '#include "gvd_raster.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(GvdRasterForwardArgs),' \
-          ' sizeof(GvdRasterBackwardArgs), sizeof(GvdRasterLayout), sizeof(GvdRasterStageTimes));return 0;}\n'
+    src = '#include "gvd_raster.h"\n#include "gvd_exchange.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n", ' \
+          'sizeof(GvdRasterForwardArgs), sizeof(GvdRasterBackwardArgs), sizeof(GvdRasterLayout), sizeof(GvdRasterStageTimes), ' \
+          'sizeof(GvdExchangeArgs));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
@@ -58,7 +59,22 @@ def test_struct_sizes_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(gvd_native.RasterForwardArgs), C.sizeof(gvd_native.RasterBackwardArgs),
-                     C.sizeof(gvd_native.RasterLayout), C.sizeof(gvd_native.RasterStageTimes)]
+                     C.sizeof(gvd_native.RasterLayout), C.sizeof(gvd_native.RasterStageTimes), C.sizeof(gvd_native.ExchangeArgs)]
+
+
+def test_exchange_rejects_bad_arguments():
+    """No GPU needed: argument validation of the peer-memory gradient sum happens before any CUDA call."""
+    import gvd_native
+
+    lib = gvd_native.raster()
+    assert lib.gvd_exchange_allreduce_sum(None, None) != 0
+    a = gvd_native.ExchangeArgs()
+    a.world, a.rank = 1, 0
+    assert lib.gvd_exchange_allreduce_sum(C.byref(a), None) != 0 and b"world" in lib.gvd_last_error()
+    a.world, a.rank, a.payload_bytes, a.n_floats = 2, 0, 64, 6
+    assert lib.gvd_exchange_allreduce_sum(C.byref(a), None) != 0 and b"multiple of 4" in lib.gvd_last_error()
+    a.n_floats = 16
+    assert lib.gvd_exchange_allreduce_sum(C.byref(a), None) != 0 and b"null buffer" in lib.gvd_last_error()
 
 
 def test_null_args_fail_cleanly():
