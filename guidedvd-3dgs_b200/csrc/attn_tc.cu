@@ -6,15 +6,22 @@
 //   warp 0    : TMA producer  (Q once, then K_j / V_j tiles, 128-byte swizzle)
 //   warp 1    : MMA issuer    S = Q K_j^T        (SS: both operands in smem, accumulator S in TMEM, 128 fp32 columns)
 //                             O_j = P_j V_j      (TS: A = P_j read from TMEM as packed bf16, B = V_j smem tile, MN-major)
-//   warps 2-5 : softmax       thread = query row. Two passes over its S row in TMEM (row max, then exp -> bf16 P written
-//                             back to TMEM with tcgen05.st), running max / sum / output row (64 fp32) in registers;
-//                             O_j is read from TMEM and folded in with the usual exp(m_old - m_new) correction.
-// TMEM: S [0,128) | P [128,192) | O_j [192,256)  -> 256 columns, two CTAs per SM.
+//   warps 2-5 : softmax       thread = query row. The whole S row (128 fp32) is pulled into registers with four
+//                             back-to-back tcgen05.ld and ONE wait; row max, exp -> bf16 P written back to TMEM with
+//                             tcgen05.st. O accumulates IN TMEM across key blocks (the PV MMA runs with accumulate on);
+//                             the softmax thread rescales its O row in place only when its running max has grown by
+//                             more than 2^8 (lazy rescale: P stays <= 256, far inside bf16/fp32 range, and the final
+//                             1/l normalisation uses the same stale max, so the result is unchanged).  Optionally one
+//                             exponential in four is evaluated on the FMA pipe (Cody-Waite split + cubic).
+// TMEM: S [0,128) | P [128,192) | O [192,256)  -> 256 columns, two CTAs per SM.
+// (flash_attn_v1_kernel below is the first version -- two passes over S, O folded in registers every block -- kept
+// selectable with GVD_FLASH_V1=1 for A/B timing.)
 // Logits stay in fp32 (acc * scale); the reference rounds them to bf16 twice before its fp32 softmax (attention.py:103),
 // which this kernel deliberately does not emulate: the emulation costs three ALU ops per score in a loop that is
 // MUFU/ALU-bound, and the difference is below the bf16 noise of the PV product (tests bound the error).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/gvd_nn.h"
@@ -72,7 +79,7 @@ struct FaParams {
 };
 
 __global__ void __launch_bounds__(FA_THREADS, 2)
-flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+flash_attn_v1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                   const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -243,6 +250,207 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
 }
 
+
+// 2^x for x <= ~8 on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a cubic (max rel. error 1.1e-4,
+// below the 2^-9 rounding of the bf16 P it feeds); 2^n by adding n to the exponent field.
+__device__ __forceinline__ float ex2_fma(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits of t now hold n
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.05550410866f, 0.24022650696f);
+    p = fmaf(p, f, 0.69314718056f);
+    p = fmaf(p, f, 1.0f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
+template <bool POLY>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                  const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sq = smem;
+    uint8_t* sk = smem + FA_TILE_BYTES;
+    uint8_t* sv = smem + FA_TILE_BYTES * (1 + FA_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;              // [2]
+    uint64_t* kv_empty = bars + 3;             // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.Nk + FA_BN - 1) / FA_BN;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_q);
+        tc::prefetch_tmap(&tmap_k);
+        tc::prefetch_tmap(&tmap_v);
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < FA_STAGES; ++s) {
+            tc::mbar_init(&kv_full[s], 1);
+            tc::mbar_init(&kv_empty[s], 1);
+        }
+        tc::mbar_init(s_full, 1);
+        tc::mbar_init(p_full, 4);  // one arrival per softmax warp
+        tc::mbar_init(o_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(q_full, FA_TILE_BYTES);
+            tc::tma_load_4d(sq, &tmap_q, q_full, 0, m0, h, b);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA_STAGES) & 1) ^ 1));
+                tc::mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+                tc::tma_load_4d(sk + s * FA_TILE_BYTES, &tmap_k, &kv_full[s], 0, j * FA_BN, h, b);
+                tc::tma_load_4d(sv + s * FA_TILE_BYTES, &tmap_v, &kv_full[s], 0, j * FA_BN, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = tc::make_idesc_bf16(FA_BM, FA_BN);
+            const uint32_t idesc_pv = make_idesc_pv();
+            const uint32_t q_addr = tc::smem_u32(sq);
+            tc::mbar_wait(q_full, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_full[s], (uint32_t)((j / FA_STAGES) & 1));
+                // S_j may overwrite S_{j-1}: the softmax warps read it before they arrived on p_full(j-1), waited below
+                tc::fence_after_sync();
+                const uint32_t k_addr = tc::smem_u32(sk + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k)
+                    tc::umma_bf16(tmem_base + FA_S_COL, tc::make_desc_kmajor_sw128(q_addr + k * 32),
+                                  tc::make_desc_kmajor_sw128(k_addr + k * 32), idesc_qk, k != 0);
+                // s_full(j) also certifies that PV_{j-1} (issued earlier by this thread) is complete: O is quiescent
+                // while the softmax warps rescale it
+                tc::umma_commit(s_full);
+                tc::mbar_wait(p_full, (uint32_t)(j & 1));
+                tc::fence_after_sync();
+                const uint32_t v_addr = tc::smem_u32(sv + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < FA_BN / 16; ++k)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 smem rows of V
+                    umma_bf16_ts(tmem_base + FA_O_COL, tmem_base + FA_P_COL + k * 8,
+                                 tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (j | k) != 0);
+                tc::umma_commit(&kv_empty[s]);
+            }
+            tc::umma_commit(o_full);
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quadrant of this warp
+        const int row = m0 + q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sl2 = p.scale * 1.4426950408889634f;  // exp(x*scale - m) = exp2(x*sl2 - m2), m2 in log2 units
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            tc::mbar_wait(s_full, (uint32_t)(j & 1));
+            tc::fence_after_sync();
+            const int key0 = j * FA_BN;
+            uint32_t v[FA_BN];
+#pragma unroll
+            for (int c = 0; c < FA_BN; c += 32)
+                tc::tmem_ld32(tmem_base + lane_off + FA_S_COL + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+            tc::tmem_ld_wait();
+            if (key0 + FA_BN > p.Nk) {  // only the last key block can hold out-of-range keys
+#pragma unroll
+                for (int e = 0; e < FA_BN; ++e)
+                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < FA_BN; e += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+            }
+            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;  // scale > 0: max commutes with it
+            float m_new = m_run;
+            if (j == 0) {
+                m_new = m_blk;
+            } else {
+                const bool grow = m_blk > m_run + 8.0f;
+                if (__any_sync(0xffffffffu, grow)) {  // warp-uniform: tcgen05.ld/st are warp-collective
+                    float alpha = 1.0f;
+                    if (grow) {
+                        m_new = m_blk;
+                        alpha = ex2(m_run - m_new);
+                        l_run *= alpha;
+                    }
+#pragma unroll
+                    for (int c = 0; c < FA_D; c += 16) {
+                        uint32_t o[16];
+                        tc::tmem_ld16(tmem_base + lane_off + FA_O_COL + c, o);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st16(tmem_base + lane_off + FA_O_COL + c, o);
+                    }
+                }
+            }
+            const float mneg = -m_new;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < FA_BN; c += 32) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const float x0 = fmaf(__uint_as_float(v[c + e]), sl2, mneg);
+                    const float x1 = fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg);
+                    const float p0 = ex2(x0);
+                    const float p1 = (POLY && (e & 2)) ? ex2_fma(x1) : ex2(x1);
+                    l0 += p0;
+                    l1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st16(tmem_base + lane_off + FA_P_COL + c / 2, pk);
+            }
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(p_full);
+            l_run += l0 + l1;
+            m_run = m_new;
+        }
+        tc::mbar_wait(o_full, 0);
+        tc::fence_after_sync();
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
+#pragma unroll
+        for (int c = 0; c < FA_D; c += 32) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem_base + lane_off + FA_O_COL + c, o);
+            tc::tmem_ld_wait();
+            if (row < p.Nq) {
+#pragma unroll
+                for (int e8 = 0; e8 < 32; e8 += 8) {
+                    uint4 u;
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c + e8) = u;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -285,15 +493,25 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    // A/B timing knobs. GVD_FLASH_V1=1: first-generation kernel. GVD_FLASH_POLY=1: one exponential in four on the FMA
+    // pipe; off by default -- measured on B200 at N=9216: 4.13 ms without, 4.46 ms with (v1: 5.03 ms); the kernel is
+    // bound by the softmax warps' issue slots and synchronisation, not by MUFU throughput alone.
+    static int variant = -1;
+    if (variant < 0) {
+        const char* v1 = getenv("GVD_FLASH_V1");
+        const char* poly = getenv("GVD_FLASH_POLY");
+        const int want = (v1 && v1[0] == '1') ? 0 : ((poly && poly[0] == '1') ? 2 : 1);
+        const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
+                                   : (want == 1 ? (const void*)flash_attn_kernel<false> : (const void*)flash_attn_kernel<true>);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
-        attr_set = true;
+        variant = want;
     }
     FaParams p{reinterpret_cast<__nv_bfloat16*>(out), ld, 64, q_batch_stride, Nq, Nk, H, scale};
     dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
-    flash_attn_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    if (variant == 0) flash_attn_v1_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 1) flash_attn_kernel<false><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else flash_attn_kernel<true><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }
     return 0;

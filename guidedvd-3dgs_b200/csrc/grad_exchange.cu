@@ -12,7 +12,11 @@ extern thread_local std::string g_raster_err;  // raster_api.cu: text behind gvd
 namespace {
 
 // Signal words of one rank (uint32 each): [0, 8) ready[q], [8, 16) done[q], [16] CTA ticket.
-constexpr int kReady = 0, kDone = 8, kTicket = 16;
+constexpr int kReady = 0, kDone = 8, kTicket = 16, kTimedOut = 17;
+// A peer that never launches (crashed rank, mismatched call sequence) must not wedge this GPU: every flag wait gives
+// up after this many nanoseconds of %globaltimer, records the epoch in kTimedOut (gvd_exchange_status reads it) and
+// lets the kernel finish with an unspecified payload.
+constexpr unsigned long long kWaitLimitNs = 20ull * 1000 * 1000 * 1000;
 
 struct Params {
     float4* buf[GVD_EXCHANGE_MAX_RANKS];
@@ -38,6 +42,25 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 }
 __device__ __forceinline__ void st_peer(float4* p, float4 v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spins until *p has reached `epoch` (wrap-safe); false = gave up.
+__device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch, uint32_t* timed_out_word) {
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > kWaitLimitNs) {
+            *timed_out_word = epoch;
+            return false;
+        }
+    }
+    return true;
 }
 
 template <int WORLD>
@@ -79,9 +102,7 @@ __global__ void __launch_bounds__(512) grad_allreduce_kernel(const Params p) {
     uint32_t* mine = p.flag[p.rank];
     // ---- entry: every peer has finished producing its gradients (its kernel is stream-ordered behind them) ----
     if (blockIdx.x == 0 && threadIdx.x < WORLD) st_release_sys(p.flag[threadIdx.x] + kReady + p.rank, p.epoch);
-    if (threadIdx.x < WORLD) {
-        while ((int32_t)(ld_acquire_sys(mine + kReady + threadIdx.x) - p.epoch) < 0) __nanosleep(64);
-    }
+    if (threadIdx.x < WORLD) wait_flag(mine + kReady + threadIdx.x, p.epoch, mine + kTimedOut);
     __syncthreads();
     // ---- rank r sums slice r of every buffer and stores the sum into every buffer ----
     const unsigned long long per = (p.n_vec + WORLD - 1) / WORLD;
@@ -100,7 +121,7 @@ __global__ void __launch_bounds__(512) grad_allreduce_kernel(const Params p) {
     if (threadIdx.x == 0) mine[kTicket] = 0u;
     if (threadIdx.x < WORLD) {
         st_release_sys(p.flag[threadIdx.x] + kDone + p.rank, p.epoch);
-        while ((int32_t)(ld_acquire_sys(mine + kDone + threadIdx.x) - p.epoch) < 0) __nanosleep(64);
+        wait_flag(mine + kDone + threadIdx.x, p.epoch, mine + kTimedOut);
     }
 }
 
@@ -152,6 +173,13 @@ int gvd_exchange_close(void* peer_ptr) {
     if (!peer_ptr) return 0;
     cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
     return e == cudaSuccess ? 0 : fail("gvd_exchange_close", e);
+}
+
+int gvd_exchange_status(const void* own_ptr, size_t payload_bytes, uint32_t* timed_out_epoch) {
+    if (!own_ptr || !timed_out_epoch) { g_raster_err = "gvd_exchange_status: null argument"; return 2; }
+    const char* word = reinterpret_cast<const char*>(own_ptr) + padded(payload_bytes) + kTimedOut * sizeof(uint32_t);
+    cudaError_t e = cudaMemcpy(timed_out_epoch, word, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? 0 : fail("gvd_exchange_status", e);
 }
 
 int gvd_exchange_allreduce_sum(const GvdExchangeArgs* a, void* stream_) {

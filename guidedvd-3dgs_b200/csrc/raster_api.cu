@@ -219,7 +219,8 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
         ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
         return fail_msg("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
-    if (!a->geom_alloc || !a->binning_alloc || !a->img_alloc) return fail_msg("gvd_raster_forward: null allocator");
+    if ((!a->geom_alloc && !a->geom_buffer) || (!a->binning_alloc && !a->spec_binning_buffer) || (!a->img_alloc && !a->img_buffer))
+        return fail_msg("gvd_raster_forward: null allocator");
     if (a->shs && (a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
         return fail_msg("gvd_raster_forward: SH degree / coefficient count mismatch");
 
@@ -231,10 +232,14 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     if (grid.x > 0xffff || grid.y > 0xffff || tiles > GVD_MAX_TILES)
         return fail_msg("gvd_raster_forward: image too large (more than 49152 tiles of 16x16)");
 
-    char* gp = (char*)a->geom_alloc(a->alloc_user, gvd_raster_geom_bytes(P, a->width, a->height));
+    const size_t geom_need = gvd_raster_geom_bytes(P, a->width, a->height);
+    if (a->geom_buffer && a->geom_bytes < geom_need) return fail_msg("gvd_raster_forward: geom_buffer too small");
+    char* gp = a->geom_buffer ? (char*)a->geom_buffer : (char*)a->geom_alloc(a->alloc_user, geom_need);
     if (!gp) return fail_msg("gvd_raster_forward: geometry allocator returned null");
     RasterGeomPtrs g = carve_geom(gp, (size_t)P, tiles);
-    char* ip = (char*)a->img_alloc(a->alloc_user, gvd_raster_img_bytes(a->width, a->height));
+    const size_t img_need = gvd_raster_img_bytes(a->width, a->height);
+    if (a->img_buffer && a->img_bytes < img_need) return fail_msg("gvd_raster_forward: img_buffer too small");
+    char* ip = a->img_buffer ? (char*)a->img_buffer : (char*)a->img_alloc(a->alloc_user, img_need);
     if (!ip) return fail_msg("gvd_raster_forward: image allocator returned null");
     RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
 
@@ -283,6 +288,7 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
                   "copy num_rendered");
         GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
         a->num_rendered = num_rendered;
+        if (!a->binning_alloc) return fail_msg("gvd_raster_forward: null binning allocator");
         char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered, a->export_keys));
         if (!bp) return fail_msg("gvd_raster_forward: binning allocator returned null");
         b = carve_binning(bp, (size_t)num_rendered, a->export_keys != 0);

@@ -295,6 +295,7 @@ __device__ __forceinline__ void store_p3_coalesced(float* __restrict__ dst, floa
     __syncthreads();
 }
 
+#define GVD_SH_STAGE_STRIDE 52
 #define SH(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
 #define OUT(k, val)                                 \
     {                                               \
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(256, 2) gaussian_backward_kernel(
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dcov3D,
     float* __restrict__ dL_dsh, float* __restrict__ dL_dscales, float* __restrict__ dL_drots) {
     __shared__ float stage[3 * 256];
+    extern __shared__ __align__(16) float sh_stage[];  // [8 warps][32 rows][GVD_SH_STAGE_STRIDE] (only when dL_dsh, M == 16)
     const int block_first = blockIdx.x * blockDim.x;
     const int idx = block_first + threadIdx.x;
     const bool valid = idx < P;
@@ -592,20 +594,38 @@ __global__ void __launch_bounds__(256, 2) gaussian_backward_kernel(
     store_p3_coalesced(dL_dmeans3D, stage, block_first, P, o_m3.x, o_m3.y, o_m3.z);
     if (dL_dscales) store_p3_coalesced(dL_dscales, stage, block_first, P, o_sc.x, o_sc.y, o_sc.z);
     if (dL_dcolors) store_p3_coalesced(dL_dcolors, stage, block_first, P, o_col.x, o_col.y, o_col.z);
-    if (!valid) return;
-    dL_dopacity[idx] = o_op;
-    if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
-    if (dL_dcov3D) {
+    if (valid) {
+        dL_dopacity[idx] = o_op;
+        if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
+        if (dL_dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = o_cov[k];
+            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = o_cov[k];
+        }
     }
+    if (block_first + (int)(threadIdx.x & ~31u) >= P) return;  // whole warp past the end
     if (dL_dsh) {
-        float* row = dL_dsh + (size_t)idx * 3 * M;
-        if (M == 16 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
-            float4* r4 = reinterpret_cast<float4*>(row);
+        float* row = dL_dsh + (size_t)(valid ? idx : 0) * 3 * M;
+        if (M == 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0)) {
+            // The 32 rows of a warp are one contiguous 6 KB span of dL_dsh. Written row-per-thread, every store
+            // instruction would touch 32 half-filled sectors; instead the rows are transposed through shared
+            // memory (row stride 52 floats: conflict-free 16-byte accesses) and the span leaves the SM as twelve
+            // unit-stride 512-byte stores.  Streaming stores: 96 MB per step that nothing in this step re-reads.
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            float* wstage = sh_stage + warp * (32 * GVD_SH_STAGE_STRIDE);
+            float4* mine = reinterpret_cast<float4*>(wstage + lane * GVD_SH_STAGE_STRIDE);
 #pragma unroll
-            for (int k = 0; k < 12; ++k) r4[k] = make_float4(o_sh[4 * k], o_sh[4 * k + 1], o_sh[4 * k + 2], o_sh[4 * k + 3]);
-        } else {
+            for (int k = 0; k < 12; ++k) mine[k] = make_float4(o_sh[4 * k], o_sh[4 * k + 1], o_sh[4 * k + 2], o_sh[4 * k + 3]);
+            __syncwarp();
+            const int warp_first = block_first + warp * 32;
+            const int nrows = min(32, P - warp_first);
+            float4* dst = reinterpret_cast<float4*>(dL_dsh + (size_t)warp_first * 48);
+#pragma unroll
+            for (int it = 0; it < 12; ++it) {
+                const int f = it * 32 + lane;  // float4 index inside the span
+                const int r = f / 12, c4 = f - r * 12;
+                if (r < nrows) __stcs(dst + f, *reinterpret_cast<const float4*>(wstage + r * GVD_SH_STAGE_STRIDE + 4 * c4));
+            }
+        } else if (valid) {
 #pragma unroll
             for (int k = 0; k < 48; ++k)
                 if (k < 3 * M) row[k] = o_sh[k];
@@ -631,7 +651,14 @@ void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeom
 
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
                                   float focal_x, float focal_y, cudaStream_t s) {
-    gaussian_backward_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
+    const size_t sh_smem = (a.dL_dsh && a.M == 16) ? (size_t)8 * 32 * GVD_SH_STAGE_STRIDE * sizeof(float) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute((const void*)gaussian_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             8 * 32 * GVD_SH_STAGE_STRIDE * (int)sizeof(float));
+        attr_set = true;
+    }
+    gaussian_backward_kernel<<<(a.P + 255) / 256, 256, sh_smem, s>>>(
         a.P, a.D, a.M, (const float3*)a.means3D, a.radii, a.shs, g.clamped, (const float3*)a.scales,
         (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
         a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,

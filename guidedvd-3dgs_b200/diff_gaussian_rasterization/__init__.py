@@ -41,6 +41,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
                 rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        # With a backward to come, validation of the speculative instance buffer is deferred to it (see _C.DEFER):
+        # num_rendered is then a _C.PendingR until the backward (or int()) resolves it.
+        defer = any(ctx.needs_input_grad)
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy before they can be corrupted
             try:
@@ -50,7 +53,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            out = _C.rasterize_gaussians(*args)
+            out = _C.rasterize_gaussians(*args, defer=defer)
         num_rendered, color, depth, alpha, radii, geomBuffer, binningBuffer, imgBuffer = out
 
         ctx.raster_settings = rs
@@ -66,6 +69,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
          imgBuffer, alpha) = ctx.saved_tensors
         conf = rs.confidence
+        ctx.num_rendered = int(ctx.num_rendered)  # resolves a deferred R; raises if that frame outgrew its buffer
         if conf is not None and conf.numel() != means3D.size(0):
             raise RuntimeError("confidence must hold one value per Gaussian")
         args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,

@@ -25,6 +25,7 @@ class RasterForwardArgs(C.Structure):
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
         ("geom_alloc", ALLOC_FN), ("binning_alloc", ALLOC_FN), ("img_alloc", ALLOC_FN),
         ("alloc_user", C.c_void_p),
+        ("geom_buffer", C.c_void_p), ("geom_bytes", C.c_size_t), ("img_buffer", C.c_void_p), ("img_bytes", C.c_size_t),
         ("spec_binning_buffer", C.c_void_p), ("spec_binning_bytes", C.c_size_t),
         ("num_rendered_pinned", C.c_void_p), ("r_ready_event", C.c_void_p),
         ("num_rendered", C.c_int),
@@ -70,7 +71,7 @@ RASTER_SYMBOLS = (
     "gvd_raster_abi_version", "gvd_last_error", "gvd_raster_geom_bytes", "gvd_raster_binning_bytes",
     "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes", "gvd_raster_layout",
     "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible",
-    "gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum",
+    "gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum", "gvd_exchange_status",
 )
 
 EXCHANGE_MAX_RANKS = 8
@@ -83,7 +84,7 @@ class ExchangeArgs(C.Structure):
                 ("payload_bytes", C.c_size_t), ("n_floats", C.c_size_t), ("epoch", C.c_uint32)]
 
 _raster = None
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 def lib_path(name="libgvd_raster.so"):
@@ -122,7 +123,8 @@ def raster():
     lib.gvd_exchange_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     lib.gvd_exchange_close.argtypes = [C.c_void_p]
     lib.gvd_exchange_allreduce_sum.argtypes = [C.POINTER(ExchangeArgs), C.c_void_p]
-    for n in ("gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum"):
+    lib.gvd_exchange_status.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+    for n in ("gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum", "gvd_exchange_status"):
         getattr(lib, n).restype = C.c_int
     lib.gvd_raster_profile_enable.argtypes = [C.c_int]
     lib.gvd_raster_profile_read.argtypes = [C.POINTER(RasterStageTimes)]

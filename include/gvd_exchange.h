@@ -52,6 +52,11 @@ typedef struct {
  * must make the call (like any collective). */
 GVD_API int gvd_exchange_allreduce_sum(const GvdExchangeArgs* args, void* stream);
 
+/* The kernel's cross-GPU flag waits are bounded (20 s): a peer that never makes the call cannot wedge this GPU.  A wait
+ * that gave up leaves the payload unspecified and records its epoch; this reads it back (synchronising copy).
+ * *timed_out_epoch == 0 = every call so far completed its barriers. */
+GVD_API int gvd_exchange_status(const void* own_ptr, size_t payload_bytes, uint32_t* timed_out_epoch);
+
 #ifdef __cplusplus
 }
 #endif

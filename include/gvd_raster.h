@@ -40,7 +40,7 @@ typedef struct CUstream_st* gvd_stream_t; /* == cudaStream_t */
 typedef void* (*gvd_alloc_fn)(void* user, size_t bytes);
 
 /* Layout/version of the scratch buffers (bumped when the packed layouts change). */
-#define GVD_RASTER_ABI_VERSION 6
+#define GVD_RASTER_ABI_VERSION 7
 
 typedef struct GvdRasterForwardArgs {
     /* sizes -- DGR/cuda_rasterizer/rasterizer_impl.cu:197-224 */
@@ -75,6 +75,13 @@ typedef struct GvdRasterForwardArgs {
     gvd_alloc_fn binning_alloc;  /* called once with gvd_raster_binning_bytes(R,export_keys) */
     gvd_alloc_fn img_alloc;      /* called once with gvd_raster_img_bytes(W,H)       */
     void* alloc_user;
+    /* Optional pre-sized scratch: both sizes are pure functions of (P, W, H), so a caller that knows them can hand the
+     * buffers over directly and save the two callbacks.  Used when non-NULL (must hold gvd_raster_geom_bytes(P,W,H) /
+     * gvd_raster_img_bytes(W,H) bytes, 128-byte aligned); geom_alloc / img_alloc may then be NULL. */
+    void* geom_buffer;
+    size_t geom_bytes;
+    void* img_buffer;
+    size_t img_bytes;
     /* Optional speculative instance buffer (no host round trip).  When spec_binning_buffer != NULL the library does NOT
      * synchronise to learn R: it copies R asynchronously to *num_rendered_pinned (pinned host memory), records
      * r_ready_event (a cudaEvent_t) right after that copy, and queues the remaining stages against the caller's buffer

@@ -25,10 +25,12 @@ def make_inputs(P, W, H, seed, sh_degree=3, device="cuda", fovx_deg=90.0):
     return sc, cam, cot, bg, sh_degree
 
 
-def run(pkg, sc, cam, cot, bg, sh_degree, use_conf=True, precomp=False, debug=False, backward=True):
+def run(pkg, sc, cam, cot, bg, sh_degree, use_conf=True, precomp=False, debug=False, backward=True, export_keys=True):
     """One forward(+backward) through the package's public API. Returns dict of outputs/grads/buffers."""
     if hasattr(pkg, "_C") and hasattr(pkg._C, "EXPORT_KEYS"):
-        pkg._C.EXPORT_KEYS = True  # ours: also materialise the sorted 64-bit keys for comparison
+        # ours: also materialise the sorted 64-bit keys for comparison (this selects the exact, synchronous path;
+        # export_keys=False exercises the speculative instance buffer the way a training loop does)
+        pkg._C.EXPORT_KEYS = bool(export_keys)
     dev = sc["means3D"].device
     conf = sc["confidence"] if use_conf else torch.ones_like(sc["confidence"])
     settings = pkg.GaussianRasterizationSettings(
@@ -56,7 +58,8 @@ def run(pkg, sc, cam, cot, bg, sh_degree, use_conf=True, precomp=False, debug=Fa
     saved = getattr(fn, "saved_tensors", None)
     if saved is not None:
         out["geom"], out["binning"], out["img"] = saved[7], saved[8], saved[9]
-    out["num_rendered"] = getattr(fn, "num_rendered", None)
+    nr = getattr(fn, "num_rendered", None)
+    out["num_rendered"] = None if nr is None else int(nr)  # ours: may be a deferred R (validated on conversion)
     if backward:
         loss = (color * cot["color"]).sum() + (depth * cot["depth"]).sum() + (alpha * cot["alpha"]).sum()
         loss.backward()

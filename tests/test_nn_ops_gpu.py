@@ -150,3 +150,17 @@ def test_attention_paths(fn):
     q2 = torch.randn(2, 700, H * 64, device="cuda", generator=g).to(BF)
     k2, v2 = (torch.randn(2, 700, H * 64, device="cuda", generator=g).to(BF) for _ in range(2))
     _close(attn(q2, k2, v2, 2, 700, 700, H, 0.125), ref(q2, k2, v2), tol=1.0 / 64)
+    if fn != "flash_attention":
+        return
+    # Fused kernel only (it keeps fp32 logits; the bf16-rounded logits of the materialised path are too coarse at this
+    # magnitude): logits that climb by ~0.05 per key (35 over the row) -- the running max overtakes the lazy-rescale
+    # threshold several times, so the in-TMEM rescale of O is exercised -- and logits that fall (it never rescales).
+    def ref32(q, k, v):
+        qh, kh, vh = (t.float().view(t.shape[0], -1, H, 64).transpose(1, 2) for t in (q, k, v))
+        return (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(q.shape[0], -1, H * 64)
+
+    for sign in (1.0, -1.0):
+        q3, k3 = q2.clone(), k2.clone()
+        q3.view(2, 700, H, 64)[..., 0] = 4.0
+        k3.view(2, 700, H, 64)[..., 0] = (sign * 0.1 * torch.arange(700, device="cuda"))[None, :, None].to(BF)
+        _close(attn(q3, k3, v2, 2, 700, 700, H, 0.125), ref32(q3, k3, v2), tol=1.0 / 64)

@@ -197,3 +197,52 @@ def test_properties_at_full_size(cfg):
     c = pr.run(ours, sc, cam, cot2, bg, D)
     for k in a["grads"]:
         assert _grad_err(c["grads"][k], 2 * a["grads"][k])[1] < 1e-5, k
+
+
+def test_speculative_instance_buffer_matches_exact_path():
+    """The production path (no key export): from the second frame on the instance buffer is sized from history, the
+    forward makes no host round trip and R is validated in the backward.  Results must equal the exact path's."""
+    import parity_raster as pr
+    import synth
+
+    ours, _ = _pkgs()
+    P, W, H, seed = synth.CONFIGS["small"]
+    sc, cam, cot, bg, D = pr.make_inputs(P, W, H, seed, 3)
+    exact = pr.run(ours, sc, cam, cot, bg, D)
+    ours._C._spec_state.clear()
+    runs = [pr.run(ours, sc, cam, cot, bg, D, export_keys=False) for _ in range(3)]  # 1st: no history -> exact path
+    st = ours._C._spec_state[sc["means3D"].device]
+    assert st["max_R"] == exact["num_rendered"] and len(st["free"]) >= 1
+    for r in runs:
+        assert r["num_rendered"] == exact["num_rendered"]
+        for k in ("color", "depth", "alpha", "radii"):
+            assert torch.equal(r[k], exact[k]), k
+        for k in exact["grads"]:
+            assert _grad_err(r["grads"][k], exact["grads"][k])[1] < 1e-5, k
+    nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
+    assert torch.equal(nograd["color"], exact["color"])
+
+
+def test_speculative_instance_buffer_overflow(monkeypatch):
+    """A frame that outgrows the speculative buffer: without autograd the shim silently redoes it on the exact path;
+    with a deferred validation the backward raises (the image was already consumed) and the history grows."""
+    import parity_raster as pr
+    import synth
+
+    ours, _ = _pkgs()
+    P, W, H, seed = synth.CONFIGS["small"]
+    sc, cam, cot, bg, D = pr.make_inputs(P, W, H, seed, 3)
+    exact = pr.run(ours, sc, cam, cot, bg, D)
+    dev = sc["means3D"].device
+    ours._C._spec_state.clear()
+    pr.run(ours, sc, cam, cot, bg, D, export_keys=False)          # builds the history
+    monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)  # every later guess is far too small
+    nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
+    for k in ("color", "depth", "alpha", "radii"):
+        assert torch.equal(nograd[k], exact[k]), k
+    with pytest.raises(RuntimeError, match="speculative instance buffer"):
+        pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
+    torch.cuda.synchronize()
+    monkeypatch.undo()
+    again = pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
+    assert torch.equal(again["color"], exact["color"]) and ours._C._spec_state[dev]["max_R"] == exact["num_rendered"]
