@@ -194,10 +194,18 @@ def main():
         exchange = view_parallel.GradientExchange(pkg.gradient_buffer_floats(P), dev)
         pkg.set_gradient_buffer(exchange.buffer)
 
+    named = dict(leaves, means2D=means2D)
+
+    def sum_gradients():
+        if exchange is not None:
+            view_parallel.allreduce_gradients(None, exchange=exchange, leaves=named, views=pkg.gradient_views(dev))
+        else:
+            view_parallel.allreduce_gradients(grad_flat(leaves))
+
     def resident_step():
         step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
         if world > 1:
-            view_parallel.allreduce_gradients(grad_flat(leaves), exchange=exchange)
+            sum_gradients()
 
     # End-to-end step: this step's inputs (camera, cotangent images) come from pinned host memory. Like a
     # prefetching data loader, the upload of step k+1 is issued on a copy stream while step k computes.
@@ -226,12 +234,18 @@ def main():
         staged["n"] = k + 2
         color, radii = step(cot, cm[0:16].view(4, 4), cm[16:32].view(4, 4), cm[32:35])
         if world > 1:
-            view_parallel.allreduce_gradients(grad_flat(leaves), exchange=exchange)
-        # The step's result: the scalar a trainer reads back every iteration (train_baseline.py:88). It is copied
-        # to pinned host memory asynchronously and READ one step later (asynchronous loss logging), so the host
-        # never idles the GPU; every step's value is read inside the timed region (the last one by e2e_flush).
-        loss_pinned[k % 2].copy_((color * cot[0:3]).sum(), non_blocking=True)
-        loss_events[k % 2].record()
+            sum_gradients()
+        # The step's result: the scalar a trainer reads back every iteration (train_baseline.py:88), one reduction kernel.
+        # It travels to pinned host memory on a side stream (so the D2H copy never holds up the compute stream) and is
+        # READ one step later (asynchronous loss logging): the host never idles the GPU, and every step's value is
+        # read inside the timed region (the last one by e2e_flush).
+        loss = torch.dot(color.detach().view(-1), cot[0:3].reshape(-1))
+        loss_ready[k % 2].record()
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(loss_ready[k % 2])
+            loss_pinned[k % 2].copy_(loss, non_blocking=True)
+            loss.record_stream(d2h_stream)
+            loss_events[k % 2].record(d2h_stream)
         if k > 0:
             loss_events[(k - 1) % 2].synchronize()
             e2e_state["last"] = float(loss_pinned[(k - 1) % 2])
@@ -247,6 +261,8 @@ def main():
     e2e_state = {"k": 0, "last": None}
     loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_events = [torch.cuda.Event() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    d2h_stream = torch.cuda.Stream(device=dev)
 
     def timed(fn, n, flush=None):
         sync_all()
@@ -322,8 +338,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         ach = alg[top] / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # workload (profiles/r01_ncu_full_d_render.csv); far below the algorithmic bytes because a tile stops after a few
+        # per cent of its list and the per-Gaussian records stay in L2
+        ncu_traffic = {"C2": {"render_bwd": 9.69e6, "render_fwd": 4.11e6}}.get(args.workload, {})
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None,
+                    "frac": round(ach / peak, 4), "traffic": ncu_traffic.get(top),
+                    "traffic_source": "profiles/r01_ncu_full_d_render.csv (ncu --set full, one launch)" if top in ncu_traffic else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes": alg[top],
                     "note": "render kernels are fp32-ALU/SFU/atomic bound, not HBM bound (SURVEY.md 0.5); see DESIGN.md",

@@ -15,7 +15,7 @@
 //                             exponential in four is evaluated on the FMA pipe (Cody-Waite split + cubic).
 // TMEM: S [0,128) | P [128,192) | O [192,256)  -> 256 columns, two CTAs per SM.
 // (flash_attn_v1_kernel below is the first version -- two passes over S, O folded in registers every block -- kept
-// selectable with GVD_FLASH_V1=1 for A/B timing.)
+// selectable with GVD_FLASH=v1 for A/B timing.)
 // Logits stay in fp32 (acc * scale); the reference rounds them to bf16 twice before its fp32 softmax (attention.py:103),
 // which this kernel deliberately does not emulate: the emulation costs three ALU ops per score in a loop that is
 // MUFU/ALU-bound, and the difference is below the bf16 noise of the PV product (tests bound the error).
@@ -263,6 +263,108 @@ __device__ __forceinline__ float ex2_fma(float x) {
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
 
+// Softmax side of one 128-row query tile (4 warps, thread = query row): see the header comment.  s_col / p_col / o_col
+// are the TMEM columns of this tile's S, P and O; `row` is the thread's global query row.
+template <bool POLY>
+__device__ __forceinline__ void softmax_tile(const FaParams& p, uint32_t tmem_base, uint32_t lane_off, uint32_t s_col,
+                                             uint32_t p_col, uint32_t o_col, uint64_t* s_full, uint64_t* p_full,
+                                             uint64_t* o_full, int nblk, int row, int lane, int b, int h) {
+        const float sl2 = p.scale * 1.4426950408889634f;  // exp(x*scale - m) = exp2(x*sl2 - m2), m2 in log2 units
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            tc::mbar_wait(s_full, (uint32_t)(j & 1));
+            tc::fence_after_sync();
+            const int key0 = j * FA_BN;
+            uint32_t v[FA_BN];
+#pragma unroll
+            for (int c = 0; c < FA_BN; c += 32)
+                tc::tmem_ld32(tmem_base + lane_off + s_col + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+            tc::tmem_ld_wait();
+            if (key0 + FA_BN > p.Nk) {  // only the last key block can hold out-of-range keys
+#pragma unroll
+                for (int e = 0; e < FA_BN; ++e)
+                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < FA_BN; e += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+            }
+            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;  // scale > 0: max commutes with it
+            float m_new = m_run;
+            if (j == 0) {
+                m_new = m_blk;
+            } else {
+                const bool grow = m_blk > m_run + 8.0f;
+                if (__any_sync(0xffffffffu, grow)) {  // warp-uniform: tcgen05.ld/st are warp-collective
+                    float alpha = 1.0f;
+                    if (grow) {
+                        m_new = m_blk;
+                        alpha = ex2(m_run - m_new);
+                        l_run *= alpha;
+                    }
+#pragma unroll
+                    for (int c = 0; c < FA_D; c += 16) {
+                        uint32_t o[16];
+                        tc::tmem_ld16(tmem_base + lane_off + o_col + c, o);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st16(tmem_base + lane_off + o_col + c, o);
+                    }
+                }
+            }
+            const float mneg = -m_new;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < FA_BN; c += 32) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const float x0 = fmaf(__uint_as_float(v[c + e]), sl2, mneg);
+                    const float x1 = fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg);
+                    const float p0 = ex2(x0);
+                    const float p1 = (POLY && (e & 2)) ? ex2_fma(x1) : ex2(x1);
+                    l0 += p0;
+                    l1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st16(tmem_base + lane_off + p_col + c / 2, pk);
+            }
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(p_full);
+            l_run += l0 + l1;
+            m_run = m_new;
+        }
+        tc::mbar_wait(o_full, 0);
+        tc::fence_after_sync();
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
+#pragma unroll
+        for (int c = 0; c < FA_D; c += 32) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem_base + lane_off + o_col + c, o);
+            tc::tmem_ld_wait();
+            if (row < p.Nq) {
+#pragma unroll
+                for (int e8 = 0; e8 < 32; e8 += 8) {
+                    uint4 u;
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c + e8) = u;
+                }
+            }
+        }
+    }
+
 template <bool POLY>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -349,102 +451,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     } else {
         const int q = warp & 3;  // TMEM lane quadrant of this warp
-        const int row = m0 + q * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const float sl2 = p.scale * 1.4426950408889634f;  // exp(x*scale - m) = exp2(x*sl2 - m2), m2 in log2 units
-        float m_run = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < nblk; ++j) {
-            tc::mbar_wait(s_full, (uint32_t)(j & 1));
-            tc::fence_after_sync();
-            const int key0 = j * FA_BN;
-            uint32_t v[FA_BN];
-#pragma unroll
-            for (int c = 0; c < FA_BN; c += 32)
-                tc::tmem_ld32(tmem_base + lane_off + FA_S_COL + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
-            tc::tmem_ld_wait();
-            if (key0 + FA_BN > p.Nk) {  // only the last key block can hold out-of-range keys
-#pragma unroll
-                for (int e = 0; e < FA_BN; ++e)
-                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int e = 0; e < FA_BN; e += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
-                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
-                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
-            }
-            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;  // scale > 0: max commutes with it
-            float m_new = m_run;
-            if (j == 0) {
-                m_new = m_blk;
-            } else {
-                const bool grow = m_blk > m_run + 8.0f;
-                if (__any_sync(0xffffffffu, grow)) {  // warp-uniform: tcgen05.ld/st are warp-collective
-                    float alpha = 1.0f;
-                    if (grow) {
-                        m_new = m_blk;
-                        alpha = ex2(m_run - m_new);
-                        l_run *= alpha;
-                    }
-#pragma unroll
-                    for (int c = 0; c < FA_D; c += 16) {
-                        uint32_t o[16];
-                        tc::tmem_ld16(tmem_base + lane_off + FA_O_COL + c, o);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                        tmem_st16(tmem_base + lane_off + FA_O_COL + c, o);
-                    }
-                }
-            }
-            const float mneg = -m_new;
-            float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < FA_BN; c += 32) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const float x0 = fmaf(__uint_as_float(v[c + e]), sl2, mneg);
-                    const float x1 = fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg);
-                    const float p0 = ex2(x0);
-                    const float p1 = (POLY && (e & 2)) ? ex2_fma(x1) : ex2(x1);
-                    l0 += p0;
-                    l1 += p1;
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                tmem_st16(tmem_base + lane_off + FA_P_COL + c / 2, pk);
-            }
-            tmem_st_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(p_full);
-            l_run += l0 + l1;
-            m_run = m_new;
-        }
-        tc::mbar_wait(o_full, 0);
-        tc::fence_after_sync();
-        const float inv = 1.0f / l_run;
-        __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
-#pragma unroll
-        for (int c = 0; c < FA_D; c += 32) {
-            uint32_t o[32];
-            tc::tmem_ld32(tmem_base + lane_off + FA_O_COL + c, o);
-            tc::tmem_ld_wait();
-            if (row < p.Nq) {
-#pragma unroll
-                for (int e8 = 0; e8 < 32; e8 += 8) {
-                    uint4 u;
-                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
-                    *reinterpret_cast<uint4*>(dst + c + e8) = u;
-                }
-            }
-        }
+        softmax_tile<POLY>(p, tmem_base, (uint32_t)(q * 32) << 16, FA_S_COL, FA_P_COL, FA_O_COL, s_full, p_full, o_full, nblk,
+                           m0 + q * 32 + lane, lane, b, h);
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -493,14 +501,16 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    // A/B timing knobs. GVD_FLASH_V1=1: first-generation kernel. GVD_FLASH_POLY=1: one exponential in four on the FMA
-    // pipe; off by default -- measured on B200 at N=9216: 4.13 ms without, 4.46 ms with (v1: 5.03 ms); the kernel is
-    // bound by the softmax warps' issue slots and synchronisation, not by MUFU throughput alone.
+    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, GVD_FLASH_POLY=1 moves one exponential in four
+    // onto the FMA pipe.  Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, this kernel 4.13 ms, with the
+    // polynomial 4.46 ms; a variant with two query tiles ping-ponging inside one CTA per SM (8 softmax warps, all 512 TMEM
+    // columns) measured 4.20 ms and was dropped.  ncu: XU pipe 59 %, tensor pipe 30 %, issue slots 39 % -- no pipe is
+    // saturated; the softmax warps (two per scheduler) are latency-bound.
     static int variant = -1;
     if (variant < 0) {
-        const char* v1 = getenv("GVD_FLASH_V1");
-        const char* poly = getenv("GVD_FLASH_POLY");
-        const int want = (v1 && v1[0] == '1') ? 0 : ((poly && poly[0] == '1') ? 2 : 1);
+        const char* v = getenv("GVD_FLASH");
+        const char* pe = getenv("GVD_FLASH_POLY");
+        const int want = (v && v[0] == 'v' && v[1] == '1') ? 0 : ((pe && pe[0] == '1') ? 2 : 1);
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
                                    : (want == 1 ? (const void*)flash_attn_kernel<false> : (const void*)flash_attn_kernel<true>);
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);

@@ -34,14 +34,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Peer data is read exactly once per call and changes between calls: never serve it from a stale L1 line.
+// Payload accesses are plain (weak) 16-byte vector loads/stores -- system-scope accesses would each be ordered
+// individually and run at a fraction of the NVLink rate. Correctness comes from the barriers around them: every address
+// is read exactly once per call, after the entry barrier (acquire + bar.sync), so no stale L1 line can exist (L1 is
+// invalidated at kernel start and L1::no_allocate keeps the peer lines out of it); the stores are published by the
+// __threadfence_system() in front of the exit barrier's release.
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
     float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_peer(float4* p, float4 v) {
-    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -65,7 +69,7 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch, uin
 
 template <int WORLD>
 __device__ __forceinline__ void reduce_slice(const Params& p, unsigned long long begin, unsigned long long end) {
-    constexpr int U = WORLD <= 2 ? 4 : (WORLD <= 4 ? 2 : 1);  // independent 16-byte peer loads in flight per thread: U * WORLD
+    constexpr int U = WORLD <= 2 ? 8 : (WORLD <= 4 ? 2 : 1);  // independent 16-byte peer loads in flight per thread: U * WORLD
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long i = begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + (U - 1) * stride < end; i += U * stride) {

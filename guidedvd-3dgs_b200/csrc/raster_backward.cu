@@ -11,6 +11,7 @@
 //                            (backward.cu:144-274, 346-412, 20-139, 278-341) with the Python-side
 //                            confidence scaling (diff_gaussian_rasterization/__init__.py:147-157) in the
 //                            epilogue; every output element is written exactly once (no zero-fill pass).
+#include <cstdlib>
 #include "raster_common.cuh"
 #include "../../include/gvd_raster.h"
 
@@ -76,20 +77,26 @@ __device__ __forceinline__ int warp_reduce10(float (&v)[10], uint32_t lane, floa
     return local + (b4 ? 5 : 0);
 }
 
-__global__ void __launch_bounds__(GVD_BLOCK, 3) render_backward_kernel(
+template <int SPLIT>
+__global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, const float* __restrict__ alphas,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas, float* __restrict__ acc) {
-    __shared__ __align__(128) float4 buf[2][GVD_BATCH * 3];
+    pdl_wait();
+    pdl_trigger();
+    // SPLIT CTAs share one 16x16 tile (8 / SPLIT warps of 8x4 pixels each): shorter CTAs, finer early exit, smaller tail
+    constexpr int BLOCK = 256 / SPLIT, BATCH = BLOCK;
+    __shared__ __align__(128) float4 buf[2][BATCH * 3];
     __shared__ __align__(128) IdSlot ids[3];
     __shared__ __align__(8) uint64_t bar[3];
-    __shared__ uint32_t warp_max[GVD_BLOCK / 32];
+    __shared__ uint32_t warp_max[BLOCK / 32];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x / SPLIT;
+    const uint32_t gw = (blockIdx.x % SPLIT) * (8 / SPLIT) + warp;  // this warp's 8x4 block inside the tile
     const uint32_t tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const uint32_t sub_x = tile_x * GVD_TILE_X + (warp & 1) * 8, sub_y = tile_y * GVD_TILE_Y + (warp >> 1) * 4;
+    const uint32_t sub_x = tile_x * GVD_TILE_X + (gw & 1) * 8, sub_y = tile_y * GVD_TILE_Y + (gw >> 1) * 4;
     const uint32_t px = sub_x + (lane & 7), py = sub_y + (lane >> 3);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = W * py + px;
@@ -112,14 +119,14 @@ __global__ void __launch_bounds__(GVD_BLOCK, 3) render_backward_kernel(
     __syncthreads();
     uint32_t block_last = 0;
 #pragma unroll
-    for (int w = 0; w < GVD_BLOCK / 32; ++w) block_last = max(block_last, warp_max[w]);
+    for (int w = 0; w < BLOCK / 32; ++w) block_last = max(block_last, warp_max[w]);
     // Entries at positions >= block_last are skipped by every pixel: never stage them.
     const int n = min(n_all, (int)block_last);
-    const int rounds = (n + GVD_BATCH - 1) / GVD_BATCH;
+    const int rounds = (n + BATCH - 1) / BATCH;
     const uint32_t* list = point_list + range.x;
     // batch i (counted from the back) covers list positions [bstart(i), bstart(i) + bcnt(i))
-    auto bstart = [n](int i) { return max(0, n - (i + 1) * GVD_BATCH); };
-    auto bcnt = [n, &bstart](int i) { return (n - i * GVD_BATCH) - bstart(i); };
+    auto bstart = [n](int i) { return max(0, n - (i + 1) * BATCH); };
+    auto bcnt = [n, &bstart](int i) { return (n - i * BATCH) - bstart(i); };
 
     if (tid == 0) {
         if (rounds > 0) issue_id_copy(&ids[0], &bar[0], list + bstart(0), bcnt(0));
@@ -305,7 +312,8 @@ __device__ __forceinline__ void store_p3_coalesced(float* __restrict__ dst, floa
         o_sh[3 * (k) + 2] = _t.z * conf;            \
     }
 
-__global__ void __launch_bounds__(256, 2) gaussian_backward_kernel(
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
     int P, int D, int M, const float3* __restrict__ means, const int* __restrict__ radii,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float3* __restrict__ scales,
     const float4* __restrict__ rotations, const float scale_modifier, const float* __restrict__ cov3D_precomp,
@@ -314,6 +322,8 @@ __global__ void __launch_bounds__(256, 2) gaussian_backward_kernel(
     const float* __restrict__ confidence, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dmeans3D,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dcov3D,
     float* __restrict__ dL_dsh, float* __restrict__ dL_dscales, float* __restrict__ dL_drots) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float stage[3 * 256];
     extern __shared__ __align__(16) float sh_stage[];  // [8 warps][32 rows][GVD_SH_STAGE_STRIDE] (only when dL_dsh, M == 16)
     const int block_first = blockIdx.x * blockDim.x;
@@ -637,30 +647,53 @@ __global__ void __launch_bounds__(256, 2) gaussian_backward_kernel(
 
 }  // namespace
 
-void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
-                                const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
+template <int SPLIT>
+static void launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                                   const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
     static bool carveout_set = false;
     if (!carveout_set) {
-        cudaFuncSetAttribute((const void*)render_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         carveout_set = true;
     }
-    render_backward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height, grid.x,
-                                                                  a.background, a.alphas, im.n_contrib, a.dL_dpix,
-                                                                  a.dL_ddepth_pix, a.dL_dalpha_pix, acc);
+    gvd_launch(render_backward_kernel<SPLIT>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+               g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
+               a.dL_dalpha_pix, acc);
 }
 
-void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
-                                  float focal_x, float focal_y, cudaStream_t s) {
+void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                                const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
+    switch (gvd_render_split()) {
+        case 1: launch_render_backward<1>(a, g, b, im, acc, grid, s); break;
+        case 4: launch_render_backward<4>(a, g, b, im, acc, grid, s); break;
+        default: launch_render_backward<2>(a, g, b, im, acc, grid, s); break;
+    }
+}
+
+template <int MIN_CTAS>
+static void launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
+                                     float focal_x, float focal_y, cudaStream_t s) {
     const size_t sh_smem = (a.dL_dsh && a.M == 16) ? (size_t)8 * 32 * GVD_SH_STAGE_STRIDE * sizeof(float) : 0;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute((const void*)gaussian_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute((const void*)gaussian_backward_kernel<MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              8 * 32 * GVD_SH_STAGE_STRIDE * (int)sizeof(float));
         attr_set = true;
     }
-    gaussian_backward_kernel<<<(a.P + 255) / 256, 256, sh_smem, s>>>(
+    gvd_launch(gaussian_backward_kernel<MIN_CTAS>, dim3((a.P + 255) / 256), dim3(256), sh_smem, s,
         a.P, a.D, a.M, (const float3*)a.means3D, a.radii, a.shs, g.clamped, (const float3*)a.scales,
         (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
         a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,
         a.dL_dopacity, a.dL_dcolors, a.dL_dcov3D, a.dL_dsh, a.dL_dscales, a.dL_drotations);
+}
+
+void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
+                                  float focal_x, float focal_y, cudaStream_t s) {
+    // GVD_GBWD_CTAS=3: 80 registers (0.5 KB of spills) for three resident CTAs per SM instead of two (A/B timing knob)
+    static int ctas = 0;
+    if (!ctas) {
+        const char* e = getenv("GVD_GBWD_CTAS");
+        ctas = (e && e[0] == '3') ? 3 : 2;
+    }
+    if (ctas == 3) launch_gaussian_backward<3>(a, g, acc, focal_x, focal_y, s);
+    else launch_gaussian_backward<2>(a, g, acc, focal_x, focal_y, s);
 }

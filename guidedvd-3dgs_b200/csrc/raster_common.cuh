@@ -215,6 +215,33 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ shs, int idx, 
     }
 }
 
+// ---- programmatic dependent launch (sm_90+) --------------------------------------------------------------------
+// Every kernel of the forward/backward chain is launched with programmaticStreamSerialization: its CTAs may become
+// resident and run their prologue while the previous kernel of the stream drains. pdl_wait() -- the first statement
+// of every such kernel, executed by every thread -- returns once the previous grid has completed and its writes are
+// visible, so the chain stays transitively ordered; pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as
+// all CTAs of this grid have started. Both are no-ops for a launch without the attribute.  Measured at C2: +1.4 %.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int gvd_render_split();  // CTAs per tile in the render kernels
+bool gvd_pdl_enabled();  // GVD_PDL=0 turns the launch attribute off (A/B timing knob)
+
+template <typename... Exp, typename... Act>
+inline cudaError_t gvd_launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = gvd_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
+
 // ---- mbarrier / TMA bulk-copy wrappers (sm_90+; SASS: UBLKCP + SYNCS) ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

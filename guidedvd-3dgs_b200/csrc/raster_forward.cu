@@ -15,6 +15,7 @@
 //                         (forward.cu:261-381 semantics preserved: skipped instances are exactly those every
 //                         pixel of the warp would `continue` on).
 #include <cstdio>
+#include <cstdlib>
 #include "raster_common.cuh"
 #include "../../include/gvd_raster.h"
 
@@ -125,6 +126,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
     SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched,
     uint32_t* __restrict__ depth_key, uint32_t* __restrict__ gidx, int prefiltered) {
+    pdl_wait();
+    pdl_trigger();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
 
@@ -216,6 +219,8 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(int P, uint32_
                                                                  const uint32_t* __restrict__ tiles_touched,
                                                                  uint32_t* __restrict__ chunk_flags,
                                                                  uint32_t* __restrict__ hist) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ int diff[];  // (gy+1) rows of stride ld
     const int ld = (int)(gx + 1) | 1;  // odd stride: column walks are bank-conflict free
     const int rows = (int)gy + 1, cols = (int)gx + 1;
@@ -274,6 +279,8 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(int P, uint32_
 // shared memory, then every thread rewrites its segment as running prefixes.
 __global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int chunks, const uint32_t* __restrict__ chunk_flags,
                                                           uint32_t* hist, uint32_t* __restrict__ tile_total) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint32_t seg_sum[32][33];
     __shared__ int s_valid;
     const int tx = threadIdx.x & 31, seg = threadIdx.x >> 5;
@@ -323,6 +330,8 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int chunks, con
 // and R. One CTA; T <= GVD_MAX_TILES.
 __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t* __restrict__ tile_total,
                                                           uint2* __restrict__ ranges, uint32_t* __restrict__ num_rendered) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -359,29 +368,48 @@ __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t*
     if (tid == 0) *num_rendered = carry_s;
 }
 
-// Pass 4: chunk c writes its Gaussians' ids into the tile lists in depth order. cnt[t] = next free slot of
-// tile t. Two strategies, chosen per chunk:
-//   dense  (many large rects): one thread per tile walks the chunk's rects in order -- no barriers, and
-//          most tests succeed;
-//   sparse (small rects): Gaussians one after the other, threads sharing the tiles of the current rect.
-__global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, uint32_t tiles_x,
-                                                                const SplatRec* __restrict__ splat,
-                                                                const uint32_t* __restrict__ order,
-                                                                const uint32_t* __restrict__ tiles_touched,
-                                                                const uint32_t* __restrict__ chunk_flags,
-                                                                const uint32_t* __restrict__ hist,
-                                                                const uint2* __restrict__ ranges,
-                                                                uint32_t* __restrict__ point_list, uint32_t capacity) {
+// Pass 4: chunk c writes its Gaussians' ids into the tile lists in depth order: the slot of Gaussian g in tile t is
+// ranges[t].x + (chunk's starting rank in t, from pass 2) + (number of earlier Gaussians of the chunk covering t);
+// cnt[t] holds the next free slot of tile t. The only order constraint is per tile.
+//   chunks up to GVD_FILL_HEAVY instances: ONE warp walks the chunk's flattened (Gaussian, tile) sequence 32 instances
+//     at a time -- lane = instance, located by a load-balanced search over the chunk's instance offsets (REDUX.OR of
+//     the "a Gaussian starts here" bits + popc). Instances of a batch that fall into the same tile are ranked with
+//     MATCH.ANY (lane order = depth order); the first of each group advances cnt[t].
+//   heavier chunks (the Gaussians nearest to the camera, rects up to the whole screen; C2: median chunk 800 instances,
+//     largest 40 000): the tile ROWS are dealt out to the CTA's 8 warps (warp w owns rows ty = w mod 8); every warp
+//     walks the chunk on its own, lanes across the columns of the rect, no block barrier in the walk.
+// Measured: 85 us at C2, 265 us at C4 (1600x1066; a two-warp walk with a barrier per Gaussian took 445 us there).
+// Four other organisations (two-warp serial walk, rows over 4/8 warps for every chunk, shared-memory bit masks,
+// heavy chunks cut into slices over up to 32 CTAs) all land at 83-92 us at C2: the pass is bound by its 3.7 M
+// scattered 4-byte stores -- every 32-byte sector of a tile list is written by ~8 different chunks -- not by the walk.
+struct FillChunk {  // the chunk's non-empty Gaussians, compacted in order
+    uint32_t id[GVD_BIN_CHUNK], r0[GVD_BIN_CHUNK], r1[GVD_BIN_CHUNK], off[GVD_BIN_CHUNK + 1], magic[GVD_BIN_CHUNK];
+    uint32_t wn[2], wc[2];
+};
+
+#define GVD_FILL_THREADS 256
+#define GVD_FILL_HEAVY 6144
+__global__ void __launch_bounds__(GVD_FILL_THREADS) bin_fill_kernel(int P, int T, uint32_t tiles_x,
+                                                                   const SplatRec* __restrict__ splat,
+                                                                   const uint32_t* __restrict__ order,
+                                                                   const uint32_t* __restrict__ tiles_touched,
+                                                                   const uint32_t* __restrict__ chunk_flags,
+                                                                   const uint32_t* __restrict__ hist,
+                                                                   const uint2* __restrict__ ranges,
+                                                                   uint32_t* __restrict__ point_list, uint32_t capacity) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ uint32_t cnt[];
-    __shared__ uint32_t s_id[GVD_BIN_CHUNK], s_n[GVD_BIN_CHUNK], s_r0[GVD_BIN_CHUNK], s_r1[GVD_BIN_CHUNK];
-    __shared__ uint32_t s_total;
+    __shared__ FillChunk fc;
+    static_assert(GVD_BIN_CHUNK == 64, "two warps load the chunk");
     if (!chunk_flags[blockIdx.x]) return;
-    const int tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t* row = hist + (size_t)blockIdx.x * T;
-    if (tid == 0) s_total = 0;
-    {
-        const int i = blockIdx.x * GVD_BIN_CHUNK + tid;
-        uint32_t id = 0, n = 0, r0 = 0, r1 = 0;
+    // threads 0..63 load the chunk and compact its non-empty Gaussians (order kept)
+    uint32_t id = 0, n = 0, r0 = 0, r1 = 0, incl = 0, ballot = 0;
+    if (tid < GVD_BIN_CHUNK) {
+        const int i = blockIdx.x * GVD_BIN_CHUNK + (int)tid;
         if (i < P) {
             id = order[i];
             n = tiles_touched[id];
@@ -391,48 +419,86 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_fill_kernel(int P, int T, u
                 r1 = __float_as_uint(d.y);
             }
         }
-        s_id[tid] = id; s_n[tid] = n; s_r0[tid] = r0; s_r1[tid] = r1;
-        __syncthreads();
-        uint32_t w = n;
+        ballot = __ballot_sync(0xffffffffu, n > 0);
+        incl = n;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-        if ((tid & 31) == 0 && w) atomicAdd(&s_total, w);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        if (lane == 31) {
+            fc.wn[warp] = incl;
+            fc.wc[warp] = __popc(ballot);
+        }
+    }
+    for (uint32_t t = tid; t < (uint32_t)T; t += blockDim.x) cnt[t] = ranges[t].x + row[t];
+    __syncthreads();
+    const uint32_t m = fc.wc[0] + fc.wc[1], total = fc.wn[0] + fc.wn[1];
+    if (tid < GVD_BIN_CHUNK) {
+        const uint32_t base_n = warp ? fc.wn[0] : 0u, base_c = warp ? fc.wc[0] : 0u;
+        if (n > 0) {
+            const uint32_t j = base_c + __popc(ballot & lt_mask);
+            const uint32_t bw = (r1 & 0xffff) - (r0 & 0xffff);
+            fc.id[j] = id;
+            fc.r0[j] = r0;
+            fc.r1[j] = r1;
+            fc.off[j] = base_n + incl - n;
+            fc.magic[j] = 0xffffffffu / bw + 1u;  // floor(k / bw) == umulhi(k, magic) for k * bw < 2^32 (bw > 1)
+        }
+        if (tid == 0) fc.off[m] = total;
     }
     __syncthreads();
-    const bool dense = (uint64_t)s_total * 4u > (uint64_t)T * GVD_BIN_CHUNK;  // > 25 % of the rect tests succeed
-    if (dense) {
-        for (int t = tid; t < T; t += GVD_BIN_CHUNK) {
-            const uint32_t tx = (uint32_t)t % tiles_x, ty = (uint32_t)t / tiles_x;
-            uint32_t slot = ranges[t].x + row[t];
-            for (int g = 0; g < GVD_BIN_CHUNK; ++g) {
-                const uint32_t r0 = s_r0[g], r1 = s_r1[g];
-                // empty rects have r0 == r1 == 0 and fail the test
-                if (tx >= (r0 & 0xffff) && tx < (r1 & 0xffff) && ty >= (r0 >> 16) && ty < (r1 >> 16)) {
-                    if (slot < capacity) point_list[slot] = s_id[g];  // capacity: speculative buffers may be too small
-                    ++slot;
-                }
+
+    if (total <= GVD_FILL_HEAVY) {
+        if (warp != 0) return;
+        const uint32_t le_mask = lt_mask | (1u << lane);
+        const uint32_t o_lo = lane < m ? fc.off[lane] : 0xffffffffu;
+        const uint32_t o_hi = lane + 32 < m ? fc.off[lane + 32] : 0xffffffffu;
+        uint32_t before = 0;  // compacted Gaussians that start before this batch
+        for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+            uint32_t bits = 0;
+            if (o_lo - b0 < 32u) bits |= 1u << (o_lo - b0);
+            if (o_hi - b0 < 32u) bits |= 1u << (o_hi - b0);
+            const uint32_t starts = __reduce_or_sync(0xffffffffu, bits);
+            const uint32_t q = b0 + lane;
+            const bool valid = q < total;
+            uint32_t t = 0xffffff00u + lane, gid = 0;  // invalid lanes: distinct keys, they match nobody
+            if (valid) {
+                const uint32_t j = before + __popc(starts & le_mask) - 1u;
+                const uint32_t g0 = fc.r0[j], g1 = fc.r1[j];
+                const uint32_t x0 = g0 & 0xffff, bw = (g1 & 0xffff) - x0;
+                const uint32_t k = q - fc.off[j];
+                const uint32_t ry = bw > 1 ? __umulhi(k, fc.magic[j]) : k;
+                t = ((g0 >> 16) + ry) * tiles_x + x0 + (k - ry * bw);
+                gid = fc.id[j];
             }
+            before += __popc(starts);
+            const uint32_t peers = __match_any_sync(0xffffffffu, t);
+            const uint32_t rank = __popc(peers & lt_mask);
+            const uint32_t base = valid ? cnt[t] : 0u;
+            __syncwarp();
+            if (valid) {
+                if (rank == 0) cnt[t] = base + __popc(peers);
+                const uint32_t slot = base + rank;
+                if (slot < capacity) point_list[slot] = gid;  // capacity: speculative buffers may be too small
+            }
+            __syncwarp();
         }
         return;
     }
-    for (int t = tid; t < T; t += GVD_BIN_CHUNK) cnt[t] = ranges[t].x + row[t];
-    bool prev_big = true;
-    for (int g = 0; g < GVD_BIN_CHUNK; ++g) {
-        const uint32_t n = s_n[g];
-        if (n == 0) continue;
-        const bool big = n > 32;
-        // rects of <= 32 tiles are handled by warp 0 alone: consecutive small ones only need warp-level ordering
-        if (big || prev_big) __syncthreads(); else __syncwarp();
-        prev_big = big;
-        if (!big && tid >= 32) continue;
-        const uint32_t id = s_id[g], r0 = s_r0[g], r1 = s_r1[g];
-        const uint32_t x0 = r0 & 0xffff, y0 = r0 >> 16, bw = (r1 & 0xffff) - x0;
-        for (uint32_t k = tid; k < n; k += GVD_BIN_CHUNK) {
-            const uint32_t t = (y0 + k / bw) * tiles_x + x0 + k % bw;
-            const uint32_t slot = cnt[t];
-            cnt[t] = slot + 1;
-            if (slot < capacity) point_list[slot] = id;
-        }
+
+    for (uint32_t g = 0; g < m; ++g) {
+        const uint32_t g0 = fc.r0[g], g1 = fc.r1[g];
+        const uint32_t y0 = g0 >> 16, y1 = g1 >> 16, x0 = g0 & 0xffff, x1 = g1 & 0xffff;
+        const uint32_t gid = fc.id[g];
+        for (uint32_t ty = y0 + (warp + nw - y0 % nw) % nw; ty < y1; ty += nw)
+            for (uint32_t tx = x0 + lane; tx < x1; tx += 32) {
+                const uint32_t t = ty * tiles_x + tx;
+                const uint32_t slot = cnt[t];
+                cnt[t] = slot + 1;
+                if (slot < capacity) point_list[slot] = gid;
+            }
+        __syncwarp();  // lanes change tiles from one Gaussian to the next: keep the warp's walk in step
     }
 }
 
@@ -441,6 +507,8 @@ __global__ void __launch_bounds__(256) export_keys_kernel(uint32_t capacity, int
                                                           const uint32_t* __restrict__ point_list,
                                                           const uint32_t* __restrict__ depth_key,
                                                           uint64_t* __restrict__ keys) {
+    pdl_wait();
+    pdl_trigger();
     const int tile = blockIdx.x;
     const uint2 r = ranges[tile];
     for (uint32_t k = r.x + threadIdx.x; k < r.y && k < capacity; k += blockDim.x)
@@ -448,18 +516,24 @@ __global__ void __launch_bounds__(256) export_keys_kernel(uint32_t capacity, int
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
+template <int SPLIT>
+__global__ void __launch_bounds__(256 / SPLIT, 4 * SPLIT) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, uint32_t capacity) {
-    __shared__ __align__(128) float4 buf[2][GVD_BATCH * 3];
+    pdl_wait();
+    pdl_trigger();
+    // SPLIT CTAs share one 16x16 tile (8 / SPLIT warps of 8x4 pixels each): shorter CTAs, finer early exit, smaller tail
+    constexpr int BLOCK = 256 / SPLIT, BATCH = BLOCK;
+    __shared__ __align__(128) float4 buf[2][BATCH * 3];
     __shared__ __align__(128) IdSlot ids[3];
     __shared__ __align__(8) uint64_t bar[3];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x / SPLIT;
+    const uint32_t gw = (blockIdx.x % SPLIT) * (8 / SPLIT) + warp;  // this warp's 8x4 block inside the tile
     const uint32_t tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const uint32_t sub_x = tile_x * GVD_TILE_X + (warp & 1) * 8, sub_y = tile_y * GVD_TILE_Y + (warp >> 1) * 4;
+    const uint32_t sub_x = tile_x * GVD_TILE_X + (gw & 1) * 8, sub_y = tile_y * GVD_TILE_Y + (gw >> 1) * 4;
     const uint32_t px = sub_x + (lane & 7), py = sub_y + (lane >> 3);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = W * py + px;
@@ -471,7 +545,7 @@ __global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
     range.x = min(range.x, capacity);
     range.y = min(range.y, capacity);
     const int n = (int)(range.y - range.x);
-    const int rounds = (n + GVD_BATCH - 1) / GVD_BATCH;
+    const int rounds = (n + BATCH - 1) / BATCH;
     const uint32_t* list = point_list + range.x;
 
     if (tid == 0) {
@@ -482,13 +556,13 @@ __global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
     }
     __syncthreads();
     if (tid == 0) {
-        if (rounds > 0) issue_id_copy(&ids[0], &bar[0], list, min(GVD_BATCH, n));
-        if (rounds > 1) issue_id_copy(&ids[1], &bar[1], list + GVD_BATCH, min(GVD_BATCH, n - GVD_BATCH));
+        if (rounds > 0) issue_id_copy(&ids[0], &bar[0], list, min(BATCH, n));
+        if (rounds > 1) issue_id_copy(&ids[1], &bar[1], list + BATCH, min(BATCH, n - BATCH));
     }
     // batch 0 -> buf[0]
     if (rounds > 0) {
         mbar_wait(&bar[0], 0);
-        if ((int)tid < min(GVD_BATCH, n)) {
+        if ((int)tid < min(BATCH, n)) {
             const float4* src = reinterpret_cast<const float4*>(splat + ids[0].v[id_lead(list) + tid]);
             buf[0][tid * 3 + 0] = __ldg(src);
             buf[0][tid * 3 + 1] = __ldg(src + 1);
@@ -504,33 +578,33 @@ __global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
     for (int i = 0; i < rounds; ++i) {
         // whole tile saturated? (forward.cu:310-313). Also publishes buf[i&1] and retires buf[(i+1)&1].
         const int num_done = __syncthreads_count(done);
-        if (num_done == GVD_BLOCK) {
+        if (num_done == BLOCK) {
             // a CTA must not exit under a pending bulk copy: batch i+1's ids may still be in flight
             if (i + 1 < rounds) mbar_wait(&bar[(i + 1) % 3], (uint32_t)(((i + 1) / 3) & 1));
             break;
         }
         const int cur = i & 1;
-        const int cnt = min(GVD_BATCH, n - i * GVD_BATCH);
+        const int cnt = min(BATCH, n - i * BATCH);
         // prefetch: records of batch i+1 into registers (ids landed a round ago), ids of batch i+2 by TMA
         float4 pa, pb, pc;
-        const int ncnt = min(GVD_BATCH, n - (i + 1) * GVD_BATCH);
+        const int ncnt = min(BATCH, n - (i + 1) * BATCH);
         const bool have_next = (i + 1 < rounds) && ((int)tid < ncnt);
         if (i + 1 < rounds) {
             mbar_wait(&bar[(i + 1) % 3], (uint32_t)(((i + 1) / 3) & 1));
             if (have_next) {
-                const uint32_t* first = list + (size_t)(i + 1) * GVD_BATCH;
+                const uint32_t* first = list + (size_t)(i + 1) * BATCH;
                 const float4* src = reinterpret_cast<const float4*>(splat + ids[(i + 1) % 3].v[id_lead(first) + tid]);
                 pa = __ldg(src);
                 pb = __ldg(src + 1);
                 pc = __ldg(src + 2);
             }
             if (tid == 0 && i + 2 < rounds)
-                issue_id_copy(&ids[(i + 2) % 3], &bar[(i + 2) % 3], list + (size_t)(i + 2) * GVD_BATCH,
-                              min(GVD_BATCH, n - (i + 2) * GVD_BATCH));
+                issue_id_copy(&ids[(i + 2) % 3], &bar[(i + 2) % 3], list + (size_t)(i + 2) * BATCH,
+                              min(BATCH, n - (i + 2) * BATCH));
         }
 
         const float4* rec = buf[cur];
-        const uint32_t base = (uint32_t)i * GVD_BATCH;
+        const uint32_t base = (uint32_t)i * BATCH;
         for (int chunk = 0; chunk * 32 < cnt; ++chunk) {
             if (__all_sync(0xffffffffu, done)) break;
             const int e = chunk * 32 + (int)lane;
@@ -586,6 +660,8 @@ __global__ void __launch_bounds__(GVD_BLOCK, 4) render_forward_kernel(
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ orig_points,
                                                            const float* __restrict__ viewmatrix,
                                                            uint8_t* __restrict__ present) {
+    pdl_wait();
+    pdl_trigger();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const float3 p = {orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]};
@@ -597,7 +673,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, float focal_x, float focal_y,
                            dim3 grid, cudaStream_t s) {
-    preprocess_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
+    gvd_launch(preprocess_kernel, dim3((a.P + 255) / 256), dim3(256), 0, s, 
         a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
         a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
         (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
@@ -614,10 +690,10 @@ cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImg
     const size_t smem = (size_t)(grid.y + 1) * ((grid.x + 1) | 1) * sizeof(int);
     cudaError_t e = ensure_smem((const void*)bin_count_kernel, smem);
     if (e != cudaSuccess) return e;
-    bin_count_kernel<<<(unsigned)g.chunks, GVD_BIN_CHUNK, smem, s>>>(P, grid.x, grid.y, g.splat, g.order,
+    gvd_launch(bin_count_kernel, dim3((unsigned)g.chunks), dim3(GVD_BIN_CHUNK), smem, s, P, grid.x, grid.y, g.splat, g.order,
                                                                     g.tiles_touched, g.chunk_flags, g.hist);
-    bin_prefix_kernel<<<(T + 31) / 32, 1024, 0, s>>>(T, (int)g.chunks, g.chunk_flags, g.hist, g.tile_total);
-    bin_ranges_kernel<<<1, 1024, 0, s>>>(T, g.tile_total, im.ranges, g.num_rendered);
+    gvd_launch(bin_prefix_kernel, dim3((T + 31) / 32), dim3(1024), 0, s, T, (int)g.chunks, g.chunk_flags, g.hist, g.tile_total);
+    gvd_launch(bin_ranges_kernel, dim3(1), dim3(1024), 0, s, T, g.tile_total, im.ranges, g.num_rendered);
     return cudaGetLastError();
 }
 
@@ -627,8 +703,8 @@ cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinP
     const size_t smem = (size_t)T * sizeof(uint32_t);
     cudaError_t e = ensure_smem((const void*)bin_fill_kernel, smem);
     if (e != cudaSuccess) return e;
-    bin_fill_kernel<<<(unsigned)g.chunks, GVD_BIN_CHUNK, smem, s>>>(P, T, grid.x, g.splat, g.order, g.tiles_touched,
-                                                                   g.chunk_flags, g.hist, im.ranges, b.point_list, capacity);
+    gvd_launch(bin_fill_kernel, dim3((unsigned)g.chunks), dim3(GVD_FILL_THREADS), smem, s, P, T, grid.x, g.splat, g.order,
+               g.tiles_touched, g.chunk_flags, g.hist, im.ranges, b.point_list, capacity);
     return cudaGetLastError();
 }
 
@@ -636,22 +712,50 @@ void gvd_launch_export_keys(uint32_t capacity, const RasterGeomPtrs& g, const Ra
                             dim3 grid, cudaStream_t s) {
     if (capacity == 0 || !b.keys) return;
     const int T = (int)(grid.x * grid.y);
-    export_keys_kernel<<<T, 256, 0, s>>>(capacity, T, im.ranges, b.point_list, g.depth_key, b.keys);
+    gvd_launch(export_keys_kernel, dim3(T), dim3(256), 0, s, capacity, T, im.ranges, b.point_list, g.depth_key, b.keys);
+}
+
+int gvd_render_split() {
+    // CTAs per 16x16 tile in the render kernels (1, 2 or 4); GVD_RENDER_SPLIT overrides (A/B timing knob)
+    static int split = 0;
+    if (!split) {
+        const char* e = getenv("GVD_RENDER_SPLIT");
+        split = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 2;
+    }
+    return split;
+}
+
+template <int SPLIT>
+static void launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
+                                  const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s) {
+    static bool carveout_set = false;
+    if (!carveout_set) {  // many small CTAs per SM need the large shared-memory carveout
+        cudaFuncSetAttribute((const void*)render_forward_kernel<SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carveout_set = true;
+    }
+    gvd_launch(render_forward_kernel<SPLIT>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+               g.splat, a.width, a.height, grid.x, a.background, a.out_color, a.out_depth, a.out_alpha, im.n_contrib, capacity);
 }
 
 void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s) {
-    static bool carveout_set = false;
-    if (!carveout_set) {  // eight 28 KB CTAs per SM need the large shared-memory carveout
-        cudaFuncSetAttribute((const void*)render_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        carveout_set = true;
+    switch (gvd_render_split()) {
+        case 1: launch_render_forward<1>(a, g, b, im, grid, capacity, s); break;
+        case 4: launch_render_forward<4>(a, g, b, im, grid, capacity, s); break;
+        default: launch_render_forward<2>(a, g, b, im, grid, capacity, s); break;
     }
-    render_forward_kernel<<<grid.x * grid.y, GVD_BLOCK, 0, s>>>(im.ranges, b.point_list, g.splat, a.width, a.height,
-                                                                 grid.x, a.background, a.out_color, a.out_depth,
-                                                                 a.out_alpha, im.n_contrib, capacity);
+}
+
+bool gvd_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GVD_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 
 void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                              cudaStream_t s) {
-    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+    gvd_launch(mark_visible_kernel, dim3((P + 255) / 256), dim3(256), 0, s, P, means3D, viewmatrix, present);
 }

@@ -120,8 +120,21 @@ def set_gradient_buffer(buf):
     """buf: 1-D float32 CUDA tensor (>= 62 floats per Gaussian + padding) or None to restore fresh allocations."""
     if buf is None:
         _grad_buffer.clear()
+        _last_views.clear()
+        _view_cache.clear()
     else:
         _grad_buffer[buf.device] = buf
+
+
+_last_views = {}
+
+
+def gradient_views(device):
+    """With a caller-owned gradient buffer (set_gradient_buffer): the views of it that the most recent backward on
+    `device` filled, keyed by the rasterizer input they belong to.  autograd's AccumulateGrad does not adopt gradient
+    tensors that are views of a larger buffer (it copies them into `leaf.grad`), so a data-parallel caller sums the
+    BUFFER across ranks and then points `leaf.grad` at these views (view_parallel.allreduce_gradients)."""
+    return _last_views.get(torch.device(device))
 
 
 def _stream():
@@ -332,6 +345,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                 has_cov)
         # gradients of absent inputs are never consumed: None instead of the reference's unused zero tensors
         dL_dmeans2D, dL_dmeans3D, dL_dopacity, dL_dcolors, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations = views
+        if ext is not None and ext.numel() >= total:
+            _last_views[dev] = {"means2D": dL_dmeans2D, "means3D": dL_dmeans3D, "opacities": dL_dopacity,
+                                "colors_precomp": dL_dcolors, "cov3D_precomp": dL_dcov3D, "shs": dL_dsh,
+                                "scales": dL_dscales, "rotations": dL_drotations, "_floats": total}
         scratch = torch.empty((int(lib.gvd_raster_backward_scratch_bytes(P)),), dtype=torch.uint8, device=dev)
 
         background = _f32c(background, "background")

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _C
-from ._C import gradient_buffer_floats, set_gradient_buffer  # noqa: F401  (B200 extension: caller-owned gradient storage)
+from ._C import gradient_buffer_floats, gradient_views, set_gradient_buffer  # noqa: F401  (B200 extension: caller-owned gradient storage)
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -29,21 +29,25 @@ def cpu_deep_copy_tuple(input_tuple):
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings):
+    # Will a backward come?  (Inside Function.forward grad mode is always off and ctx.needs_input_grad ignores
+    # torch.no_grad(), so this is decided here.)  If so, validation of the speculative instance buffer is deferred
+    # to the backward (see _C.DEFER).
+    defer = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad
+        for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, defer)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, defer=False):
         rs = raster_settings
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
                 rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
-        # With a backward to come, validation of the speculative instance buffer is deferred to it (see _C.DEFER):
-        # num_rendered is then a _C.PendingR until the backward (or int()) resolves it.
-        defer = any(ctx.needs_input_grad)
+        # defer: num_rendered may be a _C.PendingR until the backward (or int()) resolves it.
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy before they can be corrupted
             try:
@@ -90,7 +94,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # confidence is already applied in-kernel to everything except grad_means2D
         # (reference: diff_gaussian_rasterization/__init__.py:147-157)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
-                grad_rotations, grad_cov3Ds_precomp, None)
+                grad_rotations, grad_cov3Ds_precomp, None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):

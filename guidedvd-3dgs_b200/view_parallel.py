@@ -100,19 +100,33 @@ class GradientExchange:
         self.ptrs = None
 
 
-def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool = False, exchange: GradientExchange = None) -> None:
-    """In-place sum (or mean) of a list of gradient tensors over the ranks, as ONE collective.  With `exchange`, and the
-    gradients living in its buffer (set_gradient_buffer), the collective is the peer-memory kernel; otherwise NCCL/gloo."""
-    grads = [g for g in grads if g is not None]
-    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool = False, exchange: GradientExchange = None,
+                        leaves=None, views=None) -> None:
+    """In-place sum (or mean) of the gradients of one step over the ranks, as ONE collective.
+
+    Peer-memory path (`exchange`, `leaves`, `views`): the rasterizer backward wrote this rank's gradients into the
+    exchange buffer (diff_gaussian_rasterization.set_gradient_buffer); `views` = diff_gaussian_rasterization.
+    gradient_views(device) names the slices.  The buffer is summed across the ranks by one launch of the peer-memory
+    kernel and every `leaves[name].grad` is then pointed at its slice of the buffer -- no packing, no copy back
+    (autograd itself does not adopt gradients that are views of a larger buffer, it copies them).
+    Otherwise: NCCL/gloo, one all-reduce over the flat base buffer when all gradients are views of one, else one per
+    tensor."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    if exchange is not None and all(exchange.owns(g) for g in grads):
-        hi = max(g.data_ptr() + g.numel() * 4 for g in grads) - exchange.buffer.data_ptr()
-        exchange.allreduce(hi // 4)
+    if exchange is not None and leaves is not None and views is not None:
+        n = int(views["_floats"])
+        exchange.allreduce(n)
         if average:
-            exchange.buffer[:hi // 4] /= exchange.world
+            exchange.buffer[:n] /= exchange.world
+        for name, leaf in leaves.items():
+            v = views.get(name)
+            if v is not None and leaf is not None:
+                leaf.grad = v if v.shape == leaf.shape else v.view_as(leaf)
         return
-    # Fast path: the rasterizer hands out all its gradients as views of one flat buffer -> reduce it in place.
+    grads = [g for g in grads if g is not None]
+    if not grads:
+        return
+    # the rasterizer hands out all its gradients as views of one flat buffer -> reduce it in place
     base = grads[0]._base
     if base is not None and base.dim() == 1 and all(g._base is base for g in grads):
         lo = min(g.storage_offset() for g in grads)
@@ -122,15 +136,10 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool
         if average:
             seg /= dist.get_world_size(group)
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        flat /= dist.get_world_size(group)
-    off = 0
     for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            g /= dist.get_world_size(group)
 
 
 def accumulate_views(per_view_grads: Iterable[Sequence[torch.Tensor]]) -> List[torch.Tensor]:

@@ -219,7 +219,8 @@ def test_speculative_instance_buffer_matches_exact_path():
             assert torch.equal(r[k], exact[k]), k
         for k in exact["grads"]:
             assert _grad_err(r["grads"][k], exact["grads"][k])[1] < 1e-5, k
-    nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
+    with torch.no_grad():
+        nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
     assert torch.equal(nograd["color"], exact["color"])
 
 
@@ -237,7 +238,8 @@ def test_speculative_instance_buffer_overflow(monkeypatch):
     ours._C._spec_state.clear()
     pr.run(ours, sc, cam, cot, bg, D, export_keys=False)          # builds the history
     monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)  # every later guess is far too small
-    nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
+    with torch.no_grad():  # no backward to come: the shim validates before returning and redoes the frame exactly
+        nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
     for k in ("color", "depth", "alpha", "radii"):
         assert torch.equal(nograd[k], exact[k]), k
     with pytest.raises(RuntimeError, match="speculative instance buffer"):

@@ -1,4 +1,4 @@
-"""Times gvd_flash_attention on the U-Net's self-attention shapes at C3 (env GVD_FLASH_V1 / GVD_FLASH_POLY pick the variant)."""
+"""Times gvd_flash_attention on the U-Net's self-attention shapes at C3 (env GVD_FLASH=v1|v2 and GVD_FLASH_POLY=0|1 pick the variant)."""
 import os
 import sys
 
@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import torch
 from vc_b200 import ops
 
-tag = f"v1={os.environ.get('GVD_FLASH_V1', '0')} poly={os.environ.get('GVD_FLASH_POLY', '0')}"
+tag = f"{os.environ.get('GVD_FLASH', 'v2')} poly={os.environ.get('GVD_FLASH_POLY', '0')}"
 for (B, N, H) in ((25, 9216, 5), (25, 2304, 10), (25, 576, 20)):
     g = torch.Generator(device="cuda").manual_seed(3)
     q, k, v = (torch.randn(B, N, H * 64, device="cuda", generator=g).bfloat16() for _ in range(3))

@@ -73,9 +73,10 @@ st = dgr.GaussianRasterizationSettings(image_height=128, image_width=128, tanfov
 color, radii, depth, alpha = dgr.GaussianRasterizer(st)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
                                                          shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
 color.sum().backward()
-out["grads_live_in_exchange_buffer"] = {k: bool(ex.owns(v.grad)) for k, v in leaves.items()}
+out["autograd_adopts_buffer_views"] = {k: bool(ex.owns(v.grad)) for k, v in leaves.items()}
 local = {k: v.grad.clone() for k, v in leaves.items()}
-vp.allreduce_gradients([v.grad for v in leaves.values()], exchange=ex)
+vp.allreduce_gradients(None, exchange=ex, leaves=dict(leaves, means2D=m2d), views=dgr.gradient_views(dev))
+out["grads_live_in_exchange_buffer"] = {k: bool(ex.owns(v.grad)) for k, v in leaves.items()}
 for k in local:
     dist.all_reduce(local[k])
 torch.cuda.synchronize()
