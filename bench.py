@@ -110,7 +110,7 @@ def make_step(pkg, sc, cam, bg, D):
     means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
     conf = sc["confidence"]
 
-    def step(cot, viewmatrix, projmatrix, campos):
+    def step(cot, viewmatrix, projmatrix, campos, after_forward=None):
         settings = pkg.GaussianRasterizationSettings(
             image_height=cam["height"], image_width=cam["width"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
             bg=bg, scale_modifier=1.0, viewmatrix=viewmatrix, projmatrix=projmatrix, sh_degree=D, campos=campos,
@@ -121,6 +121,8 @@ def make_step(pkg, sc, cam, bg, D):
         means2D.grad = None
         color, radii, depth, alpha = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
                                           shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        if after_forward is not None:
+            after_forward()
         torch.autograd.backward([color, depth, alpha], [cot[0:3], cot[3:4], cot[4:5]])
         return color, radii
 
@@ -139,6 +141,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spinup-seconds", type=float, default=1.5, help="untimed load before the warm-up steps (both arms)")
     ap.add_argument("--no-denoise", action="store_true", help="skip the secondary DDIM denoise-steps/s measurement")
     ap.add_argument("--ref-device", default="gpu", choices=["gpu", "cpu"],
                     help="reference arm: compiled reference CUDA on the GPU (default) or the C oracle port on host cores")
@@ -207,62 +210,86 @@ def main():
         if world > 1:
             sum_gradients()
 
-    # End-to-end step: this step's inputs (camera, cotangent images) come from pinned host memory. Like a
-    # prefetching data loader, the upload of step k+1 is issued on a copy stream while step k computes.
+    # End-to-end step: this step's inputs (camera matrices + cotangent images, one pinned host buffer) are uploaded
+    # every step. Like a prefetching data loader, the upload of step k+1 is issued on a copy stream while step k
+    # computes (two device slots). The step's result -- the scalar a trainer reads back every iteration
+    # (train_baseline.py:88), one reduction kernel -- travels to pinned host memory on the same side stream and is READ
+    # `LAG` steps later (asynchronous loss logging), so the host never idles the GPU; every step's value is read inside
+    # the timed region (the last ones by e2e_flush).
+    LAG = 2
+    NCAM = 64  # camera block padded to 256 bytes so the cotangent images stay 256-byte aligned
+    in_host = torch.cat([cam_host, torch.zeros(NCAM - cam_host.numel()), cot_host.flatten()]).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    dev_slots = [(torch.empty_like(cam_host, device=dev), torch.empty_like(cot_host, device=dev)) for _ in range(2)]
+    dev_slots = [torch.empty_like(in_host, device=dev) for _ in range(2)]
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     slot_free = [torch.cuda.Event() for _ in range(2)]
-    staged = {"n": 0}
+    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    loss_ready = [torch.cuda.Event() for _ in range(LAG + 1)]
+    loss_events = [torch.cuda.Event() for _ in range(LAG + 1)]
+    e2e_state = {"k": 0, "last": None, "staged": 0, "pending": None, "fwd_recorded": False}
+    # The 6 MB upload of the next step's inputs is timed to run under the current step's BACKWARD. Anything the copy
+    # engines serve inside the compute stream (cudaMemsetAsync: CUB's radix-sort counters in the forward; formerly also
+    # the backward's accumulator clear and the 4-byte read-back of R, both now done by kernels) queues behind a
+    # transfer in flight: with the upload running under the forward a step took 625 us, under the backward 589 us
+    # (device-resident inputs: 571 us). GVD_E2E_H2D_AT=start restores the earlier placement (A/B knob).
+    H2D_AT_BWD = os.environ.get("GVD_E2E_H2D_AT", "bwd") != "start"
+    fwd_event = torch.cuda.Event()
 
-    def stage_inputs(k):
-        cm, cot = dev_slots[k % 2]
+    def side_stream_work(k):
+        """One visit to the copy stream per step: result of step k-1 to the host, inputs of step k+1 to the device."""
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(slot_free[k % 2])  # the step that last used this slot has finished
-            cm.copy_(cam_host, non_blocking=True)
-            cot.copy_(cot_host, non_blocking=True)
-            h2d_done[k % 2].record(copy_stream)
+            pend = e2e_state["pending"]
+            if pend is not None:
+                j, loss = pend
+                copy_stream.wait_event(loss_ready[j % (LAG + 1)])
+                loss_pinned[j % (LAG + 1)].copy_(loss, non_blocking=True)
+                loss.record_stream(copy_stream)
+                loss_events[j % (LAG + 1)].record(copy_stream)
+                e2e_state["pending"] = None
+            if k is not None and e2e_state["staged"] <= k:
+                copy_stream.wait_event(slot_free[k % 2])  # the step that last used this slot has finished
+                if H2D_AT_BWD and e2e_state["fwd_recorded"]:
+                    copy_stream.wait_event(fwd_event)      # ... and the current step has reached its backward
+                dev_slots[k % 2].copy_(in_host, non_blocking=True)
+                h2d_done[k % 2].record(copy_stream)
+                e2e_state["staged"] = k + 1
+
+    def read_back(j):
+        loss_events[j % (LAG + 1)].synchronize()
+        e2e_state["last"] = float(loss_pinned[j % (LAG + 1)])
 
     def e2e_step():
         k = e2e_state["k"]
-        if staged["n"] <= k:
-            stage_inputs(k)
-            staged["n"] = k + 1
-        cm, cot = dev_slots[k % 2]
+        if e2e_state["staged"] <= k:
+            side_stream_work(k)
+        def prefetch():  # D2H of the previous result + H2D of the next inputs overlap this step's kernels
+            if H2D_AT_BWD:
+                fwd_event.record()
+                e2e_state["fwd_recorded"] = True
+            side_stream_work(k + 1)
+
+        if not H2D_AT_BWD:
+            prefetch()
+        buf = dev_slots[k % 2]
         torch.cuda.current_stream().wait_event(h2d_done[k % 2])
-        stage_inputs(k + 1)  # H2D of the next step overlaps this step's kernels
-        staged["n"] = k + 2
-        color, radii = step(cot, cm[0:16].view(4, 4), cm[16:32].view(4, 4), cm[32:35])
+        cot = buf[NCAM:].view(5, H, W)
+        color, radii = step(cot, buf[0:16].view(4, 4), buf[16:32].view(4, 4), buf[32:35],
+                            after_forward=prefetch if H2D_AT_BWD else None)
         if world > 1:
             sum_gradients()
-        # The step's result: the scalar a trainer reads back every iteration (train_baseline.py:88), one reduction kernel.
-        # It travels to pinned host memory on a side stream (so the D2H copy never holds up the compute stream) and is
-        # READ one step later (asynchronous loss logging): the host never idles the GPU, and every step's value is
-        # read inside the timed region (the last one by e2e_flush).
-        loss = torch.dot(color.detach().view(-1), cot[0:3].reshape(-1))
-        loss_ready[k % 2].record()
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(loss_ready[k % 2])
-            loss_pinned[k % 2].copy_(loss, non_blocking=True)
-            loss.record_stream(d2h_stream)
-            loss_events[k % 2].record(d2h_stream)
-        if k > 0:
-            loss_events[(k - 1) % 2].synchronize()
-            e2e_state["last"] = float(loss_pinned[(k - 1) % 2])
         slot_free[k % 2].record()
+        loss = torch.dot(color.detach().view(-1), cot[0:3].reshape(-1))
+        loss_ready[k % (LAG + 1)].record()
+        e2e_state["pending"] = (k, loss)
+        if k >= LAG:
+            read_back(k - LAG)
         e2e_state["k"] = k + 1
 
     def e2e_flush():
         k = e2e_state["k"]
-        if k > 0:
-            loss_events[(k - 1) % 2].synchronize()
-            e2e_state["last"] = float(loss_pinned[(k - 1) % 2])
-
-    e2e_state = {"k": 0, "last": None}
-    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_events = [torch.cuda.Event() for _ in range(2)]
-    loss_ready = [torch.cuda.Event() for _ in range(2)]
-    d2h_stream = torch.cuda.Stream(device=dev)
+        side_stream_work(None)
+        for j in range(max(0, k - LAG), k):
+            read_back(j)
 
     def timed(fn, n, flush=None):
         sync_all()
@@ -281,9 +308,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), wall
 
-    # untimed: let the caching allocator reach its steady state, then the W warm-up steps proper
-    for _ in range(20):
-        resident_step()
+    # untimed: let the caching allocator reach its steady state and the GPU leave its idle clocks (a fresh box needs
+    # about a second of load before the SM clock settles: the first 0.4 s of work measured 25 % slow), then the W warm-up
+    # steps proper
+    t_spin = time.perf_counter()
+    while True:
+        for _ in range(20):
+            resident_step()
+        torch.cuda.synchronize()
+        if time.perf_counter() - t_spin > args.spinup_seconds:
+            break
     for _ in range(Wm):
         resident_step()
         e2e_step()
@@ -373,7 +407,7 @@ def main():
 
     views_per_s = world * K / (ms_res * 1e-3)
     e2e_views_per_s = world * K / (ms_e2e * 1e-3)
-    h2d = cot_host.numel() * 4 + cam_host.numel() * 4
+    h2d = in_host.numel() * 4
     ws_mb = (P * 236 + P * 248 + R * (12 * 2 + 48 + 12) + HWp * 48) / 1e6
     line = {
         "metric": "3DGS train-step views/sec (rasterizer fwd+bwd)", "value": round(views_per_s, 2), "unit": "views/s",

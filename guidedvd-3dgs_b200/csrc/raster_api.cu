@@ -259,7 +259,9 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     {
         // level 2a: per-chunk tile histograms -> per-tile prefixes -> ranges and R
         StageScope t(GVD_STAGE_SCAN, stream);
-        GVD_CHECK(gvd_launch_bin_count(P, g, im, grid, stream), "bin_count");
+        const bool spec = a->spec_binning_buffer != nullptr && !debug;
+        if (spec && !a->num_rendered_pinned) return fail_msg("gvd_raster_forward: speculative path needs num_rendered_pinned");
+        GVD_CHECK(gvd_launch_bin_count(P, g, im, grid, spec ? a->num_rendered_pinned : nullptr, stream), "bin_count");
     }
     GVD_STAGE("bin_count");
 
@@ -268,9 +270,7 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     bool have_instances = true;
     if (a->spec_binning_buffer != nullptr && !debug) {
         // speculative path: no host round trip; the caller validates R afterwards
-        if (!a->num_rendered_pinned) return fail_msg("gvd_raster_forward: speculative path needs num_rendered_pinned");
-        GVD_CHECK(cudaMemcpyAsync(a->num_rendered_pinned, g.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, stream),
-                  "copy num_rendered (async)");
+        // R was written into *num_rendered_pinned by the last binning kernel (no copy-engine work in this stream)
         if (a->r_ready_event) GVD_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->r_ready_event), stream), "record R event");
         a->num_rendered = -1;
         // largest R whose layout fits the caller's buffer
@@ -343,7 +343,8 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
 
     float* acc = reinterpret_cast<float*>(((uintptr_t)a->scratch + 127) & ~(uintptr_t)127);
-    GVD_CHECK(cudaMemsetAsync(acc, 0, (size_t)P * GVD_ACC_STRIDE * sizeof(float), stream), "memset acc");
+    gvd_launch_zero_fill(acc, (size_t)P * GVD_ACC_STRIDE, stream);
+    GVD_STAGE("zero accumulator");
 
     if (a->R > 0) {
         {

@@ -647,6 +647,20 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
 
 }  // namespace
 
+// Zero-fill of the backward accumulator as a kernel: cudaMemsetAsync may be served by a copy engine and then queues
+// behind any host<->device transfer in flight on another stream.
+__global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, size_t n4) {
+    pdl_wait();
+    pdl_trigger();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+void gvd_launch_zero_fill(float* p, size_t floats, cudaStream_t s) {
+    const size_t n4 = floats / 4;  // GVD_ACC_STRIDE is a multiple of 4 floats and the buffer is 128-byte aligned
+    const unsigned blocks = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    if (blocks) gvd_launch(zero_fill_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<float4*>(p), n4);
+}
+
 template <int SPLIT>
 static void launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                    const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {

@@ -69,7 +69,8 @@ struct GvdRasterBackwardArgs;
 
 void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, float focal_x, float focal_y,
                            dim3 grid, cudaStream_t s);
-cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, cudaStream_t s);
+cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, int* r_host,
+                                 cudaStream_t s);
 cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
                                 dim3 grid, uint32_t capacity, cudaStream_t s);
 void gvd_launch_export_keys(uint32_t capacity, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
@@ -78,6 +79,7 @@ void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPt
                                const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s);
 void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                 const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s);
+void gvd_launch_zero_fill(float* p, size_t floats, cudaStream_t s);
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
                                   float focal_x, float focal_y, cudaStream_t s);
 void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,

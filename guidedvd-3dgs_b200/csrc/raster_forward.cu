@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int chunks, con
 // Pass 3: exclusive scan over the tiles -> ranges (rasterizer_impl.cu:116-138 semantics: empty tiles (0,0))
 // and R. One CTA; T <= GVD_MAX_TILES.
 __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t* __restrict__ tile_total,
-                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ num_rendered) {
+                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ num_rendered,
+                                                          int* r_host) {
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t warp_sums[32];
@@ -365,7 +366,16 @@ __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t*
         if (tid == 1023) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
-    if (tid == 0) *num_rendered = carry_s;
+    if (tid == 0) {
+        *num_rendered = carry_s;
+        // speculative path: R goes straight into the caller's pinned (device-mapped) host word. A cudaMemcpyAsync in
+        // the compute stream queues behind whatever the copy engines are busy with -- measured +46 us per step while
+        // a 6 MB host-to-device upload of the next step's inputs was in flight.
+        if (r_host != nullptr) {
+            *reinterpret_cast<volatile int*>(r_host) = (int)carry_s;
+            __threadfence_system();
+        }
+    }
 }
 
 // Pass 4: chunk c writes its Gaussians' ids into the tile lists in depth order: the slot of Gaussian g in tile t is
@@ -685,7 +695,8 @@ static cudaError_t ensure_smem(const void* fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, cudaStream_t s) {
+cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, int* r_host,
+                                 cudaStream_t s) {
     const int T = (int)(grid.x * grid.y);
     const size_t smem = (size_t)(grid.y + 1) * ((grid.x + 1) | 1) * sizeof(int);
     cudaError_t e = ensure_smem((const void*)bin_count_kernel, smem);
@@ -693,7 +704,7 @@ cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImg
     gvd_launch(bin_count_kernel, dim3((unsigned)g.chunks), dim3(GVD_BIN_CHUNK), smem, s, P, grid.x, grid.y, g.splat, g.order,
                                                                     g.tiles_touched, g.chunk_flags, g.hist);
     gvd_launch(bin_prefix_kernel, dim3((T + 31) / 32), dim3(1024), 0, s, T, (int)g.chunks, g.chunk_flags, g.hist, g.tile_total);
-    gvd_launch(bin_ranges_kernel, dim3(1), dim3(1024), 0, s, T, g.tile_total, im.ranges, g.num_rendered);
+    gvd_launch(bin_ranges_kernel, dim3(1), dim3(1024), 0, s, T, g.tile_total, im.ranges, g.num_rendered, r_host);
     return cudaGetLastError();
 }
 

@@ -83,8 +83,9 @@ typedef struct GvdRasterForwardArgs {
     void* img_buffer;
     size_t img_bytes;
     /* Optional speculative instance buffer (no host round trip).  When spec_binning_buffer != NULL the library does NOT
-     * synchronise to learn R: it copies R asynchronously to *num_rendered_pinned (pinned host memory), records
-     * r_ready_event (a cudaEvent_t) right after that copy, and queues the remaining stages against the caller's buffer
+     * synchronise to learn R: the binning kernel stores R directly into *num_rendered_pinned (pinned host memory that is
+     * mapped into the device address space, as cudaHostAlloc memory is under unified addressing), the library records
+     * r_ready_event (a cudaEvent_t) right behind that kernel, and queues the remaining stages against the caller's buffer
      * of spec_binning_bytes bytes (writes and reads are clamped to it).  The caller waits on the event, reads R, and if
      * gvd_raster_binning_bytes(R, export_keys) > spec_binning_bytes the outputs are invalid and the call must be
      * repeated with a larger buffer (or with spec_binning_buffer = NULL, the synchronous path of the reference,
