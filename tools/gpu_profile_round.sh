@@ -7,6 +7,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
     python bench.py --steps 5 --warmup 3 --no-denoise --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'render_(forward|backward)_kernel' --launch-skip 20 -c 2 \
     -o gpurun_out/render_full -f python bench.py --steps 5 --warmup 3 --no-denoise --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
+    --clock-control none -k regex:flash_attn -c 3 --csv --log-file gpurun_out/ncu_flash.csv python tools/bench_attn.py > gpurun_out/ncu_flash.log 2>&1
+timeout 120 python tools/bench_attn.py > gpurun_out/bench_attn.log 2>&1
+timeout 300 python tools/profile_unet.py 25 72 128 ours > gpurun_out/unet_profile.txt 2>&1
 python -c "
 import json
 for f in ('bench_reference','bench_ours'):
