@@ -373,12 +373,12 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         ach = alg[top] / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # workload (profiles/r01_ncu_full_d_render.csv); far below the algorithmic bytes because a tile stops after a few
+        # workload (profiles/r01_ncu_full_e_render.csv); far below the algorithmic bytes because a tile stops after a few
         # per cent of its list and the per-Gaussian records stay in L2
-        ncu_traffic = {"C2": {"render_bwd": 9.69e6, "render_fwd": 4.11e6}}.get(args.workload, {})
+        ncu_traffic = {"C2": {"render_bwd": 9.69e6, "render_fwd": 2.76e6}}.get(args.workload, {})
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": ncu_traffic.get(top),
-                    "traffic_source": "profiles/r01_ncu_full_d_render.csv (ncu --set full, one launch)" if top in ncu_traffic else None,
+                    "traffic_source": "profiles/r01_ncu_full_e_render.csv (ncu --set full, one launch)" if top in ncu_traffic else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes": alg[top],
                     "note": "render kernels are fp32-ALU/SFU/atomic bound, not HBM bound (SURVEY.md 0.5); see DESIGN.md",
@@ -421,10 +421,10 @@ def main():
                                    if args.impl == "ours" else "NCCL all-reduce")) if world > 1 else "")},
         "e2e": {"value": round(e2e_views_per_s, 2), "unit": "views/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4), "wall_ms_per_step": round(wall_e2e / K * 1e3, 4)},
-        "gpu_launches": ((8 + (1 if world > 1 else 0)) * K * 2) if args.impl == "ours" else 0,
+        "gpu_launches": ((9 + (1 if world > 1 else 0)) * K * 2) if args.impl == "ours" else 0,
         "gpu_launches_note": "own kernels in the two timed regions: preprocess, bin_count, bin_prefix, bin_ranges, bin_fill, "
-                             "render_fwd, render_bwd, gaussian_bwd per step, + grad_allreduce_kernel at N > 1 (+ CUB radix-sort "
-                             "library kernels for the depth sort, not counted)",
+                             "render_fwd, zero_fill, render_bwd, gaussian_bwd per step, + grad_allreduce_kernel at N > 1 (+ CUB "
+                             "radix-sort library kernels for the depth sort and the cuBLAS dot of the e2e result, not counted)",
         "clocks": clocks,
     }
     if roofline:
