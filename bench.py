@@ -310,14 +310,18 @@ def main():
 
     # untimed: let the caching allocator reach its steady state and the GPU leave its idle clocks (a fresh box needs
     # about a second of load before the SM clock settles: the first 0.4 s of work measured 25 % slow), then the W warm-up
-    # steps proper
+    # steps proper. The spin-up is time-based, so the number of iterations differs from rank to rank: it runs the LOCAL
+    # step only -- no collective may sit inside a loop whose trip count is not the same on every rank.
     t_spin = time.perf_counter()
     while True:
         for _ in range(20):
-            resident_step()
+            step(cot_dev, cam["viewmatrix"], cam["projmatrix"], cam["campos"])
         torch.cuda.synchronize()
         if time.perf_counter() - t_spin > args.spinup_seconds:
             break
+    sync_all()
+    for _ in range(5):
+        resident_step()
     for _ in range(Wm):
         resident_step()
         e2e_step()
