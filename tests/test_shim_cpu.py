@@ -1,0 +1,92 @@
+"""CPU: host-side logic of the ctypes shim (diff_gaussian_rasterization/_C.py) that needs no GPU -- the layout of the
+flat gradient buffer, the deferred-R bookkeeping of the speculative instance buffer, and the argument contract of
+GaussianRasterizer (DGR/diff_gaussian_rasterization/__init__.py:192-212)."""
+import pytest
+import torch
+
+
+def _C():
+    import diff_gaussian_rasterization as dgr
+
+    return dgr._C
+
+
+@pytest.mark.parametrize("P,M,flags", [(1000, 16, (True, True, False, False)), (37, 16, (False, False, True, True)),
+                                       (5, 4, (True, True, True, True)), (1, 16, (True, False, False, True))])
+def test_gradient_views_layout(P, M, flags):
+    """Eight gradients = disjoint, 16-byte aligned slices of one flat buffer, in the documented order; the size helper
+    covers the largest case."""
+    c = _C()
+    has_sh, has_scales, has_colors, has_cov = flags
+    widths = (3, 3 * M if has_sh else 0, 1, 3 if has_scales else 0, 4 if has_scales else 0, 3 if has_colors else 0,
+              6 if has_cov else 0, 3)
+    total = sum((P * w + 3) // 4 * 4 for w in widths)
+    assert total <= c.gradient_buffer_floats(P, M)
+    flat = torch.arange(total, dtype=torch.float32)
+    m2, m3, op, col, cov, sh, sc, rot = c._grad_views(flat, P, M, has_sh, has_scales, has_colors, has_cov)
+    assert m2.shape == (P, 3) and m3.shape == (P, 3) and op.shape == (P, 1)
+    assert (sh is not None) == has_sh and (sc is not None) == has_scales == (rot is not None)
+    assert (col is not None) == has_colors and (cov is not None) == has_cov
+    seen = torch.zeros(total, dtype=torch.int32)
+    for v in (m2, m3, op, col, cov, sh, sc, rot):
+        if v is None:
+            continue
+        assert v._base is flat and v.is_contiguous()
+        assert (v.storage_offset() * 4) % 16 == 0
+        seen[v.storage_offset():v.storage_offset() + v.numel()] += 1
+    assert int(seen.max()) == 1  # disjoint
+    # order inside the buffer: means3D first, means2D last (view_parallel sums [0, total) in one go)
+    assert m3.storage_offset() == 0 and m2.storage_offset() + m2.numel() <= total
+    if has_sh:
+        assert sh.shape == (P, M, 3) and float(sh.reshape(-1)[0]) == float(sh.storage_offset())
+
+
+class _FakeEvent:
+    def __init__(self):
+        self.syncs = 0
+
+    def synchronize(self):
+        self.syncs += 1
+
+
+def test_pending_r_validation_and_bookkeeping():
+    """PendingR: resolves once, returns its slot, grows the history, raises (every time) when the frame outgrew the buffer."""
+    c = _C()
+    st = {"max_R": 100, "free": []}
+    slot = {"event": _FakeEvent(), "host": [1234]}
+    p = c.PendingR(slot, c._capacity(100), st)
+    assert int(p) == 1234 and int(p) == 1234 and slot["event"].syncs == 1
+    assert st["free"] == [slot] and st["max_R"] == 1234
+
+    st = {"max_R": 10, "free": []}
+    slot = {"event": _FakeEvent(), "host": [5000]}
+    p = c.PendingR(slot, 4096, st)
+    for _ in range(2):
+        with pytest.raises(RuntimeError, match="speculative instance buffer"):
+            p.resolve()
+    assert st["max_R"] == 5000 and st["free"] == [slot]  # the history grew: the retry will fit
+    assert c._capacity(5000) >= 2 * 5000
+
+
+def test_rasterizer_argument_contract():
+    """Exactly one colour source and exactly one covariance source, with the reference's messages (raised before any
+    native call, so this runs without a GPU)."""
+    import diff_gaussian_rasterization as dgr
+
+    rs = dgr.GaussianRasterizationSettings(
+        image_height=8, image_width=8, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3), scale_modifier=1.0,
+        viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3), prefiltered=False,
+        debug=False, confidence=torch.ones(4, 1))
+    assert rs._fields[-1] == "confidence" and len(rs._fields) == 13
+    r = dgr.GaussianRasterizer(rs)
+    x = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), scales=x, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), colors_precomp=x, scales=x,
+          rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), colors_precomp=x, scales=x)
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), colors_precomp=x, scales=x, rotations=torch.zeros(4, 4),
+          cov3D_precomp=torch.zeros(4, 6))
