@@ -57,7 +57,7 @@ def _worker(rank, world, port, q, cfg_split):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,cfg_split,expect", [(2, True, (2, 1)), (2, False, (1, 2)), (3, True, (1, 3)), (4, True, (2, 2))])
+@pytest.mark.parametrize("world,cfg_split,expect", [(2, True, (2, 1)), (2, False, (1, 2)), (3, True, (1, 3)), (4, True, (2, 2)), (8, True, (2, 4))])
 def test_frame_partition_gloo(world, cfg_split, expect):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
