@@ -1,6 +1,6 @@
 // raster_backward.cu -- backward kernels of the B200-native Gaussian rasterizer (sm_100a).
 //
-//   render_backward_kernel   per tile, back-to-front replay (DGR/cuda_rasterizer/backward.cu:415-601).
+//   render_backward_kernel   SPLIT CTAs per tile (default 2), back-to-front replay (DGR/cuda_rasterizer/backward.cu:415-601).
 //                            Same staging as the forward (ids by TMA bulk copy, records gathered from the
 //                            L2-resident per-Gaussian array one batch ahead, sub-tile culling). The ten
 //                            per-(pixel,Gaussian) partial gradients are summed across the warp with a

@@ -9,9 +9,10 @@
 //                         run over the depth-sorted Gaussians; produces point_list + ranges exactly as the
 //                         reference's duplicateWithKeys + 64-bit radix sort + identifyTileRanges
 //                         (rasterizer_impl.cu:70-138,304-319) without materialising keys
-//   render_forward_kernel per tile: ids staged by TMA bulk copy (cp.async.bulk + mbarrier), records gathered
-//                         from the L2-resident per-Gaussian array one batch ahead; each warp owns an 8x4
-//                         pixel sub-tile and visits only the instances that can touch it
+//   render_forward_kernel SPLIT CTAs per 16x16 tile (default 2: 16x8 pixels, 4 warps each): ids staged by TMA bulk
+//                         copy (cp.async.bulk + mbarrier), records gathered from the L2-resident per-Gaussian
+//                         array one batch ahead; each warp owns an 8x4 pixel sub-tile and visits only the
+//                         instances that can touch it
 //                         (forward.cu:261-381 semantics preserved: skipped instances are exactly those every
 //                         pixel of the warp would `continue` on).
 #include <cstdio>
