@@ -1,6 +1,6 @@
 """CPU: host-side logic of the ctypes shim (diff_gaussian_rasterization/_C.py) that needs no GPU -- the layout of the
-flat gradient buffer, the deferred-R bookkeeping of the speculative instance buffer, and the argument contract of
-GaussianRasterizer (DGR/diff_gaussian_rasterization/__init__.py:192-212)."""
+flat gradient buffer and the deferred-R bookkeeping of the speculative instance buffer (the argument contract of
+GaussianRasterizer is covered by test_abi_cpu.py::test_shim_argument_contract)."""
 import pytest
 import torch
 
@@ -66,27 +66,3 @@ def test_pending_r_validation_and_bookkeeping():
             p.resolve()
     assert st["max_R"] == 5000 and st["free"] == [slot]  # the history grew: the retry will fit
     assert c._capacity(5000) >= 2 * 5000
-
-
-def test_rasterizer_argument_contract():
-    """Exactly one colour source and exactly one covariance source, with the reference's messages (raised before any
-    native call, so this runs without a GPU)."""
-    import diff_gaussian_rasterization as dgr
-
-    rs = dgr.GaussianRasterizationSettings(
-        image_height=8, image_width=8, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3), scale_modifier=1.0,
-        viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3), prefiltered=False,
-        debug=False, confidence=torch.ones(4, 1))
-    assert rs._fields[-1] == "confidence" and len(rs._fields) == 13
-    r = dgr.GaussianRasterizer(rs)
-    x = torch.zeros(4, 3)
-    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
-        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), scales=x, rotations=torch.zeros(4, 4))
-    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
-        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), colors_precomp=x, scales=x,
-          rotations=torch.zeros(4, 4))
-    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
-        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), colors_precomp=x, scales=x)
-    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
-        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), colors_precomp=x, scales=x, rotations=torch.zeros(4, 4),
-          cov3D_precomp=torch.zeros(4, 6))
