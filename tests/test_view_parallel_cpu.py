@@ -37,6 +37,41 @@ def _worker(rank, world, port, q):
     vp.allreduce_gradients(grads)
     expect = [sum(torch.randn(P, 3, generator=torch.Generator().manual_seed(10 * v + k)) for v in range(5)) for k in range(3)]
     ok = all(torch.allclose(a, b, atol=1e-5) for a, b in zip(grads, expect))
+
+    # the three collective shapes of allreduce_gradients: (a) views of one flat buffer -> a single all-reduce on it,
+    # (b) the exchange path -- sum the caller-owned buffer, then point every leaf.grad at its slice (a CPU stand-in for
+    # GradientExchange keeps the host logic testable without GPUs), (c) averaging
+    import diff_gaussian_rasterization as dgr
+
+    Pg, M = 37, 16
+    flat = torch.full((dgr.gradient_buffer_floats(Pg, M),), float(rank + 1))
+    v = dgr._C._grad_views(flat[:sum((Pg * w + 3) // 4 * 4 for w in (3, 48, 1, 3, 4, 0, 0, 3))], Pg, M, True, True, False, False)
+    vp.allreduce_gradients([t for t in v if t is not None])
+    ok &= bool((v[1] == 3.0).all() and (v[5] == 3.0).all() and (v[0] == 3.0).all())  # 1 + 2 on both ranks
+
+    class FakeExchange:
+        def __init__(self, n):
+            self.buffer, self.world, self.calls = torch.full((n,), float(rank + 1)), world, []
+
+        def allreduce(self, n):
+            self.calls.append(n)
+            dist.all_reduce(self.buffer[:n])
+
+    ex = FakeExchange(dgr.gradient_buffer_floats(Pg, M))
+    total = sum((Pg * w + 3) // 4 * 4 for w in (3, 48, 1, 3, 4, 0, 0, 3))
+    m2, m3, op, col, cov, sh, sc, rot = dgr._C._grad_views(ex.buffer[:total], Pg, M, True, True, False, False)
+    views_named = {"means2D": m2, "means3D": m3, "opacities": op, "colors_precomp": col, "cov3D_precomp": cov, "shs": sh,
+                   "scales": sc, "rotations": rot, "_floats": total}
+    leaves = {"means3D": torch.zeros(Pg, 3, requires_grad=True), "shs": torch.zeros(Pg, M, 3, requires_grad=True),
+              "opacities": torch.zeros(Pg, 1, requires_grad=True), "scales": torch.zeros(Pg, 3, requires_grad=True),
+              "rotations": torch.zeros(Pg, 4, requires_grad=True), "means2D": torch.zeros(Pg, 3, requires_grad=True)}
+    for leaf in leaves.values():
+        leaf.grad = torch.full_like(leaf, -7.0)  # what autograd's copy would have left there
+    vp.allreduce_gradients(None, exchange=ex, leaves=leaves, views=views_named, average=True)
+    ok &= ex.calls == [total]
+    for name, leaf in leaves.items():
+        ok &= leaf.grad.shape == leaf.shape and bool((leaf.grad == 1.5).all())                # (1 + 2) / 2
+        ok &= leaf.grad.untyped_storage().data_ptr() == ex.buffer.untyped_storage().data_ptr()  # a slice of the buffer
     q.put((rank, ok, views))
     dist.destroy_process_group()
 
