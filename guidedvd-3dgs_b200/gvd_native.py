@@ -184,9 +184,23 @@ class DdimArgs(C.Structure):
     ]
 
 
+class DdimVjpArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_longlong), ("e_cond", C.c_void_p), ("e_uncond", C.c_void_p), ("grad_pred_x0", C.c_void_p),
+        ("dx", C.c_void_p), ("de_cond", C.c_void_p), ("de_uncond", C.c_void_p), ("scratch", C.c_void_p),
+        ("scratch_bytes", C.c_size_t),
+        ("cfg_scale", C.c_float), ("guidance_rescale", C.c_float),
+        ("sqrt_alphas_cumprod_t", C.c_float), ("sqrt_one_minus_alphas_cumprod_t", C.c_float),
+        ("scale_t", C.c_float), ("scale_prev", C.c_float), ("use_dynamic_rescale", C.c_int),
+    ]
+
+
 NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", "gvd_groupnorm_cl", "gvd_layernorm",
               "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention",
-              "gvd_ddim_step", "gvd_flash_attention", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply")
+              "gvd_ddim_step", "gvd_flash_attention", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply",
+              # input-gradient operators of the guided sampler (csrc/nn_backward.cu)
+              "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
+              "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp")
 _nn = None
 
 
@@ -217,6 +231,19 @@ def nn():
     lib.gvd_ddim_step.argtypes = [C.POINTER(DdimArgs), vp]
     lib.gvd_flash_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]
     lib.gvd_flash_attention.restype = C.c_int
+    lib.gvd_groupnorm_bwd_tmp_bytes.restype = C.c_size_t
+    lib.gvd_groupnorm_bwd_tmp_bytes.argtypes = [i32, ll, i32]
+    lib.gvd_groupnorm_cl_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    lib.gvd_layernorm_bwd.argtypes = [vp, vp, vp, vp, ll, i32, f32, vp]
+    lib.gvd_geglu_bwd.argtypes = [vp, vp, vp, ll, i32, vp]
+    lib.gvd_softmax_bwd_rows.argtypes = [vp, vp, vp, ll, ll, i32, vp]
+    lib.gvd_col2im3x3_cl.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.gvd_col2im_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
+    lib.gvd_temporal_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
+    lib.gvd_ddim_pred_x0_vjp.argtypes = [C.POINTER(DdimVjpArgs), vp]
+    for n in ("gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows", "gvd_col2im3x3_cl",
+              "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp"):
+        getattr(lib, n).restype = C.c_int
     for n in ("gvd_groupnorm_cl", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply", "gvd_layernorm", "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl",
               "gvd_temporal_attention", "gvd_ddim_step"):
         getattr(lib, n).restype = C.c_int

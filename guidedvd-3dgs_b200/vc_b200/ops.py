@@ -22,6 +22,18 @@ ACT = {"none": 0, "silu": 1, "gelu": 2, "round_scale": 3}
 BF16 = torch.bfloat16
 
 
+def _wants_grad(*tensors):
+    """True when a call must be recorded for the guided sampler's backward (vc_b200.grad): autograd is on and one of
+    the activations carries a graph.  Parameters never require grad here, and every U-Net call of the plain sampler
+    runs under torch.no_grad(), so the inference path never takes this branch."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _grad():
+    from . import grad
+    return grad
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -51,8 +63,11 @@ def gemm_raw(A, B, Cout, M, N, K, lda, ldb, ldc, batch_h=1, batch_b=1, a_strides
     return Cout
 
 
-def linear(x, weight, bias=None, act="none", residual=None, out_dtype=BF16, alpha=1.0, bias2=None):
+def linear(x, weight, bias=None, act="none", residual=None, out_dtype=None, alpha=1.0, bias2=None):
     """y = act(x @ weight^T + bias) (+ bias2) + residual.  x [..., K] bf16, weight [N, K] bf16, biases fp32 [N]."""
+    if _wants_grad(x, residual):
+        return _grad().Linear.apply(x, weight, bias, act, residual, out_dtype, alpha, bias2)
+    out_dtype = out_dtype or BF16
     K = x.shape[-1]
     N = weight.shape[0]
     x2 = x.reshape(-1, K)
@@ -70,6 +85,8 @@ _gn_tmp = {}
 
 def groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
     """x viewed as [F, S, C] channels-last bf16; statistics over S x (C/groups)."""
+    if _wants_grad(x):
+        return _grad().GroupNorm.apply(x, gamma, beta, F, S, groups, eps, int(silu))
     lib = _n.nn()
     Cc = x.shape[-1]
     x = x.contiguous()
@@ -87,6 +104,8 @@ def groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
 def groupnorm_sharded(x, gamma, beta, F, S_local, S_total, part, groups=32, eps=1e-5, silu=False):
     """GroupNorm whose rows are spread over the ranks of `part` (vc_b200.frame_parallel.FramePartition): local
     (sum, sumsq) -> one all-reduce of F*groups*2 floats -> local normalisation with the global statistics."""
+    if _wants_grad(x):
+        raise RuntimeError("groupnorm_sharded: the frame-sharded plan is inference-only (no backward)")
     lib = _n.nn()
     Cc = x.shape[-1]
     x = x.contiguous()
@@ -107,6 +126,8 @@ def groupnorm_sharded(x, gamma, beta, F, S_local, S_total, part, groups=32, eps=
 
 
 def layernorm(x, gamma, beta, eps=1e-5):
+    if _wants_grad(x):
+        return _grad().LayerNorm.apply(x, gamma, beta, eps)
     lib = _n.nn()
     x = x.contiguous()
     y = torch.empty_like(x)
@@ -117,6 +138,8 @@ def layernorm(x, gamma, beta, eps=1e-5):
 
 
 def geglu(h):
+    if _wants_grad(h):
+        return _grad().Geglu.apply(h)
     lib = _n.nn()
     D = h.shape[-1] // 2
     h = h.contiguous()
@@ -137,10 +160,12 @@ def softmax_rows(scores, cols, ldy):
 
 def conv3x3(x, F, H, W, weight, bias=None, stride=1, upsample=False, bias2=None, residual=None, act="none"):
     """3x3 / pad 1 convolution of channels-last x[F, H*W, Cin] with weight [Cout, 9*Cin] (K order ky, kx, cin)."""
-    lib = _n.nn()
     Cin = x.shape[-1]
     Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
     Ho, Wo = (Hin + 2 - 3) // stride + 1, (Win + 2 - 3) // stride + 1
+    if _wants_grad(x, residual):
+        return _grad().Conv3x3.apply(x, F, H, W, weight, bias, stride, bool(upsample), bias2, residual, act), Ho, Wo
+    lib = _n.nn()
     col = torch.empty(F * Ho * Wo, 9 * Cin, dtype=BF16, device=x.device)
     _check(lib.gvd_im2col3x3_cl(x.data_ptr(), col.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),
                                 _stream()), lib, "gvd_im2col3x3_cl")
@@ -150,6 +175,8 @@ def conv3x3(x, F, H, W, weight, bias=None, stride=1, upsample=False, bias2=None,
 
 def conv_t3(x, B, T, S, weight, bias=None, residual=None):
     """(3,1,1) / pad (1,0,0) temporal convolution of x[B*T, S, C] with weight [Cout, 3*Cin] (K order kt, cin)."""
+    if _wants_grad(x, residual):
+        return _grad().ConvT3.apply(x, B, T, S, weight, bias, residual)
     lib = _n.nn()
     Cin = x.shape[-1]
     col = torch.empty(B * T * S, 3 * Cin, dtype=BF16, device=x.device)
@@ -159,6 +186,8 @@ def conv_t3(x, B, T, S, weight, bias=None, residual=None):
 
 
 def temporal_attention(q, k, v, B, T, S, H, scale):
+    if _wants_grad(q, k, v):
+        return _grad().TemporalAttention.apply(q, k, v, B, T, S, H, scale)
     lib = _n.nn()
     out = torch.empty_like(q)
     _check(lib.gvd_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), int(B), int(T), int(S), int(H),
@@ -168,6 +197,8 @@ def temporal_attention(q, k, v, B, T, S, H, scale):
 
 def flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False):
     """Fused softmax(q k^T * scale) v (gvd_flash_attention). Same arguments/layouts as `attention` below."""
+    if _wants_grad(q, k, v):
+        return _grad().FlashAttention.apply(q, k, v, Bq, Nq, Nk, H, scale, bool(shared_kv))
     lib = _n.nn()
     HD = H * 64
     out = torch.empty(Bq, Nq, HD, dtype=BF16, device=q.device)
@@ -239,3 +270,227 @@ def ddim_step(x, e_cond, e_uncond, noise, coef):
     with torch.cuda.device(x.device):
         _check(lib.gvd_ddim_step(C.byref(a), _stream()), lib, "gvd_ddim_step")
     return x_prev, pred_x0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Input-gradient operators (include/gvd_nn.h, csrc/nn_backward.cu): the adjoints vc_b200.grad strings together for the
+# guided sampler (lvdm/models/samplers/ddim_guidance.py:259-337).  Parameters are frozen, only activations get gradients.
+# ---------------------------------------------------------------------------------------------------------------------
+_wt_cache = {}
+
+
+def _transposed(weight):
+    """weight [N, K] -> cached [K, Np] copy (Np = N rounded up to 8, zero padded): the B operand of dX = dY @ W."""
+    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
+    wt = _wt_cache.get(key)
+    if wt is None:
+        N, K = weight.shape
+        Np = (N + 7) // 8 * 8
+        wt = torch.zeros(K, Np, dtype=weight.dtype, device=weight.device)
+        wt[:, :N] = weight.t()
+        _wt_cache[key] = wt
+    return wt
+
+
+def linear_dx(dy, weight, alpha=1.0):
+    """dX = alpha * dY @ W for y = alpha * x @ W^T: dy [..., N], weight [N, K] -> [..., K] (one tensor-core GEMM against
+    the cached transposed weight)."""
+    N, K = weight.shape
+    wt = _transposed(weight)
+    Np = wt.shape[1]
+    d2 = dy.reshape(-1, N)
+    if Np != N:
+        d2 = torch.nn.functional.pad(d2, (0, Np - N))
+    elif not d2.is_contiguous():
+        d2 = d2.contiguous()
+    M = d2.shape[0]
+    out = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
+    gemm_raw(d2, wt, out, M, K, Np, Np, Np, K, alpha=alpha)
+    return out.reshape(*dy.shape[:-1], K)
+
+
+_gn_bwd_tmp = {}
+
+
+def groupnorm_bwd(x, dy, gamma, beta, F, S, groups=32, eps=1e-5, silu=0):
+    """dx of `groupnorm` (same arguments); statistics are recomputed from x."""
+    lib = _n.nn()
+    Cc = x.shape[-1]
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    nfl = int(lib.gvd_groupnorm_tmp_floats(int(F), int(S), int(groups)))
+    nby = int(lib.gvd_groupnorm_bwd_tmp_bytes(int(F), int(S), int(groups)))
+    key = (x.device, nfl, nby)
+    tmp = _gn_bwd_tmp.get(key)
+    if tmp is None:
+        tmp = _gn_bwd_tmp[key] = (torch.empty(nfl, dtype=torch.float32, device=x.device),
+                                  torch.empty(nby // 8 + 1, dtype=torch.float64, device=x.device))
+    stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
+    _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S), int(Cc), int(groups), tmp[0].data_ptr(), nfl,
+                                      _stream()), lib, "gvd_groupnorm_cl_stats")
+    _check(lib.gvd_groupnorm_cl_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                    int(F), int(S), int(Cc), int(groups), float(eps), int(silu), tmp[1].data_ptr(), nby, _stream()),
+           lib, "gvd_groupnorm_cl_bwd")
+    return dx
+
+
+def layernorm_bwd(x, dy, gamma, eps=1e-5):
+    lib = _n.nn()
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    Cc = x.shape[-1]
+    _check(lib.gvd_layernorm_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), x.numel() // Cc, int(Cc), float(eps),
+                                 _stream()), lib, "gvd_layernorm_bwd")
+    return dx
+
+
+def geglu_bwd(h, dout):
+    lib = _n.nn()
+    D = h.shape[-1] // 2
+    h, dout = h.contiguous(), dout.contiguous()
+    dh = torch.empty_like(h)
+    _check(lib.gvd_geglu_bwd(h.data_ptr(), dout.data_ptr(), dh.data_ptr(), h.numel() // (2 * D), int(D), _stream()), lib,
+           "gvd_geglu_bwd")
+    return dh
+
+
+def softmax_bwd_rows(p, dp, cols):
+    """ds = p o (dp - rowsum(p o dp)) over the first `cols` columns, written over dp (padding columns zeroed)."""
+    lib = _n.nn()
+    ld = p.shape[-1]
+    _check(lib.gvd_softmax_bwd_rows(p.data_ptr(), dp.data_ptr(), dp.data_ptr(), int(ld), p.numel() // ld, int(cols), _stream()), lib,
+           "gvd_softmax_bwd_rows")
+    return dp
+
+
+def conv3x3_dx(dy, F, H, W, Cin, weight, stride=1, upsample=False):
+    """dX of `conv3x3`: dcol = dY @ W (tensor-core GEMM), then the col2im gather.  dy [F, Ho*Wo, Cout] -> [F, H*W, Cin]."""
+    lib = _n.nn()
+    dcol = linear_dx(dy.reshape(-1, dy.shape[-1]), weight)  # [F*Ho*Wo, 9*Cin]
+    dx = torch.empty(F, H * W, Cin, dtype=dy.dtype, device=dy.device)
+    _check(lib.gvd_col2im3x3_cl(dcol.data_ptr(), dx.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),
+                                _stream()), lib, "gvd_col2im3x3_cl")
+    return dx
+
+
+def conv_t3_dx(dy, B, T, S, Cin, weight):
+    lib = _n.nn()
+    dcol = linear_dx(dy.reshape(-1, dy.shape[-1]), weight)  # [B*T*S, 3*Cin]
+    dx = torch.empty(B * T, S, Cin, dtype=dy.dtype, device=dy.device)
+    _check(lib.gvd_col2im_t3_cl(dcol.data_ptr(), dx.data_ptr(), int(B), int(T), int(S), int(Cin), _stream()), lib,
+           "gvd_col2im_t3_cl")
+    return dx
+
+
+def temporal_attention_bwd(q, k, v, dout, B, T, S, H, scale):
+    lib = _n.nn()
+    q, k, v, dout = q.contiguous(), k.contiguous(), v.contiguous(), dout.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    _check(lib.gvd_temporal_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                          dv.data_ptr(), int(B), int(T), int(S), int(H), float(scale), _stream()), lib,
+           "gvd_temporal_attention_bwd")
+    return dq, dk, dv
+
+
+def _heads_t(x, nb, N, H, Np):
+    """x [nb, N, H*64] -> [nb, H, 64, Np] (token axis last, zero padded to Np): the K-major B operand of a product that
+    contracts over tokens."""
+    D = 64
+    if Np == N:
+        return x.reshape(nb, N, H, D).permute(0, 2, 3, 1).contiguous()
+    out = torch.zeros(nb, H, D, Np, dtype=x.dtype, device=x.device)
+    out[..., :N] = x.reshape(nb, N, H, D).permute(0, 2, 3, 1)
+    return out
+
+
+def _mat_t(m, rows, cols, colsp):
+    """m [..., rows, ld] (first `cols` columns valid) -> [..., cols, colsp'] transposed copy, rows padded to a multiple of 8."""
+    rp = (rows + 7) // 8 * 8
+    mt = m[..., :cols].transpose(-1, -2)
+    if rp == rows:
+        return mt.contiguous(), rp
+    out = torch.zeros(*m.shape[:-2], cols, rp, dtype=m.dtype, device=m.device)
+    out[..., :rows] = mt
+    return out, rp
+
+
+def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=True, max_score_bytes=4 << 30):
+    """Backward of `flash_attention` / `attention` (head dim 64): returns (dq, dk, dv); dk = dv = None when
+    need_kv is False (keys/values that come from the frozen context).  The probabilities are recomputed and
+    materialised one chunk of batch items at a time (bf16, the rounding points of `attention`); every product --
+    S = QK^T, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO -- is a launch of the tensor-core GEMM."""
+    D = 64
+    HD = H * D
+    dev = q.device
+    q, k, v, dout = q.contiguous(), k.contiguous(), v.contiguous(), dout.contiguous()
+    dq = torch.empty_like(q)
+    Nkp = (Nk + 7) // 8 * 8
+    if shared_kv:
+        if need_kv:
+            raise NotImplementedError("attention_bwd: shared keys/values are frozen-context projections (no dk/dv)")
+        kt = _heads_t(k.reshape(1, Nk, HD), 1, Nk, H, Nkp)[0]  # [H, 64, Nkp]
+        rows_total = Bq * Nq
+        rows_chunk = max(128, min(rows_total, max_score_bytes // (2 * H * Nkp * 2) // 128 * 128))
+        q2, d2, dq2 = q.view(rows_total, HD), dout.view(rows_total, HD), dq.view(rows_total, HD)
+        for r0 in range(0, rows_total, rows_chunk):
+            m = min(rows_chunk, rows_total - r0)
+            sim = torch.empty(H, m, Nkp, dtype=q.dtype, device=dev)
+            gemm_raw(q2[r0:], k, sim, m, Nk, D, HD, HD, Nkp, batch_h=H, a_strides=(D, 0), b_strides=(D, 0),
+                     c_strides=(m * Nkp, 0), alpha=scale, act="round_scale")
+            p = softmax_rows(sim, Nk, Nkp)
+            gemm_raw(d2[r0:], v, sim, m, Nk, D, HD, HD, Nkp, batch_h=H, a_strides=(D, 0), b_strides=(D, 0),
+                     c_strides=(m * Nkp, 0))  # dP over the score buffer
+            ds = softmax_bwd_rows(p, sim, Nk)
+            gemm_raw(ds, kt, dq2[r0:], m, D, Nkp, Nkp, Nkp, HD, batch_h=H, a_strides=(m * Nkp, 0), b_strides=(D * Nkp, 0),
+                     c_strides=(D, 0), alpha=scale)
+        return dq, None, None
+    dk, dv = (torch.empty_like(k), torch.empty_like(v)) if need_kv else (None, None)
+    per_item = H * Nq * Nkp * 2
+    bchunk = max(1, min(Bq, max_score_bytes // (4 * per_item)))  # scores/dS, P, and their two transposes
+    for b0 in range(0, Bq, bchunk):
+        nb = min(bchunk, Bq - b0)
+        sim = torch.empty(nb, H, Nq, Nkp, dtype=q.dtype, device=dev)
+        gemm_raw(q[b0:], k[b0:], sim, Nq, Nk, D, HD, HD, Nkp, batch_h=H, batch_b=nb, a_strides=(D, Nq * HD),
+                 b_strides=(D, Nk * HD), c_strides=(Nq * Nkp, H * Nq * Nkp), alpha=scale, act="round_scale")
+        p = softmax_rows(sim, Nk, Nkp)
+        gemm_raw(dout[b0:], v[b0:], sim, Nq, Nk, D, HD, HD, Nkp, batch_h=H, batch_b=nb, a_strides=(D, Nq * HD),
+                 b_strides=(D, Nk * HD), c_strides=(Nq * Nkp, H * Nq * Nkp))
+        ds = softmax_bwd_rows(p, sim, Nk)
+        kt = _heads_t(k[b0:b0 + nb], nb, Nk, H, Nkp)
+        gemm_raw(ds, kt, dq[b0:], Nq, D, Nkp, Nkp, Nkp, HD, batch_h=H, batch_b=nb, a_strides=(Nq * Nkp, H * Nq * Nkp),
+                 b_strides=(D * Nkp, H * D * Nkp), c_strides=(D, Nq * HD), alpha=scale)
+        if need_kv:
+            dst, Nqp = _mat_t(ds, Nq, Nk, Nkp)   # [nb, H, Nk, Nqp]
+            pt, _ = _mat_t(p, Nq, Nk, Nkp)
+            qt = _heads_t(q[b0:b0 + nb], nb, Nq, H, Nqp)
+            dot = _heads_t(dout[b0:b0 + nb], nb, Nq, H, Nqp)
+            gemm_raw(dst, qt, dk[b0:], Nk, D, Nqp, Nqp, Nqp, HD, batch_h=H, batch_b=nb, a_strides=(Nk * Nqp, H * Nk * Nqp),
+                     b_strides=(D * Nqp, H * D * Nqp), c_strides=(D, Nk * HD), alpha=scale)
+            gemm_raw(pt, dot, dv[b0:], Nk, D, Nqp, Nqp, Nqp, HD, batch_h=H, batch_b=nb, a_strides=(Nk * Nqp, H * Nk * Nqp),
+                     b_strides=(D * Nqp, H * D * Nqp), c_strides=(D, Nk * HD))
+    return dq, dk, dv
+
+
+def ddim_pred_x0_vjp(e_cond, e_uncond, grad_pred_x0, coef):
+    """(dx_direct, de_cond, de_uncond) for G = dL/dpred_x0 of one guided step (gvd_ddim_pred_x0_vjp); fp32 tensors of one
+    batch item, `coef` from DdimSchedule.coefficients."""
+    lib = _n.nn()
+    n = e_cond.numel()
+    e_cond, grad_pred_x0 = e_cond.contiguous(), grad_pred_x0.contiguous()
+    dx, de_c = torch.empty_like(e_cond), torch.empty_like(e_cond)
+    de_u = None
+    if e_uncond is not None:
+        e_uncond = e_uncond.contiguous()
+        de_u = torch.empty_like(e_cond)
+    scratch = torch.empty(8, dtype=torch.float64, device=e_cond.device)
+    a = _n.DdimVjpArgs()
+    a.n = n
+    a.e_cond, a.e_uncond, a.grad_pred_x0 = e_cond.data_ptr(), _p(e_uncond), grad_pred_x0.data_ptr()
+    a.dx, a.de_cond, a.de_uncond = dx.data_ptr(), de_c.data_ptr(), _p(de_u)
+    a.scratch, a.scratch_bytes = scratch.data_ptr(), 64
+    for key in ("cfg_scale", "guidance_rescale", "sqrt_alphas_cumprod_t", "sqrt_one_minus_alphas_cumprod_t", "scale_t", "scale_prev"):
+        setattr(a, key, float(coef[key]))
+    a.use_dynamic_rescale = int(coef["use_dynamic_rescale"])
+    with torch.cuda.device(e_cond.device):
+        _check(lib.gvd_ddim_pred_x0_vjp(C.byref(a), _stream()), lib, "gvd_ddim_pred_x0_vjp")
+    return dx, de_c, de_u

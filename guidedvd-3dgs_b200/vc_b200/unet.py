@@ -266,14 +266,26 @@ class UNetB200:
         if self.trace is not None:
             self.trace.append((name, h.view(st["F"], st["H"], st["W"], -1).permute(0, 3, 1, 2).float()))
 
-    @torch.no_grad()
     def forward(self, x, timesteps, context, fs=None):
         """x [1, C_in, t, h, w] fp32; timesteps [1]; context [1, 77+256, 1024]; fs [1] -> [1, C_out, t, h, w] bf16.
         With an active `self.part` the input is still the full clip; the result holds this rank's frames only
-        ([1, C_out, F_r, h, w]); DiffusionModelB200 gathers them."""
+        ([1, C_out, F_r, h, w]); DiffusionModelB200 gathers them.  Inference: no graph is recorded."""
+        with torch.no_grad():
+            return self._forward(x, timesteps, context, fs)
+
+    def forward_with_grad(self, x, timesteps, context, fs=None):
+        """Same network with the tape on: when `x.requires_grad`, every operator records its input-gradient
+        (vc_b200.grad), so `y.backward(gradient=g, inputs=x)` yields dL/dx -- the call the guided sampler makes
+        (ddim_guidance.py:264-265,309).  Single GPU (no frame partition)."""
+        if self.part is not None and self.part.active:
+            raise RuntimeError("forward_with_grad: the frame-sharded plan is inference-only")
+        with torch.enable_grad():
+            return self._forward(x, timesteps, context, fs)
+
+    def _forward(self, x, timesteps, context, fs=None):
         b, cin, t, hh, ww = x.shape
         if b != 1:
-            return torch.cat([self.forward(x[i:i + 1], timesteps[i:i + 1], context[i:i + 1], None if fs is None else fs[i:i + 1])
+            return torch.cat([self._forward(x[i:i + 1], timesteps[i:i + 1], context[i:i + 1], None if fs is None else fs[i:i + 1])
                               for i in range(b)])
         emb = self._mlp(timestep_embedding(timesteps, self.model_channels), self.time_embed)
         if self.fs_condition:
@@ -326,6 +338,8 @@ class DiffusionModelB200:
     def _local(self, x, t, cond, fs):
         xc = torch.cat([x] + list(cond["c_concat"]), dim=1)
         cc = torch.cat(list(cond["c_crossattn"]), dim=1)
+        if torch.is_grad_enabled() and x.requires_grad:  # the guided sampler differentiates through this call
+            return self.unet.forward_with_grad(xc, t, cc, fs=fs).float()
         return self.unet(xc, t, cc, fs=fs).float()
 
     def apply_model(self, x, t, cond, fs=None, **kwargs):

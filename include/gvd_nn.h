@@ -126,6 +126,65 @@ typedef struct GvdDdimArgs {
 } GvdDdimArgs;
 GVD_NN_API int gvd_ddim_step(const GvdDdimArgs* args, gvd_nn_stream_t stream);
 
+/* ---- input-gradient operators: the guided sampler (lvdm/models/samplers/ddim_guidance.py:259-337) differentiates
+ * pred_x0 with respect to the latent x through both U-Net forwards (`pred_x0.backward(gradient=..., inputs=x)`, :309);
+ * the reference leaves that to autograd over ATen/cuDNN.  Parameters are frozen there, so only activations get
+ * gradients: dX of a linear / conv layer is the tensor-core GEMM above against the transposed weight; the entries
+ * below are the adjoints of the memory-bound layers.  bf16 in/out, fp32 arithmetic, same layouts as the forwards. ---- */
+
+/* GroupNorm backward.  stats[F, groups, 2] = (sum x, sum x^2) from gvd_groupnorm_cl_stats over the same rows;
+ * do_silu as in the forward (the SiLU derivative is taken where the forward evaluated it).
+ * tmp: gvd_groupnorm_bwd_tmp_bytes(F, S, groups) bytes, 8-byte aligned. */
+GVD_NN_API size_t gvd_groupnorm_bwd_tmp_bytes(int F, long long S, int groups);
+GVD_NN_API int gvd_groupnorm_cl_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* beta,
+                                    const float* stats, int F, long long S, int C, int groups, float eps, int do_silu,
+                                    void* tmp, size_t tmp_bytes, gvd_nn_stream_t stream);
+
+/* LayerNorm backward over the last dimension: x, dy, dx [rows, C] bf16. */
+GVD_NN_API int gvd_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, long long rows, int C,
+                                 float eps, gvd_nn_stream_t stream);
+
+/* GEGLU backward: h [rows, 2D] (the forward's input), dout [rows, D] -> dh [rows, 2D]. */
+GVD_NN_API int gvd_geglu_bwd(const void* h, const void* dout, void* dh, long long rows, int D, gvd_nn_stream_t stream);
+
+/* Row softmax backward: ds = p o (dp - sum_j p_j dp_j) over the first `cols` columns of p, dp, ds [rows, ld] bf16
+ * (ds may alias dp); columns cols..ld-1 of ds are zeroed so it can feed a GEMM with K = ld. */
+GVD_NN_API int gvd_softmax_bwd_rows(const void* p, const void* dp, void* ds, long long ld, long long rows, int cols,
+                                    gvd_nn_stream_t stream);
+
+/* Adjoints of the two im2col layouts: dcol [F, Ho, Wo, 9*C] -> dx [F, H, W, C] (same stride / upsample meaning as
+ * gvd_im2col3x3_cl; every input pixel gathers its taps, no atomics) and dcol [B, T, S, 3*C] -> dx [B, T, S, C]. */
+GVD_NN_API int gvd_col2im3x3_cl(const void* dcol, void* dx, int F, int H, int W, int C, int stride, int upsample,
+                                gvd_nn_stream_t stream);
+GVD_NN_API int gvd_col2im_t3_cl(const void* dcol, void* dx, int B, int T, long long S, int C, gvd_nn_stream_t stream);
+
+/* Backward of gvd_temporal_attention: q, k, v, dout -> dq, dk, dv, all [B, T, S, H*64] bf16 (the probabilities are
+ * recomputed with the forward's rounding points). */
+GVD_NN_API int gvd_temporal_attention_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq,
+                                          void* dk, void* dv, int B, int T, long long S, int H, float scale,
+                                          gvd_nn_stream_t stream);
+
+/* Vector-Jacobian product of the guided step's pred_x0 arithmetic (ddim_guidance.py:263-278: CFG mix,
+ * rescale_noise_cfg, predict_start_from_z_and_v, dynamic rescale): given grad_pred_x0 = dL/dpred_x0 writes
+ * dx = the gradient through the explicit x_t term and de_cond / de_uncond = the cotangents of the two U-Net outputs.
+ * All tensors fp32 with n elements; e_uncond / de_uncond may be NULL together.  scratch: 64 bytes, 8-byte aligned. */
+typedef struct GvdDdimVjpArgs {
+    long long n;
+    const float* e_cond;
+    const float* e_uncond;
+    const float* grad_pred_x0;
+    float* dx;
+    float* de_cond;
+    float* de_uncond;
+    void* scratch;
+    size_t scratch_bytes;
+    float cfg_scale, guidance_rescale;
+    float sqrt_alphas_cumprod_t, sqrt_one_minus_alphas_cumprod_t;
+    float scale_t, scale_prev;
+    int use_dynamic_rescale;
+} GvdDdimVjpArgs;
+GVD_NN_API int gvd_ddim_pred_x0_vjp(const GvdDdimVjpArgs* args, gvd_nn_stream_t stream);
+
 GVD_NN_API const char* gvd_nn_last_error(void);
 
 #ifdef __cplusplus
