@@ -273,9 +273,9 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __r
 }
 
 // ---------------- softmax backward per row: ds = p * (dp - sum_j p_j dp_j) (one warp per row) ----------------
-__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p,
-                                                               const __nv_bfloat16* __restrict__ dp, __nv_bfloat16* __restrict__ ds,
-                                                               long long ld, long long rows, int cols) {
+// ds may alias dp (a lane reads and writes only its own columns), so neither is __restrict__.
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* dp,
+                                                               __nv_bfloat16* ds, long long ld, long long rows, int cols) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;

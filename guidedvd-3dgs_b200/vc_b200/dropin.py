@@ -7,10 +7,15 @@ DiffusionWrapper.forward, lvdm/models/ddpm3d.py:1426-1443) reaches the denoiser 
 forward runs vc_b200.unet.UNetB200; `replace_unet(latent_diffusion)` installs it, so `ViewCrafterWrapper`,
 `ViewCrafter.run_diffusion`, `image_guided_synthesis` and the reference samplers run unchanged on top of it.
 
-Scope: the plain DDIM path (`no_guidance=True`, and every U-Net call made under torch.no_grad()).  The guided sampler
-(lvdm/models/samplers/ddim_guidance.py:259-337) differentiates through the U-Net; this forward is inference-only, so
-`B200UNet` hands calls that need a graph back to the reference module it wraps (next).
+Scope: the plain DDIM path (`no_guidance=True`, and every U-Net call made under torch.no_grad()) always runs native.
+The guided sampler (lvdm/models/samplers/ddim_guidance.py:259-337) differentiates through the U-Net with respect to
+the latent: with GVD_GUIDED_NATIVE=1 such a call runs `UNetB200.forward_with_grad` (vc_b200.grad: the same forward
+kernels with the tape on, input-gradient kernels in the backward); without it -- the default until that path has its
+first green GPU run -- `B200UNet` hands calls that need a graph back to the reference module it wraps.  Calls that
+want PARAMETER gradients (nobody on this path) always go to the reference module.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -31,9 +36,14 @@ class B200UNet(nn.Module):
         self.native = UNetB200(reference_unet.state_dict(), device=dev, **cfg)
 
     def forward(self, x, timesteps, context=None, features_adapter=None, fs=None, **kwargs):
-        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.reference.parameters()))
-        if needs_graph or features_adapter is not None:
+        if features_adapter is not None:
             return self.reference(x, timesteps, context=context, features_adapter=features_adapter, fs=fs, **kwargs)
+        if torch.is_grad_enabled() and x.requires_grad:
+            if os.environ.get("GVD_GUIDED_NATIVE", "0") == "1":
+                return self.native.forward_with_grad(x.float(), timesteps, context.float(), fs=fs).to(x.dtype)
+            return self.reference(x, timesteps, context=context, fs=fs, **kwargs)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.reference.parameters()):
+            return self.reference(x, timesteps, context=context, fs=fs, **kwargs)
         return self.native(x.float(), timesteps, context.float(), fs=fs).to(x.dtype)
 
 
