@@ -394,56 +394,90 @@ def main():
     if exchange is not None:
         pkg.set_gradient_buffer(None)
         exchange.close()
+    emitted = []
+
+    def emit(denoise_result):
+        """Rank 0: build and print THE json line (once)."""
+        if emitted:
+            return
+        emitted.append(1)
+        views_per_s = world * K / (ms_res * 1e-3)
+        e2e_views_per_s = world * K / (ms_e2e * 1e-3)
+        h2d = in_host.numel() * 4
+        ws_mb = (P * 236 + P * 248 + R * (12 * 2 + 48 + 12) + HWp * 48) / 1e6
+        line = {
+            "metric": "3DGS train-step views/sec (rasterizer fwd+bwd)", "value": round(views_per_s, 2), "unit": "views/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_res / K, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": args.impl,
+            "config": {"workload": args.workload, "description": desc, "P": P, "width": W, "height": H, "sh_degree": D,
+                       "num_rendered": R, "visible": visible, "tiles": tiles,
+                       "l2_policy": f"inputs larger than L2: per-step working set ~{ws_mb:.0f} MB > 126 MB",
+                       "parallelism": f"view-parallel dp{world}" + ((" + gradient sum of 59 floats/Gaussian per step: " + ("one NVLink peer-memory kernel (gvd_exchange_allreduce_sum)"
+                                       if args.impl == "ours" else "NCCL all-reduce")) if world > 1 else "")},
+            "e2e": {"value": round(e2e_views_per_s, 2), "unit": "views/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4), "wall_ms_per_step": round(wall_e2e / K * 1e3, 4)},
+            "gpu_launches": ((9 + (1 if world > 1 else 0)) * K * 2) if args.impl == "ours" else 0,
+            "gpu_launches_note": "own kernels in the two timed regions: preprocess, bin_count, bin_prefix, bin_ranges, bin_fill, "
+                                 "render_fwd, zero_fill, render_bwd, gaussian_bwd per step, + grad_allreduce_kernel at N > 1 (+ CUB "
+                                 "radix-sort library kernels for the depth sort and the cuBLAS dot of the e2e result, not counted)",
+            "clocks": clocks,
+        }
+        if roofline:
+            line["roofline"] = roofline
+        if denoise_result is not None:
+            line["denoise"] = denoise_result
+        if args.impl == "reference":
+            line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": "reference",
+                                    "sample": "the reference has no CPU rasterizer: this arm is its own CUDA code "
+                                              "(oracle/_ref, compiled unmodified for sm_100a) on the same B200, full workload"}
+        elif world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(P, W, H, seed, D)
+        print(json.dumps(line))
+        sys.stdout.flush()
+
     denoise_result = None
     if not args.no_denoise and (world == 1 or args.impl == "ours"):
         # every rank takes part: at N > 1 the DDIM step is CFG-split x frame-sharded (vc_b200/frame_parallel.py)
+        guard = None
+        if world > 1:
+            # a peer that died (or a mismatched collective) would park this rank inside NCCL until its watchdog aborts
+            # the process -- and the headline line with it: after DENOISE_DEADLINE_S print what was measured and leave
+            def bail():
+                if rank == 0:
+                    emit({"error": f"secondary metric did not finish within {DENOISE_DEADLINE_S} s at N = {world}"})
+                sys.stdout.flush()
+                os._exit(0)
+            guard = threading.Timer(DENOISE_DEADLINE_S, bail)
+            guard.daemon = True
+            guard.start()
         try:
             del sc, leaves, means2D
             torch.cuda.empty_cache()
             denoise_result = denoise_bench(args.impl, dev, world=world)
+            if guard is not None:
+                guard.cancel()
         except Exception as ex:  # the secondary metric must never take the headline line down
             denoise_result = {"error": repr(ex)[:300]}
+            if world > 1:
+                # a rank that failed alone would leave its peers waiting inside a collective until the NCCL watchdog
+                # kills the job -- and the headline line with it.  Print what was measured and leave.
+                if rank == 0:
+                    emit(denoise_result)
+                sys.stdout.flush()
+                os._exit(0)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    views_per_s = world * K / (ms_res * 1e-3)
-    e2e_views_per_s = world * K / (ms_e2e * 1e-3)
-    h2d = in_host.numel() * 4
-    ws_mb = (P * 236 + P * 248 + R * (12 * 2 + 48 + 12) + HWp * 48) / 1e6
-    line = {
-        "metric": "3DGS train-step views/sec (rasterizer fwd+bwd)", "value": round(views_per_s, 2), "unit": "views/s",
-        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_res / K, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "impl": args.impl,
-        "config": {"workload": args.workload, "description": desc, "P": P, "width": W, "height": H, "sh_degree": D,
-                   "num_rendered": R, "visible": visible, "tiles": tiles,
-                   "l2_policy": f"inputs larger than L2: per-step working set ~{ws_mb:.0f} MB > 126 MB",
-                   "parallelism": f"view-parallel dp{world}" + ((" + gradient sum of 59 floats/Gaussian per step: " + ("one NVLink peer-memory kernel (gvd_exchange_allreduce_sum)"
-                                   if args.impl == "ours" else "NCCL all-reduce")) if world > 1 else "")},
-        "e2e": {"value": round(e2e_views_per_s, 2), "unit": "views/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4), "wall_ms_per_step": round(wall_e2e / K * 1e3, 4)},
-        "gpu_launches": ((9 + (1 if world > 1 else 0)) * K * 2) if args.impl == "ours" else 0,
-        "gpu_launches_note": "own kernels in the two timed regions: preprocess, bin_count, bin_prefix, bin_ranges, bin_fill, "
-                             "render_fwd, zero_fill, render_bwd, gaussian_bwd per step, + grad_allreduce_kernel at N > 1 (+ CUB "
-                             "radix-sort library kernels for the depth sort and the cuBLAS dot of the e2e result, not counted)",
-        "clocks": clocks,
-    }
-    if roofline:
-        line["roofline"] = roofline
-    if denoise_result is not None:
-        line["denoise"] = denoise_result
-    if args.impl == "reference":
-        line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": "reference",
-                                "sample": "the reference has no CPU rasterizer: this arm is its own CUDA code "
-                                          "(oracle/_ref, compiled unmodified for sm_100a) on the same B200, full workload"}
-    elif world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(P, W, H, seed, D)
-    print(json.dumps(line))
+    emit(denoise_result)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+DENOISE_DEADLINE_S = 420
 
 
 def denoise_bench(impl, dev, steps=2, t=25, h=72, w=128, world=1):
