@@ -56,3 +56,34 @@ def replace_unet(latent_diffusion):
     new = B200UNet(unet)
     wrapper.diffusion_model = new
     return new
+
+
+def replace_first_stage_decoder(latent_diffusion):
+    """latent_diffusion.first_stage_model.decode <- the B200-native VAE decoder (vc_b200.vae.DecoderB200).
+
+    `decode_core` (lvdm/models/ddpm3d.py:646-667) keeps its per-frame loop and its 1/scale_factor; each
+    `first_stage_model.decode(frame_z)` (autoencoder.py:104-107: post_quant_conv + Decoder) lands here.  Same routing
+    rule as B200UNet: no graph wanted -> native forward; graph with respect to the latent wanted (the guided sampler,
+    ddim_guidance.py:288) -> native forward with the tape on when GVD_GUIDED_NATIVE=1, else the reference module.
+    Returns the DecoderB200."""
+    from .vae import DecoderB200
+
+    fs = latent_diffusion.first_stage_model
+    if getattr(fs, "_b200_decoder", None) is not None:
+        return fs._b200_decoder
+    dev = next(fs.parameters()).device
+    native = DecoderB200(fs.state_dict(), device=dev, scale_factor=1.0)
+    reference_decode = fs.decode
+
+    def decode(z, **kwargs):
+        if torch.is_grad_enabled() and z.requires_grad:
+            if os.environ.get("GVD_GUIDED_NATIVE", "0") == "1":
+                return native.differentiable_decode(z.float()).to(z.dtype)
+            return reference_decode(z, **kwargs)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in fs.parameters()):
+            return reference_decode(z, **kwargs)
+        return native.decode(z.float()).to(z.dtype)
+
+    fs.decode = decode
+    fs._b200_decoder = native
+    return native

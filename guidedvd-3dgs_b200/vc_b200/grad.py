@@ -143,3 +143,22 @@ class FlashAttention(Function):
         dq, dk, dv = ops.attention_bwd(q, k, v, _c(dout), Bq, Nq, Nk, H, scale, shared_kv, need_kv)
         return (dq.view_as(q), dk.view_as(k) if dk is not None else None, dv.view_as(v) if dv is not None else None,
                 None, None, None, None, None, None)
+
+
+class MaterialisedAttention(Function):
+    """`ops.attention` (scores materialised, any head dim): the VAE decoder's single-head 512-channel AttnBlock."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, Bq, Nq, Nk, H, scale, shared_kv, head_dim):
+        ctx.save_for_backward(q, k, v)
+        ctx.args = (Bq, Nq, Nk, H, scale, shared_kv, head_dim)
+        return ops.attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv, head_dim=head_dim)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v = ctx.saved_tensors
+        Bq, Nq, Nk, H, scale, shared_kv, head_dim = ctx.args
+        need_kv = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dq, dk, dv = ops.attention_bwd(q, k, v, _c(dout), Bq, Nq, Nk, H, scale, shared_kv, need_kv, head_dim=head_dim)
+        return (dq.view_as(q), dk.view_as(k) if dk is not None else None, dv.view_as(v) if dv is not None else None,
+                None, None, None, None, None, None, None)

@@ -14,9 +14,10 @@ One guided step:
   5. rho = rms(e_cond - e_uncond) * cfg / rms(dL/dx) * 0.2 * scale_guidance_weight; x_prev -= rho * dL/dx (:318-326)
   6. (recurrence, :334) x = sqrt(beta_t) x_prev + sqrt(1 - beta_t) N(0, 1), beta_t = a_t / a_prev.
 
-`model` protocol beyond vc_b200.sampler.DDIMSampler's: `model.differentiable_decode_first_stage(z[1,4,1,h,w]) ->
-[1,3,1,H,W]` (ddpm3d.py:674-675).  The VAE decoder itself is still the reference module under autograd (SURVEY.md 8f1
-lists it after the U-Net backward).  `loss_guidance_fn` protocol: SURVEY.md section 8b.
+`model` protocol beyond vc_b200.sampler.DDIMSampler's: `model.differentiable_decode_first_stage(z[1,4,n,h,w]) ->
+[1,3,n,H,W]` (ddpm3d.py:674-675; vc_b200.vae.DecoderB200.differentiable_decode is the native one) and, optionally,
+`model.guided_decode_frames` = how many frames to decode per call (default 1, the reference's loop; frames are a batch
+dimension of the decoder, so any chunk size gives the same gradients).  `loss_guidance_fn` protocol: SURVEY.md 8b.
 """
 import numpy as np
 import torch
@@ -67,14 +68,20 @@ class DDIMSamplerGuidance(DDIMSampler):
             e_ud = None if e_u is None else e_u.detach().float().contiguous()
             x_prev, pred_x0 = ops.ddim_step(x.detach().contiguous(), e_cd, e_ud, nz.float().contiguous(), coef)
             grads, decoded = [], []
-            for f in range(n_frames):
-                z = pred_x0[:, :, f:f + 1].clone().requires_grad_(True)  # the decoder graph ends here (:285)
+            chunk = max(1, int(getattr(model, "guided_decode_frames", 1)))
+            for f0 in range(0, n_frames, chunk):
+                f1 = min(n_frames, f0 + chunk)
+                z = pred_x0[:, :, f0:f1].clone().requires_grad_(True)  # the decoder graph ends here (:285)
                 with torch.enable_grad():
                     d_x0 = model.differentiable_decode_first_stage(z)
-                    loss_dict, numel = lg(d_x0[0], index, f, f + 1)
-                    g = torch.autograd.grad(outputs=loss_dict["recon"], inputs=z)[0]
-                if not lg.mean_loss:
-                    g = g / numel
+                    # frames are independent through the decoder, so one backward over sum_f loss_f / numel_f gives
+                    # every frame the gradient the reference's one-frame-at-a-time loop gives it
+                    total = None
+                    for f in range(f0, f1):
+                        loss_dict, numel = lg(d_x0[0][:, f - f0:f - f0 + 1], index, f, f + 1)
+                        term = loss_dict["recon"] if lg.mean_loss else loss_dict["recon"] / numel
+                        total = term if total is None else total + term
+                    g = torch.autograd.grad(outputs=total, inputs=z)[0]
                 grads.append(g.detach())
                 decoded.append(d_x0.detach())
             lg.save_pred_x0(torch.cat(decoded, dim=2), index)

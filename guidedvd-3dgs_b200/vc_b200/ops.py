@@ -212,12 +212,14 @@ def flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False):
     return out
 
 
-def attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False, max_score_bytes=6 << 30):
-    """softmax(q k^T * scale) v with head dim 64.
+def attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False, max_score_bytes=6 << 30, head_dim=64):
+    """softmax(q k^T * scale) v with head dim `head_dim` (64 in the U-Net; 512, one head, in the VAE's AttnBlock).
     q [Bq, Nq, H*64]; k, v [Bq, Nk, H*64] (or [1, Nk, H*64] when shared_kv: the same keys for every batch item, then
     the batch is folded into the query rows).  Scores are materialised in bf16 (rounded exactly where the reference
     rounds them) one chunk of batch items at a time, probabilities feed the PV product as bf16."""
-    D = 64
+    if _wants_grad(q, k, v):
+        return _grad().MaterialisedAttention.apply(q, k, v, Bq, Nq, Nk, H, scale, bool(shared_kv), int(head_dim))
+    D = int(head_dim)
     HD = H * D
     dev = q.device
     out = torch.empty(Bq, Nq, HD, dtype=BF16, device=dev)
@@ -392,10 +394,9 @@ def temporal_attention_bwd(q, k, v, dout, B, T, S, H, scale):
     return dq, dk, dv
 
 
-def _heads_t(x, nb, N, H, Np):
-    """x [nb, N, H*64] -> [nb, H, 64, Np] (token axis last, zero padded to Np): the K-major B operand of a product that
+def _heads_t(x, nb, N, H, Np, D=64):
+    """x [nb, N, H*D] -> [nb, H, D, Np] (token axis last, zero padded to Np): the K-major B operand of a product that
     contracts over tokens."""
-    D = 64
     if Np == N:
         return x.reshape(nb, N, H, D).permute(0, 2, 3, 1).contiguous()
     out = torch.zeros(nb, H, D, Np, dtype=x.dtype, device=x.device)
@@ -414,12 +415,12 @@ def _mat_t(m, rows, cols, colsp):
     return out, rp
 
 
-def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=True, max_score_bytes=4 << 30):
+def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=True, max_score_bytes=4 << 30, head_dim=64):
     """Backward of `flash_attention` / `attention` (head dim 64): returns (dq, dk, dv); dk = dv = None when
     need_kv is False (keys/values that come from the frozen context).  The probabilities are recomputed and
     materialised one chunk of batch items at a time (bf16, the rounding points of `attention`); every product --
     S = QK^T, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO -- is a launch of the tensor-core GEMM."""
-    D = 64
+    D = int(head_dim)
     HD = H * D
     dev = q.device
     q, k, v, dout = q.contiguous(), k.contiguous(), v.contiguous(), dout.contiguous()
@@ -428,7 +429,7 @@ def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=
     if shared_kv:
         if need_kv:
             raise NotImplementedError("attention_bwd: shared keys/values are frozen-context projections (no dk/dv)")
-        kt = _heads_t(k.reshape(1, Nk, HD), 1, Nk, H, Nkp)[0]  # [H, 64, Nkp]
+        kt = _heads_t(k.reshape(1, Nk, HD), 1, Nk, H, Nkp, D)[0]  # [H, D, Nkp]
         rows_total = Bq * Nq
         rows_chunk = max(128, min(rows_total, max_score_bytes // (2 * H * Nkp * 2) // 128 * 128))
         q2, d2, dq2 = q.view(rows_total, HD), dout.view(rows_total, HD), dq.view(rows_total, HD)
@@ -456,14 +457,14 @@ def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=
         gemm_raw(dout[b0:], v[b0:], sim, Nq, Nk, D, HD, HD, Nkp, batch_h=H, batch_b=nb, a_strides=(D, Nq * HD),
                  b_strides=(D, Nk * HD), c_strides=(Nq * Nkp, H * Nq * Nkp))
         ds = softmax_bwd_rows(p, sim, Nk)
-        kt = _heads_t(k[b0:b0 + nb], nb, Nk, H, Nkp)
+        kt = _heads_t(k[b0:b0 + nb], nb, Nk, H, Nkp, D)
         gemm_raw(ds, kt, dq[b0:], Nq, D, Nkp, Nkp, Nkp, HD, batch_h=H, batch_b=nb, a_strides=(Nq * Nkp, H * Nq * Nkp),
                  b_strides=(D * Nkp, H * D * Nkp), c_strides=(D, Nq * HD), alpha=scale)
         if need_kv:
             dst, Nqp = _mat_t(ds, Nq, Nk, Nkp)   # [nb, H, Nk, Nqp]
             pt, _ = _mat_t(p, Nq, Nk, Nkp)
-            qt = _heads_t(q[b0:b0 + nb], nb, Nq, H, Nqp)
-            dot = _heads_t(dout[b0:b0 + nb], nb, Nq, H, Nqp)
+            qt = _heads_t(q[b0:b0 + nb], nb, Nq, H, Nqp, D)
+            dot = _heads_t(dout[b0:b0 + nb], nb, Nq, H, Nqp, D)
             gemm_raw(dst, qt, dk[b0:], Nk, D, Nqp, Nqp, Nqp, HD, batch_h=H, batch_b=nb, a_strides=(Nk * Nqp, H * Nk * Nqp),
                      b_strides=(D * Nqp, H * D * Nqp), c_strides=(D, Nk * HD), alpha=scale)
             gemm_raw(pt, dot, dv[b0:], Nk, D, Nqp, Nqp, Nqp, HD, batch_h=H, batch_b=nb, a_strides=(Nk * Nqp, H * Nk * Nqp),

@@ -98,7 +98,7 @@ def build_knn():
 
 def build_vc():
     """Install (copy) the pure-python ViewCrafter denoiser/sampler modules the parity tests import on the GPU box:
-    lvdm/{basics,common}.py, lvdm/modules/{attention.py,networks/openaimodel3d.py},
+    lvdm/{basics,common}.py, lvdm/modules/{attention.py,networks/openaimodel3d.py,networks/ae_modules.py},
     lvdm/models/{utils_diffusion.py,samplers/*.py}, utils_vc/diffusion_utils.py.  They need torch, einops, cv2, tqdm."""
     src = os.path.join(REF, "third_party", "ViewCrafter")
     if not os.path.isdir(src):
@@ -108,7 +108,7 @@ def build_vc():
     # utils_vc/diffusion_utils.py is pulled in by lvdm/basics.py (instantiate_from_config) and itself imports the
     # three sampler modules
     for rel in ("lvdm/basics.py", "lvdm/common.py", "lvdm/modules/attention.py", "lvdm/modules/networks/openaimodel3d.py",
-                "lvdm/models/utils_diffusion.py", "lvdm/models/samplers/ddim.py", "lvdm/models/samplers/ddim_guidance.py",
+                "lvdm/modules/networks/ae_modules.py", "lvdm/models/utils_diffusion.py", "lvdm/models/samplers/ddim.py", "lvdm/models/samplers/ddim_guidance.py",
                 "lvdm/models/samplers/ddim_multiplecond.py", "utils_vc/diffusion_utils.py"):
         d = os.path.join(dst, rel)
         os.makedirs(os.path.dirname(d), exist_ok=True)

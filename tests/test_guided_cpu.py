@@ -32,10 +32,10 @@ class StubDecoder(torch.nn.Module):
         self.w2 = torch.nn.Parameter(torch.randn(3, 8, 3, 3, generator=g) * 0.3)
 
     def forward(self, z):
-        x = z[:, :, 0]
+        x = z[0].permute(1, 0, 2, 3)  # frames as batch
         x = torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
         x = torch.tanh(torch.nn.functional.conv2d(x, self.w1, padding=1))
-        return torch.tanh(torch.nn.functional.conv2d(x, self.w2, padding=1)).unsqueeze(2)
+        return torch.tanh(torch.nn.functional.conv2d(x, self.w2, padding=1)).permute(1, 0, 2, 3).unsqueeze(0)
 
 
 class StubGuidance:
@@ -107,8 +107,8 @@ def _reference_sampler(ref_unet, decoder):
 
 
 @needs_ref
-@pytest.mark.parametrize("index,recur", [(40, 1), (12, 2)])
-def test_guided_step_matches_reference_sampler(monkeypatch, index, recur):
+@pytest.mark.parametrize("index,recur,decode_frames", [(40, 1, 1), (12, 2, 2), (25, 1, 3)])
+def test_guided_step_matches_reference_sampler(monkeypatch, index, recur, decode_frames):
     from vc_b200.guided import DDIMSamplerGuidance
     from vc_b200.schedule import ModelSchedule
     from vc_b200.unet import DiffusionModelB200, UNetB200
@@ -140,6 +140,7 @@ def test_guided_step_matches_reference_sampler(monkeypatch, index, recur):
     # ---- ours
     model = DiffusionModelB200(UNetB200(ref.state_dict(), device="cpu", **cfg), ModelSchedule())
     model.differentiable_decode_first_stage = decoder
+    model.guided_decode_frames = decode_frames  # the reference decodes one frame per call; any chunking must agree
     sampler = DDIMSamplerGuidance(model)
     sampler.make_schedule(50, ddim_discretize="uniform_trailing", ddim_eta=1.0)
     lg = StubGuidance(targets, masks, recur)
@@ -184,3 +185,58 @@ def test_pred_x0_vjp_against_autograd(monkeypatch):
     p0.backward(G)
     dx, de_c, de_u = ops.ddim_pred_x0_vjp(e_c.detach().float(), None, G.float(), coef)
     assert de_u is None and _rel(dx, x.grad) < 1e-6 and _rel(de_c, e_c.grad) < 1e-6
+
+
+@needs_ref
+def test_guided_step_with_native_vae_decoder(monkeypatch):
+    """The whole guided step native -- U-Net forward + input-gradient AND the VAE decoder forward + latent-gradient
+    (vc_b200.vae.DecoderB200, three frames per decoder call) -- against the reference sampler driving the reference
+    UNetModel and the reference Decoder one frame at a time (ddpm3d.py:646-667)."""
+    import test_vae_cpu as tv
+    if not tv.HAVE:
+        pytest.skip("ae_modules.py not installed")
+    from vc_b200.guided import DDIMSamplerGuidance
+    from vc_b200.schedule import ModelSchedule
+    from vc_b200.unet import DiffusionModelB200, UNetB200
+    from vc_b200.vae import DecoderB200
+
+    install_fake(monkeypatch)
+    ref, cfg = unet_ref.build_reference_unet(model_channels=64, device="cpu")
+    vae = tv.RefFirstStage().eval()
+    T, h, w, index = 3, 8, 8, 30
+    x, cc, ctx, ctx_uc = unet_ref.synth_inputs(T, h, w, device="cpu")
+    cond, uc = {"c_concat": [cc], "c_crossattn": [ctx]}, {"c_concat": [cc], "c_crossattn": [ctx_uc]}
+    fs = torch.tensor([10])
+    g = torch.Generator().manual_seed(123)
+    targets = [torch.rand(3, 8 * h, 8 * w, generator=g) * 2 - 1 for _ in range(T)]
+    masks = [(torch.rand(1, 8 * h, 8 * w, generator=g) > 0.3).float() for _ in range(T)]
+    noises = [torch.randn(x.shape, generator=g) for _ in range(2)]
+
+    class PerFrame(torch.nn.Module):  # decode_core: frames one at a time through AutoencoderKL.decode
+        def __init__(self):
+            super().__init__()
+            self.vae = vae
+
+        def forward(self, z):
+            return torch.stack([self.vae(z[:, :, f])[0] for f in range(z.shape[2])], dim=1).unsqueeze(0)
+
+    sampler_ref, dg = _reference_sampler(ref, PerFrame())
+    queue = list(noises)
+    monkeypatch.setattr(dg, "noise_like", lambda shape, device, repeat=False: queue.pop(0))
+    ts = torch.full((1,), int(sampler_ref.ddim_timesteps[index]), dtype=torch.long)
+    xp_ref, p0_ref = sampler_ref.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5,
+                                               unconditional_conditioning=uc, guidance_rescale=0.7, fs=fs,
+                                               loss_guidance_fn=StubGuidance(targets, masks, 1))
+
+    model = DiffusionModelB200(UNetB200(ref.state_dict(), device="cpu", **cfg), ModelSchedule())
+    dec = DecoderB200(vae.state_dict(), device="cpu", scale_factor=tv.SCALE)
+    model.differentiable_decode_first_stage = dec.differentiable_decode
+    model.guided_decode_frames = 3
+    sampler = DDIMSamplerGuidance(model)
+    sampler.make_schedule(50, ddim_discretize="uniform_trailing", ddim_eta=1.0)
+    lg = StubGuidance(targets, masks, 1)
+    xp, p0 = sampler.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
+                                   guidance_rescale=0.7, fs=fs, loss_guidance_fn=lg, noise=noises[0:1], recur_noise=noises[1:2])
+    print(f"fully native guided step: x_prev rel {_rel(xp, xp_ref):.2e}")
+    assert _rel(xp, xp_ref) < 2e-4 and _rel(p0, p0_ref) < 2e-4
+    assert lg.saved[0][1].shape == (1, 3, T, 8 * h, 8 * w)

@@ -226,3 +226,98 @@ def test_dropin_routes_guided_calls_to_native_when_enabled(monkeypatch):
     xr = xg.detach().clone().requires_grad_(True)
     ref(xr, ts, context=ctx, fs=fs).sum().backward(inputs=[xr])
     assert _rel(xg.grad, xr.grad) < 0.15
+
+
+def test_vae_decoder_forward_and_latent_gradient_vs_reference():
+    """vc_b200.vae.DecoderB200 (full-width VAE, ch 128) on the GPU vs the reference Decoder in fp32 and under bf16 autocast."""
+    import test_vae_cpu as tv
+    from vc_b200.vae import DecoderB200
+
+    if not tv.HAVE:
+        pytest.skip("oracle/_ref/ViewCrafter/.../ae_modules.py not installed")
+    vae = tv.RefFirstStage(ch=128).cuda().eval()
+    ours = DecoderB200(vae.state_dict(), device="cuda", scale_factor=tv.SCALE)
+    g = torch.Generator().manual_seed(3)
+    z = (torch.randn(2, 4, 20, 32, generator=g) * tv.SCALE * 3).cuda()
+    cot = torch.randn(2, 3, 160, 256, generator=g).cuda()
+    res = {}
+    for name in ("fp32", "bf16"):
+        zr = z.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=BF, enabled=(name == "bf16")):
+            y = vae(zr)
+        y.float().backward(cot)
+        res[name] = (y.detach().float(), zr.grad)
+    y_inf = ours.decode(z)
+    zo = z.clone().requires_grad_(True)
+    yo = ours.differentiable_decode(zo)
+    yo.backward(cot)
+    torch.cuda.synchronize()
+    assert torch.equal(y_inf, yo.detach())  # the tape does not change the forward
+    e_y, e_y_ref = _rel(yo, res["fp32"][0]), _rel(res["bf16"][0], res["fp32"][0])
+    e_g, e_g_ref = _rel(zo.grad, res["fp32"][1]), _rel(res["bf16"][1], res["fp32"][1])
+    print(f"VAE decoder: image {e_y:.2e} (reference autocast {e_y_ref:.2e}); latent gradient {e_g:.2e} (reference autocast {e_g_ref:.2e})")
+    assert e_y <= 1.25 * e_y_ref + 2e-3 and e_g <= 1.25 * e_g_ref + 5e-3
+
+
+def test_guided_step_native_vs_reference_sampler_on_gpu(monkeypatch):
+    """One guided DDIM step, everything native (U-Net fwd + dX, VAE decoder fwd + dX, fused DDIM update and its VJP),
+    against the reference DDIMSamplerGuidance over the reference modules under bf16 autocast on the same GPU.  The step is
+    x_prev = plain_step - rho * grad with rho normalising the gradient's RMS, so bf16 noise in the gradient enters
+    x_prev scaled by 0.2 * sgw * cfg * rms(e_c - e_u): compared on x_prev with the bf16 noise bound of the forward test."""
+    import test_guided_cpu as tg
+    import test_vae_cpu as tv
+    import unet_ref
+    from vc_b200.guided import DDIMSamplerGuidance
+    from vc_b200.schedule import ModelSchedule
+    from vc_b200.unet import DiffusionModelB200, UNetB200
+    from vc_b200.vae import DecoderB200
+
+    if not (unet_ref.ref_available() and tv.HAVE):
+        pytest.skip("oracle/_ref/ViewCrafter not installed")
+    ref, cfg = unet_ref.build_reference_unet(model_channels=64)
+    vae = tv.RefFirstStage().cuda().eval()
+    T, h, w, index = 3, 16, 16, 30
+    x, cc, ctx, ctx_uc = unet_ref.synth_inputs(T, h, w)
+    cond, uc = {"c_concat": [cc], "c_crossattn": [ctx]}, {"c_concat": [cc], "c_crossattn": [ctx_uc]}
+    fs = torch.tensor([10], device="cuda")
+    g = torch.Generator().manual_seed(123)
+    targets = [(torch.rand(3, 8 * h, 8 * w, generator=g) * 2 - 1).cuda() for _ in range(T)]
+    masks = [(torch.rand(1, 8 * h, 8 * w, generator=g) > 0.3).float().cuda() for _ in range(T)]
+    noises = [torch.randn(x.shape, generator=g).cuda() for _ in range(2)]
+
+    class PerFrame(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vae = vae
+
+        def forward(self, z):
+            return torch.stack([self.vae(z[:, :, f])[0] for f in range(z.shape[2])], dim=1).unsqueeze(0)
+
+    sampler_ref, dg = tg._reference_sampler(ref, PerFrame())
+    for name, val in list(vars(sampler_ref.model).items()):
+        if isinstance(val, torch.Tensor):
+            setattr(sampler_ref.model, name, val.cuda())
+    sampler_ref.model.device = torch.device("cuda")
+    sampler_ref.make_schedule(50, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    ts = torch.full((1,), int(sampler_ref.ddim_timesteps[index]), dtype=torch.long, device="cuda")
+    outs = {}
+    for name in ("fp32", "bf16"):
+        queue = list(noises)
+        monkeypatch.setattr(dg, "noise_like", lambda shape, device, repeat=False: queue.pop(0))
+        with torch.autocast("cuda", dtype=BF, enabled=(name == "bf16")):
+            outs[name] = sampler_ref.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5,
+                                                   unconditional_conditioning=uc, guidance_rescale=0.7, fs=fs,
+                                                   loss_guidance_fn=tg.StubGuidance(targets, masks, 1))[0].float()
+    model = DiffusionModelB200(UNetB200(ref.state_dict(), device="cuda", **cfg), ModelSchedule())
+    dec = DecoderB200(vae.state_dict(), device="cuda", scale_factor=tv.SCALE)
+    model.differentiable_decode_first_stage = dec.differentiable_decode
+    model.guided_decode_frames = 3
+    sampler = DDIMSamplerGuidance(model)
+    sampler.make_schedule(50, ddim_discretize="uniform_trailing", ddim_eta=1.0)
+    xp, _ = sampler.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
+                                  guidance_rescale=0.7, fs=fs, loss_guidance_fn=tg.StubGuidance(targets, masks, 1),
+                                  noise=noises[0:1], recur_noise=noises[1:2])
+    torch.cuda.synchronize()
+    e_ours, e_ref = _rel(xp, outs["fp32"]), _rel(outs["bf16"], outs["fp32"])
+    print(f"guided x_prev rel L2: ours vs fp32 {e_ours:.3e}, reference-bf16 vs fp32 {e_ref:.3e}")
+    assert e_ours <= 1.25 * e_ref + 5e-3
