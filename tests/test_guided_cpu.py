@@ -240,3 +240,57 @@ def test_guided_step_with_native_vae_decoder(monkeypatch):
     print(f"fully native guided step: x_prev rel {_rel(xp, xp_ref):.2e}")
     assert _rel(xp, xp_ref) < 2e-4 and _rel(p0, p0_ref) < 2e-4
     assert lg.saved[0][1].shape == (1, 3, T, 8 * h, 8 * w)
+
+
+@needs_ref
+def test_reference_sampler_runs_unchanged_over_the_dropins(monkeypatch):
+    """INTEGRATION.md 'Guided sampling': the REFERENCE DDIMSamplerGuidance, untouched, over a model whose U-Net is
+    vc_b200.dropin.B200UNet and whose first_stage_model.decode was replaced, with GVD_GUIDED_NATIVE=1 -- same x_prev as
+    the all-reference run (the sampler's own torch arithmetic and autograd glue around our tapes)."""
+    import test_vae_cpu as tv
+    if not tv.HAVE:
+        pytest.skip("ae_modules.py not installed")
+    from vc_b200.dropin import B200UNet, replace_first_stage_decoder
+
+    fake = install_fake(monkeypatch)
+    ref, _ = unet_ref.build_reference_unet(model_channels=64, device="cpu")
+    vae = tv.RefFirstStage().eval()
+    T, h, w, index = 2, 8, 8, 20
+    x, cc, ctx, ctx_uc = unet_ref.synth_inputs(T, h, w, device="cpu")
+    cond, uc = {"c_concat": [cc], "c_crossattn": [ctx]}, {"c_concat": [cc], "c_crossattn": [ctx_uc]}
+    fs = torch.tensor([10])
+    g = torch.Generator().manual_seed(321)
+    targets = [torch.rand(3, 8 * h, 8 * w, generator=g) * 2 - 1 for _ in range(T)]
+    masks = [(torch.rand(1, 8 * h, 8 * w, generator=g) > 0.3).float() for _ in range(T)]
+    noises = [torch.randn(x.shape, generator=g) for _ in range(2)]
+
+    class FirstStage(torch.nn.Module):  # AutoencoderKL.decode + decode_core's per-frame loop and 1/scale_factor
+        def __init__(self):
+            super().__init__()
+            self.decoder, self.post_quant_conv = vae.decoder, vae.post_quant_conv
+
+        def decode(self, z, **kwargs):
+            return self.decoder(self.post_quant_conv(z))
+
+        def forward(self, z):
+            return torch.stack([self.decode(z[:, :, f] / tv.SCALE)[0] for f in range(z.shape[2])], dim=1).unsqueeze(0)
+
+    results = []
+    for native in (False, True):
+        fs_model = FirstStage()
+        sampler, dg = _reference_sampler(ref, fs_model)
+        if native:
+            monkeypatch.setenv("GVD_GUIDED_NATIVE", "1")
+            unet = B200UNet(ref)
+            sampler.model.model.diffusion_model = unet
+            sampler.model.apply_model = lambda xx, t, c, fs=None, **kw: unet(torch.cat([xx] + c["c_concat"], 1), t,
+                                                                             context=torch.cat(c["c_crossattn"], 1), fs=fs)
+            replace_first_stage_decoder(sampler.model)
+        queue = list(noises)
+        monkeypatch.setattr(dg, "noise_like", lambda shape, device, repeat=False: queue.pop(0))
+        ts = torch.full((1,), int(sampler.ddim_timesteps[index]), dtype=torch.long)
+        results.append(sampler.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5,
+                                             unconditional_conditioning=uc, guidance_rescale=0.7, fs=fs,
+                                             loss_guidance_fn=StubGuidance(targets, masks, 1))[0])
+    assert fake.calls.get("groupnorm_bwd", 0) > 0 and fake.calls.get("col2im3x3", 0) > 0
+    assert _rel(results[1], results[0]) < 2e-4

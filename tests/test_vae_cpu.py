@@ -118,3 +118,44 @@ def test_decoder_bf16_rounding_points(monkeypatch, ref_vae):
     e_g, e_g_ref = _rel(zo.grad, res["fp32"][1]), _rel(res["bf16"][1], res["fp32"][1])
     print(f"bf16: image {e_y:.2e} (reference autocast {e_y_ref:.2e}); latent gradient {e_g:.2e} (reference autocast {e_g_ref:.2e})")
     assert e_y <= 1.25 * e_y_ref + 2e-3 and e_g <= 1.25 * e_g_ref + 5e-3
+
+
+def test_first_stage_dropin_routing(monkeypatch, ref_vae):
+    """vc_b200.dropin.replace_first_stage_decoder: `first_stage_model.decode` (autoencoder.py:104-107) runs native without
+    a graph, forwards to the reference module when a graph is wanted, and runs native WITH the tape under
+    GVD_GUIDED_NATIVE=1 -- the three routes give the same image / latent gradient."""
+    from vc_b200.dropin import replace_first_stage_decoder
+
+    install_fake(monkeypatch)
+
+    class FirstStage(torch.nn.Module):  # AutoencoderKL's decode half
+        def __init__(self, src):
+            super().__init__()
+            self.decoder, self.post_quant_conv = src.decoder, src.post_quant_conv
+
+        def decode(self, z, **kwargs):
+            return self.decoder(self.post_quant_conv(z))
+
+    class LD:
+        pass
+
+    ld = LD()
+    ld.first_stage_model = FirstStage(ref_vae)
+    fs_ref = FirstStage(ref_vae)
+    native = replace_first_stage_decoder(ld)
+    assert replace_first_stage_decoder(ld) is native
+    z = torch.randn(1, 4, 5, 4, generator=torch.Generator().manual_seed(8)) * 2
+    with torch.no_grad():
+        y_ref = fs_ref.decode(z)
+        y = ld.first_stage_model.decode(z)
+    assert _rel(y, y_ref) < 2e-5
+    cot = torch.randn(y.shape, generator=torch.Generator().manual_seed(9))
+    grads = []
+    for env in ("0", "1"):
+        monkeypatch.setenv("GVD_GUIDED_NATIVE", env)
+        zg = z.clone().requires_grad_(True)
+        yg = ld.first_stage_model.decode(zg)
+        yg.backward(cot)
+        grads.append(zg.grad)
+        assert ("ConvolutionBackward" in type(yg.grad_fn).__name__) == (env == "0")
+    assert _rel(grads[1], grads[0]) < 1e-4
