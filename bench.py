@@ -552,9 +552,32 @@ def cpu_baseline(P, W, H, seed, D, budget_s=20.0):
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import raster_oracle
-        return raster_oracle.timed_sample(P, W, H, seed, D, budget_s=budget_s)
+        cb = raster_oracle.timed_sample(P, W, H, seed, D, budget_s=budget_s)
     except Exception as ex:  # the baseline is a reported number, never the product path
-        return {"value": None, "unit": "views/s", "cores": 1, "kind": "port", "sample": f"unavailable: {ex!r}"}
+        cb = {"value": None, "unit": "views/s", "cores": 1, "kind": "port", "sample": f"unavailable: {ex!r}"}
+    cb["also"] = cpu_point_render_rows()
+    return cb
+
+
+def cpu_point_render_rows():
+    """BASELINE.md CPU row 4 (configs[0]): the numpy z-buffer point projection (scene/pcd2img.py:4-70, restated in
+    oracle/pcd2img_oracle.py and pinned to the reference's outputs) timed on this host at 1 000 points / 128x128 and at
+    500 000 points / 640x480.  (The reference's pytorch3d point renderer is not installable offline.)"""
+    try:
+        import pcd2img_oracle as po
+        out = {"what": "scene/pcd2img.py::project_point_cloud_to_image restated in numpy (single thread), best of 5",
+               "host_cores": os.cpu_count()}
+        for name, (n, w, h) in (("c1_1k_128x128_ms", (1000, 128, 128)), ("point_render_500k_640x480_ms", (500000, 640, 480))):
+            pts, col, K, E = po.synth_case(n, w, h, seed=0)
+            best = 1e30
+            for _ in range(5):
+                t0 = time.perf_counter()
+                po.project_point_cloud_to_image(pts, col, K, E, w, h)
+                best = min(best, time.perf_counter() - t0)
+            out[name] = round(best * 1e3, 3)
+        return out
+    except Exception as ex:
+        return {"unavailable": repr(ex)[:200]}
 
 
 def cpu_reference_line(args, P, W, H, seed, D, desc, K, Wm):

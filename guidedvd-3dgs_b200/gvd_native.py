@@ -161,6 +161,30 @@ def knn():
     return lib
 
 
+# ---- libgvd_points.so (include/gvd_points.h) ------------------------------------------------------------
+POINTS_SYMBOLS = ("gvd_point_project_scratch_bytes", "gvd_point_project", "gvd_points_last_error")
+_points = None
+
+
+def points():
+    """Load libgvd_points.so once; raise loudly when it is absent (there is no fallback)."""
+    global _points
+    if _points is not None:
+        return _points
+    path = lib_path("libgvd_points.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `make -C guidedvd-3dgs_b200/csrc`. No fallback path exists.")
+    lib = C.CDLL(path)
+    lib.gvd_points_last_error.restype = C.c_char_p
+    lib.gvd_point_project_scratch_bytes.restype = C.c_size_t
+    lib.gvd_point_project_scratch_bytes.argtypes = [C.c_int, C.c_int]
+    lib.gvd_point_project.restype = C.c_int
+    lib.gvd_point_project.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    _points = lib
+    return lib
+
+
 # ---- libgvd_nn.so (include/gvd_nn.h) --------------------------------------------------------------------
 class GemmArgs(C.Structure):
     _fields_ = [

@@ -40,11 +40,15 @@ def rewrite(src):
         dyn.append(f"alignas(16) {m.group(2)} {m.group(3)}[1 << 17];")
         return f"/* dynamic shared memory: file-scope array {m.group(3)} */"
     src = DYN_SHARED.sub(hoist, src)
-    src = src.replace('#include "../../include/gvd_nn.h"', f'#include "{os.path.join(ROOT, "include", "gvd_nn.h")}"')
+    src = re.sub(r'#include "\.\./\.\./include/(\w+\.h)"', lambda m: f'#include "{os.path.join(ROOT, "include", m.group(1))}"', src)
     # the file-scope arrays must be visible before their first use: put them right after the includes
-    marker = "extern thread_local std::string g_nn_err_ext;"
-    assert marker in src
-    src = src.replace(marker, "thread_local std::string g_nn_err_ext;\nnamespace {\n" + "\n".join(dyn) + "\n}\n", 1)
+    block = "namespace {\n" + "\n".join(dyn) + "\n}\n" if dyn else ""
+    marker = "extern thread_local std::string g_nn_err_ext;"  # defined in gemm_tc.cu, which is not part of a host build
+    if marker in src:
+        src = src.replace(marker, "thread_local std::string g_nn_err_ext;\n" + block, 1)
+    elif block:
+        last = max(m.end() for m in re.finditer(r"^#include .*$", src, re.M))
+        src = src[:last] + "\n" + block + src[last:]
     return src
 
 
@@ -60,7 +64,7 @@ def build(name="nn_backward"):
         text = rewrite(f.read())
     with open(cpp, "w") as f:
         f.write(text)
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-I", HERE, "-o", so, cpp])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", HERE, "-o", so, cpp])
     return so
 
 

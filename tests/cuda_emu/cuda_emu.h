@@ -70,6 +70,19 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return std::atomic_ref<unsigned long long>(*p).fetch_add(v); }
+template <class T> inline T emu_atomic_min(T* p, T v) {
+    std::atomic_ref<T> a(*p);
+    T old = a.load();
+    while (v < old && !a.compare_exchange_weak(old, v)) {}
+    return old;
+}
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { return emu_atomic_min(p, v); }
+inline int atomicMin(int* p, int v) { return emu_atomic_min(p, v); }
+inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+// round-to-nearest double arithmetic that the compiler must not contract into FMAs (build_emu.py passes -ffp-contract=off)
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
 
 // ---- block / warp machinery ----
 struct EmuBlock {
