@@ -492,6 +492,7 @@ def denoise_bench(impl, dev, steps=2, t=25, h=72, w=128, world=1):
     from vc_b200.schedule import ModelSchedule
     from vc_b200.unet import DiffusionModelB200, UNetB200
     ref, cfg = unet_ref.build_reference_unet(model_channels=320, device=dev)
+    ref_cpu = None
     x, cc, ctx, ctx_uc = unet_ref.synth_inputs(t, h, w, device=dev)
     fs = torch.tensor([10], device=dev)
     cond = {"c_concat": [cc], "c_crossattn": [ctx]}
@@ -503,6 +504,8 @@ def denoise_bench(impl, dev, steps=2, t=25, h=72, w=128, world=1):
             from vc_b200.frame_parallel import DenoisePlan
             plan = DenoisePlan(t)
         model = DiffusionModelB200(UNetB200(ref.state_dict(), device=dev, **cfg), sched, plan=plan)
+        if world == 1 and os.environ.get("GVD_BENCH_CPU_UNET", "1") == "1":
+            ref_cpu = ref.cpu()  # kept for the CPU row below (BASELINE.md CPU row 5); leaves the GPU
         del ref
     else:
         class RefModel:  # apply_model of DiffusionWrapper 'hybrid' (ddpm3d.py:1437-1443) around the reference module
@@ -538,6 +541,39 @@ def denoise_bench(impl, dev, steps=2, t=25, h=72, w=128, world=1):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
     flops = 2 * 82.76e12
+    cpu_row = cpu_unet_row(ref_cpu, flops) if ref_cpu is not None else None
+    res = _denoise_line(ms, steps, t, h, w, world, plan, flops)
+    if cpu_row is not None:
+        res["cpu_baseline"] = cpu_row
+    return res
+
+
+def cpu_unet_row(ref_cpu, step_flops, frames=2, h=40, w=56):
+    """BASELINE.md CPU row 5: the reference UNetModel in fp32 on the host cores.  A bounded sample -- one forward at the
+    reference's training resolution (latent 40x56) with `frames` frames instead of 25 -- turned into a FLOP-scaled
+    denoise-steps/s estimate for the benchmarked shape, and labelled as an estimate."""
+    try:
+        g = torch.Generator().manual_seed(11)
+        xc = torch.randn(1, 8, frames, h, w, generator=g)
+        ctxc = torch.randn(1, 333, 1024, generator=g)
+        ts, fs = torch.tensor([481]), torch.tensor([10])
+        best = 1e30
+        with torch.no_grad():
+            for _ in range(2):
+                t0 = time.perf_counter()
+                ref_cpu(xc, ts, context=ctxc, fs=fs)
+                best = min(best, time.perf_counter() - t0)
+        fl = 17.59e12 * frames / 25.0
+        return {"value": round(fl / best / step_flops, 6), "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "cpu_tflops_per_s": round(fl / best / 1e12, 3),
+                "sample": f"reference UNetModel fp32 on the host, one forward at [1,8,{frames},{h},{w}] ({fl / 1e12:.2f} TFLOP, best of 2: "
+                          f"{best:.2f} s); value = FLOP-scaled ESTIMATE of denoise-steps/s at the benchmarked shape (a step = "
+                          f"{step_flops / 1e12:.1f} TFLOP), not a measured step"}
+    except Exception as ex:
+        return {"value": None, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "reference", "sample": f"unavailable: {ex!r}"[:200]}
+
+
+def _denoise_line(ms, steps, t, h, w, world, plan, flops):
     return {"metric": "DDIM denoise-steps/sec", "value": round(1e3 / ms, 4), "unit": "steps/s", "ms_per_step": round(ms, 2),
             "steps": steps, "dtype": "bf16", "config": {"workload": "C3", "frames": t, "latent": [h, w], "cfg": 7.5,
             "ddim_steps": 50, "unet_params_M": 1438.9, "n_gpus": world,
