@@ -18,16 +18,69 @@ One guided step:
 [1,3,n,H,W]` (ddpm3d.py:674-675; vc_b200.vae.DecoderB200.differentiable_decode is the native one) and, optionally,
 `model.guided_decode_frames` = how many frames to decode per call (default 1, the reference's loop; frames are a batch
 dimension of the decoder, so any chunk size gives the same gradients).  `loss_guidance_fn` protocol: SURVEY.md 8b.
+
+One process per GPU (`GuidedPlan`, SURVEY.md section 8e "Guided path"): the conditional and the unconditional U-Net
+forward + backward are independent given the two cotangents, so even ranks evaluate `cond` and odd ranks `uncond`
+(one exchange of the two outputs before the coupled pred_x0 arithmetic, one sum of the two dL/dx after the
+backward); the 25 decoder forward + backward passes are independent frames and are dealt out over ALL ranks (one
+gather of dL/dpred_x0 and of the decoded frames).  Noise is drawn on rank 0 and broadcast.  Everything else (fused
+DDIM update, VJP, rho) is replicated -- it is a few passes over a 256 k-element latent.
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import ops
+from .frame_parallel import split_sizes
 from .sampler import DDIMSampler, _randn
+
+
+class GuidedPlan:
+    """World layout of one guided step: `branch` (0 = cond, 1 = uncond) for the U-Net forward + backward, a contiguous
+    frame slice for the decoder passes.  With an odd world size (or one rank) every rank evaluates both branches."""
+
+    def __init__(self, n_frames):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.split_cfg = self.world > 1 and self.world % 2 == 0
+        self.branch = self.rank % 2 if self.split_cfg else None
+        self.frames = split_sizes(n_frames, self.world)
+        self.f0 = sum(self.frames[:self.rank])
+        self.f1 = self.f0 + self.frames[self.rank]
+
+    def exchange_outputs(self, e_local):
+        """e_local = this rank's branch output -> (e_cond, e_uncond), identical on every rank."""
+        both = [torch.empty_like(e_local) for _ in range(self.world)]
+        dist.all_gather(both, e_local.contiguous())
+        return both[0], both[1]  # ranks 0 and 1 hold cond and uncond
+
+    def sum_branches(self, dx_local):
+        """dL/dx of this rank's branch -> sum over the two branches (each branch is replicated world/2 times)."""
+        total = dx_local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        return total / (self.world // 2)
+
+    def gather_frames(self, local, dim=2):
+        """Concatenate per-rank frame slices (ragged: 25 frames over 8 ranks = 4,3,...,3) along `dim` on every rank."""
+        fmax = max(self.frames)
+        shape = list(local.shape)
+        shape[dim] = fmax
+        pad = torch.zeros(shape, dtype=local.dtype, device=local.device)
+        pad.narrow(dim, 0, local.shape[dim]).copy_(local)
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad)
+        return torch.cat([p.narrow(dim, 0, n) for p, n in zip(parts, self.frames) if n > 0], dim=dim)
 
 
 def _rms(t):
     return (t.float() * t.float()).mean().sqrt().item()
+
+
+def gp_image_size(gp, like, hw):
+    """Decoded image size (H, W) known to every rank, including one that owns no frame: max over ranks of a 2-vector."""
+    v = torch.tensor([0, 0] if hw is None else [int(hw[0]), int(hw[1])], dtype=torch.int64, device=like.device)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return v.tolist()
 
 
 class DDIMSamplerGuidance(DDIMSampler):
@@ -54,23 +107,37 @@ class DDIMSamplerGuidance(DDIMSampler):
         uc = unconditional_conditioning
         model = self.model
         n_frames = x.shape[2]
+        gp = getattr(model, "guided_plan", None)
+        if gp is not None and gp.world == 1:
+            gp = None
+        if gp is not None and uc is None:
+            raise ValueError("the multi-GPU guided plan splits the cond / uncond pair: unconditional_conditioning is required")
         pick = lambda src, j: None if src is None else (src[j] if isinstance(src, (list, tuple)) else src)  # noqa: E731
         x_prev = pred_x0 = None
         for j in range(repeat):
             x = x.detach().float().requires_grad_(True)
+            e_mine = None
             with torch.enable_grad():
-                e_c = model.apply_model(x, t, c, **kwargs)
-                e_u = model.apply_model(x, t, uc, **kwargs) if uc is not None else None
+                if gp is not None and gp.split_cfg:   # this rank's branch only; its partner rank runs the other one
+                    e_mine = model.apply_model(x, t, c if gp.branch == 0 else uc, **kwargs)
+                    e_c = e_u = None
+                else:
+                    e_c = model.apply_model(x, t, c, **kwargs)
+                    e_u = model.apply_model(x, t, uc, **kwargs) if uc is not None else None
             nz = pick(noise, j)
             if nz is None:
                 nz = _randn(model, x.shape, x.device)
-            e_cd = e_c.detach().float().contiguous()
-            e_ud = None if e_u is None else e_u.detach().float().contiguous()
+            if e_mine is not None:
+                e_cd, e_ud = gp.exchange_outputs(e_mine.detach().float())
+            else:
+                e_cd = e_c.detach().float().contiguous()
+                e_ud = None if e_u is None else e_u.detach().float().contiguous()
             x_prev, pred_x0 = ops.ddim_step(x.detach().contiguous(), e_cd, e_ud, nz.float().contiguous(), coef)
             grads, decoded = [], []
             chunk = max(1, int(getattr(model, "guided_decode_frames", 1)))
-            for f0 in range(0, n_frames, chunk):
-                f1 = min(n_frames, f0 + chunk)
+            lo, hi = (0, n_frames) if gp is None else (gp.f0, gp.f1)   # this rank's frames of the decoder passes
+            for f0 in range(lo, hi, chunk):
+                f1 = min(hi, f0 + chunk)
                 z = pred_x0[:, :, f0:f1].clone().requires_grad_(True)  # the decoder graph ends here (:285)
                 with torch.enable_grad():
                     d_x0 = model.differentiable_decode_first_stage(z)
@@ -84,14 +151,29 @@ class DDIMSamplerGuidance(DDIMSampler):
                     g = torch.autograd.grad(outputs=total, inputs=z)[0]
                 grads.append(g.detach())
                 decoded.append(d_x0.detach())
-            lg.save_pred_x0(torch.cat(decoded, dim=2), index)
-            G = torch.cat(grads, dim=2).float().contiguous()
-            dx, de_c, de_u = ops.ddim_pred_x0_vjp(e_cd, e_ud, G, coef)
-            if e_u is None:
-                torch.autograd.backward([e_c], [de_c.to(e_c.dtype)], inputs=[x])
+            if gp is None:
+                d_all, G = torch.cat(decoded, dim=2), torch.cat(grads, dim=2).float().contiguous()
             else:
-                torch.autograd.backward([e_c, e_u], [de_c.to(e_c.dtype), de_u.to(e_u.dtype)], inputs=[x])
-            guided = x.grad.detach().float() + dx
+                empty = lambda ch, hw: pred_x0.new_zeros(1, ch, 0, *hw)  # noqa: E731  (a rank may own no frame)
+                hw_img = decoded[0].shape[3:] if decoded else None
+                if hw_img is None:  # learn the image size from a peer: sizes travel with the gather below
+                    hw_img = tuple(int(v) for v in gp_image_size(gp, pred_x0, None))
+                else:
+                    gp_image_size(gp, pred_x0, hw_img)
+                d_all = gp.gather_frames(torch.cat(decoded, dim=2) if decoded else empty(3, hw_img))
+                G = gp.gather_frames(torch.cat(grads, dim=2).float() if grads else empty(pred_x0.shape[1], pred_x0.shape[3:])).contiguous()
+            lg.save_pred_x0(d_all, index)
+            dx, de_c, de_u = ops.ddim_pred_x0_vjp(e_cd, e_ud, G, coef)
+            if e_mine is not None:
+                cot = de_c if gp.branch == 0 else de_u
+                torch.autograd.backward([e_mine], [cot.to(e_mine.dtype)], inputs=[x])
+                guided = gp.sum_branches(x.grad.detach().float()) + dx
+            else:
+                if e_u is None:
+                    torch.autograd.backward([e_c], [de_c.to(e_c.dtype)], inputs=[x])
+                else:
+                    torch.autograd.backward([e_c, e_u], [de_c.to(e_c.dtype), de_u.to(e_u.dtype)], inputs=[x])
+                guided = x.grad.detach().float() + dx
             x.grad = None
             tmp_s = _rms(guided)
             rho = 0.0
