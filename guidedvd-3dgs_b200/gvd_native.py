@@ -224,7 +224,8 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
               "gvd_ddim_step", "gvd_flash_attention", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply",
               # input-gradient operators of the guided sampler (csrc/nn_backward.cu)
               "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
-              "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp")
+              "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp",
+              "gvd_im2col3x3_down_cl")
 _nn = None
 
 
@@ -265,6 +266,8 @@ def nn():
     lib.gvd_col2im_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
     lib.gvd_temporal_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
     lib.gvd_ddim_pred_x0_vjp.argtypes = [C.POINTER(DdimVjpArgs), vp]
+    lib.gvd_im2col3x3_down_cl.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.gvd_im2col3x3_down_cl.restype = C.c_int
     for n in ("gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows", "gvd_col2im3x3_cl",
               "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp"):
         getattr(lib, n).restype = C.c_int

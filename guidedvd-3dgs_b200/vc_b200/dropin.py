@@ -87,3 +87,31 @@ def replace_first_stage_decoder(latent_diffusion):
     fs.decode = decode
     fs._b200_decoder = native
     return native
+
+
+def replace_first_stage_encoder(latent_diffusion):
+    """latent_diffusion.first_stage_model.encode <- the B200-native VAE encoder (vc_b200.vae.EncoderB200).
+
+    `encode_first_stage` (lvdm/models/ddpm3d.py:620-644, reached from `get_latent_z`, VC/utils_vc/diffusion_utils.py:111-116,
+    once per diffusion round for the 25 conditioning frames) keeps its own posterior object: the hook computes the
+    moments natively and hands them to the reference's `DiagonalGaussianDistribution` (lvdm/distributions.py), so
+    sampling, scale_factor and the per-frame / batched switch stay the reference's.  Returns the EncoderB200."""
+    from lvdm.distributions import DiagonalGaussianDistribution  # the reference package this drop-in lives next to
+
+    from .vae import EncoderB200
+
+    fs = latent_diffusion.first_stage_model
+    if getattr(fs, "_b200_encoder", None) is not None:
+        return fs._b200_encoder
+    dev = next(fs.parameters()).device
+    native = EncoderB200(fs.state_dict(), device=dev)
+    reference_encode = fs.encode
+
+    def encode(x, **kwargs):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in fs.parameters())):
+            return reference_encode(x, **kwargs)  # nobody on this path differentiates the encoder
+        return DiagonalGaussianDistribution(native.moments(x.float()).to(x.dtype))
+
+    fs.encode = encode
+    fs._b200_encoder = native
+    return native

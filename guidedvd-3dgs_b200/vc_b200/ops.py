@@ -173,6 +173,20 @@ def conv3x3(x, F, H, W, weight, bias=None, stride=1, upsample=False, bias2=None,
     return y.view(F, Ho * Wo, -1), Ho, Wo
 
 
+def conv3x3_down(x, F, H, W, weight, bias=None):
+    """The VAE encoder's Downsample (ae_modules.py:93-106): pad right/bottom by one, 3x3 stride 2, no padding.
+    x[F, H*W, Cin] -> (y[F, Ho*Wo, Cout], Ho, Wo).  Inference only (the encoder is never differentiated)."""
+    if _wants_grad(x):
+        raise RuntimeError("conv3x3_down: the VAE encoder is inference-only (no backward)")
+    lib = _n.nn()
+    Cin = x.shape[-1]
+    Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    col = torch.empty(F * Ho * Wo, 9 * Cin, dtype=BF16, device=x.device)
+    _check(lib.gvd_im2col3x3_down_cl(x.data_ptr(), col.data_ptr(), int(F), int(H), int(W), int(Cin), _stream()), lib,
+           "gvd_im2col3x3_down_cl")
+    return linear(col, weight, bias=bias).view(F, Ho * Wo, -1), Ho, Wo
+
+
 def conv_t3(x, B, T, S, weight, bias=None, residual=None):
     """(3,1,1) / pad (1,0,0) temporal convolution of x[B*T, S, C] with weight [Cout, 3*Cin] (K order kt, cin)."""
     if _wants_grad(x, residual):

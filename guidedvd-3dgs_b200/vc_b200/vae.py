@@ -139,3 +139,68 @@ class DecoderB200:
         return self._decode(z)
 
     __call__ = decode
+
+
+class EncoderB200:
+    """VAE encoder (ae_modules.py:363-464) + quant_conv (autoencoder.py:97-102): frames [F, 3, H, W] in [-1, 1] -> the
+    posterior's moments [F, 2 * z_channels, H/8, W/8] (mean, log-variance) -- what `get_latent_z`
+    (VC/utils_vc/diffusion_utils.py:111-116) runs over the 25 conditioning frames before every diffusion round.
+    Inference only.  The 3 image channels travel as 8 (16-byte rows); the Downsample layers use the right/bottom-padded
+    stride-2 im2col (gvd_im2col3x3_down_cl)."""
+
+    def __init__(self, state_dict, device="cuda", ch_mult=(1, 2, 4, 4), num_res_blocks=2):
+        p = _P(state_dict, device)
+        self.dev = device
+        w = state_dict["encoder.conv_in.weight"].detach().to(device)   # [C, 3, 3, 3] -> [C, (ky, kx, 8)]
+        self.in_ch = w.shape[1]
+        w8 = torch.zeros(w.shape[0], 8, 3, 3, dtype=w.dtype, device=device)
+        w8[:, :w.shape[1]] = w
+        self.conv_in = (w8.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(ops.BF16).contiguous(), p.f32("encoder.conv_in.bias"))
+        self.down = []
+        for level in range(len(ch_mult)):
+            blocks = [_ResnetBlock(p, f"encoder.down.{level}.block.{i}") for i in range(num_res_blocks)]
+            if p.has(f"encoder.down.{level}.attn.0.norm.weight"):
+                raise NotImplementedError("attn_resolutions is empty in the ViewCrafter VAE")
+            ds = p.conv3x3(f"encoder.down.{level}.downsample.conv") if level != len(ch_mult) - 1 else None
+            self.down.append((blocks, ds))
+        self.mid = (_ResnetBlock(p, "encoder.mid.block_1"), _AttnBlock(p, "encoder.mid.attn_1"), _ResnetBlock(p, "encoder.mid.block_2"))
+        self.norm_out = p.norm("encoder.norm_out")
+        self.conv_out = p.conv3x3("encoder.conv_out")          # 2 * z_channels = 8 outputs
+        self.quant = p.lin("quant_conv")                       # 1x1, 8 -> 8
+
+    @torch.no_grad()
+    def moments(self, x):
+        F, c, H, W = x.shape
+        h = x.float().permute(0, 2, 3, 1).reshape(F, H * W, c)
+        h = torch.nn.functional.pad(h, (0, 8 - c)).to(ops.BF16).contiguous()
+        h, _, _ = ops.conv3x3(h, F, H, W, *self.conv_in)
+        for blocks, ds in self.down:
+            for blk in blocks:
+                h = blk(h, F, H, W)
+            if ds is not None:
+                h, H, W = ops.conv3x3_down(h, F, H, W, *ds)
+        h = self.mid[0](h, F, H, W)
+        h = self.mid[1](h, F, H * W)
+        h = self.mid[2](h, F, H, W)
+        h = ops.groupnorm(h, *self.norm_out, F, H * W, eps=EPS, silu=2)
+        h, _, _ = ops.conv3x3(h, F, H, W, *self.conv_out)
+        m = ops.linear(h, *self.quant)
+        return m.view(F, H, W, -1).permute(0, 3, 1, 2).float()
+
+    def encode(self, x, scale_factor=0.18215, noise=None, sample=True):
+        """`encode_first_stage` (ddpm3d.py:620-644 + :611-618): scale_factor * posterior.sample() (or the mode).
+        x [F, 3, H, W] or a video [b, 3, t, H, W]; noise: optional N(0, 1) of the latent's shape."""
+        video = x.dim() == 5
+        if video:
+            b, c, t, H, W = x.shape
+            x = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, H, W)
+        m = self.moments(x)
+        zc = m.shape[1] // 2
+        mean, logvar = m[:, :zc], m[:, zc:].clamp(-30.0, 20.0)   # lvdm/distributions.py: DiagonalGaussianDistribution
+        z = mean
+        if sample:
+            if noise is None:
+                noise = torch.randn(mean.shape, device=mean.device)
+            z = mean + torch.exp(0.5 * logvar) * noise
+        z = scale_factor * z
+        return z.view(b, t, *z.shape[1:]).permute(0, 2, 1, 3, 4) if video else z

@@ -90,6 +90,10 @@ GVD_NN_API int gvd_softmax_rows(const void* x, int x_is_bf16, long long ldx, voi
 GVD_NN_API int gvd_im2col3x3_cl(const void* x, void* col, int F, int H, int W, int C, int stride, int upsample,
                                 gvd_nn_stream_t stream);
 
+/* im2col for the VAE encoder's Downsample (lvdm/modules/networks/ae_modules.py:93-106): zero padding on the right and
+ * bottom only, stride 2, no further padding -- x[F, H, W, C] -> col[F, Ho, Wo, 9*C] with Ho = (H - 2) / 2 + 1. */
+GVD_NN_API int gvd_im2col3x3_down_cl(const void* x, void* col, int F, int H, int W, int C, gvd_nn_stream_t stream);
+
 /* im2col for the (3,1,1) / pad (1,0,0) temporal convolutions on x[B, T, S, C] -> col[B, T, S, 3*C], K order (kt, c)
  * (TemporalConvBlock, openaimodel3d.py:246-266). */
 GVD_NN_API int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long long S, int C, gvd_nn_stream_t stream);

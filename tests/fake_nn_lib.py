@@ -232,6 +232,16 @@ class FakeNN:
             cc[:, :, :, tap, :] = xx[:, sy, sx, :] * ok.view(1, Ho, Wo, 1).to(self.act)
         return 0
 
+    def gvd_im2col3x3_down_cl(self, x, col, F, H, W, C, stream):
+        self._count("im2col3x3_down")
+        Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+        xp = torch.nn.functional.pad(self._a(x, F, H, W, C), (0, 0, 0, 1, 0, 1))  # right / bottom only (ae_modules.py:101-102)
+        cc = self._a(col, F, Ho, Wo, 9, C)
+        for tap in range(9):
+            ky, kx = tap // 3, tap % 3
+            cc[:, :, :, tap, :] = xp[:, ky:ky + 2 * Ho:2, kx:kx + 2 * Wo:2, :][:, :Ho, :Wo]
+        return 0
+
     def gvd_col2im3x3_cl(self, dcol, dx, F, H, W, C, stride, up, stream):
         self._count("col2im3x3")
         _, _, Ho, Wo = self._conv_geom(H, W, stride, up)

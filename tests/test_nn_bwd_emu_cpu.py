@@ -211,3 +211,28 @@ def test_emulated_kernels_reject_bad_arguments(emu_lib):
     assert emu_lib.gvd_col2im3x3_cl(p, p, 1, 4, 4, 16, 2, 1, None) == 2
     assert emu_lib.gvd_temporal_attention_bwd(p, p, p, p, p, p, p, 1, 33, 4, 1, 0.125, None) == 2
     assert emu_lib.gvd_layernorm_bwd(p, p, p, p, 0, 64, 1e-5, None) == 0   # empty input is a no-op
+
+
+@pytest.mark.parametrize("H,W", [(8, 6), (9, 7), (2, 2)])
+def test_encoder_downsample_im2col_kernel(monkeypatch, H, W):
+    """csrc/nn_vae.cu executed on the host: the right/bottom-padded stride-2 im2col of the VAE encoder's Downsample
+    (ae_modules.py:93-106) through ops.conv3x3_down vs F.pad(x, (0,1,0,1)) + conv2d(stride=2, padding=0)."""
+    import build_emu
+    import gvd_native
+    from vc_b200 import ops
+
+    lib = C.CDLL(build_emu.build("nn_vae"))
+    lib.gvd_im2col3x3_down_cl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    fake = install_fake(monkeypatch, BF)
+    fake.gvd_im2col3x3_down_cl = lib.gvd_im2col3x3_down_cl
+    monkeypatch.setattr(gvd_native, "nn", lambda: fake)
+    F_, Cin, Cout = 2, 16, 8
+    x = _bf(F_, H * W, Cin, seed=40)
+    w4 = (torch.randn(Cout, Cin, 3, 3, generator=torch.Generator().manual_seed(41)) / (9 * Cin) ** 0.5).to(BF)
+    w = w4.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    y, Ho, Wo = ops.conv3x3_down(x, F_, H, W, w, None)
+    img = torch.nn.functional.pad(x.float().view(F_, H, W, Cin).permute(0, 3, 1, 2), (0, 1, 0, 1))
+    y_ref = torch.nn.functional.conv2d(img, w4.float(), stride=2, padding=0)
+    assert (Ho, Wo) == tuple(y_ref.shape[2:])
+    assert _rel(y, y_ref.permute(0, 2, 3, 1).reshape(F_, Ho * Wo, Cout)) < 1e-2
+    assert lib.gvd_im2col3x3_down_cl(x.data_ptr(), x.data_ptr(), 1, 1, 4, 16, None) == 2   # H < 2

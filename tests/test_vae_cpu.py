@@ -159,3 +159,53 @@ def test_first_stage_dropin_routing(monkeypatch, ref_vae):
         grads.append(zg.grad)
         assert ("ConvolutionBackward" in type(yg.grad_fn).__name__) == (env == "0")
     assert _rel(grads[1], grads[0]) < 1e-4
+
+
+class RefEncoderStage(torch.nn.Module):
+    """AutoencoderKL.encode's arithmetic (autoencoder.py:97-102) around the reference Encoder, parameters re-drawn."""
+
+    def __init__(self, ch=32, seed=6):
+        super().__init__()
+        if unet_ref.REF_VC not in sys.path:
+            sys.path.insert(0, unet_ref.REF_VC)
+        from lvdm.modules.networks.ae_modules import Encoder
+
+        self.encoder = Encoder(ch=ch, out_ch=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0,
+                               in_channels=3, resolution=256, z_channels=4, double_z=True)
+        self.quant_conv = torch.nn.Conv2d(8, 8, 1)
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if p.dim() >= 2:
+                    p.copy_(torch.randn(p.shape, generator=g) / p[0].numel() ** 0.5)
+                elif name.endswith("weight"):
+                    p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g))
+                else:
+                    p.copy_(0.05 * torch.randn(p.shape, generator=g))
+
+    def forward(self, x):
+        return self.quant_conv(self.encoder(x))
+
+
+@pytest.mark.parametrize("H,W", [(32, 48), (24, 40)])
+def test_encoder_moments_and_latent(monkeypatch, H, W):
+    """EncoderB200 (incl. the right/bottom-padded stride-2 Downsample) vs the reference Encoder + quant_conv in fp32, and the
+    sampled latent vs DiagonalGaussianDistribution's arithmetic with the same noise."""
+    from vc_b200.vae import EncoderB200
+
+    fake = install_fake(monkeypatch)
+    ref = RefEncoderStage().eval()
+    ours = EncoderB200(ref.state_dict(), device="cpu")
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, H, W, generator=g) * 2 - 1
+    with torch.no_grad():
+        m_ref = ref(x)
+    m = ours.moments(x)
+    assert m.shape == m_ref.shape == (2, 8, H // 8, W // 8)
+    assert _rel(m, m_ref) < 2e-5 and fake.calls["im2col3x3_down"] == 3
+    noise = torch.randn(2, 4, H // 8, W // 8, generator=g)
+    z = ours.encode(x, scale_factor=SCALE, noise=noise)
+    mean, logvar = m_ref[:, :4], m_ref[:, 4:].clamp(-30.0, 20.0)
+    assert _rel(z, SCALE * (mean + torch.exp(0.5 * logvar) * noise)) < 2e-5
+    zv = ours.encode(x.view(1, 2, 3, H, W).permute(0, 2, 1, 3, 4), scale_factor=SCALE, sample=False)
+    assert zv.shape == (1, 4, 2, H // 8, W // 8) and _rel(zv[0].permute(1, 0, 2, 3), SCALE * mean) < 2e-5
