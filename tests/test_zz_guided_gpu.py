@@ -321,3 +321,24 @@ def test_guided_step_native_vs_reference_sampler_on_gpu(monkeypatch):
     e_ours, e_ref = _rel(xp, outs["fp32"]), _rel(outs["bf16"], outs["fp32"])
     print(f"guided x_prev rel L2: ours vs fp32 {e_ours:.3e}, reference-bf16 vs fp32 {e_ref:.3e}")
     assert e_ours <= 1.25 * e_ref + 5e-3
+
+
+def test_vae_encoder_moments_vs_reference():
+    """vc_b200.vae.EncoderB200 (full width) on the GPU vs the reference Encoder + quant_conv in fp32 / bf16 autocast."""
+    import test_vae_cpu as tv
+    from vc_b200.vae import EncoderB200
+
+    if not tv.HAVE:
+        pytest.skip("oracle/_ref/ViewCrafter/.../ae_modules.py not installed")
+    ref = tv.RefEncoderStage(ch=128).cuda().eval()
+    ours = EncoderB200(ref.state_dict(), device="cuda")
+    x = (torch.rand(3, 3, 160, 256, generator=torch.Generator().manual_seed(4)) * 2 - 1).cuda()
+    with torch.no_grad():
+        m32 = ref(x)
+        with torch.autocast("cuda", dtype=BF):
+            mbf = ref(x).float()
+    m = ours.moments(x)
+    torch.cuda.synchronize()
+    e, e_ref = _rel(m, m32), _rel(mbf, m32)
+    print(f"VAE encoder moments: ours vs fp32 {e:.2e}, reference autocast vs fp32 {e_ref:.2e}")
+    assert m.shape == (3, 8, 20, 32) and e <= 1.25 * e_ref + 2e-3
