@@ -185,6 +185,39 @@ def points():
     return lib
 
 
+# ---- libgvd_train.so (include/gvd_train.h) --------------------------------------------------------------
+TRAIN_SYMBOLS = ("gvd_photometric_loss_scratch_bytes", "gvd_photometric_loss_forward", "gvd_photometric_loss_backward",
+                 "gvd_densification_stats", "gvd_adam_step", "gvd_train_last_error")
+_train = None
+
+
+def bind_train(lib):
+    """argtypes / restypes of include/gvd_train.h (shared with the host build the CPU tests execute)."""
+    vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+    lib.gvd_train_last_error.restype = C.c_char_p
+    lib.gvd_photometric_loss_scratch_bytes.restype = C.c_size_t
+    lib.gvd_photometric_loss_scratch_bytes.argtypes = [i32, i32, i32]
+    lib.gvd_photometric_loss_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
+    lib.gvd_photometric_loss_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.gvd_densification_stats.argtypes = [vp, vp, ll, vp, vp, vp, vp]
+    lib.gvd_adam_step.argtypes = [vp, vp, vp, vp, ll, C.c_double, C.c_double, C.c_double, C.c_double, i32, vp]
+    for n in ("gvd_photometric_loss_forward", "gvd_photometric_loss_backward", "gvd_densification_stats", "gvd_adam_step"):
+        getattr(lib, n).restype = C.c_int
+    return lib
+
+
+def train():
+    """Load libgvd_train.so once; raise loudly when it is absent (there is no fallback)."""
+    global _train
+    if _train is not None:
+        return _train
+    path = lib_path("libgvd_train.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `make -C guidedvd-3dgs_b200/csrc`. No fallback path exists.")
+    _train = bind_train(C.CDLL(path))
+    return _train
+
+
 # ---- libgvd_nn.so (include/gvd_nn.h) --------------------------------------------------------------------
 class GemmArgs(C.Structure):
     _fields_ = [

@@ -9,5 +9,6 @@ tail -15 gpurun_out/guided_pytest.log
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_zz_guided_gpu.py -q --runxfail -k "groupnorm_bwd or temporal_attention_bwd or conv3x3_dx or layernorm" > gpurun_out/guided_memcheck.log 2>&1
 grep -E "ERROR SUMMARY|passed|failed" gpurun_out/guided_memcheck.log | tail -3
 ( timeout 300 python -m pytest tests/test_zz_pcd2img_gpu.py -q -rxXs --runxfail -p no:cacheprovider ) > gpurun_out/pcd2img_pytest.log 2>&1; tail -3 gpurun_out/pcd2img_pytest.log
+( timeout 300 python -m pytest tests/test_zz_train_ops_gpu.py -q -rxXs --runxfail -p no:cacheprovider ) > gpurun_out/train_ops_pytest.log 2>&1; tail -3 gpurun_out/train_ops_pytest.log
 timeout 900 python tools/bench_guided.py --arm both > gpurun_out/guided_bench.jsonl 2> gpurun_out/guided_bench.err
 cat gpurun_out/guided_bench.jsonl; tail -3 gpurun_out/guided_bench.err
