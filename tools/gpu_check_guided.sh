@@ -12,3 +12,5 @@ grep -E "ERROR SUMMARY|passed|failed" gpurun_out/guided_memcheck.log | tail -3
 ( timeout 300 python -m pytest tests/test_zz_train_ops_gpu.py -q -rxXs --runxfail -p no:cacheprovider ) > gpurun_out/train_ops_pytest.log 2>&1; tail -3 gpurun_out/train_ops_pytest.log
 timeout 900 python tools/bench_guided.py --arm both > gpurun_out/guided_bench.jsonl 2> gpurun_out/guided_bench.err
 cat gpurun_out/guided_bench.jsonl; tail -3 gpurun_out/guided_bench.err
+timeout 600 python tools/bench_train_step.py --arm both --iters 100 > gpurun_out/train_step_bench.jsonl 2> gpurun_out/train_step_bench.err
+cat gpurun_out/train_step_bench.jsonl; tail -2 gpurun_out/train_step_bench.err
