@@ -52,21 +52,34 @@ def rewrite(src):
     return src
 
 
-def build(name="nn_backward"):
+def build(name="nn_backward", sources=None, extra_flags=()):
+    """name: a single csrc/<name>.cu, or the library name when `sources` lists several files that link into one .so."""
     os.makedirs(OUT, exist_ok=True)
-    cu = os.path.join(CSRC, name + ".cu")
-    cpp = os.path.join(OUT, name + "_emu.cpp")
+    sources = list(sources or [name + ".cu"])
     so = os.path.join(OUT, f"lib{name}_emu.so")
-    if os.path.exists(so) and os.path.getmtime(so) > max(os.path.getmtime(cu), os.path.getmtime(os.path.join(HERE, "cuda_emu.h")),
-                                                        os.path.getmtime(__file__)):
+    deps = [os.path.join(CSRC, s) for s in sources] + [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cub", "cub.cuh"), __file__]
+    deps += [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
+    if os.path.exists(so) and os.path.getmtime(so) > max(os.path.getmtime(d) for d in deps):
         return so
-    with open(cu) as f:
-        text = rewrite(f.read())
-    with open(cpp, "w") as f:
-        f.write(text)
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", HERE, "-o", so, cpp])
+    cpps = []
+    for src in sources:
+        with open(os.path.join(CSRC, src)) as f:
+            text = rewrite(f.read())
+        cpp = os.path.join(OUT, os.path.splitext(src)[0] + "_emu.cpp")
+        with open(cpp, "w") as f:
+            f.write(text)
+        cpps.append(cpp)
+    # -I CSRC: the rewritten copies live in _build/ but still include their neighbours ("raster_common.cuh")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-DGVD_HOST_EMU", "-D__CUDACC__",
+                           "-x", "c++", "-I", HERE, "-I", CSRC, *extra_flags, "-o", so, *cpps])
     return so
 
 
+RASTER_SOURCES = ["raster_api.cu", "raster_forward.cu", "raster_backward.cu"]
+
+
 if __name__ == "__main__":
-    print(build(*sys.argv[1:]))
+    if sys.argv[1:] == ["raster"]:
+        print(build("raster", RASTER_SOURCES))
+    else:
+        print(build(*sys.argv[1:]))

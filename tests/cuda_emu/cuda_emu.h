@@ -12,10 +12,13 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <string>
 #include <thread>
+#include <tuple>
+#include <algorithm>
 #include <vector>
 
 #define __global__
@@ -25,22 +28,42 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct uint3_emu { unsigned x, y, z; };
-struct uint4 { unsigned x, y, z, w; };
-struct float2 { float x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(8) int2 { int x, y; };
+struct alignas(8) float2 { float x, y; };
+struct float3 { float x, y, z; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+inline int2 make_int2(int a, int b) { return int2{a, b}; }
+inline float2 make_float2(float a, float b) { return float2{a, b}; }
+inline float3 make_float3(float a, float b, float c) { return float3{a, b, c}; }
+inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 
 inline thread_local uint3_emu threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
 using std::max;
 using std::min;
+// CUDA's mixed-signedness overloads
+inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
+inline unsigned min(int a, unsigned b) { return (unsigned)a < b ? (unsigned)a : b; }
+inline unsigned max(unsigned a, int b) { return a > (unsigned)b ? a : (unsigned)b; }
+inline unsigned max(int a, unsigned b) { return (unsigned)a > b ? (unsigned)a : b; }
+inline long long min(long long a, int b) { return a < b ? a : b; }
+inline long long max(long long a, int b) { return a > b ? a : b; }
+inline unsigned long long min(unsigned long long a, unsigned b) { return a < b ? a : b; }
+[[noreturn]] inline void __trap() { abort(); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 
 // ---- bf16 ----
 struct __nv_bfloat16 { uint16_t v; };
@@ -64,6 +87,33 @@ inline float2 __bfloat1622float2(__nv_bfloat162 h) { return float2{__bfloat162fl
 inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{__float2bfloat16(a), __float2bfloat16(b)}; }
 
 // ---- math / memory intrinsics ----
+inline void emu_yield() { std::this_thread::yield(); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+template <class T> inline void __stcs(T* p, T v) { *p = v; }
+template <class T> inline void __stcg(T* p, T v) { *p = v; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __frcp_rn(float a) { return 1.0f / a; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __saturatef(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline unsigned atomicMax(unsigned* p, unsigned v) { std::atomic_ref<unsigned> a(*p); unsigned o = a.load(); while (v > o && !a.compare_exchange_weak(o, v)) {} return o; }
+inline int atomicMax(int* p, int v) { std::atomic_ref<int> a(*p); int o = a.load(); while (v > o && !a.compare_exchange_weak(o, v)) {} return o; }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_or(v); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).exchange(v); }
 inline float __expf(float x) { return expf(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 template <class T> inline T __ldg(const T* p) { return *p; }
@@ -89,14 +139,30 @@ struct EmuBlock {
     std::barrier<> block_bar;
     std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
     std::vector<uint64_t> slots;
+    std::atomic<int> vote[2] = {0, 0};
     EmuBlock(int nthreads) : block_bar(nthreads), slots(nthreads) {
         for (int w = 0; w * 32 < nthreads; ++w) warp_bars.emplace_back(new std::barrier<>(std::min(32, nthreads - w * 32)));
     }
 };
 inline thread_local EmuBlock* emu_blk = nullptr;
 inline thread_local int emu_tid = 0;
+inline thread_local unsigned emu_votes = 0;  // block-wide votes this thread has taken part in (selects the accumulator)
 
 inline void __syncthreads() { emu_blk->block_bar.arrive_and_wait(); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+// barrier + block-wide vote: every thread adds its predicate, reads the total after the barrier, and clears the
+// accumulator after a second barrier (the next vote uses the other accumulator, so a fast thread cannot race the clear)
+inline int __syncthreads_count(int pred) {
+    std::atomic<int>& acc = emu_blk->vote[emu_votes++ & 1];
+    if (pred) acc.fetch_add(1);
+    emu_blk->block_bar.arrive_and_wait();
+    const int r = acc.load();
+    emu_blk->block_bar.arrive_and_wait();
+    acc.store(0);
+    return r;
+}
+inline int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
+inline int __syncthreads_and(int pred) { return __syncthreads_count(!pred) == 0; }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_blk->warp_bars[emu_tid >> 5]->arrive_and_wait(); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     static_assert(sizeof(T) <= 8, "shuffle payload");
@@ -111,6 +177,48 @@ template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     return out;
 }
 
+// generic "every lane publishes a value, then reads what it needs": all warp collectives below are built on it
+template <class T, class F> inline auto emu_warp_exchange(T v, F&& reader) {
+    static_assert(sizeof(T) <= 8, "warp payload");
+    uint64_t raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    emu_blk->slots[emu_tid] = raw;
+    __syncwarp();
+    const int base = emu_tid & ~31;
+    auto get = [&](int lane) { T o; uint64_t r = emu_blk->slots[base + (lane & 31)]; std::memcpy(&o, &r, sizeof(T)); return o; };
+    auto out = reader(get, emu_tid & 31);
+    __syncwarp();
+    return out;
+}
+inline int emu_warp_lanes() { return std::min(32, (int)(blockDim.x * blockDim.y * blockDim.z) - (emu_tid & ~31)); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) {
+    return emu_warp_exchange(v, [&](auto get, int) { return get(src); });
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+    return emu_warp_exchange(v, [&](auto get, int lane) { return lane >= (int)delta ? get(lane - (int)delta) : v; });
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+    return emu_warp_exchange(v, [&](auto get, int lane) { return lane + (int)delta < 32 ? get(lane + (int)delta) : v; });
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    return emu_warp_exchange((unsigned)(pred != 0), [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m |= get(l) << l; return m; });
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    return emu_warp_exchange(v, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m |= get(l); return m; });
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    return emu_warp_exchange(v, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m = std::max(m, get(l)); return m; });
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    return emu_warp_exchange(v, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m += get(l); return m; });
+}
+template <class T> inline unsigned __match_any_sync(unsigned, T v) {
+    return emu_warp_exchange(v, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m |= (unsigned)(get(l) == v) << l; return m; });
+}
+inline unsigned __activemask() { return 0xffffffffu; }
+
 inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
     const int nthreads = (int)(block.x * block.y * block.z);
     for (unsigned bz = 0; bz < grid.z; ++bz)
@@ -123,6 +231,7 @@ inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body)
                     ts.emplace_back([&, t]() {
                         emu_blk = &blk;
                         emu_tid = t;
+                        emu_votes = 0;
                         threadIdx = uint3_emu{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
                         blockIdx = uint3_emu{bx, by, bz};
                         blockDim = block;
@@ -144,3 +253,25 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+enum { cudaFuncAttributePreferredSharedMemoryCarveout = 9, cudaMemcpyDeviceToHost = 2, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3,
+       cudaLaunchAttributeProgrammaticStreamSerialization = 4, cudaSharedmemCarveoutMaxShared = 100, cudaSharedmemCarveoutMaxL1 = 0 };
+typedef struct CUevent_st* cudaEvent_t;
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+struct cudaLaunchAttribute { int id; struct { int programmaticStreamSerializationAllowed; } val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute* attrs; unsigned numAttrs; };
+template <class... Exp, class... Act> inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(Exp...), Act&&... args) {
+    auto tup = std::make_tuple(static_cast<Exp>(args)...);
+    emu_launch(cfg->gridDim, cfg->blockDim, [&]() { std::apply(kernel, tup); });
+    return cudaSuccess;
+}
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }

@@ -1,0 +1,86 @@
+"""The rasterizer's CUDA sources executed on the HOST (tests/cuda_emu: raster_api.cu, raster_forward.cu,
+raster_backward.cu compiled as they are; CUDA threads are OS threads, warp collectives / barriers / atomics keep their
+meaning, the TMA bulk copy + mbarrier pair and the programmatic-dependent-launch intrinsics are replaced by host
+equivalents under GVD_HOST_EMU in raster_common.cuh, CUB's radix sort by a stable sort) through the C ABI, against the
+golden vectors of the compiled REFERENCE (tests/golden/raster_*.npz, produced on a B200 by tests/make_golden.py).
+
+What this pins without a GPU: the whole kernel chain's logic -- preprocess, depth sort, the rect-aware counting sort
+(bin_count / bin_prefix / bin_ranges / bin_fill), both render kernels with their sub-tile culling and batched id
+staging, the transposing-butterfly reduction of the backward, the fused per-Gaussian backward.  Integer buffers are
+compared exactly; floats with the bounds of tests/test_oracle_cpu.py (x86 expf / no FMA contraction differ from the
+GPU's in the last ulp and flip isolated alpha < 1/255 decisions on a 2 000-Gaussian scene)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "guidedvd-3dgs_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import test_oracle_cpu as toc  # noqa: E402
+
+
+@pytest.mark.parametrize("path", toc.GOLDEN, ids=[os.path.basename(p) for p in toc.GOLDEN])
+def test_kernel_chain_matches_reference_golden(path):
+    import raster_emu
+
+    g = np.load(path)
+    _, sc, cam, cot, bg, D, precomp = toc._inputs(g)
+    backward = "d0" not in os.path.basename(path)      # two of the three fixtures run the backward as well (time)
+    o = raster_emu.run(sc, cam, bg, D, cot=cot if backward else None, use_conf=bool(g["use_conf"]), precomp=precomp)
+    P = int(g["P"])
+    assert (o["radii"] != g["radii"]).sum() <= max(1, P // 2000)
+    assert (o["tiles_touched"].astype(np.int64) != g["tiles_touched"].astype(np.int64)).sum() <= max(1, P // 2000)
+    assert abs(o["num_rendered"] - int(g["num_rendered"])) <= 64
+    if o["num_rendered"] == int(g["num_rendered"]):
+        assert (o["point_list"].astype(np.int64) != g["point_list"].astype(np.int64)).mean() < 2e-3
+        # keys = tile << 32 | depth bits: the tile half exactly; the depth half to 2 ulp (this host build does not contract
+        # the view-space z into FMAs as nvcc does -- the ORDER, i.e. point_list above, is what has to agree)
+        ke, kg = o["point_list_keys"].astype(np.uint64), g["point_list_keys"].astype(np.uint64)
+        assert np.array_equal(ke >> np.uint64(32), kg >> np.uint64(32))
+        lo = np.uint64(0xffffffff)
+        assert np.abs((ke & lo).astype(np.int64) - (kg & lo).astype(np.int64)).max() <= 2
+        assert (o["ranges"] != g["ranges"]).sum() == 0
+    assert (o["n_contrib"].reshape(-1).astype(np.int64) != g["n_contrib"].reshape(-1).astype(np.int64)).mean() < 5e-3
+    for k in ("color", "depth", "alpha"):
+        a, b = o[k].astype(np.float64), g[k].astype(np.float64).reshape(o[k].shape)
+        bad = np.abs(a - b) > 1e-4 * np.abs(b) + 1e-5
+        assert bad.mean() < 2e-3, (k, bad.mean())
+    if backward:
+        for k, go in o["grads"].items():
+            gr = g["grad_" + k].astype(np.float64).reshape(go.shape)
+            rel = np.sqrt(((go - gr) ** 2).sum()) / max(np.sqrt((gr ** 2).sum()), 1e-30)
+            assert rel < 5e-3, (k, rel)
+        # untouched Gaussians get exact zeros (the kernel writes them; there is no zero-fill pass)
+        inv = g["radii"] == 0
+        assert all(not np.any(v[inv]) for v in o["grads"].values())
+
+
+def test_everything_behind_the_camera_and_tiny_inputs():
+    import raster_emu
+    import raster_oracle as ro
+    import synth
+
+    sc = ro.to_numpy_scene(synth.synth_scene(64, 1))
+    cam = ro.to_numpy_scene(synth.synth_camera(2, 64, 48))
+    sc["means3D"] = (sc["means3D"] * 0 - np.array(cam["viewmatrix"])[2, :3] * 5.0 + np.asarray(cam["campos"])).astype(np.float32)
+    bg = np.array([0.3, 0.6, 0.9], np.float32)
+    cot = dict(color=np.ones((3, 48, 64), np.float32), depth=np.ones((1, 48, 64), np.float32), alpha=np.ones((1, 48, 64), np.float32))
+    o = raster_emu.run(sc, cam, bg, 3, cot=cot)
+    assert o["num_rendered"] == 0 and (o["radii"] == 0).all()
+    assert np.allclose(o["color"], bg[:, None, None]) and (o["alpha"] == 0).all() and (o["depth"] == 0).all()
+    assert all((v == 0).all() for v in o["grads"].values())
+    # a ragged image (not a multiple of the 16x16 tile) with a handful of Gaussians: same answer as the C oracle
+    sc = ro.to_numpy_scene(synth.synth_scene(40, 3))
+    cam = ro.to_numpy_scene(synth.synth_camera(4, 37, 29))
+    cot = {k: np.random.default_rng(0).normal(size=s).astype(np.float32) for k, s in dict(color=(3, 29, 37), depth=(1, 29, 37), alpha=(1, 29, 37)).items()}
+    o = raster_emu.run(sc, cam, bg, 2, cot=cot, use_conf=True)
+    r = ro.run(sc, cam, bg, 2, cot=cot, use_conf=True)
+    assert o["num_rendered"] == r["num_rendered"] and np.array_equal(o["radii"], r["radii"])
+    if o["num_rendered"]:
+        assert np.array_equal(o["point_list"], r["point_list"]) and np.array_equal(o["ranges"], r["ranges"])
+    for k in ("color", "depth", "alpha"):
+        assert np.abs(o[k] - r[k].reshape(o[k].shape)).max() < 1e-4
