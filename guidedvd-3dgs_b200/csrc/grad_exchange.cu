@@ -3,6 +3,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <ctime>
 #include <string>
 
 #include "../../include/gvd_exchange.h"
@@ -26,6 +27,7 @@ struct Params {
     uint32_t epoch;
 };
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -53,6 +55,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#else  // GVD_HOST_EMU (tests/cuda_emu): ranks are processes sharing host memory; same ordering with C++ atomics
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ float4 ld_peer(const float4* p) { return *p; }
+__device__ __forceinline__ void st_peer(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ unsigned long long global_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+__device__ __forceinline__ void __nanosleep(unsigned) { emu_yield(); }
+#endif
 // Spins until *p has reached `epoch` (wrap-safe); false = gave up.
 __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch, uint32_t* timed_out_word) {
     const unsigned long long t0 = global_ns();

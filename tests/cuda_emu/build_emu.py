@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "guidedvd-3dgs_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-LAUNCH = re.compile(r"(\w+)<<<(.*?)>>>\s*\(", re.S)
+LAUNCH = re.compile(r"([\w:]+(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\(", re.S)  # kernel or kernel<targs>
 DYN_SHARED = re.compile(r"extern\s+__shared__\s+((?:__align__\(\d+\)\s+)?)([\w ]+?)\s+(\w+)\[\];")
 
 
@@ -75,7 +75,7 @@ def build(name="nn_backward", sources=None, extra_flags=()):
     return so
 
 
-RASTER_SOURCES = ["raster_api.cu", "raster_forward.cu", "raster_backward.cu"]
+RASTER_SOURCES = ["raster_api.cu", "raster_forward.cu", "raster_backward.cu", "grad_exchange.cu"]
 
 
 if __name__ == "__main__":

@@ -275,3 +275,12 @@ template <class... Exp, class... Act> inline cudaError_t cudaLaunchKernelEx(cons
     return cudaSuccess;
 }
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 256, n) == 0 ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+// no inter-process mapping on the host build: the multi-rank tests share memory themselves and pass the pointers
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
