@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ dy,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const float* __restrict__ stats, int S, int C, int groups,
-                                                             int rows_per_chunk, float eps, int do_silu,
+                                                             int rows_per_chunk, float eps, int do_silu, long long stat_rows,
                                                              double* __restrict__ partial) {
     extern __shared__ double gn_sh[];  // acc[groups*2] doubles, then mean[groups], rstd[groups] floats
     double* acc = gn_sh;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16
     const int cpg = C / groups, vecs = C / 8;
     for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) acc[i] = 0.0;
     if (threadIdx.x < groups) {
-        const double n = (double)S * cpg;
+        const double n = (double)stat_rows * cpg;  // rows behind the statistics (> S when they were summed across shards)
         const double s = stats[((size_t)f * groups + threadIdx.x) * 2], q = stats[((size_t)f * groups + threadIdx.x) * 2 + 1];
         const double mean = s / n;
         const double var = fmax(q / n - mean * mean, 0.0);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ stats, const double* __restrict__ partial,
                                                            int S, int C, int groups, int nchunks, int rows_per_cta, float eps,
-                                                           int do_silu) {
+                                                           int do_silu, long long stat_rows) {
     extern __shared__ float gn_shf[];  // mean, rstd, m1, m2: [groups] each
     float* smean = gn_shf;
     float* srstd = smean + groups;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
     const int f = blockIdx.y;
     const int cpg = C / groups, vecs = C / 8;
     if (threadIdx.x < groups) {
-        const double n = (double)S * cpg;
+        const double n = (double)stat_rows * cpg;
         const double s = stats[((size_t)f * groups + threadIdx.x) * 2], q = stats[((size_t)f * groups + threadIdx.x) * 2 + 1];
         const double mean = s / n;
         const double var = fmax(q / n - mean * mean, 0.0);
@@ -212,6 +212,18 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
             }
             dout[(size_t)r * vecs] = pack8(o);
         }
+    }
+}
+
+// Fold the per-chunk partial sums of one frame into (sum g, sum g xh) per group: the exchange unit when the rows of a
+// group are spread over several GPUs (the mirror image of gn_fold_kernel in the forward).
+__global__ void __launch_bounds__(256) gn_bwd_fold_kernel(const double* __restrict__ partial, double* __restrict__ sums, int nchunks,
+                                                          int groups) {
+    const int f = blockIdx.x;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+        double a = 0.0;
+        for (int c = 0; c < nchunks; ++c) a += partial[((size_t)f * nchunks + c) * groups * 2 + i];
+        sums[(size_t)f * groups * 2 + i] = a;
     }
 }
 
@@ -550,16 +562,21 @@ size_t gvd_groupnorm_bwd_tmp_bytes(int F, long long S, int groups) {
     return (size_t)F * (gn_bwd_chunks(F, S) + 1) * groups * 2 * sizeof(double);
 }
 
+static int gn_bwd_check(const char* who, int C, int groups, int do_silu) {
+    if (C % groups != 0 || C % 8 != 0 || groups > 128 || do_silu < 0 || do_silu > 2) {
+        g_nn_err_ext = std::string(who) + ": needs C % groups == 0, C % 8 == 0, groups <= 128, do_silu in 0..2";
+        return 2;
+    }
+    return 0;
+}
+
 int gvd_groupnorm_cl_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* beta, const float* stats, int F,
                          long long S, int C, int groups, float eps, int do_silu, void* tmp, size_t tmp_bytes,
                          gvd_nn_stream_t stream_) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (F <= 0 || S <= 0) return 0;
     if (!x || !dy || !dx || !gamma || !beta || !stats || !tmp) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: null pointer"; return 2; }
-    if (C % groups != 0 || C % 8 != 0 || groups > 128 || do_silu < 0 || do_silu > 2) {
-        g_nn_err_ext = "gvd_groupnorm_cl_bwd: needs C % groups == 0, C % 8 == 0, groups <= 128, do_silu in 0..2";
-        return 2;
-    }
+    if (gn_bwd_check("gvd_groupnorm_cl_bwd", C, groups, do_silu)) return 2;
     if (reinterpret_cast<uintptr_t>(tmp) & 7) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: scratch must be 8-byte aligned"; return 2; }
     int nchunks = gn_bwd_chunks(F, S);
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
@@ -567,12 +584,58 @@ int gvd_groupnorm_cl_bwd(const void* x, const void* dy, void* dx, const float* g
     if (tmp_bytes < (size_t)F * nchunks * groups * 2 * sizeof(double)) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: scratch too small"; return 2; }
     double* partial = reinterpret_cast<double*>(tmp);
     gn_bwd_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(double) + groups * 2 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups, rows_per_chunk, eps, do_silu, partial);
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups, rows_per_chunk, eps, do_silu, S, partial);
     gn_bwd_apply_kernel<<<dim3(nchunks, F), 256, groups * 4 * sizeof(float), s>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats, partial, (int)S, C, groups, nchunks,
-        rows_per_chunk, eps, do_silu);
+        rows_per_chunk, eps, do_silu, S);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+int gvd_groupnorm_cl_bwd_sums(const void* x, const void* dy, const float* gamma, const float* beta, const float* stats, double* sums,
+                              int F, long long S, long long stat_rows, int C, int groups, float eps, int do_silu, void* tmp,
+                              size_t tmp_bytes, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (F <= 0) return 0;
+    if (!sums || !stats) { g_nn_err_ext = "gvd_groupnorm_cl_bwd_sums: null pointer"; return 2; }
+    if (gn_bwd_check("gvd_groupnorm_cl_bwd_sums", C, groups, do_silu)) return 2;
+    if (S <= 0) return cudaMemsetAsync(sums, 0, sizeof(double) * F * groups * 2, s) == cudaSuccess ? 0 : 1;  // a shard without rows
+    if (!x || !dy || !gamma || !beta || !tmp || stat_rows < S) { g_nn_err_ext = "gvd_groupnorm_cl_bwd_sums: null pointer or stat_rows < S"; return 2; }
+    if (reinterpret_cast<uintptr_t>(tmp) & 7) { g_nn_err_ext = "gvd_groupnorm_cl_bwd_sums: scratch must be 8-byte aligned"; return 2; }
+    int nchunks = gn_bwd_chunks(F, S);
+    const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
+    nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
+    if (tmp_bytes < (size_t)F * nchunks * groups * 2 * sizeof(double)) { g_nn_err_ext = "gvd_groupnorm_cl_bwd_sums: scratch too small"; return 2; }
+    double* partial = reinterpret_cast<double*>(tmp);
+    gn_bwd_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(double) + groups * 2 * sizeof(float), s>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups, rows_per_chunk, eps, do_silu, stat_rows,
+        partial);
+    gn_bwd_fold_kernel<<<F, 256, 0, s>>>(partial, sums, nchunks, groups);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd_sums: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+int gvd_groupnorm_cl_bwd_apply(const void* x, const void* dy, void* dx, const float* gamma, const float* beta, const float* stats,
+                               const double* sums, int F, long long S, long long stat_rows, int C, int groups, float eps, int do_silu,
+                               gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (F <= 0 || S <= 0) return 0;
+    if (!x || !dy || !dx || !gamma || !beta || !stats || !sums || stat_rows < S) {
+        g_nn_err_ext = "gvd_groupnorm_cl_bwd_apply: null pointer or stat_rows < S";
+        return 2;
+    }
+    if (gn_bwd_check("gvd_groupnorm_cl_bwd_apply", C, groups, do_silu)) return 2;
+    int nchunks = gn_bwd_chunks(F, S);
+    const int rows_per_cta = (int)((S + nchunks - 1) / nchunks);
+    nchunks = (int)((S + rows_per_cta - 1) / rows_per_cta);
+    // the folded sums stand in for a one-chunk partial array
+    gn_bwd_apply_kernel<<<dim3(nchunks, F), 256, groups * 4 * sizeof(float), s>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats, sums, (int)S, C, groups, 1, rows_per_cta,
+        eps, do_silu, stat_rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd_apply: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
 

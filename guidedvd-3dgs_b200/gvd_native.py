@@ -256,7 +256,7 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
               "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention",
               "gvd_ddim_step", "gvd_flash_attention", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply",
               # input-gradient operators of the guided sampler (csrc/nn_backward.cu)
-              "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
+              "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_groupnorm_cl_bwd_sums", "gvd_groupnorm_cl_bwd_apply", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
               "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp",
               "gvd_im2col3x3_down_cl")
 _nn = None
@@ -292,6 +292,9 @@ def nn():
     lib.gvd_groupnorm_bwd_tmp_bytes.restype = C.c_size_t
     lib.gvd_groupnorm_bwd_tmp_bytes.argtypes = [i32, ll, i32]
     lib.gvd_groupnorm_cl_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    lib.gvd_groupnorm_cl_bwd_sums.argtypes = [vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    lib.gvd_groupnorm_cl_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]
+    lib.gvd_groupnorm_cl_bwd_sums.restype = lib.gvd_groupnorm_cl_bwd_apply.restype = C.c_int
     lib.gvd_layernorm_bwd.argtypes = [vp, vp, vp, vp, ll, i32, f32, vp]
     lib.gvd_geglu_bwd.argtypes = [vp, vp, vp, ll, i32, vp]
     lib.gvd_softmax_bwd_rows.argtypes = [vp, vp, vp, ll, ll, i32, vp]

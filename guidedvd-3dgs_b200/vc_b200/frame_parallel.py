@@ -53,6 +53,9 @@ class FramePartition:
         """x[F_r, S, C] -> [T, S_r, C]."""
         if not self.active:
             return x
+        if torch.is_grad_enabled() and x.requires_grad:  # guided sampler: record the adjoint all-to-all (vc_b200.grad)
+            from .grad import ToPixels
+            return ToPixels.apply(x, self)
         Fr, S, Cc = x.shape
         px = self.pixels(S)
         Sr = px[self.rank]
@@ -70,6 +73,9 @@ class FramePartition:
         """y[T, S_r, C] -> [F_r, S, C] (S = total pixels)."""
         if not self.active:
             return y
+        if torch.is_grad_enabled() and y.requires_grad:
+            from .grad import ToFrames
+            return ToFrames.apply(y, self, S)
         T, Sr, Cc = y.shape
         px = self.pixels(S)
         Fr = self.F

@@ -55,6 +55,47 @@ class GroupNorm(Function):
         return dx, None, None, None, None, None, None, None
 
 
+class GroupNormSharded(Function):
+    """GroupNorm whose rows are spread over the ranks of a FramePartition (TemporalConvBlock / TemporalTransformer norms
+    under the frame-sharded plan): the backward needs the mirror-image exchanges (two small all-reduces)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, F, S_local, S_total, part, groups, eps, silu):
+        ctx.save_for_backward(x)
+        ctx.args = (gamma, beta, F, S_local, S_total, part, groups, eps, silu)
+        return ops.groupnorm_sharded(x, gamma, beta, F, S_local, S_total, part, groups, eps, silu)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = ops.groupnorm_sharded_bwd(x, _c(dy), *ctx.args).view_as(x)
+        return (dx,) + (None,) * 9
+
+
+class ToPixels(Function):
+    """FramePartition.to_pixels with its adjoint: the all-to-all back (a re-sharding is a permutation)."""
+
+    @staticmethod
+    def forward(ctx, x, part):
+        ctx.part, ctx.S = part, x.shape[1]
+        return part.to_pixels(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ctx.part.to_frames(_c(dy), ctx.S), None
+
+
+class ToFrames(Function):
+    @staticmethod
+    def forward(ctx, y, part, S):
+        ctx.part = part
+        return part.to_frames(y, S)
+
+    @staticmethod
+    def backward(ctx, dx):
+        return ctx.part.to_pixels(_c(dx)), None, None
+
+
 class LayerNorm(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):

@@ -20,8 +20,9 @@ One guided step:
 dimension of the decoder, so any chunk size gives the same gradients).  `loss_guidance_fn` protocol: SURVEY.md 8b.
 
 One process per GPU (`GuidedPlan`, SURVEY.md section 8e "Guided path"): the conditional and the unconditional U-Net
-forward + backward are independent given the two cotangents, so even ranks evaluate `cond` and odd ranks `uncond`
-(one exchange of the two outputs before the coupled pred_x0 arithmetic, one sum of the two dL/dx after the
+forward + backward are independent given the two cotangents, so the first half of the ranks evaluates `cond`, the second
+half `uncond`, each half with its frames sharded as in the plain sampler's plan and the adjoint exchanges recorded for
+the backward (one gather of the outputs before the coupled pred_x0 arithmetic, one all-reduce of dL/dx after the
 backward); the 25 decoder forward + backward passes are independent frames and are dealt out over ALL ranks (one
 gather of dL/dpred_x0 and of the decoded frames).  Noise is drawn on rank 0 and broadcast.  Everything else (fused
 DDIM update, VJP, rho) is replicated -- it is a few passes over a 256 k-element latent.
@@ -36,29 +37,62 @@ from .sampler import DDIMSampler, _randn
 
 
 class GuidedPlan:
-    """World layout of one guided step: `branch` (0 = cond, 1 = uncond) for the U-Net forward + backward, a contiguous
-    frame slice for the decoder passes.  With an odd world size (or one rank) every rank evaluates both branches."""
+    """World layout of one guided step (one process per GPU).
 
-    def __init__(self, n_frames):
+    U-Net forward + backward: the DenoisePlan layout of the plain sampler -- `cfg_ways` (2 when the world size is even)
+    x `frame_ways` ranks; rank -> (branch: 0 = cond / 1 = uncond, frame slice).  Inside a branch the frames are sharded
+    like at inference (FramePartition: all-to-all re-shard around the temporal layers, summed GroupNorm statistics),
+    with the adjoint exchanges recorded for the backward (vc_b200.grad.ToPixels / ToFrames / GroupNormSharded).
+    Decoder forward + backward: the frames dealt out over ALL ranks.
+    Exchanges per step: one all-gather of the local U-Net outputs, one ragged gather of dL/dpred_x0 and of the decoded
+    frames, one all-reduce of dL/dx (every (branch, frame slice) pair lives on exactly one rank)."""
+
+    def __init__(self, n_frames, model=None):
+        from .frame_parallel import DenoisePlan
+
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
-        self.split_cfg = self.world > 1 and self.world % 2 == 0
-        self.branch = self.rank % 2 if self.split_cfg else None
-        self.frames = split_sizes(n_frames, self.world)
+        self.denoise = DenoisePlan(n_frames)
+        self.part = self.denoise.part
+        self.split_cfg = self.denoise.cfg_ways == 2
+        self.branch = self.denoise.cfg_index if self.split_cfg else None
+        self.frames = split_sizes(n_frames, self.world)       # decoder passes
         self.f0 = sum(self.frames[:self.rank])
         self.f1 = self.f0 + self.frames[self.rank]
+        if model is not None:
+            self.attach(model)
 
-    def exchange_outputs(self, e_local):
-        """e_local = this rank's branch output -> (e_cond, e_uncond), identical on every rank."""
-        both = [torch.empty_like(e_local) for _ in range(self.world)]
-        dist.all_gather(both, e_local.contiguous())
-        return both[0], both[1]  # ranks 0 and 1 hold cond and uncond
+    def attach(self, model):
+        """model: DiffusionModelB200.  Its U-Net runs frame-sharded from now on; the sampler finds the plan on the model."""
+        model.unet.part = self.part
+        model.guided_plan = self
+        return self
 
-    def sum_branches(self, dx_local):
-        """dL/dx of this rank's branch -> sum over the two branches (each branch is replicated world/2 times)."""
-        total = dx_local.clone()
+    def unet_outputs(self, model, x, t, c, uc, **kwargs):
+        """-> (graph-carrying local outputs [list, in cond/uncond order of what THIS rank evaluated], e_cond, e_uncond
+        full clips without graph, identical on every rank)."""
+        if self.split_cfg:
+            mine = [model._local(x, t, c if self.branch == 0 else uc, kwargs.get("fs"))]
+            e_c, e_u = self.denoise.gather_outputs(mine[0].detach().float().contiguous())
+        else:  # odd world: both branches on this rank's frame slice
+            mine = [model._local(x, t, c, kwargs.get("fs")), model._local(x, t, uc, kwargs.get("fs"))]
+            e_c = self.denoise.gather_outputs(mine[0].detach().float().contiguous())[0]
+            e_u = self.denoise.gather_outputs(mine[1].detach().float().contiguous())[0]
+        return mine, e_c.contiguous(), e_u.contiguous()
+
+    def backward(self, mine, de_c, de_u, x):
+        """Cotangents of the full clips -> this rank's slices -> both tapes -> dL/dx summed over the world."""
+        sl = self.part.frame_slice() if self.part.active else slice(None)
+        cots = [de_c if self.branch == 0 else de_u] if self.split_cfg else [de_c, de_u]
+        torch.autograd.backward(mine, [ct[:, :, sl].to(m.dtype).contiguous() for ct, m in zip(cots, mine)], inputs=[x])
+        total = x.grad.detach().float().clone()
         dist.all_reduce(total, op=dist.ReduceOp.SUM)
-        return total / (self.world // 2)
+        return total
+
+    def randn(self, shape, device):
+        z = torch.randn(shape, device=device)
+        dist.broadcast(z, src=0)
+        return z
 
     def gather_frames(self, local, dim=2):
         """Concatenate per-rank frame slices (ragged: 25 frames over 8 ranks = 4,3,...,3) along `dim` on every rank."""
@@ -116,20 +150,18 @@ class DDIMSamplerGuidance(DDIMSampler):
         x_prev = pred_x0 = None
         for j in range(repeat):
             x = x.detach().float().requires_grad_(True)
-            e_mine = None
+            mine = None
             with torch.enable_grad():
-                if gp is not None and gp.split_cfg:   # this rank's branch only; its partner rank runs the other one
-                    e_mine = model.apply_model(x, t, c if gp.branch == 0 else uc, **kwargs)
+                if gp is not None:   # this rank's (branch, frame slice) only
+                    mine, e_cd, e_ud = gp.unet_outputs(model, x, t, c, uc, **kwargs)
                     e_c = e_u = None
                 else:
                     e_c = model.apply_model(x, t, c, **kwargs)
                     e_u = model.apply_model(x, t, uc, **kwargs) if uc is not None else None
             nz = pick(noise, j)
             if nz is None:
-                nz = _randn(model, x.shape, x.device)
-            if e_mine is not None:
-                e_cd, e_ud = gp.exchange_outputs(e_mine.detach().float())
-            else:
+                nz = gp.randn(x.shape, x.device) if gp is not None else _randn(model, x.shape, x.device)
+            if mine is None:
                 e_cd = e_c.detach().float().contiguous()
                 e_ud = None if e_u is None else e_u.detach().float().contiguous()
             x_prev, pred_x0 = ops.ddim_step(x.detach().contiguous(), e_cd, e_ud, nz.float().contiguous(), coef)
@@ -164,10 +196,8 @@ class DDIMSamplerGuidance(DDIMSampler):
                 G = gp.gather_frames(torch.cat(grads, dim=2).float() if grads else empty(pred_x0.shape[1], pred_x0.shape[3:])).contiguous()
             lg.save_pred_x0(d_all, index)
             dx, de_c, de_u = ops.ddim_pred_x0_vjp(e_cd, e_ud, G, coef)
-            if e_mine is not None:
-                cot = de_c if gp.branch == 0 else de_u
-                torch.autograd.backward([e_mine], [cot.to(e_mine.dtype)], inputs=[x])
-                guided = gp.sum_branches(x.grad.detach().float()) + dx
+            if mine is not None:
+                guided = gp.backward(mine, de_c, de_u, x) + dx
             else:
                 if e_u is None:
                     torch.autograd.backward([e_c], [de_c.to(e_c.dtype)], inputs=[x])
@@ -183,6 +213,6 @@ class DDIMSamplerGuidance(DDIMSampler):
             x_prev = x_prev - rho * guided
             rz = pick(recur_noise, j)
             if rz is None:
-                rz = _randn(model, x.shape, x.device)
+                rz = gp.randn(x.shape, x.device) if gp is not None else _randn(model, x.shape, x.device)
             x = float(np.sqrt(beta_t)) * x_prev + float(np.sqrt(np.float32(1) - beta_t)) * rz
         return x_prev.detach(), pred_x0.detach()

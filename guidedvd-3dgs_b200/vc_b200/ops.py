@@ -105,7 +105,7 @@ def groupnorm_sharded(x, gamma, beta, F, S_local, S_total, part, groups=32, eps=
     """GroupNorm whose rows are spread over the ranks of `part` (vc_b200.frame_parallel.FramePartition): local
     (sum, sumsq) -> one all-reduce of F*groups*2 floats -> local normalisation with the global statistics."""
     if _wants_grad(x):
-        raise RuntimeError("groupnorm_sharded: the frame-sharded plan is inference-only (no backward)")
+        return _grad().GroupNormSharded.apply(x, gamma, beta, F, S_local, S_total, part, groups, eps, int(silu))
     lib = _n.nn()
     Cc = x.shape[-1]
     x = x.contiguous()
@@ -196,7 +196,7 @@ def conv_t3(x, B, T, S, weight, bias=None, residual=None):
     col = torch.empty(B * T * S, 3 * Cin, dtype=BF16, device=x.device)
     _check(lib.gvd_im2col_t3_cl(x.data_ptr(), col.data_ptr(), int(B), int(T), int(S), int(Cin), _stream()), lib,
            "gvd_im2col_t3_cl")
-    return linear(col, weight, bias=bias, residual=residual).view(B * T, S, -1)
+    return linear(col, weight, bias=bias, residual=residual).view(B * T, S, weight.shape[0])
 
 
 def temporal_attention(q, k, v, B, T, S, H, scale):
@@ -347,6 +347,32 @@ def groupnorm_bwd(x, dy, gamma, beta, F, S, groups=32, eps=1e-5, silu=0):
     _check(lib.gvd_groupnorm_cl_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                     int(F), int(S), int(Cc), int(groups), float(eps), int(silu), tmp[1].data_ptr(), nby, _stream()),
            lib, "gvd_groupnorm_cl_bwd")
+    return dx
+
+
+def groupnorm_sharded_bwd(x, dy, gamma, beta, F, S_local, S_total, part, groups=32, eps=1e-5, silu=0):
+    """dx of `groupnorm_sharded`: local (sum x, sum x^2) -> all-reduce -> local (sum g, sum g xh) -> all-reduce -> local dx."""
+    lib = _n.nn()
+    Cc = x.shape[-1]
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    Sl = int(max(S_local, 1))
+    nfl = int(lib.gvd_groupnorm_tmp_floats(int(F), Sl, int(groups)))
+    nby = int(lib.gvd_groupnorm_bwd_tmp_bytes(int(F), Sl, int(groups)))
+    tmpf = torch.empty(nfl, dtype=torch.float32, device=x.device)
+    tmpd = torch.empty(nby // 8 + 1, dtype=torch.float64, device=x.device)
+    stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
+    _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S_local), int(Cc), int(groups), tmpf.data_ptr(), nfl,
+                                      _stream()), lib, "gvd_groupnorm_cl_stats")
+    part.sum_stats(stats)
+    sums = torch.empty(F * groups * 2, dtype=torch.float64, device=x.device)
+    _check(lib.gvd_groupnorm_cl_bwd_sums(x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), sums.data_ptr(),
+                                         int(F), int(S_local), int(S_total), int(Cc), int(groups), float(eps), int(silu), tmpd.data_ptr(),
+                                         nby, _stream()), lib, "gvd_groupnorm_cl_bwd_sums")
+    part.sum_stats(sums)
+    _check(lib.gvd_groupnorm_cl_bwd_apply(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                          sums.data_ptr(), int(F), int(S_local), int(S_total), int(Cc), int(groups), float(eps), int(silu),
+                                          _stream()), lib, "gvd_groupnorm_cl_bwd_apply")
     return dx
 
 

@@ -276,9 +276,9 @@ class UNetB200:
     def forward_with_grad(self, x, timesteps, context, fs=None):
         """Same network with the tape on: when `x.requires_grad`, every operator records its input-gradient
         (vc_b200.grad), so `y.backward(gradient=g, inputs=x)` yields dL/dx -- the call the guided sampler makes
-        (ddim_guidance.py:264-265,309).  Single GPU (no frame partition)."""
-        if self.part is not None and self.part.active:
-            raise RuntimeError("forward_with_grad: the frame-sharded plan is inference-only")
+        (ddim_guidance.py:264-265,309).  Under a frame partition the input is the full clip and x.grad comes back non-zero
+        in this rank's frames only: the temporal layers' re-shardings and sharded GroupNorms record their adjoint
+        exchanges, the caller sums x.grad over the ranks (vc_b200.guided.GuidedPlan)."""
         with torch.enable_grad():
             return self._forward(x, timesteps, context, fs)
 

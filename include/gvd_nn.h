@@ -144,6 +144,17 @@ GVD_NN_API int gvd_groupnorm_cl_bwd(const void* x, const void* dy, void* dx, con
                                     const float* stats, int F, long long S, int C, int groups, float eps, int do_silu,
                                     void* tmp, size_t tmp_bytes, gvd_nn_stream_t stream);
 
+/* The same backward split at its reduction, for a group whose rows are sharded across GPUs (the mirror image of
+ * gvd_groupnorm_cl_stats / _apply): `_sums` writes (sum g, sum g*xh) per (frame, group) of the LOCAL rows into
+ * sums[F, groups, 2] (float64), the caller adds the shards' sums (one all-reduce), `_apply` forms dx of the local rows.
+ * stats = the already summed forward statistics, stat_rows = total rows behind them. */
+GVD_NN_API int gvd_groupnorm_cl_bwd_sums(const void* x, const void* dy, const float* gamma, const float* beta, const float* stats,
+                                         double* sums, int F, long long S, long long stat_rows, int C, int groups, float eps,
+                                         int do_silu, void* tmp, size_t tmp_bytes, gvd_nn_stream_t stream);
+GVD_NN_API int gvd_groupnorm_cl_bwd_apply(const void* x, const void* dy, void* dx, const float* gamma, const float* beta,
+                                          const float* stats, const double* sums, int F, long long S, long long stat_rows, int C,
+                                          int groups, float eps, int do_silu, gvd_nn_stream_t stream);
+
 /* LayerNorm backward over the last dimension: x, dy, dx [rows, C] bf16. */
 GVD_NN_API int gvd_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, long long rows, int C,
                                  float eps, gvd_nn_stream_t stream);

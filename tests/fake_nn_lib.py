@@ -159,6 +159,40 @@ class FakeNN:
         self._a(dx, F, S, C).copy_(out.view(F, S, C).to(self.act))
         return 0
 
+    def _gn_bwd_terms(self, x, dy, gamma, beta, stats, F, S, stat_rows, C, groups, eps, silu):
+        cpg = C // groups
+        mean, rstd = self._stats_to_moments(stats, F, groups, stat_rows * cpg, eps)
+        gm = self._f(gamma, C)
+        _, xh, z = self._gn(self._a(x, F, S, C).float(), gm, self._f(beta, C), mean, rstd, C, groups, 0)
+        g = self._a(dy, F, S, C).float() * gm
+        if silu:
+            zz = self._rnd(z) if silu == 1 else z
+            sg = torch.sigmoid(zz)
+            g = g * (sg * (1 + zz * (1 - sg)))
+        return g.view(F, S, groups, cpg), xh.view(F, S, groups, cpg), rstd
+
+    def gvd_groupnorm_cl_bwd_sums(self, x, dy, gamma, beta, stats, sums, F, S, stat_rows, C, groups, eps, silu, tmp, tmp_bytes, stream):
+        self._count("groupnorm_bwd_sums")
+        out = self._t(sums, F * groups * 2, torch.float64).view(F, groups, 2)
+        if S <= 0:
+            out.zero_()
+            return 0
+        gg, xg, _ = self._gn_bwd_terms(x, dy, gamma, beta, stats, F, S, stat_rows, C, groups, eps, silu)
+        out[..., 0] = gg.double().sum(dim=(1, 3))
+        out[..., 1] = (gg * xg).double().sum(dim=(1, 3))
+        return 0
+
+    def gvd_groupnorm_cl_bwd_apply(self, x, dy, dx, gamma, beta, stats, sums, F, S, stat_rows, C, groups, eps, silu, stream):
+        self._count("groupnorm_bwd_apply")
+        if S <= 0:
+            return 0
+        gg, xg, rstd = self._gn_bwd_terms(x, dy, gamma, beta, stats, F, S, stat_rows, C, groups, eps, silu)
+        sm = self._t(sums, F * groups * 2, torch.float64).view(F, groups, 2) / (stat_rows * (C // groups))
+        m1, m2 = sm[..., 0].float().view(F, 1, groups, 1), sm[..., 1].float().view(F, 1, groups, 1)
+        out = rstd.view(F, 1, groups, 1) * (gg - m1 - xg * m2)
+        self._a(dx, F, S, C).copy_(out.view(F, S, C).to(self.act))
+        return 0
+
     # ---- LayerNorm / GEGLU / softmax ----
     def gvd_layernorm(self, x, y, gamma, beta, rows, C, eps, stream):
         self._count("layernorm")

@@ -3,7 +3,8 @@ backward on alternating ranks, decoder passes dealt out by frame, one exchange o
 dL/dpred_x0 and of the decoded frames, one sum of the two dL/dx.  Every rank must end with the x_prev / pred_x0 of the
 single-process step.  The library underneath is the pointer-level stand-in of tests/fake_nn_lib.py (host memory), so
 everything that differs between 1 and N ranks is exercised here; world sizes 2, 3 (odd: no CFG split) and 4 (more
-ranks than frames: one rank owns no frame)."""
+ranks than frames: one rank owns no frame; cfg 2 x frames 2: the U-Net itself is frame-sharded, with the adjoint
+all-to-alls and the two-stage sharded GroupNorm backward)."""
 import contextlib
 import os
 import socket
@@ -34,8 +35,16 @@ def _install_fake():
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception:  # report instead of leaving the peers (and the test) waiting for a collective
+        import traceback
+        q.put((rank, "error", traceback.format_exc()[-1500:]))
+
+
+def _worker_body(rank, world, port, q):
     torch.set_num_threads(2)
-    _install_fake()
+    fake = _install_fake()
     import unet_ref
     from test_guided_cpu import StubDecoder, StubGuidance
     from vc_b200.guided import DDIMSamplerGuidance, GuidedPlan
@@ -45,7 +54,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ref, cfg = unet_ref.build_reference_unet(model_channels=64, device="cpu")
-    T, h, w, index = 3, 8, 8, 22
+    T, h, w, index = 3, 16, 16, 22   # 2 x 2 pixels at the coarsest level: no rank is left without a pixel of a temporal layer
     x, cc, ctx, ctx_uc = unet_ref.synth_inputs(T, h, w, device="cpu")
     cond, uc = {"c_concat": [cc], "c_crossattn": [ctx]}, {"c_concat": [cc], "c_crossattn": [ctx_uc]}
     fs = torch.tensor([10])
@@ -65,12 +74,13 @@ def _worker(rank, world, port, q):
 
     lg1 = StubGuidance(targets, masks, 2)
     xp1, p01 = step(lg1)                                 # single-process answer (no plan)
-    model.guided_plan = GuidedPlan(T)
+    GuidedPlan(T, model)
     lgn = StubGuidance(targets, masks, 2)
     xpn, p0n = step(lgn)
     rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
     gp = model.guided_plan
-    q.put((rank, rel(xpn, xp1), rel(p0n, p01), rel(lgn.saved[-1][1], lg1.saved[-1][1]), gp.branch, (gp.f0, gp.f1)))
+    sharded_ok = (fake.calls.get("groupnorm_bwd_sums", 0) > 0) == gp.part.active   # the sharded GroupNorm backward ran iff frames are sharded
+    q.put((rank, rel(xpn, xp1), rel(p0n, p01), rel(lgn.saved[-1][1], lg1.saved[-1][1]), gp.branch, (gp.f0, gp.f1), sharded_ok))
     dist.destroy_process_group()
 
 
@@ -86,12 +96,21 @@ def test_guided_plan_matches_single_process(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in range(world))
+    res = []
+    for _ in range(world):
+        item = q.get(timeout=900)
+        if item[1] == "error":
+            for p in procs:
+                p.terminate()
+            pytest.fail(f"rank {item[0]}: {item[2]}")
+        res.append(item)
+    res.sort()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     frames = [r[5] for r in res]
     assert frames[0][0] == 0 and frames[-1][1] == 3 and all(a[1] == b[0] for a, b in zip(frames, frames[1:]))
-    for rank, e_xp, e_p0, e_img, branch, _ in res:
-        assert branch == (rank % 2 if world % 2 == 0 else None)
+    for rank, e_xp, e_p0, e_img, branch, _, sharded_ok in res:
+        assert sharded_ok
+        assert branch == ((rank // (world // 2)) if world % 2 == 0 else None)
         assert e_xp < 2e-5 and e_p0 < 2e-5 and e_img < 2e-5, (rank, e_xp, e_p0, e_img)  # fp32 sums in a different order

@@ -236,3 +236,59 @@ def test_encoder_downsample_im2col_kernel(monkeypatch, H, W):
     assert (Ho, Wo) == tuple(y_ref.shape[2:])
     assert _rel(y, y_ref.permute(0, 2, 3, 1).reshape(F_, Ho * Wo, Cout)) < 1e-2
     assert lib.gvd_im2col3x3_down_cl(x.data_ptr(), x.data_ptr(), 1, 1, 4, 16, None) == 2   # H < 2
+
+
+@pytest.mark.parametrize("silu", [0, 2])
+def test_groupnorm_bwd_split_at_its_reduction(monkeypatch, emu_lib, silu):
+    """gvd_groupnorm_cl_bwd_sums / _apply (rows of a group sharded over GPUs) executed on the host: two row shards with
+    their statistics and sums added up by hand reproduce the one-piece backward; an empty shard contributes zeros."""
+    import gvd_native
+    from vc_b200 import ops
+
+    vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+    emu_lib.gvd_groupnorm_cl_bwd_sums.argtypes = [vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    emu_lib.gvd_groupnorm_cl_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]
+    fake = install_fake(monkeypatch, BF)
+    for name in ("gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_groupnorm_cl_bwd_sums", "gvd_groupnorm_cl_bwd_apply"):
+        setattr(fake, name, getattr(emu_lib, name))
+    monkeypatch.setattr(gvd_native, "nn", lambda: fake)
+    F, S, Cc = 2, 90, 64
+    x, dy = _bf(F, S, Cc, seed=1, scale=2.0) + 0.5, _bf(F, S, Cc, seed=2)
+    g = torch.Generator().manual_seed(3)
+    gamma, beta = 1 + 0.1 * torch.randn(Cc, generator=g), 0.1 * torch.randn(Cc, generator=g)
+    whole = ops.groupnorm_bwd(x, dy, gamma, beta, F, S, 32, 1e-5, silu)
+
+    cut = 37
+    shards = [(x[:, :cut].contiguous(), dy[:, :cut].contiguous()), (x[:, cut:].contiguous(), dy[:, cut:].contiguous())]
+    # FramePartition.sum_stats stand-in: call k of a backward is the k-th all-reduce (0: statistics, 1: backward sums).
+    # Run the shards once to collect their local statistics, add them; again for the sums; a third time for dx.
+    totals = {}
+
+    class Collect:
+        def __init__(self, sid):
+            self.sid, self.calls = sid, 0
+
+        def sum_stats(self, t):
+            k = self.calls
+            self.calls += 1
+            if (k, "total") in totals:
+                t.copy_(totals[(k, "total")])
+            else:
+                totals[(k, self.sid)] = t.clone()
+            return t
+
+    for sid, (xs, ds) in enumerate(shards):   # statistics of each shard
+        ops.groupnorm_sharded_bwd(xs, ds, gamma, beta, F, xs.shape[1], S, Collect(sid), 32, 1e-5, silu)
+    totals[(0, "total")] = totals[(0, 0)] + totals[(0, 1)]
+    for k in [key for key in totals if key[0] == 1]:   # sums were formed with partial statistics: recompute
+        del totals[k]
+    for sid, (xs, ds) in enumerate(shards):
+        ops.groupnorm_sharded_bwd(xs, ds, gamma, beta, F, xs.shape[1], S, Collect(sid), 32, 1e-5, silu)
+    totals[(1, "total")] = totals[(1, 0)] + totals[(1, 1)]
+    parts = [ops.groupnorm_sharded_bwd(xs, ds, gamma, beta, F, xs.shape[1], S, Collect(sid), 32, 1e-5, silu) for sid, (xs, ds) in enumerate(shards)]
+    assert _rel(torch.cat(parts, dim=1), whole) < 4e-3
+    # a shard without rows writes zero sums (what a rank with no pixel of a coarse level contributes)
+    sums = torch.full((F * 32 * 2,), 5.0, dtype=torch.float64)
+    stats = torch.zeros(F * 32 * 2)
+    assert emu_lib.gvd_groupnorm_cl_bwd_sums(None, None, None, None, stats.data_ptr(), sums.data_ptr(), F, 0, S, Cc, 32, 1e-5, silu, None, 0, None) == 0
+    assert float(sums.abs().max()) == 0.0
