@@ -207,6 +207,29 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// Binary erosion / dilation of N masks [N, H, W] with a rectangular structuring element given as the window offsets
+// [lo, hi] it covers around a pixel on each axis (scipy.ndimage.binary_erosion / binary_dilation with np.ones((k, k)),
+// border_value = 0: utils/viewcrafter_wrapper.py:602-647).  Non-zero input = set; output is 0 / 1 in float.
+__global__ void __launch_bounds__(256) morph_rect_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int H, int W,
+                                                         int lo_y, int hi_y, int lo_x, int hi_x, int dilate) {
+    const long long total = N * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const float* img = in + (i / ((long long)H * W)) * (long long)H * W;
+        bool r = !dilate;  // erosion: all set (outside the image counts as unset); dilation: any set
+        for (int dy = lo_y; dy <= hi_y && r != (bool)dilate; ++dy) {
+            const int yy = y + dy;
+            for (int dx = lo_x; dx <= hi_x; ++dx) {
+                const int xx = x + dx;
+                const bool set = yy >= 0 && yy < H && xx >= 0 && xx < W && img[(long long)yy * W + xx] != 0.f;
+                if (dilate ? set : !set) { r = dilate; break; }
+            }
+        }
+        out[i] = r ? 1.f : 0.f;
+    }
+}
+
 int grid_for(long long n) {
     long long g = (n + 255) / 256;
     const long long cap = 148 * 8;
@@ -265,6 +288,16 @@ int gvd_densification_stats(const float* means2D_grad, const int* radii, long lo
     if (P == 0) return 0;
     if (!means2D_grad || !radii || !xyz_gradient_accum || !denom || !max_radii2D) { g_train_err = "gvd_densification_stats: null pointer"; return 2; }
     densification_stats_kernel<<<grid_for(P), 256, 0, s>>>(means2D_grad, radii, P, xyz_gradient_accum, denom, max_radii2D);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_mask_morphology(const float* in, float* out, long long N, int H, int W, int lo_y, int hi_y, int lo_x, int hi_x, int dilate,
+                        gvd_train_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (N < 0 || H <= 0 || W <= 0 || lo_y > hi_y || lo_x > hi_x) { g_train_err = "gvd_mask_morphology: needs N >= 0, H, W > 0, lo <= hi"; return 2; }
+    if (N == 0) return 0;
+    if (!in || !out || in == out) { g_train_err = "gvd_mask_morphology: null pointer or in-place call (the window reads neighbours)"; return 2; }
+    morph_rect_kernel<<<grid_for(N * H * W), 256, 0, s>>>(in, out, N, H, W, lo_y, hi_y, lo_x, hi_x, dilate ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -187,7 +187,7 @@ def points():
 
 # ---- libgvd_train.so (include/gvd_train.h) --------------------------------------------------------------
 TRAIN_SYMBOLS = ("gvd_photometric_loss_scratch_bytes", "gvd_photometric_loss_forward", "gvd_photometric_loss_backward",
-                 "gvd_densification_stats", "gvd_adam_step", "gvd_train_last_error")
+                 "gvd_densification_stats", "gvd_adam_step", "gvd_mask_morphology", "gvd_train_last_error")
 _train = None
 
 
@@ -201,7 +201,8 @@ def bind_train(lib):
     lib.gvd_photometric_loss_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.gvd_densification_stats.argtypes = [vp, vp, ll, vp, vp, vp, vp]
     lib.gvd_adam_step.argtypes = [vp, vp, vp, vp, ll, C.c_double, C.c_double, C.c_double, C.c_double, i32, vp]
-    for n in ("gvd_photometric_loss_forward", "gvd_photometric_loss_backward", "gvd_densification_stats", "gvd_adam_step"):
+    lib.gvd_mask_morphology.argtypes = [vp, vp, ll, i32, i32, i32, i32, i32, i32, i32, vp]
+    for n in ("gvd_photometric_loss_forward", "gvd_photometric_loss_backward", "gvd_densification_stats", "gvd_adam_step", "gvd_mask_morphology"):
         getattr(lib, n).restype = C.c_int
     return lib
 

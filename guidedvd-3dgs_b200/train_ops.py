@@ -6,6 +6,8 @@
                                 one fused forward and one fused backward launch
   add_densification_stats       scene/gaussian_model.py:524-527 + train_baseline.py:109 without boolean-mask indexing
                                 (each `x[mask]` of the reference is a nonzero() and a host synchronisation)
+  mask_erosion, mask_dilation,  utils/viewcrafter_wrapper.py:602-647 (scipy.ndimage on the CPU, one mask at a time) on device
+  decide_unobserved_regions     tensors, any batch of masks in one launch
   FusedAdam                     torch.optim.Adam(eps=1e-15) semantics and state layout (`step`, `exp_avg`, `exp_avg_sq`), so
                                 the reference's optimizer surgery at densification (gaussian_model.py:379-470) keeps working
 
@@ -105,6 +107,38 @@ def add_densification_stats(means2D_grad, radii, xyz_gradient_accum, denom, max_
     with torch.cuda.device(g.device):
         _check(lib.gvd_densification_stats(g.data_ptr(), r.data_ptr(), P, xyz_gradient_accum.data_ptr(), denom.data_ptr(),
                                            max_radii2D.data_ptr(), _stream()), "gvd_densification_stats")
+
+
+def _morph(mask, size, dilate):
+    lib = _n.train()
+    m = mask.float().contiguous()
+    if m.dim() < 2:
+        raise ValueError("mask must be [..., H, W]")
+    H, W = m.shape[-2:]
+    N = m.numel() // (H * W) if H * W else 0
+    out = torch.empty_like(m)
+    c = size // 2   # scipy centres a size-k structure at index k // 2; dilation uses the mirrored window
+    lo, hi = (-c, size - 1 - c) if not dilate else (-(size - 1 - c), c)
+    with torch.cuda.device(m.device):
+        _check(lib.gvd_mask_morphology(m.data_ptr(), out.data_ptr(), N, H, W, lo, hi, lo, hi, int(dilate), _stream()), "gvd_mask_morphology")
+    return out.to(mask.dtype)
+
+
+def mask_erosion(mask, size=3):
+    """ViewCrafterWrapper.mask_erosion (utils/viewcrafter_wrapper.py:617-619) on device masks [..., H, W], any batch."""
+    return _morph(mask, size, False)
+
+
+def mask_dilation(mask, size=5):
+    """ViewCrafterWrapper.mask_dilation (:621-624)."""
+    return _morph(mask, size, True)
+
+
+def decide_unobserved_regions(gs_render_results):
+    """utils/viewcrafter_wrapper.py:602-615: pixels no Gaussian covered (rendering exactly 0), eroded by 3, dilated by 5.
+    [N, 3, H, W] in [0, 1] -> [N, 1, H, W] float masks, without the trip through numpy / scipy."""
+    empty = (gs_render_results.sum(1) == 0.).to(torch.float32)
+    return mask_dilation(mask_erosion(empty, 3), 5).unsqueeze(1)
 
 
 class FusedAdam(torch.optim.Optimizer):

@@ -57,6 +57,13 @@ GVD_TRAIN_API int gvd_densification_stats(const float* means2D_grad, const int* 
 GVD_TRAIN_API int gvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr,
                                 double beta1, double beta2, double eps, int step, gvd_train_stream_t stream);
 
+/* Binary erosion (dilate = 0) / dilation (dilate = 1) of N float masks [N, H, W] (non-zero = set) with a rectangular
+ * structuring element covering the offsets [lo_y, hi_y] x [lo_x, hi_x] around each pixel, outside the image = unset:
+ * scipy.ndimage.binary_erosion / binary_dilation(structure=np.ones((k, k))) as utils/viewcrafter_wrapper.py:602-647 applies
+ * them on the CPU, one mask at a time, to the rendered guidance masks of every diffusion round.  out != in. */
+GVD_TRAIN_API int gvd_mask_morphology(const float* in, float* out, long long N, int H, int W, int lo_y, int hi_y, int lo_x,
+                                      int hi_x, int dilate, gvd_train_stream_t stream);
+
 GVD_TRAIN_API const char* gvd_train_last_error(void);
 
 #ifdef __cplusplus

@@ -96,3 +96,17 @@ def test_fused_adam_and_densification_stats():
     r_maxr[vis] = torch.max(r_maxr[vis], radii[vis].float())
     train_ops.add_densification_stats(grad, radii, accum, denom, maxr)
     assert torch.allclose(accum, r_accum[:, 0], rtol=1e-6, atol=0) and torch.equal(denom, r_denom[:, 0]) and torch.equal(maxr, r_maxr)
+
+
+def test_mask_morphology_matches_scipy_on_gpu():
+    import train_ops
+    from scipy import ndimage
+
+    rng = np.random.default_rng(7)
+    masks = (rng.random((25, 320, 512)) > 0.4).astype(np.float32)
+    t = torch.from_numpy(masks).cuda()
+    for k, dilate in ((3, False), (5, True), (5, False), (10, True)):
+        fn = ndimage.binary_dilation if dilate else ndimage.binary_erosion
+        want = np.stack([fn(m, structure=np.ones((k, k))).astype(np.float32) for m in masks[:4]])
+        got = (train_ops.mask_dilation if dilate else train_ops.mask_erosion)(t, k)
+        assert np.array_equal(got[:4].cpu().numpy(), want), (k, dilate)
