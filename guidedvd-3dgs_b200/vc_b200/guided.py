@@ -65,6 +65,7 @@ class GuidedPlan:
     def attach(self, model):
         """model: DiffusionModelB200.  Its U-Net runs frame-sharded from now on; the sampler finds the plan on the model."""
         model.unet.part = self.part
+        model.plan = self.denoise      # un-guided steps on the same model take the plain sampler's sharded path
         model.guided_plan = self
         return self
 

@@ -81,6 +81,14 @@ def _worker_body(rank, world, port, q):
     lgn = StubGuidance(targets, masks, recur)
     xpn, p0n = step(lgn)
     rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    # an un-guided step on the same (now sharded) model still returns the full clip, equal to the single-process one
+    plain_n = sampler.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
+                                    guidance_rescale=0.7, fs=fs, noise=noises[0])[0]
+    model.plan, part, model.unet.part = None, model.unet.part, None
+    plain_1 = sampler.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
+                                    guidance_rescale=0.7, fs=fs, noise=noises[0])[0]
+    model.unet.part = part
+    assert plain_n.shape == plain_1.shape and rel(plain_n, plain_1) < 2e-5
     gp = model.guided_plan
     sharded_ok = (fake.calls.get("groupnorm_bwd_sums", 0) > 0) == gp.part.active   # the sharded GroupNorm backward ran iff frames are sharded
     q.put((rank, rel(xpn, xp1), rel(p0n, p01), rel(lgn.saved[-1][1], lg1.saved[-1][1]), gp.branch, (gp.f0, gp.f1), sharded_ok))
