@@ -1,7 +1,7 @@
 """Drop-ins for the per-iteration pieces of the reference's 3DGS training step that sit around the rasterizer
 (SURVEY.md section 8f row f3), computed by the sm_100a kernels behind include/gvd_train.h:
 
-  l1_loss, ssim                 same names / arguments as utils/loss_utils.py:18-20,46-82 (mask=None, window 11, mean)
+  l1_loss, l1_loss_mask, ssim   same names / arguments as utils/loss_utils.py:18-28,46-82 (window 11, mean; optional mask)
   photometric_loss              (1 - lambda) * l1_loss + lambda * (1 - ssim) as train_baseline.py:82-83 combines them,
                                 one fused forward and one fused backward launch
   add_densification_stats       scene/gaussian_model.py:524-527 + train_baseline.py:109 without boolean-mask indexing
@@ -81,10 +81,22 @@ def l1_loss(network_output, gt, return_map=False):
     return _PhotometricLoss.apply(network_output, gt)[0]
 
 
+def l1_loss_mask(network_output, gt, mask=None):
+    """utils/loss_utils.py:24-28: without a mask the plain L1 mean (the training loops' call); with one, the masked mean
+    of the evaluation code (three elementwise torch launches, not worth a kernel)."""
+    if mask is None:
+        return l1_loss(network_output, gt)
+    return torch.abs((network_output - gt) * mask).sum() / mask.sum()
+
+
 def ssim(img1, img2, mask=None, window_size=11, size_average=True):
-    """utils/loss_utils.py:46-82 for the arguments the training loops use (no mask, 11x11 window, global mean)."""
-    if mask is not None or window_size != 11 or not size_average:
-        raise NotImplementedError("train_ops.ssim covers the training-loop call ssim(image, gt); other variants are evaluation code")
+    """utils/loss_utils.py:46-82 (11x11 window, global mean).  With a mask both images are blended towards 1 outside it
+    first (:50-52), exactly as the reference does before its convolutions."""
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("train_ops.ssim: the reference's callers use window_size=11, size_average=True")
+    if mask is not None:
+        img1 = img1 * mask + (1 - mask)
+        img2 = img2 * mask + (1 - mask)
     return _PhotometricLoss.apply(img1, img2)[1]
 
 

@@ -36,8 +36,14 @@ def main():
         loss.backward()
         xs = img.clone().requires_grad_(True)
         ref.ssim(xs, gt).backward()
+        # the evaluation code's masked variants (train_guidedvd.py:691; loss_utils.py:24-28,50-52)
+        mask = (torch.rand(1, H, W, generator=torch.Generator().manual_seed(77 + seed)) > 0.3).float()
+        xm = img.clone().requires_grad_(True)
+        sm = ref.ssim(xm, gt, mask)
+        sm.backward()
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"loss_{name}.npz"), l1=l1.item(), ssim=s.item(), loss=loss.item(),
-                            grad=x.grad.numpy(), grad_ssim=xs.grad.numpy())
+                            grad=x.grad.numpy(), grad_ssim=xs.grad.numpy(), ssim_masked=sm.item(), grad_ssim_masked=xm.grad.numpy(),
+                            l1_masked=ref.l1_loss_mask(img, gt, mask).item())
         print(name, "l1", l1.item(), "ssim", s.item())
 
 
