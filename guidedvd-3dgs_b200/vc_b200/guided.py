@@ -95,6 +95,17 @@ class GuidedPlan:
         dist.broadcast(z, src=0)
         return z
 
+    def gather_decoder_results(self, decoded, grads, pred_x0):
+        """This rank's decoded frames and dL/dpred_x0 slices (lists of [1, C, n, H, W] chunks, possibly empty) -> the full
+        clips on every rank.  A rank that owns no frame learns the image size from its peers (one 3-int all-reduce)."""
+        dims = torch.tensor(list(decoded[0].shape[1:2]) + list(decoded[0].shape[3:]) if decoded else [0, 0, 0], dtype=torch.int64,
+                            device=pred_x0.device)
+        dist.all_reduce(dims, op=dist.ReduceOp.MAX)
+        ci, H, W = (int(v) for v in dims.tolist())
+        d_local = torch.cat(decoded, dim=2) if decoded else pred_x0.new_zeros(1, ci, 0, H, W)
+        g_local = torch.cat(grads, dim=2).float() if grads else pred_x0.new_zeros(1, pred_x0.shape[1], 0, *pred_x0.shape[3:])
+        return self.gather_frames(d_local), self.gather_frames(g_local).contiguous()
+
     def gather_frames(self, local, dim=2):
         """Concatenate per-rank frame slices (ragged: 25 frames over 8 ranks = 4,3,...,3) along `dim` on every rank."""
         fmax = max(self.frames)
@@ -109,13 +120,6 @@ class GuidedPlan:
 
 def _rms(t):
     return (t.float() * t.float()).mean().sqrt().item()
-
-
-def gp_image_size(gp, like, hw):
-    """Decoded image size (H, W) known to every rank, including one that owns no frame: max over ranks of a 2-vector."""
-    v = torch.tensor([0, 0] if hw is None else [int(hw[0]), int(hw[1])], dtype=torch.int64, device=like.device)
-    dist.all_reduce(v, op=dist.ReduceOp.MAX)
-    return v.tolist()
 
 
 class DDIMSamplerGuidance(DDIMSampler):
@@ -187,14 +191,7 @@ class DDIMSamplerGuidance(DDIMSampler):
             if gp is None:
                 d_all, G = torch.cat(decoded, dim=2), torch.cat(grads, dim=2).float().contiguous()
             else:
-                empty = lambda ch, hw: pred_x0.new_zeros(1, ch, 0, *hw)  # noqa: E731  (a rank may own no frame)
-                hw_img = decoded[0].shape[3:] if decoded else None
-                if hw_img is None:  # learn the image size from a peer: sizes travel with the gather below
-                    hw_img = tuple(int(v) for v in gp_image_size(gp, pred_x0, None))
-                else:
-                    gp_image_size(gp, pred_x0, hw_img)
-                d_all = gp.gather_frames(torch.cat(decoded, dim=2) if decoded else empty(3, hw_img))
-                G = gp.gather_frames(torch.cat(grads, dim=2).float() if grads else empty(pred_x0.shape[1], pred_x0.shape[3:])).contiguous()
+                d_all, G = gp.gather_decoder_results(decoded, grads, pred_x0)
             lg.save_pred_x0(d_all, index)
             dx, de_c, de_u = ops.ddim_pred_x0_vjp(e_cd, e_ud, G, coef)
             if mine is not None:
