@@ -43,7 +43,7 @@ def _worker(rank, world, port, q):
 
 
 def _worker_body(rank, world, port, q):
-    torch.set_num_threads(2)
+    torch.set_num_threads(1 if world == 8 else 2)
     fake = _install_fake()
     import unet_ref
     from test_guided_cpu import StubDecoder, StubGuidance
@@ -57,7 +57,7 @@ def _worker_body(rank, world, port, q):
     # frame-sharded worlds need >= frame_ways pixels at the coarsest level (16x16 -> 2x2); the pure CFG split runs the small
     # latent with two recurrences instead
     (h, w, recur) = (8, 8, 2) if world == 2 else (16, 16, 1)
-    T, index = 3, 22
+    T, index = (4 if world == 8 else 3), 22   # world 8 = cfg 2 x frames 4: one frame per rank of a branch, four ranks without a decoder frame
     x, cc, ctx, ctx_uc = unet_ref.synth_inputs(T, h, w, device="cpu")
     cond, uc = {"c_concat": [cc], "c_crossattn": [ctx]}, {"c_concat": [cc], "c_crossattn": [ctx_uc]}
     fs = torch.tensor([10])
@@ -95,7 +95,7 @@ def _worker_body(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_guided_plan_matches_single_process(world):
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ViewCrafter", "lvdm", "modules", "networks", "openaimodel3d.py")):
         pytest.skip("oracle/_ref/ViewCrafter not installed")
@@ -120,7 +120,7 @@ def test_guided_plan_matches_single_process(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     frames = [r[5] for r in res]
-    assert frames[0][0] == 0 and frames[-1][1] == 3 and all(a[1] == b[0] for a, b in zip(frames, frames[1:]))
+    assert frames[0][0] == 0 and frames[-1][1] == (4 if world == 8 else 3) and all(a[1] == b[0] for a, b in zip(frames, frames[1:]))
     for rank, e_xp, e_p0, e_img, branch, _, sharded_ok in res:
         assert sharded_ok
         assert branch == ((rank // (world // 2)) if world % 2 == 0 else None)
