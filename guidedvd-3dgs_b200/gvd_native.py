@@ -263,6 +263,50 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
 _nn = None
 
 
+def _nn_signatures():
+    vp, ll, i32, f32, sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
+    I, S = C.c_int, C.c_size_t  # return types
+    return {  # name: (restype, argtypes) -- include/gvd_nn.h
+        "gvd_nn_last_error": (C.c_char_p, []),
+        "gvd_gemm_bf16": (I, [C.POINTER(GemmArgs), vp]),
+        "gvd_groupnorm_tmp_floats": (S, [i32, ll, i32]),
+        "gvd_groupnorm_cl": (I, [vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, sz, vp]),
+        "gvd_groupnorm_cl_stats": (I, [vp, vp, i32, ll, i32, i32, vp, sz, vp]),
+        "gvd_groupnorm_cl_apply": (I, [vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]),
+        "gvd_layernorm": (I, [vp, vp, vp, vp, ll, i32, f32, vp]),
+        "gvd_geglu": (I, [vp, vp, ll, i32, vp]),
+        "gvd_softmax_rows": (I, [vp, i32, ll, vp, ll, ll, i32, vp]),
+        "gvd_im2col3x3_cl": (I, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "gvd_im2col3x3_down_cl": (I, [vp, vp, i32, i32, i32, i32, vp]),
+        "gvd_im2col_t3_cl": (I, [vp, vp, i32, i32, ll, i32, vp]),
+        "gvd_temporal_attention": (I, [vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]),
+        "gvd_flash_attention": (I, [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]),
+        "gvd_ddim_step": (I, [C.POINTER(DdimArgs), vp]),
+        "gvd_groupnorm_bwd_tmp_bytes": (S, [i32, ll, i32]),
+        "gvd_groupnorm_cl_bwd": (I, [vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, sz, vp]),
+        "gvd_groupnorm_cl_bwd_sums": (I, [vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp, sz, vp]),
+        "gvd_groupnorm_cl_bwd_apply": (I, [vp, vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]),
+        "gvd_layernorm_bwd": (I, [vp, vp, vp, vp, ll, i32, f32, vp]),
+        "gvd_geglu_bwd": (I, [vp, vp, vp, ll, i32, vp]),
+        "gvd_softmax_bwd_rows": (I, [vp, vp, vp, ll, ll, i32, vp]),
+        "gvd_col2im3x3_cl": (I, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "gvd_col2im_t3_cl": (I, [vp, vp, i32, i32, ll, i32, vp]),
+        "gvd_temporal_attention_bwd": (I, [vp, vp, vp, vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]),
+        "gvd_ddim_pred_x0_vjp": (I, [C.POINTER(DdimVjpArgs), vp]),
+    }
+
+
+def bind_nn(lib, partial=False):
+    """restype / argtypes of include/gvd_nn.h on a loaded library.  partial=True: bind whatever subset the library exports
+    (the host builds of single source files that the CPU tests execute)."""
+    for name, (res, args) in _nn_signatures().items():
+        if partial and not hasattr(lib, name):
+            continue
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
 def nn():
     """Load libgvd_nn.so once; raise loudly when it is absent (there is no fallback)."""
     global _nn
@@ -271,45 +315,5 @@ def nn():
     path = lib_path("libgvd_nn.so")
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: build it with `make -C guidedvd-3dgs_b200/csrc`. No fallback path exists.")
-    lib = C.CDLL(path)
-    lib.gvd_nn_last_error.restype = C.c_char_p
-    lib.gvd_gemm_bf16.restype = C.c_int
-    lib.gvd_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
-    vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
-    lib.gvd_groupnorm_tmp_floats.restype = C.c_size_t
-    lib.gvd_groupnorm_tmp_floats.argtypes = [i32, ll, i32]
-    lib.gvd_groupnorm_cl.argtypes = [vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
-    lib.gvd_groupnorm_cl_stats.argtypes = [vp, vp, i32, ll, i32, i32, vp, C.c_size_t, vp]
-    lib.gvd_groupnorm_cl_apply.argtypes = [vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]
-    lib.gvd_layernorm.argtypes = [vp, vp, vp, vp, ll, i32, f32, vp]
-    lib.gvd_geglu.argtypes = [vp, vp, ll, i32, vp]
-    lib.gvd_softmax_rows.argtypes = [vp, i32, ll, vp, ll, ll, i32, vp]
-    lib.gvd_im2col3x3_cl.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
-    lib.gvd_im2col_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
-    lib.gvd_temporal_attention.argtypes = [vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
-    lib.gvd_ddim_step.argtypes = [C.POINTER(DdimArgs), vp]
-    lib.gvd_flash_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]
-    lib.gvd_flash_attention.restype = C.c_int
-    lib.gvd_groupnorm_bwd_tmp_bytes.restype = C.c_size_t
-    lib.gvd_groupnorm_bwd_tmp_bytes.argtypes = [i32, ll, i32]
-    lib.gvd_groupnorm_cl_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
-    lib.gvd_groupnorm_cl_bwd_sums.argtypes = [vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp, C.c_size_t, vp]
-    lib.gvd_groupnorm_cl_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, ll, ll, i32, i32, f32, i32, vp]
-    lib.gvd_groupnorm_cl_bwd_sums.restype = lib.gvd_groupnorm_cl_bwd_apply.restype = C.c_int
-    lib.gvd_layernorm_bwd.argtypes = [vp, vp, vp, vp, ll, i32, f32, vp]
-    lib.gvd_geglu_bwd.argtypes = [vp, vp, vp, ll, i32, vp]
-    lib.gvd_softmax_bwd_rows.argtypes = [vp, vp, vp, ll, ll, i32, vp]
-    lib.gvd_col2im3x3_cl.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
-    lib.gvd_col2im_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
-    lib.gvd_temporal_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
-    lib.gvd_ddim_pred_x0_vjp.argtypes = [C.POINTER(DdimVjpArgs), vp]
-    lib.gvd_im2col3x3_down_cl.argtypes = [vp, vp, i32, i32, i32, i32, vp]
-    lib.gvd_im2col3x3_down_cl.restype = C.c_int
-    for n in ("gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows", "gvd_col2im3x3_cl",
-              "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp"):
-        getattr(lib, n).restype = C.c_int
-    for n in ("gvd_groupnorm_cl", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply", "gvd_layernorm", "gvd_geglu", "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl",
-              "gvd_temporal_attention", "gvd_ddim_step"):
-        getattr(lib, n).restype = C.c_int
-    _nn = lib
-    return lib
+    _nn = bind_nn(C.CDLL(path))
+    return _nn

@@ -128,6 +128,7 @@ template <class T> inline T emu_atomic_min(T* p, T v) {
 }
 inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { return emu_atomic_min(p, v); }
 inline int atomicMin(int* p, int v) { return emu_atomic_min(p, v); }
+inline long long __double2ll_rn(double d) { return llrint(d); }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 // round-to-nearest double arithmetic that the compiler must not contract into FMAs (build_emu.py passes -ffp-contract=off)
 inline double __dadd_rn(double a, double b) { return a + b; }
