@@ -212,6 +212,12 @@ inline unsigned __reduce_or_sync(unsigned, unsigned v) {
 inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     return emu_warp_exchange(v, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m = std::max(m, get(l)); return m; });
 }
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    return emu_warp_exchange(v, [&](auto get, int) { unsigned m = ~0u; for (int l = 0; l < emu_warp_lanes(); ++l) m = std::min(m, get(l)); return m; });
+}
+inline int __reduce_min_sync(unsigned, int v) {
+    return emu_warp_exchange(v, [&](auto get, int) { int m = 0x7fffffff; for (int l = 0; l < emu_warp_lanes(); ++l) m = std::min(m, get(l)); return m; });
+}
 inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     return emu_warp_exchange(v, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < emu_warp_lanes(); ++l) m += get(l); return m; });
 }
