@@ -5,11 +5,25 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/gvd_nn.h"
 
 extern thread_local std::string g_nn_err_ext;
+
+// nn_fast.cu: re-indexed variants, off unless GVD_NN_FAST=1 (not yet timed on a GPU)
+bool gvd_fast_geglu(const void* h, void* out, long long rows, int D, cudaStream_t s);
+bool gvd_fast_im2col3x3(const void* x, void* col, int F, int H, int W, int C, int Ho, int Wo, int stride, int up, cudaStream_t s);
+bool gvd_fast_im2col_t3(const void* x, void* col, int B, int T, long long S, int C, cudaStream_t s);
+static int g_nn_fast = -1;  // -1: not decided yet (GVD_NN_FAST), 0 / 1 afterwards or through gvd_nn_set_fast
+static bool nn_fast_enabled() {
+    if (g_nn_fast < 0) {
+        const char* e = getenv("GVD_NN_FAST");
+        g_nn_fast = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_nn_fast == 1;
+}
 
 namespace {
 
@@ -463,6 +477,12 @@ int grid_for(long long n, int block = 256, int cap = 148 * 16) {
 
 extern "C" {
 
+int gvd_nn_set_fast(int on) {
+    const int was = nn_fast_enabled() ? 1 : 0;
+    if (on == 0 || on == 1) g_nn_fast = on;
+    return was;
+}
+
 int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* beta, int F, long long S, int C, int groups,
                      float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
@@ -542,6 +562,7 @@ int gvd_geglu(const void* h, void* out, long long rows, int D, gvd_nn_stream_t s
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (rows <= 0) return 0;
     if (D % 2) { g_nn_err_ext = "gvd_geglu: D must be even"; return 2; }
+    if (nn_fast_enabled() && gvd_fast_geglu(h, out, rows, D, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     geglu_kernel<<<grid_for(rows * (D / 2)), 256, 0, s>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)out, rows, D);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -564,6 +585,7 @@ int gvd_im2col3x3_cl(const void* x, void* col, int F, int H, int W, int C, int s
     const int Ho = (Hin + 2 - 3) / stride + 1, Wo = (Win + 2 - 3) / stride + 1;
     const long long total = (long long)F * Ho * Wo * 9 * (C / 8);
     if (total <= 0) return 0;
+    if (nn_fast_enabled() && gvd_fast_im2col3x3(x, col, F, H, W, C, Ho, Wo, stride, upsample, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     im2col3x3_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, F, H, W, C, Ho, Wo, stride, upsample);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -573,6 +595,7 @@ int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long long S, int C,
     if (C % 8) { g_nn_err_ext = "gvd_im2col_t3_cl: C must be a multiple of 8"; return 2; }
     const long long total = (long long)B * T * S * 3 * (C / 8);
     if (total <= 0) return 0;
+    if (nn_fast_enabled() && gvd_fast_im2col_t3(x, col, B, T, S, C, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     im2col_t3_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, B, T, S, C);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

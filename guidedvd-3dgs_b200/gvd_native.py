@@ -259,7 +259,7 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
               # input-gradient operators of the guided sampler (csrc/nn_backward.cu)
               "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_groupnorm_cl_bwd_sums", "gvd_groupnorm_cl_bwd_apply", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
               "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp",
-              "gvd_im2col3x3_down_cl")
+              "gvd_im2col3x3_down_cl", "gvd_nn_set_fast")
 _nn = None
 
 
@@ -268,6 +268,7 @@ def _nn_signatures():
     I, S = C.c_int, C.c_size_t  # return types
     return {  # name: (restype, argtypes) -- include/gvd_nn.h
         "gvd_nn_last_error": (C.c_char_p, []),
+        "gvd_nn_set_fast": (I, [i32]),
         "gvd_gemm_bf16": (I, [C.POINTER(GemmArgs), vp]),
         "gvd_groupnorm_tmp_floats": (S, [i32, ll, i32]),
         "gvd_groupnorm_cl": (I, [vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, sz, vp]),

@@ -51,6 +51,9 @@ class FakeNN:
     def gvd_nn_last_error(self):
         return b"fake"
 
+    def gvd_nn_set_fast(self, on):
+        return 0
+
     # ---- GEMM ----
     def gvd_gemm_bf16(self, args, stream):
         self._count("gemm")

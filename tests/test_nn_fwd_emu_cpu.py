@@ -30,7 +30,7 @@ def emu_lib():
     import build_emu
     import gvd_native
 
-    return gvd_native.bind_nn(C.CDLL(build_emu.build("nn_kernels")), partial=True)
+    return gvd_native.bind_nn(C.CDLL(build_emu.build("nn_kernels", ["nn_kernels.cu", "nn_fast.cu"])), partial=True)
 
 
 def _both(monkeypatch, lib, fn):
@@ -175,3 +175,51 @@ def test_ddim_step_kernels_match_reference_golden(monkeypatch, emu_lib):
         t = lambda name: torch.from_numpy(g[f"{name}_{k}"]).float().contiguous()  # noqa: E731
         x_prev, pred_x0 = ops.ddim_step(t("x"), t("e_c"), t("e_u"), t("noise"), coef)
         assert _rel(x_prev, t("x_prev")) < 5e-6 and _rel(pred_x0, t("pred_x0")) < 5e-6
+
+
+def test_fast_variants_are_bit_identical(monkeypatch, emu_lib):
+    """csrc/nn_fast.cu (GVD_NN_FAST=1: vectorised GEGLU, 32-bit-indexed im2col kernels) against the kernels they replace:
+    the same bits, on shapes that exercise row / vector boundaries, stride 2 and the fused upsampling."""
+    import gvd_native
+    from vc_b200 import ops
+
+    fake = install_fake(monkeypatch, BF)
+    for name in FWD + ("gvd_nn_set_fast",):
+        setattr(fake, name, getattr(emu_lib, name))
+    monkeypatch.setattr(gvd_native, "nn", lambda: fake)
+    lib = emu_lib
+
+    def both(fn):
+        was = lib.gvd_nn_set_fast(0)
+        a = fn()
+        lib.gvd_nn_set_fast(1)
+        b = fn()
+        lib.gvd_nn_set_fast(was)
+        return a, b
+
+    for rows, D in ((21, 128), (7, 1280), (130, 8)):
+        h = _bf(rows, 2 * D, seed=rows, scale=1.5)
+        a, b = both(lambda: ops.geglu(h))
+        assert torch.equal(a, b), (rows, D)
+    for (F_, H, W, Cin, stride, up) in ((2, 6, 5, 16, 1, 0), (1, 7, 8, 8, 2, 0), (3, 5, 4, 24, 1, 1)):
+        x = _bf(F_, H * W, Cin, seed=H)
+        Hin, Win = (2 * H, 2 * W) if up else (H, W)
+        Ho, Wo = (Hin - 1) // stride + 1, (Win - 1) // stride + 1
+        outs = []
+        for fast in (0, 1):
+            lib.gvd_nn_set_fast(fast)
+            c = torch.full((F_ * Ho * Wo, 9 * Cin), 3.0, dtype=BF)
+            assert lib.gvd_im2col3x3_cl(x.data_ptr(), c.data_ptr(), F_, H, W, Cin, stride, up, None) == 0
+            outs.append(c)
+        assert torch.equal(outs[0], outs[1]), (F_, H, W, Cin, stride, up)
+    for (B, T, S, Cin) in ((1, 5, 7, 16), (2, 3, 9, 8)):
+        x = _bf(B * T, S, Cin, seed=T)
+        outs = []
+        for fast in (0, 1):
+            lib.gvd_nn_set_fast(fast)
+            c = torch.full((B * T * S, 3 * Cin), 3.0, dtype=BF)
+            assert lib.gvd_im2col_t3_cl(x.data_ptr(), c.data_ptr(), B, T, S, Cin, None) == 0
+            outs.append(c)
+        assert torch.equal(outs[0], outs[1])
+    lib.gvd_nn_set_fast(0)
+    assert lib.gvd_nn_set_fast(7) == 0   # any other value only queries

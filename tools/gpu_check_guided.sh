@@ -14,3 +14,4 @@ timeout 900 python tools/bench_guided.py --arm both > gpurun_out/guided_bench.js
 cat gpurun_out/guided_bench.jsonl; tail -3 gpurun_out/guided_bench.err
 timeout 600 python tools/bench_train_step.py --arm both --iters 100 > gpurun_out/train_step_bench.jsonl 2> gpurun_out/train_step_bench.err
 cat gpurun_out/train_step_bench.jsonl; tail -2 gpurun_out/train_step_bench.err
+timeout 300 python tools/bench_nn_fast.py > gpurun_out/nn_fast_bench.json 2> gpurun_out/nn_fast_bench.err; cat gpurun_out/nn_fast_bench.json; ( timeout 300 python -m pytest tests/test_zz_nn_fast_gpu.py -q -rxXs --runxfail -p no:cacheprovider ) 2>&1 | tail -2
