@@ -16,6 +16,8 @@ extern thread_local std::string g_nn_err_ext;
 bool gvd_fast_geglu(const void* h, void* out, long long rows, int D, cudaStream_t s);
 bool gvd_fast_im2col3x3(const void* x, void* col, int F, int H, int W, int C, int Ho, int Wo, int stride, int up, cudaStream_t s);
 bool gvd_fast_im2col_t3(const void* x, void* col, int B, int T, long long S, int C, cudaStream_t s);
+bool gvd_fast_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S, int H, float scale,
+                                 cudaStream_t s);
 static int g_nn_fast = -1;  // -1: not decided yet (GVD_NN_FAST), 0 / 1 afterwards or through gvd_nn_set_fast
 static bool nn_fast_enabled() {
     if (g_nn_fast < 0) {
@@ -606,6 +608,7 @@ int gvd_temporal_attention(const void* q, const void* k, const void* v, void* ou
     if (T > 32 || T <= 0) { g_nn_err_ext = "gvd_temporal_attention: needs 1 <= T <= 32"; return 2; }
     const long long warps = (long long)B * S * H;
     if (warps <= 0) return 0;
+    if (nn_fast_enabled() && gvd_fast_temporal_attention(q, k, v, out, B, T, S, H, scale, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     temporal_attn_kernel<<<(unsigned)((warps + TA_WARPS - 1) / TA_WARPS), TA_WARPS * 32, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                     (const __nv_bfloat16*)v, (__nv_bfloat16*)out, B, T, S, H, scale);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -221,5 +221,9 @@ def test_fast_variants_are_bit_identical(monkeypatch, emu_lib):
             assert lib.gvd_im2col_t3_cl(x.data_ptr(), c.data_ptr(), B, T, S, Cin, None) == 0
             outs.append(c)
         assert torch.equal(outs[0], outs[1])
+    for T in (25, 32, 3, 1):
+        q, k, v = (_bf(T, 6, 2 * 64, seed=50 + i + T) for i in range(3))
+        a, b = both(lambda: ops.temporal_attention(q, k, v, 1, T, 6, 2, 0.125))
+        assert torch.equal(a, b), T
     lib.gvd_nn_set_fast(0)
     assert lib.gvd_nn_set_fast(7) == 0   # any other value only queries

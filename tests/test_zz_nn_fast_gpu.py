@@ -35,3 +35,6 @@ def test_fast_variants_bit_identical_on_gpu():
     wt = torch.zeros(8, 3 * 320, dtype=BF, device="cuda")
     a, b = both(lambda: ops.conv_t3(x, 1, 5, 72 * 128, wt, None))
     assert torch.equal(a, b)
+    q, k, v = (torch.randn(25, 2000, 5 * 64, generator=g).to(BF).cuda() for _ in range(3))
+    a, b = both(lambda: ops.temporal_attention(q, k, v, 1, 25, 2000, 5, 0.125))
+    assert torch.equal(a, b)

@@ -1,5 +1,6 @@
 """A/B timing of csrc/nn_fast.cu against the kernels it replaces, at the C3 shapes of the U-Net (25 frames, 72x128):
-GEGLU of the ds1 / ds2 / ds4 feed-forwards, 3x3 im2col at ds1 (320 and 640 channels), temporal im2col at ds1.
+GEGLU of the ds1 / ds2 / ds4 feed-forwards, 3x3 im2col at ds1 (320 and 640 channels), temporal im2col at ds1, temporal
+attention at ds1 / ds2.
 Prints one JSON line: per kernel, microseconds and achieved GB/s (algorithmic bytes) for both variants.
 usage: python tools/bench_nn_fast.py     NOT yet run on hardware."""
 import json
@@ -47,6 +48,12 @@ def main():
     col = torch.empty(F * S, 3 * 320, dtype=BF, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     cases["im2col_t3_ds1"] = (lambda: lib.gvd_im2col_t3_cl(x.data_ptr(), col.data_ptr(), 1, F, S, 320, st), F * S * 320 * 2 * 4)
+    for name, Sx, Hh in (("temporal_attention_ds1", S, 5), ("temporal_attention_ds2", S // 4, 10)):
+        qkv = [torch.randn(F, Sx, Hh * 64, device="cuda").to(BF) for _ in range(3)]
+        o = torch.empty_like(qkv[0])
+        st = torch.cuda.current_stream().cuda_stream
+        cases[name] = (lambda qkv=qkv, o=o, Sx=Sx, Hh=Hh: lib.gvd_temporal_attention(qkv[0].data_ptr(), qkv[1].data_ptr(), qkv[2].data_ptr(),
+                                                                                     o.data_ptr(), 1, F, Sx, Hh, 0.125, st), F * Sx * Hh * 64 * 2 * 4)
     res = {}
     for name, (fn, nbytes) in cases.items():
         row = {}
