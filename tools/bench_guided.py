@@ -31,8 +31,14 @@ def main():
     ap.add_argument("--decode-frames", type=int, default=5)
     ap.add_argument("--mc", type=int, default=320, help="U-Net model_channels (320 = full size)")
     ap.add_argument("--vae-ch", type=int, default=128)
+    ap.add_argument("--dry-cpu", action="store_true",
+                    help="walk the script on the CPU over the tests' stand-in of the library (host-side check of this tool; no timing value)")
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cpu") if a.dry_cpu else torch.device("cuda", 0)
+    if a.dry_cpu:
+        import pytest
+        import test_unet_grad_cpu
+        test_unet_grad_cpu.install_fake(pytest.MonkeyPatch())
     T, (h, w) = a.frames, a.latent
     ref, cfg = unet_ref.build_reference_unet(model_channels=a.mc, device=dev)
     vae = tv.RefFirstStage(ch=a.vae_ch).to(dev).eval()
@@ -48,6 +54,11 @@ def main():
 
     def timed(step):
         step()
+        if a.dry_cpu:
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                step()
+            return (time.perf_counter() - t0) / a.steps * 1e3
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.reset_peak_memory_stats()
@@ -61,7 +72,7 @@ def main():
     def line(arm, ms):
         print(json.dumps({"metric": "guided DDIM steps/sec", "impl": arm, "value": round(1e3 / ms, 4), "unit": "steps/s",
                           "ms_per_step": round(ms, 1), "tflops_per_s": round(flops / ms / 1e9, 1), "dtype": "bf16",
-                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+                          "peak_mem_gb": None if a.dry_cpu else round(torch.cuda.max_memory_allocated() / 1e9, 1),
                           "config": {"workload": "C4 guided", "frames": T, "latent": [h, w], "cfg": 7.5, "recur_steps": 1,
                                      "unet_model_channels": a.mc, "vae_ch": a.vae_ch,
                                      "decode_frames_per_call": a.decode_frames if arm == "ours" else 1}}), flush=True)
@@ -86,7 +97,8 @@ def main():
         line("ours", ms)
         print(f"# ours: wall {time.perf_counter() - t0:.1f} s", file=sys.stderr)
         del model, dec, s
-        torch.cuda.empty_cache()
+        if not a.dry_cpu:
+            torch.cuda.empty_cache()
     if a.arm in ("reference", "both"):
         class PerFrame(torch.nn.Module):
             def __init__(self):
@@ -106,12 +118,12 @@ def main():
         lg = tg.StubGuidance(targets, masks, 1)
 
         def step():
-            with torch.autocast("cuda", dtype=torch.bfloat16):
+            with torch.autocast("cpu" if a.dry_cpu else "cuda", dtype=torch.bfloat16):
                 s.p_sample_ddim(x, cond, ts, index=index, unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
                                 guidance_rescale=0.7, fs=fs, loss_guidance_fn=lg)
         try:
             line("reference", timed(step))
-        except torch.cuda.OutOfMemoryError as ex:
+        except torch.OutOfMemoryError as ex:
             print(json.dumps({"impl": "reference", "unavailable": "out of memory: " + str(ex)[:120]}))
 
 

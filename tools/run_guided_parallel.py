@@ -28,12 +28,21 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--decode-frames", type=int, default=5)
     ap.add_argument("--skip-single", action="store_true", help="do not run the single-GPU step first (memory / time)")
+    ap.add_argument("--dry-cpu", action="store_true", help="walk the script on the CPU (gloo, the tests' library stand-in): host-side check only")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    if a.dry_cpu:
+        import pytest
+        import test_unet_grad_cpu
+        test_unet_grad_cpu.install_fake(pytest.MonkeyPatch())
+        dev = torch.device("cpu")
+        if world > 1:
+            dist.init_process_group("gloo")
+    else:
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+        torch.cuda.set_device(dev)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
     import test_guided_cpu as tg
     import test_vae_cpu as tv
     import unet_ref
@@ -67,16 +76,23 @@ def main():
                                      noise=noises[0:1], recur_noise=noises[1:2])[0]
 
     def timed(n):
-        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            out = step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if a.dry_cpu:
+            import time
+            t0 = time.perf_counter()
+            for _ in range(n):
+                out = step()
+            ms = torch.tensor([(time.perf_counter() - t0) / n * 1e3])
+        else:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                out = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), out
