@@ -47,7 +47,8 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
-def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None):
+def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=None):
+    """spec_capacity: run the SPECULATIVE forward (no host round trip for R) with an instance buffer of that many entries."""
     import gvd_native as n
 
     L = lib()
@@ -83,10 +84,22 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None):
     a.prefiltered, a.debug, a.export_keys = 0, 0, 1
     a.out_color, a.out_depth, a.out_alpha, a.radii = _p(color), _p(depth), _p(alpha), _p(radii)
     a.geom_alloc, a.binning_alloc, a.img_alloc = cbs
+    r_word = np.zeros(1, np.int32)
+    if spec_capacity is not None:
+        nb = int(L.gvd_raster_binning_bytes(int(spec_capacity), 1)) + 512
+        raw, ptr = _aligned(nb)
+        keep["binning"] = (raw, ptr, nb)
+        a.spec_binning_buffer, a.spec_binning_bytes = ptr, nb
+        a.num_rendered_pinned = r_word.ctypes.data
     rc = L.gvd_raster_forward(C.byref(a), None)
     if rc != 0:
         raise RuntimeError("gvd_raster_forward (host build): " + (L.gvd_last_error() or b"").decode())
     R = int(a.num_rendered)
+    if spec_capacity is not None:
+        assert R == -1                    # the library did not learn R on this path; it arrives through the pinned word
+        R = int(r_word[0])
+        if R > spec_capacity:             # the caller's validation: outputs of this frame are invalid
+            return dict(num_rendered=R, overflow=True, color=color, radii=radii)
     lay = n.RasterLayout()
     L.gvd_raster_layout(P, R, W, H, C.byref(lay))
     T = ((W + 15) // 16) * ((H + 15) // 16)

@@ -84,3 +84,22 @@ def test_everything_behind_the_camera_and_tiny_inputs():
         assert np.array_equal(o["point_list"], r["point_list"]) and np.array_equal(o["ranges"], r["ranges"])
     for k in ("color", "depth", "alpha"):
         assert np.abs(o[k] - r[k].reshape(o[k].shape)).max() < 1e-4
+
+
+def test_speculative_forward_equals_exact_and_survives_overflow():
+    """The no-host-round-trip forward (`GVD_SPECULATE`): with an instance buffer sized from a guess it
+    writes R through the caller's pinned word and produces exactly the exact path's buffers; with a buffer that is too
+    small every write and read is clamped (no out-of-bounds access -- the buffer ends where the allocation ends) and the
+    caller sees R > capacity."""
+    import raster_emu
+
+    g = np.load(toc.GOLDEN[0])
+    _, sc, cam, cot, bg, D, precomp = toc._inputs(g)
+    exact = raster_emu.run(sc, cam, bg, D, use_conf=bool(g["use_conf"]), precomp=precomp)
+    R = exact["num_rendered"]
+    spec = raster_emu.run(sc, cam, bg, D, use_conf=bool(g["use_conf"]), precomp=precomp, spec_capacity=2 * R + 1000)
+    assert spec["num_rendered"] == R
+    for k in ("radii", "point_list", "ranges", "n_contrib", "color", "depth", "alpha"):
+        assert np.array_equal(spec[k], exact[k]), k
+    small = raster_emu.run(sc, cam, bg, D, use_conf=bool(g["use_conf"]), precomp=precomp, spec_capacity=R // 3)
+    assert small.get("overflow") and small["num_rendered"] == R and np.array_equal(small["radii"], exact["radii"])
