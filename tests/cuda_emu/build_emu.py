@@ -56,7 +56,10 @@ def build(name="nn_backward", sources=None, extra_flags=()):
     """name: a single csrc/<name>.cu, or the library name when `sources` lists several files that link into one .so."""
     os.makedirs(OUT, exist_ok=True)
     sources = list(sources or [name + ".cu"])
-    so = os.path.join(OUT, f"lib{name}_emu.so")
+    asan = os.environ.get("GVD_EMU_ASAN") == "1"   # tools/emu_memcheck.sh: AddressSanitizer build of the same sources
+    if asan:
+        extra_flags = tuple(extra_flags) + ("-fsanitize=address", "-fno-omit-frame-pointer")
+    so = os.path.join(OUT, f"lib{name}_emu{'_asan' if asan else ''}.so")
     deps = [os.path.join(CSRC, s) for s in sources] + [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cub", "cub.cuh"), __file__]
     deps += [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
     if os.path.exists(so) and os.path.getmtime(so) > max(os.path.getmtime(d) for d in deps):
@@ -65,7 +68,7 @@ def build(name="nn_backward", sources=None, extra_flags=()):
     for src in sources:
         with open(os.path.join(CSRC, src)) as f:
             text = rewrite(f.read())
-        cpp = os.path.join(OUT, os.path.splitext(src)[0] + "_emu.cpp")
+        cpp = os.path.join(OUT, os.path.splitext(src)[0] + ("_emu_asan.cpp" if asan else "_emu.cpp"))
         with open(cpp, "w") as f:
             f.write(text)
         cpps.append(cpp)
