@@ -505,7 +505,10 @@ def denoise_bench(impl, dev, steps=2, t=25, h=72, w=128, world=1):
             plan = DenoisePlan(t)
         model = DiffusionModelB200(UNetB200(ref.state_dict(), device=dev, **cfg), sched, plan=plan)
         if world == 1 and os.environ.get("GVD_BENCH_CPU_UNET", "1") == "1":
-            ref_cpu = ref.cpu()  # kept for the CPU row below (BASELINE.md CPU row 5); leaves the GPU
+            try:
+                ref_cpu = ref.cpu()  # kept for the CPU row below (BASELINE.md CPU row 5); leaves the GPU
+            except Exception:        # the CPU row is a reported extra: never let it cost the GPU measurement
+                ref_cpu = None
         del ref
     else:
         class RefModel:  # apply_model of DiffusionWrapper 'hybrid' (ddpm3d.py:1437-1443) around the reference module
