@@ -52,6 +52,11 @@ def _rank(rank, world, names, n_floats, payload, epochs, q):
 
 @pytest.mark.parametrize("world,n_floats", [(2, 4 * 1237), (3, 4 * 1001), (5, 4 * 777), (8, 4 * 1237), (8, 4 * 40001), (8, 8)])
 def test_peer_memory_allreduce_all_world_sizes(world, n_floats):
+    for p in (os.path.join(ROOT, "guidedvd-3dgs_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "cuda_emu")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import raster_emu
+    raster_emu.lib()                                    # build the host library HERE, once, not in every rank process at once
     payload = (n_floats + 64) * 4                       # a tail the reduction must not touch
     shms = [shared_memory.SharedMemory(create=True, size=payload + FLAG_BYTES) for _ in range(world)]
     try:
