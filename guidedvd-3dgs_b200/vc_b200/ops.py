@@ -292,19 +292,23 @@ def ddim_step(x, e_cond, e_uncond, noise, coef):
 # Input-gradient operators (include/gvd_nn.h, csrc/nn_backward.cu): the adjoints vc_b200.grad strings together for the
 # guided sampler (lvdm/models/samplers/ddim_guidance.py:259-337).  Parameters are frozen, only activations get gradients.
 # ---------------------------------------------------------------------------------------------------------------------
-_wt_cache = {}
-
-
 def _transposed(weight):
-    """weight [N, K] -> cached [K, Np] copy (Np = N rounded up to 8, zero padded): the B operand of dX = dY @ W."""
-    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
-    wt = _wt_cache.get(key)
-    if wt is None:
-        N, K = weight.shape
-        Np = (N + 7) // 8 * 8
-        wt = torch.zeros(K, Np, dtype=weight.dtype, device=weight.device)
-        wt[:, :N] = weight.t()
-        _wt_cache[key] = wt
+    """weight [N, K] -> [K, Np] copy (Np = N rounded up to 8, zero padded): the B operand of dX = dY @ W.
+    The copy lives ON the weight tensor object (layers hold their weights as attributes and pass the same object every
+    call), so it dies with the layer and can never be served to another model whose weight lands at a recycled
+    address -- a process-wide cache keyed on data_ptr did exactly that on the first hardware run: the second model
+    built in a process got the first one's transposed weights.  `_version` catches in-place updates."""
+    cached = getattr(weight, "_gvd_wt", None)
+    if cached is not None and cached[0] == weight._version and cached[1].device == weight.device:
+        return cached[1]
+    N, K = weight.shape
+    Np = (N + 7) // 8 * 8
+    wt = torch.zeros(K, Np, dtype=weight.dtype, device=weight.device)
+    wt[:, :N] = weight.t()
+    try:
+        weight._gvd_wt = (weight._version, wt)
+    except AttributeError:  # objects that refuse attributes: no caching, still correct
+        pass
     return wt
 
 

@@ -36,7 +36,7 @@ def install_fake(monkeypatch, act_dtype=torch.float32):
     monkeypatch.setattr(ops, "BF16", act_dtype)
     monkeypatch.setattr(unet, "BF16", act_dtype)
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
-    for cache in (ops._wt_cache, ops._gn_tmp, ops._gn_bwd_tmp):
+    for cache in (ops._gn_tmp, ops._gn_bwd_tmp):
         cache.clear()
     return fake
 
@@ -210,3 +210,20 @@ def test_temporal_conv_adjoint_against_autograd(monkeypatch):
     x.grad = res.grad = None
     y_ref.backward(dy)
     assert _rel(gx, x.grad) < 1e-5 and _rel(gr, res.grad) < 1e-6
+
+
+def test_transposed_weight_copy_belongs_to_the_weight_object():
+    """Regression for the first hardware run of the guided path: the transposed copies of dX = dY @ W were cached
+    process-wide under data_ptr, so a second model whose weights landed at recycled addresses got the first model's.
+    The copy now lives on the weight tensor object: another tensor at the same address must not see it, an in-place
+    update of the weight invalidates it."""
+    from vc_b200 import ops
+
+    w = torch.arange(12.0).view(3, 4)
+    t1 = ops._transposed(w)
+    assert ops._transposed(w) is t1 and torch.equal(t1[:, :3], w.t()) and t1.shape == (4, 8)
+    alias = w.view(3, 4)  # same storage and address, different Python object: as after free + reallocation
+    w.mul_(2.0)
+    assert torch.equal(ops._transposed(alias)[:, :3], w.t())
+    t2 = ops._transposed(w)
+    assert t2 is not t1 and torch.equal(t2[:, :3], w.t())

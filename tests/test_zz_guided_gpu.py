@@ -7,18 +7,17 @@ assert).  The whole network's d(output)/d(latent) is compared with autograd over
 under torch.autocast(bfloat16), with the same rule as the forward test (tests/test_unet_gpu.py): at least as close to
 fp32 as the reference's own bf16 run.
 
-STATUS: these kernels were written after the round's GPU budget was spent; host logic, bindings and formulas are pinned
-on the CPU (tests/test_unet_grad_cpu.py, tests/test_guided_cpu.py) but the CUDA code below has not yet run on hardware.
-The file therefore sorts last and every test is a NON-STRICT xfail: it runs, a pass is reported as XPASS, a failure
-cannot hide the rest of the suite.  Remove the marker once a GPU run is green.
+First hardware run (round 2, profiles/r02_first_hw_run.txt): all 23 operator-level cases green; the four model-level
+cases failed because the transposed-weight copies of dX = dY @ W were cached process-wide under data_ptr and a second
+model built in the same process was served the first one's (fixed in ops._transposed; regression test in
+tests/test_unet_grad_cpu.py).  No xfail markers: a failure here fails the suite.
 """
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access); see module docstring")]
+pytestmark = [pytest.mark.gpu]
 
 BF = torch.bfloat16
 

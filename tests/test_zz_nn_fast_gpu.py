@@ -1,9 +1,9 @@
 """GPU: the re-indexed GEGLU / im2col variants (csrc/nn_fast.cu, GVD_NN_FAST / gvd_nn_set_fast) against the kernels they
-replace -- the same bits at the denoiser's real shapes.  First hardware run pending (non-strict xfail, sorts last)."""
+replace -- the same bits at the denoiser's real shapes.  Green on B200 (round 2, profiles/r02_first_hw_run.txt)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access)")]
+pytestmark = [pytest.mark.gpu]
 BF = torch.bfloat16
 
 

@@ -3,8 +3,7 @@
 (tests/golden/pcd2img_*.npz, scene/pcd2img.py:4-70) and against the oracle at BASELINE's larger "point render" size
 (500 000 points, 640x480), plus the edge cases.  Integer / byte outputs: the bar is equality.
 
-STATUS: written after the round's GPU budget was spent; the CUDA source has been executed on the host
-(tests/test_pcd2img_cpu.py, bit-exact) but not yet on hardware -> non-strict xfail, file sorts last."""
+Green on B200 since round 2 (profiles/r02_first_hw_run.txt); the same source also runs on the host (tests/test_pcd2img_cpu.py)."""
 import os
 import sys
 
@@ -14,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("name", ["c1", "dense", "wide"])

@@ -4,8 +4,7 @@ forward/backward against the reference's goldens (tests/golden/loss_*.npz) and, 
 torch.optim.Adam(eps=1e-15); densification statistics against the reference's masked statements.
 Tolerances: 1e-5 relative on loss values, 2e-4 relative L2 on gradients (fp32, different summation order).
 
-STATUS: written after the round's GPU budget was spent; the CUDA source has been executed on the host
-(tests/test_train_ops_cpu.py) but not yet on hardware -> non-strict xfail, file sorts last."""
+Green on B200 since round 2 (profiles/r02_first_hw_run.txt); the same source also runs on the host (tests/test_train_ops_cpu.py)."""
 import os
 import sys
 
@@ -16,7 +15,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _rel(a, b):
