@@ -12,20 +12,23 @@
 
 extern thread_local std::string g_nn_err_ext;
 
-// nn_fast.cu: re-indexed variants, off unless GVD_NN_FAST=1 (not yet timed on a GPU)
+// nn_fast.cu: re-indexed variants. Measured on B200 (profiles/r02_first_hw_run.txt): GEGLU 722 -> 379 us, im2col 3x3
+// 1110 -> 564 us, temporal im2col 168 -> 127 us at the C3 shapes (4.6-5.2 TB/s), so level 1 is the default; the
+// temporal-attention variant measured 10 % SLOWER (583 -> 640 us) and stays behind level 2.
 bool gvd_fast_geglu(const void* h, void* out, long long rows, int D, cudaStream_t s);
 bool gvd_fast_im2col3x3(const void* x, void* col, int F, int H, int W, int C, int Ho, int Wo, int stride, int up, cudaStream_t s);
 bool gvd_fast_im2col_t3(const void* x, void* col, int B, int T, long long S, int C, cudaStream_t s);
 bool gvd_fast_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S, int H, float scale,
                                  cudaStream_t s);
-static int g_nn_fast = -1;  // -1: not decided yet (GVD_NN_FAST), 0 / 1 afterwards or through gvd_nn_set_fast
-static bool nn_fast_enabled() {
+static int g_nn_fast = -1;  // -1: not decided yet (GVD_NN_FAST), 0 / 1 / 2 afterwards or through gvd_nn_set_fast
+static int nn_fast_level() {
     if (g_nn_fast < 0) {
         const char* e = getenv("GVD_NN_FAST");
-        g_nn_fast = (e && e[0] == '1') ? 1 : 0;
+        g_nn_fast = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     }
-    return g_nn_fast == 1;
+    return g_nn_fast;
 }
+static bool nn_fast_enabled() { return nn_fast_level() >= 1; }
 
 namespace {
 
@@ -480,8 +483,8 @@ int grid_for(long long n, int block = 256, int cap = 148 * 16) {
 extern "C" {
 
 int gvd_nn_set_fast(int on) {
-    const int was = nn_fast_enabled() ? 1 : 0;
-    if (on == 0 || on == 1) g_nn_fast = on;
+    const int was = nn_fast_level();
+    if (on >= 0 && on <= 2) g_nn_fast = on;
     return was;
 }
 
@@ -608,7 +611,7 @@ int gvd_temporal_attention(const void* q, const void* k, const void* v, void* ou
     if (T > 32 || T <= 0) { g_nn_err_ext = "gvd_temporal_attention: needs 1 <= T <= 32"; return 2; }
     const long long warps = (long long)B * S * H;
     if (warps <= 0) return 0;
-    if (nn_fast_enabled() && gvd_fast_temporal_attention(q, k, v, out, B, T, S, H, scale, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    if (nn_fast_level() >= 2 && gvd_fast_temporal_attention(q, k, v, out, B, T, S, H, scale, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     temporal_attn_kernel<<<(unsigned)((warps + TA_WARPS - 1) / TA_WARPS), TA_WARPS * 32, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                     (const __nv_bfloat16*)v, (__nv_bfloat16*)out, B, T, S, H, scale);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

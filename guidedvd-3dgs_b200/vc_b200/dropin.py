@@ -9,14 +9,27 @@ forward runs vc_b200.unet.UNetB200; `replace_unet(latent_diffusion)` installs it
 
 Scope: the plain DDIM path (`no_guidance=True`, and every U-Net call made under torch.no_grad()) always runs native.
 The guided sampler (lvdm/models/samplers/ddim_guidance.py:259-337) differentiates through the U-Net with respect to
-the latent: with GVD_GUIDED_NATIVE=1 such a call runs `UNetB200.forward_with_grad` (vc_b200.grad: the same forward
-kernels with the tape on, input-gradient kernels in the backward); without it -- the default until that path has its
-first green GPU run -- `B200UNet` hands calls that need a graph back to the reference module it wraps.  Calls that
-want PARAMETER gradients (nobody on this path) always go to the reference module.
+the latent: such a call runs `UNetB200.forward_with_grad` (vc_b200.grad: the same forward kernels with the tape on,
+input-gradient kernels in the backward).  GVD_GUIDED_NATIVE=0 hands calls that need a graph back to the reference
+module the wrapper keeps (A/B switch; the native path is the default since its hardware parity run in round 2,
+profiles/r02_*guided*).  Calls that want PARAMETER gradients (nobody on this path: the guided sampler sets
+requires_grad on the modules but only ever asks for `inputs=x`) go to the reference module unless the latent itself
+requires grad.
+
+Zero-edit activation: vc_b200.autoinstall (loaded by guidedvd-3dgs_b200/sitecustomize.py when that directory is on
+PYTHONPATH) wraps `ViewCrafter.setup_diffusion` (third_party/ViewCrafter/viewcrafter.py:315-335) so the three
+replace_* calls below run right after the reference has built and loaded its model.
 """
 import os
 
 import torch
+
+
+def guided_native():
+    """Native input-gradient path on (default) or off (GVD_GUIDED_NATIVE=0)."""
+    return os.environ.get("GVD_GUIDED_NATIVE", "1") != "0"
+
+
 import torch.nn as nn
 
 from .unet import UNetB200
@@ -39,7 +52,7 @@ class B200UNet(nn.Module):
         if features_adapter is not None:
             return self.reference(x, timesteps, context=context, features_adapter=features_adapter, fs=fs, **kwargs)
         if torch.is_grad_enabled() and x.requires_grad:
-            if os.environ.get("GVD_GUIDED_NATIVE", "0") == "1":
+            if guided_native():
                 return self.native.forward_with_grad(x.float(), timesteps, context.float(), fs=fs).to(x.dtype)
             return self.reference(x, timesteps, context=context, fs=fs, **kwargs)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.reference.parameters()):
@@ -64,7 +77,7 @@ def replace_first_stage_decoder(latent_diffusion):
     `decode_core` (lvdm/models/ddpm3d.py:646-667) keeps its per-frame loop and its 1/scale_factor; each
     `first_stage_model.decode(frame_z)` (autoencoder.py:104-107: post_quant_conv + Decoder) lands here.  Same routing
     rule as B200UNet: no graph wanted -> native forward; graph with respect to the latent wanted (the guided sampler,
-    ddim_guidance.py:288) -> native forward with the tape on when GVD_GUIDED_NATIVE=1, else the reference module.
+    ddim_guidance.py:288) -> native forward with the tape on (GVD_GUIDED_NATIVE=0: the reference module).
     Returns the DecoderB200."""
     from .vae import DecoderB200
 
@@ -77,7 +90,7 @@ def replace_first_stage_decoder(latent_diffusion):
 
     def decode(z, **kwargs):
         if torch.is_grad_enabled() and z.requires_grad:
-            if os.environ.get("GVD_GUIDED_NATIVE", "0") == "1":
+            if guided_native():
                 return native.differentiable_decode(z.float()).to(z.dtype)
             return reference_decode(z, **kwargs)
         if torch.is_grad_enabled() and any(p.requires_grad for p in fs.parameters()):

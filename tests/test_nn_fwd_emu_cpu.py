@@ -192,7 +192,7 @@ def test_fast_variants_are_bit_identical(monkeypatch, emu_lib):
     def both(fn):
         was = lib.gvd_nn_set_fast(0)
         a = fn()
-        lib.gvd_nn_set_fast(1)
+        lib.gvd_nn_set_fast(2)
         b = fn()
         lib.gvd_nn_set_fast(was)
         return a, b
@@ -227,3 +227,4 @@ def test_fast_variants_are_bit_identical(monkeypatch, emu_lib):
         assert torch.equal(a, b), T
     lib.gvd_nn_set_fast(0)
     assert lib.gvd_nn_set_fast(7) == 0   # any other value only queries
+    lib.gvd_nn_set_fast(1)
