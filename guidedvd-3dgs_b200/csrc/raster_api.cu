@@ -1,7 +1,7 @@
-// raster_api.cu -- C-ABI entry points (include/gvd_raster.h): buffer carving, stage sequencing,
-// CUB scan + radix sort. Mirrors the control flow of DGR/cuda_rasterizer/rasterizer_impl.cu:197-447
-// on an explicit stream; no torch types, no allocation.
-#include <cub/cub.cuh>
+// raster_api.cu -- C-ABI entry points (include/gvd_raster.h): buffer carving and stage sequencing.
+// Mirrors the control flow of DGR/cuda_rasterizer/rasterizer_impl.cu:197-447 on an explicit stream;
+// no torch types, no allocation, no library kernels (the reference's CUB scan and radix sort are
+// replaced by the compaction / depth-sort / counting-sort kernels of raster_forward.cu).
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -92,26 +92,44 @@ void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128) {
     chunk = reinterpret_cast<char*>(ptr + count);
 }
 
-// The three carve_* functions define the scratch layouts; calling them on a null base yields sizes
+// The carve_* functions define the scratch layouts; calling them on a null base yields sizes
 // (same trick as CudaRasterizer::required<T>, rasterizer_impl.h:63-69).
-RasterGeomPtrs carve_geom(char*& chunk, size_t P, size_t T) {
+RasterGeomPtrs carve_geom(char*& chunk, size_t P) {
     RasterGeomPtrs g;
     obtain(chunk, g.splat, P);
     obtain(chunk, g.clamped, P);
     obtain(chunk, g.tiles_touched, P);
-    obtain(chunk, g.depth_key, P);
-    obtain(chunk, g.gidx, P);
-    obtain(chunk, g.depth_sorted, P);
-    obtain(chunk, g.order, P);
-    g.sort_temp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, g.sort_temp_bytes, g.depth_key, g.depth_sorted, g.gidx, g.order, (int)P);
-    obtain(chunk, g.sort_temp, g.sort_temp_bytes);
-    g.chunks = (P + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK;
-    obtain(chunk, g.chunk_flags, g.chunks);
-    obtain(chunk, g.hist, g.chunks * T);
-    obtain(chunk, g.tile_total, T);
-    obtain(chunk, g.num_rendered, 1);
+    obtain(chunk, g.vis_id, P);
+    obtain(chunk, g.counts, 8);
     return g;
+}
+
+RasterSortPtrs carve_sort(char*& chunk, size_t P) {
+    RasterSortPtrs so;
+    so.nb = (P + GVD_PRE_BLOCK - 1) / GVD_PRE_BLOCK;
+    so.nt = (P + GVD_SORT_TILE - 1) / GVD_SORT_TILE;
+    so.ns = (so.nt + GVD_SORT_SUPER - 1) / GVD_SORT_SUPER;
+    obtain(chunk, so.depth_key, P);
+    obtain(chunk, so.blk_vis, so.nb);
+    obtain(chunk, so.blk_tiles, so.nb);
+    obtain(chunk, so.key[0], P);
+    obtain(chunk, so.key[1], P);
+    obtain(chunk, so.val[0], P);
+    obtain(chunk, so.val[1], P);
+    so.zeroed_words = 4 * 256 + 4 * so.nt * 256 + 4 * so.ns * 256;
+    obtain(chunk, so.zeroed, so.zeroed_words);
+    so.ghist = so.zeroed;
+    so.thist = so.ghist + 4 * 256;
+    so.shist = so.thist + 4 * so.nt * 256;
+    return so;
+}
+
+RasterHistPtrs carve_hist(char*& chunk, size_t rows, size_t T) {
+    RasterHistPtrs h;
+    h.rows = rows;
+    obtain(chunk, h.hist, rows * T);
+    obtain(chunk, h.tile_total, T);
+    return h;
 }
 
 RasterBinPtrs carve_binning(char*& chunk, size_t R, bool with_keys) {
@@ -127,21 +145,6 @@ RasterImgPtrs carve_img(char*& chunk, size_t tiles, size_t pixels) {
     obtain(chunk, im.ranges, tiles);
     obtain(chunk, im.n_contrib, pixels);
     return im;
-}
-
-// rasterizer_impl.cu:35-50
-uint32_t higher_msb(uint32_t n) {
-    uint32_t msb = sizeof(n) * 4;
-    uint32_t step = msb;
-    while (step > 1) {
-        step /= 2;
-        if (n >> msb)
-            msb += step;
-        else
-            msb -= step;
-    }
-    if (n >> msb) msb++;
-    return msb;
 }
 
 inline dim3 tile_grid(int width, int height) {
@@ -169,9 +172,21 @@ int gvd_raster_profile_read(GvdRasterStageTimes* out) {
 const char* gvd_last_error(void) { return g_err.c_str(); }
 
 size_t gvd_raster_geom_bytes(int P, int width, int height) {
+    (void)width;
+    (void)height;
+    char* p = nullptr;
+    carve_geom(p, (size_t)P);
+    return (size_t)p + 128;
+}
+size_t gvd_raster_sort_bytes(int P) {
+    char* p = nullptr;
+    carve_sort(p, (size_t)P);
+    return (size_t)p + 128;
+}
+size_t gvd_raster_hist_bytes(int num_visible, int width, int height) {
     char* p = nullptr;
     dim3 g = tile_grid(width, height);
-    carve_geom(p, (size_t)P, (size_t)g.x * g.y);
+    carve_hist(p, ((size_t)num_visible + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK, (size_t)g.x * g.y);
     return (size_t)p + 128;
 }
 size_t gvd_raster_binning_bytes(int R, int export_keys) {
@@ -191,11 +206,12 @@ int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out)
     if (!out) return fail_msg("gvd_raster_layout: null out");
     dim3 tg = tile_grid(width, height);
     char* p = nullptr;
-    RasterGeomPtrs g = carve_geom(p, (size_t)P, (size_t)tg.x * tg.y);
+    RasterGeomPtrs g = carve_geom(p, (size_t)P);
     out->geom_splat = (size_t)g.splat;
     out->geom_clamped = (size_t)g.clamped;
     out->geom_tiles_touched = (size_t)g.tiles_touched;
-    out->geom_order = (size_t)g.order;
+    out->geom_visible_ids = (size_t)g.vis_id;
+    out->geom_counts = (size_t)g.counts;
     p = nullptr;
     RasterBinPtrs b = carve_binning(p, (size_t)R, true);
     out->bin_point_list = (size_t)b.point_list;
@@ -207,11 +223,21 @@ int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayout* out)
     return 0;
 }
 
+// Event the exact path waits on for R when the caller supplied none: one per host thread and device, created lazily.
+static cudaEvent_t internal_r_event() {
+    thread_local cudaEvent_t ev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) ev[dev] = nullptr;
+    return ev[dev];
+}
+
 int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!a) return fail_msg("gvd_raster_forward: null args");
     const bool debug = a->debug != 0;
     a->num_rendered = 0;
+    a->num_visible = 0;
     if (a->P <= 0) return 0;
     if (a->width <= 0 || a->height <= 0) return fail_msg("gvd_raster_forward: bad image size");
     if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
@@ -219,8 +245,12 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
         ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
         return fail_msg("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
-    if ((!a->geom_alloc && !a->geom_buffer) || (!a->binning_alloc && !a->spec_binning_buffer) || (!a->img_alloc && !a->img_buffer))
+    const bool spec = a->spec_binning_buffer != nullptr && !debug;
+    if ((!a->geom_alloc && !a->geom_buffer) || (!a->img_alloc && !a->img_buffer) || (!a->temp_alloc && !a->sort_buffer))
         return fail_msg("gvd_raster_forward: null allocator");
+    if (!spec && (!a->binning_alloc || !a->temp_alloc)) return fail_msg("gvd_raster_forward: null binning / temp allocator");
+    if (spec && (!a->spec_hist_buffer || !a->num_rendered_pinned))
+        return fail_msg("gvd_raster_forward: the speculative path needs spec_hist_buffer and num_rendered_pinned");
     if (a->shs && (a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
         return fail_msg("gvd_raster_forward: SH degree / coefficient count mismatch");
 
@@ -236,75 +266,101 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
     if (a->geom_buffer && a->geom_bytes < geom_need) return fail_msg("gvd_raster_forward: geom_buffer too small");
     char* gp = a->geom_buffer ? (char*)a->geom_buffer : (char*)a->geom_alloc(a->alloc_user, geom_need);
     if (!gp) return fail_msg("gvd_raster_forward: geometry allocator returned null");
-    RasterGeomPtrs g = carve_geom(gp, (size_t)P, tiles);
+    RasterGeomPtrs g = carve_geom(gp, (size_t)P);
     const size_t img_need = gvd_raster_img_bytes(a->width, a->height);
     if (a->img_buffer && a->img_bytes < img_need) return fail_msg("gvd_raster_forward: img_buffer too small");
     char* ip = a->img_buffer ? (char*)a->img_buffer : (char*)a->img_alloc(a->alloc_user, img_need);
     if (!ip) return fail_msg("gvd_raster_forward: image allocator returned null");
     RasterImgPtrs im = carve_img(ip, tiles, (size_t)a->width * a->height);
+    const size_t sort_need = gvd_raster_sort_bytes(P);
+    if (a->sort_buffer && a->sort_bytes < sort_need) return fail_msg("gvd_raster_forward: sort_buffer too small");
+    char* sp = a->sort_buffer ? (char*)a->sort_buffer : (char*)a->temp_alloc(a->alloc_user, sort_need);
+    if (!sp) return fail_msg("gvd_raster_forward: temp allocator returned null (sort scratch)");
+    RasterSortPtrs so = carve_sort(sp, (size_t)P);
 
     {
         StageScope t(GVD_STAGE_PREPROCESS, stream);
-        gvd_launch_preprocess(*a, g, focal_x, focal_y, grid, stream);
+        gvd_launch_preprocess(*a, g, so, focal_x, focal_y, grid, stream);
     }
     GVD_STAGE("preprocess");
+    // R and V leave the GPU ~40 us into the frame, right behind the compaction kernel -- long before the instance list
+    // is needed -- so the exact path below can size its buffers without ever letting the GPU run dry: the depth sort
+    // is already queued behind the event the host waits on.
+    cudaEvent_t r_event = a->r_ready_event ? reinterpret_cast<cudaEvent_t>(a->r_ready_event) : nullptr;
     {
-        // level 1: Gaussians by depth (stable; ties keep id order). Culled ones carry key 0xFFFFFFFF.
         StageScope t(GVD_STAGE_SORT, stream);
-        GVD_CHECK(cub::DeviceRadixSort::SortPairs(g.sort_temp, g.sort_temp_bytes, g.depth_key, g.depth_sorted, g.gidx,
-                                                  g.order, P, 0, 32, stream),
-                  "SortPairs(depth)");
+        gvd_launch_compact(P, g, so, a->num_rendered_pinned, stream);
+        if (a->num_rendered_pinned && !debug) {
+            if (!r_event && !spec) r_event = internal_r_event();
+            if (r_event) GVD_CHECK(cudaEventRecord(r_event, stream), "record R event");
+        }
+        gvd_launch_depth_sort(P, g, so, stream);
     }
-    GVD_STAGE("depth sort");
-    {
-        // level 2a: per-chunk tile histograms -> per-tile prefixes -> ranges and R
-        StageScope t(GVD_STAGE_SCAN, stream);
-        const bool spec = a->spec_binning_buffer != nullptr && !debug;
-        if (spec && !a->num_rendered_pinned) return fail_msg("gvd_raster_forward: speculative path needs num_rendered_pinned");
-        GVD_CHECK(gvd_launch_bin_count(P, g, im, grid, spec ? a->num_rendered_pinned : nullptr, stream), "bin_count");
-    }
-    GVD_STAGE("bin_count");
+    GVD_STAGE("compact + depth sort");
 
     RasterBinPtrs b;
+    RasterHistPtrs h;
     uint32_t capacity = 0xffffffffu;  // instance slots available in the binning buffer
     bool have_instances = true;
-    if (a->spec_binning_buffer != nullptr && !debug) {
-        // speculative path: no host round trip; the caller validates R afterwards
-        // R was written into *num_rendered_pinned by the last binning kernel (no copy-engine work in this stream)
-        if (a->r_ready_event) GVD_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->r_ready_event), stream), "record R event");
+    if (spec) {
+        // speculative path: no host round trip; the caller validates R and V afterwards (both were in pinned memory
+        // when r_ready_event fired)
         a->num_rendered = -1;
-        // largest R whose layout fits the caller's buffer
+        a->num_visible = -1;
         const size_t per = sizeof(uint32_t) + (a->export_keys ? sizeof(uint64_t) : 0);
         const size_t fixed = gvd_raster_binning_bytes(0, a->export_keys);
         const size_t room = a->spec_binning_bytes > fixed + 256 ? a->spec_binning_bytes - fixed - 256 : 0;
         capacity = (uint32_t)std::min<size_t>(room / per, 0x7fffffffu);
         char* bp = (char*)a->spec_binning_buffer;
         b = carve_binning(bp, (size_t)capacity, a->export_keys != 0);
+        // largest number of chunk rows whose layout fits the caller's hist buffer
+        const size_t hfixed = gvd_raster_hist_bytes(0, a->width, a->height);
+        const size_t hroom = a->spec_hist_bytes > hfixed + 256 ? a->spec_hist_bytes - hfixed - 256 : 0;
+        const size_t rows = std::min<size_t>(hroom / (tiles * sizeof(uint32_t)), ((size_t)P + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK);
+        char* hp = (char*)a->spec_hist_buffer;
+        h = carve_hist(hp, rows, tiles);
     } else {
-        // Size of the instance list. Like the reference (rasterizer_impl.cu:281-282) this is the one
-        // host round trip of the forward: the binning buffer is caller-owned and sized from R.
-        int num_rendered = 0;
-        GVD_CHECK(cudaMemcpyAsync(&num_rendered, g.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, stream),
-                  "copy num_rendered");
-        GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
-        a->num_rendered = num_rendered;
-        if (!a->binning_alloc) return fail_msg("gvd_raster_forward: null binning allocator");
-        char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(num_rendered, a->export_keys));
+        // Sizes of the instance list and of the chunk histogram. Like the reference (rasterizer_impl.cu:281-282) the
+        // buffers are caller-owned and sized from R; unlike it, the wait is for the first two kernels only.
+        int rv[2] = {0, 0};
+        if (a->num_rendered_pinned && r_event && !debug) {
+            GVD_CHECK(cudaEventSynchronize(r_event), "wait for R");
+            rv[0] = reinterpret_cast<volatile int*>(a->num_rendered_pinned)[0];
+            rv[1] = reinterpret_cast<volatile int*>(a->num_rendered_pinned)[1];
+        } else {
+            uint32_t c[2] = {0, 0};
+            GVD_CHECK(cudaMemcpyAsync(c, g.counts, sizeof(c), cudaMemcpyDeviceToHost, stream), "copy num_rendered");
+            GVD_CHECK(cudaStreamSynchronize(stream), "sync num_rendered");
+            rv[0] = (int)c[1];
+            rv[1] = (int)c[0];
+        }
+        a->num_rendered = rv[0];
+        a->num_visible = rv[1];
+        char* bp = (char*)a->binning_alloc(a->alloc_user, gvd_raster_binning_bytes(rv[0], a->export_keys));
         if (!bp) return fail_msg("gvd_raster_forward: binning allocator returned null");
-        b = carve_binning(bp, (size_t)num_rendered, a->export_keys != 0);
-        have_instances = num_rendered > 0;
+        b = carve_binning(bp, (size_t)rv[0], a->export_keys != 0);
+        char* hp = (char*)a->temp_alloc(a->alloc_user, gvd_raster_hist_bytes(rv[1], a->width, a->height));
+        if (!hp) return fail_msg("gvd_raster_forward: temp allocator returned null (chunk histogram)");
+        h = carve_hist(hp, ((size_t)rv[1] + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK, tiles);
+        have_instances = rv[0] > 0;
     }
 
+    {
+        // level 2a: per-chunk tile histograms -> per-tile prefixes -> ranges
+        StageScope t(GVD_STAGE_SCAN, stream);
+        GVD_CHECK(gvd_launch_bin_count(g, so, h, im, grid, stream), "bin_count");
+    }
+    GVD_STAGE("bin_count");
     if (have_instances) {
         {
             // level 2b: stable scatter of the Gaussian ids into the tile lists
             StageScope t(GVD_STAGE_EMIT, stream);
-            GVD_CHECK(gvd_launch_bin_fill(P, g, b, im, grid, capacity, stream), "bin_fill");
+            GVD_CHECK(gvd_launch_bin_fill(g, so, h, b, im, grid, capacity, stream), "bin_fill");
         }
         GVD_STAGE("bin_fill");
         if (a->export_keys) {
             StageScope t(GVD_STAGE_PACK, stream);
-            gvd_launch_export_keys(capacity, g, b, im, grid, stream);
+            gvd_launch_export_keys(capacity, so, b, im, grid, stream);
         }
         GVD_STAGE("export_keys");
     }
@@ -336,7 +392,7 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     const size_t tiles = (size_t)grid.x * grid.y;
 
     char* gp = (char*)a->geom_buffer;
-    RasterGeomPtrs g = carve_geom(gp, (size_t)P, tiles);
+    RasterGeomPtrs g = carve_geom(gp, (size_t)P);
     char* bp = (char*)a->binning_buffer;
     RasterBinPtrs b = carve_binning(bp, (size_t)a->R, false);
     char* ip = (char*)a->img_buffer;
@@ -346,16 +402,42 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     gvd_launch_zero_fill(acc, (size_t)P * GVD_ACC_STRIDE, stream);
     GVD_STAGE("zero accumulator");
 
+    // The dense gradient outputs are zero everywhere except on the V visible Gaussians (the reference zero-fills them
+    // with torch::zeros, rasterize_points.cu:158-167). When the caller says they all lie in one region, the render CTAs
+    // clear it on the side -- that kernel is issue-bound and leaves the memory system idle; otherwise each output is
+    // cleared by its own launch.
+    float4* zero = nullptr;
+    size_t zero_n4 = 0;
+    if (a->zero_region && a->zero_region_bytes >= 16 && ((uintptr_t)a->zero_region & 15) == 0 && a->R > 0) {
+        zero = reinterpret_cast<float4*>(a->zero_region);
+        zero_n4 = a->zero_region_bytes / 16;
+        if (a->zero_region_bytes & 15)
+            gvd_launch_zero_bytes((char*)a->zero_region + zero_n4 * 16, a->zero_region_bytes & 15, stream);
+    } else if (a->zero_region) {
+        gvd_launch_zero_bytes(a->zero_region, a->zero_region_bytes, stream);
+    } else {
+        const size_t M3 = (size_t)a->M * 3;
+        gvd_launch_zero_bytes(a->dL_dmeans2D, (size_t)P * 3 * 4, stream);
+        gvd_launch_zero_bytes(a->dL_dmeans3D, (size_t)P * 3 * 4, stream);
+        gvd_launch_zero_bytes(a->dL_dopacity, (size_t)P * 4, stream);
+        if (a->dL_dcolors) gvd_launch_zero_bytes(a->dL_dcolors, (size_t)P * 3 * 4, stream);
+        if (a->dL_dcov3D) gvd_launch_zero_bytes(a->dL_dcov3D, (size_t)P * 6 * 4, stream);
+        if (a->dL_dsh) gvd_launch_zero_bytes(a->dL_dsh, (size_t)P * M3 * 4, stream);
+        if (a->dL_dscales) gvd_launch_zero_bytes(a->dL_dscales, (size_t)P * 3 * 4, stream);
+        if (a->dL_drotations) gvd_launch_zero_bytes(a->dL_drotations, (size_t)P * 4 * 4, stream);
+    }
+    GVD_STAGE("zero gradients");
+
     if (a->R > 0) {
         {
             StageScope t(GVD_STAGE_RENDER_BWD, stream);
-            gvd_launch_render_backward(*a, g, b, im, acc, grid, stream);
+            gvd_launch_render_backward(*a, g, b, im, acc, zero, zero_n4, grid, stream);
         }
         GVD_STAGE("render_backward");
     }
     {
         StageScope t(GVD_STAGE_GAUSSIAN_BWD, stream);
-        gvd_launch_gaussian_backward(*a, g, acc, focal_x, focal_y, stream);
+        gvd_launch_gaussian_backward(*a, g, acc, focal_x, focal_y, a->num_visible, stream);
     }
     GVD_STAGE("gaussian_backward");
     return 0;

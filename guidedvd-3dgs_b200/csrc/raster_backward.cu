@@ -7,10 +7,13 @@
 //                            transposing butterfly (12 shuffles instead of 50) and leave the SM as ONE
 //                            predicated RED.ADD.F32 instruction per (warp, instance) into a packed
 //                            48-B-per-Gaussian accumulator (the reference issues 10 atomics per pixel hit).
-//   gaussian_backward_kernel per Gaussian: computeCov2DCUDA + preprocessCUDA(bwd) fused
-//                            (backward.cu:144-274, 346-412, 20-139, 278-341) with the Python-side
-//                            confidence scaling (diff_gaussian_rasterization/__init__.py:147-157) in the
-//                            epilogue; every output element is written exactly once (no zero-fill pass).
+//                            On the side every CTA clears its share of the dense gradient outputs (the kernel is
+//                            issue-bound; the 118 MB of zero stores at C2 ride on an idle memory system).
+//   gaussian_backward_kernel per VISIBLE Gaussian (the forward's compacted id list): computeCov2DCUDA +
+//                            preprocessCUDA(bwd) fused (backward.cu:144-274, 346-412, 20-139, 278-341) with the
+//                            Python-side confidence scaling (diff_gaussian_rasterization/__init__.py:147-157) in
+//                            the epilogue; writes the rows of the visible Gaussians over the zeros.
+#include <algorithm>
 #include <cstdlib>
 #include "raster_common.cuh"
 #include "../../include/gvd_raster.h"
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, const float* __restrict__ alphas,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-    const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas, float* __restrict__ acc) {
+    const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas, float* __restrict__ acc,
+    float4* __restrict__ zero, size_t zero_n4) {
     pdl_wait();
     pdl_trigger();
     // SPLIT CTAs share one 16x16 tile (8 / SPLIT warps of 8x4 pixels each): shorter CTAs, finer early exit, smaller tail
@@ -93,6 +97,11 @@ __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel
     __shared__ uint32_t warp_max[BLOCK / 32];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (zero_n4) {  // this CTA's slice of the dense gradient outputs (streaming stores; nothing here reads them)
+        const size_t per = (zero_n4 + gridDim.x - 1) / gridDim.x;
+        const size_t i0 = (size_t)blockIdx.x * per, i1 = i0 + per < zero_n4 ? i0 + per : zero_n4;
+        for (size_t i = i0 + tid; i < i1; i += BLOCK) __stcs(zero + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
     const uint32_t tile = blockIdx.x / SPLIT;
     const uint32_t gw = (blockIdx.x % SPLIT) * (8 / SPLIT) + warp;  // this warp's 8x4 block inside the tile
     const uint32_t tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -283,26 +292,6 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
     return r;
 }
 
-// Block-cooperative store of one [P,3] tensor: each thread parks its 3 floats in shared memory
-// (stride 3 is conflict-free), then the block writes the 768 floats back with unit-stride stores.
-__device__ __forceinline__ void store_p3_coalesced(float* __restrict__ dst, float* stage, int block_first, int P,
-                                                   float x, float y, float z) {
-    const int t = threadIdx.x;
-    stage[3 * t] = x;
-    stage[3 * t + 1] = y;
-    stage[3 * t + 2] = z;
-    __syncthreads();
-    const int n = 3 * min(256, P - block_first);
-    float* base = dst + 3 * (size_t)block_first;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int i = t + 256 * k;
-        if (i < n) base[i] = stage[i];
-    }
-    __syncthreads();
-}
-
-#define GVD_SH_STAGE_STRIDE 52
 #define SH(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
 #define OUT(k, val)                                 \
     {                                               \
@@ -314,7 +303,7 @@ __device__ __forceinline__ void store_p3_coalesced(float* __restrict__ dst, floa
 
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
-    int P, int D, int M, const float3* __restrict__ means, const int* __restrict__ radii,
+    int D, int M, const float3* __restrict__ means, const uint32_t* __restrict__ vis_id, const uint32_t* __restrict__ counts,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float3* __restrict__ scales,
     const float4* __restrict__ rotations, const float scale_modifier, const float* __restrict__ cov3D_precomp,
     const float* __restrict__ view, const float* __restrict__ proj, const float h_x, float h_y, const float tan_fovx,
@@ -324,15 +313,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
     float* __restrict__ dL_dsh, float* __restrict__ dL_dscales, float* __restrict__ dL_drots) {
     pdl_wait();
     pdl_trigger();
-    __shared__ float stage[3 * 256];
-    extern __shared__ __align__(16) float sh_stage[];  // [8 warps][32 rows][GVD_SH_STAGE_STRIDE] (only when dL_dsh, M == 16)
-    const int block_first = blockIdx.x * blockDim.x;
-    const int idx = block_first + threadIdx.x;
-    const bool valid = idx < P;
-    const bool visible = valid && (radii[idx] > 0);
+    // One thread per visible Gaussian, in ascending id order (vis_id comes from the forward's compaction), so the
+    // gathers of a warp stay close together. Everything else was zero-filled before this kernel.
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[0]) return;
+    const int idx = (int)vis_id[i];
 
-    // Everything the reference leaves at torch::zeros for untouched Gaussians (rasterize_points.cu:158-167)
-    // is produced here as explicit zeros, so no separate zero-fill pass over the outputs is needed.
     float2 o_m2 = {0.f, 0.f};
     float3 o_m3 = {0.f, 0.f, 0.f}, o_sc = {0.f, 0.f, 0.f}, o_col = {0.f, 0.f, 0.f};
     float4 o_rot = {0.f, 0.f, 0.f, 0.f};
@@ -342,7 +328,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
 #pragma unroll
     for (int k = 0; k < 48; ++k) o_sh[k] = 0.f;
 
-    if (visible) {
+    {
         const float conf = confidence ? confidence[idx] : 1.0f;
         const float4* ap = reinterpret_cast<const float4*>(acc + (size_t)idx * GVD_ACC_STRIDE);
         const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
@@ -599,43 +585,35 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
         for (int k = 0; k < 6; ++k) o_cov[k] = dcov[k] * conf;
     }
 
-    // ---------------- stores: every output element written exactly once ----------------
-    store_p3_coalesced(dL_dmeans2D, stage, block_first, P, o_m2.x, o_m2.y, 0.f);
-    store_p3_coalesced(dL_dmeans3D, stage, block_first, P, o_m3.x, o_m3.y, o_m3.z);
-    if (dL_dscales) store_p3_coalesced(dL_dscales, stage, block_first, P, o_sc.x, o_sc.y, o_sc.z);
-    if (dL_dcolors) store_p3_coalesced(dL_dcolors, stage, block_first, P, o_col.x, o_col.y, o_col.z);
-    if (valid) {
-        dL_dopacity[idx] = o_op;
-        if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
-        if (dL_dcov3D) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = o_cov[k];
-        }
+    // ---------------- stores: the rows of this Gaussian ----------------
+    dL_dmeans2D[3 * (size_t)idx] = o_m2.x;
+    dL_dmeans2D[3 * (size_t)idx + 1] = o_m2.y;
+    dL_dmeans3D[3 * (size_t)idx] = o_m3.x;
+    dL_dmeans3D[3 * (size_t)idx + 1] = o_m3.y;
+    dL_dmeans3D[3 * (size_t)idx + 2] = o_m3.z;
+    dL_dopacity[idx] = o_op;
+    if (dL_dscales) {
+        dL_dscales[3 * (size_t)idx] = o_sc.x;
+        dL_dscales[3 * (size_t)idx + 1] = o_sc.y;
+        dL_dscales[3 * (size_t)idx + 2] = o_sc.z;
     }
-    if (block_first + (int)(threadIdx.x & ~31u) >= P) return;  // whole warp past the end
+    if (dL_dcolors) {
+        dL_dcolors[3 * (size_t)idx] = o_col.x;
+        dL_dcolors[3 * (size_t)idx + 1] = o_col.y;
+        dL_dcolors[3 * (size_t)idx + 2] = o_col.z;
+    }
+    if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
+    if (dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = o_cov[k];
+    }
     if (dL_dsh) {
-        float* row = dL_dsh + (size_t)(valid ? idx : 0) * 3 * M;
+        float* row = dL_dsh + (size_t)idx * 3 * M;
         if (M == 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0)) {
-            // The 32 rows of a warp are one contiguous 6 KB span of dL_dsh. Written row-per-thread, every store
-            // instruction would touch 32 half-filled sectors; instead the rows are transposed through shared
-            // memory (row stride 52 floats: conflict-free 16-byte accesses) and the span leaves the SM as twelve
-            // unit-stride 512-byte stores.  Streaming stores: 96 MB per step that nothing in this step re-reads.
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            float* wstage = sh_stage + warp * (32 * GVD_SH_STAGE_STRIDE);
-            float4* mine = reinterpret_cast<float4*>(wstage + lane * GVD_SH_STAGE_STRIDE);
+            float4* r4 = reinterpret_cast<float4*>(row);  // one 192-byte row: six full sectors
 #pragma unroll
-            for (int k = 0; k < 12; ++k) mine[k] = make_float4(o_sh[4 * k], o_sh[4 * k + 1], o_sh[4 * k + 2], o_sh[4 * k + 3]);
-            __syncwarp();
-            const int warp_first = block_first + warp * 32;
-            const int nrows = min(32, P - warp_first);
-            float4* dst = reinterpret_cast<float4*>(dL_dsh + (size_t)warp_first * 48);
-#pragma unroll
-            for (int it = 0; it < 12; ++it) {
-                const int f = it * 32 + lane;  // float4 index inside the span
-                const int r = f / 12, c4 = f - r * 12;
-                if (r < nrows) __stcs(dst + f, *reinterpret_cast<const float4*>(wstage + r * GVD_SH_STAGE_STRIDE + 4 * c4));
-            }
-        } else if (valid) {
+            for (int k = 0; k < 12; ++k) r4[k] = make_float4(o_sh[4 * k], o_sh[4 * k + 1], o_sh[4 * k + 2], o_sh[4 * k + 3]);
+        } else {
 #pragma unroll
             for (int k = 0; k < 48; ++k)
                 if (k < 3 * M) row[k] = o_sh[k];
@@ -661,9 +639,27 @@ void gvd_launch_zero_fill(float* p, size_t floats, cudaStream_t s) {
     if (blocks) gvd_launch(zero_fill_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<float4*>(p), n4);
 }
 
+__global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ p, size_t n) {
+    pdl_wait();
+    pdl_trigger();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = 0u;
+}
+
+// Generic clear (gradient tensors are float arrays: 4-byte aligned, size a multiple of 4): head words up to the first
+// 16-byte boundary, float4 body, tail words.
+void gvd_launch_zero_bytes(void* p, size_t bytes, cudaStream_t s) {
+    if (!p || bytes < 4) return;
+    char* c = reinterpret_cast<char*>(p);
+    const size_t head = std::min<size_t>(bytes, (16 - (reinterpret_cast<uintptr_t>(c) & 15)) & 15);
+    const size_t body = (bytes - head) & ~(size_t)15, tail = bytes - head - body;
+    if (head) gvd_launch(zero_words_kernel, dim3(1), dim3(256), 0, s, reinterpret_cast<uint32_t*>(c), head / 4);
+    if (body) gvd_launch_zero_fill(reinterpret_cast<float*>(c + head), body / 4, s);
+    if (tail) gvd_launch(zero_words_kernel, dim3(1), dim3(256), 0, s, reinterpret_cast<uint32_t*>(c + head + body), tail / 4);
+}
+
 template <int SPLIT>
 static void launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
-                                   const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
+                                   const RasterImgPtrs& im, float* acc, float4* zero, size_t zero_n4, dim3 grid, cudaStream_t s) {
     static bool carveout_set = false;
     if (!carveout_set) {
         cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -671,43 +667,38 @@ static void launch_render_backward(const GvdRasterBackwardArgs& a, const RasterG
     }
     gvd_launch(render_backward_kernel<SPLIT>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
                g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
-               a.dL_dalpha_pix, acc);
+               a.dL_dalpha_pix, acc, zero, zero_n4);
 }
 
 void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
-                                const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s) {
+                                const RasterImgPtrs& im, float* acc, float4* zero, size_t zero_n4, dim3 grid, cudaStream_t s) {
     switch (gvd_render_split()) {
-        case 1: launch_render_backward<1>(a, g, b, im, acc, grid, s); break;
-        case 4: launch_render_backward<4>(a, g, b, im, acc, grid, s); break;
-        default: launch_render_backward<2>(a, g, b, im, acc, grid, s); break;
+        case 1: launch_render_backward<1>(a, g, b, im, acc, zero, zero_n4, grid, s); break;
+        case 4: launch_render_backward<4>(a, g, b, im, acc, zero, zero_n4, grid, s); break;
+        default: launch_render_backward<2>(a, g, b, im, acc, zero, zero_n4, grid, s); break;
     }
 }
 
 template <int MIN_CTAS>
 static void launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
-                                     float focal_x, float focal_y, cudaStream_t s) {
-    const size_t sh_smem = (a.dL_dsh && a.M == 16) ? (size_t)8 * 32 * GVD_SH_STAGE_STRIDE * sizeof(float) : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute((const void*)gaussian_backward_kernel<MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             8 * 32 * GVD_SH_STAGE_STRIDE * (int)sizeof(float));
-        attr_set = true;
-    }
-    gvd_launch(gaussian_backward_kernel<MIN_CTAS>, dim3((a.P + 255) / 256), dim3(256), sh_smem, s,
-        a.P, a.D, a.M, (const float3*)a.means3D, a.radii, a.shs, g.clamped, (const float3*)a.scales,
+                                     float focal_x, float focal_y, int num_visible, cudaStream_t s) {
+    const int n = num_visible >= 0 ? num_visible : a.P;  // V unknown on the host: cover P, surplus CTAs return at once
+    if (n <= 0) return;
+    gvd_launch(gaussian_backward_kernel<MIN_CTAS>, dim3((n + 255) / 256), dim3(256), 0, s,
+        a.D, a.M, (const float3*)a.means3D, g.vis_id, g.counts, a.shs, g.clamped, (const float3*)a.scales,
         (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
         a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,
         a.dL_dopacity, a.dL_dcolors, a.dL_dcov3D, a.dL_dsh, a.dL_dscales, a.dL_drotations);
 }
 
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
-                                  float focal_x, float focal_y, cudaStream_t s) {
-    // GVD_GBWD_CTAS=3: 80 registers (0.5 KB of spills) for three resident CTAs per SM instead of two (A/B timing knob)
+                                  float focal_x, float focal_y, int num_visible, cudaStream_t s) {
+    // GVD_GBWD_CTAS=3: 80 registers (spills) for three resident CTAs per SM instead of two (A/B timing knob)
     static int ctas = 0;
     if (!ctas) {
         const char* e = getenv("GVD_GBWD_CTAS");
         ctas = (e && e[0] == '3') ? 3 : 2;
     }
-    if (ctas == 3) launch_gaussian_backward<3>(a, g, acc, focal_x, focal_y, s);
-    else launch_gaussian_backward<2>(a, g, acc, focal_x, focal_y, s);
+    if (ctas == 3) launch_gaussian_backward<3>(a, g, acc, focal_x, focal_y, num_visible, s);
+    else launch_gaussian_backward<2>(a, g, acc, focal_x, focal_y, num_visible, s);
 }

@@ -1,10 +1,12 @@
 // raster_common.cuh -- shared definitions for the B200-native Gaussian rasterizer.
 //
 // Data layout in HBM (all caller-owned scratch, see include/gvd_raster.h):
-//   geom   : SplatRec[P] (64 B per Gaussian, written by preprocess, gathered on demand by the render
-//            kernels -- the visible set is a few MB and lives in the 126 MB L2), clamped[P],
-//            tiles_touched[P], depth keys / order[P] (depth sort), per-chunk tile histogram matrix
-//            [ceil(P/GVD_BIN_CHUNK)][T] (binning), tile totals.
+//   geom   : kept until the backward. SplatRec[P] (64 B per Gaussian, written by preprocess, gathered on demand by the
+//            render kernels -- the visible set is a few MB and lives in the 126 MB L2), clamped[P], tiles_touched[P],
+//            vis_id[P] (ids of the V visible Gaussians, ascending), counts {V, R}.
+//   sort   : forward-only, sized by P. depth keys by id, per-block visible / instance counts, the two (key, id)
+//            ping-pong arrays of the depth sort and its digit histograms.
+//   hist   : forward-only, sized by V. Per-chunk tile histogram matrix [ceil(V/GVD_BIN_CHUNK)][T], tile totals.
 //   binning: uint32 point_list[R] -- Gaussian ids, tile-major, depth-sorted inside a tile (identical to
 //            the reference's sorted value array); optional uint64 keys[R] for parity checks.
 //   img    : uint2 ranges[T], uint32 n_contrib[H*W]
@@ -35,17 +37,35 @@ struct RasterGeomPtrs {
     SplatRec* splat;
     uint8_t* clamped;
     uint32_t* tiles_touched;   // per Gaussian id
-    uint32_t* depth_key;       // per Gaussian id: depth bits, 0xFFFFFFFF when culled
-    uint32_t* gidx;            // iota (values fed to the depth sort)
-    uint32_t* depth_sorted;    // sorted depth keys (sort output, otherwise unused)
-    uint32_t* order;           // Gaussian ids in (depth, id) order; culled ones last
-    char* sort_temp;
-    size_t sort_temp_bytes;
-    uint32_t* chunk_flags;     // [chunks] 1 = chunk holds at least one visible Gaussian
-    uint32_t* hist;            // [chunks][T] per-chunk tile counts, turned into exclusive prefixes in place
+    uint32_t* vis_id;          // [P] ids of the visible Gaussians in ascending id order; V valid entries
+    uint32_t* counts;          // [8] {V = visible Gaussians, R = instances, ...}
+};
+
+// Depth sort = least-significant-digit radix sort (4 passes of 8 bits) over the V compacted (depth bits, id) pairs,
+// V read from device memory. One kernel per pass: a CTA ranks its tile of GVD_SORT_TILE keys stably and finds its
+// global offsets from per-tile digit histograms that the PREVIOUS kernel accumulated with atomics while it
+// scattered (the compaction kernel for pass 0), so there is neither a histogram kernel per pass nor a chained scan.
+#define GVD_PRE_BLOCK 256        // threads per preprocess CTA
+#define GVD_COMPACT_BLOCK 1024   // threads per compaction CTA (= 4 preprocess CTAs)
+#define GVD_SORT_TILE 1024       // keys per sort CTA
+#define GVD_SORT_THREADS 256
+#define GVD_SORT_SUPER 32        // tiles per super-tile (second histogram level bounds the offset lookup)
+struct RasterSortPtrs {
+    uint32_t* depth_key;       // [P] per Gaussian id: depth bits (undefined when culled)
+    uint32_t* blk_vis;         // [nb] visible Gaussians per preprocess CTA
+    uint32_t* blk_tiles;       // [nb] instances per preprocess CTA
+    uint32_t* key[2];          // [P] ping-pong
+    uint32_t* val[2];          // [P] ping-pong; val[0] holds the depth-sorted ids after the 4th pass
+    uint32_t* zeroed;          // ghist[4][256] | thist[4][nt][256] | shist[4][ns][256], cleared by preprocess
+    size_t zeroed_words;
+    uint32_t *ghist, *thist, *shist;
+    size_t nb, nt, ns;
+};
+
+struct RasterHistPtrs {
+    uint32_t* hist;            // [rows][T] per-chunk tile counts, turned into exclusive prefixes in place
     uint32_t* tile_total;      // [T]
-    uint32_t* num_rendered;    // [1] device copy of R
-    size_t chunks;
+    size_t rows;               // chunk rows available (>= ceil(V / GVD_BIN_CHUNK) unless a speculative guess was too small)
 };
 
 // Binning = depth sort of the Gaussians (P 32-bit keys) followed by a rect-aware STABLE counting sort on
@@ -67,21 +87,27 @@ struct RasterImgPtrs {
 struct GvdRasterForwardArgs;
 struct GvdRasterBackwardArgs;
 
-void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, float focal_x, float focal_y,
-                           dim3 grid, cudaStream_t s);
-cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, int* r_host,
-                                 cudaStream_t s);
-cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                                dim3 grid, uint32_t capacity, cudaStream_t s);
-void gvd_launch_export_keys(uint32_t capacity, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterSortPtrs& so, float focal_x,
+                           float focal_y, dim3 grid, cudaStream_t s);
+// compaction of the visible Gaussians (+ V, R to `counts` and, when given, to the pinned host words r_host[0] = R, r_host[1] = V)
+void gvd_launch_compact(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, int* r_host, cudaStream_t s);
+void gvd_launch_depth_sort(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, cudaStream_t s);
+cudaError_t gvd_launch_bin_count(const RasterGeomPtrs& g, const RasterSortPtrs& so, const RasterHistPtrs& h, const RasterImgPtrs& im,
+                                 dim3 grid, cudaStream_t s);
+cudaError_t gvd_launch_bin_fill(const RasterGeomPtrs& g, const RasterSortPtrs& so, const RasterHistPtrs& h, const RasterBinPtrs& b,
+                                const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s);
+void gvd_launch_export_keys(uint32_t capacity, const RasterSortPtrs& so, const RasterBinPtrs& b, const RasterImgPtrs& im,
                             dim3 grid, cudaStream_t s);
 void gvd_launch_render_forward(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s);
+// zero / zero_n4: a region (float4 units) the render CTAs clear on the side (the dense gradient outputs), or null
 void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
-                                const RasterImgPtrs& im, float* acc, dim3 grid, cudaStream_t s);
+                                const RasterImgPtrs& im, float* acc, float4* zero, size_t zero_n4, dim3 grid, cudaStream_t s);
 void gvd_launch_zero_fill(float* p, size_t floats, cudaStream_t s);
+void gvd_launch_zero_bytes(void* p, size_t bytes, cudaStream_t s);  // any alignment / size
+// num_visible < 0: unknown on the host, the grid covers P and reads V from g.counts
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,
-                                  float focal_x, float focal_y, cudaStream_t s);
+                                  float focal_x, float focal_y, int num_visible, cudaStream_t s);
 void gvd_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                              cudaStream_t s);
 

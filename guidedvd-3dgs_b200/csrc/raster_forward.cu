@@ -15,6 +15,7 @@
 //                         instances that can touch it
 //                         (forward.cu:261-381 semantics preserved: skipped instances are exactly those every
 //                         pixel of the warp would `continue` on).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include "raster_common.cuh"
@@ -118,24 +119,17 @@ __device__ __forceinline__ void alpha_extent(const float3 conic, float opac, flo
     hy = ey;
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(
-    int P, int D, int M, const float* __restrict__ orig_points, const float3* __restrict__ scales,
+// One Gaussian of preprocessCUDA (forward.cu:155-256). Returns the number of tiles its rect covers; 0 = not rendered
+// (near-culled, degenerate covariance or empty rect), in which case nothing but radii = 0 has been written.
+__device__ __forceinline__ uint32_t preprocess_one(
+    int idx, int D, int M, const float* __restrict__ orig_points, const float3* __restrict__ scales,
     const float scale_modifier, const float4* __restrict__ rotations, const float* __restrict__ opacities,
     const float* __restrict__ shs, uint8_t* __restrict__ clamped, const float* __restrict__ cov3D_precomp,
     const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
     const float* __restrict__ projmatrix, const float3* __restrict__ cam_pos, const int W, int H,
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
-    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched,
-    uint32_t* __restrict__ depth_key, uint32_t* __restrict__ gidx, int prefiltered) {
-    pdl_wait();
-    pdl_trigger();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-
+    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ depth_key, int prefiltered) {
     radii[idx] = 0;
-    tiles_touched[idx] = 0;
-    depth_key[idx] = 0xFFFFFFFFu;  // culled Gaussians sort behind every visible one
-    gidx[idx] = idx;
 
     // near cull (auxiliary.h:139-164): only p_view.z <= 0.2 rejects.
     const float3 p_orig = {orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]};
@@ -145,7 +139,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
             printf("Point is filtered although prefiltered is set. This shouldn't happen!");
             __trap();
         }
-        return;
+        return 0;
     }
 
     const float4 p_hom = xform_point_4x4(p_orig, projmatrix);
@@ -164,7 +158,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float3 cov = cov2d_from_cov3d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, viewmatrix);
 
     const float det = (cov.x * cov.z - cov.y * cov.y);
-    if (det == 0.0f) return;
+    if (det == 0.0f) return 0;
     const float det_inv = 1.f / det;
     const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
 
@@ -175,7 +169,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float2 point_image = {ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H)};
     uint2 rect_min, rect_max;
     tile_rect(point_image, (int)my_radius, rect_min, rect_max, grid);
-    if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) return;
+    if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) return 0;
 
     float3 rgb;
     if (colors_precomp == nullptr) {
@@ -187,7 +181,6 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     }
 
     radii[idx] = (int)my_radius;
-    tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
     depth_key[idx] = __float_as_uint(p_view.z);
 
     SplatRec rec;
@@ -199,12 +192,232 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     rec.d = make_float4(__uint_as_float(rect_min.x | (rect_min.y << 16)), __uint_as_float(rect_max.x | (rect_max.y << 16)),
                         0.f, 0.f);
     splat[idx] = rec;
+    return (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+}
+
+// Per Gaussian: preprocess_one. Per CTA: how many of its Gaussians are rendered and how many (Gaussian, tile) instances
+// they make -- the compaction kernel turns these into offsets, V and R (R is therefore known ~40 us into the frame,
+// long before the instance list is needed). On the side the grid clears the depth sort's digit histograms.
+__global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
+    int P, int D, int M, const float* __restrict__ orig_points, const float3* __restrict__ scales,
+    const float scale_modifier, const float4* __restrict__ rotations, const float* __restrict__ opacities,
+    const float* __restrict__ shs, uint8_t* __restrict__ clamped, const float* __restrict__ cov3D_precomp,
+    const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
+    const float* __restrict__ projmatrix, const float3* __restrict__ cam_pos, const int W, int H,
+    const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
+    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched,
+    uint32_t* __restrict__ depth_key, uint32_t* __restrict__ blk_vis, uint32_t* __restrict__ blk_tiles,
+    uint32_t* __restrict__ zeroed, size_t zeroed_words, int prefiltered) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ uint32_t warp_tiles[GVD_PRE_BLOCK / 32];
+    const int idx = blockIdx.x * GVD_PRE_BLOCK + threadIdx.x;
+    for (size_t i = (size_t)idx; i < zeroed_words; i += (size_t)gridDim.x * GVD_PRE_BLOCK) zeroed[i] = 0u;
+    uint32_t tiles = 0;
+    if (idx < P) {
+        tiles = preprocess_one(idx, D, M, orig_points, scales, scale_modifier, rotations, opacities, shs, clamped, cov3D_precomp,
+                               colors_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y, radii,
+                               splat, grid, depth_key, prefiltered);
+        tiles_touched[idx] = tiles;
+    }
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
+    if ((threadIdx.x & 31) == 0) warp_tiles[threadIdx.x >> 5] = wsum;
+    const int nvis = __syncthreads_count(tiles > 0);
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < GVD_PRE_BLOCK / 32; ++w) t += warp_tiles[w];
+        blk_vis[blockIdx.x] = (uint32_t)nvis;
+        blk_tiles[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ---- compaction of the visible Gaussians + depth sort ---------------------------------------------
+
+__device__ __forceinline__ uint32_t block_sum_1024(uint32_t v, uint32_t* warp_buf) {  // warp_buf[32]; result valid in warp 0
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0) warp_buf[warp] = v;
+    __syncthreads();
+    uint32_t r = 0;
+    if (warp == 0) r = __reduce_add_sync(0xffffffffu, warp_buf[lane]);
+    return r;
+}
+
+// CTA b owns the ids [b * 1024, (b + 1) * 1024): its visible ones go, in id order, to the compacted positions
+// base_b + rank (base_b = visible Gaussians of all earlier preprocess CTAs). Writes the (depth bits, id) pairs the sort
+// starts from, vis_id (kept for the backward), the four 8-bit digit histograms of all keys and pass 0's per-tile
+// histograms; the last CTA publishes V and R (device words and, if given, pinned host words).
+__global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
+    int P, int nb, const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ depth_key,
+    const uint32_t* __restrict__ blk_vis, const uint32_t* __restrict__ blk_tiles, uint32_t* __restrict__ key0,
+    uint32_t* __restrict__ val0, uint32_t* __restrict__ vis_id, uint32_t* __restrict__ counts, uint32_t* ghist,
+    uint32_t* thist0, uint32_t* shist0, int* r_host) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ uint32_t hist_s[4 * 256];
+    __shared__ uint32_t warp_buf[32];
+    __shared__ uint32_t warp_cnt[32];
+    __shared__ uint32_t s_base, s_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    hist_s[tid] = 0u;
+    const int first_blk = (int)blockIdx.x * (GVD_COMPACT_BLOCK / GVD_PRE_BLOCK);
+    uint32_t s = 0;
+    for (int k = (int)tid; k < first_blk && k < nb; k += GVD_COMPACT_BLOCK) s += blk_vis[k];
+    const int idx = (int)(blockIdx.x * GVD_COMPACT_BLOCK + tid);
+    const bool vis = idx < P && tiles_touched[idx] > 0;
+    const uint32_t key = vis ? depth_key[idx] : 0u;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) warp_cnt[warp] = __popc(ballot);
+    const uint32_t base_w0 = block_sum_1024(s, warp_buf);  // contains a __syncthreads: warp_cnt is visible below
+    if (warp == 0) {
+        const uint32_t c = warp_cnt[lane];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        warp_cnt[lane] = incl - c;
+        if (lane == 31) s_total = incl;
+        if (lane == 0) s_base = base_w0;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (vis) {
+        const uint32_t pos = base + warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u));
+        key0[pos] = key;
+        val0[pos] = (uint32_t)idx;
+        vis_id[pos] = (uint32_t)idx;
+        const uint32_t d0 = key & 255u;
+        atomicAdd(&hist_s[d0], 1u);
+        atomicAdd(&hist_s[256 + ((key >> 8) & 255u)], 1u);
+        atomicAdd(&hist_s[512 + ((key >> 16) & 255u)], 1u);
+        atomicAdd(&hist_s[768 + (key >> 24)], 1u);
+        atomicAdd(&thist0[(size_t)(pos / GVD_SORT_TILE) * 256 + d0], 1u);
+        atomicAdd(&shist0[(size_t)(pos / (GVD_SORT_TILE * GVD_SORT_SUPER)) * 256 + d0], 1u);
+    }
+    __syncthreads();
+    if (hist_s[tid]) atomicAdd(&ghist[tid], hist_s[tid]);
+    if (blockIdx.x == gridDim.x - 1) {
+        uint32_t r = 0;
+        for (int k = (int)tid; k < nb; k += GVD_COMPACT_BLOCK) r += blk_tiles[k];
+        // blocks past first_blk (this CTA's own preprocess blocks) are in s_total; earlier ones in base
+        const uint32_t R = block_sum_1024(r, warp_buf);
+        if (tid == 0) {
+            const uint32_t V = base + s_total;
+            counts[0] = V;
+            counts[1] = R;
+            // R (and V) go straight into the caller's pinned, device-mapped host words: a cudaMemcpyAsync in the compute
+            // stream queues behind whatever the copy engines are busy with (measured +46 us per step in round 1).
+            if (r_host != nullptr) {
+                reinterpret_cast<volatile int*>(r_host)[0] = (int)R;
+                reinterpret_cast<volatile int*>(r_host)[1] = (int)V;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// One pass of the stable LSD radix sort: CTA j ranks keys [j * 1024, ...) on the digit (key >> shift) & 255.
+//   offsets: digit d of tile j starts at  (keys of smaller digits, from ghist)
+//                                        + (keys with digit d in earlier tiles: full super-tiles from shist, the rest from thist)
+//   ranking: warp w owns 128 consecutive keys, 4 rounds of 32 (lane = consecutive index, so lane order = input order);
+//            same-digit lanes of a round are ranked with MATCH.ANY, rounds and warps through per-warp counters wh[w][d]
+//   while scattering, the CTA adds every key's NEXT digit to the histogram of the tile the key lands in, which is what the
+//   next pass looks up.
+__global__ void __launch_bounds__(GVD_SORT_THREADS) sort_pass_kernel(
+    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+    uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, const uint32_t* __restrict__ ghist,
+    const uint32_t* __restrict__ thist, const uint32_t* __restrict__ shist, uint32_t* thist_next, uint32_t* shist_next,
+    int shift, int next_shift) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int WARPS = GVD_SORT_THREADS / 32, PER_WARP = GVD_SORT_TILE / WARPS, ROUNDS = PER_WARP / 32;
+    static_assert(GVD_SORT_THREADS == 256, "one thread per digit in the offset phase");
+    __shared__ uint32_t wh[WARPS][256];
+    __shared__ uint32_t warp_tot[WARPS];
+    const uint32_t V = counts[0];
+    const uint32_t tile = blockIdx.x, start = tile * GVD_SORT_TILE;
+    if (start >= V) return;
+    const uint32_t n = min((uint32_t)GVD_SORT_TILE, V - start);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) wh[w][tid] = 0u;
+
+    uint32_t key[ROUNDS], val[ROUNDS];
+    bool valid[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint32_t off = warp * PER_WARP + r * 32 + lane;
+        valid[r] = off < n;
+        key[r] = valid[r] ? kin[start + off] : 0u;
+        val[r] = valid[r] ? vin[start + off] : 0u;
+    }
+    __syncthreads();
+    // phase A: per-warp digit counts
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint32_t d = valid[r] ? ((key[r] >> shift) & 255u) : (256u + lane);  // invalid lanes match nobody
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (valid[r] && (peers & lt_mask) == 0u) wh[warp][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase B: thread = digit. Exclusive scan over the warps, global start of the digit for this tile.
+    {
+        const uint32_t g = ghist[tid];
+        uint32_t incl = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        uint32_t prior = 0;
+        const uint32_t sup = tile / GVD_SORT_SUPER;
+        for (uint32_t sblk = 0; sblk < sup; ++sblk) prior += shist[(size_t)sblk * 256 + tid];
+        for (uint32_t t = sup * GVD_SORT_SUPER; t < tile; ++t) prior += thist[(size_t)t * 256 + tid];
+        __syncthreads();
+        uint32_t digit_base = incl - g;
+        for (uint32_t w = 0; w < warp; ++w) digit_base += warp_tot[w];
+        uint32_t run = digit_base + prior;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = wh[w][tid];
+            wh[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase C: stable scatter
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint32_t d = valid[r] ? ((key[r] >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pos = 0;
+        if (valid[r]) pos = wh[warp][d] + (uint32_t)__popc(peers & lt_mask);
+        __syncwarp();
+        if (valid[r] && (peers & lt_mask) == 0u) wh[warp][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+        if (valid[r]) {
+            kout[pos] = key[r];
+            vout[pos] = val[r];
+            if (next_shift >= 0) {
+                const uint32_t nd = (key[r] >> next_shift) & 255u;
+                atomicAdd(&thist_next[(size_t)(pos / GVD_SORT_TILE) * 256 + nd], 1u);
+                atomicAdd(&shist_next[(size_t)(pos / (GVD_SORT_TILE * GVD_SORT_SUPER)) * 256 + nd], 1u);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // ---- binning: rect-aware stable counting sort on the tile id -------------------------------------
 // Instance order required (and produced by the reference's stable sort on tile<<32|depth): tile-major;
-// inside a tile by depth, ties by Gaussian id. `order` already lists the Gaussians by (depth, id).
+// inside a tile by depth, ties by Gaussian id. `order` lists the V visible Gaussians by (depth, id).
 
 __device__ __forceinline__ void unpack_rect(const float4 d, uint32_t& x0, uint32_t& y0, uint32_t& x1, uint32_t& y1) {
     const uint32_t w0 = __float_as_uint(d.x), w1 = __float_as_uint(d.y);
@@ -214,31 +427,25 @@ __device__ __forceinline__ void unpack_rect(const float4 d, uint32_t& x0, uint32
 // Pass 1: chunk c = GVD_BIN_CHUNK depth-consecutive Gaussians order[c*CHUNK ..]. hist[c][t] = how many of them cover tile t.
 // A rect adds +1/-1 at its four corners of a (gy+1) x (gx+1) difference grid; a 2-D prefix sum then yields
 // the per-tile counts. Cost per chunk is O(CHUNK + T) whatever the rect sizes (no per-instance atomics).
-__global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(int P, uint32_t gx, uint32_t gy,
+__global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(const uint32_t* __restrict__ counts, uint32_t gx, uint32_t gy,
                                                                  const SplatRec* __restrict__ splat,
                                                                  const uint32_t* __restrict__ order,
-                                                                 const uint32_t* __restrict__ tiles_touched,
-                                                                 uint32_t* __restrict__ chunk_flags,
                                                                  uint32_t* __restrict__ hist) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ int diff[];  // (gy+1) rows of stride ld
+    const uint32_t V = counts[0];
+    if (blockIdx.x * GVD_BIN_CHUNK >= V) return;  // only a speculatively sized grid has such CTAs
     const int ld = (int)(gx + 1) | 1;  // odd stride: column walks are bank-conflict free
     const int rows = (int)gy + 1, cols = (int)gx + 1;
-    const int i = blockIdx.x * GVD_BIN_CHUNK + threadIdx.x;
+    const uint32_t i = blockIdx.x * GVD_BIN_CHUNK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t n = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    if (i < P) {
-        const uint32_t id = order[i];
-        n = tiles_touched[id];
-        if (n > 0) unpack_rect(splat[id].d, x0, y0, x1, y1);
-    }
-    const int any = __syncthreads_or(n > 0);
-    if (threadIdx.x == 0) chunk_flags[blockIdx.x] = any ? 1u : 0u;
-    if (!any) return;  // culled Gaussians sort last: this and all later chunks are empty
+    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    const bool live = i < V;
+    if (live) unpack_rect(splat[order[i]].d, x0, y0, x1, y1);
     for (int t = threadIdx.x; t < rows * ld; t += GVD_BIN_CHUNK) diff[t] = 0;
     __syncthreads();
-    if (n > 0) {
+    if (live) {
         atomicAdd(&diff[y0 * ld + x0], 1);
         atomicAdd(&diff[y0 * ld + x1], -1);
         atomicAdd(&diff[y1 * ld + x0], -1);
@@ -275,27 +482,16 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(int P, uint32_
     for (uint32_t t = threadIdx.x; t < gx * gy; t += GVD_BIN_CHUNK) row[t] = (uint32_t)diff[(t / gx) * ld + (t % gx)];
 }
 
-// Pass 2: per tile, exclusive prefix over the (valid) chunks, in place, and the tile's total.
+// Pass 2: per tile, exclusive prefix over the chunks, in place, and the tile's total.
 // CTA = 32 tiles x 32 chunk segments: every thread sums its segment, the segment sums are scanned through
 // shared memory, then every thread rewrites its segment as running prefixes.
-__global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int chunks, const uint32_t* __restrict__ chunk_flags,
+__global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int rows_cap, const uint32_t* __restrict__ counts,
                                                           uint32_t* hist, uint32_t* __restrict__ tile_total) {
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t seg_sum[32][33];
-    __shared__ int s_valid;
     const int tx = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_valid = 0;
-    __syncthreads();
-    {   // valid chunks form a prefix of the chunk array: count them
-        int c = 0;
-        for (int k = threadIdx.x; k < chunks; k += 1024) c += chunk_flags[k] ? 1 : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (tx == 0 && c) atomicAdd(&s_valid, c);
-    }
-    __syncthreads();
-    const int nv = s_valid;
+    const int nv = min(rows_cap, (int)((counts[0] + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK));
     const int per = (nv + 31) / 32;
     const int c0 = seg * per, c1 = min(nv, c0 + per);
     const int t = blockIdx.x * 32 + tx;
@@ -327,11 +523,10 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int chunks, con
     }
 }
 
-// Pass 3: exclusive scan over the tiles -> ranges (rasterizer_impl.cu:116-138 semantics: empty tiles (0,0))
-// and R. One CTA; T <= GVD_MAX_TILES.
+// Pass 3: exclusive scan over the tiles -> ranges (rasterizer_impl.cu:116-138 semantics: empty tiles (0,0)).
+// One CTA; T <= GVD_MAX_TILES. The scan total equals counts[1] (R) unless a speculative hist buffer was too small.
 __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t* __restrict__ tile_total,
-                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ num_rendered,
-                                                          int* r_host) {
+                                                          uint2* __restrict__ ranges) {
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t warp_sums[32];
@@ -367,149 +562,146 @@ __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t*
         if (tid == 1023) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
-    if (tid == 0) {
-        *num_rendered = carry_s;
-        // speculative path: R goes straight into the caller's pinned (device-mapped) host word. A cudaMemcpyAsync in
-        // the compute stream queues behind whatever the copy engines are busy with -- measured +46 us per step while
-        // a 6 MB host-to-device upload of the next step's inputs was in flight.
-        if (r_host != nullptr) {
-            *reinterpret_cast<volatile int*>(r_host) = (int)carry_s;
-            __threadfence_system();
-        }
-    }
 }
 
-// Pass 4: chunk c writes its Gaussians' ids into the tile lists in depth order: the slot of Gaussian g in tile t is
-// ranges[t].x + (chunk's starting rank in t, from pass 2) + (number of earlier Gaussians of the chunk covering t);
-// cnt[t] holds the next free slot of tile t. The only order constraint is per tile.
-//   chunks up to GVD_FILL_HEAVY instances: ONE warp walks the chunk's flattened (Gaussian, tile) sequence 32 instances
-//     at a time -- lane = instance, located by a load-balanced search over the chunk's instance offsets (REDUX.OR of
-//     the "a Gaussian starts here" bits + popc). Instances of a batch that fall into the same tile are ranked with
-//     MATCH.ANY (lane order = depth order); the first of each group advances cnt[t].
-//   heavier chunks (the Gaussians nearest to the camera, rects up to the whole screen; C2: median chunk 800 instances,
-//     largest 40 000): the tile ROWS are dealt out to the CTA's 8 warps (warp w owns rows ty = w mod 8); every warp
-//     walks the chunk on its own, lanes across the columns of the rect, no block barrier in the walk.
-// Measured: 85 us at C2, 265 us at C4 (1600x1066; a two-warp walk with a barrier per Gaussian took 445 us there).
-// Four other organisations (two-warp serial walk, rows over 4/8 warps for every chunk, shared-memory bit masks,
-// heavy chunks cut into slices over up to 32 CTAs) all land at 83-92 us at C2: the pass is bound by its 3.7 M
-// scattered 4-byte stores -- every 32-byte sector of a tile list is written by ~8 different chunks -- not by the walk.
-struct FillChunk {  // the chunk's non-empty Gaussians, compacted in order
-    uint32_t id[GVD_BIN_CHUNK], r0[GVD_BIN_CHUNK], r1[GVD_BIN_CHUNK], off[GVD_BIN_CHUNK + 1], magic[GVD_BIN_CHUNK];
-    uint32_t wn[2], wc[2];
+// Pass 4: chunk c writes its Gaussians' ids into the tile lists. The slot of Gaussian j (0..63, depth order inside the
+// chunk) in tile t is  ranges[t].x + hist[c][t] (the chunk's starting rank in t, from pass 2) + the number of earlier
+// Gaussians of the chunk that cover t.  That last term comes from two 32-bit coverage masks per tile in shared memory:
+//   phase 1  every (Gaussian, tile) instance of the chunk ORs bit j into mask[j / 32][t]   (native 32-bit ATOMS.OR)
+//   phase 2  every instance reads its tile's masks back: rank = popc(bits below j); one 4-byte store.
+// Both phases spread the chunk's flattened instance sequence over all 256 threads (binary search over the 64 instance
+// offsets), so there is no serial walk and no ordering between instances. Chunks above GVD_FILL_ROWS instances (the
+// Gaussians nearest to the camera, rects up to the whole screen) skip the per-instance search: (Gaussian, tile row)
+// units are dealt to the warps and the lanes run along the row.
+// Round 1's version walked each chunk with ONE warp, 32 instances at a time (load-balanced search + MATCH.ANY ranking,
+// 8.3 warp-instructions per instance, 80 us at C2). tools/ubench_scatter_store.cu showed the 3.7 M scattered 4-byte
+// stores themselves cost 25 us against 18.5 us for a coalesced stream, i.e. the walk was the cost, not the stores.
+// The masks cover a BAND of tile rows (the whole image when 2 * T words fit the shared-memory budget: always at the
+// benchmark sizes; larger images are walked band by band, restricted to the rows the chunk's Gaussians reach).
+struct FillChunk {  // the chunk's Gaussians in depth order
+    uint32_t id[GVD_BIN_CHUNK], r0[GVD_BIN_CHUNK], r1[GVD_BIN_CHUNK], off[GVD_BIN_CHUNK + 1], roff[GVD_BIN_CHUNK + 1], magic[GVD_BIN_CHUNK];
+    uint32_t wn[2], wr[2], wy0[2], wy1[2];
 };
 
 #define GVD_FILL_THREADS 256
-#define GVD_FILL_HEAVY 6144
-__global__ void __launch_bounds__(GVD_FILL_THREADS) bin_fill_kernel(int P, int T, uint32_t tiles_x,
-                                                                   const SplatRec* __restrict__ splat,
+#define GVD_FILL_ROWS 4096
+#define GVD_FILL_MASK_BYTES (160 * 1024)  // shared-memory budget of the two mask planes
+__device__ __forceinline__ uint32_t upper_slot(const uint32_t* off, uint32_t m, uint32_t q) {  // largest j < m with off[j] <= q
+    uint32_t lo = 0, hi = m;  // invariant: off[lo] <= q < off[hi]
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        if (hi - lo <= 1) break;
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(GVD_FILL_THREADS) bin_fill_kernel(const uint32_t* __restrict__ counts, int T, uint32_t tiles_x,
+                                                                   uint32_t band_rows, const SplatRec* __restrict__ splat,
                                                                    const uint32_t* __restrict__ order,
-                                                                   const uint32_t* __restrict__ tiles_touched,
-                                                                   const uint32_t* __restrict__ chunk_flags,
                                                                    const uint32_t* __restrict__ hist,
                                                                    const uint2* __restrict__ ranges,
                                                                    uint32_t* __restrict__ point_list, uint32_t capacity) {
     pdl_wait();
     pdl_trigger();
-    extern __shared__ uint32_t cnt[];
+    extern __shared__ uint32_t mask[];  // [2][band_rows * tiles_x]: bits 0..31 / 32..63 of the chunk's coverage of every tile
     __shared__ FillChunk fc;
-    static_assert(GVD_BIN_CHUNK == 64, "two warps load the chunk");
-    if (!chunk_flags[blockIdx.x]) return;
+    static_assert(GVD_BIN_CHUNK == 64, "two warps load the chunk; two mask words per tile");
+    const uint32_t V = counts[0];
+    if (blockIdx.x * GVD_BIN_CHUNK >= V) return;
+    const uint32_t m = min((uint32_t)GVD_BIN_CHUNK, V - blockIdx.x * GVD_BIN_CHUNK);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t* row = hist + (size_t)blockIdx.x * T;
-    // threads 0..63 load the chunk and compact its non-empty Gaussians (order kept)
-    uint32_t id = 0, n = 0, r0 = 0, r1 = 0, incl = 0, ballot = 0;
+    const uint32_t plane = band_rows * tiles_x;
     if (tid < GVD_BIN_CHUNK) {
-        const int i = blockIdx.x * GVD_BIN_CHUNK + (int)tid;
-        if (i < P) {
-            id = order[i];
-            n = tiles_touched[id];
-            if (n > 0) {
-                const float4 d = splat[id].d;
-                r0 = __float_as_uint(d.x);
-                r1 = __float_as_uint(d.y);
-            }
+        uint32_t n = 0, nr = 0, r0 = 0, r1 = 0, id = 0, ymin = 0xffffu, ymax = 0u;
+        if (tid < m) {
+            id = order[blockIdx.x * GVD_BIN_CHUNK + tid];
+            const float4 d = splat[id].d;
+            r0 = __float_as_uint(d.x);
+            r1 = __float_as_uint(d.y);
+            ymin = r0 >> 16;
+            ymax = r1 >> 16;
+            nr = ymax - ymin;
+            n = nr * ((r1 & 0xffff) - (r0 & 0xffff));
         }
-        ballot = __ballot_sync(0xffffffffu, n > 0);
-        incl = n;
+        uint32_t incl = n, rincl = nr;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += u;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o), ur = __shfl_up_sync(0xffffffffu, rincl, o);
+            if (lane >= (uint32_t)o) { incl += u; rincl += ur; }
         }
-        if (lane == 31) {
-            fc.wn[warp] = incl;
-            fc.wc[warp] = __popc(ballot);
-        }
-    }
-    for (uint32_t t = tid; t < (uint32_t)T; t += blockDim.x) cnt[t] = ranges[t].x + row[t];
-    __syncthreads();
-    const uint32_t m = fc.wc[0] + fc.wc[1], total = fc.wn[0] + fc.wn[1];
-    if (tid < GVD_BIN_CHUNK) {
-        const uint32_t base_n = warp ? fc.wn[0] : 0u, base_c = warp ? fc.wc[0] : 0u;
-        if (n > 0) {
-            const uint32_t j = base_c + __popc(ballot & lt_mask);
-            const uint32_t bw = (r1 & 0xffff) - (r0 & 0xffff);
-            fc.id[j] = id;
-            fc.r0[j] = r0;
-            fc.r1[j] = r1;
-            fc.off[j] = base_n + incl - n;
-            fc.magic[j] = 0xffffffffu / bw + 1u;  // floor(k / bw) == umulhi(k, magic) for k * bw < 2^32 (bw > 1)
-        }
-        if (tid == 0) fc.off[m] = total;
+        ymin = __reduce_min_sync(0xffffffffu, ymin);
+        ymax = __reduce_max_sync(0xffffffffu, ymax);
+        if (lane == 31) { fc.wn[warp] = incl; fc.wr[warp] = rincl; fc.wy0[warp] = ymin; fc.wy1[warp] = ymax; }
+        fc.id[tid] = id; fc.r0[tid] = r0; fc.r1[tid] = r1;
+        const uint32_t bw = (r1 & 0xffff) - (r0 & 0xffff);
+        fc.magic[tid] = bw > 1 ? 0xffffffffu / bw + 1u : 0u;  // floor(k / bw) == umulhi(k, magic) for k * bw < 2^32 (bw > 1)
+        fc.off[tid] = incl - n;     // warp 1's entries get warp 0's total added below
+        fc.roff[tid] = rincl - nr;
     }
     __syncthreads();
+    if (tid >= 32 && tid < GVD_BIN_CHUNK) { fc.off[tid] += fc.wn[0]; fc.roff[tid] += fc.wr[0]; }
+    if (tid == 0) { fc.off[GVD_BIN_CHUNK] = fc.wn[0] + fc.wn[1]; fc.roff[GVD_BIN_CHUNK] = fc.wr[0] + fc.wr[1]; }
+    __syncthreads();
+    const uint32_t total = fc.off[GVD_BIN_CHUNK], units = fc.roff[GVD_BIN_CHUNK];
+    const uint32_t ylo = min(fc.wy0[0], fc.wy0[1]), yhi = max(fc.wy1[0], fc.wy1[1]);  // tile rows the chunk reaches
 
-    if (total <= GVD_FILL_HEAVY) {
-        if (warp != 0) return;
-        const uint32_t le_mask = lt_mask | (1u << lane);
-        const uint32_t o_lo = lane < m ? fc.off[lane] : 0xffffffffu;
-        const uint32_t o_hi = lane + 32 < m ? fc.off[lane + 32] : 0xffffffffu;
-        uint32_t before = 0;  // compacted Gaussians that start before this batch
-        for (uint32_t b0 = 0; b0 < total; b0 += 32) {
-            uint32_t bits = 0;
-            if (o_lo - b0 < 32u) bits |= 1u << (o_lo - b0);
-            if (o_hi - b0 < 32u) bits |= 1u << (o_hi - b0);
-            const uint32_t starts = __reduce_or_sync(0xffffffffu, bits);
-            const uint32_t q = b0 + lane;
-            const bool valid = q < total;
-            uint32_t t = 0xffffff00u + lane, gid = 0;  // invalid lanes: distinct keys, they match nobody
-            if (valid) {
-                const uint32_t j = before + __popc(starts & le_mask) - 1u;
-                const uint32_t g0 = fc.r0[j], g1 = fc.r1[j];
-                const uint32_t x0 = g0 & 0xffff, bw = (g1 & 0xffff) - x0;
-                const uint32_t k = q - fc.off[j];
-                const uint32_t ry = bw > 1 ? __umulhi(k, fc.magic[j]) : k;
-                t = ((g0 >> 16) + ry) * tiles_x + x0 + (k - ry * bw);
-                gid = fc.id[j];
-            }
-            before += __popc(starts);
-            const uint32_t peers = __match_any_sync(0xffffffffu, t);
-            const uint32_t rank = __popc(peers & lt_mask);
-            const uint32_t base = valid ? cnt[t] : 0u;
-            __syncwarp();
-            if (valid) {
-                if (rank == 0) cnt[t] = base + __popc(peers);
-                const uint32_t slot = base + rank;
-                if (slot < capacity) point_list[slot] = gid;  // capacity: speculative buffers may be too small
-            }
-            __syncwarp();
+    for (uint32_t b0 = ylo - ylo % band_rows; b0 < yhi; b0 += band_rows) {
+        const uint32_t b1 = b0 + band_rows;
+        {   // clear the mask rows this chunk can touch inside the band
+            const uint32_t z0 = (max(b0, ylo) - b0) * tiles_x, z1 = (min(b1, yhi) - b0) * tiles_x;
+            for (uint32_t t = z0 + tid; t < z1; t += blockDim.x) { mask[t] = 0u; mask[plane + t] = 0u; }
         }
-        return;
-    }
-
-    for (uint32_t g = 0; g < m; ++g) {
-        const uint32_t g0 = fc.r0[g], g1 = fc.r1[g];
-        const uint32_t y0 = g0 >> 16, y1 = g1 >> 16, x0 = g0 & 0xffff, x1 = g1 & 0xffff;
-        const uint32_t gid = fc.id[g];
-        for (uint32_t ty = y0 + (warp + nw - y0 % nw) % nw; ty < y1; ty += nw)
-            for (uint32_t tx = x0 + lane; tx < x1; tx += 32) {
-                const uint32_t t = ty * tiles_x + tx;
-                const uint32_t slot = cnt[t];
-                cnt[t] = slot + 1;
-                if (slot < capacity) point_list[slot] = gid;
+        __syncthreads();
+        for (int phase = 0; phase < 2; ++phase) {
+            if (total <= GVD_FILL_ROWS) {
+                // flattened (Gaussian, tile) instances over all threads
+                for (uint32_t q = tid; q < total; q += blockDim.x) {
+                    const uint32_t j = upper_slot(fc.off, GVD_BIN_CHUNK, q);
+                    const uint32_t g0 = fc.r0[j], g1 = fc.r1[j];
+                    const uint32_t x0 = g0 & 0xffff, bw = (g1 & 0xffff) - x0;
+                    const uint32_t k = q - fc.off[j];
+                    const uint32_t ry = bw > 1 ? __umulhi(k, fc.magic[j]) : k;
+                    const uint32_t ty = (g0 >> 16) + ry, tx = x0 + (k - ry * bw);
+                    if (ty < b0 || ty >= b1) continue;
+                    const uint32_t lt = (ty - b0) * tiles_x + tx;
+                    if (phase == 0) {
+                        atomicOr(&mask[(j >> 5) * plane + lt], 1u << (j & 31));
+                    } else {
+                        const uint32_t lo = mask[lt];
+                        const uint32_t rank = j < 32 ? __popc(lo & ((1u << j) - 1u))
+                                                     : __popc(lo) + __popc(mask[plane + lt] & ((1u << (j - 32)) - 1u));
+                        const uint32_t t = ty * tiles_x + tx;
+                        const uint32_t slot = ranges[t].x + row[t] + rank;
+                        if (slot < capacity) point_list[slot] = fc.id[j];  // capacity: speculative buffers may be too small
+                    }
+                }
+            } else {
+                // heavy chunk: (Gaussian, tile row) units over the warps, lanes along the row
+                for (uint32_t u = warp; u < units; u += nw) {
+                    const uint32_t j = upper_slot(fc.roff, GVD_BIN_CHUNK, u);
+                    const uint32_t g0 = fc.r0[j], g1 = fc.r1[j];
+                    const uint32_t ty = (g0 >> 16) + (u - fc.roff[j]), x0 = g0 & 0xffff, x1 = g1 & 0xffff;
+                    if (ty < b0 || ty >= b1) continue;
+                    const uint32_t gid = fc.id[j], bit = 1u << (j & 31), below = bit - 1u;
+                    for (uint32_t tx = x0 + lane; tx < x1; tx += 32) {
+                        const uint32_t lt = (ty - b0) * tiles_x + tx;
+                        if (phase == 0) {
+                            atomicOr(&mask[(j >> 5) * plane + lt], bit);
+                        } else {
+                            const uint32_t lo = mask[lt];
+                            const uint32_t rank = j < 32 ? __popc(lo & below) : __popc(lo) + __popc(mask[plane + lt] & below);
+                            const uint32_t t = ty * tiles_x + tx;
+                            const uint32_t slot = ranges[t].x + row[t] + rank;
+                            if (slot < capacity) point_list[slot] = gid;
+                        }
+                    }
+                }
             }
-        __syncwarp();  // lanes change tiles from one Gaussian to the next: keep the warp's walk in step
+            __syncthreads();
+        }
     }
 }
 
@@ -682,13 +874,33 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 }  // namespace
 
-void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, float focal_x, float focal_y,
-                           dim3 grid, cudaStream_t s) {
-    gvd_launch(preprocess_kernel, dim3((a.P + 255) / 256), dim3(256), 0, s, 
+void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterSortPtrs& so, float focal_x,
+                           float focal_y, dim3 grid, cudaStream_t s) {
+    gvd_launch(preprocess_kernel, dim3((unsigned)so.nb), dim3(GVD_PRE_BLOCK), 0, s,
         a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
         a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
         (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
-        g.tiles_touched, g.depth_key, g.gidx, a.prefiltered);
+        g.tiles_touched, so.depth_key, so.blk_vis, so.blk_tiles, so.zeroed, so.zeroed_words, a.prefiltered);
+}
+
+void gvd_launch_compact(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, int* r_host, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((P + GVD_COMPACT_BLOCK - 1) / GVD_COMPACT_BLOCK);
+    gvd_launch(compact_kernel, dim3(blocks), dim3(GVD_COMPACT_BLOCK), 0, s, P, (int)so.nb, g.tiles_touched, so.depth_key, so.blk_vis,
+               so.blk_tiles, so.key[0], so.val[0], g.vis_id, g.counts, so.ghist, so.thist, so.shist, r_host);
+}
+
+void gvd_launch_depth_sort(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, cudaStream_t s) {
+    // grid sized for V = P (V lives in device memory); CTAs whose tile starts at or past V return at once
+    const unsigned blocks = (unsigned)so.nt;
+    (void)P;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int in = pass & 1, out = in ^ 1;
+        uint32_t* th_next = pass < 3 ? so.thist + (size_t)(pass + 1) * so.nt * 256 : nullptr;
+        uint32_t* sh_next = pass < 3 ? so.shist + (size_t)(pass + 1) * so.ns * 256 : nullptr;
+        gvd_launch(sort_pass_kernel, dim3(blocks), dim3(GVD_SORT_THREADS), 0, s, g.counts, so.key[in], so.val[in], so.key[out],
+                   so.val[out], so.ghist + pass * 256, so.thist + (size_t)pass * so.nt * 256, so.shist + (size_t)pass * so.ns * 256,
+                   th_next, sh_next, 8 * pass, pass < 3 ? 8 * (pass + 1) : -1);
+    }
 }
 
 static cudaError_t ensure_smem(const void* fn, size_t bytes) {
@@ -696,35 +908,38 @@ static cudaError_t ensure_smem(const void* fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t gvd_launch_bin_count(int P, const RasterGeomPtrs& g, const RasterImgPtrs& im, dim3 grid, int* r_host,
-                                 cudaStream_t s) {
+cudaError_t gvd_launch_bin_count(const RasterGeomPtrs& g, const RasterSortPtrs& so, const RasterHistPtrs& h, const RasterImgPtrs& im,
+                                 dim3 grid, cudaStream_t s) {
     const int T = (int)(grid.x * grid.y);
     const size_t smem = (size_t)(grid.y + 1) * ((grid.x + 1) | 1) * sizeof(int);
     cudaError_t e = ensure_smem((const void*)bin_count_kernel, smem);
     if (e != cudaSuccess) return e;
-    gvd_launch(bin_count_kernel, dim3((unsigned)g.chunks), dim3(GVD_BIN_CHUNK), smem, s, P, grid.x, grid.y, g.splat, g.order,
-                                                                    g.tiles_touched, g.chunk_flags, g.hist);
-    gvd_launch(bin_prefix_kernel, dim3((T + 31) / 32), dim3(1024), 0, s, T, (int)g.chunks, g.chunk_flags, g.hist, g.tile_total);
-    gvd_launch(bin_ranges_kernel, dim3(1), dim3(1024), 0, s, T, g.tile_total, im.ranges, g.num_rendered, r_host);
+    if (h.rows > 0)
+        gvd_launch(bin_count_kernel, dim3((unsigned)h.rows), dim3(GVD_BIN_CHUNK), smem, s, g.counts, grid.x, grid.y, g.splat, so.val[0], h.hist);
+    gvd_launch(bin_prefix_kernel, dim3((T + 31) / 32), dim3(1024), 0, s, T, (int)h.rows, g.counts, h.hist, h.tile_total);
+    gvd_launch(bin_ranges_kernel, dim3(1), dim3(1024), 0, s, T, h.tile_total, im.ranges);
     return cudaGetLastError();
 }
 
-cudaError_t gvd_launch_bin_fill(int P, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
-                                dim3 grid, uint32_t capacity, cudaStream_t s) {
+cudaError_t gvd_launch_bin_fill(const RasterGeomPtrs& g, const RasterSortPtrs& so, const RasterHistPtrs& h, const RasterBinPtrs& b,
+                                const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s) {
     const int T = (int)(grid.x * grid.y);
-    const size_t smem = (size_t)T * sizeof(uint32_t);
+    // rows of tiles whose two mask planes fit the budget (all of them up to 20 480 tiles)
+    const uint32_t band_rows = (uint32_t)std::max<size_t>(1, std::min<size_t>(grid.y, GVD_FILL_MASK_BYTES / (2 * sizeof(uint32_t) * grid.x)));
+    const size_t smem = (size_t)2 * band_rows * grid.x * sizeof(uint32_t);
     cudaError_t e = ensure_smem((const void*)bin_fill_kernel, smem);
     if (e != cudaSuccess) return e;
-    gvd_launch(bin_fill_kernel, dim3((unsigned)g.chunks), dim3(GVD_FILL_THREADS), smem, s, P, T, grid.x, g.splat, g.order,
-               g.tiles_touched, g.chunk_flags, g.hist, im.ranges, b.point_list, capacity);
+    if (h.rows > 0)
+        gvd_launch(bin_fill_kernel, dim3((unsigned)h.rows), dim3(GVD_FILL_THREADS), smem, s, g.counts, T, grid.x, band_rows, g.splat,
+                   so.val[0], h.hist, im.ranges, b.point_list, capacity);
     return cudaGetLastError();
 }
 
-void gvd_launch_export_keys(uint32_t capacity, const RasterGeomPtrs& g, const RasterBinPtrs& b, const RasterImgPtrs& im,
+void gvd_launch_export_keys(uint32_t capacity, const RasterSortPtrs& so, const RasterBinPtrs& b, const RasterImgPtrs& im,
                             dim3 grid, cudaStream_t s) {
     if (capacity == 0 || !b.keys) return;
     const int T = (int)(grid.x * grid.y);
-    gvd_launch(export_keys_kernel, dim3(T), dim3(256), 0, s, capacity, T, im.ranges, b.point_list, g.depth_key, b.keys);
+    gvd_launch(export_keys_kernel, dim3(T), dim3(256), 0, s, capacity, T, im.ranges, b.point_list, so.depth_key, b.keys);
 }
 
 int gvd_render_split() {

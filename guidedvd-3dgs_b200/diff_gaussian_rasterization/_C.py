@@ -37,32 +37,47 @@ def _f32c(t, name):
 EXPORT_KEYS = False
 
 
-# Speculative sizing of the instance buffer: after the first frame on a device the shim allocates the buffer from the
-# largest R seen so far (x2 + 1 Mi entries; 4 bytes each) and lets the library queue every stage without the host round
-# trip the reference makes (rasterizer_impl.cu:281-282).  R arrives through pinned memory and is validated
-#   * before the forward returns when called without autograd (GVD_SPECULATE=sync forces this everywhere), falling
-#     back to the exact, synchronous path when a frame outgrows the guess;
-#   * at the start of the backward when called through the autograd Function: the host never waits for the GPU
-#     between forward and backward, so launch overhead hides behind the kernels.  A frame that outgrew the buffer
-#     (R more than doubled against every earlier frame) cannot be repaired at that point -- its image was already
-#     consumed -- and raises RuntimeError there; the grown history makes the retry fit.
-_MODE = os.environ.get("GVD_SPECULATE", "1")
-SPECULATE = _MODE != "0"
-DEFER = _MODE not in ("0", "sync")
+# How the instance buffer (4 bytes x R) and the chunk histogram (sized by V) get their sizes.  R and V are produced by
+# the second kernel of the forward, ~40 us into the frame (include/gvd_raster.h), and stored straight into pinned
+# host memory.
+#   EXACT (default): the library waits for those two words only -- the depth sort is already queued behind them, so
+#     the GPU never idles -- and calls back for exactly sized buffers.  Always valid, never raises later; this is the
+#     reference's contract (rasterizer_impl.cu:281-286) without its pipeline bubble.
+#   DEFER (GVD_SPECULATE=defer, opt-in; bench.py names it in `config` when used): from the second frame on a device
+#     the buffers are sized from the largest R / V seen so far (x2 + slack) and NOTHING waits: R is validated at the
+#     start of the backward (or at the next forward for a frame that never got one).  A frame that outgrew its buffers
+#     has already been consumed by then; the backward repairs what it can -- it re-renders the frame exactly, warns,
+#     and returns the gradients of the exact frame -- so an unmodified trainer keeps running.
+_MODE = os.environ.get("GVD_SPECULATE", "exact")
+DEFER = _MODE in ("1", "defer")
+SPECULATE = DEFER  # kept for callers that probe the old name
 _spec_state = {}
+
+
+class SpeculationOverflow(RuntimeError):
+    """A deferred frame produced more instances / visible Gaussians than its speculative buffers held."""
+
+
+class Counts(int):
+    """R (the reference's `num_rendered`) as an int that also carries V, the number of visible Gaussians."""
+
+    def __new__(cls, R, V):
+        o = int.__new__(cls, R)
+        o.visible = int(V)
+        return o
 
 
 def _new_slot(dev):
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(dev))  # forces creation of the underlying cudaEvent_t
-    pinned = torch.zeros(1, dtype=torch.int32).pin_memory()
+    pinned = torch.zeros(2, dtype=torch.int32).pin_memory()
     return {"pinned": pinned, "host": pinned.numpy(), "ptr": pinned.data_ptr(), "event": ev, "cuda_event": ev.cuda_event}
 
 
 def _spec(dev):
     st = _spec_state.get(dev)
     if st is None:
-        st = _spec_state[dev] = {"max_R": None, "free": [_new_slot(dev)]}
+        st = _spec_state[dev] = {"max_R": None, "max_V": None, "free": [_new_slot(dev)], "open": []}
     return st
 
 
@@ -70,31 +85,48 @@ def _capacity(max_R):
     return 2 * int(max_R) + (1 << 20)
 
 
-class PendingR:
-    """R of a forward whose validation was deferred (see DEFER above).  int(obj) / obj.resolve() waits for the scan of
-    that frame (not for its render kernels), validates the speculative buffer and returns R."""
-    __slots__ = ("slot", "cap", "st", "value", "error")
+def _visible_capacity(max_V, P):
+    return min(int(P), 2 * int(max_V) + (1 << 14))
 
-    def __init__(self, slot, cap, st):
-        self.slot, self.cap, self.st, self.value, self.error = slot, cap, st, None, None
+
+def _note(st, R, V):
+    if st["max_R"] is None or R > st["max_R"]:
+        st["max_R"] = R
+    if st["max_V"] is None or V > st["max_V"]:
+        st["max_V"] = V
+
+
+class PendingR:
+    """R and V of a forward whose validation was deferred (see DEFER above).  int(obj) / obj.resolve() waits for the
+    second kernel of that frame (not for its render kernels), validates the speculative buffers and returns a Counts."""
+    __slots__ = ("slot", "cap", "vcap", "st", "value", "error", "__weakref__")
+
+    def __init__(self, slot, cap, vcap, st):
+        self.slot, self.cap, self.vcap, self.st, self.value, self.error = slot, cap, vcap, st, None, None
+
+    def done(self):
+        return self.slot is None or self.slot["event"].query()
 
     def resolve(self):
         if self.value is None:
             slot, self.slot = self.slot, None
             slot["event"].synchronize()
-            R = self.value = int(slot["host"][0])
+            R, V = int(slot["host"][0]), int(slot["host"][1])
+            self.value = Counts(R, V)
             self.st["free"].append(slot)
-            if self.st["max_R"] is None or R > self.st["max_R"]:
-                self.st["max_R"] = R
-            if R + 128 > self.cap:
-                self.error = (f"diff_gaussian_rasterization: this frame produced R={R} (Gaussian, tile) instances, more "
-                              f"than the speculative instance buffer of {self.cap} entries sized from earlier frames; its "
-                              "outputs are invalid. Repeat the step (the buffer has grown) or set GVD_SPECULATE=sync.")
+            _note(self.st, R, V)
+            if R + 128 > self.cap or V > self.vcap:
+                self.error = (f"diff_gaussian_rasterization: this frame produced R={R} instances from V={V} visible Gaussians, "
+                              f"more than its speculative buffers (R <= {self.cap - 128}, V <= {self.vcap}) sized from earlier "
+                              "frames; the image it returned is incomplete.  GVD_SPECULATE=exact (the default) never does this.")
         if self.error is not None:
-            raise RuntimeError(self.error)
+            raise SpeculationOverflow(self.error)
         return self.value
 
-    __int__ = __index__ = resolve
+    def __int__(self):
+        return int(self.resolve())
+
+    __index__ = __int__
 
     def __del__(self):
         if self.value is None and self.slot is not None:
@@ -103,6 +135,26 @@ class PendingR:
             except Exception as ex:  # never raise from a finaliser
                 import warnings
                 warnings.warn(str(ex))
+
+
+def _settle_open(st):
+    """Deferred frames that never reached a backward (renders under grad mode that were only looked at): validate the
+    ones whose counts have arrived, so an overflow is reported at the next render instead of at garbage collection."""
+    import warnings
+
+    keep = []
+    for ref in st["open"]:
+        p = ref()
+        if p is None or p.value is not None or p.error is not None:
+            continue
+        if p.done():
+            try:
+                p.resolve()
+            except SpeculationOverflow as ex:
+                warnings.warn(str(ex))
+        else:
+            keep.append(ref)
+    st["open"] = keep
 
 
 # Optional caller-owned gradient storage per device (set_gradient_buffer): the backward then writes its gradients there
@@ -158,22 +210,23 @@ class _on_device:
         return False
 
 
-class _BinningAlloc:
-    """Caller-owned instance buffer of the exact path, sized by the library through a C callback once R is known
-    (the reference's resizeFunctional, DGR/rasterize_points.cu:27-33)."""
+class _Alloc:
+    """Caller-owned scratch handed to the library through a C callback once the size is known (the reference's
+    resizeFunctional, DGR/rasterize_points.cu:27-33).  Every buffer it hands out stays referenced in `bufs`."""
 
     def __init__(self, device):
-        self.device, self.buf = device, None
+        self.device, self.bufs = device, []
         self.cb = _n.ALLOC_FN(self._alloc)
 
     def _alloc(self, user, nbytes):
-        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self.buf.data_ptr()
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.bufs.append(buf)
+        return buf.data_ptr()
 
     def take(self):
-        """Hand the buffer over and drop the callback closure: it references `self`, and a reference cycle would
+        """Hand the buffers over and drop the callback closure: it references `self`, and a reference cycle would
         keep the scratch alive until the cyclic GC runs."""
-        out, self.buf, self.cb = self.buf, None, None
+        out, self.bufs, self.cb = self.bufs, [], None
         return out
 
 
@@ -213,9 +266,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
     sizes = _scratch_sizes.get((P, W, H))
     if sizes is None:
-        sizes = _scratch_sizes[(P, W, H)] = (int(lib.gvd_raster_geom_bytes(P, W, H)), int(lib.gvd_raster_img_bytes(W, H)))
-    spec_on = SPECULATE and not debug and not EXPORT_KEYS
-    st = _spec(dev) if spec_on else None
+        sizes = _scratch_sizes[(P, W, H)] = (int(lib.gvd_raster_geom_bytes(P, W, H)), int(lib.gvd_raster_img_bytes(W, H)),
+                                             int(lib.gvd_raster_sort_bytes(P)), int(lib.gvd_raster_hist_bytes(0, W, H)),
+                                             4 * ((W + 15) // 16) * ((H + 15) // 16))
+    plain = debug or EXPORT_KEYS          # debug / parity runs: the library's own synchronous route, no pinned words
+    st = None if plain else _spec(dev)
     pending = None
     with _on_device(dev):
         out_color = torch.empty((3, H, W), dtype=_F32, device=dev)
@@ -224,6 +279,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom = torch.empty((sizes[0],), dtype=torch.uint8, device=dev)
         img = torch.empty((sizes[1],), dtype=torch.uint8, device=dev)
+        sort = torch.empty((sizes[2],), dtype=torch.uint8, device=dev)  # forward-only; released when this call returns
 
         a = _n.RasterForwardArgs()
         a.P, a.D, a.M, a.width, a.height = P, int(degree), (sh.size(1) if sh is not None and sh.numel() else 0), W, H
@@ -244,45 +300,51 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         a.out_color, a.out_depth, a.out_alpha, a.radii = (out_color.data_ptr(), out_depth.data_ptr(),
                                                             out_alpha.data_ptr(), radii.data_ptr())
         a.geom_buffer, a.geom_bytes, a.img_buffer, a.img_bytes = geom.data_ptr(), sizes[0], img.data_ptr(), sizes[1]
+        a.sort_buffer, a.sort_bytes = sort.data_ptr(), sizes[2]
         stream = _stream()
 
         binning, rc, done = None, 0, False
-        if st is not None and st["max_R"] is not None:
-            cap = _capacity(st["max_R"])
+        if st is not None:
+            _settle_open(st)
+        if st is not None and DEFER and defer and st["max_R"] is not None:
+            cap, vcap = _capacity(st["max_R"]), _visible_capacity(st["max_V"], P)
             nbytes = 4 * cap + 1024  # >= gvd_raster_binning_bytes(cap, 0)
+            hbytes = sizes[3] + sizes[4] * ((vcap + 63) // 64) + 1024  # >= gvd_raster_hist_bytes(vcap, W, H)
             binning = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            hist = torch.empty((hbytes,), dtype=torch.uint8, device=dev)
             slot = st["free"].pop() if st["free"] else _new_slot(dev)
             a.spec_binning_buffer, a.spec_binning_bytes = binning.data_ptr(), nbytes
+            a.spec_hist_buffer, a.spec_hist_bytes = hist.data_ptr(), hbytes
             a.num_rendered_pinned, a.r_ready_event = slot["ptr"], slot["cuda_event"]
             rc = lib.gvd_raster_forward(C.byref(a), stream)
             if rc != 0:
                 st["free"].append(slot)
             else:
-                pending = PendingR(slot, cap, st)
-                if defer and DEFER:
-                    done = True
-                else:
-                    try:
-                        a.num_rendered = pending.resolve()  # waits for the scan, not for the render kernels behind it
-                        done = True
-                    except RuntimeError:
-                        # the guess was too small: redo this frame on the exact path below
-                        a.spec_binning_buffer, a.spec_binning_bytes, binning = None, 0, None
-                    pending = None
+                import weakref
+                pending = PendingR(slot, cap, vcap, st)
+                st["open"].append(weakref.ref(pending))
+                done = True
         if rc == 0 and not done:
-            alloc = _BinningAlloc(dev)
-            a.binning_alloc = alloc.cb
+            alloc = _Alloc(dev)
+            a.binning_alloc = a.temp_alloc = alloc.cb
+            slot = None
+            if st is not None:
+                slot = st["free"].pop() if st["free"] else _new_slot(dev)
+                a.num_rendered_pinned, a.r_ready_event = slot["ptr"], slot["cuda_event"]
             rc = lib.gvd_raster_forward(C.byref(a), stream)
-            a.binning_alloc = _n.ALLOC_FN(0)
-            binning = alloc.take()
-            if rc == 0 and st is not None and (st["max_R"] is None or a.num_rendered > st["max_R"]):
-                st["max_R"] = int(a.num_rendered)
+            a.binning_alloc = a.temp_alloc = _n.ALLOC_FN(0)
+            bufs = alloc.take()  # [instance list, chunk histogram]; the histogram is forward-only
+            binning = bufs[0] if bufs else None
+            if slot is not None:
+                st["free"].append(slot)
+            if rc == 0 and st is not None:
+                _note(st, int(a.num_rendered), int(a.num_visible))
     if rc != 0:
         raise RuntimeError("gvd_raster_forward failed: " + _n.last_error(lib))
     if binning is None:
         binning = torch.empty(0, dtype=torch.uint8, device=dev)
-    return (pending if pending is not None else int(a.num_rendered), out_color, out_depth, out_alpha, radii, geom,
-            binning, img)
+    return (pending if pending is not None else Counts(a.num_rendered, a.num_visible), out_color, out_depth, out_alpha, radii,
+            geom, binning, img)
 
 
 _view_cache = {}
@@ -327,7 +389,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     if P == 0:
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
         return z(0, 3), z(0, 3), z(0, 1), z(0, 3), z(0, 6), z(0, M, 3), z(0, 3), z(0, 4)
-    R = int(R)  # a deferred R is validated here (raises if the frame outgrew its speculative buffer)
+    if isinstance(R, PendingR):
+        R = R.resolve()  # a deferred R is validated here (SpeculationOverflow if the frame outgrew its speculative buffers)
+    V, R = getattr(R, "visible", -1), int(R)
 
     total = sum((P * w + 3) // 4 * 4 for w in (3, 3 * M if has_sh else 0, 1, 3 if has_scales else 0,
                                                 4 if has_scales else 0, 3 if has_colors else 0, 6 if has_cov else 0, 3))
@@ -341,11 +405,13 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 _view_cache.clear()
                 views = _view_cache[key] = _grad_views(ext[:total], P, M, has_sh, has_scales, has_colors, has_cov)
         else:
-            views = _grad_views(torch.empty((total,), dtype=_F32, device=dev), P, M, has_sh, has_scales, has_colors,
-                                has_cov)
+            ext = None
+            flat = torch.empty((total,), dtype=_F32, device=dev)
+            views = _grad_views(flat, P, M, has_sh, has_scales, has_colors, has_cov)
         # gradients of absent inputs are never consumed: None instead of the reference's unused zero tensors
         dL_dmeans2D, dL_dmeans3D, dL_dopacity, dL_dcolors, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations = views
-        if ext is not None and ext.numel() >= total:
+        zero_ptr = ext.data_ptr() if ext is not None else flat.data_ptr()
+        if ext is not None:
             _last_views[dev] = {"means2D": dL_dmeans2D, "means3D": dL_dmeans3D, "opacities": dL_dopacity,
                                 "colors_precomp": dL_dcolors, "cov3D_precomp": dL_dcov3D, "shs": dL_dsh,
                                 "scales": dL_dscales, "rotations": dL_drotations, "_floats": total}
@@ -370,6 +436,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
 
         a = _n.RasterBackwardArgs()
         a.P, a.D, a.M, a.R, a.width, a.height = P, int(degree), M, R, W, H
+        a.num_visible = int(V)
+        a.zero_region, a.zero_region_bytes = zero_ptr, 4 * total  # all eight gradients are views of this one region
         a.background, a.means3D, a.shs = _ptr(background), _ptr(means3D), _ptr(sh)
         a.colors_precomp, a.scales, a.rotations = _ptr(colors), _ptr(scales), _ptr(rotations)
         a.cov3D_precomp, a.viewmatrix, a.projmatrix, a.campos = (_ptr(cov3D_precomp), _ptr(viewmatrix),

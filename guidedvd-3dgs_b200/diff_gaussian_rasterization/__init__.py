@@ -30,8 +30,9 @@ def cpu_deep_copy_tuple(input_tuple):
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings):
     # Will a backward come?  (Inside Function.forward grad mode is always off and ctx.needs_input_grad ignores
-    # torch.no_grad(), so this is decided here.)  If so, validation of the speculative instance buffer is deferred
-    # to the backward (see _C.DEFER).
+    # torch.no_grad(), so this is decided here.)  Only matters under the opt-in GVD_SPECULATE=defer mode, where the
+    # validation of the speculative buffers then moves to the backward (see _C.DEFER); the default sizes every
+    # buffer exactly inside the forward.
     defer = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad
         for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
@@ -62,6 +63,9 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
+        # a deferred frame may have to be re-rendered by its backward (see there); opacities is the one forward input
+        # the backward does not otherwise keep
+        ctx.opacities = opacities if isinstance(num_rendered, _C.PendingR) else None
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
                               binningBuffer, imgBuffer, alpha)
         ctx.mark_non_differentiable(radii)
@@ -73,7 +77,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
          imgBuffer, alpha) = ctx.saved_tensors
         conf = rs.confidence
-        ctx.num_rendered = int(ctx.num_rendered)  # resolves a deferred R; raises if that frame outgrew its buffer
+        if isinstance(ctx.num_rendered, _C.PendingR):
+            try:
+                ctx.num_rendered = ctx.num_rendered.resolve()
+            except _C.SpeculationOverflow as ex:
+                # GVD_SPECULATE=defer only.  The image this frame returned was incomplete and has been consumed; what
+                # can still be done is to keep the trainer alive and hand it the gradients of the frame as it should
+                # have been: re-render exactly (same inputs, exact buffers) and continue with those buffers.
+                import warnings
+                warnings.warn(str(ex) + "  Re-rendered exactly for the backward; this step's loss saw the incomplete image.")
+                redo = _C.rasterize_gaussians(rs.bg, means3D, colors_precomp, ctx.opacities, scales, rotations, rs.scale_modifier,
+                                              cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+                                              rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered,
+                                              rs.debug, defer=False)
+                ctx.num_rendered, _, _, alpha, radii, geomBuffer, binningBuffer, imgBuffer = redo
         if conf is not None and conf.numel() != means3D.size(0):
             raise RuntimeError("confidence must hold one value per Gaussian")
         args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,

@@ -23,18 +23,20 @@ class RasterForwardArgs(C.Structure):
         ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
         ("prefiltered", C.c_int), ("debug", C.c_int), ("export_keys", C.c_int),
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
-        ("geom_alloc", ALLOC_FN), ("binning_alloc", ALLOC_FN), ("img_alloc", ALLOC_FN),
+        ("geom_alloc", ALLOC_FN), ("binning_alloc", ALLOC_FN), ("img_alloc", ALLOC_FN), ("temp_alloc", ALLOC_FN),
         ("alloc_user", C.c_void_p),
         ("geom_buffer", C.c_void_p), ("geom_bytes", C.c_size_t), ("img_buffer", C.c_void_p), ("img_bytes", C.c_size_t),
+        ("sort_buffer", C.c_void_p), ("sort_bytes", C.c_size_t),
         ("spec_binning_buffer", C.c_void_p), ("spec_binning_bytes", C.c_size_t),
+        ("spec_hist_buffer", C.c_void_p), ("spec_hist_bytes", C.c_size_t),
         ("num_rendered_pinned", C.c_void_p), ("r_ready_event", C.c_void_p),
-        ("num_rendered", C.c_int),
+        ("num_rendered", C.c_int), ("num_visible", C.c_int),
     ]
 
 
 class RasterBackwardArgs(C.Structure):
     _fields_ = [
-        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int), ("width", C.c_int), ("height", C.c_int),
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int), ("num_visible", C.c_int), ("width", C.c_int), ("height", C.c_int),
         ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p),
         ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
         ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
@@ -45,6 +47,7 @@ class RasterBackwardArgs(C.Structure):
         ("dL_dpix", C.c_void_p), ("dL_ddepth_pix", C.c_void_p), ("dL_dalpha_pix", C.c_void_p),
         ("confidence", C.c_void_p),
         ("scratch", C.c_void_p),
+        ("zero_region", C.c_void_p), ("zero_region_bytes", C.c_size_t),
         ("dL_dmeans2D", C.c_void_p), ("dL_dmeans3D", C.c_void_p), ("dL_dopacity", C.c_void_p),
         ("dL_dcolors", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
         ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
@@ -54,7 +57,7 @@ class RasterBackwardArgs(C.Structure):
 
 class RasterLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "geom_splat", "geom_clamped", "geom_tiles_touched", "geom_order",
+        "geom_splat", "geom_clamped", "geom_tiles_touched", "geom_visible_ids", "geom_counts",
         "bin_point_list", "bin_point_list_keys",
         "img_ranges", "img_n_contrib")]
 
@@ -69,7 +72,7 @@ class RasterStageTimes(C.Structure):
 RASTER_SYMBOLS = (
     "gvd_raster_profile_enable", "gvd_raster_profile_read",
     "gvd_raster_abi_version", "gvd_last_error", "gvd_raster_geom_bytes", "gvd_raster_binning_bytes",
-    "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes", "gvd_raster_layout",
+    "gvd_raster_img_bytes", "gvd_raster_sort_bytes", "gvd_raster_hist_bytes", "gvd_raster_backward_scratch_bytes", "gvd_raster_layout",
     "gvd_raster_forward", "gvd_raster_backward", "gvd_raster_mark_visible",
     "gvd_exchange_alloc", "gvd_exchange_free", "gvd_exchange_open", "gvd_exchange_close", "gvd_exchange_allreduce_sum", "gvd_exchange_status",
 )
@@ -84,7 +87,7 @@ class ExchangeArgs(C.Structure):
                 ("payload_bytes", C.c_size_t), ("n_floats", C.c_size_t), ("epoch", C.c_uint32)]
 
 _raster = None
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 def lib_path(name="libgvd_raster.so"):
@@ -112,6 +115,10 @@ def raster():
     lib.gvd_raster_backward_scratch_bytes.argtypes = [C.c_int]
     lib.gvd_raster_img_bytes.restype = C.c_size_t
     lib.gvd_raster_img_bytes.argtypes = [C.c_int, C.c_int]
+    lib.gvd_raster_sort_bytes.restype = C.c_size_t
+    lib.gvd_raster_sort_bytes.argtypes = [C.c_int]
+    lib.gvd_raster_hist_bytes.restype = C.c_size_t
+    lib.gvd_raster_hist_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.gvd_raster_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RasterLayout)]
     lib.gvd_raster_forward.argtypes = [C.POINTER(RasterForwardArgs), C.c_void_p]
     lib.gvd_raster_backward.argtypes = [C.POINTER(RasterBackwardArgs), C.c_void_p]

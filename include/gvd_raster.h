@@ -40,7 +40,7 @@ typedef struct CUstream_st* gvd_stream_t; /* == cudaStream_t */
 typedef void* (*gvd_alloc_fn)(void* user, size_t bytes);
 
 /* Layout/version of the scratch buffers (bumped when the packed layouts change). */
-#define GVD_RASTER_ABI_VERSION 7
+#define GVD_RASTER_ABI_VERSION 8
 
 typedef struct GvdRasterForwardArgs {
     /* sizes -- DGR/cuda_rasterizer/rasterizer_impl.cu:197-224 */
@@ -74,6 +74,9 @@ typedef struct GvdRasterForwardArgs {
     gvd_alloc_fn geom_alloc;     /* called once with gvd_raster_geom_bytes(P,W,H)    */
     gvd_alloc_fn binning_alloc;  /* called once with gvd_raster_binning_bytes(R,export_keys) */
     gvd_alloc_fn img_alloc;      /* called once with gvd_raster_img_bytes(W,H)       */
+    gvd_alloc_fn temp_alloc;     /* forward-only scratch: called with gvd_raster_sort_bytes(P) at the start (unless
+                                  * sort_buffer is given) and with gvd_raster_hist_bytes(V,W,H) once V is known; both
+                                  * buffers may be released (stream-ordered) as soon as the call returns            */
     void* alloc_user;
     /* Optional pre-sized scratch: both sizes are pure functions of (P, W, H), so a caller that knows them can hand the
      * buffers over directly and save the two callbacks.  Used when non-NULL (must hold gvd_raster_geom_bytes(P,W,H) /
@@ -82,24 +85,35 @@ typedef struct GvdRasterForwardArgs {
     size_t geom_bytes;
     void* img_buffer;
     size_t img_bytes;
-    /* Optional speculative instance buffer (no host round trip).  When spec_binning_buffer != NULL the library does NOT
-     * synchronise to learn R: the binning kernel stores R directly into *num_rendered_pinned (pinned host memory that is
-     * mapped into the device address space, as cudaHostAlloc memory is under unified addressing), the library records
-     * r_ready_event (a cudaEvent_t) right behind that kernel, and queues the remaining stages against the caller's buffer
-     * of spec_binning_bytes bytes (writes and reads are clamped to it).  The caller waits on the event, reads R, and if
-     * gvd_raster_binning_bytes(R, export_keys) > spec_binning_bytes the outputs are invalid and the call must be
-     * repeated with a larger buffer (or with spec_binning_buffer = NULL, the synchronous path of the reference,
-     * rasterizer_impl.cu:281-286).  num_rendered is set to -1 on this path. */
+    void* sort_buffer;           /* gvd_raster_sort_bytes(P), forward-only */
+    size_t sort_bytes;
+    /* R (instances) and V (visible Gaussians) are produced by the second kernel of the forward, ~40 us into the frame.
+     * num_rendered_pinned: optional int[2] in pinned host memory that is mapped into the device address space (as
+     * cudaHostAlloc memory is under unified addressing); the kernel stores {R, V} there directly.
+     *   EXACT path (default, spec_binning_buffer == NULL): the library queues the depth sort behind that kernel, waits
+     *   on the host for R and V only (event r_ready_event if given, else an internal one; without num_rendered_pinned
+     *   it falls back to cudaMemcpyAsync + stream synchronisation like the reference, rasterizer_impl.cu:281-282),
+     *   calls binning_alloc / temp_alloc with the exact sizes and queues the rest.  The GPU never idles for the round
+     *   trip and the outputs are always valid.
+     *   SPECULATIVE path (spec_binning_buffer != NULL; needs spec_hist_buffer and num_rendered_pinned): no host wait at
+     *   all.  The remaining stages are queued against the caller's buffers (writes and reads are clamped to them), the
+     *   library records r_ready_event behind the kernel that stores {R, V}; the caller waits on it later and, if
+     *   gvd_raster_binning_bytes(R, export_keys) > spec_binning_bytes or gvd_raster_hist_bytes(V,W,H) > spec_hist_bytes,
+     *   the outputs are invalid and the call must be repeated.  num_rendered / num_visible are -1 on this path. */
     void* spec_binning_buffer;
     size_t spec_binning_bytes;
+    void* spec_hist_buffer;
+    size_t spec_hist_bytes;
     int* num_rendered_pinned;
     void* r_ready_event;
     /* result */
     int num_rendered;            /* out: R = number of (Gaussian,tile) instances     */
+    int num_visible;             /* out: V = number of Gaussians with radii > 0      */
 } GvdRasterForwardArgs;
 
 typedef struct GvdRasterBackwardArgs {
     int P, D, M, R;
+    int num_visible;             /* V from the forward, or -1 when the host does not know it (costs idle CTAs) */
     int width, height;
     /* forward inputs again (dev) -- DGR/rasterize_points.cu:121-146 */
     const float* background;
@@ -129,6 +143,11 @@ typedef struct GvdRasterBackwardArgs {
     const float* confidence;     /* [P] or NULL */
     /* scratch: zero-filled by this call; gvd_raster_backward_scratch_bytes(P) bytes */
     void* scratch;
+    /* Optional: one region that contains ALL the gradient outputs below (e.g. a flat allocation the eight tensors are
+     * views of).  The outputs are zero except on the V visible Gaussians; given the region, its zero-fill is folded
+     * into the (issue-bound) render kernel instead of costing one streaming launch per output. */
+    void* zero_region;
+    size_t zero_region_bytes;
     /* outputs (dev); all fully written by this call (no pre-zeroing needed).      */
     float* dL_dmeans2D;          /* [P,3]  (z = 0), NOT confidence-scaled          */
     float* dL_dmeans3D;          /* [P,3]                                          */
@@ -147,6 +166,8 @@ typedef struct GvdRasterBackwardArgs {
 GVD_API size_t gvd_raster_geom_bytes(int P, int width, int height);
 GVD_API size_t gvd_raster_binning_bytes(int R, int export_keys);
 GVD_API size_t gvd_raster_img_bytes(int width, int height);
+GVD_API size_t gvd_raster_sort_bytes(int P);                                  /* forward-only scratch, stage 1 */
+GVD_API size_t gvd_raster_hist_bytes(int num_visible, int width, int height);  /* forward-only scratch, stage 2 */
 GVD_API size_t gvd_raster_backward_scratch_bytes(int P);
 
 /* Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer_impl.cu:197-339)
@@ -170,7 +191,8 @@ typedef struct GvdRasterLayout {
     size_t geom_splat;          /* float4[4P]: {x,y,conA,conB},{conC,opac,r,g},{b,depth,hx,hy},{rect_lo,rect_hi,0,0} */
     size_t geom_clamped;        /* uint8[P]: bit c set = channel c was clamped at 0                          */
     size_t geom_tiles_touched;  /* uint32[P]                                                                 */
-    size_t geom_order;          /* uint32[P] Gaussian ids sorted by (depth bits, id); culled ones last       */
+    size_t geom_visible_ids;    /* uint32[P] ids of the V visible Gaussians, ascending (V entries valid)       */
+    size_t geom_counts;         /* uint32[8] {V, R, ...}                                                     */
     size_t bin_point_list;      /* uint32[R] sorted Gaussian ids (tile-major, depth order inside a tile)     */
     size_t bin_point_list_keys; /* uint64[R] sorted keys (tile<<32 | depth bits); only with export_keys      */
     size_t img_ranges;          /* uint2[T]                                                                  */
@@ -182,7 +204,7 @@ GVD_API int gvd_raster_layout(int P, int R, int width, int height, GvdRasterLayo
  * Off by default; used by bench.py for the live roofline numbers. Not thread-safe; single stream. */
 enum {
     GVD_STAGE_PREPROCESS = 0, GVD_STAGE_SCAN /* bin count+prefix+ranges */, GVD_STAGE_EMIT /* bin fill */,
-    GVD_STAGE_SORT /* depth sort */, GVD_STAGE_PACK /* export_keys (tests only) */,
+    GVD_STAGE_SORT /* compaction + depth sort */, GVD_STAGE_PACK /* export_keys (tests only) */,
     GVD_STAGE_RENDER_FWD, GVD_STAGE_RENDER_BWD, GVD_STAGE_GAUSSIAN_BWD, GVD_STAGE_COUNT
 };
 typedef struct GvdRasterStageTimes {

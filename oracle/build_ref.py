@@ -19,7 +19,13 @@ The python front-end file of the rasterizer package (the autograd.Function) is
 can be driven through its own public API on the GPU box, where /root/reference
 does not exist.
 
-Usage:  python oracle/build_ref.py [dgr] [knn]
+  oracle/_ref/ViewCrafter/...                     <- pure-python denoiser / sampler / VAE modules (build_vc)
+  oracle/_ref/gs/...                              <- the reference's own Python ABOVE the rasterizer boundary
+        (gaussian_renderer/__init__.py::render, utils/easy_renderer.py::EasyRenderer, scene/gaussian_model.py,
+        scene/cameras.py, arguments/, utils/{sh,graphics,general,system,loss}_utils.py), installed unmodified so the
+        GPU tests can drive `render()` over the drop-in packages exactly as train_*.py does (tests/gs_refload.py)
+
+Usage:  python oracle/build_ref.py [dgr] [knn] [vc] [gs]
 """
 import os
 import shutil
@@ -120,8 +126,27 @@ def build_vc():
     return True
 
 
+def build_gs():
+    """Install (copy, unmodified) the reference's Python above the rasterizer boundary; see the module docstring."""
+    if not os.path.isdir(os.path.join(REF, "gaussian_renderer")):
+        print("reference not present, skip gs")
+        return False
+    dst = os.path.join(OUT, "gs")
+    for rel in ("gaussian_renderer/__init__.py", "utils/easy_renderer.py", "utils/sh_utils.py", "utils/graphics_utils.py",
+                "utils/general_utils.py", "utils/system_utils.py", "utils/loss_utils.py", "scene/gaussian_model.py",
+                "scene/cameras.py", "arguments/__init__.py"):
+        d = os.path.join(dst, rel)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        if os.path.exists(d):
+            os.chmod(d, 0o644)
+        shutil.copyfile(os.path.join(REF, rel), d)
+        os.chmod(d, 0o644)
+    print("installed", dst)
+    return True
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dgr", "knn", "vc"]
+    which = sys.argv[1:] or ["dgr", "knn", "vc", "gs"]
     if len(which) > 1:
         # one process per extension: torch's JIT loader renames a second "_C" built in the
         # same process to "_C_v1", which the packages' `from . import _C` would not find.
@@ -135,3 +160,5 @@ if __name__ == "__main__":
         build_knn()
     elif which[0] == "vc":
         build_vc()
+    elif which[0] == "gs":
+        build_gs()

@@ -58,13 +58,16 @@ def run(pkg, sc, cam, cot, bg, sh_degree, use_conf=True, precomp=False, debug=Fa
     saved = getattr(fn, "saved_tensors", None)
     if saved is not None:
         out["geom"], out["binning"], out["img"] = saved[7], saved[8], saved[9]
-    nr = getattr(fn, "num_rendered", None)
-    out["num_rendered"] = None if nr is None else int(nr)  # ours: may be a deferred R (validated on conversion)
     if backward:
         loss = (color * cot["color"]).sum() + (depth * cot["depth"]).sum() + (alpha * cot["alpha"]).sum()
         loss.backward()
         out["grads"] = {k: (v.grad.detach() if v.grad is not None else None) for k, v in leaf.items()}
         out["grads"]["means2D"] = means2D.grad.detach() if means2D.grad is not None else None
+    nr = getattr(fn, "num_rendered", None)
+    if backward or not (hasattr(nr, "resolve") and type(nr).__name__ == "PendingR"):
+        out["num_rendered"] = None if nr is None else int(nr)  # ours under GVD_SPECULATE=defer: resolved by the backward
+    else:
+        out["num_rendered"] = None  # a deferred frame without a backward: left for the shim to settle
     return out
 
 

@@ -24,8 +24,11 @@ def lib():
 
         L = C.CDLL(build_emu.build("raster", build_emu.RASTER_SOURCES))
         L.gvd_last_error.restype = C.c_char_p
-        for name in ("gvd_raster_geom_bytes", "gvd_raster_binning_bytes", "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes"):
+        for name in ("gvd_raster_geom_bytes", "gvd_raster_binning_bytes", "gvd_raster_img_bytes", "gvd_raster_backward_scratch_bytes",
+                     "gvd_raster_sort_bytes", "gvd_raster_hist_bytes"):
             getattr(L, name).restype = C.c_size_t
+        L.gvd_raster_sort_bytes.argtypes = [C.c_int]
+        L.gvd_raster_hist_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.gvd_raster_geom_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.gvd_raster_binning_bytes.argtypes = [C.c_int, C.c_int]
         L.gvd_raster_img_bytes.argtypes = [C.c_int, C.c_int]
@@ -47,8 +50,13 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
-def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=None):
-    """spec_capacity: run the SPECULATIVE forward (no host round trip for R) with an instance buffer of that many entries."""
+def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=None, spec_visible=None, pinned=False, flat_grads=False,
+        know_visible=True):
+    """spec_capacity: run the SPECULATIVE forward (no host round trip for R) with an instance buffer of that many entries
+    (spec_visible: and a chunk-histogram buffer for that many visible Gaussians, default P).
+    pinned: hand the exact path a host word pair for {R, V} (its event-wait route instead of the memcpy fallback).
+    flat_grads: the gradient outputs are views of one allocation and the backward is told so (zero_region).
+    know_visible=False: the backward is not told V (num_visible = -1)."""
     import gvd_native as n
 
     L = lib()
@@ -75,6 +83,13 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
         return n.ALLOC_FN(fn)
 
     cbs = [make_alloc(t) for t in ("geom", "binning", "img")]
+    temps = []
+
+    def temp_fn(user, nbytes):
+        raw, ptr = _aligned(int(nbytes))
+        temps.append(raw)
+        return ptr
+    temp_cb = n.ALLOC_FN(temp_fn)
     a = n.RasterForwardArgs()
     a.P, a.D, a.M, a.width, a.height = P, D, M, W, H
     a.background, a.means3D, a.shs, a.colors_precomp = _p(bgf), _p(means3D), _p(shs), _p(colors_pre)
@@ -84,22 +99,31 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
     a.prefiltered, a.debug, a.export_keys = 0, 0, 1
     a.out_color, a.out_depth, a.out_alpha, a.radii = _p(color), _p(depth), _p(alpha), _p(radii)
     a.geom_alloc, a.binning_alloc, a.img_alloc = cbs
-    r_word = np.zeros(1, np.int32)
+    a.temp_alloc = temp_cb
+    r_word = np.full(2, -7, np.int32)
+    if pinned:
+        a.num_rendered_pinned = r_word.ctypes.data
     if spec_capacity is not None:
         nb = int(L.gvd_raster_binning_bytes(int(spec_capacity), 1)) + 512
         raw, ptr = _aligned(nb)
         keep["binning"] = (raw, ptr, nb)
         a.spec_binning_buffer, a.spec_binning_bytes = ptr, nb
+        hb = int(L.gvd_raster_hist_bytes(int(P if spec_visible is None else spec_visible), W, H)) + 512
+        hraw, hptr = _aligned(hb)
+        keep["hist"] = (hraw, hptr, hb)
+        a.spec_hist_buffer, a.spec_hist_bytes = hptr, hb
         a.num_rendered_pinned = r_word.ctypes.data
     rc = L.gvd_raster_forward(C.byref(a), None)
     if rc != 0:
         raise RuntimeError("gvd_raster_forward (host build): " + (L.gvd_last_error() or b"").decode())
-    R = int(a.num_rendered)
+    R, V = int(a.num_rendered), int(a.num_visible)
+    if pinned:
+        assert (R, V) == (int(r_word[0]), int(r_word[1]))
     if spec_capacity is not None:
-        assert R == -1                    # the library did not learn R on this path; it arrives through the pinned word
-        R = int(r_word[0])
-        if R > spec_capacity:             # the caller's validation: outputs of this frame are invalid
-            return dict(num_rendered=R, overflow=True, color=color, radii=radii)
+        assert R == -1 and V == -1        # the library did not learn R on this path; it arrives through the pinned words
+        R, V = int(r_word[0]), int(r_word[1])
+        if R > spec_capacity or (spec_visible is not None and V > spec_visible):  # the caller's validation: this frame is invalid
+            return dict(num_rendered=R, num_visible=V, overflow=True, color=color, radii=radii)
     lay = n.RasterLayout()
     L.gvd_raster_layout(P, R, W, H, C.byref(lay))
     T = ((W + 15) // 16) * ((H + 15) // 16)
@@ -109,7 +133,9 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
         start = ptr - raw.ctypes.data + off
         return raw[start:start + count * np.dtype(dtype).itemsize].view(dtype).copy()
 
-    out = dict(color=color, depth=depth, alpha=alpha, radii=radii, num_rendered=R,
+    out = dict(color=color, depth=depth, alpha=alpha, radii=radii, num_rendered=R, num_visible=V,
+               visible_ids=view_of("geom", lay.geom_visible_ids, np.uint32, P)[:V],
+               counts=view_of("geom", lay.geom_counts, np.uint32, 2),
                tiles_touched=view_of("geom", lay.geom_tiles_touched, np.uint32, P),
                ranges=view_of("img", lay.img_ranges, np.uint32, 2 * T).reshape(T, 2),
                n_contrib=view_of("img", lay.img_n_contrib, np.uint32, H * W).reshape(H, W))
@@ -120,12 +146,26 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
     out["g_xy"], out["g_depth"] = splat[:, 0:2], splat[:, 9]
     if cot is None:
         return out
-    g = {k: np.zeros(s, np.float32) for k, s in dict(means2D=(P, 3), means3D=(P, 3), opacities=(P,), colors_precomp=(P, 3),
-                                                      cov3D_precomp=(P, 6), shs=(P, M, 3), scales=(P, 3), rotations=(P, 4)).items()}
+    shapes = dict(means2D=(P, 3), means3D=(P, 3), opacities=(P,), colors_precomp=(P, 3), cov3D_precomp=(P, 6), shs=(P, M, 3),
+                  scales=(P, 3), rotations=(P, 4))
+    # every output starts as garbage: the backward has to produce the zeros of the invisible Gaussians itself
+    if flat_grads:
+        sizes = {k: (int(np.prod(s)) + 3) // 4 * 4 for k, s in shapes.items()}
+        flat_raw = np.full(sum(sizes.values()) + 8, 7.5, np.float32)
+        flat_off = (-flat_raw.ctypes.data // 4) % 4  # 16-byte aligned start
+        g, pos = {}, flat_off
+        for k, s_ in shapes.items():
+            g[k] = flat_raw[pos:pos + int(np.prod(s_))].reshape(s_)
+            pos += sizes[k]
+    else:
+        g = {k: np.full(s_, 7.5, np.float32) for k, s_ in shapes.items()}
     conf = f32(sc["confidence"]).reshape(-1) if use_conf else None
     sraw, sptr = _aligned(int(L.gvd_raster_backward_scratch_bytes(P)))
     b = n.RasterBackwardArgs()
     b.P, b.D, b.M, b.R, b.width, b.height = P, D, M, R, W, H
+    b.num_visible = V if know_visible else -1
+    if flat_grads:
+        b.zero_region, b.zero_region_bytes = flat_raw.ctypes.data + 4 * flat_off, 4 * sum(sizes.values())
     b.background, b.means3D, b.shs, b.colors_precomp = _p(bgf), _p(means3D), _p(shs), _p(colors_pre)
     b.scales, b.rotations, b.cov3D_precomp = _p(scales), _p(rots), _p(cov_pre)
     b.viewmatrix, b.projmatrix, b.campos = _p(view), _p(proj), _p(campos)

@@ -1,12 +1,14 @@
 """The rasterizer's CUDA sources executed on the HOST (tests/cuda_emu: raster_api.cu, raster_forward.cu,
 raster_backward.cu compiled as they are; CUDA threads are OS threads, warp collectives / barriers / atomics keep their
 meaning, the TMA bulk copy + mbarrier pair and the programmatic-dependent-launch intrinsics are replaced by host
-equivalents under GVD_HOST_EMU in raster_common.cuh, CUB's radix sort by a stable sort) through the C ABI, against the
-golden vectors of the compiled REFERENCE (tests/golden/raster_*.npz, produced on a B200 by tests/make_golden.py).
+equivalents under GVD_HOST_EMU in raster_common.cuh) through the C ABI, against the golden vectors of the compiled
+REFERENCE (tests/golden/raster_*.npz, produced on a B200 by tests/make_golden.py).
 
-What this pins without a GPU: the whole kernel chain's logic -- preprocess, depth sort, the rect-aware counting sort
-(bin_count / bin_prefix / bin_ranges / bin_fill), both render kernels with their sub-tile culling and batched id
-staging, the transposing-butterfly reduction of the backward, the fused per-Gaussian backward.  Integer buffers are
+What this pins without a GPU: the whole kernel chain's logic -- preprocess with its per-CTA counts, the compaction of
+the visible Gaussians (V, R), the hand-written 4-pass radix depth sort, the rect-aware counting sort (bin_count /
+bin_prefix / bin_ranges / the mask-ranked bin_fill), both render kernels with their sub-tile culling and batched id
+staging, the transposing-butterfly reduction of the backward with its fused zero fill, the per-visible-Gaussian
+backward.  Integer buffers are
 compared exactly; floats with the bounds of tests/test_oracle_cpu.py (x86 expf / no FMA contraction differ from the
 GPU's in the last ulp and flip isolated alpha < 1/255 decisions on a 2 000-Gaussian scene)."""
 import os
@@ -30,8 +32,14 @@ def test_kernel_chain_matches_reference_golden(path):
     g = np.load(path)
     _, sc, cam, cot, bg, D, precomp = toc._inputs(g)
     backward = "d0" not in os.path.basename(path)      # two of the three fixtures run the backward as well (time)
-    o = raster_emu.run(sc, cam, bg, D, cot=cot if backward else None, use_conf=bool(g["use_conf"]), precomp=precomp)
+    flat = "precomp" in os.path.basename(path)          # one fixture hands the backward one flat gradient region
+    o = raster_emu.run(sc, cam, bg, D, cot=cot if backward else None, use_conf=bool(g["use_conf"]), precomp=precomp,
+                       pinned="d3" in os.path.basename(path), flat_grads=flat, know_visible=not flat)
     P = int(g["P"])
+    # the compacted id list is exactly the Gaussians with a radius, ascending; V and R are the device counts
+    assert np.array_equal(o["visible_ids"], np.nonzero(o["radii"] > 0)[0].astype(np.uint32))
+    assert o["num_visible"] == int((o["radii"] > 0).sum()) == int(o["counts"][0]) and int(o["counts"][1]) == o["num_rendered"]
+    assert o["num_rendered"] == int(o["tiles_touched"].astype(np.int64).sum())
     assert (o["radii"] != g["radii"]).sum() <= max(1, P // 2000)
     assert (o["tiles_touched"].astype(np.int64) != g["tiles_touched"].astype(np.int64)).sum() <= max(1, P // 2000)
     assert abs(o["num_rendered"] - int(g["num_rendered"])) <= 64
@@ -54,7 +62,7 @@ def test_kernel_chain_matches_reference_golden(path):
             gr = g["grad_" + k].astype(np.float64).reshape(go.shape)
             rel = np.sqrt(((go - gr) ** 2).sum()) / max(np.sqrt((gr ** 2).sum()), 1e-30)
             assert rel < 5e-3, (k, rel)
-        # untouched Gaussians get exact zeros (the kernel writes them; there is no zero-fill pass)
+        # untouched Gaussians get exact zeros (the outputs start as garbage: the backward's own zero fill produced them)
         inv = g["radii"] == 0
         assert all(not np.any(v[inv]) for v in o["grads"].values())
 
@@ -103,3 +111,31 @@ def test_speculative_forward_equals_exact_and_survives_overflow():
         assert np.array_equal(spec[k], exact[k]), k
     small = raster_emu.run(sc, cam, bg, D, use_conf=bool(g["use_conf"]), precomp=precomp, spec_capacity=R // 3)
     assert small.get("overflow") and small["num_rendered"] == R and np.array_equal(small["radii"], exact["radii"])
+    # the chunk-histogram buffer can be the one that is too small (V outgrew the guess): clamped as well, reported through V
+    V = exact["num_visible"]
+    few = raster_emu.run(sc, cam, bg, D, use_conf=bool(g["use_conf"]), precomp=precomp, spec_capacity=2 * R + 1000, spec_visible=V // 3)
+    assert few.get("overflow") and few["num_visible"] == V and few["num_rendered"] == R
+    fit = raster_emu.run(sc, cam, bg, D, use_conf=bool(g["use_conf"]), precomp=precomp, spec_capacity=R, spec_visible=V)
+    for k in ("radii", "point_list", "ranges", "n_contrib", "color", "depth", "alpha"):
+        assert np.array_equal(fit[k], exact[k]), k
+
+
+def test_depth_sort_and_fill_at_sizes_that_cross_tile_boundaries():
+    """More visible Gaussians than one sort tile (1024) and one super-tile of the offset lookup would need 32 768, which
+    the host emulation cannot afford; 5 000 visible ones cross four sort tiles and exercise the per-tile histograms the
+    passes hand to each other.  Big rects (scale x 6) push chunks over the row-walk threshold of bin_fill.  Checked
+    against the C oracle (oracle/raster_oracle.c), integer buffers exactly."""
+    import raster_emu
+    import raster_oracle as ro
+    import synth
+
+    sc = ro.to_numpy_scene(synth.synth_scene(9000, 11))
+    sc["scales"] = (sc["scales"] * 6.0).astype(np.float32)
+    cam = ro.to_numpy_scene(synth.synth_camera(12, 208, 160))
+    bg = np.zeros(3, np.float32)
+    o = raster_emu.run(sc, cam, bg, 1)
+    r = ro.run(sc, cam, bg, 1)
+    assert o["num_visible"] > 4 * 1024 and o["num_rendered"] > 64 * 4096 // 8
+    assert o["num_rendered"] == r["num_rendered"] and np.array_equal(o["radii"], r["radii"])
+    assert np.array_equal(o["ranges"], r["ranges"])
+    assert np.array_equal(o["point_list"], r["point_list"])

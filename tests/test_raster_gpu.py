@@ -199,22 +199,23 @@ def test_properties_at_full_size(cfg):
         assert _grad_err(c["grads"][k], 2 * a["grads"][k])[1] < 1e-5, k
 
 
-def test_speculative_instance_buffer_matches_exact_path():
-    """The production path (no key export): from the second frame on the instance buffer is sized from history, the
-    forward makes no host round trip and R is validated in the backward.  Results must equal the exact path's."""
+def test_default_path_is_exact_and_learns_counts_early():
+    """The production path (no key export): every buffer is sized exactly inside the forward from the {R, V} the second
+    kernel stored in pinned memory; nothing is deferred.  Results must equal the parity (synchronous) path's."""
     import parity_raster as pr
     import synth
 
     ours, _ = _pkgs()
+    assert not ours._C.DEFER
     P, W, H, seed = synth.CONFIGS["small"]
     sc, cam, cot, bg, D = pr.make_inputs(P, W, H, seed, 3)
     exact = pr.run(ours, sc, cam, cot, bg, D)
     ours._C._spec_state.clear()
-    runs = [pr.run(ours, sc, cam, cot, bg, D, export_keys=False) for _ in range(3)]  # 1st: no history -> exact path
+    runs = [pr.run(ours, sc, cam, cot, bg, D, export_keys=False) for _ in range(3)]
     st = ours._C._spec_state[sc["means3D"].device]
-    assert st["max_R"] == exact["num_rendered"] and len(st["free"]) >= 1
+    assert st["max_R"] == exact["num_rendered"] and st["max_V"] == int((exact["radii"] > 0).sum()) and len(st["free"]) >= 1
     for r in runs:
-        assert r["num_rendered"] == exact["num_rendered"]
+        assert r["num_rendered"] == exact["num_rendered"] and isinstance(r["num_rendered"], int)
         for k in ("color", "depth", "alpha", "radii"):
             assert torch.equal(r[k], exact[k]), k
         for k in exact["grads"]:
@@ -224,9 +225,10 @@ def test_speculative_instance_buffer_matches_exact_path():
     assert torch.equal(nograd["color"], exact["color"])
 
 
-def test_speculative_instance_buffer_overflow(monkeypatch):
-    """A frame that outgrows the speculative buffer: without autograd the shim silently redoes it on the exact path;
-    with a deferred validation the backward raises (the image was already consumed) and the history grows."""
+def test_deferred_mode_matches_exact_and_repairs_an_overflow(monkeypatch):
+    """GVD_SPECULATE=defer (opt-in): no host wait between forward and backward.  Same results as the exact path while the
+    guesses fit; a frame that outgrows them is re-rendered exactly by its backward, with a warning -- never an
+    exception inside an unmodified trainer -- and the grown history makes the next frame fit."""
     import parity_raster as pr
     import synth
 
@@ -235,16 +237,34 @@ def test_speculative_instance_buffer_overflow(monkeypatch):
     sc, cam, cot, bg, D = pr.make_inputs(P, W, H, seed, 3)
     exact = pr.run(ours, sc, cam, cot, bg, D)
     dev = sc["means3D"].device
+    monkeypatch.setattr(ours._C, "DEFER", True)
     ours._C._spec_state.clear()
-    pr.run(ours, sc, cam, cot, bg, D, export_keys=False)          # builds the history
-    monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)  # every later guess is far too small
-    with torch.no_grad():  # no backward to come: the shim validates before returning and redoes the frame exactly
+    runs = [pr.run(ours, sc, cam, cot, bg, D, export_keys=False) for _ in range(3)]  # 1st: no history -> exact path
+    for r in runs:
+        assert r["num_rendered"] == exact["num_rendered"]
+        for k in ("color", "depth", "alpha", "radii"):
+            assert torch.equal(r[k], exact[k]), k
+        for k in exact["grads"]:
+            assert _grad_err(r["grads"][k], exact["grads"][k])[1] < 1e-5, k
+    with torch.no_grad():  # no backward to come: never deferred
         nograd = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
-    for k in ("color", "depth", "alpha", "radii"):
-        assert torch.equal(nograd[k], exact[k]), k
-    with pytest.raises(RuntimeError, match="speculative instance buffer"):
-        pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
+    assert torch.equal(nograd["color"], exact["color"])
+    real_capacity = ours._C._capacity
+    monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)  # every later guess is far too small
+    with pytest.warns(UserWarning, match="Re-rendered exactly"):
+        broken = pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
     torch.cuda.synchronize()
-    monkeypatch.undo()
+    assert torch.equal(broken["radii"], exact["radii"])
+    for k in exact["grads"]:  # gradients of the frame as it should have been
+        assert _grad_err(broken["grads"][k], exact["grads"][k])[1] < 1e-5, k
+    monkeypatch.setattr(ours._C, "_capacity", real_capacity)
     again = pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
     assert torch.equal(again["color"], exact["color"]) and ours._C._spec_state[dev]["max_R"] == exact["num_rendered"]
+    # a deferred frame that never gets a backward is validated at the next render on that device, not at GC
+    monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)
+    lost = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
+    torch.cuda.synchronize()
+    monkeypatch.setattr(ours._C, "_capacity", real_capacity)
+    with pytest.warns(UserWarning, match="speculative buffers"):
+        pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
+    del lost

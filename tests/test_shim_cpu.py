@@ -50,19 +50,24 @@ class _FakeEvent:
 
 
 def test_pending_r_validation_and_bookkeeping():
-    """PendingR: resolves once, returns its slot, grows the history, raises (every time) when the frame outgrew the buffer."""
+    """PendingR (GVD_SPECULATE=defer): resolves once to a Counts (R with V attached), returns its slot, grows the history,
+    raises SpeculationOverflow (every time) when the frame outgrew the instance buffer OR the chunk histogram."""
     c = _C()
-    st = {"max_R": 100, "free": []}
-    slot = {"event": _FakeEvent(), "host": [1234]}
-    p = c.PendingR(slot, c._capacity(100), st)
-    assert int(p) == 1234 and int(p) == 1234 and slot["event"].syncs == 1
-    assert st["free"] == [slot] and st["max_R"] == 1234
+    st = {"max_R": 100, "max_V": 10, "free": [], "open": []}
+    slot = {"event": _FakeEvent(), "host": [1234, 77]}
+    p = c.PendingR(slot, c._capacity(100), 500, st)
+    r = p.resolve()
+    assert int(p) == 1234 and r == 1234 and r.visible == 77 and slot["event"].syncs == 1
+    assert st["free"] == [slot] and st["max_R"] == 1234 and st["max_V"] == 77
 
-    st = {"max_R": 10, "free": []}
-    slot = {"event": _FakeEvent(), "host": [5000]}
-    p = c.PendingR(slot, 4096, st)
-    for _ in range(2):
-        with pytest.raises(RuntimeError, match="speculative instance buffer"):
-            p.resolve()
-    assert st["max_R"] == 5000 and st["free"] == [slot]  # the history grew: the retry will fit
-    assert c._capacity(5000) >= 2 * 5000
+    for host, cap, vcap in (([5000, 50], 4096, 500), ([100, 900], 4096, 500)):
+        st = {"max_R": 10, "max_V": 10, "free": [], "open": []}
+        slot = {"event": _FakeEvent(), "host": host}
+        p = c.PendingR(slot, cap, vcap, st)
+        for _ in range(2):
+            with pytest.raises(c.SpeculationOverflow, match="speculative buffers"):
+                p.resolve()
+        assert st["max_R"] == max(10, host[0]) and st["max_V"] == max(10, host[1]) and st["free"] == [slot]  # the retry will fit
+    assert c._capacity(5000) >= 2 * 5000 and c._visible_capacity(100, 150) == 150
+    assert issubclass(c.SpeculationOverflow, RuntimeError)
+    assert not c.DEFER, "exact sizing is the default; GVD_SPECULATE=defer is the opt-in"
