@@ -22,6 +22,7 @@ constexpr unsigned long long kWaitLimitNs = 20ull * 1000 * 1000 * 1000;
 struct Params {
     float4* buf[GVD_EXCHANGE_MAX_RANKS];
     uint32_t* flag[GVD_EXCHANGE_MAX_RANKS];
+    float4* mc;  // multicast (NVLS) mapping of the same buffer on all ranks, or null
     int world, rank;
     unsigned long long n_vec;  // float4 elements to reduce
     uint32_t epoch;
@@ -50,6 +51,18 @@ __device__ __forceinline__ void st_peer(float4* p, float4 v) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// NVLS: one load returns the SUM of the addressed 16 bytes over every GPU bound to the multicast object (the NVSwitch
+// fetches and adds the replicas), one store writes all replicas.  SASS: LDGMC.ADD / STG via the multicast address.
+__device__ __forceinline__ float4 mc_ld_reduce(const float4* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float4* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -60,6 +73,8 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { __atom
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ float4 ld_peer(const float4* p) { return *p; }
 __device__ __forceinline__ void st_peer(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ float4 mc_ld_reduce(const float4* p) { return *p; }  // no multicast objects on the host build
+__device__ __forceinline__ void mc_st(float4*, float4) {}
 __device__ __forceinline__ unsigned long long global_ns() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -115,6 +130,24 @@ __device__ __forceinline__ void reduce_slice(const Params& p, unsigned long long
     }
 }
 
+// Slice r of the buffer, summed inside the NVSwitch and written back to every replica through the multicast mapping:
+// per element ONE 16-byte request leaves this GPU in each direction, instead of WORLD-1 peer loads and WORLD-1 peer
+// stores.  Link traffic per GPU: (WORLD-1)/WORLD of the buffer out (its replicas of the other ranks' slices, pulled by
+// the switch) and the same amount in (the other ranks' sums, multicast by the switch) -- the two directions overlap.
+__device__ __forceinline__ void reduce_slice_nvls(const Params& p, unsigned long long begin, unsigned long long end) {
+    constexpr int U = 4;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < end; i += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = mc_ld_reduce(p.mc + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) mc_st(p.mc + i + u * stride, v[u]);
+    }
+    for (; i < end; i += stride) mc_st(p.mc + i, mc_ld_reduce(p.mc + i));
+}
+
 template <int WORLD>
 __global__ void __launch_bounds__(512) grad_allreduce_kernel(const Params p) {
     uint32_t* mine = p.flag[p.rank];
@@ -127,7 +160,10 @@ __global__ void __launch_bounds__(512) grad_allreduce_kernel(const Params p) {
     const unsigned long long begin = per * p.rank;
     unsigned long long end = begin + per;
     if (end > p.n_vec) end = p.n_vec;
-    if (begin < end) reduce_slice<WORLD>(p, begin, end);
+    if (begin < end) {
+        if (p.mc != nullptr) reduce_slice_nvls(p, begin, end);
+        else reduce_slice<WORLD>(p, begin, end);
+    }
     // ---- exit: my stores have landed everywhere, and every peer's stores have landed here ----
     __threadfence_system();
     __syncthreads();
@@ -217,6 +253,7 @@ int gvd_exchange_allreduce_sum(const GvdExchangeArgs* a, void* stream_) {
         p.buf[q] = reinterpret_cast<float4*>(a->bufs[q]);
         p.flag[q] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(a->bufs[q]) + padded(a->payload_bytes));
     }
+    p.mc = reinterpret_cast<float4*>(a->multicast);
     p.world = a->world;
     p.rank = a->rank;
     p.n_vec = a->n_floats / 4;

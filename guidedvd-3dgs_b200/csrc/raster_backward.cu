@@ -80,7 +80,7 @@ __device__ __forceinline__ int warp_reduce10(float (&v)[10], uint32_t lane, floa
     return local + (b4 ? 5 : 0);
 }
 
-template <int SPLIT>
+template <int SPLIT, bool EXACT_DIV>
 __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, const float* __restrict__ alphas,
@@ -221,8 +221,12 @@ __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel
 #pragma unroll
                     for (int k = 0; k < 10; ++k) g[k] = 0.0f;
                     if (contrib) {
-                        const float rcp_1ma = 1.0f / (1.f - alpha);  // one IEEE reciprocal feeds both quotients below
-                        T = T * rcp_1ma;
+                        // backward.cu:530,576 divide twice by (1 - alpha). EXACT_DIV keeps the two IEEE divisions, so the
+                        // transmittance chain is bit-identical to the reference's; otherwise one IEEE reciprocal feeds
+                        // both quotients (each within 1 ulp of the division, ~10 instructions fewer per contribution)
+                        const float one_m_alpha = 1.f - alpha;
+                        const float rcp_1ma = 1.0f / one_m_alpha;
+                        T = EXACT_DIV ? T / one_m_alpha : T * rcp_1ma;
                         const float dchannel_dcolor = alpha * T;
                         const float dpixel_depth_ddepth = alpha * T;
                         float dL_dopa = 0.0f;
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel
                         dL_dopa *= T;
                         last_alpha = alpha;
                         // background (backward.cu:573-578)
-                        dL_dopa += (-T_final * rcp_1ma) * bg_dot_dpixel;
+                        dL_dopa += (EXACT_DIV ? -T_final / one_m_alpha : -T_final * rcp_1ma) * bg_dot_dpixel;
 
                         const float dL_dG = rb.y * dL_dopa;
                         const float gdx = G * d.x;
@@ -660,14 +664,23 @@ void gvd_launch_zero_bytes(void* p, size_t bytes, cudaStream_t s) {
 template <int SPLIT>
 static void launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                    const RasterImgPtrs& im, float* acc, float4* zero, size_t zero_n4, dim3 grid, cudaStream_t s) {
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        carveout_set = true;
+    // GVD_BWD_EXACT_DIV=1: the reference's two IEEE divisions per contribution instead of one reciprocal + two
+    // multiplications. Measured: +12 us (200 -> 212 us at C2), no change in any parity figure; off by default.
+    static int exact = -1;
+    if (exact < 0) {
+        const char* e = getenv("GVD_BWD_EXACT_DIV");
+        exact = (e && e[0] == '1') ? 1 : 0;
+        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
-    gvd_launch(render_backward_kernel<SPLIT>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
-               g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
-               a.dL_dalpha_pix, acc, zero, zero_n4);
+    if (exact)
+        gvd_launch(render_backward_kernel<SPLIT, true>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+                   g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
+                   a.dL_dalpha_pix, acc, zero, zero_n4);
+    else
+        gvd_launch(render_backward_kernel<SPLIT, false>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+                   g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
+                   a.dL_dalpha_pix, acc, zero, zero_n4);
 }
 
 void gvd_launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,

@@ -42,23 +42,23 @@ struct RasterGeomPtrs {
 };
 
 // Depth sort = least-significant-digit radix sort (4 passes of 8 bits) over the V compacted (depth bits, id) pairs,
-// V read from device memory. One kernel per pass: a CTA ranks its tile of GVD_SORT_TILE keys stably and finds its
-// global offsets from per-tile digit histograms that the PREVIOUS kernel accumulated with atomics while it
-// scattered (the compaction kernel for pass 0), so there is neither a histogram kernel per pass nor a chained scan.
+// V read from device memory. One kernel per pass: a CTA ranks its tile of GVD_SORT_TILE keys stably, publishes its
+// digit counts as flagged words and sums those of its predecessors (groups of GVD_SORT_SUPER tiles, one running total
+// per group), so there is no histogram kernel per pass and no per-key atomic.
 #define GVD_PRE_BLOCK 256        // threads per preprocess CTA
 #define GVD_COMPACT_BLOCK 1024   // threads per compaction CTA (= 4 preprocess CTAs)
 #define GVD_SORT_TILE 1024       // keys per sort CTA
 #define GVD_SORT_THREADS 256
-#define GVD_SORT_SUPER 32        // tiles per super-tile (second histogram level bounds the offset lookup)
+#define GVD_SORT_SUPER 32        // tiles per group (bounds the number of predecessor counts a tile has to fetch)
 struct RasterSortPtrs {
     uint32_t* depth_key;       // [P] per Gaussian id: depth bits (undefined when culled)
     uint32_t* blk_vis;         // [nb] visible Gaussians per preprocess CTA
     uint32_t* blk_tiles;       // [nb] instances per preprocess CTA
     uint32_t* key[2];          // [P] ping-pong
     uint32_t* val[2];          // [P] ping-pong; val[0] holds the depth-sorted ids after the 4th pass
-    uint32_t* zeroed;          // ghist[4][256] | thist[4][nt][256] | shist[4][ns][256], cleared by preprocess
+    uint32_t* zeroed;          // ghist[4][256] | agg[4][nt][256] | incl[4][ns][256] | ticket[4], cleared by preprocess
     size_t zeroed_words;
-    uint32_t *ghist, *thist, *shist;
+    uint32_t *ghist, *agg, *incl, *ticket;
     size_t nb, nt, ns;
 };
 

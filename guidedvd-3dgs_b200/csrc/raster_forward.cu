@@ -102,18 +102,23 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
 // Half extents of the axis-aligned bound of { d : opac * exp(power(d)) >= 1/255 } (power = -q(d)/2 with the
 // conic as quadratic form), inflated by a slack that dwarfs any rounding in the per-pixel evaluation.
 // -1e30: can never contribute (opac < 1/255: alpha <= opac).  +1e30: no usable bound.
+// The extents are those of the level set of the ROUNDED conic the render kernels evaluate, sqrt(t * C / (A C - B^2)) and
+// sqrt(t * A / (A C - B^2)); the determinant is formed in double (products of floats are exact there). In fp32 it
+// cancels for elongated, rotated footprints (A C ~ B^2): round 1's fp32 version under-estimated the extents of such
+// Gaussians and dropped a few of their faintest contributions -- invisible at 1e-4 in the images of ordinary scenes,
+// 9e-4 in the gradients of a scene of large anisotropic Gaussians (tests/test_render_dropin_gpu.py).
 __device__ __forceinline__ void alpha_extent(const float3 conic, float opac, float& hx, float& hy) {
     hx = hy = 1e30f;
     if (opac * 255.0f < 0.999f) {
         hx = hy = -1e30f;
         return;
     }
-    const float A = conic.x, B = conic.y, C = conic.z;
+    const double A = conic.x, B = conic.y, C = conic.z;
     const float t = 2.0f * logf(opac * 255.0f) * 1.0005f + 1e-3f;  // q(d) <= t  <=>  power >= -t/2
-    const float det = A * C - B * B;
-    if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f) || !(t >= 0.0f)) return;
-    const float ex = sqrtf(t * C / det) * 1.0005f + 0.02f;
-    const float ey = sqrtf(t * A / det) * 1.0005f + 0.02f;
+    const double det = A * C - B * B;
+    if (!(det > 0.0) || !(A > 0.0) || !(C > 0.0) || !(t >= 0.0f)) return;
+    const float ex = (float)sqrt((double)t * C / det) * 1.0005f + 0.02f;
+    const float ey = (float)sqrt((double)t * A / det) * 1.0005f + 0.02f;
     if (!(ex < 1e9f) || !(ey < 1e9f)) return;
     hx = ex;
     hy = ey;
@@ -128,7 +133,7 @@ __device__ __forceinline__ uint32_t preprocess_one(
     const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
     const float* __restrict__ projmatrix, const float3* __restrict__ cam_pos, const int W, int H,
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
-    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ depth_key, int prefiltered) {
+    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ depth_key, int prefiltered, int no_cull) {
     radii[idx] = 0;
 
     // near cull (auxiliary.h:139-164): only p_view.z <= 0.2 rejects.
@@ -188,6 +193,7 @@ __device__ __forceinline__ uint32_t preprocess_one(
     rec.b = make_float4(conic.z, opacities[idx], rgb.x, rgb.y);
     float hx, hy;
     alpha_extent(conic, opacities[idx], hx, hy);
+    if (no_cull) hx = hy = 1e30f;  // GVD_NO_SUBTILE_CULL=1: every warp visits every instance of its tile (A/B and diagnosis knob)
     rec.c = make_float4(rgb.z, p_view.z, hx, hy);
     rec.d = make_float4(__uint_as_float(rect_min.x | (rect_min.y << 16)), __uint_as_float(rect_max.x | (rect_max.y << 16)),
                         0.f, 0.f);
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
     SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched,
     uint32_t* __restrict__ depth_key, uint32_t* __restrict__ blk_vis, uint32_t* __restrict__ blk_tiles,
-    uint32_t* __restrict__ zeroed, size_t zeroed_words, int prefiltered) {
+    uint32_t* __restrict__ zeroed, size_t zeroed_words, int prefiltered, int no_cull) {
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t warp_tiles[GVD_PRE_BLOCK / 32];
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
     if (idx < P) {
         tiles = preprocess_one(idx, D, M, orig_points, scales, scale_modifier, rotations, opacities, shs, clamped, cov3D_precomp,
                                colors_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y, radii,
-                               splat, grid, depth_key, prefiltered);
+                               splat, grid, depth_key, prefiltered, no_cull);
         tiles_touched[idx] = tiles;
     }
     const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
@@ -247,13 +253,13 @@ __device__ __forceinline__ uint32_t block_sum_1024(uint32_t v, uint32_t* warp_bu
 
 // CTA b owns the ids [b * 1024, (b + 1) * 1024): its visible ones go, in id order, to the compacted positions
 // base_b + rank (base_b = visible Gaussians of all earlier preprocess CTAs). Writes the (depth bits, id) pairs the sort
-// starts from, vis_id (kept for the backward), the four 8-bit digit histograms of all keys and pass 0's per-tile
-// histograms; the last CTA publishes V and R (device words and, if given, pinned host words).
+// starts from, vis_id (kept for the backward) and the four 8-bit digit histograms of all keys (warp-aggregated with
+// MATCH.ANY first: the top byte of a depth takes a handful of values, plain shared-memory atomics on it serialise);
+// the last CTA publishes V and R (device words and, if given, pinned host words).
 __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
     int P, int nb, const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ depth_key,
     const uint32_t* __restrict__ blk_vis, const uint32_t* __restrict__ blk_tiles, uint32_t* __restrict__ key0,
-    uint32_t* __restrict__ val0, uint32_t* __restrict__ vis_id, uint32_t* __restrict__ counts, uint32_t* ghist,
-    uint32_t* thist0, uint32_t* shist0, int* r_host) {
+    uint32_t* __restrict__ val0, uint32_t* __restrict__ vis_id, uint32_t* __restrict__ counts, uint32_t* ghist, int* r_host) {
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t hist_s[4 * 256];
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
     __shared__ uint32_t warp_cnt[32];
     __shared__ uint32_t s_base, s_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     hist_s[tid] = 0u;
     const int first_blk = (int)blockIdx.x * (GVD_COMPACT_BLOCK / GVD_PRE_BLOCK);
     uint32_t s = 0;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
     const uint32_t key = vis ? depth_key[idx] : 0u;
     const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
     if (lane == 0) warp_cnt[warp] = __popc(ballot);
-    const uint32_t base_w0 = block_sum_1024(s, warp_buf);  // contains a __syncthreads: warp_cnt is visible below
+    const uint32_t base_w0 = block_sum_1024(s, warp_buf);  // contains a __syncthreads: warp_cnt and hist_s = 0 are visible below
     if (warp == 0) {
         const uint32_t c = warp_cnt[lane];
         uint32_t incl = c;
@@ -283,32 +290,31 @@ __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
         if (lane == 31) s_total = incl;
         if (lane == 0) s_base = base_w0;
     }
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const uint32_t d = vis ? ((key >> (8 * pass)) & 255u) : (256u + lane);  // invisible lanes match nobody
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (vis && (peers & lt_mask) == 0u) atomicAdd(&hist_s[256 * pass + d], (uint32_t)__popc(peers));
+    }
     __syncthreads();
     const uint32_t base = s_base;
     if (vis) {
-        const uint32_t pos = base + warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u));
+        const uint32_t pos = base + warp_cnt[warp] + __popc(ballot & lt_mask);
         key0[pos] = key;
         val0[pos] = (uint32_t)idx;
         vis_id[pos] = (uint32_t)idx;
-        const uint32_t d0 = key & 255u;
-        atomicAdd(&hist_s[d0], 1u);
-        atomicAdd(&hist_s[256 + ((key >> 8) & 255u)], 1u);
-        atomicAdd(&hist_s[512 + ((key >> 16) & 255u)], 1u);
-        atomicAdd(&hist_s[768 + (key >> 24)], 1u);
-        atomicAdd(&thist0[(size_t)(pos / GVD_SORT_TILE) * 256 + d0], 1u);
-        atomicAdd(&shist0[(size_t)(pos / (GVD_SORT_TILE * GVD_SORT_SUPER)) * 256 + d0], 1u);
     }
-    __syncthreads();
     if (hist_s[tid]) atomicAdd(&ghist[tid], hist_s[tid]);
     if (blockIdx.x == gridDim.x - 1) {
         uint32_t r = 0;
         for (int k = (int)tid; k < nb; k += GVD_COMPACT_BLOCK) r += blk_tiles[k];
-        // blocks past first_blk (this CTA's own preprocess blocks) are in s_total; earlier ones in base
+        __syncthreads();  // warp_buf is reused
         const uint32_t R = block_sum_1024(r, warp_buf);
         if (tid == 0) {
             const uint32_t V = base + s_total;
             counts[0] = V;
             counts[1] = R;
+            counts[7] = 0u;  // error word of the depth sort (a flag wait that gave up)
             // R (and V) go straight into the caller's pinned, device-mapped host words: a cudaMemcpyAsync in the compute
             // stream queues behind whatever the copy engines are busy with (measured +46 us per step in round 1).
             if (r_host != nullptr) {
@@ -320,32 +326,49 @@ __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
     }
 }
 
-// One pass of the stable LSD radix sort: CTA j ranks keys [j * 1024, ...) on the digit (key >> shift) & 255.
-//   offsets: digit d of tile j starts at  (keys of smaller digits, from ghist)
-//                                        + (keys with digit d in earlier tiles: full super-tiles from shist, the rest from thist)
-//   ranking: warp w owns 128 consecutive keys, 4 rounds of 32 (lane = consecutive index, so lane order = input order);
-//            same-digit lanes of a round are ranked with MATCH.ANY, rounds and warps through per-warp counters wh[w][d]
-//   while scattering, the CTA adds every key's NEXT digit to the histogram of the tile the key lands in, which is what the
-//   next pass looks up.
+// One pass of the stable LSD radix sort: a CTA ranks a tile of 1024 keys on the digit (key >> shift) & 255.
+//   tile id : a ticket (atomic counter), so every predecessor of a tile has started before it -- the waits below cannot
+//             deadlock whatever the order in which the hardware dispatches CTAs
+//   ranking : warp w owns 128 consecutive keys, 4 rounds of 32 (lane = consecutive index, so lane order = input order);
+//             same-digit lanes of a round are ranked with MATCH.ANY, rounds and warps through per-warp counters wh[w][d]
+//   offsets : thread = digit d. The tile publishes its count of d (flagged word), then needs the number of keys with
+//             digit d in all earlier tiles: the flagged counts of the <= 31 predecessors in its group of 32 tiles,
+//             fetched with independent loads (re-fetched until their flags are up: all tiles of a wave publish at about
+//             the same time), plus the running total the last tile of the previous group published. Keys with smaller
+//             digits come from the global digit histogram the compaction kernel made.
+// No per-key atomics, no histogram kernel, no chain of dependent round trips longer than the number of groups.
+// A first version let each pass accumulate the next pass's per-tile histograms with two RED.ADD per key while it
+// scattered: 18-30 us per pass at C2 against 7 us for the last pass, which had none (profiles/r02_ncu_binning_*).
+#define GVD_SORT_FLAG 0x80000000u
+#define GVD_SORT_SPIN_LIMIT (1u << 22)
+#ifdef GVD_HOST_EMU
+#define gvd_nanosleep(ns) emu_yield()
+#else
+#define gvd_nanosleep(ns) __nanosleep(ns)
+#endif
+__device__ __forceinline__ uint32_t ld_flagged(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
 __global__ void __launch_bounds__(GVD_SORT_THREADS) sort_pass_kernel(
     const uint32_t* __restrict__ counts, const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-    uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, const uint32_t* __restrict__ ghist,
-    const uint32_t* __restrict__ thist, const uint32_t* __restrict__ shist, uint32_t* thist_next, uint32_t* shist_next,
-    int shift, int next_shift) {
+    uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, const uint32_t* __restrict__ ghist, uint32_t* agg,
+    uint32_t* incl, uint32_t* ticket, uint32_t* error_word, int shift) {
     pdl_wait();
     pdl_trigger();
     constexpr int WARPS = GVD_SORT_THREADS / 32, PER_WARP = GVD_SORT_TILE / WARPS, ROUNDS = PER_WARP / 32;
     static_assert(GVD_SORT_THREADS == 256, "one thread per digit in the offset phase");
     __shared__ uint32_t wh[WARPS][256];
     __shared__ uint32_t warp_tot[WARPS];
+    __shared__ uint32_t s_tile;
     const uint32_t V = counts[0];
-    const uint32_t tile = blockIdx.x, start = tile * GVD_SORT_TILE;
-    if (start >= V) return;
-    const uint32_t n = min((uint32_t)GVD_SORT_TILE, V - start);
+    if (blockIdx.x * GVD_SORT_TILE >= V) return;  // as many tickets are drawn as there are tiles with keys
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) wh[w][tid] = 0u;
+    __syncthreads();
+    const uint32_t tile = s_tile, start = tile * GVD_SORT_TILE;
+    const uint32_t n = min((uint32_t)GVD_SORT_TILE, V - start);
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     uint32_t key[ROUNDS], val[ROUNDS];
     bool valid[ROUNDS];
@@ -356,7 +379,7 @@ __global__ void __launch_bounds__(GVD_SORT_THREADS) sort_pass_kernel(
         key[r] = valid[r] ? kin[start + off] : 0u;
         val[r] = valid[r] ? vin[start + off] : 0u;
     }
-    __syncthreads();
+    const uint32_t g = ghist[tid];
     // phase A: per-warp digit counts
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
@@ -366,24 +389,55 @@ __global__ void __launch_bounds__(GVD_SORT_THREADS) sort_pass_kernel(
         __syncwarp();
     }
     __syncthreads();
-    // phase B: thread = digit. Exclusive scan over the warps, global start of the digit for this tile.
+    // phase B: thread = digit
     {
-        const uint32_t g = ghist[tid];
-        uint32_t incl = g;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) cnt += wh[w][tid];
+        *reinterpret_cast<volatile uint32_t*>(agg + (size_t)tile * 256 + tid) = cnt | GVD_SORT_FLAG;
+
+        uint32_t ginc = g;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += u;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, ginc, o);
+            if (lane >= (uint32_t)o) ginc += u;
         }
-        if (lane == 31) warp_tot[warp] = incl;
-        uint32_t prior = 0;
-        const uint32_t sup = tile / GVD_SORT_SUPER;
-        for (uint32_t sblk = 0; sblk < sup; ++sblk) prior += shist[(size_t)sblk * 256 + tid];
-        for (uint32_t t = sup * GVD_SORT_SUPER; t < tile; ++t) prior += thist[(size_t)t * 256 + tid];
+        if (lane == 31) warp_tot[warp] = ginc;
+
+        const uint32_t group = tile / GVD_SORT_SUPER, g0 = group * GVD_SORT_SUPER;
+        uint32_t prior = 0, spins = 0;
+        bool gave_up = false;
+        for (uint32_t i = g0; i < tile;) {  // the predecessors inside the group, eight independent loads at a time
+            uint32_t v[8];
+            bool ready = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] = i + k < tile ? ld_flagged(agg + (size_t)(i + k) * 256 + tid) : GVD_SORT_FLAG;
+                ready = ready && (v[k] & GVD_SORT_FLAG);
+            }
+            if (!ready) {
+                if (++spins > GVD_SORT_SPIN_LIMIT) { gave_up = true; break; }
+                gvd_nanosleep(40);
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) prior += v[k] & ~GVD_SORT_FLAG;
+            i += 8;
+        }
+        if (group > 0 && !gave_up) {  // everything before the group: the running total its predecessor group ended with
+            uint32_t v;
+            while (!((v = ld_flagged(incl + (size_t)(group - 1) * 256 + tid)) & GVD_SORT_FLAG)) {
+                if (++spins > GVD_SORT_SPIN_LIMIT) { gave_up = true; break; }
+                gvd_nanosleep(40);
+            }
+            prior += v & ~GVD_SORT_FLAG;
+        }
+        if (gave_up) *error_word = 1u;  // never hang the GPU: finish with wrong offsets and say so
+        if (tile % GVD_SORT_SUPER == GVD_SORT_SUPER - 1)
+            *reinterpret_cast<volatile uint32_t*>(incl + (size_t)group * 256 + tid) = (prior + cnt) | GVD_SORT_FLAG;
         __syncthreads();
-        uint32_t digit_base = incl - g;
-        for (uint32_t w = 0; w < warp; ++w) digit_base += warp_tot[w];
-        uint32_t run = digit_base + prior;
+        uint32_t run = ginc - g + prior;
+        for (uint32_t w = 0; w < warp; ++w) run += warp_tot[w];
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
             const uint32_t c = wh[w][tid];
@@ -405,11 +459,6 @@ __global__ void __launch_bounds__(GVD_SORT_THREADS) sort_pass_kernel(
         if (valid[r]) {
             kout[pos] = key[r];
             vout[pos] = val[r];
-            if (next_shift >= 0) {
-                const uint32_t nd = (key[r] >> next_shift) & 255u;
-                atomicAdd(&thist_next[(size_t)(pos / GVD_SORT_TILE) * 256 + nd], 1u);
-                atomicAdd(&shist_next[(size_t)(pos / (GVD_SORT_TILE * GVD_SORT_SUPER)) * 256 + nd], 1u);
-            }
         }
     }
 }
@@ -567,25 +616,33 @@ __global__ void __launch_bounds__(1024) bin_ranges_kernel(int T, const uint32_t*
 // Pass 4: chunk c writes its Gaussians' ids into the tile lists. The slot of Gaussian j (0..63, depth order inside the
 // chunk) in tile t is  ranges[t].x + hist[c][t] (the chunk's starting rank in t, from pass 2) + the number of earlier
 // Gaussians of the chunk that cover t.  That last term comes from two 32-bit coverage masks per tile in shared memory:
-//   phase 1  every (Gaussian, tile) instance of the chunk ORs bit j into mask[j / 32][t]   (native 32-bit ATOMS.OR)
-//   phase 2  every instance reads its tile's masks back: rank = popc(bits below j); one 4-byte store.
-// Both phases spread the chunk's flattened instance sequence over all 256 threads (binary search over the 64 instance
-// offsets), so there is no serial walk and no ordering between instances. Chunks above GVD_FILL_ROWS instances (the
-// Gaussians nearest to the camera, rects up to the whole screen) skip the per-instance search: (Gaussian, tile row)
-// units are dealt to the warps and the lanes run along the row.
-// Round 1's version walked each chunk with ONE warp, 32 instances at a time (load-balanced search + MATCH.ANY ranking,
-// 8.3 warp-instructions per instance, 80 us at C2). tools/ubench_scatter_store.cu showed the 3.7 M scattered 4-byte
-// stores themselves cost 25 us against 18.5 us for a coalesced stream, i.e. the walk was the cost, not the stores.
-// The masks cover a BAND of tile rows (the whole image when 2 * T words fit the shared-memory budget: always at the
+//   phase 0  every (Gaussian, tile) instance of the chunk ORs bit j into mask[j / 32][t]   (native 32-bit ATOMS.OR)
+//   phase 1  every instance reads its tile's masks back: rank = popc(bits below j); one 4-byte store.
+// The work unit is a (Gaussian, tile row) pair, found by a binary search over the 64 row offsets: one thread per unit,
+// walking along the row. No serial walk over the chunk, no ordering between instances. The per-tile bases (ranges +
+// hist row) of the chunk's bounding box are staged in shared memory once, with full memory-level parallelism, so the
+// inner loops touch shared memory only.
+// Chunks whose Gaussians cover their bounding box more than GVD_FILL_DENSE times over (the Gaussians nearest to the
+// camera: rects up to the whole screen, 40 000 instances in one chunk at C2) go tile-major instead: one thread per tile
+// of the box tests the 64 rects (one broadcast 16-byte shared load each), builds the two masks in REGISTERS and emits
+// the tile's ids in order -- no atomics, no barriers, and the chunk's work is spread evenly over the CTA whatever the
+// rect sizes.
+// History: round 1 walked each chunk with ONE warp, 32 instances at a time (load-balanced search + MATCH.ANY ranking,
+// 8.3 warp-instructions per instance, 80 us at C2); tools/ubench_scatter_store.cu showed the 3.7 M scattered 4-byte stores
+// themselves cost 25 us against 18.5 us for a coalesced stream, i.e. the walk was the cost, not the stores. Mask
+// versions that gave a heavy chunk's (Gaussian, row) units to 8 warps took 171-207 us: 200 dependent iterations per
+// warp in the heaviest chunk were the whole kernel (ncu: SMs active 49 % of the kernel's duration).
+// The planes cover a BAND of tile rows (the whole image when 3 * T words fit the shared-memory budget: always at the
 // benchmark sizes; larger images are walked band by band, restricted to the rows the chunk's Gaussians reach).
 struct FillChunk {  // the chunk's Gaussians in depth order
-    uint32_t id[GVD_BIN_CHUNK], r0[GVD_BIN_CHUNK], r1[GVD_BIN_CHUNK], off[GVD_BIN_CHUNK + 1], roff[GVD_BIN_CHUNK + 1], magic[GVD_BIN_CHUNK];
-    uint32_t wn[2], wr[2], wy0[2], wy1[2];
+    uint4 box[GVD_BIN_CHUNK];  // {x0, x1 - x0, y0, y1 - y0} in tiles
+    uint32_t id[GVD_BIN_CHUNK], roff[GVD_BIN_CHUNK + 1];
+    uint32_t wn[2], wr[2], wy0[2], wy1[2], wx0[2], wx1[2];
 };
 
 #define GVD_FILL_THREADS 256
-#define GVD_FILL_ROWS 4096
-#define GVD_FILL_MASK_BYTES (160 * 1024)  // shared-memory budget of the two mask planes
+#define GVD_FILL_DENSE 8
+#define GVD_FILL_SMEM_BYTES (192 * 1024)  // shared-memory budget of the three planes
 __device__ __forceinline__ uint32_t upper_slot(const uint32_t* off, uint32_t m, uint32_t q) {  // largest j < m with off[j] <= q
     uint32_t lo = 0, hi = m;  // invariant: off[lo] <= q < off[hi]
 #pragma unroll
@@ -605,17 +662,19 @@ __global__ void __launch_bounds__(GVD_FILL_THREADS) bin_fill_kernel(const uint32
                                                                    uint32_t* __restrict__ point_list, uint32_t capacity) {
     pdl_wait();
     pdl_trigger();
-    extern __shared__ uint32_t mask[];  // [2][band_rows * tiles_x]: bits 0..31 / 32..63 of the chunk's coverage of every tile
+    extern __shared__ uint32_t planes[];  // mask bits 0..31 | mask bits 32..63 | base slot, each [band_rows * tiles_x]
     __shared__ FillChunk fc;
     static_assert(GVD_BIN_CHUNK == 64, "two warps load the chunk; two mask words per tile");
     const uint32_t V = counts[0];
     if (blockIdx.x * GVD_BIN_CHUNK >= V) return;
     const uint32_t m = min((uint32_t)GVD_BIN_CHUNK, V - blockIdx.x * GVD_BIN_CHUNK);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* row = hist + (size_t)blockIdx.x * T;
     const uint32_t plane = band_rows * tiles_x;
+    uint32_t* mask = planes;
+    uint32_t* base = planes + 2 * plane;
     if (tid < GVD_BIN_CHUNK) {
-        uint32_t n = 0, nr = 0, r0 = 0, r1 = 0, id = 0, ymin = 0xffffu, ymax = 0u;
+        uint32_t n = 0, nr = 0, r0 = 0, r1 = 0, id = 0, ymin = 0xffffu, ymax = 0u, xmin = 0xffffu, xmax = 0u;
         if (tid < m) {
             id = order[blockIdx.x * GVD_BIN_CHUNK + tid];
             const float4 d = splat[id].d;
@@ -623,8 +682,10 @@ __global__ void __launch_bounds__(GVD_FILL_THREADS) bin_fill_kernel(const uint32
             r1 = __float_as_uint(d.y);
             ymin = r0 >> 16;
             ymax = r1 >> 16;
+            xmin = r0 & 0xffff;
+            xmax = r1 & 0xffff;
             nr = ymax - ymin;
-            n = nr * ((r1 & 0xffff) - (r0 & 0xffff));
+            n = nr * (xmax - xmin);
         }
         uint32_t incl = n, rincl = nr;
 #pragma unroll
@@ -634,69 +695,91 @@ __global__ void __launch_bounds__(GVD_FILL_THREADS) bin_fill_kernel(const uint32
         }
         ymin = __reduce_min_sync(0xffffffffu, ymin);
         ymax = __reduce_max_sync(0xffffffffu, ymax);
-        if (lane == 31) { fc.wn[warp] = incl; fc.wr[warp] = rincl; fc.wy0[warp] = ymin; fc.wy1[warp] = ymax; }
-        fc.id[tid] = id; fc.r0[tid] = r0; fc.r1[tid] = r1;
-        const uint32_t bw = (r1 & 0xffff) - (r0 & 0xffff);
-        fc.magic[tid] = bw > 1 ? 0xffffffffu / bw + 1u : 0u;  // floor(k / bw) == umulhi(k, magic) for k * bw < 2^32 (bw > 1)
-        fc.off[tid] = incl - n;     // warp 1's entries get warp 0's total added below
-        fc.roff[tid] = rincl - nr;
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        if (lane == 31) {
+            fc.wn[warp] = incl; fc.wr[warp] = rincl;
+            fc.wy0[warp] = ymin; fc.wy1[warp] = ymax; fc.wx0[warp] = xmin; fc.wx1[warp] = xmax;
+        }
+        fc.id[tid] = id;
+        fc.box[tid] = tid < m ? make_uint4(r0 & 0xffff, (r1 & 0xffff) - (r0 & 0xffff), r0 >> 16, (r1 >> 16) - (r0 >> 16))
+                              : make_uint4(0u, 0u, 0u, 0u);
+        fc.roff[tid] = rincl - nr;  // warp 1's entries get warp 0's total added below
     }
     __syncthreads();
-    if (tid >= 32 && tid < GVD_BIN_CHUNK) { fc.off[tid] += fc.wn[0]; fc.roff[tid] += fc.wr[0]; }
-    if (tid == 0) { fc.off[GVD_BIN_CHUNK] = fc.wn[0] + fc.wn[1]; fc.roff[GVD_BIN_CHUNK] = fc.wr[0] + fc.wr[1]; }
+    if (tid >= 32 && tid < GVD_BIN_CHUNK) fc.roff[tid] += fc.wr[0];
+    if (tid == 0) fc.roff[GVD_BIN_CHUNK] = fc.wr[0] + fc.wr[1];
     __syncthreads();
-    const uint32_t total = fc.off[GVD_BIN_CHUNK], units = fc.roff[GVD_BIN_CHUNK];
-    const uint32_t ylo = min(fc.wy0[0], fc.wy0[1]), yhi = max(fc.wy1[0], fc.wy1[1]);  // tile rows the chunk reaches
+    const uint32_t total = fc.wn[0] + fc.wn[1], units = fc.roff[GVD_BIN_CHUNK];
+    const uint32_t ylo = min(fc.wy0[0], fc.wy0[1]), yhi = max(fc.wy1[0], fc.wy1[1]);  // tile rows / columns the chunk reaches
+    const uint32_t xlo = min(fc.wx0[0], fc.wx0[1]), xhi = max(fc.wx1[0], fc.wx1[1]);
+    const uint32_t bbw = xhi - xlo;
+
+    if (total > GVD_FILL_DENSE * bbw * (yhi - ylo)) {
+        // tile-major: thread = tile of the bounding box
+        const uint32_t cells = (yhi - ylo) * bbw;
+        for (uint32_t c = tid; c < cells; c += blockDim.x) {
+            const uint32_t cy = c / bbw, tx = xlo + (c - cy * bbw), ty = ylo + cy;
+            const uint32_t t = ty * tiles_x + tx;
+            uint32_t slot = ranges[t].x + row[t];
+            uint32_t lo = 0u, hi = 0u;
+#pragma unroll 8
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint4 bx = fc.box[j];
+                lo |= (uint32_t)((tx - bx.x < bx.y) && (ty - bx.z < bx.w)) << j;
+            }
+#pragma unroll 8
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint4 bx = fc.box[32 + j];
+                hi |= (uint32_t)((tx - bx.x < bx.y) && (ty - bx.z < bx.w)) << j;
+            }
+            while (lo) {
+                const uint32_t j = (uint32_t)__ffs((int)lo) - 1u;
+                lo &= lo - 1u;
+                if (slot < capacity) point_list[slot] = fc.id[j];  // capacity: speculative buffers may be too small
+                ++slot;
+            }
+            while (hi) {
+                const uint32_t j = (uint32_t)__ffs((int)hi) - 1u;
+                hi &= hi - 1u;
+                if (slot < capacity) point_list[slot] = fc.id[32 + j];
+                ++slot;
+            }
+        }
+        return;
+    }
 
     for (uint32_t b0 = ylo - ylo % band_rows; b0 < yhi; b0 += band_rows) {
         const uint32_t b1 = b0 + band_rows;
-        {   // clear the mask rows this chunk can touch inside the band
-            const uint32_t z0 = (max(b0, ylo) - b0) * tiles_x, z1 = (min(b1, yhi) - b0) * tiles_x;
-            for (uint32_t t = z0 + tid; t < z1; t += blockDim.x) { mask[t] = 0u; mask[plane + t] = 0u; }
+        {   // clear the masks and stage the bases of the bounding box inside this band
+            const uint32_t y0 = max(b0, ylo), y1 = min(b1, yhi);
+            const uint32_t cells = (y1 - y0) * bbw;
+            for (uint32_t c = tid; c < cells; c += blockDim.x) {
+                const uint32_t cy = c / bbw, cx = c - cy * bbw;
+                const uint32_t t = (y0 + cy) * tiles_x + xlo + cx, lt = (y0 + cy - b0) * tiles_x + xlo + cx;
+                mask[lt] = 0u;
+                mask[plane + lt] = 0u;
+                base[lt] = ranges[t].x + row[t];
+            }
         }
         __syncthreads();
         for (int phase = 0; phase < 2; ++phase) {
-            if (total <= GVD_FILL_ROWS) {
-                // flattened (Gaussian, tile) instances over all threads
-                for (uint32_t q = tid; q < total; q += blockDim.x) {
-                    const uint32_t j = upper_slot(fc.off, GVD_BIN_CHUNK, q);
-                    const uint32_t g0 = fc.r0[j], g1 = fc.r1[j];
-                    const uint32_t x0 = g0 & 0xffff, bw = (g1 & 0xffff) - x0;
-                    const uint32_t k = q - fc.off[j];
-                    const uint32_t ry = bw > 1 ? __umulhi(k, fc.magic[j]) : k;
-                    const uint32_t ty = (g0 >> 16) + ry, tx = x0 + (k - ry * bw);
-                    if (ty < b0 || ty >= b1) continue;
-                    const uint32_t lt = (ty - b0) * tiles_x + tx;
+            for (uint32_t u = tid; u < units; u += blockDim.x) {
+                const uint32_t j = upper_slot(fc.roff, GVD_BIN_CHUNK, u);
+                const uint4 bx = fc.box[j];
+                const uint32_t ty = bx.z + (u - fc.roff[j]), x0 = bx.x, x1 = bx.x + bx.y;
+                if (ty < b0 || ty >= b1) continue;
+                const uint32_t gid = fc.id[j], bit = 1u << (j & 31), below = bit - 1u;
+                uint32_t* mrow = mask + (ty - b0) * tiles_x;
+                const uint32_t* brow = base + (ty - b0) * tiles_x;
+                for (uint32_t tx = x0; tx < x1; ++tx) {
                     if (phase == 0) {
-                        atomicOr(&mask[(j >> 5) * plane + lt], 1u << (j & 31));
+                        atomicOr(&mrow[(j >> 5) * plane + tx], bit);
                     } else {
-                        const uint32_t lo = mask[lt];
-                        const uint32_t rank = j < 32 ? __popc(lo & ((1u << j) - 1u))
-                                                     : __popc(lo) + __popc(mask[plane + lt] & ((1u << (j - 32)) - 1u));
-                        const uint32_t t = ty * tiles_x + tx;
-                        const uint32_t slot = ranges[t].x + row[t] + rank;
-                        if (slot < capacity) point_list[slot] = fc.id[j];  // capacity: speculative buffers may be too small
-                    }
-                }
-            } else {
-                // heavy chunk: (Gaussian, tile row) units over the warps, lanes along the row
-                for (uint32_t u = warp; u < units; u += nw) {
-                    const uint32_t j = upper_slot(fc.roff, GVD_BIN_CHUNK, u);
-                    const uint32_t g0 = fc.r0[j], g1 = fc.r1[j];
-                    const uint32_t ty = (g0 >> 16) + (u - fc.roff[j]), x0 = g0 & 0xffff, x1 = g1 & 0xffff;
-                    if (ty < b0 || ty >= b1) continue;
-                    const uint32_t gid = fc.id[j], bit = 1u << (j & 31), below = bit - 1u;
-                    for (uint32_t tx = x0 + lane; tx < x1; tx += 32) {
-                        const uint32_t lt = (ty - b0) * tiles_x + tx;
-                        if (phase == 0) {
-                            atomicOr(&mask[(j >> 5) * plane + lt], bit);
-                        } else {
-                            const uint32_t lo = mask[lt];
-                            const uint32_t rank = j < 32 ? __popc(lo & below) : __popc(lo) + __popc(mask[plane + lt] & below);
-                            const uint32_t t = ty * tiles_x + tx;
-                            const uint32_t slot = ranges[t].x + row[t] + rank;
-                            if (slot < capacity) point_list[slot] = gid;
-                        }
+                        const uint32_t lo = mrow[tx];
+                        const uint32_t rank = j < 32 ? __popc(lo & below) : __popc(lo) + __popc(mrow[plane + tx] & below);
+                        const uint32_t slot = brow[tx] + rank;
+                        if (slot < capacity) point_list[slot] = gid;
                     }
                 }
             }
@@ -876,17 +959,22 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& g, const RasterSortPtrs& so, float focal_x,
                            float focal_y, dim3 grid, cudaStream_t s) {
+    static int no_cull = -1;
+    if (no_cull < 0) {
+        const char* e = getenv("GVD_NO_SUBTILE_CULL");
+        no_cull = (e && e[0] == '1') ? 1 : 0;
+    }
     gvd_launch(preprocess_kernel, dim3((unsigned)so.nb), dim3(GVD_PRE_BLOCK), 0, s,
         a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
         a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
         (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
-        g.tiles_touched, so.depth_key, so.blk_vis, so.blk_tiles, so.zeroed, so.zeroed_words, a.prefiltered);
+        g.tiles_touched, so.depth_key, so.blk_vis, so.blk_tiles, so.zeroed, so.zeroed_words, a.prefiltered, no_cull);
 }
 
 void gvd_launch_compact(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, int* r_host, cudaStream_t s) {
     const unsigned blocks = (unsigned)((P + GVD_COMPACT_BLOCK - 1) / GVD_COMPACT_BLOCK);
     gvd_launch(compact_kernel, dim3(blocks), dim3(GVD_COMPACT_BLOCK), 0, s, P, (int)so.nb, g.tiles_touched, so.depth_key, so.blk_vis,
-               so.blk_tiles, so.key[0], so.val[0], g.vis_id, g.counts, so.ghist, so.thist, so.shist, r_host);
+               so.blk_tiles, so.key[0], so.val[0], g.vis_id, g.counts, so.ghist, r_host);
 }
 
 void gvd_launch_depth_sort(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, cudaStream_t s) {
@@ -895,11 +983,9 @@ void gvd_launch_depth_sort(int P, const RasterGeomPtrs& g, const RasterSortPtrs&
     (void)P;
     for (int pass = 0; pass < 4; ++pass) {
         const int in = pass & 1, out = in ^ 1;
-        uint32_t* th_next = pass < 3 ? so.thist + (size_t)(pass + 1) * so.nt * 256 : nullptr;
-        uint32_t* sh_next = pass < 3 ? so.shist + (size_t)(pass + 1) * so.ns * 256 : nullptr;
         gvd_launch(sort_pass_kernel, dim3(blocks), dim3(GVD_SORT_THREADS), 0, s, g.counts, so.key[in], so.val[in], so.key[out],
-                   so.val[out], so.ghist + pass * 256, so.thist + (size_t)pass * so.nt * 256, so.shist + (size_t)pass * so.ns * 256,
-                   th_next, sh_next, 8 * pass, pass < 3 ? 8 * (pass + 1) : -1);
+                   so.val[out], so.ghist + pass * 256, so.agg + (size_t)pass * so.nt * 256, so.incl + (size_t)pass * so.ns * 256,
+                   so.ticket + pass, g.counts + 7, 8 * pass);
     }
 }
 
@@ -924,9 +1010,9 @@ cudaError_t gvd_launch_bin_count(const RasterGeomPtrs& g, const RasterSortPtrs& 
 cudaError_t gvd_launch_bin_fill(const RasterGeomPtrs& g, const RasterSortPtrs& so, const RasterHistPtrs& h, const RasterBinPtrs& b,
                                 const RasterImgPtrs& im, dim3 grid, uint32_t capacity, cudaStream_t s) {
     const int T = (int)(grid.x * grid.y);
-    // rows of tiles whose two mask planes fit the budget (all of them up to 20 480 tiles)
-    const uint32_t band_rows = (uint32_t)std::max<size_t>(1, std::min<size_t>(grid.y, GVD_FILL_MASK_BYTES / (2 * sizeof(uint32_t) * grid.x)));
-    const size_t smem = (size_t)2 * band_rows * grid.x * sizeof(uint32_t);
+    // rows of tiles whose three planes fit the budget (all of them up to 16 384 tiles)
+    const uint32_t band_rows = (uint32_t)std::max<size_t>(1, std::min<size_t>(grid.y, GVD_FILL_SMEM_BYTES / (3 * sizeof(uint32_t) * grid.x)));
+    const size_t smem = (size_t)3 * band_rows * grid.x * sizeof(uint32_t);
     cudaError_t e = ensure_smem((const void*)bin_fill_kernel, smem);
     if (e != cudaSuccess) return e;
     if (h.rows > 0)

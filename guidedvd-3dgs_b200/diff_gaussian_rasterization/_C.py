@@ -39,18 +39,27 @@ EXPORT_KEYS = False
 
 # How the instance buffer (4 bytes x R) and the chunk histogram (sized by V) get their sizes.  R and V are produced by
 # the second kernel of the forward, ~40 us into the frame (include/gvd_raster.h), and stored straight into pinned
-# host memory.
-#   EXACT (default): the library waits for those two words only -- the depth sort is already queued behind them, so
-#     the GPU never idles -- and calls back for exactly sized buffers.  Always valid, never raises later; this is the
-#     reference's contract (rasterizer_impl.cu:281-286) without its pipeline bubble.
-#   DEFER (GVD_SPECULATE=defer, opt-in; bench.py names it in `config` when used): from the second frame on a device
-#     the buffers are sized from the largest R / V seen so far (x2 + slack) and NOTHING waits: R is validated at the
-#     start of the backward (or at the next forward for a frame that never got one).  A frame that outgrew its buffers
-#     has already been consumed by then; the backward repairs what it can -- it re-renders the frame exactly, warns,
-#     and returns the gradients of the exact frame -- so an unmodified trainer keeps running.
-_MODE = os.environ.get("GVD_SPECULATE", "exact")
-DEFER = _MODE in ("1", "defer")
-SPECULATE = DEFER  # kept for callers that probe the old name
+# host memory.  GVD_SPECULATE selects:
+#   sync (default): from the second frame on a device the buffers are sized from the largest R / V seen so far (x2 +
+#     slack), every stage is queued in one go, and the call waits for the two counts -- not for the kernels behind them
+#     -- BEFORE it returns: a frame that outgrew the guess is redone on the exact path and nobody ever sees its
+#     clamped outputs.  Always valid, never raises later, and the GPU has ~0.25 ms of queued work when the caller gets
+#     its tensors back.
+#   exact: the library itself waits for the counts (the depth sort is already queued behind them) and calls back for
+#     exactly sized buffers: the reference's contract (rasterizer_impl.cu:281-286) without its pipeline bubble; the
+#     first frame on a device, debug mode and overflowed frames always take this path.
+#   defer (opt-in; bench.py names it in `config` when used): like sync, but a frame that will get a backward is not
+#     validated until that backward starts (or, for a frame that never gets one, at the next forward), so the host
+#     can run a whole step ahead of the GPU.  A frame that outgrew its buffers has already been consumed by then; the
+#     backward repairs what it can -- it re-renders the frame exactly, warns, and returns the gradients of the exact
+#     frame -- so an unmodified trainer keeps running.
+_MODE = os.environ.get("GVD_SPECULATE", "sync")
+if _MODE == "1":
+    _MODE = "defer"
+elif _MODE in ("0",):
+    _MODE = "exact"
+DEFER = _MODE == "defer"
+SPECULATE = _MODE in ("sync", "defer")
 _spec_state = {}
 
 
@@ -304,9 +313,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         stream = _stream()
 
         binning, rc, done = None, 0, False
-        if st is not None:
+        if st is not None and st["open"]:
             _settle_open(st)
-        if st is not None and DEFER and defer and st["max_R"] is not None:
+        if st is not None and SPECULATE and st["max_R"] is not None:
             cap, vcap = _capacity(st["max_R"]), _visible_capacity(st["max_V"], P)
             nbytes = 4 * cap + 1024  # >= gvd_raster_binning_bytes(cap, 0)
             hbytes = sizes[3] + sizes[4] * ((vcap + 63) // 64) + 1024  # >= gvd_raster_hist_bytes(vcap, W, H)
@@ -320,10 +329,22 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             if rc != 0:
                 st["free"].append(slot)
             else:
-                import weakref
                 pending = PendingR(slot, cap, vcap, st)
-                st["open"].append(weakref.ref(pending))
-                done = True
+                if DEFER and defer:
+                    import weakref
+                    st["open"].append(weakref.ref(pending))
+                    done = True
+                else:
+                    try:
+                        counts = pending.resolve()  # waits for the second kernel of the frame, not for the ones behind it
+                        a.num_rendered, a.num_visible = int(counts), counts.visible
+                        done = True
+                    except SpeculationOverflow:
+                        # the guess was too small: redo this frame on the exact path below (its outputs were clamped,
+                        # in bounds, and are simply overwritten)
+                        a.spec_binning_buffer, a.spec_binning_bytes, a.spec_hist_buffer, a.spec_hist_bytes = None, 0, None, 0
+                        binning = None
+                    pending = None
         if rc == 0 and not done:
             alloc = _Alloc(dev)
             a.binning_alloc = a.temp_alloc = alloc.cb

@@ -79,12 +79,13 @@ RASTER_SYMBOLS = (
 
 EXCHANGE_MAX_RANKS = 8
 EXCHANGE_HANDLE_BYTES = 64
+EXCHANGE_FLAG_BYTES = 256
 
 
 class ExchangeArgs(C.Structure):
     """include/gvd_exchange.h::GvdExchangeArgs"""
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("bufs", C.c_void_p * EXCHANGE_MAX_RANKS),
-                ("payload_bytes", C.c_size_t), ("n_floats", C.c_size_t), ("epoch", C.c_uint32)]
+                ("payload_bytes", C.c_size_t), ("n_floats", C.c_size_t), ("epoch", C.c_uint32), ("multicast", C.c_void_p)]
 
 _raster = None
 ABI_VERSION = 8

@@ -30,12 +30,20 @@ class _RawCuda:
 
 
 class GradientExchange:
-    """The gradient sum of the view-parallel step as ONE hand-written kernel over NVLink peer memory
-    (include/gvd_exchange.h): each rank owns an exchange buffer the rasterizer backward writes its gradients into
+    """The gradient sum of the view-parallel step as ONE hand-written kernel over NVLink (include/gvd_exchange.h): each
+    rank owns an exchange buffer the rasterizer backward writes its gradients into
     (diff_gaussian_rasterization.set_gradient_buffer); `allreduce()` sums it in place across the ranks of the world.
-    torch.distributed only carries the 64-byte IPC handles at set-up.  CUDA only (there is no CPU path)."""
+
+    Two ways to obtain buffers every rank can address:
+      * "nvls" (preferred): torch.distributed._symmetric_memory allocates the buffers and binds them to ONE multicast
+        object; the kernel then sums a slice inside the NVSwitch with `multimem.ld_reduce` and writes all replicas with
+        one `multimem.st`.  torch is plumbing here (allocation + handle exchange); the collective is the library's kernel.
+      * "peer": cudaMalloc + CUDA IPC handles carried by one torch.distributed all_gather; direct peer loads/stores.
+    GVD_EXCHANGE=peer forces the second; it is also the fallback when multicast is unavailable.  CUDA only."""
 
     def __init__(self, n_floats: int, device):
+        import os
+
         import gvd_native as _n
 
         self.lib = _n.raster()
@@ -46,6 +54,44 @@ class GradientExchange:
         self.device = torch.device(device)
         self.n_floats = (int(n_floats) + 3) // 4 * 4
         self.payload = self.n_floats * 4
+        self.multicast, self.mode, self._symm, self.why_not_nvls = None, "peer", None, None
+        want = os.environ.get("GVD_EXCHANGE", "nvls")
+        ok = torch.zeros(1, device=self.device)
+        if want != "peer":
+            try:
+                self._init_symmetric()
+                ok.fill_(1.0)
+            except Exception as ex:  # no multicast on this box / this torch: every rank must take the same route
+                self.why_not_nvls = repr(ex)[:200]
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) < 1.0:
+            if want != "peer" and self.why_not_nvls is None:
+                self.why_not_nvls = "a peer rank could not map the multicast object"
+            self._symm, self.multicast = None, None
+            self._init_ipc()
+        self.epoch = 0
+        dist.barrier()  # every mapping exists before anybody launches
+
+    def _init_symmetric(self):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        flag_floats = self._n.EXCHANGE_FLAG_BYTES // 4
+        with torch.cuda.device(self.device):
+            t = symm_mem.empty(self.n_floats + flag_floats, dtype=torch.float32, device=self.device)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if not mc:
+            raise RuntimeError("symmetric memory has no multicast mapping on this system")
+        self._symm = (t, hdl)
+        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.multicast = mc
+        self.buffer = t[:self.n_floats]
+        self.mode = "nvls"
+        torch.cuda.synchronize(self.device)
+
+    def _init_ipc(self):
+        _n = self._n
         ptr, handle = C.c_void_p(), C.create_string_buffer(_n.EXCHANGE_HANDLE_BYTES)
         with torch.cuda.device(self.device):
             self._check(self.lib.gvd_exchange_alloc(self.payload, C.byref(ptr), handle), "gvd_exchange_alloc")
@@ -60,8 +106,7 @@ class GradientExchange:
                     self._check(self.lib.gvd_exchange_open(h, C.byref(pp)), "gvd_exchange_open")
                     self.ptrs.append(pp.value)
         self.buffer = torch.as_tensor(_RawCuda(ptr.value, self.n_floats), device=self.device)
-        self.epoch = 0
-        dist.barrier()  # every mapping exists before anybody launches
+        self.mode = "peer"
 
     def _check(self, rc, what):
         if rc != 0:
@@ -81,6 +126,7 @@ class GradientExchange:
         a.n_floats = self.n_floats if n_floats is None else (int(n_floats) + 3) // 4 * 4
         self.epoch += 1
         a.epoch = self.epoch
+        a.multicast = self.multicast
         with torch.cuda.device(self.device):
             self._check(self.lib.gvd_exchange_allreduce_sum(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                         "gvd_exchange_allreduce_sum")
@@ -91,6 +137,9 @@ class GradientExchange:
             return
         torch.cuda.synchronize(self.device)
         dist.barrier()
+        if self._symm is not None:   # symmetric memory: torch owns the allocation and its mappings
+            self.buffer, self._symm, self.ptrs = None, None, None
+            return
         for q, pq in enumerate(self.ptrs):
             if q != self.rank:
                 self.lib.gvd_exchange_close(pq)

@@ -12,6 +12,9 @@
  *     peers' buffers with direct peer loads (fixed rank order, so all ranks end with bit-identical sums) and writes the
  *     result into every peer's buffer with direct peer stores -> cross-GPU flag barrier.  No staging copies, no
  *     library collective; traffic per rank = (world-1)/world of the buffer in each direction.
+ *   - with a multicast (NVLS) mapping of the buffers the slice is summed INSIDE the NVSwitch (multimem.ld_reduce) and
+ *     written to all replicas by one multicast store (multimem.st): one request per element and direction instead of
+ *     world-1 peer loads and world-1 peer stores.
  *
  * Plain C types only; the handle bytes travel between processes by whatever means the host has (the Python host
  * uses one torch.distributed all_gather at set-up time).  Return value 0 = ok; message via gvd_last_error(). */
@@ -45,6 +48,11 @@ typedef struct {
     size_t payload_bytes;                    /* as given to gvd_exchange_alloc on every rank (same value everywhere) */
     size_t n_floats;                         /* leading floats of the payload to sum (multiple of 4) */
     uint32_t epoch;                          /* 1, 2, 3, ... : +1 on every call, the same value on every rank */
+    /* Optional NVLS path: a multicast mapping of the SAME buffers (one multicast object all `world` allocations are
+     * bound to, e.g. torch.distributed._symmetric_memory's multicast_ptr).  When non-NULL the slice sums are formed inside
+     * the NVSwitch (multimem.ld_reduce) and written to every replica with one multicast store (multimem.st); bufs[]
+     * then only carries the flag words.  NULL: direct peer loads / stores. */
+    void* multicast;
 } GvdExchangeArgs;
 
 /* In place: after the kernel, the first n_floats of EVERY rank's buffer hold the sum over ranks.  Stream-ordered: the

@@ -128,7 +128,10 @@ def compare(P, W, H, seed, sh_degree=3, use_conf=True, precomp=False, verbose=Tr
     sc, cam, cot, bg, D = make_inputs(P, W, H, seed, sh_degree)
     o = run(ours, sc, cam, cot, bg, D, use_conf, precomp)
     r = run(ref, sc, cam, cot, bg, D, use_conf, precomp)
-    r2 = run(ref, sc, cam, cot, bg, D, use_conf, precomp)  # the reference's own atomic-order jitter
+    # the reference's own atomic-order jitter: the largest distance among three of its runs (one pair is a noisy sample,
+    # and the max-norm figure is an extreme-value statistic on top of that)
+    r2 = run(ref, sc, cam, cot, bg, D, use_conf, precomp)
+    r3 = run(ref, sc, cam, cot, bg, D, use_conf, precomp)
     res = {"P": P, "W": W, "H": H, "R_ours": o["num_rendered"], "R_ref": r["num_rendered"],
            "visible": int((r["radii"] > 0).sum())}
     res["radii_mismatch"] = int((o["radii"] != r["radii"]).sum())
@@ -164,7 +167,8 @@ def compare(P, W, H, seed, sh_degree=3, use_conf=True, precomp=False, verbose=Tr
         res[f"grad_{k}_relerr"] = relerr(go, gr)
         res[f"grad_{k}_ref_jitter"] = relerr(r2["grads"][k], gr)
         res[f"grad_{k}_scale_err"] = scale_err(go, gr)
-        res[f"grad_{k}_ref_scale_jitter"] = scale_err(r2["grads"][k], gr)
+        pairs = [scale_err(r2["grads"][k], gr), scale_err(r3["grads"][k], gr), scale_err(r3["grads"][k], r2["grads"][k])]
+        res[f"grad_{k}_ref_scale_jitter"] = (max(p[0] for p in pairs), max(p[1] for p in pairs))
     if verbose:
         for k, v in res.items():
             print(f"  {k}: {v}")

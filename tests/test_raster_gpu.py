@@ -199,19 +199,34 @@ def test_properties_at_full_size(cfg):
         assert _grad_err(c["grads"][k], 2 * a["grads"][k])[1] < 1e-5, k
 
 
-def test_default_path_is_exact_and_learns_counts_early():
-    """The production path (no key export): every buffer is sized exactly inside the forward from the {R, V} the second
-    kernel stored in pinned memory; nothing is deferred.  Results must equal the parity (synchronous) path's."""
+def test_default_path_validates_before_returning(monkeypatch):
+    """The production path (no key export), GVD_SPECULATE=sync: buffers sized from history, everything queued in one go,
+    and the {R, V} the second kernel stored in pinned memory are checked BEFORE the forward returns -- a frame that outgrew
+    the guess is redone exactly and its clamped outputs are never seen.  Results must equal the parity (synchronous)
+    path's in every case; nothing is deferred, nothing warns, nothing raises."""
+    import warnings
+
     import parity_raster as pr
     import synth
 
     ours, _ = _pkgs()
-    assert not ours._C.DEFER
+    assert not ours._C.DEFER and ours._C.SPECULATE
     P, W, H, seed = synth.CONFIGS["small"]
     sc, cam, cot, bg, D = pr.make_inputs(P, W, H, seed, 3)
     exact = pr.run(ours, sc, cam, cot, bg, D)
     ours._C._spec_state.clear()
-    runs = [pr.run(ours, sc, cam, cot, bg, D, export_keys=False) for _ in range(3)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        runs = [pr.run(ours, sc, cam, cot, bg, D, export_keys=False) for _ in range(3)]  # 1st: no history -> exact path
+        monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)        # every later guess is far too small ...
+        runs.append(pr.run(ours, sc, cam, cot, bg, D, export_keys=False))
+        monkeypatch.undo()
+        monkeypatch.setattr(ours._C, "_visible_capacity", lambda max_V, P: 64)   # ... for the chunk histogram too
+        runs.append(pr.run(ours, sc, cam, cot, bg, D, export_keys=False))
+        monkeypatch.undo()
+        monkeypatch.setattr(ours._C, "SPECULATE", False)                     # GVD_SPECULATE=exact
+        runs.append(pr.run(ours, sc, cam, cot, bg, D, export_keys=False))
+        monkeypatch.undo()
     st = ours._C._spec_state[sc["means3D"].device]
     assert st["max_R"] == exact["num_rendered"] and st["max_V"] == int((exact["radii"] > 0).sum()) and len(st["free"]) >= 1
     for r in runs:
@@ -261,10 +276,11 @@ def test_deferred_mode_matches_exact_and_repairs_an_overflow(monkeypatch):
     again = pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
     assert torch.equal(again["color"], exact["color"]) and ours._C._spec_state[dev]["max_R"] == exact["num_rendered"]
     # a deferred frame that never gets a backward is validated at the next render on that device, not at GC
+    # (or, as here where nothing keeps the graph alive, when its autograd node is dropped)
     monkeypatch.setattr(ours._C, "_capacity", lambda max_R: 4096)
-    lost = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
-    torch.cuda.synchronize()
-    monkeypatch.setattr(ours._C, "_capacity", real_capacity)
     with pytest.warns(UserWarning, match="speculative buffers"):
+        lost = pr.run(ours, sc, cam, cot, bg, D, export_keys=False, backward=False)
+        torch.cuda.synchronize()
+        monkeypatch.setattr(ours._C, "_capacity", real_capacity)
         pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
     del lost
