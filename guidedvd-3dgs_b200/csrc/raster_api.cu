@@ -116,10 +116,10 @@ RasterSortPtrs carve_sort(char*& chunk, size_t P) {
     obtain(chunk, so.key[1], P);
     obtain(chunk, so.val[0], P);
     obtain(chunk, so.val[1], P);
-    so.zeroed_words = 4 * 256 + 4 * so.nt * 256 + 4 * so.ns * 256 + 4;
+    so.zeroed_words = GVD_GHIST_COPIES * 4 * 256 + 4 * so.nt * 256 + 4 * so.ns * 256 + 4;
     obtain(chunk, so.zeroed, so.zeroed_words);
     so.ghist = so.zeroed;
-    so.agg = so.ghist + 4 * 256;
+    so.agg = so.ghist + GVD_GHIST_COPIES * 4 * 256;
     so.incl = so.agg + 4 * so.nt * 256;
     so.ticket = so.incl + 4 * so.ns * 256;
     return so;

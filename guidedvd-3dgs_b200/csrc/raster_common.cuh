@@ -49,6 +49,7 @@ struct RasterGeomPtrs {
 #define GVD_COMPACT_BLOCK 1024   // threads per compaction CTA (= 4 preprocess CTAs)
 #define GVD_SORT_TILE 1024       // keys per sort CTA
 #define GVD_SORT_THREADS 256
+#define GVD_GHIST_COPIES 16      // replicas of the global digit histogram (spreads the compaction kernel's atomics)
 #define GVD_SORT_SUPER 32        // tiles per group (bounds the number of predecessor counts a tile has to fetch)
 struct RasterSortPtrs {
     uint32_t* depth_key;       // [P] per Gaussian id: depth bits (undefined when culled)
@@ -56,7 +57,7 @@ struct RasterSortPtrs {
     uint32_t* blk_tiles;       // [nb] instances per preprocess CTA
     uint32_t* key[2];          // [P] ping-pong
     uint32_t* val[2];          // [P] ping-pong; val[0] holds the depth-sorted ids after the 4th pass
-    uint32_t* zeroed;          // ghist[4][256] | agg[4][nt][256] | incl[4][ns][256] | ticket[4], cleared by preprocess
+    uint32_t* zeroed;          // ghist[GVD_GHIST_COPIES][4][256] | agg[4][nt][256] | incl[4][ns][256] | ticket[4], cleared by preprocess
     size_t zeroed_words;
     uint32_t *ghist, *agg, *incl, *ticket;
     size_t nb, nt, ns;

@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
         val0[pos] = (uint32_t)idx;
         vis_id[pos] = (uint32_t)idx;
     }
-    if (hist_s[tid]) atomicAdd(&ghist[tid], hist_s[tid]);
+    // GVD_GHIST_COPIES replicas of the global histogram: ~500 CTAs adding into the same 1024 words serialise in L2
+    // (the kernel took 25 us with one copy); the sort passes add the replicas up
+    if (hist_s[tid]) atomicAdd(&ghist[(blockIdx.x % GVD_GHIST_COPIES) * 1024 + tid], hist_s[tid]);
     if (blockIdx.x == gridDim.x - 1) {
         uint32_t r = 0;
         for (int k = (int)tid; k < nb; k += GVD_COMPACT_BLOCK) r += blk_tiles[k];
@@ -379,7 +381,9 @@ __global__ void __launch_bounds__(GVD_SORT_THREADS) sort_pass_kernel(
         key[r] = valid[r] ? kin[start + off] : 0u;
         val[r] = valid[r] ? vin[start + off] : 0u;
     }
-    const uint32_t g = ghist[tid];
+    uint32_t g = 0;
+#pragma unroll
+    for (int c = 0; c < GVD_GHIST_COPIES; ++c) g += ghist[c * 1024 + tid];
     // phase A: per-warp digit counts
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
@@ -984,7 +988,7 @@ void gvd_launch_depth_sort(int P, const RasterGeomPtrs& g, const RasterSortPtrs&
     for (int pass = 0; pass < 4; ++pass) {
         const int in = pass & 1, out = in ^ 1;
         gvd_launch(sort_pass_kernel, dim3(blocks), dim3(GVD_SORT_THREADS), 0, s, g.counts, so.key[in], so.val[in], so.key[out],
-                   so.val[out], so.ghist + pass * 256, so.agg + (size_t)pass * so.nt * 256, so.incl + (size_t)pass * so.ns * 256,
+                   so.val[out], so.ghist + pass * 256 /* replica c at + c * 1024 */, so.agg + (size_t)pass * so.nt * 256, so.incl + (size_t)pass * so.ns * 256,
                    so.ticket + pass, g.counts + 7, 8 * pass);
     }
 }
