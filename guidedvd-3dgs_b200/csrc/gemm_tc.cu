@@ -42,6 +42,7 @@ struct EpiParams {
     float alpha;
     int act, out_fp32;
     int M, N, K, batch_h;
+    int b_mn;  // B operand is MN-major: smem tile = BK rows of 64 n (128 bytes), tensor-map coordinates (n, k, h, b)
 };
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
@@ -328,13 +329,17 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                     tc::tma_load_4d(sa, &tmap_a, &full[s], kb * BK, m0, bh, bb);
-                    tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kb * BK, n0, bh, bb);
+                    if (p.b_mn) tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], n0, kb * BK, bh, bb);
+                    else tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kb * BK, n0, bh, bb);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(BM, BN_);
+            // MN-major B (bit 16 of the instruction descriptor): same 8-row / 1024-byte swizzle atoms, but the rows are
+            // k and one MMA (K = 16) consumes 16 of them -- the operand advances by 16 * 128 bytes per step
+            const uint32_t idesc = tc::make_idesc_bf16(BM, BN_) | (p.b_mn ? (1u << 16) : 0u);
+            const uint32_t b_step = p.b_mn ? 16u * 128u : 32u;
             int kc = 0, it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
@@ -351,7 +356,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         tc::umma_bf16(tmem_d, tc::make_desc_kmajor_sw128(a_addr + k * 32),
-                                      tc::make_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                                      tc::make_desc_kmajor_sw128(b_addr + k * b_step), idesc, (kb | k) != 0);
                     tc::umma_commit(&empty[s]);
                 }
                 tc::umma_commit(&tmem_full[buf]);
@@ -493,6 +498,21 @@ bool make_tmap(CUtensorMap* map, const void* base, long long K, long long rows, 
     return r == CUDA_SUCCESS;
 }
 
+// MN-major B: 4-D bf16 view (N contiguous, K rows with stride ld, h, b); box = 64 n x BK k
+bool make_tmap_mn(CUtensorMap* map, const void* base, long long N, long long K, long long H, long long Bn, long long ld,
+                  long long sh, long long sb) {
+    auto enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)K, (cuuint64_t)H, (cuuint64_t)Bn};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(H > 1 ? sh : ld) * 2, (cuuint64_t)(Bn > 1 ? sb : ld) * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BK, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" {
@@ -513,12 +533,23 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
     }
     CUtensorMap ta, tb;
     EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,
-                a->M, a->N, a->K, a->batch_h};
+                a->M, a->N, a->K, a->batch_h, a->b_mn_major != 0};
     const bool aligned_out = !a->out_fp32 && (a->N % 8 == 0) && (a->ldc % 8 == 0) &&
                              (a->batch_h == 1 || a->c_stride_h % 8 == 0) && (a->batch_b == 1 || a->c_stride_b % 8 == 0) &&
                              (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) &&
                              (a->residual == nullptr || reinterpret_cast<uintptr_t>(a->residual) % 16 == 0);
     const long long total_tiles128 = (long long)((a->M + BM - 1) / BM) * ((a->N + 127) / 128) * a->batch_h * a->batch_b;
+    if (a->b_mn_major) {
+        if (!aligned_out) { g_nn_err = "gvd_gemm_bf16: b_mn_major needs bf16 output with 16-byte aligned rows"; return 2; }
+        if (!make_tmap(&ta, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
+            !make_tmap_mn(&tb, a->B, a->N, a->K, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b)) {
+            g_nn_err = "gvd_gemm_bf16: cuTensorMapEncodeTiled failed";
+            return 1;
+        }
+        cudaError_t e = launch_persistent<64>(ta, tb, p, a->batch_h * a->batch_b, s);
+        if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 persistent launch: ") + cudaGetErrorString(e); return 1; }
+        return 0;
+    }
     if (aligned_out && total_tiles128 < (1ll << 30)) {
         // tile width: least padding of N, ties to the wider tile (fewer A re-reads); 64 only for narrow outputs
         auto padded = [&](int bn) { return (long long)((a->N + bn - 1) / bn) * bn; };

@@ -244,10 +244,12 @@ _scratch_sizes = {}
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, defer=False):
+                        prefiltered, debug, defer=False, force_defer=False):
     """-> (num_rendered, out_color, out_depth, out_alpha, radii, geomBuffer, binningBuffer, imgBuffer)
 
-    defer=True (used by the autograd Function): num_rendered may come back as a PendingR, see DEFER above."""
+    defer=True (used by the autograd Function): under GVD_SPECULATE=defer num_rendered may come back as a PendingR, see
+    DEFER above.  force_defer=True: always (when a history exists) -- for callers that validate a whole batch of frames
+    themselves before anybody sees them (rasterize_views)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     lib = _n.raster()
@@ -330,7 +332,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 st["free"].append(slot)
             else:
                 pending = PendingR(slot, cap, vcap, st)
-                if DEFER and defer:
+                if force_defer:
+                    done = True
+                elif DEFER and defer:
                     import weakref
                     st["open"].append(weakref.ref(pending))
                     done = True

@@ -114,6 +114,46 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_rotations, grad_cov3Ds_precomp, None, None)
 
 
+def rasterize_views(settings_list, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                    cov3D_precomp=None):
+    """B200 extension: forward-only render of MANY views of one Gaussian set -- the 25-75 trajectory
+    poses train_guidedvd.py renders one `easy_renderer.render` call at a time per diffusion round
+    (train_guidedvd.py:157-165,521-527; utils/easy_renderer.py:59-66).
+
+    settings_list: one GaussianRasterizationSettings per view (same Gaussians, any cameras / image sizes).
+    -> list of (color[3,H,W], radii[P], depth[1,H,W], alpha[1,H,W]), identical to calling GaussianRasterizer per view.
+
+    All views are queued back to back without a host wait in between (instance buffers sized from history); the counts
+    every frame stored in pinned memory are validated once at the end and a frame that outgrew its buffers is rendered
+    again on the exact path BEFORE anything is returned -- so the results are always valid, and the GPU runs the batch as
+    one uninterrupted pipeline instead of idling while the host prepares each next view."""
+    if (shs is None) == (colors_precomp is None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    pair_given = scales is not None or rotations is not None
+    pair_complete = scales is not None and rotations is not None
+    if (cov3D_precomp is None and not pair_complete) or (cov3D_precomp is not None and pair_given):
+        raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+    absent = torch.Tensor([])
+    sh, col, sc, rot, cov = [absent if t is None else t.detach() for t in (shs, colors_precomp, scales, rotations, cov3D_precomp)]
+    means3D, opacities = means3D.detach(), opacities.detach()
+
+    def args_of(rs):
+        return (rs.bg, means3D, col, opacities, sc, rot, rs.scale_modifier, cov, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+                rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+
+    with torch.no_grad():
+        outs = [_C.rasterize_gaussians(*args_of(rs), force_defer=not rs.debug) for rs in settings_list]
+        results = []
+        for rs, out in zip(settings_list, outs):
+            if isinstance(out[0], _C.PendingR):
+                try:
+                    out[0].resolve()
+                except _C.SpeculationOverflow:
+                    out = _C.rasterize_gaussians(*args_of(rs))  # this frame outgrew its buffers: render it again, exactly
+            results.append((out[1], out[4], out[2], out[3]))
+    return results
+
+
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
     image_width: int

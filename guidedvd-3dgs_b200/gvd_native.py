@@ -235,7 +235,7 @@ class GemmArgs(C.Structure):
         ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_stride_h", C.c_longlong), ("b_stride_b", C.c_longlong),
         ("C", C.c_void_p), ("ldc", C.c_longlong), ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
         ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("alpha", C.c_float), ("act", C.c_int),
-        ("out_fp32", C.c_int),
+        ("out_fp32", C.c_int), ("b_mn_major", C.c_int),
     ]
 
 

@@ -48,8 +48,9 @@ def _p(t):
 
 
 def gemm_raw(A, B, Cout, M, N, K, lda, ldb, ldc, batch_h=1, batch_b=1, a_strides=(0, 0), b_strides=(0, 0),
-             c_strides=(0, 0), bias=None, bias2=None, residual=None, alpha=1.0, act="none"):
-    """C[b,h,m,n] = act(alpha * sum_k A[b,h,m,k] B[b,h,n,k] + bias[n]) (+ bias2[n]) + residual; strides in elements."""
+             c_strides=(0, 0), bias=None, bias2=None, residual=None, alpha=1.0, act="none", b_mn_major=False):
+    """C[b,h,m,n] = act(alpha * sum_k A[b,h,m,k] B[b,h,n,k] + bias[n]) (+ bias2[n]) + residual; strides in elements.
+    b_mn_major: B is stored B[b,h,k,n] (n contiguous, ldb between consecutive k) -- no transposed copy needed."""
     lib = _n.nn()
     a = _n.GemmArgs()
     a.M, a.N, a.K, a.batch_h, a.batch_b = int(M), int(N), int(K), int(batch_h), int(batch_b)
@@ -58,6 +59,7 @@ def gemm_raw(A, B, Cout, M, N, K, lda, ldb, ldc, batch_h=1, batch_b=1, a_strides
     a.C, a.ldc, a.c_stride_h, a.c_stride_b = Cout.data_ptr(), int(ldc), int(c_strides[0]), int(c_strides[1])
     a.bias, a.bias2, a.residual = _p(bias), _p(bias2), _p(residual)
     a.alpha, a.act, a.out_fp32 = float(alpha), ACT[act], int(Cout.dtype == torch.float32)
+    a.b_mn_major = int(bool(b_mn_major))
     with torch.cuda.device(A.device):
         _check(lib.gvd_gemm_bf16(C.byref(a), _stream()), lib, "gvd_gemm_bf16")
     return Cout
@@ -505,14 +507,21 @@ def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=
         gemm_raw(ds, kt, dq[b0:], Nq, D, Nkp, Nkp, Nkp, HD, batch_h=H, batch_b=nb, a_strides=(Nq * Nkp, H * Nq * Nkp),
                  b_strides=(D * Nkp, H * D * Nkp), c_strides=(D, Nq * HD), alpha=scale)
         if need_kv:
-            dst, Nqp = _mat_t(ds, Nq, Nk, Nkp)   # [nb, H, Nk, Nqp]
-            pt, _ = _mat_t(p, Nq, Nk, Nkp)
-            qt = _heads_t(q[b0:b0 + nb], nb, Nq, H, Nqp, D)
+            # dK^T = Q^T dS and dV^T = dO^T P, each [D, Nk] per (item, head): dS / P enter as the MN-major B operand exactly
+            # as they lie in memory ([Nq, Nkp], keys contiguous).  Round 2's first hardware profile of the guided step showed
+            # the transposed copies of these two score-sized matrices (dK = dS^T Q, dV = P^T dO as K-major GEMMs) costing
+            # 73 ms of a 654 ms step; what is transposed now are the small [Nq, D] / [D, Nk] operands and results.
+            Nqp = (Nq + 7) // 8 * 8
+            qt = _heads_t(q[b0:b0 + nb], nb, Nq, H, Nqp, D)         # [nb, H, D, Nqp]
             dot = _heads_t(dout[b0:b0 + nb], nb, Nq, H, Nqp, D)
-            gemm_raw(dst, qt, dk[b0:], Nk, D, Nqp, Nqp, Nqp, HD, batch_h=H, batch_b=nb, a_strides=(Nk * Nqp, H * Nk * Nqp),
-                     b_strides=(D * Nqp, H * D * Nqp), c_strides=(D, Nk * HD), alpha=scale)
-            gemm_raw(pt, dot, dv[b0:], Nk, D, Nqp, Nqp, Nqp, HD, batch_h=H, batch_b=nb, a_strides=(Nk * Nqp, H * Nk * Nqp),
-                     b_strides=(D * Nqp, H * D * Nqp), c_strides=(D, Nk * HD))
+            dkt = torch.empty(nb, H, D, Nkp, dtype=q.dtype, device=dev)
+            dvt = torch.empty(nb, H, D, Nkp, dtype=q.dtype, device=dev)
+            gemm_raw(qt, ds, dkt, D, Nk, Nq, Nqp, Nkp, Nkp, batch_h=H, batch_b=nb, a_strides=(D * Nqp, H * D * Nqp),
+                     b_strides=(Nq * Nkp, H * Nq * Nkp), c_strides=(D * Nkp, H * D * Nkp), alpha=scale, b_mn_major=True)
+            gemm_raw(dot, p, dvt, D, Nk, Nq, Nqp, Nkp, Nkp, batch_h=H, batch_b=nb, a_strides=(D * Nqp, H * D * Nqp),
+                     b_strides=(Nq * Nkp, H * Nq * Nkp), c_strides=(D * Nkp, H * D * Nkp), b_mn_major=True)
+            dk[b0:b0 + nb] = dkt[..., :Nk].permute(0, 3, 1, 2).reshape(nb, Nk, HD)
+            dv[b0:b0 + nb] = dvt[..., :Nk].permute(0, 3, 1, 2).reshape(nb, Nk, HD)
     return dq, dk, dv
 
 

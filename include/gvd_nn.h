@@ -48,6 +48,10 @@ typedef struct GvdGemmArgs {
     float alpha;
     int act;                           /* GVD_ACT_* applied before the residual add */
     int out_fp32;
+    int b_mn_major;                    /* 1: B is given as B[k][n] (N contiguous, ldb = elements between consecutive k): the
+                                          product C = A * B without a transposed copy of B (tcgen05 MN-major operand).
+                                          Needs bf16 output with 16-byte aligned rows; tiles are 128 x 64.  Used for
+                                          dK^T = Q^T dS and dV^T = dO^T P in the attention backward. */
 } GvdGemmArgs;
 GVD_NN_API int gvd_gemm_bf16(const GvdGemmArgs* args, gvd_nn_stream_t stream);
 

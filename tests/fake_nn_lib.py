@@ -69,7 +69,10 @@ class FakeNN:
             return self._t(ptr, ext, dtype).as_strided((bb, bh, rows, cols), (sb, sh, ld, 1))
 
         A = view(a.A, M, K, a.lda, a.a_stride_h, a.a_stride_b, self.act).float()
-        B = view(a.B, N, K, a.ldb, a.b_stride_h, a.b_stride_b, self.act).float()
+        if getattr(a, "b_mn_major", 0):  # B[k][n], N contiguous
+            B = view(a.B, K, N, a.ldb, a.b_stride_h, a.b_stride_b, self.act).float().transpose(-1, -2)
+        else:
+            B = view(a.B, N, K, a.ldb, a.b_stride_h, a.b_stride_b, self.act).float()
         cdt = torch.float32 if a.out_fp32 else self.act
         Cv = view(a.C, M, N, a.ldc, a.c_stride_h, a.c_stride_b, cdt)
         acc = A @ B.transpose(-1, -2)

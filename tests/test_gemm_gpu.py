@@ -54,3 +54,25 @@ def test_batched_strided_heads():
                  b_strides=(D, Nk * H * D), c_strides=(Nq * 80, H * Nq * 80), alpha=D ** -0.5)
     ref = torch.einsum("bihd,bjhd->bhij", q.float().view(Bn, Nq, H, D), k.float().view(Bn, Nk, H, D)) * D ** -0.5
     assert (sim[..., :Nk] - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,ldb", [(64, 256, 256, 256), (64, 200, 200, 200), (512, 640, 640, 640), (64, 77, 130, 80), (100, 2560, 1000, 2560)])
+def test_mn_major_b_operand(M, N, K, ldb):
+    """C = A * B with B given as B[k][n] (n contiguous): the tcgen05 MN-major operand used for dK^T = Q^T dS and
+    dV^T = dO^T P in the attention backward (no transposed copy of the score-sized matrices).  Batched over two levels."""
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    nb, H = 2, 3
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(nb, H, M, Kp, device="cuda", dtype=torch.bfloat16)
+    A[..., :K] = torch.randn(nb, H, M, K, device="cuda", generator=g).bfloat16()
+    B = torch.zeros(nb, H, K, ldb, device="cuda", dtype=torch.bfloat16)
+    B[..., :N] = (torch.randn(nb, H, K, N, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    Np = (N + 7) // 8 * 8
+    Cout = torch.full((nb, H, M, Np), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_raw(A, B, Cout, M, N, K, Kp, ldb, Np, batch_h=H, batch_b=nb, a_strides=(M * Kp, H * M * Kp),
+                 b_strides=(K * ldb, H * K * ldb), c_strides=(M * Np, H * M * Np), alpha=0.5, b_mn_major=True)
+    ref = 0.5 * (A[..., :K].float() @ B[..., :N].float())
+    err = (Cout[..., :N].float() - ref).abs().max().item()
+    assert err <= ref.abs().max().item() / 128 + 1e-4, err

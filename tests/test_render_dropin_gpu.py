@@ -199,3 +199,30 @@ def test_frame_that_outgrows_every_earlier_frame_is_still_exact():
         assert _rel(go[keep], gr[keep]) <= max(1e-4, 4 * jitter), (i, _rel(go[keep], gr[keep]), jitter)
         Rs.append(int((pr["radii"] > 0).sum()))
     assert Rs[2] > 0 and Rs[4] > 0
+
+
+def test_trajectory_batch_render_equals_per_pose_easy_renderer(monkeypatch):
+    """batch_render.render_trajectory (activations once, all poses queued as one pipeline, counts
+    validated at the end) returns what a loop over the reference's EasyRenderer.render returns -- also when a pose in the
+    middle of the batch outgrows the speculative buffers (it is re-rendered exactly before anything is returned)."""
+    sys.path.insert(0, os.path.join(ROOT, "guidedvd-3dgs_b200"))
+    import batch_render
+    import diff_gaussian_rasterization as ours_pkg
+
+    ours, ref = gs_refload.load("ours"), gs_refload.load("reference")
+    P, W, H, seed = 40_000, 320, 240, 555
+    m_ref, _ = _model(ref, P, seed)
+    m_ours, _ = _model(ours, P, seed, like=m_ref)
+    poses = [_pose(seed + 20 + i, W, H, fovx_deg=60.0 + 7 * i) for i in range(9)]
+    er = ref.EasyRenderer.__new__(ref.EasyRenderer)
+    er.gaussians, er.pipeline_param = m_ref, _pipe()
+    er.background = torch.tensor([0, 0, 0], dtype=torch.float32, device="cuda")
+    want = [er.render(w2c, K, H, W) for w2c, K in poses]
+    for cap in (None, 4096):   # 4096: every speculative guess far too small -> every pose takes the exact redo
+        if cap is not None:
+            monkeypatch.setattr(ours_pkg._C, "_capacity", lambda max_R: cap)
+        color, alpha, depth = batch_render.render_trajectory(m_ours, _pipe(), er.background, [p[0] for p in poses], [p[1] for p in poses], H, W)
+        torch.cuda.synchronize()
+        assert color.shape == (9, 3, H, W) and alpha.shape == (9, 1, H, W) and depth.shape == (9, 1, H, W)
+        for i, (c, a, d) in enumerate(want):
+            assert torch.equal(color[i], c) and torch.equal(alpha[i], a) and torch.equal(depth[i], d), (cap, i)
