@@ -46,7 +46,7 @@ struct RasterGeomPtrs {
 // digit counts as flagged words and sums those of its predecessors (groups of GVD_SORT_SUPER tiles, one running total
 // per group), so there is no histogram kernel per pass and no per-key atomic.
 #define GVD_PRE_BLOCK 256        // threads per preprocess CTA
-#define GVD_COMPACT_BLOCK 1024   // threads per compaction CTA (= 4 preprocess CTAs)
+#define GVD_COMPACT_BLOCK 256    // threads per compaction CTA (= one preprocess CTA)
 #define GVD_SORT_TILE 1024       // keys per sort CTA
 #define GVD_SORT_THREADS 256
 #define GVD_GHIST_COPIES 16      // replicas of the global digit histogram (spreads the compaction kernel's atomics)

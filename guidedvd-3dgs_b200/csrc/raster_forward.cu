@@ -241,52 +241,56 @@ __global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
 // ------------------------------------------------------------------------------------------
 // ---- compaction of the visible Gaussians + depth sort ---------------------------------------------
 
-__device__ __forceinline__ uint32_t block_sum_1024(uint32_t v, uint32_t* warp_buf) {  // warp_buf[32]; result valid in warp 0
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Block sum for up to 1024 threads; warp_buf[32]. The result is valid in every thread of warp 0.
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* warp_buf) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     v = __reduce_add_sync(0xffffffffu, v);
     if (lane == 0) warp_buf[warp] = v;
     __syncthreads();
     uint32_t r = 0;
-    if (warp == 0) r = __reduce_add_sync(0xffffffffu, warp_buf[lane]);
+    if (warp == 0) r = __reduce_add_sync(0xffffffffu, lane < nw ? warp_buf[lane] : 0u);
     return r;
 }
 
-// CTA b owns the ids [b * 1024, (b + 1) * 1024): its visible ones go, in id order, to the compacted positions
-// base_b + rank (base_b = visible Gaussians of all earlier preprocess CTAs). Writes the (depth bits, id) pairs the sort
-// starts from, vis_id (kept for the backward) and the four 8-bit digit histograms of all keys (warp-aggregated with
-// MATCH.ANY first: the top byte of a depth takes a handful of values, plain shared-memory atomics on it serialise);
-// the last CTA publishes V and R (device words and, if given, pinned host words).
+// CTA b owns the ids of preprocess CTA b: its visible ones go, in id order, to the compacted positions base_b + rank
+// (base_b = visible Gaussians of all earlier preprocess CTAs, summed from the per-CTA counts). Writes the (depth bits,
+// id) pairs the sort starts from, vis_id (kept for the backward) and the four 8-bit digit histograms of all keys
+// (warp-aggregated with MATCH.ANY first: the top byte of a depth takes a handful of values, plain shared-memory atomics
+// on it serialise); the last CTA publishes V and R (device words and, if given, pinned host words).
+// 256-thread CTAs: a first version with 1024-thread CTAs (two resident per SM, six block barriers each) took 25 us at
+// C2 -- a chain of barrier waits, not work (ncu: 13 % issue slots used).
 __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
     int P, int nb, const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ depth_key,
     const uint32_t* __restrict__ blk_vis, const uint32_t* __restrict__ blk_tiles, uint32_t* __restrict__ key0,
     uint32_t* __restrict__ val0, uint32_t* __restrict__ vis_id, uint32_t* __restrict__ counts, uint32_t* ghist, int* r_host) {
     pdl_wait();
     pdl_trigger();
+    static_assert(GVD_COMPACT_BLOCK == GVD_PRE_BLOCK && GVD_COMPACT_BLOCK == 256, "one compaction CTA per preprocess CTA");
     __shared__ uint32_t hist_s[4 * 256];
     __shared__ uint32_t warp_buf[32];
-    __shared__ uint32_t warp_cnt[32];
+    __shared__ uint32_t warp_cnt[GVD_COMPACT_BLOCK / 32];
     __shared__ uint32_t s_base, s_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    hist_s[tid] = 0u;
-    const int first_blk = (int)blockIdx.x * (GVD_COMPACT_BLOCK / GVD_PRE_BLOCK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hist_s[k * 256 + tid] = 0u;
     uint32_t s = 0;
-    for (int k = (int)tid; k < first_blk && k < nb; k += GVD_COMPACT_BLOCK) s += blk_vis[k];
+    for (int k = (int)tid; k < (int)blockIdx.x; k += GVD_COMPACT_BLOCK) s += blk_vis[k];
     const int idx = (int)(blockIdx.x * GVD_COMPACT_BLOCK + tid);
     const bool vis = idx < P && tiles_touched[idx] > 0;
     const uint32_t key = vis ? depth_key[idx] : 0u;
     const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
     if (lane == 0) warp_cnt[warp] = __popc(ballot);
-    const uint32_t base_w0 = block_sum_1024(s, warp_buf);  // contains a __syncthreads: warp_cnt and hist_s = 0 are visible below
+    const uint32_t base_w0 = block_sum(s, warp_buf);  // contains a __syncthreads: warp_cnt and hist_s = 0 are visible below
     if (warp == 0) {
-        const uint32_t c = warp_cnt[lane];
+        const uint32_t c = lane < GVD_COMPACT_BLOCK / 32 ? warp_cnt[lane] : 0u;
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (uint32_t)o) incl += u;
         }
-        warp_cnt[lane] = incl - c;
+        if (lane < GVD_COMPACT_BLOCK / 32) warp_cnt[lane] = incl - c;
         if (lane == 31) s_total = incl;
         if (lane == 0) s_base = base_w0;
     }
@@ -304,14 +308,17 @@ __global__ void __launch_bounds__(GVD_COMPACT_BLOCK) compact_kernel(
         val0[pos] = (uint32_t)idx;
         vis_id[pos] = (uint32_t)idx;
     }
-    // GVD_GHIST_COPIES replicas of the global histogram: ~500 CTAs adding into the same 1024 words serialise in L2
-    // (the kernel took 25 us with one copy); the sort passes add the replicas up
-    if (hist_s[tid]) atomicAdd(&ghist[(blockIdx.x % GVD_GHIST_COPIES) * 1024 + tid], hist_s[tid]);
+    // GVD_GHIST_COPIES replicas of the global histogram spread the CTAs' atomics; the sort passes add the replicas up
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = hist_s[k * 256 + tid];
+        if (c) atomicAdd(&ghist[(blockIdx.x % GVD_GHIST_COPIES) * 1024 + k * 256 + tid], c);
+    }
     if (blockIdx.x == gridDim.x - 1) {
         uint32_t r = 0;
         for (int k = (int)tid; k < nb; k += GVD_COMPACT_BLOCK) r += blk_tiles[k];
         __syncthreads();  // warp_buf is reused
-        const uint32_t R = block_sum_1024(r, warp_buf);
+        const uint32_t R = block_sum(r, warp_buf);
         if (tid == 0) {
             const uint32_t V = base + s_total;
             counts[0] = V;
@@ -536,18 +543,21 @@ __global__ void __launch_bounds__(GVD_BIN_CHUNK) bin_count_kernel(const uint32_t
 }
 
 // Pass 2: per tile, exclusive prefix over the chunks, in place, and the tile's total.
-// CTA = 32 tiles x 32 chunk segments: every thread sums its segment, the segment sums are scanned through
-// shared memory, then every thread rewrites its segment as running prefixes.
-__global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int rows_cap, const uint32_t* __restrict__ counts,
-                                                          uint32_t* hist, uint32_t* __restrict__ tile_total) {
+// CTA = GVD_PFX_TILES tiles x GVD_PFX_SEGS chunk segments: every thread sums its segment, the segment sums are scanned
+// through shared memory, then every thread rewrites its segment as running prefixes. 8 consecutive tiles = one 32-byte
+// sector per hist row, and 150 CTAs at C2 (round 1's 32-tile CTAs left 110 of the 148 SMs idle: 17 us).
+#define GVD_PFX_TILES 8
+#define GVD_PFX_SEGS 128
+__global__ void __launch_bounds__(GVD_PFX_TILES * GVD_PFX_SEGS) bin_prefix_kernel(int T, int rows_cap, const uint32_t* __restrict__ counts,
+                                                                                uint32_t* hist, uint32_t* __restrict__ tile_total) {
     pdl_wait();
     pdl_trigger();
-    __shared__ uint32_t seg_sum[32][33];
-    const int tx = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    __shared__ uint32_t seg_sum[GVD_PFX_SEGS][GVD_PFX_TILES + 1];
+    const int tx = threadIdx.x % GVD_PFX_TILES, seg = threadIdx.x / GVD_PFX_TILES;
     const int nv = min(rows_cap, (int)((counts[0] + GVD_BIN_CHUNK - 1) / GVD_BIN_CHUNK));
-    const int per = (nv + 31) / 32;
-    const int c0 = seg * per, c1 = min(nv, c0 + per);
-    const int t = blockIdx.x * 32 + tx;
+    const int per = (nv + GVD_PFX_SEGS - 1) / GVD_PFX_SEGS;
+    const int c0 = min(nv, seg * per), c1 = min(nv, c0 + per);
+    const int t = blockIdx.x * GVD_PFX_TILES + tx;
     uint32_t sum = 0;
     if (t < T)
         for (int c = c0; c < c1; ++c) sum += hist[(size_t)c * T + t];
@@ -567,10 +577,10 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(int T, int rows_cap, c
                     run += v[k];
                 }
         }
-        if (seg == 31) {
+        if (seg == GVD_PFX_SEGS - 1) {
             uint32_t tot = 0;
 #pragma unroll 8
-            for (int k = 0; k < 32; ++k) tot += seg_sum[k][tx];
+            for (int k = 0; k < GVD_PFX_SEGS; ++k) tot += seg_sum[k][tx];
             tile_total[t] = tot;
         }
     }
@@ -1006,7 +1016,8 @@ cudaError_t gvd_launch_bin_count(const RasterGeomPtrs& g, const RasterSortPtrs& 
     if (e != cudaSuccess) return e;
     if (h.rows > 0)
         gvd_launch(bin_count_kernel, dim3((unsigned)h.rows), dim3(GVD_BIN_CHUNK), smem, s, g.counts, grid.x, grid.y, g.splat, so.val[0], h.hist);
-    gvd_launch(bin_prefix_kernel, dim3((T + 31) / 32), dim3(1024), 0, s, T, (int)h.rows, g.counts, h.hist, h.tile_total);
+    gvd_launch(bin_prefix_kernel, dim3((T + GVD_PFX_TILES - 1) / GVD_PFX_TILES), dim3(GVD_PFX_TILES * GVD_PFX_SEGS), 0, s, T, (int)h.rows,
+               g.counts, h.hist, h.tile_total);
     gvd_launch(bin_ranges_kernel, dim3(1), dim3(1024), 0, s, T, h.tile_total, im.ranges);
     return cudaGetLastError();
 }

@@ -516,9 +516,10 @@ def attention_bwd(q, k, v, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=
             dot = _heads_t(dout[b0:b0 + nb], nb, Nq, H, Nqp, D)
             dkt = torch.empty(nb, H, D, Nkp, dtype=q.dtype, device=dev)
             dvt = torch.empty(nb, H, D, Nkp, dtype=q.dtype, device=dev)
-            gemm_raw(qt, ds, dkt, D, Nk, Nq, Nqp, Nkp, Nkp, batch_h=H, batch_b=nb, a_strides=(D * Nqp, H * D * Nqp),
+            # N = Nkp: the padding columns of dS and P are zeros, so are the result's (the epilogue wants N % 8 == 0)
+            gemm_raw(qt, ds, dkt, D, Nkp, Nq, Nqp, Nkp, Nkp, batch_h=H, batch_b=nb, a_strides=(D * Nqp, H * D * Nqp),
                      b_strides=(Nq * Nkp, H * Nq * Nkp), c_strides=(D * Nkp, H * D * Nkp), alpha=scale, b_mn_major=True)
-            gemm_raw(dot, p, dvt, D, Nk, Nq, Nqp, Nkp, Nkp, batch_h=H, batch_b=nb, a_strides=(D * Nqp, H * D * Nqp),
+            gemm_raw(dot, p, dvt, D, Nkp, Nq, Nqp, Nkp, Nkp, batch_h=H, batch_b=nb, a_strides=(D * Nqp, H * D * Nqp),
                      b_strides=(Nq * Nkp, H * Nq * Nkp), c_strides=(D * Nkp, H * D * Nkp), b_mn_major=True)
             dk[b0:b0 + nb] = dkt[..., :Nk].permute(0, 3, 1, 2).reshape(nb, Nk, HD)
             dv[b0:b0 + nb] = dvt[..., :Nk].permute(0, 3, 1, 2).reshape(nb, Nk, HD)

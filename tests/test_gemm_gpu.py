@@ -71,8 +71,10 @@ def test_mn_major_b_operand(M, N, K, ldb):
     B[..., :N] = (torch.randn(nb, H, K, N, device="cuda", generator=g) / K ** 0.5).bfloat16()
     Np = (N + 7) // 8 * 8
     Cout = torch.full((nb, H, M, Np), 7.0, device="cuda", dtype=torch.bfloat16)
-    ops.gemm_raw(A, B, Cout, M, N, K, Kp, ldb, Np, batch_h=H, batch_b=nb, a_strides=(M * Kp, H * M * Kp),
+    # the library wants N % 8 == 0 on this path: callers pass the padded width (B's padding columns are zeros)
+    ops.gemm_raw(A, B, Cout, M, Np, K, Kp, ldb, Np, batch_h=H, batch_b=nb, a_strides=(M * Kp, H * M * Kp),
                  b_strides=(K * ldb, H * K * ldb), c_strides=(M * Np, H * M * Np), alpha=0.5, b_mn_major=True)
+    assert float(Cout[..., N:].float().abs().max()) == 0.0 if Np > N else True
     ref = 0.5 * (A[..., :K].float() @ B[..., :N].float())
     err = (Cout[..., :N].float() - ref).abs().max().item()
     assert err <= ref.abs().max().item() / 128 + 1e-4, err
