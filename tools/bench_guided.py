@@ -5,7 +5,7 @@ random weights; ours (vc_b200.guided, everything native) against the reference D
 modules under torch.autocast(bfloat16) on the same GPU.  Prints one JSON line per arm.
 
 usage: python tools/bench_guided.py [--arm ours|reference|both] [--frames 25] [--latent 40 64] [--steps 2] [--decode-frames 5]
-NOT yet run on hardware (written after the round's GPU budget was spent)."""
+First hardware numbers: profiles/r02_first_hw_run.txt (bench.py carries the measured blocks now)."""
 import argparse
 import json
 import os

@@ -2,7 +2,7 @@
 GEGLU of the ds1 / ds2 / ds4 feed-forwards, 3x3 im2col at ds1 (320 and 640 channels), temporal im2col at ds1, temporal
 attention at ds1 / ds2.
 Prints one JSON line: per kernel, microseconds and achieved GB/s (algorithmic bytes) for both variants.
-usage: python tools/bench_nn_fast.py     NOT yet run on hardware."""
+usage: python tools/bench_nn_fast.py     Results: profiles/r02_first_hw_run.txt."""
 import json
 import os
 import sys

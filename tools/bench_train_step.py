@@ -7,7 +7,7 @@ same GPU: activations -> rasterizer forward -> L1 + SSIM loss -> backward -> den
 Prints one JSON line per arm: iterations/s and ms per iteration (CUDA events, 5 warm-ups).
 
 usage: python tools/bench_train_step.py [--arm ours|reference|both] [--iters 100] [--workload C2]
-NOT yet run on hardware (written after the round's GPU budget was spent)."""
+First hardware numbers: profiles/r02_first_hw_run.txt (bench.py carries the measured blocks now)."""
 import argparse
 import json
 import math

@@ -4,7 +4,7 @@ forward + backward, decoder passes dealt out by frame):
         tools/run_guided_parallel.py [--t 25 --h 40 --w 64] [--mc 320] [--vae-ch 128] [--steps 2]
 Every rank builds the same seeded U-Net and VAE decoder, runs (a) the single-GPU guided step and (b) the planned one with
 the same noise, compares x_prev, then times (b) (CUDA events, max over ranks).  Prints one JSON line on rank 0.
-NOT yet run on hardware (written after the round's GPU budget was spent)."""
+First hardware numbers: profiles/r02_first_hw_run.txt (bench.py carries the measured blocks now)."""
 import argparse
 import json
 import os
