@@ -43,6 +43,9 @@ struct EpiParams {
     int act, out_fp32;
     int M, N, K, batch_h;
     int b_mn;  // B operand is MN-major: smem tile = BK rows of 64 n (128 bytes), tensor-map coordinates (n, k, h, b)
+    // implicit-GEMM convolution (gvd_conv_bf16): 0 = plain GEMM; 1 = 3x3 over (x, y) of a (c, x, y, frame) map;
+    // 2 = 3 taps over the frame axis of a (c, pixel, frame, batch) map.  K block kb = (tap, 64-channel block).
+    int conv_kind, conv_w, conv_cin;
 };
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
@@ -322,6 +325,33 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 const int z = tile / tiles_mn, r = tile - z * tiles_mn;
                 const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_;
                 const int bh = z % p.batch_h, bb = z / p.batch_h;
+                if (p.conv_kind) {
+                    // implicit-GEMM convolution: the A tile of tap (dy, dx) is the activation tile shifted by (dy, dx);
+                    // negative / past-the-end coordinates are zero-filled by TMA, which is the zero padding.
+                    // Coordinates advance incrementally: no division inside the k loop.
+                    // kind 2: rows are (frame, pixel) flattened, a tap shifts them by conv_w = S rows; bh is the batch item
+                    int ax = m0 - p.conv_w, ay = bh;
+                    if (p.conv_kind == 1) {
+                        ay = m0 / p.conv_w;
+                        ax = m0 - ay * p.conv_w;
+                    }
+                    const int taps = p.conv_kind == 1 ? 9 : 3;
+                    int dx = -1, dy = -1, kw = 0;  // kw: k coordinate in the weight matrix
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const int cx = p.conv_kind == 1 ? ax + dx : ax + tap * p.conv_w;
+                        const int cy = p.conv_kind == 1 ? ay + dy : ay;
+                        for (int cc = 0; cc < p.conv_cin; cc += BK, kw += BK, ++kc) {
+                            const int s = kc % ST;
+                            tc::mbar_wait(&empty[s], (uint32_t)(((kc / ST) & 1) ^ 1));
+                            tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                            tc::tma_load_4d(sa, &tmap_a, &full[s], cc, cx, cy, bb);
+                            tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kw, n0, 0, 0);
+                        }
+                        if (++dx == 2) { dx = -1; ++dy; }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++kc) {
                     const int s = kc % ST;
                     const uint32_t ph = (uint32_t)((kc / ST) & 1);
@@ -533,7 +563,7 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
     }
     CUtensorMap ta, tb;
     EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,
-                a->M, a->N, a->K, a->batch_h, a->b_mn_major != 0};
+                a->M, a->N, a->K, a->batch_h, a->b_mn_major != 0, 0, 0, 0};
     const bool aligned_out = !a->out_fp32 && (a->N % 8 == 0) && (a->ldc % 8 == 0) &&
                              (a->batch_h == 1 || a->c_stride_h % 8 == 0) && (a->batch_b == 1 || a->c_stride_b % 8 == 0) &&
                              (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) &&
@@ -583,6 +613,87 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
     gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 launch: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+// ---- implicit-GEMM convolution -------------------------------------------------------------------------------
+int gvd_conv_bf16_supported(int kind, int H, int W, int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0 || (Cin % 64) != 0 || (Cout % 8) != 0) return 0;
+    if (kind == 2) return 1;
+    if (kind != 1 || H <= 0 || W <= 0) return 0;
+    if (!((W % 128 == 0) || (W <= 128 && 128 % W == 0))) return 0;
+    // output tiles are 128 pixels of ONE frame: small frames would leave most of the last tile empty (9 x 16 pixels fill
+    // 56 % of two tiles) -- those stay on the im2col route, whose rows run across frames
+    const long long px = (long long)H * W, tiles = (px + 127) / 128;
+    return tiles * 128 * 8 <= px * 9;
+}
+
+int gvd_conv_bf16(const GvdConvArgs* a, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->x || !a->weight || !a->y) { g_nn_err = "gvd_conv_bf16: null pointer"; return 2; }
+    if (!gvd_conv_bf16_supported(a->kind, a->H, a->W, a->Cin, a->Cout)) {
+        g_nn_err = "gvd_conv_bf16: geometry not served by the implicit-GEMM route (see gvd_conv_bf16_supported)";
+        return 2;
+    }
+    if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->weight) & 15) ||
+        (reinterpret_cast<uintptr_t>(a->y) & 15) || (a->residual && (reinterpret_cast<uintptr_t>(a->residual) & 15))) {
+        g_nn_err = "gvd_conv_bf16: tensors must be 16-byte aligned";
+        return 2;
+    }
+    auto enc = get_encode();
+    if (!enc) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled unavailable"; return 1; }
+    const int taps = a->kind == 1 ? 9 : 3;
+    const int kpt = a->Cin / BK;
+    if (a->kind == 2 && a->S >= (1ll << 30)) { g_nn_err = "gvd_conv_bf16: S too large"; return 2; }
+    const long long C = a->Cin;
+    long long M;
+    int batch_h, batch_b;
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4] = {(cuuint32_t)BK, 0, 0, 1}, estr[4] = {1, 1, 1, 1};
+    if (a->kind == 1) {
+        if (a->F <= 0) return 0;
+        M = (long long)a->H * a->W;
+        batch_h = 1;
+        batch_b = a->F;
+        dims[0] = (cuuint64_t)C; dims[1] = (cuuint64_t)a->W; dims[2] = (cuuint64_t)a->H; dims[3] = (cuuint64_t)a->F;
+        strides[0] = (cuuint64_t)C * 2; strides[1] = (cuuint64_t)a->W * C * 2; strides[2] = (cuuint64_t)M * C * 2;
+        box[1] = (cuuint32_t)(a->W >= 128 ? 128 : a->W);
+        box[2] = (cuuint32_t)(128 / box[1]);
+    } else {
+        if (a->B <= 0 || a->T <= 0 || a->S <= 0) return 0;
+        // rows = (frame, pixel) flattened per batch item: a temporal tap is a shift by S rows, and the rows before the
+        // first / after the last frame are out of bounds of the map (zero-filled) -- tiles run across frames, no padding
+        M = (long long)a->T * a->S;
+        batch_h = a->B;
+        batch_b = 1;
+        dims[0] = (cuuint64_t)C; dims[1] = (cuuint64_t)M; dims[2] = (cuuint64_t)a->B; dims[3] = 1;
+        strides[0] = (cuuint64_t)C * 2; strides[1] = (cuuint64_t)M * C * 2; strides[2] = (cuuint64_t)M * C * 2;
+        box[1] = 128;
+        box[2] = 1;
+    }
+    if (M >= (1ll << 31)) { g_nn_err = "gvd_conv_bf16: more than 2^31 pixels per frame"; return 2; }
+    CUtensorMap ta, tb;
+    if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->x), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the activation map";
+        return 1;
+    }
+    const int N = a->Cout;
+    const long long Kw = (long long)taps * C;
+    auto padded = [&](int bn) { return (long long)((N + bn - 1) / bn) * bn; };
+    int bn = 128;
+    if (N <= 64) bn = 64;
+    else if (padded(256) <= padded(128)) bn = 256;
+    if (!make_tmap(&tb, a->weight, Kw, N, 1, 1, Kw, 0, 0, bn)) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the weight map"; return 1; }
+    const long long ldc = N;
+    EpiParams p{a->y, ldc, (long long)M * ldc, (long long)batch_h * M * ldc, a->bias, a->bias2, a->residual, 1.0f, a->act, 0,
+                (int)M, N, taps * kpt * BK, batch_h, 0, a->kind, a->kind == 1 ? a->W : (int)a->S, a->Cin};
+    const int batch = batch_h * batch_b;
+    cudaError_t e = bn == 256 ? launch_persistent<256>(ta, tb, p, batch, s)
+                  : bn == 128 ? launch_persistent<128>(ta, tb, p, batch, s)
+                              : launch_persistent<64>(ta, tb, p, batch, s);
+    if (e != cudaSuccess) { g_nn_err = std::string("gvd_conv_bf16 launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
 

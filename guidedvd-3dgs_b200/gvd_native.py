@@ -239,6 +239,15 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ConvArgs(C.Structure):
+    """include/gvd_nn.h::GvdConvArgs"""
+    _fields_ = [
+        ("kind", C.c_int), ("F", C.c_int), ("H", C.c_int), ("W", C.c_int), ("B", C.c_int), ("T", C.c_int), ("S", C.c_longlong),
+        ("Cin", C.c_int), ("Cout", C.c_int), ("x", C.c_void_p), ("weight", C.c_void_p), ("y", C.c_void_p),
+        ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("act", C.c_int),
+    ]
+
+
 class DdimArgs(C.Structure):
     _fields_ = [
         ("n", C.c_longlong), ("x", C.c_void_p), ("e_cond", C.c_void_p), ("e_uncond", C.c_void_p), ("noise", C.c_void_p),
@@ -267,7 +276,7 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
               # input-gradient operators of the guided sampler (csrc/nn_backward.cu)
               "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_groupnorm_cl_bwd_sums", "gvd_groupnorm_cl_bwd_apply", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
               "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp",
-              "gvd_im2col3x3_down_cl", "gvd_nn_set_fast")
+              "gvd_im2col3x3_down_cl", "gvd_nn_set_fast", "gvd_conv_bf16", "gvd_conv_bf16_supported")
 _nn = None
 
 
@@ -278,6 +287,8 @@ def _nn_signatures():
         "gvd_nn_last_error": (C.c_char_p, []),
         "gvd_nn_set_fast": (I, [i32]),
         "gvd_gemm_bf16": (I, [C.POINTER(GemmArgs), vp]),
+        "gvd_conv_bf16": (I, [C.POINTER(ConvArgs), vp]),
+        "gvd_conv_bf16_supported": (I, [i32, i32, i32, i32, i32]),
         "gvd_groupnorm_tmp_floats": (S, [i32, ll, i32]),
         "gvd_groupnorm_cl": (I, [vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, sz, vp]),
         "gvd_groupnorm_cl_stats": (I, [vp, vp, i32, ll, i32, i32, vp, sz, vp]),

@@ -160,14 +160,49 @@ def softmax_rows(scores, cols, ldy):
     return out
 
 
+IMPLICIT_CONV = os.environ.get("GVD_IMPLICIT_CONV", "1") != "0"  # A/B switch: 0 = every convolution through im2col
+
+
+def _conv_implicit(kind, x, weight, geom, bias=None, bias2=None, residual=None, act="none"):
+    """gvd_conv_bf16: implicit-GEMM convolution (no im2col buffer).  geom = (F, H, W) for kind 1, (B, T, S) for kind 2."""
+    lib = _n.nn()
+    a = _n.ConvArgs()
+    a.kind = kind
+    if kind == 1:
+        a.F, a.H, a.W = (int(v) for v in geom)
+        rows = a.F * a.H * a.W
+    else:
+        a.B, a.T, a.S = (int(v) for v in geom)
+        rows = a.B * a.T * a.S
+    a.Cin, a.Cout = int(x.shape[-1]), int(weight.shape[0])
+    x = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty(rows, a.Cout, dtype=BF16, device=x.device)
+    if residual is not None and not residual.is_contiguous():
+        residual = residual.contiguous()
+    a.x, a.weight, a.y = x.data_ptr(), weight.data_ptr(), y.data_ptr()
+    a.bias, a.bias2, a.residual, a.act = _p(bias), _p(bias2), _p(residual), ACT[act]
+    with torch.cuda.device(x.device):
+        _check(lib.gvd_conv_bf16(C.byref(a), _stream()), lib, "gvd_conv_bf16")
+    return y
+
+
+def _implicit_ok(kind, H, W, Cin, Cout, x):
+    return IMPLICIT_CONV and x.dtype == BF16 and bool(_n.nn().gvd_conv_bf16_supported(int(kind), int(H), int(W), int(Cin), int(Cout)))
+
+
 def conv3x3(x, F, H, W, weight, bias=None, stride=1, upsample=False, bias2=None, residual=None, act="none"):
-    """3x3 / pad 1 convolution of channels-last x[F, H*W, Cin] with weight [Cout, 9*Cin] (K order ky, kx, cin)."""
+    """3x3 / pad 1 convolution of channels-last x[F, H*W, Cin] with weight [Cout, 9*Cin] (K order ky, kx, cin).
+    Stride 1 without upsampling runs as an implicit GEMM (TMA fetches the shifted activation tiles); the rest builds
+    the im2col matrix first."""
     Cin = x.shape[-1]
     Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
     Ho, Wo = (Hin + 2 - 3) // stride + 1, (Win + 2 - 3) // stride + 1
     if _wants_grad(x, residual):
         return _grad().Conv3x3.apply(x, F, H, W, weight, bias, stride, bool(upsample), bias2, residual, act), Ho, Wo
     lib = _n.nn()
+    if stride == 1 and not upsample and _implicit_ok(1, H, W, Cin, weight.shape[0], x):
+        y = _conv_implicit(1, x, weight, (F, H, W), bias, bias2, residual, act)
+        return y.view(F, Ho * Wo, -1), Ho, Wo
     col = torch.empty(F * Ho * Wo, 9 * Cin, dtype=BF16, device=x.device)
     _check(lib.gvd_im2col3x3_cl(x.data_ptr(), col.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),
                                 _stream()), lib, "gvd_im2col3x3_cl")
@@ -195,6 +230,8 @@ def conv_t3(x, B, T, S, weight, bias=None, residual=None):
         return _grad().ConvT3.apply(x, B, T, S, weight, bias, residual)
     lib = _n.nn()
     Cin = x.shape[-1]
+    if _implicit_ok(2, 0, 0, Cin, weight.shape[0], x):
+        return _conv_implicit(2, x, weight, (B, T, S), bias, None, residual).view(B * T, S, weight.shape[0])
     col = torch.empty(B * T * S, 3 * Cin, dtype=BF16, device=x.device)
     _check(lib.gvd_im2col_t3_cl(x.data_ptr(), col.data_ptr(), int(B), int(T), int(S), int(Cin), _stream()), lib,
            "gvd_im2col_t3_cl")
@@ -411,9 +448,30 @@ def softmax_bwd_rows(p, dp, cols):
     return dp
 
 
+def _dgrad_weight(weight, taps):
+    """weight [Cout, taps*Cin] (tap-major K) -> [Cin, taps*Cout] with the taps reversed: the weight of the convolution
+    that maps dY to dX (dX[p] = sum_tap dY[p - off(tap)] W[tap] = sum_tap' dY[p + off(tap')] W[taps-1-tap']).  Cached on the
+    weight tensor object like `_transposed`."""
+    cached = getattr(weight, "_gvd_wd", None)
+    if cached is not None and cached[0] == weight._version and cached[1].device == weight.device:
+        return cached[1]
+    Cout, K = weight.shape
+    Cin = K // taps
+    wd = weight.view(Cout, taps, Cin).flip(1).permute(2, 1, 0).contiguous().view(Cin, taps * Cout)
+    try:
+        weight._gvd_wd = (weight._version, wd)
+    except AttributeError:
+        pass
+    return wd
+
+
 def conv3x3_dx(dy, F, H, W, Cin, weight, stride=1, upsample=False):
-    """dX of `conv3x3`: dcol = dY @ W (tensor-core GEMM), then the col2im gather.  dy [F, Ho*Wo, Cout] -> [F, H*W, Cin]."""
+    """dX of `conv3x3`.  dy [F, Ho*Wo, Cout] -> [F, H*W, Cin].  Stride 1 without upsampling: the same implicit-GEMM
+    convolution over dY with the tap-reversed, transposed weight; otherwise dcol = dY @ W and the col2im gather."""
     lib = _n.nn()
+    Cout = dy.shape[-1]
+    if stride == 1 and not upsample and _implicit_ok(1, H, W, Cout, Cin, dy):
+        return _conv_implicit(1, dy.reshape(F, H * W, Cout), _dgrad_weight(weight, 9), (F, H, W)).view(F, H * W, Cin)
     dcol = linear_dx(dy.reshape(-1, dy.shape[-1]), weight)  # [F*Ho*Wo, 9*Cin]
     dx = torch.empty(F, H * W, Cin, dtype=dy.dtype, device=dy.device)
     _check(lib.gvd_col2im3x3_cl(dcol.data_ptr(), dx.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),
@@ -423,6 +481,9 @@ def conv3x3_dx(dy, F, H, W, Cin, weight, stride=1, upsample=False):
 
 def conv_t3_dx(dy, B, T, S, Cin, weight):
     lib = _n.nn()
+    Cout = dy.shape[-1]
+    if _implicit_ok(2, 0, 0, Cout, Cin, dy):
+        return _conv_implicit(2, dy.reshape(B * T, S, Cout), _dgrad_weight(weight, 3), (B, T, S)).view(B * T, S, Cin)
     dcol = linear_dx(dy.reshape(-1, dy.shape[-1]), weight)  # [B*T*S, 3*Cin]
     dx = torch.empty(B * T, S, Cin, dtype=dy.dtype, device=dy.device)
     _check(lib.gvd_col2im_t3_cl(dcol.data_ptr(), dx.data_ptr(), int(B), int(T), int(S), int(Cin), _stream()), lib,

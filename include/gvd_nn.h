@@ -55,6 +55,35 @@ typedef struct GvdGemmArgs {
 } GvdGemmArgs;
 GVD_NN_API int gvd_gemm_bf16(const GvdGemmArgs* args, gvd_nn_stream_t stream);
 
+/* Implicit-GEMM convolution on the same tensor-core kernel: no im2col buffer.  The K loop walks (tap, 64-channel block);
+ * the A tile of a tap is the activation tile itself, fetched by TMA at shifted coordinates of a 4-D tensor map over
+ * x (channels, then the convolved axes), out-of-bounds rows zero-filled by the copy engine (= the zero padding).
+ *   kind 1: 3x3 / pad 1 / stride 1 over x[F, H, W, Cin]  (ResBlock / Downsample-free convs, openaimodel3d.py:155-236;
+ *           the VAE decoder's convs, ae_modules.py:466-579): y[F, H*W, Cout], weight [Cout, 9*Cin] in (ky, kx, cin) order.
+ *           An output tile is 128 consecutive pixels of one frame: needs W % 128 == 0 or 128 % W == 0, and frames
+ *           whose pixel count fills its tiles to at least 8/9 (smaller frames stay on the im2col route).
+ *   kind 2: (3,1,1) / pad (1,0,0) over x[B, T, S, Cin] (TemporalConvBlock, openaimodel3d.py:246-266): weight [Cout, 3*Cin]
+ *           in (kt, cin) order.  Rows are (frame, pixel) flattened, a tap is a shift by S rows.
+ * Same epilogue as gvd_gemm_bf16 (bias, activation, bias2, residual with the reference's rounding points).  With the
+ * weight re-packed as [Cin, taps*Cout] and its taps reversed the same call computes the data gradient dX of the layer
+ * (vc_b200.ops.conv3x3_dx).  Cin % 64 == 0 and Cout % 8 == 0; gvd_conv_bf16_supported() tells (1 / 0) whether a geometry
+ * is served -- callers keep the im2col route for the rest (stride 2, fused upsampling, 4-channel ends of the networks). */
+typedef struct GvdConvArgs {
+    int kind;
+    int F, H, W;                       /* kind 1 */
+    int B, T; long long S;             /* kind 2 */
+    int Cin, Cout;
+    const void* x;                     /* bf16, channels-last, pixel stride Cin */
+    const void* weight;                /* bf16 [Cout, taps*Cin] */
+    void* y;                           /* bf16 [.., Cout] */
+    const float* bias;
+    const float* bias2;
+    const void* residual;              /* same layout as y, or NULL */
+    int act;
+} GvdConvArgs;
+GVD_NN_API int gvd_conv_bf16_supported(int kind, int H, int W, int Cin, int Cout);
+GVD_NN_API int gvd_conv_bf16(const GvdConvArgs* args, gvd_nn_stream_t stream);
+
 /* GroupNorm(groups) [+ SiLU] on channels-last activations x[F, S, C] (bf16 in/out, fp32 statistics over S x C/groups
  * per (frame, group)).  Serves normalization()/nn.GroupNorm(32) in ResBlock.in_layers/out_layers
  * (openaimodel3d.py:155-181; per frame: F = b*t, S = h*w), TemporalConvBlock (openaimodel3d.py:255-266; statistics

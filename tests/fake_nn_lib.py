@@ -95,6 +95,46 @@ class FakeNN:
         Cv.copy_(y.to(cdt))
         return 0
 
+    # ---- implicit-GEMM convolution (gvd_conv_bf16): same arithmetic as im2col + GEMM, stated as a convolution ----
+    def gvd_conv_bf16_supported(self, kind, H, W, Cin, Cout):
+        if Cin <= 0 or Cout <= 0 or Cin % 64 or Cout % 8:
+            return 0
+        if kind == 2:
+            return 1
+        if not (kind == 1 and H > 0 and W > 0 and (W % 128 == 0 or (W <= 128 and 128 % W == 0))):
+            return 0
+        px = H * W
+        return int((px + 127) // 128 * 128 * 8 <= px * 9)
+
+    def gvd_conv_bf16(self, args, stream):
+        self._count("conv_implicit")
+        a = args._obj
+        assert self.gvd_conv_bf16_supported(a.kind, a.H, a.W, a.Cin, a.Cout)
+        Ci, Co = a.Cin, a.Cout
+        if a.kind == 1:
+            x = self._a(a.x, a.F, a.H, a.W, Ci).float().permute(0, 3, 1, 2)
+            w = self._a(a.weight, Co, 3, 3, Ci).float().permute(0, 3, 1, 2)
+            acc = torch.nn.functional.conv2d(x, w, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+        else:
+            x = self._a(a.x, a.B, a.T, a.S, Ci).float().permute(0, 2, 3, 1).reshape(a.B * a.S, Ci, a.T)
+            w = self._a(a.weight, Co, 3, Ci).float().permute(0, 2, 1)
+            acc = torch.nn.functional.conv1d(x, w, padding=1).view(a.B, a.S, Co, a.T).permute(0, 3, 1, 2).reshape(-1, Co)
+        rows = acc.shape[0]
+        y = acc
+        if a.bias:
+            y = y + self._f(a.bias, Co)
+        if a.act == 1:
+            y = torch.nn.functional.silu(y)
+        elif a.act == 2:
+            y = torch.nn.functional.gelu(y)
+        y = self._rnd(y)
+        if a.bias2:
+            y = y + self._f(a.bias2, Co)
+        if a.residual:
+            y = y + self._a(a.residual, rows, Co).float()
+        self._a(a.y, rows, Co).copy_(y.to(self.act))
+        return 0
+
     # ---- GroupNorm ----
     def gvd_groupnorm_tmp_floats(self, F, S, groups):
         return F * groups * 2 * 4

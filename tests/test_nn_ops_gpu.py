@@ -102,6 +102,64 @@ def test_conv3x3(F, H, W, C, stride, up):
     _close(y.view(F, Ho, Wo, Cout).permute(0, 3, 1, 2), ref)
 
 
+@pytest.mark.parametrize("F,H,W,C,Cout", [(3, 8, 16, 64, 72), (2, 18, 32, 128, 64), (2, 5, 128, 64, 320), (1, 3, 256, 192, 136),
+                                          (2, 36, 64, 320, 320), (1, 16, 8, 64, 8)])
+def test_conv3x3_implicit_gemm(F, H, W, C, Cout, monkeypatch):
+    """gvd_conv_bf16 kind 1 (TMA-shifted activation tiles, zero padding by out-of-bounds fill): bit-identical to the
+    im2col + GEMM route (same K order, same accumulation), right against fp32 torch, with every epilogue input; its
+    tap-reversed form is the data gradient."""
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(H * W + C)
+    x = torch.randn(F, C, H, W, device="cuda", generator=g).to(BF)
+    w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (3 * C ** 0.5)).to(BF)
+    b, b2 = torch.randn(Cout, device="cuda", generator=g), torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(F, H * W, Cout, device="cuda", generator=g).to(BF)
+    x_cl = x.permute(0, 2, 3, 1).reshape(F, H * W, C).contiguous()
+    w_cl = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    assert ops._implicit_ok(1, H, W, C, Cout, x_cl)
+    assert not ops._implicit_ok(1, 9, 16, C, Cout, x_cl)  # 144 pixels per frame: two tiles 56 % full -> im2col route
+    y, Ho, Wo = ops.conv3x3(x_cl, F, H, W, w_cl, b, bias2=b2, residual=res)
+    y0, _, _ = ops.conv3x3(x_cl, F, H, W, w_cl, b)
+    monkeypatch.setattr(ops, "IMPLICIT_CONV", False)
+    y_col, _, _ = ops.conv3x3(x_cl, F, H, W, w_cl, b, bias2=b2, residual=res)
+    assert torch.equal(y, y_col)
+    ref = Fn.conv2d(x.float(), w.float(), b, padding=1)
+    _close(y0.view(F, H, W, Cout).permute(0, 3, 1, 2), ref)
+    # data gradient: implicit (tap-reversed weight) vs the col2im route vs autograd
+    dy = torch.randn(F, H * W, Cout, device="cuda", generator=g).to(BF)
+    dx_col = ops.conv3x3_dx(dy, F, H, W, C, w_cl)
+    monkeypatch.setattr(ops, "IMPLICIT_CONV", True)
+    if ops._implicit_ok(1, H, W, Cout, C, dy):
+        dx = ops.conv3x3_dx(dy, F, H, W, C, w_cl)
+        xr = x.float().requires_grad_(True)
+        Fn.conv2d(xr, w.float(), None, padding=1).backward(dy.float().view(F, H, W, Cout).permute(0, 3, 1, 2))
+        want = xr.grad.permute(0, 2, 3, 1).reshape(F, H * W, C)
+        _close(dx, want)
+        _close(dx_col, want, tol=1.0 / 64)  # the col2im route rounds the nine partial products to bf16 first
+
+
+@pytest.mark.parametrize("B,T,S,C,Cout", [(1, 7, 50, 64, 128), (2, 1, 129, 128, 64), (1, 25, 300, 320, 320)])
+def test_conv_t3_implicit_gemm(B, T, S, C, Cout, monkeypatch):
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(T * S + C)
+    x = torch.randn(B * T, S, C, device="cuda", generator=g).to(BF)
+    w = (torch.randn(Cout, 3 * C, device="cuda", generator=g) / (3 * C) ** 0.5).to(BF)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B * T, S, Cout, device="cuda", generator=g).to(BF)
+    y = ops.conv_t3(x, B, T, S, w, b, residual=res)
+    dy = torch.randn(B * T, S, Cout, device="cuda", generator=g).to(BF)
+    dx = ops.conv_t3_dx(dy, B, T, S, C, w)
+    monkeypatch.setattr(ops, "IMPLICIT_CONV", False)
+    assert torch.equal(y, ops.conv_t3(x, B, T, S, w, b, residual=res))
+    xr = x.float().view(B, T, S, C).permute(0, 3, 1, 2).unsqueeze(-1).requires_grad_(True)       # [B, C, T, S, 1]
+    w5 = w.float().view(Cout, 3, C).permute(0, 2, 1)[..., None, None]
+    Fn.conv3d(xr, w5, None, padding=(1, 0, 0)).backward(dy.float().view(B, T, S, Cout).permute(0, 3, 1, 2).unsqueeze(-1))
+    _close(dx, xr.grad[..., 0].permute(0, 2, 3, 1).reshape(B * T, S, C))
+    _close(ops.conv_t3_dx(dy, B, T, S, C, w), xr.grad[..., 0].permute(0, 2, 3, 1).reshape(B * T, S, C), tol=1.0 / 64)
+
+
 def test_conv_t3_and_temporal_attention():
     from vc_b200 import ops
 
