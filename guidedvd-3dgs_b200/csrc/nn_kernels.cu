@@ -20,6 +20,19 @@ bool gvd_fast_im2col3x3(const void* x, void* col, int F, int H, int W, int C, in
 bool gvd_fast_im2col_t3(const void* x, void* col, int B, int T, long long S, int C, cudaStream_t s);
 bool gvd_fast_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S, int H, float scale,
                                  cudaStream_t s);
+#ifndef GVD_HOST_EMU
+// tattn_mma.cu: temporal attention on mma.sync tiles (default; GVD_TATTN_MMA=0 selects the first kernel for A/B timing)
+bool gvd_mma_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S, int H, float scale,
+                                cudaStream_t s);
+static bool tattn_mma_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GVD_TATTN_MMA");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+#endif
 static int g_nn_fast = -1;  // -1: not decided yet (GVD_NN_FAST), 0 / 1 / 2 afterwards or through gvd_nn_set_fast
 static int nn_fast_level() {
     if (g_nn_fast < 0) {
@@ -611,6 +624,10 @@ int gvd_temporal_attention(const void* q, const void* k, const void* v, void* ou
     if (T > 32 || T <= 0) { g_nn_err_ext = "gvd_temporal_attention: needs 1 <= T <= 32"; return 2; }
     const long long warps = (long long)B * S * H;
     if (warps <= 0) return 0;
+#ifndef GVD_HOST_EMU
+    if (nn_fast_level() == 1 && tattn_mma_enabled() && gvd_mma_temporal_attention(q, k, v, out, B, T, S, H, scale, s))
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+#endif
     if (nn_fast_level() >= 2 && gvd_fast_temporal_attention(q, k, v, out, B, T, S, H, scale, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     temporal_attn_kernel<<<(unsigned)((warps + TA_WARPS - 1) / TA_WARPS), TA_WARPS * 32, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                     (const __nv_bfloat16*)v, (__nv_bfloat16*)out, B, T, S, H, scale);

@@ -233,9 +233,10 @@ typedef struct GvdDdimVjpArgs {
 } GvdDdimVjpArgs;
 GVD_NN_API int gvd_ddim_pred_x0_vjp(const GvdDdimVjpArgs* args, gvd_nn_stream_t stream);
 
-/* Level of the re-indexed variants in csrc/nn_fast.cu (same results bit for bit): 0 = the round-1 kernels; 1 = GEGLU with
- * 16-byte vectors and gvd_im2col3x3_cl / gvd_im2col_t3_cl with 32-bit index arithmetic (default: measured 1.3-2.0x
- * faster on B200); 2 = additionally the temporal-attention variant (measured 10 % slower, kept for A/B timing).
+/* Kernel generation of the memory-bound operators: 0 = the round-1 kernels; 1 (default) = GEGLU with 16-byte vectors,
+ * gvd_im2col3x3_cl / gvd_im2col_t3_cl with 32-bit index arithmetic (same results bit for bit, 1.3-2.0x faster on B200) and
+ * temporal attention on mma.sync tiles (csrc/tattn_mma.cu: same rounding points, 4.8x faster); 2 = level 0's temporal
+ * attention with K / V staged in fp32 (measured 10 % slower than level 0, kept for A/B timing).
  * Default: the environment variable GVD_NN_FAST ("0" / "1" / "2"), read at the first call.  on in 0..2 sets the level,
  * any other value only queries; returns the previous level. */
 GVD_NN_API int gvd_nn_set_fast(int on);

@@ -7,9 +7,11 @@ pytestmark = [pytest.mark.gpu]
 BF = torch.bfloat16
 
 
-def test_fast_variants_bit_identical_on_gpu():
+def test_fast_variants_bit_identical_on_gpu(monkeypatch):
     import gvd_native
     from vc_b200 import ops
+
+    monkeypatch.setattr(ops, "IMPLICIT_CONV", False)  # the im2col kernels are what is compared here
 
     lib = gvd_native.nn()
     g = torch.Generator().manual_seed(0)
@@ -38,3 +40,10 @@ def test_fast_variants_bit_identical_on_gpu():
     q, k, v = (torch.randn(25, 2000, 5 * 64, generator=g).to(BF).cuda() for _ in range(3))
     a, b = both(lambda: ops.temporal_attention(q, k, v, 1, 25, 2000, 5, 0.125))
     assert torch.equal(a, b)
+    # level 1 (default): the mma.sync kernel (csrc/tattn_mma.cu) -- same rounding points, another fp32 summation order
+    was = lib.gvd_nn_set_fast(1)
+    c = ops.temporal_attention(q, k, v, 1, 25, 2000, 5, 0.125)
+    lib.gvd_nn_set_fast(was)
+    err = (c.float() - a.float()).abs().max().item()
+    assert err <= 2.0 ** -7 * a.float().abs().max().item(), err
+    assert (c != a).float().mean().item() < 0.05  # a bf16 ulp here and there, where a score sat on a rounding boundary
