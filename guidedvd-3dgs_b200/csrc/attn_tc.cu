@@ -459,6 +459,211 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
 }
 
+
+// ---- generation 3: two softmax threads per query row ---------------------------------------------------------------
+// tools/ubench_softmax_pipe.cu (profiles/r02_ubench_softmax.txt) measured what bounds the softmax side: MUFU.EX2 runs at
+// 16 results / clk / SM, and the per-score instruction mix (max, ffma, ex2, fadd, pack/2) sustains only 12 results / clk /
+// SM with two warps per scheduler (what generation 2 has: 4 softmax warps x 2 CTAs), 16 with four.  A 128 x 128 block
+// holds 16 384 exponentials = 1 024 clk of MUFU against 512 clk of MMA, so with head dim 64 the tensor pipe cannot
+// exceed 50 % unless exponentials leave the MUFU; the way towards that bound is more softmax warps per scheduler.
+// Here 8 softmax warps per CTA: warps w and w + 4 share a TMEM lane quadrant (hardware rule: warp id % 4) and split the
+// S row -- 64 score columns, 32 packed P columns and 32 O columns each.  The pair agrees on the row maximum through two
+// floats of shared memory and a 64-thread named barrier per key block; the row sums stay separate until the end.
+constexpr int FA3_THREADS = 64 + 8 * 32;
+constexpr int FA3_SMEM = FA_SMEM + 2 * 2 * 128 * 4;  // + pair exchange: [parity][half][row] floats
+
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+__global__ void __launch_bounds__(FA3_THREADS, 2)
+flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sq = smem;
+    uint8_t* sk = smem + FA_TILE_BYTES;
+    uint8_t* sv = smem + FA_TILE_BYTES * (1 + FA_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;              // [2]
+    uint64_t* kv_empty = bars + 3;             // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    float* xchg = reinterpret_cast<float*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256);  // [2][2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.Nk + FA_BN - 1) / FA_BN;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_q);
+        tc::prefetch_tmap(&tmap_k);
+        tc::prefetch_tmap(&tmap_v);
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < FA_STAGES; ++s) {
+            tc::mbar_init(&kv_full[s], 1);
+            tc::mbar_init(&kv_empty[s], 1);
+        }
+        tc::mbar_init(s_full, 1);
+        tc::mbar_init(p_full, 8);  // one arrival per softmax warp
+        tc::mbar_init(o_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(q_full, FA_TILE_BYTES);
+            tc::tma_load_4d(sq, &tmap_q, q_full, 0, m0, h, b);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA_STAGES) & 1) ^ 1));
+                tc::mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+                tc::tma_load_4d(sk + s * FA_TILE_BYTES, &tmap_k, &kv_full[s], 0, j * FA_BN, h, b);
+                tc::tma_load_4d(sv + s * FA_TILE_BYTES, &tmap_v, &kv_full[s], 0, j * FA_BN, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = tc::make_idesc_bf16(FA_BM, FA_BN);
+            const uint32_t idesc_pv = make_idesc_pv();
+            const uint32_t q_addr = tc::smem_u32(sq);
+            tc::mbar_wait(q_full, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_full[s], (uint32_t)((j / FA_STAGES) & 1));
+                tc::fence_after_sync();
+                const uint32_t k_addr = tc::smem_u32(sk + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k)
+                    tc::umma_bf16(tmem_base + FA_S_COL, tc::make_desc_kmajor_sw128(q_addr + k * 32),
+                                  tc::make_desc_kmajor_sw128(k_addr + k * 32), idesc_qk, k != 0);
+                tc::umma_commit(s_full);  // also certifies PV_{j-1}: O is quiescent while the softmax warps rescale it
+                tc::mbar_wait(p_full, (uint32_t)(j & 1));
+                tc::fence_after_sync();
+                const uint32_t v_addr = tc::smem_u32(sv + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < FA_BN / 16; ++k)
+                    umma_bf16_ts(tmem_base + FA_O_COL, tmem_base + FA_P_COL + k * 8,
+                                 tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (j | k) != 0);
+                tc::umma_commit(&kv_empty[s]);
+            }
+            tc::umma_commit(o_full);
+        }
+    } else {
+        const int q = warp & 3;             // TMEM lane quadrant
+        const int hf = (warp - 2) >> 2;     // which half of the row's columns
+        const int rloc = q * 32 + lane;     // row inside the tile
+        const int row = m0 + rloc;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t s_col = FA_S_COL + 64 * hf, p_col = FA_P_COL + 32 * hf, o_col = FA_O_COL + 32 * hf;
+        const float sl2 = p.scale * 1.4426950408889634f;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            tc::mbar_wait(s_full, (uint32_t)(j & 1));
+            tc::fence_after_sync();
+            const int key0 = j * FA_BN + 64 * hf;
+            uint32_t v[64];
+            tc::tmem_ld32(tmem_base + lane_off + s_col, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tc::tmem_ld32(tmem_base + lane_off + s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tc::tmem_ld_wait();
+            if (key0 + 64 > p.Nk) {
+#pragma unroll
+                for (int e = 0; e < 64; ++e)
+                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+            }
+            const float m_loc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            float* xb = xchg + (j & 1) * 256;
+            xb[hf * 128 + rloc] = m_loc;
+            pair_sync(q);
+            const float m_blk = fmaxf(m_loc, xb[(hf ^ 1) * 128 + rloc]) * sl2;  // scale > 0: max commutes with it
+            float m_new = m_run;
+            if (j == 0) {
+                m_new = m_blk;
+            } else {
+                const bool grow = m_blk > m_run + 8.0f;  // both threads of a row see the same m_blk and m_run
+                if (__any_sync(0xffffffffu, grow)) {
+                    float alpha = 1.0f;
+                    if (grow) {
+                        m_new = m_blk;
+                        alpha = ex2(m_run - m_new);
+                        l_run *= alpha;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 16) {
+                        uint32_t o[16];
+                        tc::tmem_ld16(tmem_base + lane_off + o_col + c, o);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st16(tmem_base + lane_off + o_col + c, o);
+                    }
+                }
+            }
+            const float mneg = -m_new;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const float p0 = ex2(fmaf(__uint_as_float(v[c + e]), sl2, mneg));
+                    const float p1 = ex2(fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg));
+                    l0 += p0;
+                    l1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st16(tmem_base + lane_off + p_col + c / 2, pk);
+            }
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(p_full);
+            l_run += l0 + l1;
+            m_run = m_new;
+        }
+        // the two halves of a row ran with the same maximum: their sums add
+        float* xb = xchg + (nblk & 1) * 256;
+        xb[hf * 128 + rloc] = l_run;
+        pair_sync(q);
+        const float inv = 1.0f / (l_run + xb[(hf ^ 1) * 128 + rloc]);
+        tc::mbar_wait(o_full, 0);
+        tc::fence_after_sync();
+        __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo + 32 * hf;
+        uint32_t o[32];
+        tc::tmem_ld32(tmem_base + lane_off + o_col, o);
+        tc::tmem_ld_wait();
+        if (row < p.Nq) {
+#pragma unroll
+            for (int e8 = 0; e8 < 32; e8 += 8) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
+                *reinterpret_cast<uint4*>(dst + e8) = u;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -501,19 +706,21 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, GVD_FLASH_POLY=1 moves one exponential in four
-    // onto the FMA pipe.  Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, this kernel 4.13 ms, with the
-    // polynomial 4.46 ms; a variant with two query tiles ping-ponging inside one CTA per SM (8 softmax warps, all 512 TMEM
-    // columns) measured 4.20 ms and was dropped.  ncu: XU pipe 59 %, tensor pipe 30 %, issue slots 39 % -- no pipe is
-    // saturated; the softmax warps (two per scheduler) are latency-bound.
+    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, v2 the second (one softmax thread per row;
+    // GVD_FLASH_POLY=1: with one exponential in four on the FMA pipe), default v3 (two softmax threads per row).
+    // Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms, v2 with the polynomial 4.46 ms; a v2 variant
+    // with two query tiles ping-ponging inside one CTA per SM (8 softmax warps, all 512 TMEM columns) 4.20 ms, dropped.
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("GVD_FLASH");
         const char* pe = getenv("GVD_FLASH_POLY");
-        const int want = (v && v[0] == 'v' && v[1] == '1') ? 0 : ((pe && pe[0] == '1') ? 2 : 1);
+        int want = 3;
+        if (v && v[0] == 'v' && v[1] == '1') want = 0;
+        else if (v && v[0] == 'v' && v[1] == '2') want = (pe && pe[0] == '1') ? 2 : 1;
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
-                                   : (want == 1 ? (const void*)flash_attn_kernel<false> : (const void*)flash_attn_kernel<true>);
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+                       : want == 1 ? (const void*)flash_attn_kernel<false>
+                       : want == 2 ? (const void*)flash_attn_kernel<true> : (const void*)flash_attn3_kernel;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want == 3 ? FA3_SMEM : FA_SMEM);
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
         variant = want;
     }
@@ -521,7 +728,8 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
     dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
     if (variant == 0) flash_attn_v1_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 1) flash_attn_kernel<false><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
-    else flash_attn_kernel<true><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 2) flash_attn_kernel<true><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else flash_attn3_kernel<<<grid, FA3_THREADS, FA3_SMEM, s>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }
     return 0;

@@ -174,8 +174,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
     const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
     uint4* yout = reinterpret_cast<uint4*>(y + (size_t)f * S * C) + v;
-    for (int r = r0 + rsub; r < r1; r += rows_par) {
-        uint4 u = __ldg(xin + (size_t)r * vecs);
+    auto norm8 = [&](uint4 u) {
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -190,8 +189,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
             }
             h2[e] = __floats2bfloat162_rn(a, b);
         }
-        yout[(size_t)r * vecs] = u;
+        return u;
+    };
+    int r = r0 + rsub;
+    for (; r + 3 * rows_par < r1; r += 4 * rows_par) {  // four independent 16-byte loads in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(xin + (size_t)(r + k * rows_par) * vecs);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) yout[(size_t)(r + k * rows_par) * vecs] = norm8(u[k]);
     }
+    for (; r < r1; r += rows_par) yout[(size_t)r * vecs] = norm8(__ldg(xin + (size_t)r * vecs));
     }
 }
 
@@ -221,6 +229,62 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
         const float2 v = __bfloat1622float2(xin[i]);
         yout[i] = __floats2bfloat162_rn((v.x - mean) * rstd * gamma[2 * i] + beta[2 * i],
                                         (v.y - mean) * rstd * gamma[2 * i + 1] + beta[2 * i + 1]);
+    }
+}
+
+// The same normalisation with the row held in registers: one warp per row, NV 16-byte vectors per lane (C <= 256 * NV,
+// C % 8 == 0), x read once and y written once with full-sector accesses (the kernel above reads the row three times
+// with 4-byte accesses).  Same two-pass mean / variance arithmetic; only the order of the lane sums differs.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            long long rows, int C, float eps) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, vecs = C >> 3;
+    const uint4* xin = reinterpret_cast<const uint4*>(x + row * C);
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (i < vecs) u = __ldg(xin + i);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 t = __bfloat1622float2(h2[e]);
+            v[k][2 * e] = t.x;
+            v[k][2 * e + 1] = t.y;
+            s += t.x + t.y;
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        if (lane + 32 * k < vecs) {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) q += (v[k][e] - mean) * (v[k][e] - mean) + (v[k][e + 1] - mean) * (v[k][e + 1] - mean);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    uint4* yout = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < vecs) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * i + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                h2[e] = __floats2bfloat162_rn((v[k][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
+                                              (v[k][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]);
+            yout[i] = u;
+        }
     }
 }
 
@@ -572,6 +636,17 @@ int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta,
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (rows <= 0) return 0;
     if (C % 2) { g_nn_err_ext = "gvd_layernorm: C must be even"; return 2; }
+    const bool vec_ok = nn_fast_enabled() && (C % 8 == 0) && C <= 256 * 6 &&
+                        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                          reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y;
+    if (vec_ok && C <= 512) layernorm_vec_kernel<2><<<grid, 256, 0, s>>>(xb, yb, gamma, beta, rows, C, eps);
+    else if (vec_ok && C <= 768) layernorm_vec_kernel<3><<<grid, 256, 0, s>>>(xb, yb, gamma, beta, rows, C, eps);
+    else if (vec_ok && C <= 1280) layernorm_vec_kernel<5><<<grid, 256, 0, s>>>(xb, yb, gamma, beta, rows, C, eps);
+    else if (vec_ok) layernorm_vec_kernel<6><<<grid, 256, 0, s>>>(xb, yb, gamma, beta, rows, C, eps);
+    else
     layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, rows, C, eps);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
