@@ -465,8 +465,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 // 16 results / clk / SM, and the per-score instruction mix (max, ffma, ex2, fadd, pack/2) sustains only 12 results / clk /
 // SM with two warps per scheduler (what generation 2 has: 4 softmax warps x 2 CTAs), 16 with four.  A 128 x 128 block
 // holds 16 384 exponentials = 1 024 clk of MUFU against 512 clk of MMA, so with head dim 64 the tensor pipe cannot
-// exceed 50 % unless exponentials leave the MUFU; the way towards that bound is more softmax warps per scheduler.
-// Here 8 softmax warps per CTA: warps w and w + 4 share a TMEM lane quadrant (hardware rule: warp id % 4) and split the
+// exceed 50 % unless exponentials leave the MUFU.  This variant tries more softmax warps per scheduler -- measured
+// 4.45 ms against generation 2's 4.13 ms (the 96-register cap of 2 x 320 threads and the pair barrier cost more than the
+// extra warps bring), so generation 2 stays the default; selectable with GVD_FLASH=v3.
+// 8 softmax warps per CTA: warps w and w + 4 share a TMEM lane quadrant (hardware rule: warp id % 4) and split the
 // S row -- 64 score columns, 32 packed P columns and 32 O columns each.  The pair agrees on the row maximum through two
 // floats of shared memory and a 64-thread named barrier per key block; the row sums stay separate until the end.
 constexpr int FA3_THREADS = 64 + 8 * 32;
@@ -706,17 +708,17 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, v2 the second (one softmax thread per row;
-    // GVD_FLASH_POLY=1: with one exponential in four on the FMA pipe), default v3 (two softmax threads per row).
-    // Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms, v2 with the polynomial 4.46 ms; a v2 variant
-    // with two query tiles ping-ponging inside one CTA per SM (8 softmax warps, all 512 TMEM columns) 4.20 ms, dropped.
+    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, v3 the third (two softmax threads per row);
+    // default: the second (one softmax thread per row; GVD_FLASH_POLY=1: one exponential in four on the FMA pipe).
+    // Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms, v2 with the polynomial 4.46 ms, v3 4.45 ms;
+    // a v2 variant with two query tiles ping-ponging inside one CTA per SM (8 softmax warps, all 512 TMEM columns) 4.20 ms.
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("GVD_FLASH");
         const char* pe = getenv("GVD_FLASH_POLY");
-        int want = 3;
+        int want = (pe && pe[0] == '1') ? 2 : 1;
         if (v && v[0] == 'v' && v[1] == '1') want = 0;
-        else if (v && v[0] == 'v' && v[1] == '2') want = (pe && pe[0] == '1') ? 2 : 1;
+        else if (v && v[0] == 'v' && v[1] == '3') want = 3;
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
                        : want == 1 ? (const void*)flash_attn_kernel<false>
                        : want == 2 ? (const void*)flash_attn_kernel<true> : (const void*)flash_attn3_kernel;

@@ -17,6 +17,7 @@
 // main loop.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the epilogue.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/gvd_nn.h"
@@ -219,7 +220,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 constexpr int P_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 
 template <int BN_> struct PCfg {
-    static constexpr int STAGES_ = BN_ == 256 ? 3 : (BN_ == 128 ? 4 : 6);
+    static constexpr int STAGES_ = BN_ == 256 ? 3 : (BN_ == 128 ? 6 : 8);
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_ * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int HALF = BN_ / 2;                           // columns handled by one epilogue warp
@@ -476,6 +477,242 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ====================================================================================================================
+// CTA-pair kernel (cta_group::2): one cluster of two CTAs (the two SMs of a TPC) computes a 256 x BN_ tile.
+// Each CTA stages ITS 128 rows of A and ITS half of the B tile (BN_/2 rows); the leader's single thread issues
+// tcgen05.mma.cta_group::2 (M = 256), which reads A and B from both CTAs' shared memory and accumulates rows 0-127 in
+// the leader's TMEM and rows 128-255 in the peer's.  Per SM and K = 16 step that is 4 KB of A + BN_/2 x 32 B of B from
+// shared memory instead of 4 KB + BN_ x 32 B: at BN_ = 128 the one-CTA kernel needs the whole 128 B/clk of its SM's
+// shared memory, the pair 96 B/clk; at BN_ = 256 96 -> 64 B/clk.  Same roles and epilogue as the one-CTA kernel.
+// Barriers: full[s] lives in the leader (its producer arms it for the bytes of BOTH CTAs, both CTAs' TMA loads
+// complete on it), empty[s] / tmem_full[b] are signalled in both CTAs by multicast commits, tmem_empty[b] collects
+// the 16 epilogue warps of the pair in the leader.
+// ====================================================================================================================
+template <int BN_> struct P2Cfg {
+    static constexpr int BH = BN_ / 2;  // B rows staged per CTA
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BH * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int HALF = BN_ / 2;
+    static constexpr int EPI_WARP_BYTES = 32 * HALF * 2;
+    static constexpr int STAGES_ = BN_ == 256 ? 5 : 7;
+    static constexpr int BAR_OFF = STAGES_ * STAGE_BYTES + 8 * EPI_WARP_BYTES;
+    static constexpr int SMEM = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 2 * BN_ <= 256 ? 256 : 512;
+};
+
+template <int BN_>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p,
+                      int tiles_m, int tiles_n, int total_tiles) {
+    using Cfg = P2Cfg<BN_>;
+    constexpr int ST = Cfg::STAGES_;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_epi = smem + ST * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* full = bars;                     // [ST]  used in the leader only
+    uint64_t* empty = bars + ST;               // [ST]  per CTA
+    uint64_t* tmem_full = bars + 2 * ST;       // [2]   per CTA
+    uint64_t* tmem_empty = bars + 2 * ST + 2;  // [2]   used in the leader only
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < ST; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&tmem_full[b], 1);
+            tc::mbar_init(&tmem_empty[b], 16);  // the 8 epilogue warps of each CTA of the pair
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc_2cta(tmem_ptr, Cfg::TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int tiles_mn = tiles_m * tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int kc = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                const int z = tile / tiles_mn, r = tile - z * tiles_mn;
+                const int m0 = (r / tiles_n) * (2 * BM) + (int)rank * BM, nb0 = (r % tiles_n) * BN_ + (int)rank * Cfg::BH;
+                const int bh = z % p.batch_h, bb = z / p.batch_h;
+                int ax = m0 - p.conv_w, ay = bh;  // implicit-GEMM convolution coordinates (see the one-CTA kernel)
+                if (p.conv_kind == 1) {
+                    ay = m0 / p.conv_w;
+                    ax = m0 - ay * p.conv_w;
+                }
+                const int taps = p.conv_kind == 1 ? 9 : (p.conv_kind == 2 ? 3 : 1);
+                const int kper = p.conv_kind ? p.conv_cin : num_kb * BK;
+                int dx = -1, dy = -1, kw = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int cx = p.conv_kind == 1 ? ax + dx : (p.conv_kind == 2 ? ax + tap * p.conv_w : m0);
+                    const int cy = p.conv_kind == 1 ? ay + dy : bh;
+                    for (int cc = 0; cc < kper; cc += BK, kw += BK, ++kc) {
+                        const int s = kc % ST;
+                        tc::mbar_wait(&empty[s], (uint32_t)(((kc / ST) & 1) ^ 1));
+                        const uint32_t fb = tc::mapa(tc::smem_u32(&full[s]), 0);
+                        if (rank == 0) tc::mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+                        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                        tc::tma_load_4d_2cta(sa, &tmap_a, fb, cc, cx, cy, bb);
+                        if (p.conv_kind) tc::tma_load_4d_2cta(sa + Cfg::A_BYTES, &tmap_b, fb, kw, nb0, 0, 0);
+                        else tc::tma_load_4d_2cta(sa + Cfg::A_BYTES, &tmap_b, fb, kw, nb0, bh, bb);
+                    }
+                    if (++dx == 2) { dx = -1; ++dy; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(2 * BM, BN_);
+            int kc = 0, it = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+                const int buf = it & 1;
+                tc::mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc::fence_after_sync();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN_);
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const int s = kc % ST;
+                    tc::mbar_wait(&full[s], (uint32_t)((kc / ST) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc::umma_bf16_2cta(tmem_d, tc::make_desc_kmajor_sw128(a_addr + k * 32),
+                                           tc::make_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    tc::umma_commit_2cta(&empty[s]);
+                }
+                tc::umma_commit_2cta(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        constexpr int HALF = Cfg::HALF;
+        uint8_t* stage = smem_epi + ew * Cfg::EPI_WARP_BYTES;
+        constexpr int ROW_BYTES = HALF * 2, CHUNKS = ROW_BYTES / 16;
+        constexpr int ROWS_PER_PASS = 32 / CHUNKS;
+        constexpr int SWZ = CHUNKS >= 8 ? 7 : CHUNKS - 1;
+        const bool plain = (p.act == GVD_ACT_NONE) && (p.bias2 == nullptr);
+        const uint32_t te0 = tc::mapa(tc::smem_u32(&tmem_empty[0]), 0), te1 = tc::mapa(tc::smem_u32(&tmem_empty[1]), 0);
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+            const int z = tile / tiles_mn, r = tile - z * tiles_mn;
+            const int m0 = (r / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (r % tiles_n) * BN_ + half * HALF;
+            const int bh = z % p.batch_h, bb = z / p.batch_h;
+            const int buf = it & 1;
+            const long long base_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h;
+            const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
+            const int n = n0 + chunk * 8;
+            uint4 resv[32 / ROWS_PER_PASS];
+            if (p.residual != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
+                    const int m = m0 + q * 32 + i * ROWS_PER_PASS + rsub;
+                    resv[i] = make_uint4(0, 0, 0, 0);
+                    if (m < p.M && n < p.N)
+                        resv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                                       base_off + (long long)m * p.ldc + n));
+                }
+            }
+            tc::mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            tc::fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + half * HALF);
+#pragma unroll 1
+            for (int c = 0; c < HALF; c += 32) {
+                if (n0 + c >= p.N) break;
+                uint32_t v[32], packed[16];
+                tc::tmem_ld32(taddr + (uint32_t)c, v);
+                tc::tmem_ld_wait();
+                if (plain) epi_convert32<0>(v, packed, p, n0 + c);
+                else epi_convert32<1>(v, packed, p, n0 + c);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ch = c / 8 + k;
+                    *reinterpret_cast<uint4*>(stage + lane * ROW_BYTES + ((ch ^ (lane & SWZ)) << 4)) =
+                        make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(buf ? te1 : te0);
+#pragma unroll
+            for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
+                const int rr = i * ROWS_PER_PASS + rsub;
+                const int m = m0 + q * 32 + rr;
+                if (m < p.M && n < p.N) {
+                    uint4 val = *reinterpret_cast<const uint4*>(stage + rr * ROW_BYTES + ((chunk ^ (rr & SWZ)) << 4));
+                    const long long off = base_off + (long long)m * p.ldc + n;
+                    if (p.residual != nullptr) {
+                        const uint4 rv = resv[i];
+                        __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&val);
+                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 af = __bfloat1622float2(a2[e]), rf = __bfloat1622float2(r2[e]);
+                            a2[e] = __floats2bfloat162_rn(af.x + rf.x, af.y + rf.y);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = val;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();  // both CTAs are done with the pair's tensor memory and with each other's barriers
+    if (warp == 1) tc::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN_>
+cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int batch, cudaStream_t s) {
+    using Cfg = P2Cfg<BN_>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN_ - 1) / BN_;
+    const long long total = (long long)tiles_m * tiles_n * batch;
+    const int pairs = (int)(total < num_sms / 2 ? total : num_sms / 2);
+    gemm_bf16_pair_kernel<BN_><<<2 * pairs, P_THREADS, Cfg::SMEM, s>>>(ta, tb, p, tiles_m, tiles_n, (int)total);
+    return cudaGetLastError();
+}
+
+// GVD_GEMM_PAIR: 1 (default) = CTA-pair kernel where it applies, 0 = one-CTA kernels only (A/B timing)
+bool pair_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GVD_GEMM_PAIR");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 template <int BN_>
 cudaError_t launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int batch, cudaStream_t s) {
     using Cfg = PCfg<BN_>;
@@ -543,6 +780,18 @@ bool make_tmap_mn(CUtensorMap* map, const void* base, long long N, long long K, 
     return r == CUDA_SUCCESS;
 }
 
+// When the CTA-pair kernel pays (B200, tools/bench_gemm_pair.py, profiles/r02_gemm_pair_sweep.txt): 256-wide tiles with
+// K >= 640 (+3 % at K = 640, +11-13 % at 1280-5120, +24 % at K = 11520); at K = 320 its per-tile cross-CTA hand-overs cost
+// 13-17 %, its 128-wide form loses everywhere, and few tiles leave the second wave of 74 pairs empty.
+bool use_pair(long long M, int N, int K, int batch, int bn) {
+    if (!pair_enabled() || bn != 256 || K < 640) return false;
+    const long long t128 = (M + 127) / 128, t256 = (M + 255) / 256, tn = (N + bn - 1) / bn;
+    if (t256 * 2 * 8 > t128 * 9) return false;  // 256-row tiles would pad M by more than 12.5 % over 128-row tiles
+    const long long tp = t256 * tn * batch, to = t128 * tn * batch;
+    const double eff_pair = (double)tp / (double)((tp + 73) / 74 * 74), eff_one = (double)to / (double)((to + 147) / 148 * 148);
+    return eff_pair >= 0.9 * eff_one;
+}
+
 }  // namespace
 
 extern "C" {
@@ -586,12 +835,18 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         int bn = 128;
         if (a->N <= 64) bn = 64;
         else if (padded(256) <= padded(128)) bn = 256;
+        const int batch = a->batch_h * a->batch_b;
+        const bool pair = use_pair(a->M, a->N, a->K, batch, bn);
         if (!make_tmap(&ta, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
-            !make_tmap(&tb, a->B, a->K, a->N, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b, bn)) {
+            !make_tmap(&tb, a->B, a->K, a->N, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b, pair ? bn / 2 : bn)) {
             g_nn_err = "gvd_gemm_bf16: cuTensorMapEncodeTiled failed";
             return 1;
         }
-        const int batch = a->batch_h * a->batch_b;
+        if (pair) {
+            cudaError_t e = launch_pair<256>(ta, tb, p, batch, s);
+            if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 pair launch: ") + cudaGetErrorString(e); return 1; }
+            return 0;
+        }
         cudaError_t e = bn == 256 ? launch_persistent<256>(ta, tb, p, batch, s)
                       : bn == 128 ? launch_persistent<128>(ta, tb, p, batch, s)
                                   : launch_persistent<64>(ta, tb, p, batch, s);
@@ -685,12 +940,14 @@ int gvd_conv_bf16(const GvdConvArgs* a, gvd_nn_stream_t stream_) {
     int bn = 128;
     if (N <= 64) bn = 64;
     else if (padded(256) <= padded(128)) bn = 256;
-    if (!make_tmap(&tb, a->weight, Kw, N, 1, 1, Kw, 0, 0, bn)) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the weight map"; return 1; }
+    const bool pair = use_pair(M, N, taps * a->Cin, batch_h * batch_b, bn);
+    if (!make_tmap(&tb, a->weight, Kw, N, 1, 1, Kw, 0, 0, pair ? bn / 2 : bn)) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the weight map"; return 1; }
     const long long ldc = N;
     EpiParams p{a->y, ldc, (long long)M * ldc, (long long)batch_h * M * ldc, a->bias, a->bias2, a->residual, 1.0f, a->act, 0,
                 (int)M, N, taps * kpt * BK, batch_h, 0, a->kind, a->kind == 1 ? a->W : (int)a->S, a->Cin};
     const int batch = batch_h * batch_b;
-    cudaError_t e = bn == 256 ? launch_persistent<256>(ta, tb, p, batch, s)
+    cudaError_t e = pair ? launch_pair<256>(ta, tb, p, batch, s)
+                  : bn == 256 ? launch_persistent<256>(ta, tb, p, batch, s)
                   : bn == 128 ? launch_persistent<128>(ta, tb, p, batch, s)
                               : launch_persistent<64>(ta, tb, p, batch, s);
     if (e != cudaSuccess) { g_nn_err = std::string("gvd_conv_bf16 launch: ") + cudaGetErrorString(e); return 1; }
