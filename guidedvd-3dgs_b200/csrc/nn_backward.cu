@@ -17,7 +17,7 @@ extern thread_local std::string g_nn_err_ext;
 
 namespace {
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }  // approximate reciprocal, <= 2 ulp
 // d/dx [x * sigmoid(x)]
 __device__ __forceinline__ float dsilu(float x) {
     const float s = sigmoid_f(x);
@@ -125,17 +125,25 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16
             }
             const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
             const uint4* din = reinterpret_cast<const uint4*>(dy + (size_t)f * S * C) + v;
-            for (int r = r0 + rsub; r < r1; r += rows_par) {
+            auto accum = [&](const uint4& ux, const uint4& ud) {
                 float xv[8], dv[8];
-                unpack8(__ldg(xin + (size_t)r * vecs), xv);
-                unpack8(__ldg(din + (size_t)r * vecs), dv);
+                unpack8(ux, xv);
+                unpack8(ud, dv);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float g = gn_upstream(xv[e], dv[e], sc[e], sf[e], gm[e], do_silu);
                     a1[e] += g;
                     a2[e] = fmaf(g, (xv[e] - mu[e]) * rs[e], a2[e]);
                 }
+            };
+            int r = r0 + rsub;
+            for (; r + rows_par < r1; r += 2 * rows_par) {  // four independent 16-byte loads in flight per thread
+                const uint4 x0 = __ldg(xin + (size_t)r * vecs), d0 = __ldg(din + (size_t)r * vecs);
+                const uint4 x1 = __ldg(xin + (size_t)(r + rows_par) * vecs), d1 = __ldg(din + (size_t)(r + rows_par) * vecs);
+                accum(x0, d0);
+                accum(x1, d1);
             }
+            for (; r < r1; r += rows_par) accum(__ldg(xin + (size_t)r * vecs), __ldg(din + (size_t)r * vecs));
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int g = (8 * v + e) / cpg;
@@ -200,18 +208,26 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
         const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
         const uint4* din = reinterpret_cast<const uint4*>(dy + (size_t)f * S * C) + v;
         uint4* dout = reinterpret_cast<uint4*>(dx + (size_t)f * S * C) + v;
-        for (int r = r0 + rsub; r < r1; r += rows_par) {
+        auto dx8 = [&](const uint4& ux, const uint4& ud) {
             float xv[8], dv[8], o[8];
-            unpack8(__ldg(xin + (size_t)r * vecs), xv);
-            unpack8(__ldg(din + (size_t)r * vecs), dv);
+            unpack8(ux, xv);
+            unpack8(ud, dv);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float g = gn_upstream(xv[e], dv[e], sc[e], sf[e], gm[e], do_silu);
                 const float xh = (xv[e] - mu[e]) * rs[e];
                 o[e] = rs[e] * (g - m1[e] - xh * m2[e]);
             }
-            dout[(size_t)r * vecs] = pack8(o);
+            return pack8(o);
+        };
+        int r = r0 + rsub;
+        for (; r + rows_par < r1; r += 2 * rows_par) {  // four independent 16-byte loads in flight per thread
+            const uint4 x0 = __ldg(xin + (size_t)r * vecs), d0 = __ldg(din + (size_t)r * vecs);
+            const uint4 x1 = __ldg(xin + (size_t)(r + rows_par) * vecs), d1 = __ldg(din + (size_t)(r + rows_par) * vecs);
+            dout[(size_t)r * vecs] = dx8(x0, d0);
+            dout[(size_t)(r + rows_par) * vecs] = dx8(x1, d1);
         }
+        for (; r < r1; r += rows_par) dout[(size_t)r * vecs] = dx8(__ldg(xin + (size_t)r * vecs), __ldg(din + (size_t)r * vecs));
     }
 }
 

@@ -45,7 +45,9 @@ static bool nn_fast_enabled() { return nn_fast_level() >= 1; }
 
 namespace {
 
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the approximate reciprocal (MUFU.RCP + FMUL, <= 2 ulp in fp32, far below the bf16 rounding that
+// follows): the IEEE division it replaces was ~10 of the ~22 instructions per element of gn_apply_kernel.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

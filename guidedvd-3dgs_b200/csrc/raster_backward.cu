@@ -80,7 +80,10 @@ __device__ __forceinline__ int warp_reduce10(float (&v)[10], uint32_t lane, floa
     return local + (b4 ? 5 : 0);
 }
 
-template <int SPLIT, bool EXACT_DIV>
+// MOM: accumulate the raw moments  sum w, sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2  (w = G dL/dalpha-term) per
+// Gaussian and let gaussian_backward apply the conic / opacity factors once per Gaussian instead of once per pixel
+// (14 of ~155 instructions per visited (warp, instance); tools/moments_error.py: 2e-6 relative on the mean2D gradients).
+template <int SPLIT, bool EXACT_DIV, bool MOM>
 __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const SplatRec* __restrict__ splat,
     int W, int H, uint32_t tiles_x, const float* __restrict__ bg_color, const float* __restrict__ alphas,
@@ -258,17 +261,28 @@ __global__ void __launch_bounds__(256 / SPLIT, 3 * SPLIT) render_backward_kernel
                         // background (backward.cu:573-578)
                         dL_dopa += (EXACT_DIV ? -T_final / one_m_alpha : -T_final * rcp_1ma) * bg_dot_dpixel;
 
-                        const float dL_dG = rb.y * dL_dopa;
-                        const float gdx = G * d.x;
-                        const float gdy = G * d.y;
-                        const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-                        const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-                        g[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        g[1] = dL_dG * dG_ddely * ddely_dy;
-                        g[2] = -0.5f * gdx * d.x * dL_dG;
-                        g[3] = -0.5f * gdx * d.y * dL_dG;
-                        g[4] = -0.5f * gdy * d.y * dL_dG;
-                        g[5] = G * dL_dopa;
+                        if (MOM) {
+                            const float w = G * dL_dopa;
+                            const float wdx = w * d.x, wdy = w * d.y;
+                            g[0] = wdx;
+                            g[1] = wdy;
+                            g[2] = wdx * d.x;
+                            g[3] = wdx * d.y;
+                            g[4] = wdy * d.y;
+                            g[5] = w;
+                        } else {
+                            const float dL_dG = rb.y * dL_dopa;
+                            const float gdx = G * d.x;
+                            const float gdy = G * d.y;
+                            const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
+                            const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                            g[0] = dL_dG * dG_ddelx * ddelx_dx;
+                            g[1] = dL_dG * dG_ddely * ddely_dy;
+                            g[2] = -0.5f * gdx * d.x * dL_dG;
+                            g[3] = -0.5f * gdx * d.y * dL_dG;
+                            g[4] = -0.5f * gdy * d.y * dL_dG;
+                            g[5] = G * dL_dopa;
+                        }
                     }
                     float total;
                     const int slot = warp_reduce10(g, lane, total);
@@ -305,9 +319,9 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
         o_sh[3 * (k) + 2] = _t.z * conf;            \
     }
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool MOM>
 __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
-    int D, int M, const float3* __restrict__ means, const uint32_t* __restrict__ vis_id, const uint32_t* __restrict__ counts,
+    const SplatRec* __restrict__ splat, int W, int H, int D, int M, const float3* __restrict__ means, const uint32_t* __restrict__ vis_id, const uint32_t* __restrict__ counts,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float3* __restrict__ scales,
     const float4* __restrict__ rotations, const float scale_modifier, const float* __restrict__ cov3D_precomp,
     const float* __restrict__ view, const float* __restrict__ proj, const float h_x, float h_y, const float tan_fovx,
@@ -336,9 +350,19 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
         const float conf = confidence ? confidence[idx] : 1.0f;
         const float4* ap = reinterpret_cast<const float4*>(acc + (size_t)idx * GVD_ACC_STRIDE);
         const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
-        const float2 dL_dmean2D = {a0.x, a0.y};
-        const float3 dL_dconic = {a0.z, a0.w, a1.x};
+        float2 dL_dmean2D = {a0.x, a0.y};
+        float3 dL_dconic = {a0.z, a0.w, a1.x};
         const float dL_dopac = a1.y;
+        if (MOM) {  // the accumulator holds raw moments (see render_backward_kernel): apply conic / opacity here, once
+            const float4* rec = reinterpret_cast<const float4*>(splat + idx);
+            const float4 ra = __ldg(rec), rb = __ldg(rec + 1);  // ra.z, ra.w, rb.x = conic; rb.y = opacity (as composited)
+            const float o = rb.y;
+            dL_dmean2D.x = -o * (0.5f * W) * (ra.z * a0.x + ra.w * a0.y);
+            dL_dmean2D.y = -o * (0.5f * H) * (rb.x * a0.y + ra.w * a0.x);
+            dL_dconic.x = -0.5f * o * a0.z;
+            dL_dconic.y = -0.5f * o * a0.w;
+            dL_dconic.z = -0.5f * o * a1.x;
+        }
         const float3 dL_dcolor = {a1.z, a1.w, a2.x};
         const float dL_ddepth = a2.y;
 
@@ -661,24 +685,42 @@ void gvd_launch_zero_bytes(void* p, size_t bytes, cudaStream_t s) {
     if (tail) gvd_launch(zero_words_kernel, dim3(1), dim3(256), 0, s, reinterpret_cast<uint32_t*>(c + head + body), tail / 4);
 }
 
+// GVD_BWD_MOMENTS=0: per-pixel conic factors as in the reference (A/B switch); default: raw moments.  Both backward
+// kernels of a frame read the same switch.
+static bool gvd_bwd_moments() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GVD_BWD_MOMENTS");
+        const char* x = getenv("GVD_BWD_EXACT_DIV");
+        on = ((e && e[0] == '0') || (x && x[0] == '1')) ? 0 : 1;
+    }
+    return on == 1;
+}
+
 template <int SPLIT>
 static void launch_render_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const RasterBinPtrs& b,
                                    const RasterImgPtrs& im, float* acc, float4* zero, size_t zero_n4, dim3 grid, cudaStream_t s) {
     // GVD_BWD_EXACT_DIV=1: the reference's two IEEE divisions per contribution instead of one reciprocal + two
-    // multiplications. Measured: +12 us (200 -> 212 us at C2), no change in any parity figure; off by default.
+    // multiplications. Measured: +12 us (200 -> 212 us at C2), no change in any parity figure; off by default (and it
+    // implies the per-pixel conic factors, i.e. no moments).
     static int exact = -1;
     if (exact < 0) {
         const char* e = getenv("GVD_BWD_EXACT_DIV");
         exact = (e && e[0] == '1') ? 1 : 0;
-        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute((const void*)render_backward_kernel<SPLIT, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
     if (exact)
-        gvd_launch(render_backward_kernel<SPLIT, true>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+        gvd_launch(render_backward_kernel<SPLIT, true, false>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+                   g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
+                   a.dL_dalpha_pix, acc, zero, zero_n4);
+    else if (gvd_bwd_moments())
+        gvd_launch(render_backward_kernel<SPLIT, false, true>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
                    g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
                    a.dL_dalpha_pix, acc, zero, zero_n4);
     else
-        gvd_launch(render_backward_kernel<SPLIT, false>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
+        gvd_launch(render_backward_kernel<SPLIT, false, false>, dim3(grid.x * grid.y * SPLIT), dim3(256 / SPLIT), 0, s, im.ranges, b.point_list,
                    g.splat, a.width, a.height, grid.x, a.background, a.alphas, im.n_contrib, a.dL_dpix, a.dL_ddepth_pix,
                    a.dL_dalpha_pix, acc, zero, zero_n4);
 }
@@ -697,7 +739,14 @@ static void launch_gaussian_backward(const GvdRasterBackwardArgs& a, const Raste
                                      float focal_x, float focal_y, int num_visible, cudaStream_t s) {
     const int n = num_visible >= 0 ? num_visible : a.P;  // V unknown on the host: cover P, surplus CTAs return at once
     if (n <= 0) return;
-    gvd_launch(gaussian_backward_kernel<MIN_CTAS>, dim3((n + 255) / 256), dim3(256), 0, s,
+    if (gvd_bwd_moments())
+        gvd_launch(gaussian_backward_kernel<MIN_CTAS, true>, dim3((n + 255) / 256), dim3(256), 0, s, g.splat, a.width, a.height,
+            a.D, a.M, (const float3*)a.means3D, g.vis_id, g.counts, a.shs, g.clamped, (const float3*)a.scales,
+            (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
+            a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,
+            a.dL_dopacity, a.dL_dcolors, a.dL_dcov3D, a.dL_dsh, a.dL_dscales, a.dL_drotations);
+    else
+    gvd_launch(gaussian_backward_kernel<MIN_CTAS, false>, dim3((n + 255) / 256), dim3(256), 0, s, g.splat, a.width, a.height,
         a.D, a.M, (const float3*)a.means3D, g.vis_id, g.counts, a.shs, g.clamped, (const float3*)a.scales,
         (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
         a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,

@@ -43,15 +43,16 @@ class Linear(Function):
 class GroupNorm(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, F, S, groups, eps, silu):
-        ctx.save_for_backward(x)
+        y, stats = ops.groupnorm_with_stats(x, gamma, beta, F, S, groups, eps, silu)  # the backward reuses the statistics
+        ctx.save_for_backward(x, stats)
         ctx.args = (gamma, beta, F, S, groups, eps, silu)
-        return ops.groupnorm(x, gamma, beta, F, S, groups, eps, silu)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
+        x, stats = ctx.saved_tensors
         gamma, beta, F, S, groups, eps, silu = ctx.args
-        dx = ops.groupnorm_bwd(x, _c(dy), gamma, beta, F, S, groups, eps, silu).view_as(x)
+        dx = ops.groupnorm_bwd(x, _c(dy), gamma, beta, F, S, groups, eps, silu, stats=stats).view_as(x)
         return dx, None, None, None, None, None, None, None
 
 

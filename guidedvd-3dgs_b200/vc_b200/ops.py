@@ -34,8 +34,35 @@ def _grad():
     return grad
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Current stream of the current device as a cudaStream_t (the raw-handle query: torch.cuda.current_stream() costs
+    ~26 us per call, and an eager forward makes ~1 300 launches)."""
+    if _raw_stream is not None and torch.cuda.is_available():
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _on_device:
+    """`with _on_device(dev)` only when dev is not already current (the guard costs ~10 us per use, and the eager
+    guided step makes ~2 000 launches)."""
+    __slots__ = ("guard",)
+
+    def __init__(self, dev):
+        self.guard = None
+        if dev.type == "cuda" and dev.index is not None and torch.cuda.current_device() != dev.index:
+            self.guard = torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
 
 
 def _check(rc, lib, what):
@@ -60,7 +87,7 @@ def gemm_raw(A, B, Cout, M, N, K, lda, ldb, ldc, batch_h=1, batch_b=1, a_strides
     a.bias, a.bias2, a.residual = _p(bias), _p(bias2), _p(residual)
     a.alpha, a.act, a.out_fp32 = float(alpha), ACT[act], int(Cout.dtype == torch.float32)
     a.b_mn_major = int(bool(b_mn_major))
-    with torch.cuda.device(A.device):
+    with _on_device(A.device):
         _check(lib.gvd_gemm_bf16(C.byref(a), _stream()), lib, "gvd_gemm_bf16")
     return Cout
 
@@ -101,6 +128,27 @@ def groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
     _check(lib.gvd_groupnorm_cl(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(F), int(S), int(Cc),
                                 int(groups), float(eps), int(silu), tmp.data_ptr(), nfl, _stream()), lib, "gvd_groupnorm_cl")
     return y
+
+
+def groupnorm_with_stats(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
+    """`groupnorm` through the split entry points, returning (y, stats[F, groups, 2] = (sum x, sum x^2)) so the guided
+    sampler's backward does not have to read x a second time for the statistics (vc_b200.grad.GroupNorm)."""
+    lib = _n.nn()
+    Cc = x.shape[-1]
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    nfl = int(lib.gvd_groupnorm_tmp_floats(int(F), int(S), int(groups)))
+    key = (x.device, nfl)
+    tmp = _gn_tmp.get(key)
+    if tmp is None:
+        tmp = _gn_tmp[key] = torch.empty(nfl, dtype=torch.float32, device=x.device)
+    stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
+    _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S), int(Cc), int(groups), tmp.data_ptr(), nfl,
+                                      _stream()), lib, "gvd_groupnorm_cl_stats")
+    _check(lib.gvd_groupnorm_cl_apply(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), int(F),
+                                      int(S), int(S), int(Cc), int(groups), float(eps), int(silu), _stream()), lib,
+           "gvd_groupnorm_cl_apply")
+    return y, stats
 
 
 def groupnorm_sharded(x, gamma, beta, F, S_local, S_total, part, groups=32, eps=1e-5, silu=False):
@@ -181,7 +229,7 @@ def _conv_implicit(kind, x, weight, geom, bias=None, bias2=None, residual=None, 
         residual = residual.contiguous()
     a.x, a.weight, a.y = x.data_ptr(), weight.data_ptr(), y.data_ptr()
     a.bias, a.bias2, a.residual, a.act = _p(bias), _p(bias2), _p(residual), ACT[act]
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(lib.gvd_conv_bf16(C.byref(a), _stream()), lib, "gvd_conv_bf16")
     return y
 
@@ -259,7 +307,7 @@ def flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False):
         B, nq, qs, ks = 1, Bq * Nq, Bq * Nq * HD, Nk * HD
     else:
         B, nq, qs, ks = Bq, Nq, Nq * HD, Nk * HD
-    with torch.cuda.device(q.device):
+    with _on_device(q.device):
         _check(lib.gvd_flash_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), int(B), int(nq), int(Nk), int(H),
                                        int(qs), int(ks), float(scale), _stream()), lib, "gvd_flash_attention")
     return out
@@ -322,7 +370,7 @@ def ddim_step(x, e_cond, e_uncond, noise, coef):
               "ddim_sigma", "temperature", "scale_t", "scale_prev"):
         setattr(a, k, float(coef[k]))
     a.use_dynamic_rescale = int(coef["use_dynamic_rescale"])
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(lib.gvd_ddim_step(C.byref(a), _stream()), lib, "gvd_ddim_step")
     return x_prev, pred_x0
 
@@ -371,8 +419,8 @@ def linear_dx(dy, weight, alpha=1.0):
 _gn_bwd_tmp = {}
 
 
-def groupnorm_bwd(x, dy, gamma, beta, F, S, groups=32, eps=1e-5, silu=0):
-    """dx of `groupnorm` (same arguments); statistics are recomputed from x."""
+def groupnorm_bwd(x, dy, gamma, beta, F, S, groups=32, eps=1e-5, silu=0, stats=None):
+    """dx of `groupnorm` (same arguments); statistics are recomputed from x unless the forward's are handed in."""
     lib = _n.nn()
     Cc = x.shape[-1]
     x, dy = x.contiguous(), dy.contiguous()
@@ -384,9 +432,10 @@ def groupnorm_bwd(x, dy, gamma, beta, F, S, groups=32, eps=1e-5, silu=0):
     if tmp is None:
         tmp = _gn_bwd_tmp[key] = (torch.empty(nfl, dtype=torch.float32, device=x.device),
                                   torch.empty(nby // 8 + 1, dtype=torch.float64, device=x.device))
-    stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
-    _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S), int(Cc), int(groups), tmp[0].data_ptr(), nfl,
-                                      _stream()), lib, "gvd_groupnorm_cl_stats")
+    if stats is None:
+        stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
+        _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S), int(Cc), int(groups), tmp[0].data_ptr(), nfl,
+                                          _stream()), lib, "gvd_groupnorm_cl_stats")
     _check(lib.gvd_groupnorm_cl_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                     int(F), int(S), int(Cc), int(groups), float(eps), int(silu), tmp[1].data_ptr(), nby, _stream()),
            lib, "gvd_groupnorm_cl_bwd")
@@ -607,6 +656,6 @@ def ddim_pred_x0_vjp(e_cond, e_uncond, grad_pred_x0, coef):
     for key in ("cfg_scale", "guidance_rescale", "sqrt_alphas_cumprod_t", "sqrt_one_minus_alphas_cumprod_t", "scale_t", "scale_prev"):
         setattr(a, key, float(coef[key]))
     a.use_dynamic_rescale = int(coef["use_dynamic_rescale"])
-    with torch.cuda.device(e_cond.device):
+    with _on_device(e_cond.device):
         _check(lib.gvd_ddim_pred_x0_vjp(C.byref(a), _stream()), lib, "gvd_ddim_pred_x0_vjp")
     return dx, de_c, de_u
