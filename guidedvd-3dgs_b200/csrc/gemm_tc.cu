@@ -280,7 +280,125 @@ __device__ __forceinline__ void epi_convert32(const uint32_t (&v)[32], uint32_t 
     }
 }
 
-template <int BN_>
+// GELU for the fused GEGLU epilogue: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, two MUFU + ~12 FMA-pipe
+// instructions instead of erff's ~30), evaluated so that the negative tail keeps its relative accuracy:
+//   gelu(g) = g - 0.5 g q  (g >= 0),  0.5 g q  (g < 0),  q = erfc(|g| / sqrt 2) = poly(t) exp(-g^2 / 2),  t = 1 / (1 + p |g| / sqrt 2)
+__device__ __forceinline__ float gelu_fast(float g) {
+    const float y = fabsf(g) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, y, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float q = poly * t * __expf(-y * y);
+    const float hq = 0.5f * g * q;
+    return g >= 0.0f ? g - hq : hq;
+}
+
+// One epilogue warp's share of a 128 x BN_ accumulator tile: its TMEM lane quadrant q (32 rows) x one half of the columns.
+//   phase 1: TMEM -> registers -> alpha / bias / activation (reference rounding points) -> bf16 -> swizzled smem row `lane`
+//   phase 2: coalesced 16-byte write-out (+ residual, prefetched before the accumulator was ready)
+// GEGLU (act == GVD_ACT_GEGLU): the weight rows were interleaved in blocks of 16 ([16 value rows | 16 gate rows], see
+// vc_b200.ops.geglu_weight), so every 32 accumulator columns hold 16 values and their 16 gates; the warp writes
+// out[., n / 2 ..] = bf16(value) * bf16(gelu(bf16(gate))) -- GEGLU (attention.py:415-423) without the 2D-wide intermediate.
+// PAIR: the accumulator buffer is handed back to the LEADER CTA's MMA thread (cluster-scope arrive).
+template <int BN_, bool GEGLU, bool PAIR>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint8_t* stage, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                              uint32_t full_parity, uint64_t* tmem_empty_bar, uint32_t tmem_empty_cluster, int m0,
+                                              int n0, long long base_off, int buf, int q, int half, int lane, bool plain) {
+    constexpr int HALF = BN_ / 2;                       // accumulator columns of this warp
+    constexpr int OUT_HALF = GEGLU ? HALF / 2 : HALF;   // output columns of this warp
+    constexpr int ROW_BYTES = OUT_HALF * 2, CHUNKS = ROW_BYTES / 16;  // 16-byte chunks per staged row
+    constexpr int ROWS_PER_PASS = 32 / CHUNKS;
+    constexpr int SWZ = CHUNKS >= 8 ? 7 : CHUNKS - 1;
+    const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
+    const int n_out0 = GEGLU ? n0 / 2 : n0, n_lim = GEGLU ? p.N / 2 : p.N;
+    const int n = n_out0 + chunk * 8;
+    uint4 resv[32 / ROWS_PER_PASS];
+    if (!GEGLU && p.residual != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
+            const int m = m0 + q * 32 + i * ROWS_PER_PASS + rsub;
+            resv[i] = make_uint4(0, 0, 0, 0);
+            if (m < p.M && n < n_lim)
+                resv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + base_off +
+                                                               (long long)m * p.ldc + n));
+        }
+    }
+    tc::mbar_wait(tmem_full_bar, full_parity);
+    tc::fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + half * HALF);
+#pragma unroll 1
+    for (int c = 0; c < HALF; c += 32) {
+        if (n0 + c >= p.N) break;
+        uint32_t v[32], packed[16];
+        tc::tmem_ld32(taddr + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+        if (GEGLU) {
+            const int nb = n0 + c;  // 32 | nb; p.N % 32 == 0, so the block is whole
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                float o2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float a = __uint_as_float(v[j + e]) * p.alpha, g = __uint_as_float(v[16 + j + e]) * p.alpha;
+                    if (p.bias != nullptr) {
+                        a += p.bias[nb + j + e];
+                        g += p.bias[nb + 16 + j + e];
+                    }
+                    o2[e] = bf16r(a) * bf16r(gelu_fast(bf16r(g)));
+                }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(o2[0], o2[1]);
+                packed[j / 2] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int ch = c / 16 + k;
+                *reinterpret_cast<uint4*>(stage + lane * ROW_BYTES + ((ch ^ (lane & SWZ)) << 4)) =
+                    make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+            }
+        } else {
+            if (plain) epi_convert32<0>(v, packed, p, n0 + c);
+            else epi_convert32<1>(v, packed, p, n0 + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ch = c / 8 + k;
+                *reinterpret_cast<uint4*>(stage + lane * ROW_BYTES + ((ch ^ (lane & SWZ)) << 4)) =
+                    make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+            }
+        }
+    }
+    // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA thread
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_cluster(tmem_empty_cluster);
+        else tc::mbar_arrive(tmem_empty_bar);
+    }
+#pragma unroll
+    for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
+        const int rr = i * ROWS_PER_PASS + rsub;
+        const int m = m0 + q * 32 + rr;
+        if (m < p.M && n < n_lim) {
+            uint4 val = *reinterpret_cast<const uint4*>(stage + rr * ROW_BYTES + ((chunk ^ (rr & SWZ)) << 4));
+            const long long off = base_off + (long long)m * p.ldc + n;
+            if (!GEGLU && p.residual != nullptr) {
+                const uint4 rv = resv[i];
+                __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&val);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 af = __bfloat1622float2(a2[e]), rf = __bfloat1622float2(r2[e]);
+                    a2[e] = __floats2bfloat162_rn(af.x + rf.x, af.y + rf.y);
+                }
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = val;
+        }
+    }
+    __syncwarp();  // the staging rows are rewritten by the next tile
+}
+
+template <int BN_, bool GEGLU>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             EpiParams p, int tiles_m, int tiles_n, int total_tiles) {
@@ -397,79 +515,16 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int ew = warp - 2;
         const int q = warp & 3;      // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
         const int half = ew >> 2;    // which half of the tile's columns
-        constexpr int HALF = Cfg::HALF;
         uint8_t* stage = smem_epi + ew * Cfg::EPI_WARP_BYTES;
-        constexpr int ROW_BYTES = HALF * 2, CHUNKS = ROW_BYTES / 16;   // 16-byte chunks per staged row: 4 / 8 / 16
-        constexpr int ROWS_PER_PASS = 32 / CHUNKS;
-        constexpr int SWZ = CHUNKS >= 8 ? 7 : CHUNKS - 1;
         const bool plain = (p.act == GVD_ACT_NONE) && (p.bias2 == nullptr);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int z = tile / tiles_mn, r = tile - z * tiles_mn;
-            const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_ + half * HALF;
+            const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_ + half * Cfg::HALF;
             const int bh = z % p.batch_h, bb = z / p.batch_h;
             const int buf = it & 1;
-            // residual rows of this warp's sub-tile: issue the (coalesced) loads now, they land while the tile's
-            // MMAs are still running
-            const long long base_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h;
-            const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
-            const int n = n0 + chunk * 8;
-            uint4 resv[32 / ROWS_PER_PASS];
-            if (p.residual != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
-                    const int m = m0 + q * 32 + i * ROWS_PER_PASS + rsub;
-                    resv[i] = make_uint4(0, 0, 0, 0);
-                    if (m < p.M && n < p.N)
-                        resv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                                       base_off + (long long)m * p.ldc + n));
-                }
-            }
-            tc::mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
-            tc::fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + half * HALF);
-            // ---- phase 1: TMEM -> registers -> bf16 -> swizzled smem row `lane` ----
-#pragma unroll 1
-            for (int c = 0; c < HALF; c += 32) {
-                if (n0 + c >= p.N) break;
-                uint32_t v[32], packed[16];
-                tc::tmem_ld32(taddr + (uint32_t)c, v);
-                tc::tmem_ld_wait();
-                if (plain) epi_convert32<0>(v, packed, p, n0 + c);
-                else epi_convert32<1>(v, packed, p, n0 + c);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ch = c / 8 + k;
-                    *reinterpret_cast<uint4*>(stage + lane * ROW_BYTES + ((ch ^ (lane & SWZ)) << 4)) =
-                        make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-                }
-            }
-            // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
-            // ---- phase 2: coalesced write-out (+ residual), ROWS_PER_PASS rows per warp instruction ----
-#pragma unroll
-            for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
-                const int rr = i * ROWS_PER_PASS + rsub;
-                const int m = m0 + q * 32 + rr;
-                if (m < p.M && n < p.N) {
-                    uint4 val = *reinterpret_cast<const uint4*>(stage + rr * ROW_BYTES + ((chunk ^ (rr & SWZ)) << 4));
-                    const long long off = base_off + (long long)m * p.ldc + n;
-                    if (p.residual != nullptr) {
-                        const uint4 rv = resv[i];
-                        __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&val);
-                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 af = __bfloat1622float2(a2[e]), rf = __bfloat1622float2(r2[e]);
-                            a2[e] = __floats2bfloat162_rn(af.x + rf.x, af.y + rf.y);
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = val;
-                }
-            }
-            __syncwarp();  // the staging rows are rewritten by the next tile
+            epilogue_tile<BN_, GEGLU, false>(p, stage, tmem_base, &tmem_full[buf], (uint32_t)((it >> 1) & 1), &tmem_empty[buf], 0u, m0, n0,
+                                             (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h, buf, q, half, lane, plain);
         }
     }
     tc::fence_before_sync();
@@ -501,7 +556,7 @@ template <int BN_> struct P2Cfg {
     static constexpr int TMEM_COLS = 2 * BN_ <= 256 ? 256 : 512;
 };
 
-template <int BN_>
+template <int BN_, bool GEGLU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p,
                       int tiles_m, int tiles_n, int total_tiles) {
@@ -603,75 +658,17 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        constexpr int HALF = Cfg::HALF;
         uint8_t* stage = smem_epi + ew * Cfg::EPI_WARP_BYTES;
-        constexpr int ROW_BYTES = HALF * 2, CHUNKS = ROW_BYTES / 16;
-        constexpr int ROWS_PER_PASS = 32 / CHUNKS;
-        constexpr int SWZ = CHUNKS >= 8 ? 7 : CHUNKS - 1;
         const bool plain = (p.act == GVD_ACT_NONE) && (p.bias2 == nullptr);
         const uint32_t te0 = tc::mapa(tc::smem_u32(&tmem_empty[0]), 0), te1 = tc::mapa(tc::smem_u32(&tmem_empty[1]), 0);
         int it = 0;
         for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
             const int z = tile / tiles_mn, r = tile - z * tiles_mn;
-            const int m0 = (r / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (r % tiles_n) * BN_ + half * HALF;
+            const int m0 = (r / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (r % tiles_n) * BN_ + half * Cfg::HALF;
             const int bh = z % p.batch_h, bb = z / p.batch_h;
             const int buf = it & 1;
-            const long long base_off = (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h;
-            const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
-            const int n = n0 + chunk * 8;
-            uint4 resv[32 / ROWS_PER_PASS];
-            if (p.residual != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
-                    const int m = m0 + q * 32 + i * ROWS_PER_PASS + rsub;
-                    resv[i] = make_uint4(0, 0, 0, 0);
-                    if (m < p.M && n < p.N)
-                        resv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                                       base_off + (long long)m * p.ldc + n));
-                }
-            }
-            tc::mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
-            tc::fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + half * HALF);
-#pragma unroll 1
-            for (int c = 0; c < HALF; c += 32) {
-                if (n0 + c >= p.N) break;
-                uint32_t v[32], packed[16];
-                tc::tmem_ld32(taddr + (uint32_t)c, v);
-                tc::tmem_ld_wait();
-                if (plain) epi_convert32<0>(v, packed, p, n0 + c);
-                else epi_convert32<1>(v, packed, p, n0 + c);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ch = c / 8 + k;
-                    *reinterpret_cast<uint4*>(stage + lane * ROW_BYTES + ((ch ^ (lane & SWZ)) << 4)) =
-                        make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-                }
-            }
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster(buf ? te1 : te0);
-#pragma unroll
-            for (int i = 0; i < 32 / ROWS_PER_PASS; ++i) {
-                const int rr = i * ROWS_PER_PASS + rsub;
-                const int m = m0 + q * 32 + rr;
-                if (m < p.M && n < p.N) {
-                    uint4 val = *reinterpret_cast<const uint4*>(stage + rr * ROW_BYTES + ((chunk ^ (rr & SWZ)) << 4));
-                    const long long off = base_off + (long long)m * p.ldc + n;
-                    if (p.residual != nullptr) {
-                        const uint4 rv = resv[i];
-                        __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&val);
-                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 af = __bfloat1622float2(a2[e]), rf = __bfloat1622float2(r2[e]);
-                            a2[e] = __floats2bfloat162_rn(af.x + rf.x, af.y + rf.y);
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = val;
-                }
-            }
-            __syncwarp();
+            epilogue_tile<BN_, GEGLU, true>(p, stage, tmem_base, &tmem_full[buf], (uint32_t)((it >> 1) & 1), nullptr, buf ? te1 : te0, m0, n0,
+                                            (long long)bb * p.c_stride_b + (long long)bh * p.c_stride_h, buf, q, half, lane, plain);
         }
     }
     tc::fence_before_sync();
@@ -680,12 +677,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 1) tc::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN_>
+template <int BN_, bool GEGLU = false>
 cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int batch, cudaStream_t s) {
     using Cfg = P2Cfg<BN_>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN_, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -699,7 +696,7 @@ cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiP
     const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN_ - 1) / BN_;
     const long long total = (long long)tiles_m * tiles_n * batch;
     const int pairs = (int)(total < num_sms / 2 ? total : num_sms / 2);
-    gemm_bf16_pair_kernel<BN_><<<2 * pairs, P_THREADS, Cfg::SMEM, s>>>(ta, tb, p, tiles_m, tiles_n, (int)total);
+    gemm_bf16_pair_kernel<BN_, GEGLU><<<2 * pairs, P_THREADS, Cfg::SMEM, s>>>(ta, tb, p, tiles_m, tiles_n, (int)total);
     return cudaGetLastError();
 }
 
@@ -713,12 +710,12 @@ bool pair_enabled() {
     return on == 1;
 }
 
-template <int BN_>
+template <int BN_, bool GEGLU = false>
 cudaError_t launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int batch, cudaStream_t s) {
     using Cfg = PCfg<BN_>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_persistent_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_persistent_kernel<BN_, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -732,7 +729,7 @@ cudaError_t launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, cons
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN_ - 1) / BN_;
     const long long total = (long long)tiles_m * tiles_n * batch;
     const int grid = (int)(total < num_sms ? total : num_sms);
-    gemm_bf16_persistent_kernel<BN_><<<grid, P_THREADS, Cfg::SMEM, s>>>(ta, tb, p, tiles_m, tiles_n, (int)total);
+    gemm_bf16_persistent_kernel<BN_, GEGLU><<<grid, P_THREADS, Cfg::SMEM, s>>>(ta, tb, p, tiles_m, tiles_n, (int)total);
     return cudaGetLastError();
 }
 
@@ -809,6 +806,28 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         (reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) {
         g_nn_err = "gvd_gemm_bf16: operand strides must be multiples of 8 elements and bases 16-byte aligned";
         return 2;
+    }
+    if (a->act == GVD_ACT_GEGLU) {
+        const bool ok = !a->out_fp32 && !a->residual && !a->bias2 && !a->b_mn_major && (a->N % 32 == 0) && (a->ldc % 8 == 0) &&
+                        (a->batch_h == 1 || a->c_stride_h % 8 == 0) && (a->batch_b == 1 || a->c_stride_b % 8 == 0) &&
+                        (reinterpret_cast<uintptr_t>(a->C) % 16 == 0);
+        if (!ok) {
+            g_nn_err = "gvd_gemm_bf16: GVD_ACT_GEGLU needs N % 32 == 0, bf16 output with 16-byte aligned rows, no residual / bias2 / b_mn_major";
+            return 2;
+        }
+        CUtensorMap ga, gb;
+        EpiParams gp{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, nullptr, nullptr, a->alpha, a->act, 0,
+                     a->M, a->N, a->K, a->batch_h, 0, 0, 0, 0};
+        const int batch = a->batch_h * a->batch_b;
+        const bool pair = use_pair(a->M, a->N, a->K, batch, 256);
+        if (!make_tmap(&ga, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
+            !make_tmap(&gb, a->B, a->K, a->N, a->batch_h, a->batch_b, a->ldb, a->b_stride_h, a->b_stride_b, pair ? 128 : 256)) {
+            g_nn_err = "gvd_gemm_bf16: cuTensorMapEncodeTiled failed";
+            return 1;
+        }
+        cudaError_t e = pair ? launch_pair<256, true>(ga, gb, gp, batch, s) : launch_persistent<256, true>(ga, gb, gp, batch, s);
+        if (e != cudaSuccess) { g_nn_err = std::string("gvd_gemm_bf16 GEGLU launch: ") + cudaGetErrorString(e); return 1; }
+        return 0;
     }
     CUtensorMap ta, tb;
     EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,

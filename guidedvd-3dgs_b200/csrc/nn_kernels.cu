@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
             s += p[0];
             q += p[1];
         }
+        // the split entry points (gvd_groupnorm_cl_stats -> _apply) hand the folded sums over as floats: round here too, so
+        // the fused call and the split one normalise with the same bits (the guided tape must not change the forward)
+        s = (double)(float)s;
+        q = (double)(float)q;
         const double n = (double)stat_rows * cpg;  // rows behind the sums (> S when the sums were added up across shards)
         const double mean = s / n;
         const double var = fmax(q / n - mean * mean, 0.0);

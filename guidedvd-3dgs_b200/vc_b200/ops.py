@@ -18,7 +18,7 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 import gvd_native as _n  # noqa: E402
 
-ACT = {"none": 0, "silu": 1, "gelu": 2, "round_scale": 3}
+ACT = {"none": 0, "silu": 1, "gelu": 2, "round_scale": 3, "geglu": 4}
 BF16 = torch.bfloat16
 
 
@@ -185,6 +185,39 @@ def layernorm(x, gamma, beta, eps=1e-5):
     _check(lib.gvd_layernorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), x.numel() // Cc, int(Cc),
                              float(eps), _stream()), lib, "gvd_layernorm")
     return y
+
+
+FUSED_GEGLU = os.environ.get("GVD_FUSED_GEGLU", "1") != "0"  # A/B switch: 0 = projection GEMM, then the GEGLU kernel
+
+
+def geglu_weight(weight, bias):
+    """GEGLU projection `proj` [2D, K] (rows 0..D-1 values, D..2D-1 gates; attention.py:415-423) -> the row order the fused
+    epilogue wants: blocks of 32 rows = 16 value rows followed by the 16 gate rows of the same outputs (GVD_ACT_GEGLU).
+    Returns (weight', bias') or None when D is not a multiple of 16."""
+    N, K = weight.shape
+    D = N // 2
+    if N % 32 or D % 16:
+        return None
+    w = torch.stack([weight[:D].view(D // 16, 16, K), weight[D:].view(D // 16, 16, K)], dim=1).reshape(N, K).contiguous()
+    b = None
+    if bias is not None:
+        b = torch.stack([bias[:D].view(D // 16, 16), bias[D:].view(D // 16, 16)], dim=1).reshape(N).contiguous()
+    return w, b
+
+
+def linear_geglu(x, weight_il, bias_il):
+    """GEGLU(x) = (x W_v^T + b_v) * gelu(x W_g^T + b_g) as ONE tensor-core GEMM whose epilogue applies the gate: the 2D-wide
+    projection never reaches memory.  weight_il / bias_il from `geglu_weight`.  Inference only (the guided sampler's tape
+    keeps the projection for its backward and goes through `linear` + `geglu`)."""
+    K = x.shape[-1]
+    N = weight_il.shape[0]
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    out = torch.empty(M, N // 2, dtype=BF16, device=x.device)
+    gemm_raw(x2, weight_il, out, M, N, K, K, K, N // 2, bias=bias_il, act="geglu")
+    return out.reshape(*x.shape[:-1], N // 2)
 
 
 def geglu(h):

@@ -132,11 +132,15 @@ class _TBlock:
         self.attn2 = _Attn(p, pre + ".attn2", image_cross)
         self.n1, self.n2, self.n3 = p.norm(pre + ".norm1"), p.norm(pre + ".norm2"), p.norm(pre + ".norm3")
         self.ff1 = p.lin(pre + ".ff.net.0.proj")
+        self.ff1_il = ops.geglu_weight(*self.ff1)  # rows interleaved for the fused GEGLU epilogue (inference path)
         self.ff2 = p.lin(pre + ".ff.net.2")
 
     def ff(self, h):
         a = ops.layernorm(h, *self.n3)
-        g = ops.geglu(ops.linear(a, *self.ff1))
+        if self.ff1_il is not None and ops.FUSED_GEGLU and not ops._wants_grad(a):
+            g = ops.linear_geglu(a, *self.ff1_il)
+        else:
+            g = ops.geglu(ops.linear(a, *self.ff1))
         return ops.linear(g, *self.ff2, residual=h)
 
 

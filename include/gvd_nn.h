@@ -27,7 +27,11 @@ typedef struct CUstream_st* gvd_nn_stream_t; /* == cudaStream_t */
 
 enum {
     GVD_ACT_NONE = 0, GVD_ACT_SILU = 1, GVD_ACT_GELU = 2,
-    GVD_ACT_ROUND_SCALE = 3 /* C = bf16(bf16(acc) * alpha): the rounding points of `einsum(q,k) * scale` under autocast */
+    GVD_ACT_ROUND_SCALE = 3, /* C = bf16(bf16(acc) * alpha): the rounding points of `einsum(q,k) * scale` under autocast */
+    GVD_ACT_GEGLU = 4        /* fused GEGLU (attention.py:415-423): B's rows (and bias) interleaved in blocks of 16 --
+                                rows 32b..32b+15 = value rows 16b.., rows 32b+16..32b+31 = the gate rows of the same outputs;
+                                C[m, j] = bf16(value_j) * bf16(gelu(bf16(gate_j))) has N/2 columns (ldc >= N/2).  N % 32 == 0,
+                                bf16 output, no residual / bias2 */
 };
 
 /* Strided-batched bf16 GEMM on tcgen05 tensor cores (fp32 accumulation in TMEM):

@@ -76,6 +76,15 @@ class FakeNN:
         cdt = torch.float32 if a.out_fp32 else self.act
         Cv = view(a.C, M, N, a.ldc, a.c_stride_h, a.c_stride_b, cdt)
         acc = A @ B.transpose(-1, -2)
+        if a.act == 4:  # fused GEGLU: B's rows interleaved in blocks of 16 values | 16 gates; C has N / 2 columns
+            assert N % 32 == 0 and not a.residual and not a.bias2  # (out_fp32 is set when the tests run with fp32 activations)
+            y = acc * a.alpha
+            if a.bias:
+                y = y + self._f(a.bias, N)
+            y = self._rnd(y).view(bb, bh, M, N // 32, 2, 16)
+            out = self._rnd(y[..., 0, :] * self._rnd(torch.nn.functional.gelu(y[..., 1, :]))).reshape(bb, bh, M, N // 2)
+            view(a.C, M, N // 2, a.ldc, a.c_stride_h, a.c_stride_b, self.act).copy_(out.to(self.act))
+            return 0
         if a.act == 3:  # C = bf16(bf16(acc) * alpha)
             y = self._rnd(acc) * a.alpha
         else:

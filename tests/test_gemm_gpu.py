@@ -78,3 +78,29 @@ def test_mn_major_b_operand(M, N, K, ldb):
     ref = 0.5 * (A[..., :K].float() @ B[..., :N].float())
     err = (Cout[..., :N].float() - ref).abs().max().item()
     assert err <= ref.abs().max().item() / 128 + 1e-4, err
+
+
+@pytest.mark.parametrize("M,D,K", [(300, 1280, 320), (4096, 2560, 640), (1000, 5120, 1280), (130, 48, 64)])
+def test_fused_geglu_epilogue(M, D, K):
+    """GVD_ACT_GEGLU: projection GEMM with the gate applied in the epilogue (interleaved weight rows) against the
+    two-step route (GEMM, then gvd_geglu) on the same inputs.  Same accumulators and rounding points; the epilogue's GELU
+    uses a 1.5e-7 erf approximation, so a result may differ by one bf16 ulp where the gate's GELU sat on a rounding
+    boundary.  K >= 640 takes the CTA-pair kernel, K = 320 the one-CTA kernel."""
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(2 * D, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(2 * D, device="cuda", generator=g)
+    il = ops.geglu_weight(w, b)
+    assert il is not None
+    fused = ops.linear_geglu(x, *il)
+    two = ops.geglu(ops.linear(x, w, b))
+    assert fused.shape == two.shape == (M, D)
+    f, t = fused.float(), two.float()
+    ulp = 2.0 ** -7 * t.abs() + 1e-6
+    assert bool(((f - t).abs() <= ulp).all()), float(((f - t).abs() / ulp).max())
+    assert (fused != two).float().mean().item() < 0.01
+    ref = (x.float() @ w.float().T + b)
+    ref = ref[:, :D] * torch.nn.functional.gelu(ref[:, D:])
+    assert (f - ref).abs().max().item() <= 2.0 ** -6 * ref.abs().max().item() + 1e-3
