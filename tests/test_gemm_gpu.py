@@ -84,8 +84,8 @@ def test_mn_major_b_operand(M, N, K, ldb):
 def test_fused_geglu_epilogue(M, D, K):
     """GVD_ACT_GEGLU: projection GEMM with the gate applied in the epilogue (interleaved weight rows) against the
     two-step route (GEMM, then gvd_geglu) on the same inputs.  Same accumulators and rounding points; the epilogue's GELU
-    uses a 1.5e-7 erf approximation, so a result may differ by one bf16 ulp where the gate's GELU sat on a rounding
-    boundary.  K >= 640 takes the CTA-pair kernel, K = 320 the one-CTA kernel."""
+    uses a 1.5e-7 erf approximation, so where the gate's GELU sat on a rounding boundary its bf16 value moves by one ulp and
+    the product, rounded again, by up to two.  K >= 640 takes the CTA-pair kernel, K = 320 the one-CTA kernel."""
     from vc_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(M + D)
@@ -98,7 +98,7 @@ def test_fused_geglu_epilogue(M, D, K):
     two = ops.geglu(ops.linear(x, w, b))
     assert fused.shape == two.shape == (M, D)
     f, t = fused.float(), two.float()
-    ulp = 2.0 ** -7 * t.abs() + 1e-6
+    ulp = 2.0 * 2.0 ** -7 * t.abs() + 1e-6
     assert bool(((f - t).abs() <= ulp).all()), float(((f - t).abs() / ulp).max())
     assert (fused != two).float().mean().item() < 0.01
     ref = (x.float() @ w.float().T + b)
