@@ -40,8 +40,8 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 def _stream():
     """Current stream of the current device as a cudaStream_t (the raw-handle query: torch.cuda.current_stream() costs
     ~26 us per call, and an eager forward makes ~1 300 launches)."""
-    if _raw_stream is not None and torch.cuda.is_available():
-        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch._C._cuda_getDevice()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -68,3 +68,12 @@ for e in prof.events():
 print(f"# {what}: {tot / 1e3:.1f} ms of kernels, {sum(v[0] for v in agg.values())} launches")
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{t / 1e3:9.2f} ms x{c:5d} {100 * t / tot:5.1f}%  {n}")
+
+if len(sys.argv) > 2 and sys.argv[2] == "host":
+    # host side of the same step: wall time of issuing it (device left asynchronous) and a cProfile of the Python path
+    import cProfile, pstats, time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); step(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"# host: issue {1e3 * (t1 - t0):.1f} ms, drain {1e3 * (t2 - t1):.1f} ms")
+    pr = cProfile.Profile(); pr.enable(); step(); pr.disable(); torch.cuda.synchronize()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(30)
