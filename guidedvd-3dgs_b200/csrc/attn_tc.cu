@@ -365,7 +365,124 @@ __device__ __forceinline__ void softmax_tile(const FaParams& p, uint32_t tmem_ba
         }
     }
 
-template <bool POLY>
+// Generation 6 softmax: ONE pass over S per key block, chunk-pipelined.
+// ncu + tools/ubench_softmax_pipe.cu explain generations 2-5: a 128 x 128 block costs 1 024 clk of MUFU (16 ex2 / clk / SM)
+// AND ~1 024 clk of TMEM reads (64 KB of fp32 scores at the 64 B / clk the tensor memory delivers) against 512 clk of
+// MMA, and every earlier generation serialises the two: all of a thread's scores are loaded (and scanned for the row
+// maximum) before its first exponential.  Here the exponentials of a block run against the STALE running maximum, so
+// no separate maximum pass exists: chunk c + 1 (32 columns) is in flight from TMEM while chunk c is exponentiated, and the
+// block's own maximum is tracked on the side.  Only if it exceeds the running maximum by more than 2^8 (the bound that
+// keeps P inside bf16 / fp32 range; the first blocks of a row, then almost never) the warp redoes the block against the new
+// maximum after rescaling O and l.  The first block has no running maximum and takes a maximum pass first.
+__device__ __forceinline__ void softmax_tile_onepass(const FaParams& p, uint32_t tmem_base, uint32_t lane_off, uint32_t s_col,
+                                                     uint32_t p_col, uint32_t o_col, uint64_t* s_full, uint64_t* p_full,
+                                                     uint64_t* o_full, int nblk, int row, int lane, int b, int h) {
+    const float sl2 = p.scale * 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+        tc::mbar_wait(s_full, (uint32_t)(j & 1));
+        tc::fence_after_sync();
+        const int key0 = j * FA_BN;
+        const bool tail = key0 + FA_BN > p.Nk;
+        if (j == 0) {  // no running maximum yet: one maximum pass over the first block
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < FA_BN; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + lane_off + s_col + c, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (!tail || key0 + c + e < p.Nk) ? __uint_as_float(v[e]) : -INFINITY);
+            }
+            m_run = mx * sl2;
+        }
+        float m_blk, l_blk;
+        // exponentials of the block against `mref`; returns the block's own maximum (log2 units) and row sum
+        auto pass = [&](float mref) {
+            const float mneg = -mref;
+            float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+            uint32_t va[32], vb[32];
+            tc::tmem_ld32(tmem_base + lane_off + s_col, va);
+#pragma unroll
+            for (int c = 0; c < FA_BN; c += 32) {
+                uint32_t(&cur)[32] = ((c >> 5) & 1) ? vb : va;
+                uint32_t(&nxt)[32] = ((c >> 5) & 1) ? va : vb;
+                tc::tmem_ld_wait();                                                        // chunk c has landed
+                if (c + 32 < FA_BN) tc::tmem_ld32(tmem_base + lane_off + s_col + c + 32, nxt);  // chunk c + 1 in flight
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float x0 = __uint_as_float(cur[e]), x1 = __uint_as_float(cur[e + 1]);
+                    if (tail) {
+                        if (key0 + c + e >= p.Nk) x0 = -INFINITY;
+                        if (key0 + c + e + 1 >= p.Nk) x1 = -INFINITY;
+                    }
+                    mx0 = fmaxf(mx0, x0);
+                    mx1 = fmaxf(mx1, x1);
+                    const float p0 = ex2(fmaf(x0, sl2, mneg));
+                    const float p1 = ex2(fmaf(x1, sl2, mneg));
+                    l0 += p0;
+                    l1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st16(tmem_base + lane_off + p_col + c / 2, pk);
+            }
+            m_blk = fmaxf(mx0, mx1) * sl2;
+            l_blk = l0 + l1;
+        };
+        pass(m_run);
+        const bool grow = m_blk > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {  // warp-uniform: tcgen05.ld / st are warp-collective
+            float alpha = 1.0f;
+            if (grow) {
+                alpha = ex2(m_run - m_blk);
+                m_run = m_blk;
+                l_run *= alpha;
+            }
+            if (j > 0) {  // s_full(j) certified PV_{j-1}: O is quiescent
+#pragma unroll
+                for (int c = 0; c < FA_D; c += 16) {
+                    uint32_t o[16];
+                    tc::tmem_ld16(tmem_base + lane_off + o_col + c, o);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                    tmem_st16(tmem_base + lane_off + o_col + c, o);
+                }
+            }
+            pass(m_run);  // rows that did not grow recompute the same values
+        }
+        tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(p_full);
+        l_run += l_blk;
+    }
+    tc::mbar_wait(o_full, 0);
+    tc::fence_after_sync();
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
+#pragma unroll
+    for (int c = 0; c < FA_D; c += 32) {
+        uint32_t o[32];
+        tc::tmem_ld32(tmem_base + lane_off + o_col + c, o);
+        tc::tmem_ld_wait();
+        if (row < p.Nq) {
+#pragma unroll
+            for (int e8 = 0; e8 < 32; e8 += 8) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
+                *reinterpret_cast<uint4*>(dst + c + e8) = u;
+            }
+        }
+    }
+}
+
+template <int MODE>  // 0: generation 2; 1: with one exponential in four on the FMA pipe; 2: generation 6 (one pass)
 __global__ void __launch_bounds__(FA_THREADS, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                   const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
@@ -451,8 +568,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     } else {
         const int q = warp & 3;  // TMEM lane quadrant of this warp
-        softmax_tile<POLY>(p, tmem_base, (uint32_t)(q * 32) << 16, FA_S_COL, FA_P_COL, FA_O_COL, s_full, p_full, o_full, nblk,
-                           m0 + q * 32 + lane, lane, b, h);
+        if (MODE == 2)
+            softmax_tile_onepass(p, tmem_base, (uint32_t)(q * 32) << 16, FA_S_COL, FA_P_COL, FA_O_COL, s_full, p_full, o_full, nblk,
+                                 m0 + q * 32 + lane, lane, b, h);
+        else
+            softmax_tile<MODE == 1>(p, tmem_base, (uint32_t)(q * 32) << 16, FA_S_COL, FA_P_COL, FA_O_COL, s_full, p_full, o_full, nblk,
+                                    m0 + q * 32 + lane, lane, b, h);
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -460,42 +581,50 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 }
 
 
-// ---- generation 3: two softmax threads per query row ---------------------------------------------------------------
-// tools/ubench_softmax_pipe.cu (profiles/r02_ubench_softmax.txt) measured what bounds the softmax side: MUFU.EX2 runs at
-// 16 results / clk / SM, and the per-score instruction mix (max, ffma, ex2, fadd, pack/2) sustains only 12 results / clk /
-// SM with two warps per scheduler (what generation 2 has: 4 softmax warps x 2 CTAs), 16 with four.  A 128 x 128 block
-// holds 16 384 exponentials = 1 024 clk of MUFU against 512 clk of MMA, so with head dim 64 the tensor pipe cannot
-// exceed 50 % unless exponentials leave the MUFU.  This variant tries more softmax warps per scheduler -- measured
-// 4.45 ms against generation 2's 4.13 ms (the 96-register cap of 2 x 320 threads and the pair barrier cost more than the
-// extra warps bring), so generation 2 stays the default; selectable with GVD_FLASH=v3.
-// 8 softmax warps per CTA: warps w and w + 4 share a TMEM lane quadrant (hardware rule: warp id % 4) and split the
-// S row -- 64 score columns, 32 packed P columns and 32 O columns each.  The pair agrees on the row maximum through two
-// floats of shared memory and a 64-thread named barrier per key block; the row sums stay separate until the end.
-constexpr int FA3_THREADS = 64 + 8 * 32;
-constexpr int FA3_SMEM = FA_SMEM + 2 * 2 * 128 * 4;  // + pair exchange: [parity][half][row] floats
+// ---- generation 5: one CTA per SM, TWO query tiles in ping-pong, two softmax threads per row --------------------------
+// tools/ubench_softmax_pipe.cu (profiles/r02_ubench_softmax.txt): MUFU.EX2 runs at 16 results / clk / SM, so a 128 x 128
+// block holds 1 024 clk of exponentials against 512 clk of MMA -- with head dim 64 the tensor pipe cannot exceed 50 %
+// unless exponentials leave the MUFU -- and the per-score instruction mix sustains 7 / 12 / 16 results per clock per SM
+// with one / two / four softmax warps per scheduler.  Two intermediate designs were measured on B200 (N = 9216, 5 heads,
+// 25 frames; generation 2: 4.13 ms) and removed: 2 CTAs x 8 softmax warps, two threads per row (4.45 ms), and one
+// software-pipelined CTA with double-buffered S and 16 softmax warps, four threads per row (4.46 ms).  In both, all
+// softmax warps of a query tile move in lockstep (wait for S, TMEM load, row maximum, exchange, exponentials, TMEM store,
+// hand-over), so the latencies around the exponentials are exposed on every scheduler at once.  This generation is the
+// ping-pong form of the same idea (the structure FlashAttention-4 uses at head dim 128): one CTA owns two 128-row query tiles A
+// and B that share every K / V tile (fetched once, used by four MMAs): while A's warps are in their load / max / store
+// phases, B's are in their exponentials and vice versa, and the tensor pipe works for one tile while the MUFU works for
+// the other.  8 softmax warps per tile (two threads per row: 64 score columns each), so every scheduler holds two warps
+// of A and two of B.  MMA order per key block: PV_A, QK_A(next), PV_B, QK_B(next) -- each tile's next scores are
+// issued right behind its PV, as early as its S columns are free.
+// TMEM: S_A S_B | P_A P_B | O_A O_B = 128 + 128 + 64 + 64 + 64 + 64 = 512 columns.
+constexpr int FA5_THREADS = 64 + 16 * 32;
+constexpr int FA5_STAGES = 3;
+constexpr int FA5_BAR_OFF = FA_TILE_BYTES * (2 + 2 * FA5_STAGES);
+constexpr int FA5_XCHG_OFF = FA5_BAR_OFF + 256;
+constexpr int FA5_SMEM = FA5_XCHG_OFF + 2 * 2 * 2 * 128 * 4 + 1024;  // exchange: [tile][parity][half][row]
 
-__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+__device__ __forceinline__ void pair_sync_id(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(FA3_THREADS, 2)
-flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+__global__ void __launch_bounds__(FA5_THREADS, 1)  // 18 warps are allocated as 20: 96 registers per thread
+flash_attn5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sq = smem;
-    uint8_t* sk = smem + FA_TILE_BYTES;
-    uint8_t* sv = smem + FA_TILE_BYTES * (1 + FA_STAGES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
+    uint8_t* sq = smem;                                          // [2] query tiles
+    uint8_t* sk = smem + 2 * FA_TILE_BYTES;                      // [3]
+    uint8_t* sv = smem + FA_TILE_BYTES * (2 + FA5_STAGES);       // [3]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA5_BAR_OFF);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;              // [2]
-    uint64_t* kv_empty = bars + 3;             // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* o_full = bars + 7;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-    float* xchg = reinterpret_cast<float*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256);  // [2][2][128]
+    uint64_t* kv_full = bars + 1;    // [3]
+    uint64_t* kv_empty = bars + 4;   // [3]
+    uint64_t* s_full = bars + 7;     // [2] per tile
+    uint64_t* p_full = bars + 9;     // [2] per tile
+    uint64_t* o_full = bars + 11;    // [2] per tile
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+    float* xchg = reinterpret_cast<float*>(smem + FA5_XCHG_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int m0 = blockIdx.x * (2 * FA_BM), h = blockIdx.y, b = blockIdx.z;
     const int nblk = (p.Nk + FA_BN - 1) / FA_BN;
 
     if (warp == 0 && lane == 0) {
@@ -503,16 +632,18 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc::prefetch_tmap(&tmap_k);
         tc::prefetch_tmap(&tmap_v);
         tc::mbar_init(q_full, 1);
-        for (int s = 0; s < FA_STAGES; ++s) {
+        for (int s = 0; s < FA5_STAGES; ++s) {
             tc::mbar_init(&kv_full[s], 1);
             tc::mbar_init(&kv_empty[s], 1);
         }
-        tc::mbar_init(s_full, 1);
-        tc::mbar_init(p_full, 8);  // one arrival per softmax warp
-        tc::mbar_init(o_full, 1);
+        for (int t = 0; t < 2; ++t) {
+            tc::mbar_init(&s_full[t], 1);
+            tc::mbar_init(&p_full[t], 8);  // the tile's 8 softmax warps
+            tc::mbar_init(&o_full[t], 1);
+        }
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -520,11 +651,12 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            tc::mbar_expect_tx(q_full, FA_TILE_BYTES);
+            tc::mbar_expect_tx(q_full, 2 * FA_TILE_BYTES);
             tc::tma_load_4d(sq, &tmap_q, q_full, 0, m0, h, b);
+            tc::tma_load_4d(sq + FA_TILE_BYTES, &tmap_q, q_full, 0, m0 + FA_BM, h, b);
             for (int j = 0; j < nblk; ++j) {
-                const int s = j % FA_STAGES;
-                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA_STAGES) & 1) ^ 1));
+                const int s = j % FA5_STAGES;
+                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA5_STAGES) & 1) ^ 1));
                 tc::mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
                 tc::tma_load_4d(sk + s * FA_TILE_BYTES, &tmap_k, &kv_full[s], 0, j * FA_BN, h, b);
                 tc::tma_load_4d(sv + s * FA_TILE_BYTES, &tmap_v, &kv_full[s], 0, j * FA_BN, h, b);
@@ -535,62 +667,87 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const uint32_t idesc_qk = tc::make_idesc_bf16(FA_BM, FA_BN);
             const uint32_t idesc_pv = make_idesc_pv();
             const uint32_t q_addr = tc::smem_u32(sq);
-            tc::mbar_wait(q_full, 0);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j % FA_STAGES;
-                tc::mbar_wait(&kv_full[s], (uint32_t)((j / FA_STAGES) & 1));
-                tc::fence_after_sync();
-                const uint32_t k_addr = tc::smem_u32(sk + s * FA_TILE_BYTES);
+            auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T
+                const uint32_t k_addr = tc::smem_u32(sk + (j % FA5_STAGES) * FA_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < FA_D / 16; ++k)
-                    tc::umma_bf16(tmem_base + FA_S_COL, tc::make_desc_kmajor_sw128(q_addr + k * 32),
+                    tc::umma_bf16(tmem_base + (uint32_t)t * 128, tc::make_desc_kmajor_sw128(q_addr + t * FA_TILE_BYTES + k * 32),
                                   tc::make_desc_kmajor_sw128(k_addr + k * 32), idesc_qk, k != 0);
-                tc::umma_commit(s_full);  // also certifies PV_{j-1}: O is quiescent while the softmax warps rescale it
-                tc::mbar_wait(p_full, (uint32_t)(j & 1));
-                tc::fence_after_sync();
+                tc::umma_commit(&s_full[t]);
+            };
+            tc::mbar_wait(q_full, 0);
+            tc::mbar_wait(&kv_full[0], 0);
+            tc::fence_after_sync();
+            issue_qk(0, 0);
+            issue_qk(1, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA5_STAGES;
                 const uint32_t v_addr = tc::smem_u32(sv + s * FA_TILE_BYTES);
+                for (int t = 0; t < 2; ++t) {
+                    tc::mbar_wait(&p_full[t], (uint32_t)(j & 1));
+                    tc::fence_after_sync();
 #pragma unroll
-                for (int k = 0; k < FA_BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + FA_O_COL, tmem_base + FA_P_COL + k * 8,
-                                 tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (j | k) != 0);
-                tc::umma_commit(&kv_empty[s]);
+                    for (int k = 0; k < FA_BN / 16; ++k)
+                        umma_bf16_ts(tmem_base + 384 + (uint32_t)t * 64, tmem_base + 256 + (uint32_t)t * 64 + k * 8,
+                                     tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (j | k) != 0);
+                    if (t == 1) tc::umma_commit(&kv_empty[s]);  // K_j and V_j have no reader left
+                    if (j + 1 < nblk) {
+                        if (t == 0) {
+                            tc::mbar_wait(&kv_full[(j + 1) % FA5_STAGES], (uint32_t)(((j + 1) / FA5_STAGES) & 1));
+                            tc::fence_after_sync();
+                        }
+                        // S_t is free: the tile's softmax warps read it before they arrived on p_full(j); s_full(j+1) also
+                        // certifies PV_t(j), so O_t is quiescent while they rescale it
+                        issue_qk(t, j + 1);
+                    } else {
+                        tc::umma_commit(&o_full[t]);
+                    }
+                }
             }
-            tc::umma_commit(o_full);
         }
     } else {
-        const int q = warp & 3;             // TMEM lane quadrant
-        const int hf = (warp - 2) >> 2;     // which half of the row's columns
-        const int rloc = q * 32 + lane;     // row inside the tile
-        const int row = m0 + rloc;
+        const int sw = warp - 2;
+        const int t = sw >> 3;            // query tile
+        const int q = warp & 3;           // TMEM lane quadrant (hardware rule: warp id % 4)
+        const int hf = (sw >> 2) & 1;     // which half of the row's columns
+        const int rloc = q * 32 + lane;
+        const int row = m0 + t * FA_BM + rloc;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t s_col = FA_S_COL + 64 * hf, p_col = FA_P_COL + 32 * hf, o_col = FA_O_COL + 32 * hf;
+        const uint32_t s_col = (uint32_t)t * 128 + 64 * hf, p_col = 256 + (uint32_t)t * 64 + 32 * hf, o_col = 384 + (uint32_t)t * 64 + 32 * hf;
+        const int bar_id = 1 + t * 4 + q;
+        float* xt = xchg + t * 512;
         const float sl2 = p.scale * 1.4426950408889634f;
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < nblk; ++j) {
-            tc::mbar_wait(s_full, (uint32_t)(j & 1));
+            tc::mbar_wait(&s_full[t], (uint32_t)(j & 1));
             tc::fence_after_sync();
             const int key0 = j * FA_BN + 64 * hf;
-            uint32_t v[64];
-            tc::tmem_ld32(tmem_base + lane_off + s_col, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            tc::tmem_ld32(tmem_base + lane_off + s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-            tc::tmem_ld_wait();
-            if (key0 + 64 > p.Nk) {
-#pragma unroll
-                for (int e = 0; e < 64; ++e)
-                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
-            }
+            const bool tail = key0 + 64 > p.Nk;
+            // pass 1: row maximum of this thread's 64 scores.  The scores are read from TMEM again for the exponentials
+            // (S stays intact until p_full): holding all 64 would not fit the 96 registers 18 warps leave per thread.
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 64; e += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
-                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
-                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + lane_off + s_col + c, v);
+                tc::tmem_ld_wait();
+                if (tail) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (key0 + c + e >= p.Nk) v[e] = 0xff800000u;  // -inf
+                }
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+                    mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+                }
             }
             const float m_loc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            float* xb = xchg + (j & 1) * 256;
+            float* xb = xt + (j & 1) * 256;
             xb[hf * 128 + rloc] = m_loc;
-            pair_sync(q);
+            pair_sync_id(bar_id);
             const float m_blk = fmaxf(m_loc, xb[(hf ^ 1) * 128 + rloc]) * sl2;  // scale > 0: max commutes with it
             float m_new = m_run;
             if (j == 0) {
@@ -619,11 +776,17 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             float l0 = 0.f, l1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 64; c += 32) {
-                uint32_t pk[16];
+                uint32_t v[32], pk[16];
+                tc::tmem_ld32(tmem_base + lane_off + s_col + c, v);
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
-                    const float p0 = ex2(fmaf(__uint_as_float(v[c + e]), sl2, mneg));
-                    const float p1 = ex2(fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg));
+                    float p0 = ex2(fmaf(__uint_as_float(v[e]), sl2, mneg));
+                    float p1 = ex2(fmaf(__uint_as_float(v[e + 1]), sl2, mneg));
+                    if (tail) {
+                        if (key0 + c + e >= p.Nk) p0 = 0.f;
+                        if (key0 + c + e + 1 >= p.Nk) p1 = 0.f;
+                    }
                     l0 += p0;
                     l1 += p1;
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
@@ -634,16 +797,15 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             tmem_st_wait();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(p_full);
+            if (lane == 0) tc::mbar_arrive(&p_full[t]);
             l_run += l0 + l1;
             m_run = m_new;
         }
-        // the two halves of a row ran with the same maximum: their sums add
-        float* xb = xchg + (nblk & 1) * 256;
+        float* xb = xt + (nblk & 1) * 256;
         xb[hf * 128 + rloc] = l_run;
-        pair_sync(q);
+        pair_sync_id(bar_id);
         const float inv = 1.0f / (l_run + xb[(hf ^ 1) * 128 + rloc]);
-        tc::mbar_wait(o_full, 0);
+        tc::mbar_wait(&o_full[t], 0);
         tc::fence_after_sync();
         __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo + 32 * hf;
         uint32_t o[32];
@@ -663,7 +825,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() {
@@ -708,30 +870,34 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, v3 the third (two softmax threads per row);
-    // default: the second (one softmax thread per row; GVD_FLASH_POLY=1: one exponential in four on the FMA pipe).
-    // Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms, v2 with the polynomial 4.46 ms, v3 4.45 ms;
-    // a v2 variant with two query tiles ping-ponging inside one CTA per SM (8 softmax warps, all 512 TMEM columns) 4.20 ms.
+    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, v5 the two-tile ping-pong kernel, v6 the one-pass
+    // chunk-pipelined softmax; default: generation 2 (one softmax thread per row; GVD_FLASH_POLY=1: one exponential in four
+    // on the FMA pipe).  Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms, v2 with the polynomial
+    // 4.46 ms, v5 4.54 ms, v6 4.15 ms; removed variants: see the generation 5 comment.  None of the restructurings beats
+    // generation 2: DESIGN.md section 7 has the accounting (MUFU 1 024 clk + TMEM reads per 128 x 128 block vs 512 clk of MMA).
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("GVD_FLASH");
         const char* pe = getenv("GVD_FLASH_POLY");
         int want = (pe && pe[0] == '1') ? 2 : 1;
         if (v && v[0] == 'v' && v[1] == '1') want = 0;
-        else if (v && v[0] == 'v' && v[1] == '3') want = 3;
+        else if (v && v[0] == 'v' && v[1] == '5') want = 5;
+        else if (v && v[0] == 'v' && v[1] == '6') want = 6;
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
-                       : want == 1 ? (const void*)flash_attn_kernel<false>
-                       : want == 2 ? (const void*)flash_attn_kernel<true> : (const void*)flash_attn3_kernel;
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want == 3 ? FA3_SMEM : FA_SMEM);
+                       : want == 1 ? (const void*)flash_attn_kernel<0>
+                       : want == 2 ? (const void*)flash_attn_kernel<1>
+                       : want == 5 ? (const void*)flash_attn5_kernel : (const void*)flash_attn_kernel<2>;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want == 5 ? FA5_SMEM : FA_SMEM);
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
         variant = want;
     }
     FaParams p{reinterpret_cast<__nv_bfloat16*>(out), ld, 64, q_batch_stride, Nq, Nk, H, scale};
     dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
     if (variant == 0) flash_attn_v1_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
-    else if (variant == 1) flash_attn_kernel<false><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
-    else if (variant == 2) flash_attn_kernel<true><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
-    else flash_attn3_kernel<<<grid, FA3_THREADS, FA3_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 1) flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 2) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 5) flash_attn5_kernel<<<dim3((Nq + 2 * FA_BM - 1) / (2 * FA_BM), H, B), FA5_THREADS, FA5_SMEM, s>>>(tq, tk, tv, p);
+    else flash_attn_kernel<2><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }
     return 0;

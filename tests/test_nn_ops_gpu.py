@@ -222,3 +222,32 @@ def test_attention_paths(fn):
         q3.view(2, 700, H, 64)[..., 0] = 4.0
         k3.view(2, 700, H, 64)[..., 0] = (sign * 0.1 * torch.arange(700, device="cuda"))[None, :, None].to(BF)
         _close(attn(q3, k3, v2, 2, 700, 700, H, 0.125), ref32(q3, k3, v2), tol=1.0 / 64)
+
+
+@pytest.mark.parametrize("variant", ["v1", "v5", "v6"])
+def test_flash_attention_variants(variant):
+    """The A/B variants of gvd_flash_attention (GVD_FLASH, read once per process): first generation, two-tile ping-pong,
+    one-pass chunk-pipelined softmax -- each in its own process against fp32 attention, ragged sizes included."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, torch
+sys.path.insert(0, "guidedvd-3dgs_b200")
+from vc_b200 import ops
+g = torch.Generator(device="cuda").manual_seed(5)
+for (B, Nq, Nk, H) in ((3, 300, 300, 2), (2, 1000, 77, 5), (1, 129, 513, 1), (2, 2304, 2304, 3)):
+    q, k, v = (torch.randn(B, n, H * 64, device="cuda", generator=g).bfloat16() for n in (Nq, Nk, Nk))
+    k = k * 3.0  # logits spread over +-20: exercises the running-maximum updates
+    o = ops.flash_attention(q, k, v, B, Nq, Nk, H, 0.125).float().view(B, Nq, H, 64)
+    qh, kh, vh = (t.float().view(B, -1, H, 64).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).permute(0, 2, 1, 3)
+    err = (o - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1.5e-2, (B, Nq, Nk, H, err)
+print("ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GVD_FLASH=variant)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
