@@ -581,6 +581,215 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 }
 
 
+// ---- generation 7: key blocks split in two, S and P double-buffered, QK issued one sub-block ahead -------------------------
+// ncu source view of generation 2 (profiles/r02_ncu_flash_v2_stalls.txt): the hottest line of the kernel, 26 % of all
+// warp samples, is the softmax warps' wait for s_full.  The chain  softmax_j -> PV_j -> QK_{j+1} -> softmax_{j+1}  is
+// serial, the MMAs' issue-to-commit latency sits on it twice per key block, and the second CTA of the SM does not fill the
+// gaps (MUFU 59 % busy).  Here a 128-key tile is processed as two 64-key sub-blocks with two S buffers (64 columns each)
+// and two P buffers: the MMA thread issues QK of sub-block i + 1 BEFORE it waits for the probabilities of sub-block i, so
+// while the softmax warps exponentiate one half, the tensor pipe computes the scores of the next and the PV of the
+// previous.  Same TMEM budget as generation 2 (S0 S1 | P0 P1 | O = 64 + 64 + 32 + 32 + 64 = 256 columns, two CTAs per SM), same
+// shared-memory tiles (the sub-blocks are the two halves of the 128-key K / V tiles), one softmax thread per row.
+// PV_{i-1} is no longer certified by s_full(i), so the lazy O rescale waits on o_done (only when a row's maximum grew).
+constexpr uint32_t FA7_S_COL = 0, FA7_P_COL = 128, FA7_O_COL = 192;
+
+__device__ __forceinline__ uint32_t make_idesc_pv_k64() { return make_idesc_pv(); }  // same shape: M 128, N 64 (d); K per MMA is 16
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sq = smem;
+    uint8_t* sk = smem + FA_TILE_BYTES;
+    uint8_t* sv = smem + FA_TILE_BYTES * (1 + FA_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;    // [2]
+    uint64_t* kv_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;     // [2]
+    uint64_t* p_full = bars + 7;     // [2]
+    uint64_t* o_done = bars + 9;     // one completion per PV_i
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.Nk + FA_BN - 1) / FA_BN;   // 128-key tiles in shared memory
+    const int nsub = (p.Nk + 63) / 64;             // 64-key sub-blocks that hold at least one key
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_q);
+        tc::prefetch_tmap(&tmap_k);
+        tc::prefetch_tmap(&tmap_v);
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < FA_STAGES; ++s) {
+            tc::mbar_init(&kv_full[s], 1);
+            tc::mbar_init(&kv_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&s_full[s], 1);
+            tc::mbar_init(&p_full[s], 4);  // one arrival per softmax warp
+        }
+        tc::mbar_init(o_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(q_full, FA_TILE_BYTES);
+            tc::tma_load_4d(sq, &tmap_q, q_full, 0, m0, h, b);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA_STAGES) & 1) ^ 1));
+                tc::mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+                tc::tma_load_4d(sk + s * FA_TILE_BYTES, &tmap_k, &kv_full[s], 0, j * FA_BN, h, b);
+                tc::tma_load_4d(sv + s * FA_TILE_BYTES, &tmap_v, &kv_full[s], 0, j * FA_BN, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = tc::make_idesc_bf16(FA_BM, 64);
+            const uint32_t idesc_pv = make_idesc_pv_k64();
+            const uint32_t q_addr = tc::smem_u32(sq);
+            auto issue_qk = [&](int i) {  // S[i & 1] = Q K_i^T, K_i = rows 64 (i & 1) .. + 63 of tile i / 2
+                const int j = i >> 1, s = j % FA_STAGES;
+                if ((i & 1) == 0) {
+                    tc::mbar_wait(&kv_full[s], (uint32_t)((j / FA_STAGES) & 1));
+                    tc::fence_after_sync();
+                }
+                const uint32_t k_addr = tc::smem_u32(sk + s * FA_TILE_BYTES) + (uint32_t)(i & 1) * 64 * 128;
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k)
+                    tc::umma_bf16(tmem_base + FA7_S_COL + (uint32_t)(i & 1) * 64, tc::make_desc_kmajor_sw128(q_addr + k * 32),
+                                  tc::make_desc_kmajor_sw128(k_addr + k * 32), idesc_qk, k != 0);
+                tc::umma_commit(&s_full[i & 1]);
+            };
+            tc::mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int i = 0; i < nsub; ++i) {
+                // S[(i+1)&1] was last read by the softmax of sub-block i-1, which finished before p_full(i-1) completed --
+                // waited on in the previous iteration
+                if (i + 1 < nsub) issue_qk(i + 1);
+                tc::mbar_wait(&p_full[i & 1], (uint32_t)((i >> 1) & 1));
+                tc::fence_after_sync();
+                const int j = i >> 1, s = j % FA_STAGES;
+                const uint32_t v_addr = tc::smem_u32(sv + s * FA_TILE_BYTES) + (uint32_t)(i & 1) * 64 * 128;
+#pragma unroll
+                for (int k = 0; k < 64 / 16; ++k)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 smem rows of V
+                    umma_bf16_ts(tmem_base + FA7_O_COL, tmem_base + FA7_P_COL + (uint32_t)(i & 1) * 32 + k * 8,
+                                 tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (i | k) != 0);
+                tc::umma_commit(o_done);
+                if ((i & 1) || i + 1 == nsub) tc::umma_commit(&kv_empty[s]);  // the tile's last sub-block: K_j, V_j have no reader left
+            }
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quadrant of this warp
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int row = m0 + q * 32 + lane;
+        const float sl2 = p.scale * 1.4426950408889634f;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int i = 0; i < nsub; ++i) {
+            tc::mbar_wait(&s_full[i & 1], (uint32_t)((i >> 1) & 1));
+            tc::fence_after_sync();
+            const int key0 = i * 64;
+            uint32_t v[64];
+            tc::tmem_ld32(tmem_base + lane_off + FA7_S_COL + (uint32_t)(i & 1) * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tc::tmem_ld32(tmem_base + lane_off + FA7_S_COL + (uint32_t)(i & 1) * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tc::tmem_ld_wait();
+            if (key0 + 64 > p.Nk) {  // only the last sub-block can hold out-of-range keys
+#pragma unroll
+                for (int e = 0; e < 64; ++e)
+                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+            }
+            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;  // scale > 0: max commutes with it
+            float m_new = m_run;
+            if (i == 0) {
+                m_new = m_blk;
+            } else {
+                const bool grow = m_blk > m_run + 8.0f;
+                if (__any_sync(0xffffffffu, grow)) {  // warp-uniform: tcgen05.ld / st are warp-collective
+                    tc::mbar_wait(o_done, (uint32_t)((i - 1) & 1));  // PV_{i-1}: O is quiescent
+                    tc::fence_after_sync();
+                    float alpha = 1.0f;
+                    if (grow) {
+                        m_new = m_blk;
+                        alpha = ex2(m_run - m_new);
+                        l_run *= alpha;
+                    }
+#pragma unroll
+                    for (int c = 0; c < FA_D; c += 16) {
+                        uint32_t o[16];
+                        tc::tmem_ld16(tmem_base + lane_off + FA7_O_COL + c, o);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st16(tmem_base + lane_off + FA7_O_COL + c, o);
+                    }
+                }
+            }
+            const float mneg = -m_new;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const float p0 = ex2(fmaf(__uint_as_float(v[c + e]), sl2, mneg));
+                    const float p1 = ex2(fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg));
+                    l0 += p0;
+                    l1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st16(tmem_base + lane_off + FA7_P_COL + (uint32_t)(i & 1) * 32 + c / 2, pk);
+            }
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&p_full[i & 1]);
+            l_run += l0 + l1;
+            m_run = m_new;
+        }
+        tc::mbar_wait(o_done, (uint32_t)((nsub - 1) & 1));
+        tc::fence_after_sync();
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
+#pragma unroll
+        for (int c = 0; c < FA_D; c += 32) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem_base + lane_off + FA7_O_COL + c, o);
+            tc::tmem_ld_wait();
+            if (row < p.Nq) {
+#pragma unroll
+                for (int e8 = 0; e8 < 32; e8 += 8) {
+                    uint4 u;
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c + e8) = u;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 // ---- generation 5: one CTA per SM, TWO query tiles in ping-pong, two softmax threads per row --------------------------
 // tools/ubench_softmax_pipe.cu (profiles/r02_ubench_softmax.txt): MUFU.EX2 runs at 16 results / clk / SM, so a 128 x 128
 // block holds 1 024 clk of exponentials against 512 clk of MMA -- with head dim 64 the tensor pipe cannot exceed 50 %
@@ -870,23 +1079,26 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         g_nn_err_ext = "gvd_flash_attention: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    // A/B timing knobs: GVD_FLASH=v1 selects the first-generation kernel, v5 the two-tile ping-pong kernel, v6 the one-pass
-    // chunk-pipelined softmax; default: generation 2 (one softmax thread per row; GVD_FLASH_POLY=1: one exponential in four
-    // on the FMA pipe).  Measured on B200 (N = 9216, 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms, v2 with the polynomial
-    // 4.46 ms, v5 4.54 ms, v6 4.15 ms; removed variants: see the generation 5 comment.  None of the restructurings beats
-    // generation 2: DESIGN.md section 7 has the accounting (MUFU 1 024 clk + TMEM reads per 128 x 128 block vs 512 clk of MMA).
+    // Default: generation 7 (64-key sub-blocks, S / P double-buffered, QK one sub-block ahead).  A/B timing knobs:
+    // GVD_FLASH=v1 first generation, v2 second (one softmax thread per row, serial chain; GVD_FLASH_POLY=1: one exponential
+    // in four on the FMA pipe), v5 two-tile ping-pong, v6 one-pass chunk-pipelined softmax.  Measured on B200 (N = 9216,
+    // 5 heads, 25 frames): v1 5.03 ms, v2 4.13 ms (659 TFLOP/s), v2 + polynomial 4.46 ms, v5 4.54 ms, v6 4.15 ms,
+    // v7 3.35 ms (810 TFLOP/s).  DESIGN.md section 7 has the accounting.
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("GVD_FLASH");
         const char* pe = getenv("GVD_FLASH_POLY");
-        int want = (pe && pe[0] == '1') ? 2 : 1;
+        int want = 7;
         if (v && v[0] == 'v' && v[1] == '1') want = 0;
+        else if (v && v[0] == 'v' && v[1] == '2') want = (pe && pe[0] == '1') ? 2 : 1;
         else if (v && v[0] == 'v' && v[1] == '5') want = 5;
         else if (v && v[0] == 'v' && v[1] == '6') want = 6;
+        else if (v && v[0] == 'v' && v[1] == '7') want = 7;
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
                        : want == 1 ? (const void*)flash_attn_kernel<0>
                        : want == 2 ? (const void*)flash_attn_kernel<1>
-                       : want == 5 ? (const void*)flash_attn5_kernel : (const void*)flash_attn_kernel<2>;
+                       : want == 5 ? (const void*)flash_attn5_kernel
+                       : want == 6 ? (const void*)flash_attn_kernel<2> : (const void*)flash_attn7_kernel;
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want == 5 ? FA5_SMEM : FA_SMEM);
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
         variant = want;
@@ -897,7 +1109,8 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
     else if (variant == 1) flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 2) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 5) flash_attn5_kernel<<<dim3((Nq + 2 * FA_BM - 1) / (2 * FA_BM), H, B), FA5_THREADS, FA5_SMEM, s>>>(tq, tk, tv, p);
-    else flash_attn_kernel<2><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 6) flash_attn_kernel<2><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else flash_attn7_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
