@@ -595,6 +595,7 @@ constexpr uint32_t FA7_S_COL = 0, FA7_P_COL = 128, FA7_O_COL = 192;
 
 __device__ __forceinline__ uint32_t make_idesc_pv_k64() { return make_idesc_pv(); }  // same shape: M 128, N 64 (d); K per MMA is 16
 
+template <int POLY>  // 0: every exponential on the MUFU; n > 0: one in 2 n on the FMA pipe (Cody-Waite + cubic, ex2_fma)
 __global__ void __launch_bounds__(FA_THREADS, 2)
 flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
@@ -747,8 +748,9 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 uint32_t pk[16];
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
-                    const float p0 = ex2(fmaf(__uint_as_float(v[c + e]), sl2, mneg));
-                    const float p1 = ex2(fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg));
+                    const float x0 = fmaf(__uint_as_float(v[c + e]), sl2, mneg), x1 = fmaf(__uint_as_float(v[c + e + 1]), sl2, mneg);
+                    const float p0 = ex2(x0);
+                    const float p1 = (POLY > 0 && (e >> 1) % (POLY > 0 ? POLY : 1) == 0) ? ex2_fma(x1) : ex2(x1);  // one in 2 * POLY
                     l0 += p0;
                     l1 += p1;
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
@@ -1094,11 +1096,14 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         else if (v && v[0] == 'v' && v[1] == '5') want = 5;
         else if (v && v[0] == 'v' && v[1] == '6') want = 6;
         else if (v && v[0] == 'v' && v[1] == '7') want = 7;
+        if (want == 7 && pe && pe[0] >= '1' && pe[0] <= '3') want = 7 + (pe[0] - '0');  // 8: one exponential in 2 on the FMA pipe, 9: 1 in 4, 10: 1 in 8
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
                        : want == 1 ? (const void*)flash_attn_kernel<0>
                        : want == 2 ? (const void*)flash_attn_kernel<1>
                        : want == 5 ? (const void*)flash_attn5_kernel
-                       : want == 6 ? (const void*)flash_attn_kernel<2> : (const void*)flash_attn7_kernel;
+                       : want == 6 ? (const void*)flash_attn_kernel<2>
+                       : want == 8 ? (const void*)flash_attn7_kernel<1> : want == 9 ? (const void*)flash_attn7_kernel<2>
+                       : want == 10 ? (const void*)flash_attn7_kernel<4> : (const void*)flash_attn7_kernel<0>;
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want == 5 ? FA5_SMEM : FA_SMEM);
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
         variant = want;
@@ -1110,7 +1115,10 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
     else if (variant == 2) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 5) flash_attn5_kernel<<<dim3((Nq + 2 * FA_BM - 1) / (2 * FA_BM), H, B), FA5_THREADS, FA5_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 6) flash_attn_kernel<2><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
-    else flash_attn7_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 8) flash_attn7_kernel<1><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 9) flash_attn7_kernel<2><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 10) flash_attn7_kernel<4><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else flash_attn7_kernel<0><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
