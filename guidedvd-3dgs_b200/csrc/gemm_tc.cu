@@ -47,6 +47,7 @@ struct EpiParams {
     // implicit-GEMM convolution (gvd_conv_bf16): 0 = plain GEMM; 1 = 3x3 over (x, y) of a (c, x, y, frame) map;
     // 2 = 3 taps over the frame axis of a (c, pixel, frame, batch) map.  K block kb = (tap, 64-channel block).
     int conv_kind, conv_w, conv_cin;
+    int tma_group;  // k blocks requested per burst by the one-CTA kernel's producer (1 .. stages / 2)
 };
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
@@ -440,6 +441,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     if (warp == 0) {
         if (lane == 0) {
             int kc = 0;  // running k-block counter across tiles -> stage / phase
+            const int G = ST >= 6 ? p.tma_group : 1;  // bursts only where the ring is deep enough to keep MMAs fed meanwhile
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_mn, r = tile - z * tiles_mn;
                 const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN_;
@@ -459,27 +461,34 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     for (int tap = 0; tap < taps; ++tap) {
                         const int cx = p.conv_kind == 1 ? ax + dx : ax + tap * p.conv_w;
                         const int cy = p.conv_kind == 1 ? ay + dy : ay;
-                        for (int cc = 0; cc < p.conv_cin; cc += BK, kw += BK, ++kc) {
-                            const int s = kc % ST;
-                            tc::mbar_wait(&empty[s], (uint32_t)(((kc / ST) & 1) ^ 1));
-                            tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-                            tc::tma_load_4d(sa, &tmap_a, &full[s], cc, cx, cy, bb);
-                            tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kw, n0, 0, 0);
+                        for (int cc = 0; cc < p.conv_cin; cc += BK * G) {  // bursts of tma_group k blocks (see below)
+                            const int g_n = min(G, (p.conv_cin - cc) / BK);
+                            for (int g = 0; g < g_n; ++g) tc::mbar_wait(&empty[(kc + g) % ST], (uint32_t)((((kc + g) / ST) & 1) ^ 1));
+                            for (int g = 0; g < g_n; ++g, ++kc, kw += BK) {
+                                const int s = kc % ST;
+                                tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                                uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                                tc::tma_load_4d(sa, &tmap_a, &full[s], cc + g * BK, cx, cy, bb);
+                                tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kw, n0, 0, 0);
+                            }
                         }
                         if (++dx == 2) { dx = -1; ++dy; }
                     }
                     continue;
                 }
-                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
-                    const int s = kc % ST;
-                    const uint32_t ph = (uint32_t)((kc / ST) & 1);
-                    tc::mbar_wait(&empty[s], ph ^ 1u);
-                    tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-                    tc::tma_load_4d(sa, &tmap_a, &full[s], kb * BK, m0, bh, bb);
-                    if (p.b_mn) tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], n0, kb * BK, bh, bb);
-                    else tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], kb * BK, n0, bh, bb);
+                // k blocks are requested in bursts of G: the rows of an A tile are far apart in memory, and the
+                // 128-byte pieces a row contributes to consecutive k blocks reach DRAM together instead of 256 clk apart
+                for (int kb = 0; kb < num_kb; kb += G) {
+                    const int g_n = min(G, num_kb - kb);
+                    for (int g = 0; g < g_n; ++g) tc::mbar_wait(&empty[(kc + g) % ST], (uint32_t)((((kc + g) / ST) & 1) ^ 1));
+                    for (int g = 0; g < g_n; ++g, ++kc) {
+                        const int s = kc % ST, k0 = (kb + g) * BK;
+                        tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                        tc::tma_load_4d(sa, &tmap_a, &full[s], k0, m0, bh, bb);
+                        if (p.b_mn) tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], n0, k0, bh, bb);
+                        else tc::tma_load_4d(sa + Cfg::A_BYTES, &tmap_b, &full[s], k0, n0, bh, bb);
+                    }
                 }
             }
         }
@@ -601,6 +610,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             int kc = 0;
+            const int G = ST >= 6 ? p.tma_group : 1;
             for (int tile = pair; tile < total_tiles; tile += npairs) {
                 const int z = tile / tiles_mn, r = tile - z * tiles_mn;
                 const int m0 = (r / tiles_n) * (2 * BM) + (int)rank * BM, nb0 = (r % tiles_n) * BN_ + (int)rank * Cfg::BH;
@@ -616,15 +626,18 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 for (int tap = 0; tap < taps; ++tap) {
                     const int cx = p.conv_kind == 1 ? ax + dx : (p.conv_kind == 2 ? ax + tap * p.conv_w : m0);
                     const int cy = p.conv_kind == 1 ? ay + dy : bh;
-                    for (int cc = 0; cc < kper; cc += BK, kw += BK, ++kc) {
-                        const int s = kc % ST;
-                        tc::mbar_wait(&empty[s], (uint32_t)(((kc / ST) & 1) ^ 1));
-                        const uint32_t fb = tc::mapa(tc::smem_u32(&full[s]), 0);
-                        if (rank == 0) tc::mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
-                        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-                        tc::tma_load_4d_2cta(sa, &tmap_a, fb, cc, cx, cy, bb);
-                        if (p.conv_kind) tc::tma_load_4d_2cta(sa + Cfg::A_BYTES, &tmap_b, fb, kw, nb0, 0, 0);
-                        else tc::tma_load_4d_2cta(sa + Cfg::A_BYTES, &tmap_b, fb, kw, nb0, bh, bb);
+                    for (int cc = 0; cc < kper; cc += BK * G) {  // bursts of tma_group k blocks, as in the one-CTA kernel
+                        const int g_n = min(G, (kper - cc + BK - 1) / BK);
+                        for (int g = 0; g < g_n; ++g) tc::mbar_wait(&empty[(kc + g) % ST], (uint32_t)((((kc + g) / ST) & 1) ^ 1));
+                        for (int g = 0; g < g_n; ++g, ++kc, kw += BK) {
+                            const int s = kc % ST;
+                            const uint32_t fb = tc::mapa(tc::smem_u32(&full[s]), 0);
+                            if (rank == 0) tc::mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+                            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                            tc::tma_load_4d_2cta(sa, &tmap_a, fb, cc + g * BK, cx, cy, bb);
+                            if (p.conv_kind) tc::tma_load_4d_2cta(sa + Cfg::A_BYTES, &tmap_b, fb, kw, nb0, 0, 0);
+                            else tc::tma_load_4d_2cta(sa + Cfg::A_BYTES, &tmap_b, fb, kw, nb0, bh, bb);
+                        }
                     }
                     if (++dx == 2) { dx = -1; ++dy; }
                 }
@@ -780,6 +793,18 @@ bool make_tmap_mn(CUtensorMap* map, const void* base, long long N, long long K, 
 // When the CTA-pair kernel pays (B200, tools/bench_gemm_pair.py, profiles/r02_gemm_pair_sweep.txt): 256-wide tiles with
 // K >= 640 (+3 % at K = 640, +11-13 % at 1280-5120, +24 % at K = 11520); at K = 320 its per-tile cross-CTA hand-overs cost
 // 13-17 %, its 128-wide form loses everywhere, and few tiles leave the second wave of 74 pairs empty.
+// GVD_GEMM_TMA_GROUP: k blocks per producer burst.  Default 2: measured on B200 against 1 in the same process order
+// (tools/bench_gemm_pair.py, A streamed from HBM): M = 230400, N = 320: K = 1280 0.26-0.29 -> 0.25 ms, K = 2880 0.59 -> 0.53 ms;
+// M = 57600, N = 640, K = 5760 0.46-0.51 -> 0.44 ms; 3 is slightly behind 2.
+int tma_group() {
+    static int g = 0;
+    if (!g) {
+        const char* e = getenv("GVD_GEMM_TMA_GROUP");
+        g = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2;
+    }
+    return g;
+}
+
 bool use_pair(long long M, int N, int K, int batch, int bn) {
     if (!pair_enabled() || bn != 256 || K < 640) return false;
     const long long t128 = (M + 127) / 128, t256 = (M + 255) / 256, tn = (N + bn - 1) / bn;
@@ -817,7 +842,7 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         }
         CUtensorMap ga, gb;
         EpiParams gp{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, nullptr, nullptr, a->alpha, a->act, 0,
-                     a->M, a->N, a->K, a->batch_h, 0, 0, 0, 0};
+                     a->M, a->N, a->K, a->batch_h, 0, 0, 0, 0, tma_group()};
         const int batch = a->batch_h * a->batch_b;
         const bool pair = use_pair(a->M, a->N, a->K, batch, 256);
         if (!make_tmap(&ga, a->A, a->K, a->M, a->batch_h, a->batch_b, a->lda, a->a_stride_h, a->a_stride_b, BM) ||
@@ -831,7 +856,7 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
     }
     CUtensorMap ta, tb;
     EpiParams p{a->C, a->ldc, a->c_stride_h, a->c_stride_b, a->bias, a->bias2, a->residual, a->alpha, a->act, a->out_fp32,
-                a->M, a->N, a->K, a->batch_h, a->b_mn_major != 0, 0, 0, 0};
+                a->M, a->N, a->K, a->batch_h, a->b_mn_major != 0, 0, 0, 0, tma_group()};
     const bool aligned_out = !a->out_fp32 && (a->N % 8 == 0) && (a->ldc % 8 == 0) &&
                              (a->batch_h == 1 || a->c_stride_h % 8 == 0) && (a->batch_b == 1 || a->c_stride_b % 8 == 0) &&
                              (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) &&
@@ -963,7 +988,7 @@ int gvd_conv_bf16(const GvdConvArgs* a, gvd_nn_stream_t stream_) {
     if (!make_tmap(&tb, a->weight, Kw, N, 1, 1, Kw, 0, 0, pair ? bn / 2 : bn)) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the weight map"; return 1; }
     const long long ldc = N;
     EpiParams p{a->y, ldc, (long long)M * ldc, (long long)batch_h * M * ldc, a->bias, a->bias2, a->residual, 1.0f, a->act, 0,
-                (int)M, N, taps * kpt * BK, batch_h, 0, a->kind, a->kind == 1 ? a->W : (int)a->S, a->Cin};
+                (int)M, N, taps * kpt * BK, batch_h, 0, a->kind, a->kind == 1 ? a->W : (int)a->S, a->Cin, tma_group()};
     const int batch = batch_h * batch_b;
     cudaError_t e = pair ? launch_pair<256>(ta, tb, p, batch, s)
                   : bn == 256 ? launch_persistent<256>(ta, tb, p, batch, s)
