@@ -2,6 +2,13 @@
 // Mirrors the control flow of DGR/cuda_rasterizer/rasterizer_impl.cu:197-447 on an explicit stream;
 // no torch types, no allocation, no library kernels (the reference's CUB scan and radix sort are
 // replaced by the compaction / depth-sort / counting-sort kernels of raster_forward.cu).
+#ifndef GVD_HOST_EMU
+#include <nvtx3/nvToolsExt.h>
+#else  // host emulation (tests/cuda_emu): no profiler tools there
+static inline void nvtxRangePushA(const char*) {}
+static inline void nvtxRangePop() {}
+#endif
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -78,11 +85,30 @@ struct StageProfiler {
 };
 StageProfiler g_prof;
 
+// NVTX ranges around the same stages (GVD_NVTX=1; header-only nvtx3, resolved by the tools at run time): an nsys / ncu
+// timeline of train_*.py then shows "gvd:preprocess", "gvd:render_bwd", ... instead of anonymous kernel runs.
+static const char* const kStageNames[] = {"gvd:preprocess", "gvd:bin_count", "gvd:bin_fill", "gvd:depth_sort", "gvd:export_keys",
+                                          "gvd:render_fwd", "gvd:render_bwd", "gvd:gaussian_bwd"};
+static bool nvtx_on() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GVD_NVTX");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 struct StageScope {
     int h;
     cudaStream_t s;
-    StageScope(int st, cudaStream_t s_) : h(g_prof.begin(st, s_)), s(s_) {}
-    ~StageScope() { g_prof.finish(h, s); }
+    bool nv;
+    StageScope(int st, cudaStream_t s_) : h(g_prof.begin(st, s_)), s(s_), nv(nvtx_on()) {
+        if (nv) nvtxRangePushA(kStageNames[st < 8 ? st : 0]);
+    }
+    ~StageScope() {
+        if (nv) nvtxRangePop();
+        g_prof.finish(h, s);
+    }
 };
 
 template <typename T>
