@@ -280,6 +280,8 @@ int gvd_raster_forward(GvdRasterForwardArgs* a, gvd_stream_t stream_) {
         return fail_msg("gvd_raster_forward: the speculative path needs spec_hist_buffer and num_rendered_pinned");
     if (a->shs && (a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
         return fail_msg("gvd_raster_forward: SH degree / coefficient count mismatch");
+    if (a->raw_params && (!a->shs || !a->scales || !a->rotations || a->cov3D_precomp || a->colors_precomp || (a->M > 1 && !a->shs_rest)))
+        return fail_msg("gvd_raster_forward: raw_params needs shs (dc) + shs_rest, scales and rotations, and no precomputed covariance / colours");
 
     const int P = a->P;
     const float focal_y = a->height / (2.0f * a->tan_fovy);
@@ -411,6 +413,9 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
     if (a->scales && (!a->dL_dscales || !a->dL_drotations || !a->rotations))
         return fail_msg("gvd_raster_backward: scales given but dL_dscales/dL_drotations is null");
     if (!a->scales && !a->cov3D_precomp) return fail_msg("gvd_raster_backward: neither scales nor cov3D_precomp");
+    if (a->raw_params && (!a->shs || !a->scales || !a->opacities || a->cov3D_precomp || a->colors_precomp ||
+                          (a->M > 1 && (!a->shs_rest || !a->dL_dsh_rest))))
+        return fail_msg("gvd_raster_backward: raw_params needs shs (dc) + shs_rest + dL_dsh_rest, scales, rotations and the raw opacities");
 
     const int P = a->P;
     const float focal_y = a->height / (2.0f * a->tan_fovy);
@@ -449,7 +454,12 @@ int gvd_raster_backward(const GvdRasterBackwardArgs* a, gvd_stream_t stream_) {
         gvd_launch_zero_bytes(a->dL_dopacity, (size_t)P * 4, stream);
         if (a->dL_dcolors) gvd_launch_zero_bytes(a->dL_dcolors, (size_t)P * 3 * 4, stream);
         if (a->dL_dcov3D) gvd_launch_zero_bytes(a->dL_dcov3D, (size_t)P * 6 * 4, stream);
-        if (a->dL_dsh) gvd_launch_zero_bytes(a->dL_dsh, (size_t)P * M3 * 4, stream);
+        if (a->dL_dsh && a->raw_params) {  // two tensors: d/d_features_dc [P,1,3] and d/d_features_rest [P,M-1,3]
+            gvd_launch_zero_bytes(a->dL_dsh, (size_t)P * 3 * 4, stream);
+            if (a->dL_dsh_rest) gvd_launch_zero_bytes(a->dL_dsh_rest, (size_t)P * (M3 - 3) * 4, stream);
+        } else if (a->dL_dsh) {
+            gvd_launch_zero_bytes(a->dL_dsh, (size_t)P * M3 * 4, stream);
+        }
         if (a->dL_dscales) gvd_launch_zero_bytes(a->dL_dscales, (size_t)P * 3 * 4, stream);
         if (a->dL_drotations) gvd_launch_zero_bytes(a->dL_drotations, (size_t)P * 4 * 4, stream);
     }

@@ -319,7 +319,8 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
         o_sh[3 * (k) + 2] = _t.z * conf;            \
     }
 
-template <int MIN_CTAS, bool MOM>
+template <int MIN_CTAS, bool MOM, bool RAW>  // RAW: gradients with respect to the un-activated GaussianModel parameters (compile-time:
+                                             // the standard instantiation keeps the reference's expression trees)
 __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
     const SplatRec* __restrict__ splat, int W, int H, int D, int M, const float3* __restrict__ means, const uint32_t* __restrict__ vis_id, const uint32_t* __restrict__ counts,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float3* __restrict__ scales,
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
     float tan_fovy, const float3* __restrict__ campos, const float* __restrict__ acc,
     const float* __restrict__ confidence, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dmeans3D,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dcov3D,
-    float* __restrict__ dL_dsh, float* __restrict__ dL_dscales, float* __restrict__ dL_drots) {
+    float* __restrict__ dL_dsh, float* __restrict__ dL_dscales, float* __restrict__ dL_drots,
+    const float* __restrict__ shs_rest, const float* __restrict__ opacities_raw, float* __restrict__ dL_dsh_rest) {
     pdl_wait();
     pdl_trigger();
     // One thread per visible Gaussian, in ascending id order (vis_id comes from the forward's compaction), so the
@@ -372,7 +374,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
         if (cov3D_precomp != nullptr)
             cov3D = cov3D_precomp + 6 * (size_t)idx;
         else {
-            cov3d_from_scale_rot(scales[idx], scale_modifier, rotations[idx], cov3D_local);
+            if (RAW) cov3d_from_scale_rot(act_scale(scales[idx]), scale_modifier, act_rotation(rotations[idx]), cov3D_local);
+            else cov3d_from_scale_rot(scales[idx], scale_modifier, rotations[idx], cov3D_local);
             cov3D = cov3D_local;
         }
         const float3 mean = means[idx];
@@ -475,7 +478,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
             const float len = sqrtf(f3_dot(dir_orig, dir_orig));
             const float3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
             float v[48];
-            load_sh(shs, idx, D, M, v);
+            if (RAW) load_sh_split(shs, shs_rest, idx, D, M, v);
+            else load_sh(shs, idx, D, M, v);
             const uint8_t cl = clamped[idx];
             float3 dL_dRGB = dL_dcolor;
             dL_dRGB.x *= (cl & 1) ? 0 : 1;
@@ -554,12 +558,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
 
         // ---------------- cov3D backward (backward.cu:278-341) ----------------
         if (scales) {
-            const float4 q = rotations[idx];
+            const float4 q_in = rotations[idx];
+            const float4 q = RAW ? act_rotation(q_in) : q_in;
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
                            2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
                            2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-            const float3 sc = scales[idx];
+            const float3 sc = RAW ? act_scale(scales[idx]) : scales[idx];
             const float3 s = {scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z};
             M3 Mm;
     #pragma unroll
@@ -584,6 +589,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
             dscale.x = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
             dscale.y = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
             dscale.z = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
+            if (RAW) {  // d exp(s) / ds = exp(s)
+                dscale.x *= sc.x;
+                dscale.y *= sc.y;
+                dscale.z *= sc.z;
+            }
             o_sc = {dscale.x * conf, dscale.y * conf, dscale.z * conf};
 
     #pragma unroll
@@ -601,6 +611,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
                    2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
             dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
                    2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
+            if (RAW) dq = dnormvdv4(q_in, dq);  // through q / ||q||
             o_rot = make_float4(dq.x * conf, dq.y * conf, dq.z * conf, dq.w * conf);
         }
 
@@ -608,6 +619,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
         o_m2 = dL_dmean2D;  // not confidence-scaled (diff_gaussian_rasterization/__init__.py:149)
         o_m3 = {dL_dmean.x * conf, dL_dmean.y * conf, dL_dmean.z * conf};
         o_op = dL_dopac * conf;
+        if (RAW) {  // d sigmoid(o) / do = sigma (1 - sigma)
+            const float sg = act_opacity(opacities_raw[idx]);
+            o_op *= sg * (1.0f - sg);
+        }
         o_col = {dL_dcolor.x * conf, dL_dcolor.y * conf, dL_dcolor.z * conf};
 #pragma unroll
         for (int k = 0; k < 6; ++k) o_cov[k] = dcov[k] * conf;
@@ -635,7 +650,16 @@ __global__ void __launch_bounds__(256, MIN_CTAS) gaussian_backward_kernel(
 #pragma unroll
         for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = o_cov[k];
     }
-    if (dL_dsh) {
+    if (dL_dsh && RAW) {  // d/d_features_dc [P,1,3] and d/d_features_rest [P,M-1,3]: two tensors, no split afterwards
+        float* dc = dL_dsh + 3 * (size_t)idx;
+        dc[0] = o_sh[0];
+        dc[1] = o_sh[1];
+        dc[2] = o_sh[2];
+        float* row = dL_dsh_rest + (size_t)idx * 3 * (M - 1);
+#pragma unroll
+        for (int k = 3; k < 48; ++k)
+            if (k < 3 * M) row[k - 3] = o_sh[k];
+    } else if (dL_dsh) {
         float* row = dL_dsh + (size_t)idx * 3 * M;
         if (M == 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0)) {
             float4* r4 = reinterpret_cast<float4*>(row);  // one 192-byte row: six full sectors
@@ -739,18 +763,17 @@ static void launch_gaussian_backward(const GvdRasterBackwardArgs& a, const Raste
                                      float focal_x, float focal_y, int num_visible, cudaStream_t s) {
     const int n = num_visible >= 0 ? num_visible : a.P;  // V unknown on the host: cover P, surplus CTAs return at once
     if (n <= 0) return;
-    if (gvd_bwd_moments())
-        gvd_launch(gaussian_backward_kernel<MIN_CTAS, true>, dim3((n + 255) / 256), dim3(256), 0, s, g.splat, a.width, a.height,
+    auto go = [&](auto kernel) {
+        gvd_launch(kernel, dim3((n + 255) / 256), dim3(256), 0, s, g.splat, a.width, a.height,
             a.D, a.M, (const float3*)a.means3D, g.vis_id, g.counts, a.shs, g.clamped, (const float3*)a.scales,
             (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
             a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,
-            a.dL_dopacity, a.dL_dcolors, a.dL_dcov3D, a.dL_dsh, a.dL_dscales, a.dL_drotations);
-    else
-    gvd_launch(gaussian_backward_kernel<MIN_CTAS, false>, dim3((n + 255) / 256), dim3(256), 0, s, g.splat, a.width, a.height,
-        a.D, a.M, (const float3*)a.means3D, g.vis_id, g.counts, a.shs, g.clamped, (const float3*)a.scales,
-        (const float4*)a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
-        a.tan_fovx, a.tan_fovy, (const float3*)a.campos, acc, a.confidence, a.dL_dmeans2D, a.dL_dmeans3D,
-        a.dL_dopacity, a.dL_dcolors, a.dL_dcov3D, a.dL_dsh, a.dL_dscales, a.dL_drotations);
+            a.dL_dopacity, a.dL_dcolors, a.dL_dcov3D, a.dL_dsh, a.dL_dscales, a.dL_drotations, a.shs_rest,
+            a.opacities, a.dL_dsh_rest);
+    };
+    const bool mom = gvd_bwd_moments();
+    if (a.raw_params) mom ? go(gaussian_backward_kernel<MIN_CTAS, true, true>) : go(gaussian_backward_kernel<MIN_CTAS, false, true>);
+    else mom ? go(gaussian_backward_kernel<MIN_CTAS, true, false>) : go(gaussian_backward_kernel<MIN_CTAS, false, false>);
 }
 
 void gvd_launch_gaussian_backward(const GvdRasterBackwardArgs& a, const RasterGeomPtrs& g, const float* acc,

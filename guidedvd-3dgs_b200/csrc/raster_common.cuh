@@ -244,6 +244,40 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ shs, int idx, 
     }
 }
 
+// ---- GaussianModel activations (scene/gaussian_model.py:36-43), applied in-kernel when raw_params is set ----
+__device__ __forceinline__ float3 act_scale(float3 s) { return {expf(s.x), expf(s.y), expf(s.z)}; }            // torch.exp
+__device__ __forceinline__ float act_opacity(float o) { return 1.0f / (1.0f + expf(-o)); }                      // torch.sigmoid
+__device__ __forceinline__ float4 act_rotation(float4 q) {  // torch.nn.functional.normalize: q / max(||q||_2, 1e-12)
+    const float n = fmaxf(sqrtf((q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w)), 1e-12f);
+    return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+// Gradient through the normalisation (auxiliary.h:119-131, float4 form): dv of q / ||q||
+__device__ __forceinline__ float4 dnormvdv4(float4 v, float4 dv) {
+    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    const float4 vdv = {v.x * dv.x, v.y * dv.y, v.z * dv.z, v.w * dv.w};
+    const float vdv_sum = vdv.x + vdv.y + vdv.z + vdv.w;
+    float4 r;
+    r.x = ((sum2 - v.x * v.x) * dv.x - v.x * (vdv_sum - vdv.x)) * invsum32;
+    r.y = ((sum2 - v.y * v.y) * dv.y - v.y * (vdv_sum - vdv.y)) * invsum32;
+    r.z = ((sum2 - v.z * v.z) * dv.z - v.z * (vdv_sum - vdv.z)) * invsum32;
+    r.w = ((sum2 - v.w * v.w) * dv.w - v.w * (vdv_sum - vdv.w)) * invsum32;
+    return r;
+}
+// SH coefficients from the two parameter tensors (no [P,M,3] concatenation): coefficient 0 from _features_dc [P,1,3],
+// coefficients 1.. from _features_rest [P,M-1,3] (rows of 180 bytes at M = 16: scalar loads)
+__device__ __forceinline__ void load_sh_split(const float* __restrict__ dc, const float* __restrict__ rest, int idx, int deg,
+                                              int max_coeffs, float (&v)[48]) {
+    const int nfl = 3 * (deg + 1) * (deg + 1);
+    v[0] = __ldg(dc + 3 * (size_t)idx);
+    v[1] = __ldg(dc + 3 * (size_t)idx + 1);
+    v[2] = __ldg(dc + 3 * (size_t)idx + 2);
+    const float* row = rest + (size_t)idx * (max_coeffs - 1) * 3;
+#pragma unroll
+    for (int k = 3; k < 48; ++k)
+        if (k < nfl) v[k] = __ldg(row + k - 3);
+}
+
 // ---- programmatic dependent launch (sm_90+) --------------------------------------------------------------------
 // Every kernel of the forward/backward chain is launched with programmaticStreamSerialization: its CTAs may become
 // resident and run their prologue while the previous kernel of the stream drains. pdl_wait() -- the first statement

@@ -26,13 +26,15 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // forward.cu:20-71
 __device__ __forceinline__ float3 sh_to_rgb(int idx, int deg, int max_coeffs, const float3 pos, const float3 campos,
-                                            const float* __restrict__ shs, uint8_t* clamped_bits) {
+                                            const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                                            uint8_t* clamped_bits) {
     float3 dir = f3_sub(pos, campos);
     float len = sqrtf(f3_dot(dir, dir));
     dir = {dir.x / len, dir.y / len, dir.z / len};
 
     float v[48];
-    load_sh(shs, idx, deg, max_coeffs, v);
+    if (shs_rest != nullptr) load_sh_split(shs, shs_rest, idx, deg, max_coeffs, v);  // raw parameters: dc | rest
+    else load_sh(shs, idx, deg, max_coeffs, v);
 #define SH(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
     float3 result = f3_scale(GVD_SH_C0, SH(0));
     if (deg > 0) {
@@ -126,6 +128,8 @@ __device__ __forceinline__ void alpha_extent(const float3 conic, float opac, flo
 
 // One Gaussian of preprocessCUDA (forward.cu:155-256). Returns the number of tiles its rect covers; 0 = not rendered
 // (near-culled, degenerate covariance or empty rect), in which case nothing but radii = 0 has been written.
+template <bool RAW>  // RAW: un-activated GaussianModel parameters (compile-time, so the standard instantiation keeps the
+                      // reference's expression trees -- and with them nvcc's FMA contraction -- untouched)
 __device__ __forceinline__ uint32_t preprocess_one(
     int idx, int D, int M, const float* __restrict__ orig_points, const float3* __restrict__ scales,
     const float scale_modifier, const float4* __restrict__ rotations, const float* __restrict__ opacities,
@@ -133,7 +137,8 @@ __device__ __forceinline__ uint32_t preprocess_one(
     const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
     const float* __restrict__ projmatrix, const float3* __restrict__ cam_pos, const int W, int H,
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
-    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ depth_key, int prefiltered, int no_cull) {
+    SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ depth_key, int prefiltered, int no_cull,
+    const float* __restrict__ shs_rest) {
     radii[idx] = 0;
 
     // near cull (auxiliary.h:139-164): only p_view.z <= 0.2 rejects.
@@ -156,7 +161,9 @@ __device__ __forceinline__ uint32_t preprocess_one(
     if (cov3D_precomp != nullptr) {
         cov3D = cov3D_precomp + (size_t)idx * 6;
     } else {
-        cov3d_from_scale_rot(scales[idx], scale_modifier, rotations[idx], cov3D_local);
+        // RAW: the GaussianModel activations happen here (gaussian_renderer/__init__.py:60-87 does them as torch launches)
+        if (RAW) cov3d_from_scale_rot(act_scale(scales[idx]), scale_modifier, act_rotation(rotations[idx]), cov3D_local);
+        else cov3d_from_scale_rot(scales[idx], scale_modifier, rotations[idx], cov3D_local);
         cov3D = cov3D_local;
     }
 
@@ -179,7 +186,7 @@ __device__ __forceinline__ uint32_t preprocess_one(
     float3 rgb;
     if (colors_precomp == nullptr) {
         uint8_t cl;
-        rgb = sh_to_rgb(idx, D, M, p_orig, *cam_pos, shs, &cl);
+        rgb = sh_to_rgb(idx, D, M, p_orig, *cam_pos, shs, RAW ? shs_rest : nullptr, &cl);
         clamped[idx] = cl;
     } else {
         rgb = {colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]};
@@ -190,9 +197,10 @@ __device__ __forceinline__ uint32_t preprocess_one(
 
     SplatRec rec;
     rec.a = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-    rec.b = make_float4(conic.z, opacities[idx], rgb.x, rgb.y);
+    const float opac = RAW ? act_opacity(opacities[idx]) : opacities[idx];
+    rec.b = make_float4(conic.z, opac, rgb.x, rgb.y);
     float hx, hy;
-    alpha_extent(conic, opacities[idx], hx, hy);
+    alpha_extent(conic, opac, hx, hy);
     if (no_cull) hx = hy = 1e30f;  // GVD_NO_SUBTILE_CULL=1: every warp visits every instance of its tile (A/B and diagnosis knob)
     rec.c = make_float4(rgb.z, p_view.z, hx, hy);
     rec.d = make_float4(__uint_as_float(rect_min.x | (rect_min.y << 16)), __uint_as_float(rect_max.x | (rect_max.y << 16)),
@@ -204,6 +212,7 @@ __device__ __forceinline__ uint32_t preprocess_one(
 // Per Gaussian: preprocess_one. Per CTA: how many of its Gaussians are rendered and how many (Gaussian, tile) instances
 // they make -- the compaction kernel turns these into offsets, V and R (R is therefore known ~40 us into the frame,
 // long before the instance list is needed). On the side the grid clears the depth sort's digit histograms.
+template <bool RAW>
 __global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
     int P, int D, int M, const float* __restrict__ orig_points, const float3* __restrict__ scales,
     const float scale_modifier, const float4* __restrict__ rotations, const float* __restrict__ opacities,
@@ -213,7 +222,8 @@ __global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
     const float tan_fovx, float tan_fovy, const float focal_x, float focal_y, int* __restrict__ radii,
     SplatRec* __restrict__ splat, const dim3 grid, uint32_t* __restrict__ tiles_touched,
     uint32_t* __restrict__ depth_key, uint32_t* __restrict__ blk_vis, uint32_t* __restrict__ blk_tiles,
-    uint32_t* __restrict__ zeroed, size_t zeroed_words, int prefiltered, int no_cull) {
+    uint32_t* __restrict__ zeroed, size_t zeroed_words, int prefiltered, int no_cull,
+    const float* __restrict__ shs_rest) {
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t warp_tiles[GVD_PRE_BLOCK / 32];
@@ -221,9 +231,9 @@ __global__ void __launch_bounds__(GVD_PRE_BLOCK) preprocess_kernel(
     for (size_t i = (size_t)idx; i < zeroed_words; i += (size_t)gridDim.x * GVD_PRE_BLOCK) zeroed[i] = 0u;
     uint32_t tiles = 0;
     if (idx < P) {
-        tiles = preprocess_one(idx, D, M, orig_points, scales, scale_modifier, rotations, opacities, shs, clamped, cov3D_precomp,
+        tiles = preprocess_one<RAW>(idx, D, M, orig_points, scales, scale_modifier, rotations, opacities, shs, clamped, cov3D_precomp,
                                colors_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y, radii,
-                               splat, grid, depth_key, prefiltered, no_cull);
+                               splat, grid, depth_key, prefiltered, no_cull, shs_rest);
         tiles_touched[idx] = tiles;
     }
     const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
@@ -978,11 +988,20 @@ void gvd_launch_preprocess(const GvdRasterForwardArgs& a, const RasterGeomPtrs& 
         const char* e = getenv("GVD_NO_SUBTILE_CULL");
         no_cull = (e && e[0] == '1') ? 1 : 0;
     }
-    gvd_launch(preprocess_kernel, dim3((unsigned)so.nb), dim3(GVD_PRE_BLOCK), 0, s,
-        a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
-        a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
-        (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
-        g.tiles_touched, so.depth_key, so.blk_vis, so.blk_tiles, so.zeroed, so.zeroed_words, a.prefiltered, no_cull);
+    if (a.raw_params)
+        gvd_launch(preprocess_kernel<true>, dim3((unsigned)so.nb), dim3(GVD_PRE_BLOCK), 0, s,
+            a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
+            a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
+            (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
+            g.tiles_touched, so.depth_key, so.blk_vis, so.blk_tiles, so.zeroed, so.zeroed_words, a.prefiltered, no_cull,
+            a.shs_rest);
+    else
+        gvd_launch(preprocess_kernel<false>, dim3((unsigned)so.nb), dim3(GVD_PRE_BLOCK), 0, s,
+            a.P, a.D, a.M, a.means3D, (const float3*)a.scales, a.scale_modifier, (const float4*)a.rotations,
+            a.opacities, a.shs, g.clamped, a.cov3D_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix,
+            (const float3*)a.campos, a.width, a.height, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g.splat, grid,
+            g.tiles_touched, so.depth_key, so.blk_vis, so.blk_tiles, so.zeroed, so.zeroed_words, a.prefiltered, no_cull,
+            a.shs_rest);
 }
 
 void gvd_launch_compact(int P, const RasterGeomPtrs& g, const RasterSortPtrs& so, int* r_host, cudaStream_t s) {

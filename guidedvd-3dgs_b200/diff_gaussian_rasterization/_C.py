@@ -255,12 +255,14 @@ _scratch_sizes = {}
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, defer=False, force_defer=False):
+                        prefiltered, debug, defer=False, force_defer=False, sh_rest=None):
     """-> (num_rendered, out_color, out_depth, out_alpha, radii, geomBuffer, binningBuffer, imgBuffer)
 
     defer=True (used by the autograd Function): under GVD_SPECULATE=defer num_rendered may come back as a PendingR, see
     DEFER above.  force_defer=True: always (when a history exists) -- for callers that validate a whole batch of frames
-    themselves before anybody sees them (rasterize_views)."""
+    themselves before anybody sees them (rasterize_views).
+    sh_rest (B200 extension): when given, `scales`, `rotations`, `opacity` are the RAW GaussianModel
+    parameters and `sh` / `sh_rest` are `_features_dc` / `_features_rest`; the kernels apply the activations."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     lib = _n.raster()
@@ -284,6 +286,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     viewmatrix = _f32c(viewmatrix, "viewmatrix")
     projmatrix = _f32c(projmatrix, "projmatrix")
     sh = _f32c(sh, "sh")
+    sh_rest = _f32c(sh_rest, "sh_rest")
     campos = _f32c(campos, "campos")
 
     sizes = _scratch_sizes.get((P, W, H))
@@ -305,6 +308,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
         a = _n.RasterForwardArgs()
         a.P, a.D, a.M, a.width, a.height = P, int(degree), (sh.size(1) if sh is not None and sh.numel() else 0), W, H
+        if sh_rest is not None:  # raw parameters: M counts the coefficients of both tensors
+            a.M = 1 + sh_rest.size(1)
+            a.raw_params, a.shs_rest = 1, _ptr(sh_rest)
         a.background = _ptr(background)
         a.means3D = _ptr(means3D)
         a.shs = _ptr(sh)
@@ -406,7 +412,7 @@ def _grad_views(flat, P, M, has_sh, has_scales, has_colors, has_cov):
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_depth, dL_dout_alpha, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                 imageBuffer, alphas, debug, confidence=None):
+                                 imageBuffer, alphas, debug, confidence=None, sh_rest=None, opacity_raw=None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
 
     Extra trailing `confidence` ([P,1] or [P]): when given, every gradient except dL_dmeans2D is
@@ -417,6 +423,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if sh is not None and sh.numel() else 0
+    raw = sh_rest is not None
+    if raw:
+        M = 1 + sh_rest.size(1)
     has_sh = M > 0
     has_scales = scales is not None and scales.numel() > 0
     has_cov = cov3D_precomp is not None and cov3D_precomp.numel() > 0
@@ -462,6 +471,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         viewmatrix = _f32c(viewmatrix, "viewmatrix")
         projmatrix = _f32c(projmatrix, "projmatrix")
         sh = _f32c(sh, "sh")
+        sh_rest = _f32c(sh_rest, "sh_rest")
+        opacity_raw = _f32c(opacity_raw, "opacity_raw")
         campos = _f32c(campos, "campos")
         dL_dout_color = _f32c(dL_dout_color, "dL_dout_color")
         dL_dout_depth = _f32c(dL_dout_depth, "dL_dout_depth")
@@ -489,9 +500,17 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         a.dL_dcolors, a.dL_dcov3D, a.dL_dsh = _ptr(dL_dcolors), _ptr(dL_dcov3D), _ptr(dL_dsh)
         a.dL_dscales, a.dL_drotations = _ptr(dL_dscales), _ptr(dL_drotations)
         a.debug = int(bool(debug))
+        if raw:
+            # the [P, M, 3] gradient region holds d/d_features_dc [P,1,3] followed by d/d_features_rest [P,M-1,3]
+            flat_sh = dL_dsh.view(-1)
+            dL_dsh, dL_dsh_rest = flat_sh[:P * 3].view(P, 1, 3), flat_sh[P * 3:].view(P, M - 1, 3)
+            a.raw_params, a.shs_rest, a.opacities = 1, _ptr(sh_rest), _ptr(opacity_raw)
+            a.dL_dsh, a.dL_dsh_rest = dL_dsh.data_ptr(), dL_dsh_rest.data_ptr()
         rc = lib.gvd_raster_backward(C.byref(a), _stream(dev))
     if rc != 0:
         raise RuntimeError("gvd_raster_backward failed: " + _n.last_error(lib))
+    if raw:
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, (dL_dsh, dL_dsh_rest), dL_dscales, dL_drotations
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 

@@ -114,6 +114,56 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_rotations, grad_cov3Ds_precomp, None, None)
 
 
+class _RasterizeGaussiansRaw(torch.autograd.Function):
+    """B200 extension: the rasterizer over the RAW GaussianModel parameters.  gaussian_renderer.render()
+    activates them with four torch launches and concatenates the SH tensors into a fresh [P,16,3] (96 MB at 500 k
+    Gaussians) on every call (gaussian_renderer/__init__.py:60-87, scene/gaussian_model.py:106-130), and autograd
+    replays all of it backwards; here `preprocess` applies exp / normalize / sigmoid and reads `_features_dc` and
+    `_features_rest` where they lie, and `gaussian_backward` returns the gradients with respect to the raw parameters
+    (two SH gradient tensors, no split)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, raster_settings):
+        rs = raster_settings
+        absent = torch.Tensor([])
+        out = _C.rasterize_gaussians(rs.bg, means3D, absent, opacity_raw, scaling_raw, rotation_raw, rs.scale_modifier, absent,
+                                     rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width,
+                                     features_dc, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug, sh_rest=features_rest)
+        num_rendered, color, depth, alpha, radii, geomBuffer, binningBuffer, imgBuffer = out
+        ctx.raster_settings, ctx.num_rendered = rs, num_rendered
+        ctx.save_for_backward(means3D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, radii, geomBuffer,
+                              binningBuffer, imgBuffer, alpha)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        rs = ctx.raster_settings
+        (means3D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, radii, geomBuffer, binningBuffer,
+         imgBuffer, alpha) = ctx.saved_tensors
+        conf = rs.confidence
+        if conf is not None and conf.numel() != means3D.size(0):
+            raise RuntimeError("confidence must hold one value per Gaussian")
+        absent = torch.Tensor([])
+        out = _C.rasterize_gaussians_backward(rs.bg, means3D, radii, absent, scaling_raw, rotation_raw, rs.scale_modifier, absent,
+                                              rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_color, grad_depth,
+                                              grad_alpha, features_dc, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered,
+                                              binningBuffer, imgBuffer, alpha, rs.debug, confidence=conf,
+                                              sh_rest=features_rest, opacity_raw=opacity_raw)
+        grad_means2D, _, grad_opacity, grad_means3D, _, (grad_dc, grad_rest), grad_scales, grad_rotations = out
+        return (grad_means3D, grad_means2D, grad_dc, grad_rest, grad_opacity.view_as(opacity_raw), grad_scales, grad_rotations,
+                None)
+
+
+def rasterize_gaussians_raw(means3D, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw,
+                            raster_settings):
+    """-> (color[3,H,W], radii[P], depth[1,H,W], alpha[1,H,W]) from the un-activated parameters: equal to
+    GaussianRasterizer(raster_settings)(means3D, means2D, sigmoid(opacity_raw), shs=cat(features_dc, features_rest),
+    scales=exp(scaling_raw), rotations=normalize(rotation_raw)) up to the rounding of the normalisation."""
+    return _RasterizeGaussiansRaw.apply(means3D, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw,
+                                        raster_settings)
+
+
 def rasterize_views(settings_list, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                     cov3D_precomp=None):
     """B200 extension: forward-only render of MANY views of one Gaussian set -- the 25-75 trajectory

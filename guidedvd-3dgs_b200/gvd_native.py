@@ -31,6 +31,7 @@ class RasterForwardArgs(C.Structure):
         ("spec_hist_buffer", C.c_void_p), ("spec_hist_bytes", C.c_size_t),
         ("num_rendered_pinned", C.c_void_p), ("r_ready_event", C.c_void_p),
         ("num_rendered", C.c_int), ("num_visible", C.c_int),
+        ("raw_params", C.c_int), ("shs_rest", C.c_void_p),
     ]
 
 
@@ -52,6 +53,7 @@ class RasterBackwardArgs(C.Structure):
         ("dL_dcolors", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
         ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
         ("debug", C.c_int),
+        ("raw_params", C.c_int), ("shs_rest", C.c_void_p), ("opacities", C.c_void_p), ("dL_dsh_rest", C.c_void_p),
     ]
 
 
@@ -88,7 +90,7 @@ class ExchangeArgs(C.Structure):
                 ("payload_bytes", C.c_size_t), ("n_floats", C.c_size_t), ("epoch", C.c_uint32), ("multicast", C.c_void_p)]
 
 _raster = None
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 def lib_path(name="libgvd_raster.so"):

@@ -40,7 +40,7 @@ typedef struct CUstream_st* gvd_stream_t; /* == cudaStream_t */
 typedef void* (*gvd_alloc_fn)(void* user, size_t bytes);
 
 /* Layout/version of the scratch buffers (bumped when the packed layouts change). */
-#define GVD_RASTER_ABI_VERSION 8
+#define GVD_RASTER_ABI_VERSION 9
 
 typedef struct GvdRasterForwardArgs {
     /* sizes -- DGR/cuda_rasterizer/rasterizer_impl.cu:197-224 */
@@ -109,6 +109,14 @@ typedef struct GvdRasterForwardArgs {
     /* result */
     int num_rendered;            /* out: R = number of (Gaussian,tile) instances     */
     int num_visible;             /* out: V = number of Gaussians with radii > 0      */
+    /* SURVEY 8 row f3 -- the activations of gaussian_renderer.render() folded into the kernels.  raw_params = 1:
+     * `scales`, `rotations` and `opacities` are the UN-activated GaussianModel parameters (_scaling, _rotation, _opacity;
+     * scene/gaussian_model.py:36-43,106-130) and the kernels apply exp / normalize / sigmoid themselves; `shs` is
+     * _features_dc [P,1,3] and `shs_rest` _features_rest [P,M-1,3] -- the [P,M,3] torch.cat (96 MB at 500 k Gaussians) and
+     * the four activation launches of every render() call disappear.  Needs scales + rotations + shs (no precomputed
+     * covariance / colours). */
+    int raw_params;
+    const float* shs_rest;       /* [P,M-1,3] when raw_params                        */
 } GvdRasterForwardArgs;
 
 typedef struct GvdRasterBackwardArgs {
@@ -158,6 +166,13 @@ typedef struct GvdRasterBackwardArgs {
     float* dL_dscales;           /* [P,3]   or NULL (needed iff scales)            */
     float* dL_drotations;        /* [P,4]   or NULL (needed iff rotations)         */
     int debug;
+    /* raw_params = 1 (see GvdRasterForwardArgs): scales / rotations are the raw parameters, `opacities` the raw opacity
+     * [P]; the gradients come back with respect to the RAW parameters (chain rule of exp / normalize / sigmoid applied in
+     * the kernel), dL_dsh is [P,1,3] (d/d_features_dc) and dL_dsh_rest [P,M-1,3] (d/d_features_rest). */
+    int raw_params;
+    const float* shs_rest;
+    const float* opacities;
+    float* dL_dsh_rest;
 } GvdRasterBackwardArgs;
 
 /* sizes of the caller-owned scratch buffers; replaces

@@ -51,12 +51,15 @@ def _p(a):
 
 
 def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=None, spec_visible=None, pinned=False, flat_grads=False,
-        know_visible=True):
+        know_visible=True, raw=None):
     """spec_capacity: run the SPECULATIVE forward (no host round trip for R) with an instance buffer of that many entries
     (spec_visible: and a chunk-histogram buffer for that many visible Gaussians, default P).
     pinned: hand the exact path a host word pair for {R, V} (its event-wait route instead of the memcpy fallback).
     flat_grads: the gradient outputs are views of one allocation and the backward is told so (zero_region).
-    know_visible=False: the backward is not told V (num_visible = -1)."""
+    know_visible=False: the backward is not told V (num_visible = -1).
+    raw: dict(scaling, rotation, opacity, features_dc, features_rest) of UN-activated GaussianModel parameters: the
+    raw_params mode of the ABI (activations folded into the kernels); gradients come back for the raw tensors, the SH
+    gradient as grads["features_dc"] / grads["features_rest"]."""
     import gvd_native as n
 
     L = lib()
@@ -67,8 +70,14 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
     cov_pre = f32(precomp["cov3D_precomp"]) if precomp else None
     if precomp:
         shs = scales = rots = None
+    sh_rest = None
+    if raw is not None:
+        scales, rots, opac = f32(raw["scaling"]), f32(raw["rotation"]), f32(raw["opacity"]).reshape(-1)
+        shs, sh_rest = f32(raw["features_dc"]), f32(raw["features_rest"])
     P, W, H = means3D.shape[0], int(cam["width"]), int(cam["height"])
     M = 16 if shs is None else shs.shape[1]
+    if raw is not None:
+        M = 1 + sh_rest.shape[1]
     view, proj, campos = f32(np.asarray(cam["viewmatrix"]).reshape(-1)), f32(np.asarray(cam["projmatrix"]).reshape(-1)), f32(cam["campos"])
     bgf = f32(bg)
     color, depth, alpha = (np.zeros((c, H, W), np.float32) for c in (3, 1, 1))
@@ -97,6 +106,8 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
     a.viewmatrix, a.projmatrix, a.campos = _p(view), _p(proj), _p(campos)
     a.scale_modifier, a.tan_fovx, a.tan_fovy = 1.0, float(cam["tanfovx"]), float(cam["tanfovy"])
     a.prefiltered, a.debug, a.export_keys = 0, 0, 1
+    if raw is not None:
+        a.raw_params, a.shs_rest = 1, _p(sh_rest)
     a.out_color, a.out_depth, a.out_alpha, a.radii = _p(color), _p(depth), _p(alpha), _p(radii)
     a.geom_alloc, a.binning_alloc, a.img_alloc = cbs
     a.temp_alloc = temp_cb
@@ -182,6 +193,10 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
     b.dL_dscales = None if precomp else _p(g["scales"])
     b.dL_drotations = None if precomp else _p(g["rotations"])
     b.debug = 0
+    if raw is not None:
+        g["features_dc"], g["features_rest"] = np.full((P, 1, 3), 7.5, np.float32), np.full((P, M - 1, 3), 7.5, np.float32)
+        b.raw_params, b.shs_rest, b.opacities = 1, _p(sh_rest), _p(opac)
+        b.dL_dsh, b.dL_dsh_rest = _p(g["features_dc"]), _p(g["features_rest"])
     rc = L.gvd_raster_backward(C.byref(b), None)
     if rc != 0:
         raise RuntimeError("gvd_raster_backward (host build): " + (L.gvd_last_error() or b"").decode())
@@ -191,5 +206,7 @@ def run(sc, cam, bg, D, cot=None, use_conf=False, precomp=None, spec_capacity=No
     else:
         for k in ("colors_precomp", "cov3D_precomp"):
             g.pop(k)
+    if raw is not None:
+        g.pop("shs")
     out["grads"] = g
     return out

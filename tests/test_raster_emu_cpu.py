@@ -139,3 +139,53 @@ def test_depth_sort_and_fill_at_sizes_that_cross_tile_boundaries():
     assert o["num_rendered"] == r["num_rendered"] and np.array_equal(o["radii"], r["radii"])
     assert np.array_equal(o["ranges"], r["ranges"])
     assert np.array_equal(o["point_list"], r["point_list"])
+
+
+def test_raw_parameter_mode_folds_the_activations():
+    """raw_params = 1 (exp / normalize / sigmoid and the dc | rest SH split inside the kernels) against the
+    standard mode fed with the activations computed the way gaussian_renderer.render() computes them
+    (scene/gaussian_model.py:36-43,106-130): same images, and raw-parameter gradients equal to torch.autograd's chain
+    rule over the standard mode's gradients."""
+    import torch
+
+    import raster_emu
+    import synth
+
+    sc = synth.synth_scene(600, 5)
+    cam = synth.synth_camera(6, 96, 64)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    g = np.random.default_rng(3)
+    f = lambda k: np.asarray(sc[k].cpu() if hasattr(sc[k], "cpu") else sc[k], dtype=np.float32)  # noqa: E731
+    shs = f("shs")
+    raw_t = dict(scaling=torch.tensor(np.log(f("scales"))), rotation=torch.tensor(f("rotations") * g.uniform(0.5, 2.0, (600, 1)).astype(np.float32)),
+                 opacity=torch.tensor(np.log(f("opacities").reshape(-1) / (1 - f("opacities").reshape(-1)))),
+                 features_dc=torch.tensor(shs[:, :1].copy()), features_rest=torch.tensor(shs[:, 1:].copy()))
+    for v in raw_t.values():
+        v.requires_grad_(True)
+    act = dict(scales=torch.exp(raw_t["scaling"]), rotations=torch.nn.functional.normalize(raw_t["rotation"]),
+               opacities=torch.sigmoid(raw_t["opacity"]), shs=torch.cat((raw_t["features_dc"], raw_t["features_rest"]), dim=1))
+    sc_act = dict(sc)
+    for k, v in act.items():
+        sc_act[k] = v.detach().numpy()
+    cot = dict(color=g.standard_normal((3, 64, 96)).astype(np.float32), depth=g.standard_normal((1, 64, 96)).astype(np.float32),
+               alpha=g.standard_normal((1, 64, 96)).astype(np.float32))
+    std = raster_emu.run(sc_act, cam, bg, 3, cot=cot)
+    raw = raster_emu.run(sc_act, cam, bg, 3, cot=cot, raw={k: v.detach().numpy() for k, v in raw_t.items()})
+    assert raw["num_rendered"] > 1000
+    assert (raw["radii"] != std["radii"]).mean() < 0.01 and abs(raw["num_rendered"] - std["num_rendered"]) <= 0.01 * std["num_rendered"]
+    for k in ("color", "depth", "alpha"):
+        assert np.abs(raw[k] - std[k]).max() <= 2e-5 * max(1.0, np.abs(std[k]).max()), k
+    # chain rule through the activations, by autograd, on the standard mode's gradients
+    gs = std["grads"]
+    torch.autograd.backward([act["scales"], act["rotations"], act["opacities"], act["shs"]],
+                            [torch.tensor(gs["scales"]), torch.tensor(gs["rotations"]), torch.tensor(gs["opacities"]).reshape(-1),
+                             torch.tensor(gs["shs"])])
+    want = {"scales": raw_t["scaling"].grad, "rotations": raw_t["rotation"].grad, "opacities": raw_t["opacity"].grad,
+            "features_dc": raw_t["features_dc"].grad, "features_rest": raw_t["features_rest"].grad}
+    for k, w in want.items():
+        got, w = raw["grads"][k].reshape(-1), w.numpy().reshape(-1)
+        rel = np.linalg.norm(got - w) / max(np.linalg.norm(w), 1e-12)
+        assert rel < 1e-3, (k, rel)  # the host build reaches 1-3e-3 against the goldens itself (libm expf, no FMA contraction)
+    for k in ("means3D", "means2D"):
+        rel = np.linalg.norm(raw["grads"][k] - gs[k]) / np.linalg.norm(gs[k])
+        assert rel < 1e-3, (k, rel)  # the host build reaches 1-3e-3 against the goldens itself (libm expf, no FMA contraction)
