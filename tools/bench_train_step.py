@@ -1,6 +1,8 @@
 """One WHOLE 3DGS training iteration at BASELINE configs[1] (C2: 500 k Gaussians, 640x480, SH degree 3), both arms on the
 same GPU: activations -> rasterizer forward -> L1 + SSIM loss -> backward -> densification statistics -> Adam.
   ours:       diff_gaussian_rasterization (this repo) + train_ops.photometric_loss / add_densification_stats / FusedAdam
+  folded:     the same with the activations folded into the rasterizer kernels (rasterize_gaussians_raw: no exp / sigmoid /
+              normalize launches, no 96 MB SH concatenation, one backward node -- SURVEY 8 row f3)
   reference:  oracle/_ref rasterizer (the reference's CUDA code) + utils/loss_utils.py's l1_loss / ssim restated in torch
               (same conv2d calls) + the masked densification statements + torch.optim.Adam(eps=1e-15)
 (train_baseline.py:73-120 without logging / densify-and-prune, which run every 100 iterations.)
@@ -43,7 +45,7 @@ def ssim_reference(img1, img2):
 
 def run(arm, P, W, H, seed, D, iters):
     dev = torch.device("cuda", 0)
-    if arm == "ours":
+    if arm in ("ours", "folded"):
         import diff_gaussian_rasterization as pkg
         import train_ops
     else:
@@ -63,7 +65,7 @@ def run(arm, P, W, H, seed, D, iters):
     params = {k: v.contiguous().requires_grad_(True) for k, v in raw.items()}
     lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "f_rest": 2.5e-3 / 20, "opacity": 5e-2, "scaling": 5e-3, "rotation": 1e-3}
     groups = [{"params": [params[k]], "lr": lrs[k], "name": k} for k in params]
-    opt = (train_ops.FusedAdam if arm == "ours" else torch.optim.Adam)(groups, lr=0.0, eps=1e-15)
+    opt = (train_ops.FusedAdam if arm != "reference" else torch.optim.Adam)(groups, lr=0.0, eps=1e-15)
     accum, denom, maxr = torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, device=dev)
     lam = 0.2
 
@@ -74,17 +76,22 @@ def run(arm, P, W, H, seed, D, iters):
             scale_modifier=1.0, viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], sh_degree=D, campos=cam["campos"],
             prefiltered=False, debug=False, confidence=sc["confidence"])
         rast = pkg.GaussianRasterizer(raster_settings=settings)
-        # gaussian_renderer/__init__.py:60-87: activations + the SH concatenation
-        image, radii, depth, alpha = rast(means3D=params["xyz"], means2D=means2D, opacities=torch.sigmoid(params["opacity"]),
+        if arm == "folded":
+            image, radii, depth, alpha = pkg.rasterize_gaussians_raw(params["xyz"], means2D, params["f_dc"], params["f_rest"],
+                                                                     params["opacity"].view(-1, 1), params["scaling"], params["rotation"],
+                                                                     settings)
+        else:
+          # gaussian_renderer/__init__.py:60-87: activations + the SH concatenation
+          image, radii, depth, alpha = rast(means3D=params["xyz"], means2D=means2D, opacities=torch.sigmoid(params["opacity"]),
                                           shs=torch.cat((params["f_dc"], params["f_rest"]), dim=1), scales=torch.exp(params["scaling"]),
                                           rotations=torch.nn.functional.normalize(params["rotation"]))
-        if arm == "ours":
+        if arm != "reference":
             loss = train_ops.photometric_loss(image, gt, lam)
         else:
             loss = (1.0 - lam) * torch.abs(image - gt).mean() + lam * (1.0 - ssim_reference(image, gt))
         loss.backward()
         with torch.no_grad():
-            if arm == "ours":
+            if arm != "reference":
                 train_ops.add_densification_stats(means2D.grad, radii, accum.view(-1), denom.view(-1), maxr)
             else:
                 vis = radii > 0
@@ -112,12 +119,12 @@ def run(arm, P, W, H, seed, D, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--arm", default="both", choices=["ours", "reference", "both"])
+    ap.add_argument("--arm", default="both", choices=["ours", "folded", "reference", "both"])
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     a = ap.parse_args()
     P, W, H, seed, D = WORKLOADS[a.workload]
-    for arm in (["ours", "reference"] if a.arm == "both" else [a.arm]):
+    for arm in (["ours", "folded", "reference"] if a.arm == "both" else [a.arm]):
         try:
             print(json.dumps(run(arm, P, W, H, seed, D, a.iters)), flush=True)
         except Exception as ex:  # one arm failing must not hide the other
