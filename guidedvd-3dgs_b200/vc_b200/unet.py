@@ -366,6 +366,51 @@ class _GraphedForward:
         return self.out.clone()
 
 
+class _GraphedGrad:
+    """The differentiated U-Net call of the guided sampler (forward WITH tape, backward to the input latent) as CUDA graphs.
+    Eagerly a guided step issues ~8 300 launches and needs ~460 ms of Python to do so -- as long as its kernels run
+    (profiles/r02_guided_kernel_breakdown.txt); ~7 000 of them are the two U-Net forwards and their backwards, whose shapes
+    never change.  torch.cuda.make_graphed_callables captures one forward graph and one backward graph per slot (static
+    inputs, saved activations in the graph's private pool).  A guided step holds two forwards (cond / uncond) before it
+    runs their backwards, so there are two slots; a slot is taken by a forward and released when its backward starts (a
+    hook on the output's gradient).  A third forward while both are taken, or any capture failure, runs eagerly."""
+
+    def __init__(self, unet, slots=2):
+        self.unet, self.max_slots, self.slots, self.error = unet, slots, [], None
+
+    def _make(self, xc, t, cc, fs):
+        unet = self.unet
+
+        def fn(xc_, t_, cc_, fs_):
+            return unet.forward_with_grad(xc_, t_, cc_, fs=fs_).float()
+
+        sample = (xc.detach().clone().requires_grad_(True), t.clone(), cc.detach().clone(), fs.clone())
+        return {"fn": torch.cuda.make_graphed_callables(fn, sample), "busy": False}
+
+    def __call__(self, xc, t, cc, fs):
+        slot = next((s for s in self.slots if not s["busy"]), None)
+        if slot is None and len(self.slots) < self.max_slots and self.error is None:
+            try:
+                slot = self._make(xc, t, cc, fs)
+                self.slots.append(slot)
+            except Exception as ex:  # same kernels either way: keep running eagerly and say why
+                import warnings
+                self.error = repr(ex)[:300]
+                warnings.warn("vc_b200: CUDA-graph capture of the differentiated U-Net failed, running it eagerly: " + self.error)
+                torch.cuda.synchronize(xc.device)
+        if slot is None:
+            return self.unet.forward_with_grad(xc, t, cc, fs=fs).float()
+        y = slot["fn"](xc, t, cc, fs)
+        slot["busy"] = True
+
+        def release(grad, slot=slot):
+            slot["busy"] = False
+            return None
+
+        y.register_hook(release)
+        return y
+
+
 class DiffusionModelB200:
     """The slice of the reference's LatentDiffusion object the sampler needs: `apply_model` with the 'hybrid'
     conditioning of DiffusionWrapper.forward (lvdm/models/ddpm3d.py:1426-1443): channel-concat c_concat, cross-attend
@@ -380,11 +425,24 @@ class DiffusionModelB200:
             unet.part = plan.part
         self.use_graph = (os.environ.get("GVD_UNET_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
         self._graphs, self.graph_error = {}, None
+        # the guided sampler's differentiated call as CUDA graphs (GVD_GUIDED_GRAPH, on; single-GPU plans only: the
+        # frame-sharded tape carries NCCL exchanges)
+        self.use_grad_graph = os.environ.get("GVD_GUIDED_GRAPH", "1") != "0"
+        self._grad_graphs = {}
 
     def _local(self, x, t, cond, fs):
         xc = torch.cat([x] + list(cond["c_concat"]), dim=1)
         cc = torch.cat(list(cond["c_crossattn"]), dim=1)
         if torch.is_grad_enabled() and x.requires_grad:  # the guided sampler differentiates through this call
+            if (self.use_grad_graph and xc.is_cuda and xc.shape[0] == 1 and self.unet.trace is None
+                    and (self.plan is None or self.plan.world == 1)):
+                if fs is None:
+                    fs = torch.full((1,), int(self.unet.default_fs), dtype=torch.long, device=xc.device)
+                key = (tuple(xc.shape), tuple(cc.shape), xc.dtype, cc.dtype, t.dtype, fs.dtype)
+                g = self._grad_graphs.get(key)
+                if g is None:
+                    g = self._grad_graphs[key] = _GraphedGrad(self.unet)
+                return g(xc, t, cc, fs)
             return self.unet.forward_with_grad(xc, t, cc, fs=fs).float()
         if self.use_graph and xc.is_cuda and xc.shape[0] == 1 and self.unet.trace is None:
             if fs is None:
