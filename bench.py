@@ -473,7 +473,7 @@ def main():
         if exchange_check is not None:
             line["exchange_check"] = exchange_check
         if denoise_result is not None:
-            for k in ("guided", "c5"):
+            for k in ("guided", "c5", "train_step"):
                 if isinstance(denoise_result, dict) and k in denoise_result:
                     line[k] = denoise_result.pop(k)
             if denoise_result:
@@ -530,6 +530,20 @@ def main():
                 os._exit(0)
     if c5_result is not None:
         denoise_result = dict(denoise_result or {}, c5=c5_result)
+    train_result = None
+    if world == 1 and not args.no_denoise and args.workload == "C2":
+        # whole training iteration (render + L1/SSIM loss + backward + densification statistics + Adam), SURVEY 8 row f3:
+        # ours with the activations folded into the rasterizer kernels; the reference arm = its rasterizer + its loss /
+        # optimizer statements in torch (tools/bench_train_step.py)
+        try:
+            sc = leaves = means2D = None
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_train_step
+            train_result = bench_train_step.run("folded" if args.impl == "ours" else "reference", P, W, H, seed, D, 100)
+        except Exception as ex:  # a secondary block must never take the headline line down
+            train_result = {"error": repr(ex)[:300]}
+        denoise_result = dict(denoise_result or {}, train_step=train_result)
 
     if rank != 0:
         if world > 1:
