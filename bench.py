@@ -825,6 +825,15 @@ def guided_bench(impl, dev, world, ref, unet, cfg, t=25, h=40, w=64, decode_fram
             sys.path.insert(0, unet_ref.REF_VC)
         import lvdm.models.samplers.ddim_guidance as dg
         dg.DDIMSamplerGuidance.register_buffer = lambda self, name, attr: setattr(self, name, attr.to(dev) if torch.is_tensor(attr) else attr)
+        # third_party/ViewCrafter/viewcrafter.py:322 sets unet_config.use_checkpoint = True before it builds the model: the
+        # reference's guided step recomputes every ResBlock / transformer block in its backward instead of keeping their
+        # activations.  Without it this arm sat at 172 of 180 GB and, on the boxes of the round's last runs, in allocator
+        # retries (15 s per step instead of 2.3-3.2 s).
+        for mod in ref.modules():
+            if isinstance(getattr(mod, "use_checkpoint", None), bool):
+                mod.use_checkpoint = True
+            if isinstance(getattr(mod, "checkpoint", None), bool):
+                mod.checkpoint = True
         s = dg.DDIMSamplerGuidance(_ref_latent_model(ref, dev, PerFrame()))
         s.make_schedule(50, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
         ts = torch.full((1,), int(s.ddim_timesteps[index]), dtype=torch.long, device=dev)

@@ -114,7 +114,7 @@ def run(arm, P, W, H, seed, D, iters):
     ms = e0.elapsed_time(e1) / iters
     return {"metric": "3DGS training iterations/sec (render + L1/SSIM loss + backward + densification stats + Adam)", "impl": arm,
             "value": round(1e3 / ms, 2), "unit": "iterations/s", "ms_per_iteration": round(ms, 4), "iters": iters, "dtype": "f32",
-            "final_loss": round(float(loss), 6), "config": {"P": P, "width": W, "height": H, "sh_degree": D, "lambda_dssim": lam}}
+            "final_loss": round(float(loss.detach()), 6), "config": {"P": P, "width": W, "height": H, "sh_degree": D, "lambda_dssim": lam}}
 
 
 def main():
