@@ -185,19 +185,27 @@ def set_gradient_buffer(buf):
         _grad_buffer.clear()
         _last_views.clear()
         _view_cache.clear()
+        _grad_pending.clear()
     else:
         _grad_buffer[buf.device] = buf
 
 
 _last_views = {}
+_grad_pending = {}   # device -> True while the caller-owned buffer holds a backward's gradients nobody has asked for yet
+_warned_alias = []
 
 
 def gradient_views(device):
     """With a caller-owned gradient buffer (set_gradient_buffer): the views of it that the most recent backward on
     `device` filled, keyed by the rasterizer input they belong to.  autograd's AccumulateGrad does not adopt gradient
     tensors that are views of a larger buffer (it copies them into `leaf.grad`), so a data-parallel caller sums the
-    BUFFER across ranks and then points `leaf.grad` at these views (view_parallel.allreduce_gradients)."""
-    return _last_views.get(torch.device(device))
+    BUFFER across ranks and then points `leaf.grad` at these views (view_parallel.allreduce_gradients).
+    Asking for the views marks the buffer as consumed: the next backward may write into it again.  A backward that
+    arrives BEFORE that (two renders feeding one loss.backward(), as train_guidedvd.py does with a train view and a
+    pseudo view) would overwrite gradients autograd still holds views of, so it gets fresh memory instead."""
+    dev = torch.device(device)
+    _grad_pending[dev] = False
+    return _last_views.get(dev)
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -442,6 +450,14 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                                 4 if has_scales else 0, 3 if has_colors else 0, 6 if has_cov else 0, 3))
     with _on_device(dev):
         ext = _grad_buffer.get(dev)
+        if ext is not None and _grad_pending.get(dev):
+            # a second backward before the first one's gradients were taken: never alias them
+            if not _warned_alias:
+                import warnings
+                _warned_alias.append(1)
+                warnings.warn("diff_gaussian_rasterization: a second backward reached the caller-owned gradient buffer before "
+                              "gradient_views() took the first one's gradients; it gets fresh memory (no in-place exchange for it)")
+            ext = None
         if ext is not None and ext.numel() >= total:
             # caller-owned storage: the same memory every step, so the eight views are built once
             key = (ext.data_ptr(), P, M, has_sh, has_scales, has_colors, has_cov)
@@ -457,6 +473,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         dL_dmeans2D, dL_dmeans3D, dL_dopacity, dL_dcolors, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations = views
         zero_ptr = ext.data_ptr() if ext is not None else flat.data_ptr()
         if ext is not None:
+            _grad_pending[dev] = True
             _last_views[dev] = {"means2D": dL_dmeans2D, "means3D": dL_dmeans3D, "opacities": dL_dopacity,
                                 "colors_precomp": dL_dcolors, "cov3D_precomp": dL_dcov3D, "shs": dL_dsh,
                                 "scales": dL_dscales, "rotations": dL_drotations, "_floats": total}

@@ -165,6 +165,14 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     if exchange is not None and leaves is not None and views is not None:
+        # `leaves` must be the tensors that were handed to the rasterizer themselves (the slices ARE their gradients).
+        # GaussianModel's parameters go through exp / sigmoid / normalize first (or through rasterize_gaussians_raw, which
+        # returns raw-parameter gradients): pass the rasterizer's direct inputs here, not upstream parameters.
+        for name, leaf in leaves.items():
+            v = views.get(name)
+            if v is not None and leaf is not None and v.numel() != leaf.numel():
+                raise ValueError(f"allreduce_gradients: leaf '{name}' has {leaf.numel()} elements, its gradient slice {v.numel()}: "
+                                 "leaves must be the rasterizer's direct inputs")
         n = int(views["_floats"])
         exchange.allreduce(n)
         if average:

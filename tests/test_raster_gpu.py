@@ -284,3 +284,43 @@ def test_deferred_mode_matches_exact_and_repairs_an_overflow(monkeypatch):
         monkeypatch.setattr(ours._C, "_capacity", real_capacity)
         pr.run(ours, sc, cam, cot, bg, D, export_keys=False)
     del lost
+
+
+def test_two_renders_into_one_backward_with_a_gradient_buffer():
+    """set_gradient_buffer (the in-place cross-GPU exchange) hands every backward the same memory.  Two renders that feed
+    ONE loss.backward() -- train_guidedvd.py's train view + pseudo view -- must still accumulate both gradients: the second
+    backward arrives before anybody asked for the first one's views and gets fresh memory (with a warning)."""
+    import warnings
+
+    import synth
+
+    ours, _ = _pkgs()
+    dev = "cuda"
+    sc = synth.synth_scene(4000, 11, device=dev)
+    cams = [synth.synth_camera(21 + i, 96, 64, device=dev) for i in range(2)]
+    bg = torch.zeros(3, device=dev)
+
+    def grads(use_buffer):
+        leaf = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        if use_buffer:
+            ours.set_gradient_buffer(torch.empty(ours.gradient_buffer_floats(4000), device=dev))
+        try:
+            total = 0.0
+            for cam in cams:
+                r = ours.GaussianRasterizer(_settings(ours, cam, bg, 3, sc["confidence"]))
+                color, radii, depth, alpha = r(leaf["means3D"], torch.zeros_like(leaf["means3D"]), leaf["opacities"], shs=leaf["shs"],
+                                               scales=leaf["scales"], rotations=leaf["rotations"])
+                total = total + (color ** 2).sum() + depth.sum()
+            with warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter("always")
+                total.backward()
+            torch.cuda.synchronize()
+            return {k: v.grad.clone() for k, v in leaf.items()}, [str(x.message) for x in w]
+        finally:
+            ours.set_gradient_buffer(None)
+
+    plain, _ = grads(False)
+    buffered, msgs = grads(True)
+    for k in plain:
+        rel = ((buffered[k] - plain[k]).double().norm() / plain[k].double().norm().clamp_min(1e-30)).item()
+        assert rel < 1e-5, (k, rel)
