@@ -792,6 +792,216 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
 }
 
+// Generation 8 = generation 7 with TWO softmax threads per query row (8 softmax warps per CTA, four per scheduler with the
+// two CTAs of the SM): warps w and w + 4 share a TMEM lane quadrant and split each 64-key sub-block -- 32 score columns,
+// 16 packed P columns and 32 of the 64 O columns each -- and agree on the row maximum through two floats of shared memory
+// and a 64-thread named barrier per sub-block; the row sums stay separate until the end.  (The same split was slower when
+// the serial MMA chain bounded the kernel -- see the generation 7 comment.)  Measured on B200 (tools/gpu_check_flash8.sh,
+// 25 x 5 heads x 9216 tokens): 3.73 ms against generation 7's 3.36 ms -- the per-sub-block pair barrier and the shared
+// memory round trip cost more than the extra warps per scheduler win back, so this stays an A/B variant (GVD_FLASH=v8).
+constexpr int FA8_THREADS = 64 + 8 * 32;
+constexpr int FA8_SMEM = FA_SMEM + 2 * 2 * 128 * 4;  // + pair exchange: [parity][half][row] floats
+
+__device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+__global__ void __launch_bounds__(FA8_THREADS, 2)
+flash_attn8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sq = smem;
+    uint8_t* sk = smem + FA_TILE_BYTES;
+    uint8_t* sv = smem + FA_TILE_BYTES * (1 + FA_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;    // [2]
+    uint64_t* kv_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;     // [2]
+    uint64_t* p_full = bars + 7;     // [2]
+    uint64_t* o_done = bars + 9;     // one completion per PV_i
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    float* xchg = reinterpret_cast<float*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256);  // [2][2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.Nk + FA_BN - 1) / FA_BN;   // 128-key tiles in shared memory
+    const int nsub = (p.Nk + 63) / 64;             // 64-key sub-blocks that hold at least one key
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_q);
+        tc::prefetch_tmap(&tmap_k);
+        tc::prefetch_tmap(&tmap_v);
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < FA_STAGES; ++s) {
+            tc::mbar_init(&kv_full[s], 1);
+            tc::mbar_init(&kv_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&s_full[s], 1);
+            tc::mbar_init(&p_full[s], 8);  // one arrival per softmax warp
+        }
+        tc::mbar_init(o_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(q_full, FA_TILE_BYTES);
+            tc::tma_load_4d(sq, &tmap_q, q_full, 0, m0, h, b);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FA_STAGES;
+                tc::mbar_wait(&kv_empty[s], (uint32_t)(((j / FA_STAGES) & 1) ^ 1));
+                tc::mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+                tc::tma_load_4d(sk + s * FA_TILE_BYTES, &tmap_k, &kv_full[s], 0, j * FA_BN, h, b);
+                tc::tma_load_4d(sv + s * FA_TILE_BYTES, &tmap_v, &kv_full[s], 0, j * FA_BN, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = tc::make_idesc_bf16(FA_BM, 64);
+            const uint32_t idesc_pv = make_idesc_pv_k64();
+            const uint32_t q_addr = tc::smem_u32(sq);
+            auto issue_qk = [&](int i) {  // S[i & 1] = Q K_i^T, K_i = rows 64 (i & 1) .. + 63 of tile i / 2
+                const int j = i >> 1, s = j % FA_STAGES;
+                if ((i & 1) == 0) {
+                    tc::mbar_wait(&kv_full[s], (uint32_t)((j / FA_STAGES) & 1));
+                    tc::fence_after_sync();
+                }
+                const uint32_t k_addr = tc::smem_u32(sk + s * FA_TILE_BYTES) + (uint32_t)(i & 1) * 64 * 128;
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k)
+                    tc::umma_bf16(tmem_base + FA7_S_COL + (uint32_t)(i & 1) * 64, tc::make_desc_kmajor_sw128(q_addr + k * 32),
+                                  tc::make_desc_kmajor_sw128(k_addr + k * 32), idesc_qk, k != 0);
+                tc::umma_commit(&s_full[i & 1]);
+            };
+            tc::mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int i = 0; i < nsub; ++i) {
+                // S[(i+1)&1] was last read by the softmax of sub-block i-1, which finished before p_full(i-1) completed --
+                // waited on in the previous iteration
+                if (i + 1 < nsub) issue_qk(i + 1);
+                tc::mbar_wait(&p_full[i & 1], (uint32_t)((i >> 1) & 1));
+                tc::fence_after_sync();
+                const int j = i >> 1, s = j % FA_STAGES;
+                const uint32_t v_addr = tc::smem_u32(sv + s * FA_TILE_BYTES) + (uint32_t)(i & 1) * 64 * 128;
+#pragma unroll
+                for (int k = 0; k < 64 / 16; ++k)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 smem rows of V
+                    umma_bf16_ts(tmem_base + FA7_O_COL, tmem_base + FA7_P_COL + (uint32_t)(i & 1) * 32 + k * 8,
+                                 tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (i | k) != 0);
+                tc::umma_commit(o_done);
+                if ((i & 1) || i + 1 == nsub) tc::umma_commit(&kv_empty[s]);  // the tile's last sub-block: K_j, V_j have no reader left
+            }
+        }
+    } else {
+        const int q = warp & 3;             // TMEM lane quadrant of this warp
+        const int hf = (warp - 2) >> 2;     // which half of the sub-block's columns
+        const int rloc = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int row = m0 + rloc;
+        const float sl2 = p.scale * 1.4426950408889634f;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int i = 0; i < nsub; ++i) {
+            tc::mbar_wait(&s_full[i & 1], (uint32_t)((i >> 1) & 1));
+            tc::fence_after_sync();
+            const int key0 = i * 64 + 32 * hf;
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + lane_off + FA7_S_COL + (uint32_t)(i & 1) * 64 + 32 * hf, v);
+            tc::tmem_ld_wait();
+            if (key0 + 32 > p.Nk) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (key0 + e >= p.Nk) v[e] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+                mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+            }
+            const float m_loc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            float* xb = xchg + (i & 1) * 256;
+            xb[hf * 128 + rloc] = m_loc;
+            pair_bar(q);
+            const float m_blk = fmaxf(m_loc, xb[(hf ^ 1) * 128 + rloc]) * sl2;  // scale > 0: max commutes with it
+            float m_new = m_run;
+            if (i == 0) {
+                m_new = m_blk;
+            } else {
+                const bool grow = m_blk > m_run + 8.0f;  // both threads of a row see the same m_blk and m_run
+                if (__any_sync(0xffffffffu, grow)) {
+                    tc::mbar_wait(o_done, (uint32_t)((i - 1) & 1));  // PV_{i-1}: O is quiescent
+                    tc::fence_after_sync();
+                    float alpha = 1.0f;
+                    if (grow) {
+                        m_new = m_blk;
+                        alpha = ex2(m_run - m_new);
+                        l_run *= alpha;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 16) {
+                        uint32_t o[16];
+                        tc::tmem_ld16(tmem_base + lane_off + FA7_O_COL + 32 * hf + c, o);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st16(tmem_base + lane_off + FA7_O_COL + 32 * hf + c, o);
+                    }
+                }
+            }
+            const float mneg = -m_new;
+            float l0 = 0.f, l1 = 0.f;
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                const float p0 = ex2(fmaf(__uint_as_float(v[e]), sl2, mneg));
+                const float p1 = ex2(fmaf(__uint_as_float(v[e + 1]), sl2, mneg));
+                l0 += p0;
+                l1 += p1;
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            tmem_st16(tmem_base + lane_off + FA7_P_COL + (uint32_t)(i & 1) * 32 + 16 * hf, pk);
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&p_full[i & 1]);
+            l_run += l0 + l1;
+            m_run = m_new;
+        }
+        float* xb = xchg + (nsub & 1) * 256;  // the two halves of a row ran with the same maximum: their sums add
+        xb[hf * 128 + rloc] = l_run;
+        pair_bar(q);
+        const float inv = 1.0f / (l_run + xb[(hf ^ 1) * 128 + rloc]);
+        tc::mbar_wait(o_done, (uint32_t)((nsub - 1) & 1));
+        tc::fence_after_sync();
+        __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo + 32 * hf;
+        uint32_t o[32];
+        tc::tmem_ld32(tmem_base + lane_off + FA7_O_COL + 32 * hf, o);
+        tc::tmem_ld_wait();
+        if (row < p.Nq) {
+#pragma unroll
+            for (int e8 = 0; e8 < 32; e8 += 8) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    h2[e] = __floats2bfloat162_rn(__uint_as_float(o[e8 + 2 * e]) * inv, __uint_as_float(o[e8 + 2 * e + 1]) * inv);
+                *reinterpret_cast<uint4*>(dst + e8) = u;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 // ---- generation 5: one CTA per SM, TWO query tiles in ping-pong, two softmax threads per row --------------------------
 // tools/ubench_softmax_pipe.cu (profiles/r02_ubench_softmax.txt): MUFU.EX2 runs at 16 results / clk / SM, so a 128 x 128
 // block holds 1 024 clk of exponentials against 512 clk of MMA -- with head dim 64 the tensor pipe cannot exceed 50 %
@@ -1096,6 +1306,7 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         else if (v && v[0] == 'v' && v[1] == '5') want = 5;
         else if (v && v[0] == 'v' && v[1] == '6') want = 6;
         else if (v && v[0] == 'v' && v[1] == '7') want = 7;
+        else if (v && v[0] == 'v' && v[1] == '8') want = 11;
         if (want == 7 && pe && pe[0] >= '1' && pe[0] <= '3') want = 7 + (pe[0] - '0');  // 8: one exponential in 2 on the FMA pipe, 9: 1 in 4, 10: 1 in 8
         const void* fn = want == 0 ? (const void*)flash_attn_v1_kernel
                        : want == 1 ? (const void*)flash_attn_kernel<0>
@@ -1103,8 +1314,10 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
                        : want == 5 ? (const void*)flash_attn5_kernel
                        : want == 6 ? (const void*)flash_attn_kernel<2>
                        : want == 8 ? (const void*)flash_attn7_kernel<1> : want == 9 ? (const void*)flash_attn7_kernel<2>
-                       : want == 10 ? (const void*)flash_attn7_kernel<4> : (const void*)flash_attn7_kernel<0>;
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want == 5 ? FA5_SMEM : FA_SMEM);
+                       : want == 10 ? (const void*)flash_attn7_kernel<4>
+                       : want == 11 ? (const void*)flash_attn8_kernel : (const void*)flash_attn7_kernel<0>;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             want == 5 ? FA5_SMEM : (want == 11 ? FA8_SMEM : FA_SMEM));
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
         variant = want;
     }
@@ -1118,6 +1331,7 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
     else if (variant == 8) flash_attn7_kernel<1><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 9) flash_attn7_kernel<2><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 10) flash_attn7_kernel<4><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    else if (variant == 11) flash_attn8_kernel<<<grid, FA8_THREADS, FA8_SMEM, s>>>(tq, tk, tv, p);
     else flash_attn7_kernel<0><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention launch: ") + cudaGetErrorString(e); return 1; }

@@ -224,7 +224,7 @@ def test_attention_paths(fn):
         _close(attn(q3, k3, v2, 2, 700, 700, H, 0.125), ref32(q3, k3, v2), tol=1.0 / 64)
 
 
-@pytest.mark.parametrize("variant", ["v1", "v2", "v5", "v6"])
+@pytest.mark.parametrize("variant", ["v1", "v2", "v5", "v6", "v8"])
 def test_flash_attention_variants(variant):
     """The A/B variants of gvd_flash_attention (GVD_FLASH, read once per process): first generation, two-tile ping-pong,
     one-pass chunk-pipelined softmax -- each in its own process against fp32 attention, ragged sizes included."""
