@@ -76,6 +76,8 @@ struct FaParams {
     long long ldo, o_stride_h, o_stride_b;
     int Nq, Nk, H;
     float scale;
+    float* lse;  // optional [B, H, lse_ld]: log2 sum_j exp2(s_ij * scale * log2 e) per query row (generation 7 only)
+    int lse_ld;
 };
 
 __global__ void __launch_bounds__(FA_THREADS, 2)
@@ -768,6 +770,8 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc::mbar_wait(o_done, (uint32_t)((nsub - 1) & 1));
         tc::fence_after_sync();
         const float inv = 1.0f / l_run;
+        // the statistic the backward needs (attn_bwd_tc.cu); m_run may be a stale maximum, m_run + log2 l_run is exact either way
+        if (p.lse != nullptr && row < p.lse_ld) p.lse[((long long)b * p.H + h) * p.lse_ld + row] = m_run + __log2f(l_run);
         __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo;
 #pragma unroll
         for (int c = 0; c < FA_D; c += 32) {
@@ -1276,9 +1280,28 @@ bool fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long H, 
 
 }  // namespace
 
+bool gvd_fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long H, long long B, long long ld, long long sb) {
+    return fa_make_tmap(map, base, N, H, B, ld, sb);
+}
+
+static int flash_forward(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk, int H,
+                         long long q_batch_stride, long long kv_batch_stride, float scale, gvd_nn_stream_t stream_);
+
 extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, void* out, int B, int Nq, int Nk, int H,
                                    long long q_batch_stride, long long kv_batch_stride, float scale,
                                    gvd_nn_stream_t stream_) {
+    return flash_forward(q, k, v, out, nullptr, B, Nq, Nk, H, q_batch_stride, kv_batch_stride, scale, stream_);
+}
+
+extern "C" int gvd_flash_attention_lse(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk,
+                                       int H, long long q_batch_stride, long long kv_batch_stride, float scale,
+                                       gvd_nn_stream_t stream_) {
+    if (!lse) { g_nn_err_ext = "gvd_flash_attention_lse: null lse"; return 2; }
+    return flash_forward(q, k, v, out, lse, B, Nq, Nk, H, q_batch_stride, kv_batch_stride, scale, stream_);
+}
+
+static int flash_forward(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk, int H,
+                         long long q_batch_stride, long long kv_batch_stride, float scale, gvd_nn_stream_t stream_) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (!q || !k || !v || !out) { g_nn_err_ext = "gvd_flash_attention: null pointer"; return 2; }
     if (B <= 0 || Nq <= 0 || H <= 0) return 0;
@@ -1321,9 +1344,17 @@ extern "C" int gvd_flash_attention(const void* q, const void* k, const void* v, 
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention attr: ") + cudaGetErrorString(e); return 1; }
         variant = want;
     }
-    FaParams p{reinterpret_cast<__nv_bfloat16*>(out), ld, 64, q_batch_stride, Nq, Nk, H, scale};
+    FaParams p{reinterpret_cast<__nv_bfloat16*>(out), ld, 64, q_batch_stride, Nq, Nk, H, scale, lse, (Nq + 127) / 128 * 128};
     dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
-    if (variant == 0) flash_attn_v1_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    if (lse != nullptr) {  // only generation 7 writes the row statistic, whatever GVD_FLASH selects for the plain forward
+        static bool attr7 = false;
+        if (!attr7) {
+            cudaError_t e7 = cudaFuncSetAttribute(flash_attn7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+            if (e7 != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention_lse attr: ") + cudaGetErrorString(e7); return 1; }
+            attr7 = true;
+        }
+        flash_attn7_kernel<0><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
+    } else if (variant == 0) flash_attn_v1_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 1) flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 2) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, s>>>(tq, tk, tv, p);
     else if (variant == 5) flash_attn5_kernel<<<dim3((Nq + 2 * FA_BM - 1) / (2 * FA_BM), H, B), FA5_THREADS, FA5_SMEM, s>>>(tq, tk, tv, p);

@@ -250,6 +250,16 @@ class ConvArgs(C.Structure):
     ]
 
 
+class FlashBwdArgs(C.Structure):
+    """include/gvd_nn.h::GvdFlashBwdArgs"""
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p),
+        ("lse", C.c_void_p), ("delta", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("B", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("H", C.c_int),
+        ("q_batch_stride", C.c_longlong), ("kv_batch_stride", C.c_longlong), ("scale", C.c_float),
+    ]
+
+
 class DdimArgs(C.Structure):
     _fields_ = [
         ("n", C.c_longlong), ("x", C.c_void_p), ("e_cond", C.c_void_p), ("e_uncond", C.c_void_p), ("noise", C.c_void_p),
@@ -278,7 +288,8 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
               # input-gradient operators of the guided sampler (csrc/nn_backward.cu)
               "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_groupnorm_cl_bwd_sums", "gvd_groupnorm_cl_bwd_apply", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
               "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp",
-              "gvd_im2col3x3_down_cl", "gvd_nn_set_fast", "gvd_conv_bf16", "gvd_conv_bf16_supported")
+              "gvd_im2col3x3_down_cl", "gvd_nn_set_fast", "gvd_conv_bf16", "gvd_conv_bf16_supported",
+              "gvd_flash_attention_lse", "gvd_flash_attention_bwd")
 _nn = None
 
 
@@ -303,6 +314,8 @@ def _nn_signatures():
         "gvd_im2col_t3_cl": (I, [vp, vp, i32, i32, ll, i32, vp]),
         "gvd_temporal_attention": (I, [vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]),
         "gvd_flash_attention": (I, [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]),
+        "gvd_flash_attention_lse": (I, [vp, vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]),
+        "gvd_flash_attention_bwd": (I, [C.POINTER(FlashBwdArgs), vp]),
         "gvd_ddim_step": (I, [C.POINTER(DdimArgs), vp]),
         "gvd_groupnorm_bwd_tmp_bytes": (S, [i32, ll, i32]),
         "gvd_groupnorm_cl_bwd": (I, [vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp, sz, vp]),

@@ -171,18 +171,30 @@ class TemporalAttention(Function):
 
 
 class FlashAttention(Function):
+    """Fused attention with its fused adjoint (csrc/attn_bwd_tc.cu): the forward keeps the output and one fp32 per query
+    row; GVD_FLASH_BWD=0 restores the first backward, which re-materialises the scores."""
+
     @staticmethod
     def forward(ctx, q, k, v, Bq, Nq, Nk, H, scale, shared_kv):
-        ctx.save_for_backward(q, k, v)
         ctx.args = (Bq, Nq, Nk, H, scale, shared_kv)
+        ctx.fused = ops.FUSED_FLASH_BWD
+        if ctx.fused:
+            out, lse = ops.flash_attention_lse(q, k, v, Bq, Nq, Nk, H, scale, shared_kv)
+            ctx.save_for_backward(q, k, v, out, lse)
+            return out
+        ctx.save_for_backward(q, k, v)
         return ops.flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv)
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v = ctx.saved_tensors
         Bq, Nq, Nk, H, scale, shared_kv = ctx.args
         need_kv = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dq, dk, dv = ops.attention_bwd(q, k, v, _c(dout), Bq, Nq, Nk, H, scale, shared_kv, need_kv)
+        if ctx.fused:
+            q, k, v, out, lse = ctx.saved_tensors
+            dq, dk, dv = ops.flash_attention_bwd(q, k, v, out, lse, _c(dout), Bq, Nq, Nk, H, scale, shared_kv, need_kv)
+        else:
+            q, k, v = ctx.saved_tensors
+            dq, dk, dv = ops.attention_bwd(q, k, v, _c(dout), Bq, Nq, Nk, H, scale, shared_kv, need_kv)
         return (dq.view_as(q), dk.view_as(k) if dk is not None else None, dv.view_as(v) if dv is not None else None,
                 None, None, None, None, None, None)
 

@@ -346,6 +346,49 @@ def flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False):
     return out
 
 
+# The guided sampler's attention adjoint: fused on chip (csrc/attn_bwd_tc.cu) unless GVD_FLASH_BWD=0, which restores the
+# first backward (`attention_bwd`: scores, probabilities and their gradients materialised, five GEMM launches).
+FUSED_FLASH_BWD = os.environ.get("GVD_FLASH_BWD", "1") != "0"
+
+
+def _flash_geometry(Bq, Nq, Nk, H, shared_kv):
+    HD = H * 64
+    if shared_kv:
+        return 1, Bq * Nq, Bq * Nq * HD, Nk * HD
+    return Bq, Nq, Nq * HD, Nk * HD
+
+
+def flash_attention_lse(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False):
+    """`flash_attention` that also returns the per-row statistic of its backward (gvd_flash_attention_lse):
+    (out, lse) with lse fp32 [B, H, rows rounded up to 128] = log2 sum_j exp2(s_ij * scale * log2 e)."""
+    lib = _n.nn()
+    B, nq, qs, ks = _flash_geometry(Bq, Nq, Nk, H, shared_kv)
+    out = torch.empty(Bq, Nq, H * 64, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, (nq + 127) // 128 * 128, dtype=torch.float32, device=q.device)
+    with _on_device(q.device):
+        _check(lib.gvd_flash_attention_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), int(B), int(nq),
+                                           int(Nk), int(H), int(qs), int(ks), float(scale), _stream()), lib, "gvd_flash_attention_lse")
+    return out, lse
+
+
+def flash_attention_bwd(q, k, v, out, lse, dout, Bq, Nq, Nk, H, scale, shared_kv=False, need_kv=True):
+    """(dq, dk, dv) of `flash_attention` from the forward's (out, lse), no score-sized intermediates
+    (gvd_flash_attention_bwd); dk = dv = None when need_kv is False."""
+    lib = _n.nn()
+    if shared_kv and need_kv:
+        raise NotImplementedError("flash_attention_bwd: shared keys/values are frozen-context projections (no dk/dv)")
+    B, nq, qs, ks = _flash_geometry(Bq, Nq, Nk, H, shared_kv)
+    q, k, v, out, dout = q.contiguous(), k.contiguous(), v.contiguous(), out.contiguous(), dout.contiguous()
+    dq = torch.empty_like(q)
+    dk, dv = (torch.empty_like(k), torch.empty_like(v)) if need_kv else (None, None)
+    delta = torch.empty_like(lse)
+    a = _n.FlashBwdArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                        dq.data_ptr(), _p(dk), _p(dv), int(B), int(nq), int(Nk), int(H), int(qs), int(ks), float(scale))
+    with _on_device(q.device):
+        _check(lib.gvd_flash_attention_bwd(C.byref(a), _stream()), lib, "gvd_flash_attention_bwd")
+    return dq, dk, dv
+
+
 def attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=False, max_score_bytes=6 << 30, head_dim=64):
     """softmax(q k^T * scale) v with head dim `head_dim` (64 in the U-Net; 512, one head, in the VAE's AttnBlock).
     q [Bq, Nq, H*64]; k, v [Bq, Nk, H*64] (or [1, Nk, H*64] when shared_kv: the same keys for every batch item, then

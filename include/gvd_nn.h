@@ -147,6 +147,35 @@ GVD_NN_API int gvd_temporal_attention(const void* q, const void* k, const void* 
 GVD_NN_API int gvd_flash_attention(const void* q, const void* k, const void* v, void* out, int B, int Nq, int Nk, int H,
                                    long long q_batch_stride, long long kv_batch_stride, float scale, gvd_nn_stream_t stream);
 
+/* The same forward, also writing the per-row statistic its backward needs: lse[b, h, i] = log2 sum_j exp2(s_ij * scale *
+ * log2 e), fp32, [B, H, Nqp] with Nqp = Nq rounded up to 128 (rows beyond Nq hold finite filler). */
+GVD_NN_API int gvd_flash_attention_lse(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk,
+                                       int H, long long q_batch_stride, long long kv_batch_stride, float scale,
+                                       gvd_nn_stream_t stream);
+
+/* Backward of gvd_flash_attention without materialising scores (the autograd adjoint of CrossAttention.forward,
+ * attention.py:81-144, as ddim_guidance.py:259-337 differentiates it): dq, and dk / dv unless both are NULL (keys and
+ * values projected from the frozen context).  out / lse are the forward's results, dout the incoming gradient; q, out,
+ * dout, dq share q_batch_stride, k, v, dk, dv share kv_batch_stride; delta is [B, H, Nqp] fp32 scratch (sum_d dO O).
+ * lse and delta must be 16-byte aligned.  P and dS are rounded to bf16 before their products, as in the reference's
+ * autocast backward; accumulation is fp32. */
+typedef struct GvdFlashBwdArgs {
+    const void* q;
+    const void* k;
+    const void* v;
+    const void* out;
+    const void* dout;
+    const float* lse;
+    float* delta;
+    void* dq;
+    void* dk;
+    void* dv;
+    int B, Nq, Nk, H;
+    long long q_batch_stride, kv_batch_stride;
+    float scale;
+} GvdFlashBwdArgs;
+GVD_NN_API int gvd_flash_attention_bwd(const GvdFlashBwdArgs* args, gvd_nn_stream_t stream);
+
 /* One DDIM update, fused (lvdm/models/samplers/ddim.py:206-280 with v-prediction, classifier-free guidance,
  * rescale_noise_cfg (utils_diffusion.py:147-158) and dynamic rescale).  All tensors fp32 with n elements (one batch
  * item); e_uncond may be NULL (no guidance).  scratch: 32 + 4*n bytes. */

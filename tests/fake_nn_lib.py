@@ -418,6 +418,49 @@ class FakeNN:
         view(out, Nq, qs).copy_(o.to(self.act))
         return 0
 
+    def gvd_flash_attention_lse(self, q, k, v, out, lse, B, Nq, Nk, H, qs, ks, scale, stream):
+        self._count("flash_attention_lse")
+        HD = H * 64
+
+        def view(ptr, n, bs):
+            ext = (B - 1) * bs + n * HD
+            return self._t(ptr, ext, self.act).as_strided((B, n, H, 64), (bs, HD, 64, 1))
+
+        qq, kk, vv = view(q, Nq, qs).float(), view(k, Nk, ks).float(), view(v, Nk, ks).float()
+        s = torch.einsum("bihd,bjhd->bhij", qq, kk) * scale
+        p = torch.softmax(s, dim=-1)
+        view(out, Nq, qs).copy_(torch.einsum("bhij,bjhd->bihd", self._rnd(p), vv).to(self.act))
+        ldl = (Nq + 127) // 128 * 128
+        L = self._f(lse, B, H, ldl)
+        L.zero_()
+        L[:, :, :Nq] = torch.logsumexp(s, dim=-1) * 1.4426950408889634
+        return 0
+
+    def gvd_flash_attention_bwd(self, args, stream):
+        self._count("flash_attention_bwd")
+        a = args._obj
+        B, Nq, Nk, H, scale = a.B, a.Nq, a.Nk, a.H, a.scale
+        HD = H * 64
+
+        def view(ptr, n, bs):
+            ext = (B - 1) * bs + n * HD
+            return self._t(ptr, ext, self.act).as_strided((B, n, H, 64), (bs, HD, 64, 1))
+
+        qs, ks = a.q_batch_stride, a.kv_batch_stride
+        qq, kk, vv = view(a.q, Nq, qs).float(), view(a.k, Nk, ks).float(), view(a.v, Nk, ks).float()
+        oo, do = view(a.out, Nq, qs).float(), view(a.dout, Nq, qs).float()
+        ldl = (Nq + 127) // 128 * 128
+        L = self._f(a.lse, B, H, ldl)[:, :, :Nq]
+        p = torch.exp2(torch.einsum("bihd,bjhd->bhij", qq, kk) * (scale * 1.4426950408889634) - L[..., None])
+        D = (do * oo).sum(-1).permute(0, 2, 1)  # [B, H, Nq]
+        dp = torch.einsum("bihd,bjhd->bhij", do, vv)
+        ds = self._rnd(p * (dp - D[..., None]))
+        view(a.dq, Nq, qs).copy_((torch.einsum("bhij,bjhd->bihd", ds, kk) * scale).to(self.act))
+        if a.dk:
+            view(a.dk, Nk, ks).copy_((torch.einsum("bhij,bihd->bjhd", ds, qq) * scale).to(self.act))
+            view(a.dv, Nk, ks).copy_(torch.einsum("bhij,bihd->bjhd", self._rnd(p), do).to(self.act))
+        return 0
+
     # ---- DDIM ----
     @staticmethod
     def _std_ratio(e_c, mo):

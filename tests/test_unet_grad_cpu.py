@@ -70,8 +70,8 @@ def test_forward_matches_reference_fp32(monkeypatch, tiny_ref):
 
 
 @needs_ref
-@pytest.mark.parametrize("seed,implicit", [(0, True), (1, True), (0, False)])
-def test_input_gradient_matches_autograd_of_reference(monkeypatch, tiny_ref, seed, implicit):
+@pytest.mark.parametrize("seed,implicit,fused_attn", [(0, True, True), (1, True, True), (0, False, False)])
+def test_input_gradient_matches_autograd_of_reference(monkeypatch, tiny_ref, seed, implicit, fused_attn):
     """d<y, g>/dx for a random cotangent g: ours (vc_b200.grad over the C-ABI stand-in) vs torch.autograd over the
     reference module -- the call `pred_x0.backward(gradient=..., inputs=x)` of ddim_guidance.py:309."""
     from vc_b200.unet import UNetB200
@@ -79,6 +79,7 @@ def test_input_gradient_matches_autograd_of_reference(monkeypatch, tiny_ref, see
     fake = install_fake(monkeypatch)
     from vc_b200 import ops
     monkeypatch.setattr(ops, "IMPLICIT_CONV", implicit)  # False: every convolution through im2col / col2im
+    monkeypatch.setattr(ops, "FUSED_FLASH_BWD", fused_attn)  # False: the attention adjoint re-materialises the scores
     ref, cfg, xin, ctx, _ = tiny_ref
     ours = UNetB200(ref.state_dict(), device="cpu", **cfg)
     ts, fs = torch.tensor([300 + 100 * seed]), torch.tensor([10])
@@ -97,8 +98,11 @@ def test_input_gradient_matches_autograd_of_reference(monkeypatch, tiny_ref, see
     assert err < 1e-4
     # every adjoint took part
     convs = ("conv_implicit",) if implicit else ("col2im3x3", "col2im_t3")
-    for name in ("groupnorm_bwd", "layernorm_bwd", "geglu_bwd", "softmax_bwd", "temporal_attention_bwd") + convs:
+    attn = ("flash_attention_lse", "flash_attention_bwd") if fused_attn else ("softmax_bwd",)
+    for name in ("groupnorm_bwd", "layernorm_bwd", "geglu_bwd", "temporal_attention_bwd") + convs + attn:
         assert fake.calls.get(name, 0) > 0, name
+    if fused_attn:
+        assert "softmax_bwd" not in fake.calls
     if not implicit:
         assert "conv_implicit" not in fake.calls
 

@@ -156,6 +156,70 @@ def test_attention_bwd(Bq, Nq, Nk, shared):
         assert _rel(dk, kf.grad) < 2e-2 and _rel(dv, vf.grad) < 2e-2
 
 
+@pytest.mark.parametrize("Bq,Nq,Nk,shared,spread", [(3, 256, 256, False, 1.0), (2, 200, 200, False, 3.0), (5, 128, 77, True, 1.0),
+                                                    (2, 384, 256, True, 3.0), (1, 129, 513, False, 2.0), (2, 1000, 77, False, 1.0),
+                                                    (2, 2560, 2560, False, 2.0), (1, 64, 1, False, 1.0)])
+def test_flash_attention_bwd_fused(Bq, Nq, Nk, shared, spread):
+    """The fused adjoint (csrc/attn_bwd_tc.cu, gvd_flash_attention_lse + gvd_flash_attention_bwd) against autograd over
+    fp32 softmax attention on the same bf16 inputs -- ragged tiles, one key, cross-attention widths, shared keys, the C4
+    self-attention length, and logits spread over +-20 (the lazily rescaled forward's statistic must still be exact).
+    Bar: the bf16 rounding of P / dS and of the outputs, relative L2 <= 2e-2 (measured ~4e-3); the row statistic itself
+    within 2e-3 absolute of torch.logsumexp in base 2."""
+    from vc_b200 import ops
+
+    H, D = 5, 64
+    q = _bf(Bq, Nq, H * D, seed=40)
+    k, v = _bf(1 if shared else Bq, Nk, H * D, seed=41, scale=spread), _bf(1 if shared else Bq, Nk, H * D, seed=42)
+    do = _bf(Bq, Nq, H * D, seed=43)
+    scale = D ** -0.5
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    kh, vh = (t.view(-1, Nk, H, D).expand(Bq, Nk, H, D) for t in (kf, vf))
+    s = torch.einsum("bihd,bjhd->bhij", qf.view(Bq, Nq, H, D), kh) * scale
+    o_ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vh).reshape(Bq, Nq, H * D)
+    o_ref.backward(do.float())
+    out, lse = ops.flash_attention_lse(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=shared)
+    assert torch.equal(out, ops.flash_attention(q, k, v, Bq, Nq, Nk, H, scale, shared_kv=shared))
+    lse_ref = torch.logsumexp(s.detach(), -1) * 1.4426950408889634  # [Bq, H, Nq]
+    if shared:
+        lse_ref = lse_ref.permute(1, 0, 2).reshape(1, H, Bq * Nq)
+    assert (lse[:, :, :lse_ref.shape[-1]] - lse_ref).abs().max().item() < 2e-3
+    dq, dk, dv = ops.flash_attention_bwd(q, k, v, out, lse, do, Bq, Nq, Nk, H, scale, shared_kv=shared, need_kv=not shared)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dq.float()).all()
+    if Nk == 1:  # softmax over one key is the constant 1: dQ = dK = 0 exactly in fp32, rounding dust here
+        assert dq.float().abs().max().item() < 1e-5 and dk.float().abs().max().item() < 1e-4
+        assert _rel(dv, vf.grad) < 1e-2
+        return
+    assert _rel(dq, qf.grad) < 2e-2, _rel(dq, qf.grad)
+    if not shared:
+        assert _rel(dk, kf.grad) < 2e-2 and _rel(dv, vf.grad) < 2e-2, (_rel(dk, kf.grad), _rel(dv, vf.grad))
+        # and against the first backward (scores materialised): same rounding points, so closer than either is to fp32
+        dq1, dk1, dv1 = ops.attention_bwd(q, k, v, do, Bq, Nq, Nk, H, scale, need_kv=True)
+        assert _rel(dq, dq1) < 2e-2 and _rel(dk, dk1) < 2e-2 and _rel(dv, dv1) < 2e-2
+
+
+def test_flash_attention_autograd_routes_to_fused_adjoint():
+    """vc_b200.grad.FlashAttention: forward under autograd saves (out, lse) and backward is the fused kernel; the
+    GVD_FLASH_BWD=0 route gives the same gradients within the bf16 bar."""
+    from vc_b200 import ops
+
+    H = 5
+    q, k, v = (_bf(2, 300, H * 64, seed=50 + i).requires_grad_(True) for i in range(3))
+    g = _bf(2, 300, H * 64, seed=53)
+    grads = []
+    for fused in (True, False):
+        ops.FUSED_FLASH_BWD = fused
+        try:
+            for t in (q, k, v):
+                t.grad = None
+            ops.flash_attention(q, k, v, 2, 300, 300, H, 0.125).backward(g)
+            grads.append([t.grad.clone() for t in (q, k, v)])
+        finally:
+            ops.FUSED_FLASH_BWD = True
+    for a, b in zip(*grads):
+        assert _rel(a, b) < 2e-2
+
+
 def test_pred_x0_vjp():
     from vc_b200 import ops
     from vc_b200.schedule import DdimSchedule, ModelSchedule
