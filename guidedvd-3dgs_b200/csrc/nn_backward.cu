@@ -15,6 +15,11 @@
 
 extern thread_local std::string g_nn_err_ext;
 
+#ifndef GVD_HOST_EMU
+bool gvd_mma_temporal_attention_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int B, int T,
+                                    long long S, int H, float scale, cudaStream_t s);
+#endif
+
 namespace {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }  // approximate reciprocal, <= 2 ulp
@@ -717,6 +722,17 @@ int gvd_temporal_attention_bwd(const void* q, const void* k, const void* v, cons
     if (T > 32 || T <= 0) { g_nn_err_ext = "gvd_temporal_attention_bwd: needs 1 <= T <= 32"; return 2; }
     const long long warps = (long long)B * S * H;
     if (warps <= 0) return 0;
+#ifndef GVD_HOST_EMU
+    {  // tattn_mma.cu: the five products on mma.sync tiles (default; GVD_TATTN_MMA=0 selects the first kernel for A/B timing)
+        static int on = -1;
+        if (on < 0) {
+            const char* e = getenv("GVD_TATTN_MMA");
+            on = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (on == 1 && gvd_mma_temporal_attention_bwd(q, k, v, dout, dq, dk, dv, B, T, S, H, scale, s))
+            return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
+#endif
     const int smem = (int)(TAB_WARPS * sizeof(TabSmem));
     static bool attr_set = false;
     if (!attr_set) {
