@@ -63,9 +63,11 @@ int grid_for(long long n, int block = 256, int cap = 148 * 16) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-// same chunking rule as the forward (nn_kernels.cu::gn_chunks): ~4 CTAs per SM in total, 16..4096 rows per CTA
+// One wave of CTAs: the backward kernels are resident two per SM (launch bounds below), so floor(296 / F) chunks per frame
+// keeps every CTA on the machine at once -- the rule it replaces (~592 CTAs) ran 2.03 waves at 25 frames.  16..4096 rows
+// per CTA.
 int gn_bwd_chunks(int F, long long S) {
-    long long want = (592 + F - 1) / F;
+    long long want = 296 / (F > 0 ? F : 1);
     long long maxc = (S + 15) / 16;
     long long minc = (S + 4095) / 4096;
     long long c = want < minc ? minc : want;
@@ -75,33 +77,61 @@ int gn_bwd_chunks(int F, long long S) {
     return (int)c;
 }
 
+// ---- a thread-private ring of 16-byte cp.async copies: GN_RING row steps in flight per thread whatever the register
+// budget (the first version kept two rows in registers: 16 warps per SM x 64 bytes could not cover the HBM latency --
+// profiles/r02_norm_bwd_bench_before.txt: 1.7 TB/s).  No slot is shared between threads, so no barrier is needed:
+// cp.async.wait_group orders a thread's own copies. ----
+constexpr int GN_RING = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef GVD_HOST_EMU
+    *reinterpret_cast<uint4*>(smem_dst) = *reinterpret_cast<const uint4*>(gsrc);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef GVD_HOST_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef GVD_HOST_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // ---------------- GroupNorm backward (channels-last) ----------------
 // y = act(xh * gamma + beta), xh = (x - mean) * rstd over S x cpg per (frame, group).  With g = dy * act'(.) * gamma:
 //     dx = rstd * (g - mean(g) - xh * mean(g * xh))            (means over the same S x cpg)
 // Pass 1 (this kernel): per (frame, chunk, group) partial sums of g and g * xh.  `stats` = (sum x, sum x^2) per
 // (frame, group) from gvd_groupnorm_cl_stats.  Thread layout as in the forward: a thread owns 8 channels, walks rows.
-__device__ __forceinline__ float gn_upstream(float xv, float d, float sc, float sf, float gm, int do_silu) {
-    float g = d * gm;
-    if (do_silu) {
-        const float z = fmaf(xv, sc, sf);
-        g *= dsilu(do_silu == 1 ? round_bf16(z) : z);  // mode 1: SiLU saw the bf16-rounded norm output
-    }
-    return g;
+// SILU: 0 none, 1 SiLU saw the bf16-rounded norm output (GroupNormSpecific), 2 SiLU in fp32 (plain nn.GroupNorm).
+template <int SILU>
+__device__ __forceinline__ float gn_dact(float xv, float sc, float sf) {
+    const float z = fmaf(xv, sc, sf);
+    return dsilu(SILU == 1 ? round_bf16(z) : z);
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ x,
-                                                             const __nv_bfloat16* __restrict__ dy,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             const float* __restrict__ stats, int S, int C, int groups,
-                                                             int rows_per_chunk, float eps, int do_silu, long long stat_rows,
-                                                             double* __restrict__ partial) {
-    extern __shared__ double gn_sh[];  // acc[groups*2] doubles, then mean[groups], rstd[groups] floats
+// merged-per-thread sums land in one of GN_COPIES shared copies (by row slot), so the shared atomics of the 6-32
+// threads that own the same channels do not serialise on one address
+constexpr int GN_COPIES = 8;
+
+template <int SILU>
+__global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const __nv_bfloat16* __restrict__ dy,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ stats, int S, int C, int groups,
+                                                                int rows_per_chunk, float eps, long long stat_rows,
+                                                                double* __restrict__ partial) {
+    extern __shared__ double gn_sh[];  // acc[GN_COPIES][groups*2] doubles, mean[groups], rstd[groups] floats, then the ring
     double* acc = gn_sh;
-    float* smean = reinterpret_cast<float*>(acc + groups * 2);
+    float* smean = reinterpret_cast<float*>(acc + GN_COPIES * groups * 2);
     float* srstd = smean + groups;
+    uint4* ring = reinterpret_cast<uint4*>(gn_sh) + (GN_COPIES * groups * 2 * sizeof(double) + groups * 2 * sizeof(float) + 15) / 16;
     const int f = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int cpg = C / groups, vecs = C / 8;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) acc[i] = 0.0;
+    for (int i = threadIdx.x; i < GN_COPIES * groups * 2; i += blockDim.x) acc[i] = 0.0;
     if (threadIdx.x < groups) {
         const double n = (double)stat_rows * cpg;  // rows behind the statistics (> S when they were summed across shards)
         const double s = stats[((size_t)f * groups + threadIdx.x) * 2], q = stats[((size_t)f * groups + threadIdx.x) * 2 + 1];
@@ -117,122 +147,169 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16
     const int rsub = threadIdx.x / vper;
     if (rsub < rows_par)
         for (int v = threadIdx.x % vper; v < vecs; v += vper) {
-            float sc[8], sf[8], gm[8], mu[8], rs[8], a1[8], a2[8];
+            float sc[8], sf[8], gm[8], mu[8], a1[8], a2[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int c = 8 * v + e, g = c / cpg;
                 mu[e] = smean[g];
-                rs[e] = srstd[g];
                 gm[e] = gamma[c];
-                sc[e] = rs[e] * gm[e];
+                sc[e] = srstd[g] * gm[e];
                 sf[e] = beta[c] - mu[e] * sc[e];
                 a1[e] = a2[e] = 0.f;
             }
             const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
             const uint4* din = reinterpret_cast<const uint4*>(dy + (size_t)f * S * C) + v;
-            auto accum = [&](const uint4& ux, const uint4& ud) {
+            const int first = r0 + rsub;
+            const int n = first < r1 ? (r1 - first + rows_par - 1) / rows_par : 0;
+#pragma unroll
+            for (int k = 0; k < GN_RING; ++k) {
+                if (k < n) {
+                    cp_async16(&ring[(2 * k) * 256 + threadIdx.x], xin + (size_t)(first + k * rows_par) * vecs);
+                    cp_async16(&ring[(2 * k + 1) * 256 + threadIdx.x], din + (size_t)(first + k * rows_par) * vecs);
+                }
+                cp_async_commit();
+            }
+            for (int k = 0; k < n; ++k) {
+                cp_async_wait<GN_RING - 1>();
+                const int slot = k % GN_RING;
+                const uint4 ux = ring[(2 * slot) * 256 + threadIdx.x], ud = ring[(2 * slot + 1) * 256 + threadIdx.x];
+                if (k + GN_RING < n) {
+                    cp_async16(&ring[(2 * slot) * 256 + threadIdx.x], xin + (size_t)(first + (k + GN_RING) * rows_par) * vecs);
+                    cp_async16(&ring[(2 * slot + 1) * 256 + threadIdx.x], din + (size_t)(first + (k + GN_RING) * rows_par) * vecs);
+                }
+                cp_async_commit();
                 float xv[8], dv[8];
                 unpack8(ux, xv);
                 unpack8(ud, dv);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float g = gn_upstream(xv[e], dv[e], sc[e], sf[e], gm[e], do_silu);
+                    // g / gamma: the factor gamma is applied once, to the sums
+                    const float g = SILU ? dv[e] * gn_dact<SILU>(xv[e], sc[e], sf[e]) : dv[e];
                     a1[e] += g;
-                    a2[e] = fmaf(g, (xv[e] - mu[e]) * rs[e], a2[e]);
+                    a2[e] = fmaf(g, xv[e] - mu[e], a2[e]);
                 }
-            };
-            int r = r0 + rsub;
-            for (; r + rows_par < r1; r += 2 * rows_par) {  // four independent 16-byte loads in flight per thread
-                const uint4 x0 = __ldg(xin + (size_t)r * vecs), d0 = __ldg(din + (size_t)r * vecs);
-                const uint4 x1 = __ldg(xin + (size_t)(r + rows_par) * vecs), d1 = __ldg(din + (size_t)(r + rows_par) * vecs);
-                accum(x0, d0);
-                accum(x1, d1);
             }
-            for (; r < r1; r += rows_par) accum(__ldg(xin + (size_t)r * vecs), __ldg(din + (size_t)r * vecs));
+            // channels of one group are summed in the thread first (cpg >= 8: at most two groups per thread)
+            double* my = acc + (rsub % GN_COPIES) * groups * 2;
+            int gcur = (8 * v) / cpg;
+            double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int g = (8 * v + e) / cpg;
-                atomicAdd(&acc[2 * g], (double)a1[e]);
-                atomicAdd(&acc[2 * g + 1], (double)a2[e]);
+                if (g != gcur) {
+                    atomicAdd(&my[2 * gcur], s1);
+                    atomicAdd(&my[2 * gcur + 1], s2 * (double)srstd[gcur]);
+                    s1 = s2 = 0.0;
+                    gcur = g;
+                }
+                s1 += (double)a1[e] * (double)gm[e];
+                s2 += (double)a2[e] * (double)gm[e];
             }
+            atomicAdd(&my[2 * gcur], s1);
+            atomicAdd(&my[2 * gcur + 1], s2 * (double)srstd[gcur]);
         }
     __syncthreads();
     double* out = partial + ((size_t)f * nchunks + chunk) * groups * 2;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = acc[i];
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+        double t = 0.0;
+#pragma unroll
+        for (int cpy = 0; cpy < GN_COPIES; ++cpy) t += acc[cpy * groups * 2 + i];
+        out[i] = t;
+    }
 }
 
-// Pass 2: dx from the folded sums.
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
-                                                           const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ stats, const double* __restrict__ partial,
-                                                           int S, int C, int groups, int nchunks, int rows_per_cta, float eps,
-                                                           int do_silu, long long stat_rows) {
-    extern __shared__ float gn_shf[];  // mean, rstd, m1, m2: [groups] each
-    float* smean = gn_shf;
+// Pass 2: dx from the folded sums.  With gr = gamma rstd, A = -rstd^2 m2, B = -rstd m1 - mean A (per channel):
+//     dx = dy act'(.) gr + x A + B
+template <int SILU>
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ stats, const double* __restrict__ partial,
+                                                              int S, int C, int groups, int nchunks, int rows_per_cta, float eps,
+                                                              long long stat_rows) {
+    extern __shared__ double gn_shd[];  // fold[256] doubles, then mean, rstd, m1, m2: [groups] floats each, then the ring
+    double* fold = gn_shd;
+    float* smean = reinterpret_cast<float*>(fold + 256);
     float* srstd = smean + groups;
     float* sm1 = srstd + groups;
     float* sm2 = sm1 + groups;
+    uint4* ring = reinterpret_cast<uint4*>(gn_shd) + (256 * sizeof(double) + groups * 4 * sizeof(float) + 15) / 16;
     const int f = blockIdx.y;
     const int cpg = C / groups, vecs = C / 8;
-    if (threadIdx.x < groups) {
-        const double n = (double)stat_rows * cpg;
-        const double s = stats[((size_t)f * groups + threadIdx.x) * 2], q = stats[((size_t)f * groups + threadIdx.x) * 2 + 1];
-        const double mean = s / n;
-        const double var = fmax(q / n - mean * mean, 0.0);
-        smean[threadIdx.x] = (float)mean;
-        srstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-        double b1 = 0.0, b2 = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-            const double* p = partial + ((size_t)f * nchunks + c) * groups * 2 + 2 * threadIdx.x;
-            b1 += p[0];
-            b2 += p[1];
+    {  // the chunks' partial sums, folded by all threads: entry i = tid % (2 groups), every (256 / (2 groups))-th chunk
+        const int width = groups * 2, parts = 256 / width;
+        const int i = threadIdx.x % width, part = threadIdx.x / width;
+        double t = 0.0;
+        if (part < parts)
+            for (int c = part; c < nchunks; c += parts) t += partial[((size_t)f * nchunks + c) * width + i];
+        fold[threadIdx.x] = t;
+        __syncthreads();
+        if (threadIdx.x < groups) {
+            const double n = (double)stat_rows * cpg;
+            const double s = stats[((size_t)f * groups + threadIdx.x) * 2], q = stats[((size_t)f * groups + threadIdx.x) * 2 + 1];
+            const double mean = s / n;
+            const double var = fmax(q / n - mean * mean, 0.0);
+            smean[threadIdx.x] = (float)mean;
+            srstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+            double b1 = 0.0, b2 = 0.0;
+            for (int pp = 0; pp < parts; ++pp) {
+                b1 += fold[pp * width + 2 * threadIdx.x];
+                b2 += fold[pp * width + 2 * threadIdx.x + 1];
+            }
+            sm1[threadIdx.x] = (float)(b1 / n);
+            sm2[threadIdx.x] = (float)(b2 / n);
         }
-        sm1[threadIdx.x] = (float)(b1 / n);
-        sm2[threadIdx.x] = (float)(b2 / n);
+        __syncthreads();
     }
-    __syncthreads();
     const int vper = vecs <= 256 ? vecs : 256;
     const int rows_par = vecs <= 256 ? 256 / vecs : 1;
     const int rsub = threadIdx.x / vper;
     if (rsub >= rows_par) return;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
     for (int v = threadIdx.x % vper; v < vecs; v += vper) {
-        float sc[8], sf[8], gm[8], mu[8], rs[8], m1[8], m2[8];
+        float sc[8], sf[8], gr[8], ca[8], cb[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = 8 * v + e, g = c / cpg;
-            mu[e] = smean[g];
-            rs[e] = srstd[g];
-            m1[e] = sm1[g];
-            m2[e] = sm2[g];
-            gm[e] = gamma[c];
-            sc[e] = rs[e] * gm[e];
-            sf[e] = beta[c] - mu[e] * sc[e];
+            const float mu = smean[g], rs = srstd[g], gm = gamma[c];
+            sc[e] = rs * gm;
+            sf[e] = beta[c] - mu * sc[e];
+            gr[e] = gm * rs;
+            ca[e] = -rs * rs * sm2[g];
+            cb[e] = -rs * sm1[g] - mu * ca[e];
         }
         const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
         const uint4* din = reinterpret_cast<const uint4*>(dy + (size_t)f * S * C) + v;
         uint4* dout = reinterpret_cast<uint4*>(dx + (size_t)f * S * C) + v;
-        auto dx8 = [&](const uint4& ux, const uint4& ud) {
+        const int first = r0 + rsub;
+        const int n = first < r1 ? (r1 - first + rows_par - 1) / rows_par : 0;
+#pragma unroll
+        for (int k = 0; k < GN_RING; ++k) {
+            if (k < n) {
+                cp_async16(&ring[(2 * k) * 256 + threadIdx.x], xin + (size_t)(first + k * rows_par) * vecs);
+                cp_async16(&ring[(2 * k + 1) * 256 + threadIdx.x], din + (size_t)(first + k * rows_par) * vecs);
+            }
+            cp_async_commit();
+        }
+        for (int k = 0; k < n; ++k) {
+            cp_async_wait<GN_RING - 1>();
+            const int slot = k % GN_RING;
+            const uint4 ux = ring[(2 * slot) * 256 + threadIdx.x], ud = ring[(2 * slot + 1) * 256 + threadIdx.x];
+            if (k + GN_RING < n) {
+                cp_async16(&ring[(2 * slot) * 256 + threadIdx.x], xin + (size_t)(first + (k + GN_RING) * rows_par) * vecs);
+                cp_async16(&ring[(2 * slot + 1) * 256 + threadIdx.x], din + (size_t)(first + (k + GN_RING) * rows_par) * vecs);
+            }
+            cp_async_commit();
             float xv[8], dv[8], o[8];
             unpack8(ux, xv);
             unpack8(ud, dv);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float g = gn_upstream(xv[e], dv[e], sc[e], sf[e], gm[e], do_silu);
-                const float xh = (xv[e] - mu[e]) * rs[e];
-                o[e] = rs[e] * (g - m1[e] - xh * m2[e]);
+                const float g = SILU ? dv[e] * gn_dact<SILU>(xv[e], sc[e], sf[e]) : dv[e];
+                o[e] = fmaf(g, gr[e], fmaf(xv[e], ca[e], cb[e]));
             }
-            return pack8(o);
-        };
-        int r = r0 + rsub;
-        for (; r + rows_par < r1; r += 2 * rows_par) {  // four independent 16-byte loads in flight per thread
-            const uint4 x0 = __ldg(xin + (size_t)r * vecs), d0 = __ldg(din + (size_t)r * vecs);
-            const uint4 x1 = __ldg(xin + (size_t)(r + rows_par) * vecs), d1 = __ldg(din + (size_t)(r + rows_par) * vecs);
-            dout[(size_t)r * vecs] = dx8(x0, d0);
-            dout[(size_t)(r + rows_par) * vecs] = dx8(x1, d1);
+            dout[(size_t)(first + k * rows_par) * vecs] = pack8(o);
         }
-        for (; r < r1; r += rows_par) dout[(size_t)r * vecs] = dx8(__ldg(xin + (size_t)r * vecs), __ldg(din + (size_t)r * vecs));
     }
 }
 
@@ -246,6 +323,29 @@ __global__ void __launch_bounds__(256) gn_bwd_fold_kernel(const double* __restri
         for (int c = 0; c < nchunks; ++c) a += partial[((size_t)f * nchunks + c) * groups * 2 + i];
         sums[(size_t)f * groups * 2 + i] = a;
     }
+}
+
+// dynamic shared memory of the two kernels above (group arrays + the cp.async ring)
+inline size_t gn_bwd_partial_smem(int groups) {
+    return (GN_COPIES * groups * 2 * sizeof(double) + groups * 2 * sizeof(float) + 15) / 16 * 16 + (size_t)GN_RING * 2 * 256 * 16;
+}
+inline size_t gn_bwd_apply_smem(int groups) { return (256 * sizeof(double) + groups * 4 * sizeof(float) + 15) / 16 * 16 + (size_t)GN_RING * 2 * 256 * 16; }
+
+void launch_gn_bwd_partial(int do_silu, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* gamma,
+                           const float* beta, const float* stats, int S, int C, int groups, int rows_per_chunk, float eps, long long stat_rows,
+                           double* partial) {
+    const size_t sm = gn_bwd_partial_smem(groups);
+    if (do_silu == 0) gn_bwd_partial_kernel<0><<<grid, 256, sm, s>>>(x, dy, gamma, beta, stats, S, C, groups, rows_per_chunk, eps, stat_rows, partial);
+    else if (do_silu == 1) gn_bwd_partial_kernel<1><<<grid, 256, sm, s>>>(x, dy, gamma, beta, stats, S, C, groups, rows_per_chunk, eps, stat_rows, partial);
+    else gn_bwd_partial_kernel<2><<<grid, 256, sm, s>>>(x, dy, gamma, beta, stats, S, C, groups, rows_per_chunk, eps, stat_rows, partial);
+}
+void launch_gn_bwd_apply(int do_silu, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx,
+                         const float* gamma, const float* beta, const float* stats, const double* partial, int S, int C, int groups, int nchunks,
+                         int rows_per_cta, float eps, long long stat_rows) {
+    const size_t sm = gn_bwd_apply_smem(groups);
+    if (do_silu == 0) gn_bwd_apply_kernel<0><<<grid, 256, sm, s>>>(x, dy, dx, gamma, beta, stats, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
+    else if (do_silu == 1) gn_bwd_apply_kernel<1><<<grid, 256, sm, s>>>(x, dy, dx, gamma, beta, stats, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
+    else gn_bwd_apply_kernel<2><<<grid, 256, sm, s>>>(x, dy, dx, gamma, beta, stats, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
 }
 
 // ---------------- LayerNorm backward over the last dim (one warp per row) ----------------
@@ -604,11 +704,10 @@ int gvd_groupnorm_cl_bwd(const void* x, const void* dy, void* dx, const float* g
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_bytes < (size_t)F * nchunks * groups * 2 * sizeof(double)) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: scratch too small"; return 2; }
     double* partial = reinterpret_cast<double*>(tmp);
-    gn_bwd_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(double) + groups * 2 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups, rows_per_chunk, eps, do_silu, S, partial);
-    gn_bwd_apply_kernel<<<dim3(nchunks, F), 256, groups * 4 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats, partial, (int)S, C, groups, nchunks,
-        rows_per_chunk, eps, do_silu, S);
+    launch_gn_bwd_partial(do_silu, dim3(nchunks, F), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups,
+                          rows_per_chunk, eps, S, partial);
+    launch_gn_bwd_apply(do_silu, dim3(nchunks, F), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats,
+                        partial, (int)S, C, groups, nchunks, rows_per_chunk, eps, S);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -629,9 +728,8 @@ int gvd_groupnorm_cl_bwd_sums(const void* x, const void* dy, const float* gamma,
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_bytes < (size_t)F * nchunks * groups * 2 * sizeof(double)) { g_nn_err_ext = "gvd_groupnorm_cl_bwd_sums: scratch too small"; return 2; }
     double* partial = reinterpret_cast<double*>(tmp);
-    gn_bwd_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(double) + groups * 2 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups, rows_per_chunk, eps, do_silu, stat_rows,
-        partial);
+    launch_gn_bwd_partial(do_silu, dim3(nchunks, F), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups,
+                          rows_per_chunk, eps, stat_rows, partial);
     gn_bwd_fold_kernel<<<F, 256, 0, s>>>(partial, sums, nchunks, groups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd_sums: ") + cudaGetErrorString(e); return 1; }
@@ -652,9 +750,8 @@ int gvd_groupnorm_cl_bwd_apply(const void* x, const void* dy, void* dx, const fl
     const int rows_per_cta = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_cta - 1) / rows_per_cta);
     // the folded sums stand in for a one-chunk partial array
-    gn_bwd_apply_kernel<<<dim3(nchunks, F), 256, groups * 4 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats, sums, (int)S, C, groups, 1, rows_per_cta,
-        eps, do_silu, stat_rows);
+    launch_gn_bwd_apply(do_silu, dim3(nchunks, F), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats,
+                        sums, (int)S, C, groups, 1, rows_per_cta, eps, stat_rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd_apply: ") + cudaGetErrorString(e); return 1; }
     return 0;

@@ -65,16 +65,45 @@ __device__ __forceinline__ float warp_max(float v) {
 // x [F, S, C]; group g = channels [g*cpg, (g+1)*cpg); statistics over S x cpg per (frame, group).
 // Thread layout: a thread owns one 16-byte vector of 8 channels and walks rows; the CTA covers
 // (256 / (C/8)) rows per step, so every load is a full coalesced 16-byte access.
+//
+// Rows reach the thread through a thread-private ring of GN_RING 16-byte cp.async copies (no slot is shared, so
+// cp.async.wait_group is the only ordering needed): the bytes in flight no longer depend on the register budget.  What the
+// first version lost (profiles/r02_norm_bwd_bench_before.txt: 2.1-2.9 TB/s over the three passes) was (1) the merge of
+// the per-thread sums -- 16 shared atomics per thread on 64 addresses, serialised, longer than the CTA's whole stream --
+// (2) a 24-deep serial chain of L2 loads in front of every apply CTA (the fold of the chunk partials by 32 threads) and
+// (3) 600 CTAs on 592 slots: two waves.
+constexpr int GN_RING = 4;
+constexpr int GN_COPIES = 8;  // shared copies of the per-group sums, picked by row slot
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef GVD_HOST_EMU
+    *reinterpret_cast<uint4*>(smem_dst) = *reinterpret_cast<const uint4*>(gsrc);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef GVD_HOST_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef GVD_HOST_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // Pass 1: grid (chunks, F): partial (sum, sumsq) per (frame, chunk, group).
-__global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int groups,
-                                                         int rows_per_chunk, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 4) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int groups,
+                                                            int rows_per_chunk, float* __restrict__ partial) {
     // Per-thread fp32 sums are merged in 2^-20 fixed point: integer adds commute, so the statistics (and with them the
     // whole denoiser) are bit-reproducible run to run, whatever order the atomics land in.
-    extern __shared__ unsigned long long sh_fix[];  // [groups*2]
+    extern __shared__ unsigned long long sh_fix[];  // [GN_COPIES][groups*2], then the ring
     unsigned long long* sh = sh_fix;
+    uint4* ring = reinterpret_cast<uint4*>(sh_fix) + (GN_COPIES * groups * 2 * sizeof(unsigned long long) + 15) / 16;
     const int f = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int cpg = C / groups, vecs = C / 8;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0ull;
+    for (int i = threadIdx.x; i < GN_COPIES * groups * 2; i += blockDim.x) sh[i] = 0ull;
     __syncthreads();
     const int r0 = chunk * rows_per_chunk, r1 = min(S, r0 + rows_per_chunk);
     // vecs <= 256: 256/vecs rows in flight per step; wider rows: one row per step, threads stride over the vectors
@@ -87,24 +116,19 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
 #pragma unroll
         for (int e = 0; e < 8; ++e) sm[e] = sq[e] = 0.f;
         const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)f * S * C) + v;
-        int r = r0 + rsub;
-        for (; r + 3 * rows_par < r1; r += 4 * rows_par) {  // four independent 16-byte loads in flight per thread
-            uint4 u[4];
+        const int first = r0 + rsub;
+        const int n = first < r1 ? (r1 - first + rows_par - 1) / rows_par : 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = __ldg(base + (size_t)(r + k * rows_par) * vecs);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 t = __bfloat1622float2(h2[e]);
-                    sm[2 * e] += t.x; sq[2 * e] += t.x * t.x;
-                    sm[2 * e + 1] += t.y; sq[2 * e + 1] += t.y * t.y;
-                }
-            }
+        for (int k = 0; k < GN_RING; ++k) {
+            if (k < n) cp_async16(&ring[k * 256 + threadIdx.x], base + (size_t)(first + k * rows_par) * vecs);
+            cp_async_commit();
         }
-        for (; r < r1; r += rows_par) {
-            const uint4 u = __ldg(base + (size_t)r * vecs);
+        for (int k = 0; k < n; ++k) {
+            cp_async_wait<GN_RING - 1>();
+            const int slot = k % GN_RING;
+            const uint4 u = ring[slot * 256 + threadIdx.x];
+            if (k + GN_RING < n) cp_async16(&ring[slot * 256 + threadIdx.x], base + (size_t)(first + (k + GN_RING) * rows_par) * vecs);
+            cp_async_commit();
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -113,50 +137,82 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
                 sm[2 * e + 1] += t.y; sq[2 * e + 1] += t.y * t.y;
             }
         }
+        // the channels of one group are added up in the thread first -- as integers, so nothing about the result changes
+        unsigned long long* my = sh + (rsub % GN_COPIES) * groups * 2;
+        int gcur = (8 * v) / cpg;
+        unsigned long long f1 = 0ull, f2 = 0ull;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int g = (8 * v + e) / cpg;
-            atomicAdd(&sh[2 * g], (unsigned long long)__double2ll_rn((double)sm[e] * 1048576.0));
-            atomicAdd(&sh[2 * g + 1], (unsigned long long)__double2ll_rn((double)sq[e] * 1048576.0));
+            if (g != gcur) {
+                atomicAdd(&my[2 * gcur], f1);
+                atomicAdd(&my[2 * gcur + 1], f2);
+                f1 = f2 = 0ull;
+                gcur = g;
+            }
+            f1 += (unsigned long long)__double2ll_rn((double)sm[e] * 1048576.0);
+            f2 += (unsigned long long)__double2ll_rn((double)sq[e] * 1048576.0);
         }
+        atomicAdd(&my[2 * gcur], f1);
+        atomicAdd(&my[2 * gcur + 1], f2);
     }
     __syncthreads();
     float* out = partial + ((size_t)f * nchunks + chunk) * groups * 2;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = (float)((double)(long long)sh[i] * (1.0 / 1048576.0));
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int cpy = 0; cpy < GN_COPIES; ++cpy) t += sh[cpy * groups * 2 + i];
+        out[i] = (float)((double)(long long)t * (1.0 / 1048576.0));
+    }
+}
+
+// The chunk partials of frame f folded by a whole 256-thread CTA: entry i = tid % (2 groups) of every (256 / (2 groups))-th
+// chunk, then the parts in fixed order.  Afterwards fold[i], i < 2 groups, holds (sum, sumsq) interleaved per group.
+// (Both callers use this one decomposition, so the fused and the split entry points see the same bits.)
+__device__ __forceinline__ void gn_fold_frame(const float* __restrict__ partial, int nchunks, int groups, int f, double* fold) {
+    const int width = groups * 2, parts = 256 / width;
+    const int i = threadIdx.x % width, part = threadIdx.x / width;
+    double t = 0.0;
+    if (part < parts)
+        for (int c = part; c < nchunks; c += parts) t += partial[((size_t)f * nchunks + c) * width + i];
+    fold[threadIdx.x] = t;
+    __syncthreads();
+    double a = 0.0;
+    if (threadIdx.x < width)
+        for (int pp = 0; pp < parts; ++pp) a += fold[pp * width + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < width) fold[threadIdx.x] = a;
+    __syncthreads();
 }
 
 // Fold the per-chunk partials of one frame into (sum, sumsq) per group: the exchange unit when the rows of a group are
 // spread over several GPUs.
 __global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks,
                                                       int groups) {
+    __shared__ double fold[256];
     const int f = blockIdx.x;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
-        double a = 0.0;
-        for (int c = 0; c < nchunks; ++c) a += partial[((size_t)f * nchunks + c) * groups * 2 + i];
-        stats[(size_t)f * groups * 2 + i] = (float)a;
-    }
+    gn_fold_frame(partial, nchunks, groups, f, fold);
+    if (threadIdx.x < groups * 2) stats[(size_t)f * groups * 2 + threadIdx.x] = (float)fold[threadIdx.x];
 }
 
 // Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU.
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ partial, int S, int C, int groups,
-                                                       int nchunks, int rows_per_cta, float eps, int do_silu,
-                                                       long long stat_rows) {
-    extern __shared__ float sh[];  // mean[groups], rstd[groups]
+template <int SILU>
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ partial, int S, int C, int groups,
+                                                          int nchunks, int rows_per_cta, float eps, long long stat_rows) {
+    extern __shared__ double gn_shd[];  // fold[256] doubles, mean[groups], rstd[groups] floats, then the ring
+    double* fold = gn_shd;
+    float* sh = reinterpret_cast<float*>(fold + 256);
+    uint4* ring = reinterpret_cast<uint4*>(gn_shd) + (256 * sizeof(double) + groups * 2 * sizeof(float) + 15) / 16;
     const int f = blockIdx.y;
     const int cpg = C / groups, vecs = C / 8;
+    gn_fold_frame(partial, nchunks, groups, f, fold);
     if (threadIdx.x < groups) {
-        double s = 0.0, q = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-            const float* p = partial + ((size_t)f * nchunks + c) * groups * 2 + 2 * threadIdx.x;
-            s += p[0];
-            q += p[1];
-        }
         // the split entry points (gvd_groupnorm_cl_stats -> _apply) hand the folded sums over as floats: round here too, so
         // the fused call and the split one normalise with the same bits (the guided tape must not change the forward)
-        s = (double)(float)s;
-        q = (double)(float)q;
+        const double s = (double)(float)fold[2 * threadIdx.x];
+        const double q = (double)(float)fold[2 * threadIdx.x + 1];
         const double n = (double)stat_rows * cpg;  // rows behind the sums (> S when the sums were added up across shards)
         const double mean = s / n;
         const double var = fmax(q / n - mean * mean, 0.0);
@@ -186,10 +242,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
         for (int e = 0; e < 4; ++e) {
             const float2 t = __bfloat1622float2(h2[e]);
             float a = fmaf(t.x, sc[2 * e], sf[2 * e]), b = fmaf(t.y, sc[2 * e + 1], sf[2 * e + 1]);
-            if (do_silu == 1) {  // GroupNormSpecific casts its output to bf16 before nn.SiLU sees it (basics.py:76-78)
+            if (SILU == 1) {  // GroupNormSpecific casts its output to bf16 before nn.SiLU sees it (basics.py:76-78)
                 a = silu(__bfloat162float(__float2bfloat16(a)));
                 b = silu(__bfloat162float(__float2bfloat16(b)));
-            } else if (do_silu == 2) {  // plain nn.GroupNorm returns fp32 under autocast: SiLU in fp32, one rounding at the end
+            } else if (SILU == 2) {  // plain nn.GroupNorm returns fp32 under autocast: SiLU in fp32, one rounding at the end
                 a = silu(a);
                 b = silu(b);
             }
@@ -197,15 +253,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
         }
         return u;
     };
-    int r = r0 + rsub;
-    for (; r + 3 * rows_par < r1; r += 4 * rows_par) {  // four independent 16-byte loads in flight per thread
-        uint4 u[4];
+    const int first = r0 + rsub;
+    const int n = first < r1 ? (r1 - first + rows_par - 1) / rows_par : 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = __ldg(xin + (size_t)(r + k * rows_par) * vecs);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) yout[(size_t)(r + k * rows_par) * vecs] = norm8(u[k]);
+    for (int k = 0; k < GN_RING; ++k) {
+        if (k < n) cp_async16(&ring[k * 256 + threadIdx.x], xin + (size_t)(first + k * rows_par) * vecs);
+        cp_async_commit();
     }
-    for (; r < r1; r += rows_par) yout[(size_t)r * vecs] = norm8(__ldg(xin + (size_t)r * vecs));
+    for (int k = 0; k < n; ++k) {
+        cp_async_wait<GN_RING - 1>();
+        const int slot = k % GN_RING;
+        const uint4 u = ring[slot * 256 + threadIdx.x];
+        if (k + GN_RING < n) cp_async16(&ring[slot * 256 + threadIdx.x], xin + (size_t)(first + (k + GN_RING) * rows_par) * vecs);
+        cp_async_commit();
+        yout[(size_t)(first + k * rows_par) * vecs] = norm8(u);
+    }
     }
 }
 
@@ -546,7 +608,7 @@ __global__ void __launch_bounds__(256) ddim_update_kernel(const float* __restric
 }
 
 int gn_chunks(int F, long long S) {
-    long long want = (592 + F - 1) / F;            // ~4 CTAs per SM in total
+    long long want = 592 / (F > 0 ? F : 1);        // one wave: the kernels are resident four per SM (148 x 4 slots), never more CTAs than slots
     long long maxc = (S + 15) / 16;                // at least 16 rows per CTA
     long long minc = (S + 4095) / 4096;            // at most 4096 rows per CTA
     long long c = want < minc ? minc : want;
@@ -554,6 +616,17 @@ int gn_chunks(int F, long long S) {
     if (c < 1) c = 1;
     if (c > 2048) c = 2048;
     return (int)c;
+}
+
+inline size_t gn_partial_smem(int groups) {
+    return (GN_COPIES * groups * 2 * sizeof(unsigned long long) + 15) / 16 * 16 + (size_t)GN_RING * 256 * 16;
+}
+void launch_gn_apply(int do_silu, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamma, const float* beta,
+                     const float* partial, int S, int C, int groups, int nchunks, int rows_per_cta, float eps, long long stat_rows) {
+    const size_t sm = (256 * sizeof(double) + groups * 2 * sizeof(float) + 15) / 16 * 16 + (size_t)GN_RING * 256 * 16;
+    if (do_silu == 1) gn_apply_kernel<1><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
+    else if (do_silu == 2) gn_apply_kernel<2><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
+    else gn_apply_kernel<0><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
 }
 
 int grid_for(long long n, int block = 256, int cap = 148 * 16) {
@@ -584,11 +657,10 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
-    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(unsigned long long), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
-                                                                                 rows_per_chunk, tmp);
+    gn_partial_kernel<<<dim3(nchunks, F), 256, gn_partial_smem(groups), s>>>((const __nv_bfloat16*)x, (int)S, C, groups, rows_per_chunk, tmp);
     const int rows_per_cta = rows_per_chunk;
-    gn_apply_kernel<<<dim3((unsigned)nchunks, F), 256, groups * 2 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups, nchunks, rows_per_cta, eps, do_silu, S);
+    launch_gn_apply(do_silu, dim3((unsigned)nchunks, F), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups,
+                    nchunks, rows_per_cta, eps, S);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -607,8 +679,7 @@ int gvd_groupnorm_cl_stats(const void* x, float* stats, int F, long long S, int 
     const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
     if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl_stats: scratch too small"; return 2; }
-    gn_partial_kernel<<<dim3(nchunks, F), 256, groups * 2 * sizeof(unsigned long long), s>>>((const __nv_bfloat16*)x, (int)S, C, groups,
-                                                                                 rows_per_chunk, tmp);
+    gn_partial_kernel<<<dim3(nchunks, F), 256, gn_partial_smem(groups), s>>>((const __nv_bfloat16*)x, (int)S, C, groups, rows_per_chunk, tmp);
     gn_fold_kernel<<<F, 256, 0, s>>>(tmp, stats, nchunks, groups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_stats: ") + cudaGetErrorString(e); return 1; }
@@ -626,8 +697,8 @@ int gvd_groupnorm_cl_apply(const void* x, void* y, const float* gamma, const flo
     int nchunks = gn_chunks(F, S);
     const int rows_per_cta = (int)((S + nchunks - 1) / nchunks);
     nchunks = (int)((S + rows_per_cta - 1) / rows_per_cta);
-    gn_apply_kernel<<<dim3((unsigned)nchunks, F), 256, groups * 2 * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, (int)S, C, groups, 1, rows_per_cta, eps, do_silu, stat_rows);
+    launch_gn_apply(do_silu, dim3((unsigned)nchunks, F), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, (int)S, C, groups, 1,
+                    rows_per_cta, eps, stat_rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_apply: ") + cudaGetErrorString(e); return 1; }
     return 0;
