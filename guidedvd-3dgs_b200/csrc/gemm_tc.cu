@@ -805,6 +805,29 @@ int tma_group() {
     return g;
 }
 
+// Column split for outputs that are neither narrow nor a multiple of 256 (N = 320, 640 in the U-Net): the leading
+// floor(N / 256) * 256 columns run on 256-wide tiles (96 B/clk of shared-memory operand traffic per SM, pairs at 64) and
+// only the remainder on a narrow tile, instead of everything on 128-wide tiles, which need the whole 128 B/clk and pad
+// N = 320 to 384.  Two launches, same k order per output element -- bit-identical results.  GVD_GEMM_SPLIT=0 turns it off.
+// Measured (profiles/r02_gemm_split_sweep.txt): implicit convolutions gain 16-23 % (25 x 72 x 128, 320 -> 320: 874 -> 1042
+// TFLOP/s; 36 x 64, 640 -> 640: 1008 -> 1241), linears only from K ~ 2560 (+5 %); below that the narrow launch is a second
+// HBM pass over A for a sliver of the flops and the split LOSES 15-22 % (K = 320: 590 -> 458), so plain GEMMs split from
+// K = 2048 and convolutions -- whose A operand is re-read nine times out of L2 anyway -- always.
+bool split_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GVD_GEMM_SPLIT");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+int split_columns(long long M, int N, int K, int batch, bool conv) {
+    if (!split_enabled() || N <= 256 || (N % 256) == 0 || (N % 8) != 0) return 0;
+    if (!conv && K < 2048) return 0;
+    if (((M + BM - 1) / BM) * batch < 148) return 0;  // each launch should fill the machine on its own
+    return N / 256 * 256;
+}
+
 bool use_pair(long long M, int N, int K, int batch, int bn) {
     if (!pair_enabled() || bn != 256 || K < 640) return false;
     const long long t128 = (M + 127) / 128, t256 = (M + 255) / 256, tn = (N + bn - 1) / bn;
@@ -815,6 +838,9 @@ bool use_pair(long long M, int N, int K, int batch, int bn) {
 }
 
 }  // namespace
+
+static int conv_columns(const GvdConvArgs* a, const CUtensorMap& ta, long long M, int batch_h, int batch_b, int taps, int kpt, int n_first,
+                        int N, cudaStream_t s);
 
 extern "C" {
 
@@ -874,6 +900,18 @@ int gvd_gemm_bf16(const GvdGemmArgs* a, gvd_nn_stream_t stream_) {
         return 0;
     }
     if (aligned_out && total_tiles128 < (1ll << 30)) {
+        if (const int n1 = split_columns(a->M, a->N, a->K, a->batch_h * a->batch_b, false)) {
+            GvdGemmArgs lo = *a, hi = *a;
+            lo.N = n1;
+            hi.N = a->N - n1;
+            hi.B = reinterpret_cast<const __nv_bfloat16*>(a->B) + (long long)n1 * a->ldb;
+            hi.C = reinterpret_cast<__nv_bfloat16*>(a->C) + n1;
+            if (a->bias) hi.bias = a->bias + n1;
+            if (a->bias2) hi.bias2 = a->bias2 + n1;
+            if (a->residual) hi.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual) + n1;
+            const int r = gvd_gemm_bf16(&lo, stream_);
+            return r ? r : gvd_gemm_bf16(&hi, stream_);
+        }
         // tile width: least padding of N, ties to the wider tile (fewer A re-reads); 64 only for narrow outputs
         auto padded = [&](int bn) { return (long long)((a->N + bn - 1) / bn) * bn; };
         int bn = 128;
@@ -971,7 +1009,7 @@ int gvd_conv_bf16(const GvdConvArgs* a, gvd_nn_stream_t stream_) {
         box[2] = 1;
     }
     if (M >= (1ll << 31)) { g_nn_err = "gvd_conv_bf16: more than 2^31 pixels per frame"; return 2; }
-    CUtensorMap ta, tb;
+    CUtensorMap ta;
     if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->x), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
@@ -979,15 +1017,34 @@ int gvd_conv_bf16(const GvdConvArgs* a, gvd_nn_stream_t stream_) {
         return 1;
     }
     const int N = a->Cout;
+    if (const int n1 = split_columns(M, N, taps * a->Cin, batch_h * batch_b, true)) {
+        // y keeps its row stride Cout: the narrow launch below must write with ldc = the full Cout, so the split lives in
+        // conv_columns(), which takes the column window explicitly
+        const int r = conv_columns(a, ta, M, batch_h, batch_b, taps, kpt, 0, n1, s);
+        return r ? r : conv_columns(a, ta, M, batch_h, batch_b, taps, kpt, n1, N - n1, s);
+    }
+    return conv_columns(a, ta, M, batch_h, batch_b, taps, kpt, 0, N, s);
+}
+
+}  // extern "C"
+
+// output columns [n_first, n_first + N) of the implicit-GEMM convolution whose activation map is `ta`
+static int conv_columns(const GvdConvArgs* a, const CUtensorMap& ta, long long M, int batch_h, int batch_b, int taps, int kpt, int n_first,
+                        int N, cudaStream_t s) {
+    const long long C = a->Cin;
     const long long Kw = (long long)taps * C;
+    CUtensorMap tb;
     auto padded = [&](int bn) { return (long long)((N + bn - 1) / bn) * bn; };
     int bn = 128;
     if (N <= 64) bn = 64;
     else if (padded(256) <= padded(128)) bn = 256;
     const bool pair = use_pair(M, N, taps * a->Cin, batch_h * batch_b, bn);
-    if (!make_tmap(&tb, a->weight, Kw, N, 1, 1, Kw, 0, 0, pair ? bn / 2 : bn)) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the weight map"; return 1; }
-    const long long ldc = N;
-    EpiParams p{a->y, ldc, (long long)M * ldc, (long long)batch_h * M * ldc, a->bias, a->bias2, a->residual, 1.0f, a->act, 0,
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(a->weight) + (long long)n_first * Kw;
+    if (!make_tmap(&tb, w, Kw, N, 1, 1, Kw, 0, 0, pair ? bn / 2 : bn)) { g_nn_err = "gvd_conv_bf16: cuTensorMapEncodeTiled failed for the weight map"; return 1; }
+    const long long ldc = a->Cout;
+    EpiParams p{reinterpret_cast<__nv_bfloat16*>(a->y) + n_first, ldc, (long long)M * ldc, (long long)batch_h * M * ldc,
+                a->bias ? a->bias + n_first : nullptr, a->bias2 ? a->bias2 + n_first : nullptr,
+                a->residual ? reinterpret_cast<const __nv_bfloat16*>(a->residual) + n_first : nullptr, 1.0f, a->act, 0,
                 (int)M, N, taps * kpt * BK, batch_h, 0, a->kind, a->kind == 1 ? a->W : (int)a->S, a->Cin, tma_group()};
     const int batch = batch_h * batch_b;
     cudaError_t e = pair ? launch_pair<256>(ta, tb, p, batch, s)
@@ -997,5 +1054,3 @@ int gvd_conv_bf16(const GvdConvArgs* a, gvd_nn_stream_t stream_) {
     if (e != cudaSuccess) { g_nn_err = std::string("gvd_conv_bf16 launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
-
-}  // extern "C"
