@@ -812,7 +812,7 @@ int tma_group() {
 // Measured (profiles/r02_gemm_split_sweep.txt): implicit convolutions gain 16-23 % (25 x 72 x 128, 320 -> 320: 874 -> 1042
 // TFLOP/s; 36 x 64, 640 -> 640: 1008 -> 1241), linears only from K ~ 2560 (+5 %); below that the narrow launch is a second
 // HBM pass over A for a sliver of the flops and the split LOSES 15-22 % (K = 320: 590 -> 458), so plain GEMMs split from
-// K = 2048 and convolutions -- whose A operand is re-read nine times out of L2 anyway -- always.
+// K = 2048 on; every 3 x 3 convolution of the U-Net qualifies (K = 9 Cin >= 2880), the temporal ones from Cin = 1280.
 bool split_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -823,7 +823,8 @@ bool split_enabled() {
 }
 int split_columns(long long M, int N, int K, int batch, bool conv) {
     if (!split_enabled() || N <= 256 || (N % 256) == 0 || (N % 8) != 0) return 0;
-    if (!conv && K < 2048) return 0;
+    (void)conv;
+    if (K < 2048) return 0;
     if (((M + BM - 1) / BM) * batch < 148) return 0;  // each launch should fill the machine on its own
     return N / 256 * 256;
 }
