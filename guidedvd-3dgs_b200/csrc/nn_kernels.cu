@@ -200,7 +200,8 @@ template <int SILU>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ partial, int S, int C, int groups,
-                                                          int nchunks, int rows_per_cta, float eps, long long stat_rows) {
+                                                          int nchunks, int rows_per_cta, float eps, long long stat_rows,
+                                                          float* __restrict__ stats_out) {
     extern __shared__ double gn_shd[];  // fold[256] doubles, mean[groups], rstd[groups] floats, then the ring
     double* fold = gn_shd;
     float* sh = reinterpret_cast<float*>(fold + 256);
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* _
     const int f = blockIdx.y;
     const int cpg = C / groups, vecs = C / 8;
     gn_fold_frame(partial, nchunks, groups, f, fold);
+    // gvd_groupnorm_cl_keep_stats: the folded sums are also the backward's input -- what gn_fold_kernel would have written
+    if (stats_out != nullptr && blockIdx.x == 0 && threadIdx.x < groups * 2) stats_out[(size_t)f * groups * 2 + threadIdx.x] = (float)fold[threadIdx.x];
     if (threadIdx.x < groups) {
         // the split entry points (gvd_groupnorm_cl_stats -> _apply) hand the folded sums over as floats: round here too, so
         // the fused call and the split one normalise with the same bits (the guided tape must not change the forward)
@@ -622,11 +625,12 @@ inline size_t gn_partial_smem(int groups) {
     return (GN_COPIES * groups * 2 * sizeof(unsigned long long) + 15) / 16 * 16 + (size_t)GN_RING * 256 * 16;
 }
 void launch_gn_apply(int do_silu, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamma, const float* beta,
-                     const float* partial, int S, int C, int groups, int nchunks, int rows_per_cta, float eps, long long stat_rows) {
+                     const float* partial, int S, int C, int groups, int nchunks, int rows_per_cta, float eps, long long stat_rows,
+                     float* stats_out = nullptr) {
     const size_t sm = (256 * sizeof(double) + groups * 2 * sizeof(float) + 15) / 16 * 16 + (size_t)GN_RING * 256 * 16;
-    if (do_silu == 1) gn_apply_kernel<1><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
-    else if (do_silu == 2) gn_apply_kernel<2><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
-    else gn_apply_kernel<0><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
+    if (do_silu == 1) gn_apply_kernel<1><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows, stats_out);
+    else if (do_silu == 2) gn_apply_kernel<2><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows, stats_out);
+    else gn_apply_kernel<0><<<grid, 256, sm, s>>>(x, y, gamma, beta, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows, stats_out);
 }
 
 int grid_for(long long n, int block = 256, int cap = 148 * 16) {
@@ -644,8 +648,22 @@ int gvd_nn_set_fast(int on) {
     return was;
 }
 
+static int groupnorm_fused(const void* x, void* y, const float* gamma, const float* beta, float* stats_out, int F, long long S, int C,
+                           int groups, float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_);
+
 int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* beta, int F, long long S, int C, int groups,
                      float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_) {
+    return groupnorm_fused(x, y, gamma, beta, nullptr, F, S, C, groups, eps, do_silu, tmp, tmp_floats, stream_);
+}
+
+int gvd_groupnorm_cl_keep_stats(const void* x, void* y, const float* gamma, const float* beta, float* stats, int F, long long S, int C,
+                                int groups, float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_) {
+    if (!stats) { g_nn_err_ext = "gvd_groupnorm_cl_keep_stats: null stats"; return 2; }
+    return groupnorm_fused(x, y, gamma, beta, stats, F, S, C, groups, eps, do_silu, tmp, tmp_floats, stream_);
+}
+
+static int groupnorm_fused(const void* x, void* y, const float* gamma, const float* beta, float* stats_out, int F, long long S, int C,
+                           int groups, float eps, int do_silu, float* tmp, size_t tmp_floats, gvd_nn_stream_t stream_) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (F <= 0 || S <= 0) return 0;
     if (C % groups != 0 || C % 8 != 0 || groups > 128) {
@@ -660,7 +678,7 @@ int gvd_groupnorm_cl(const void* x, void* y, const float* gamma, const float* be
     gn_partial_kernel<<<dim3(nchunks, F), 256, gn_partial_smem(groups), s>>>((const __nv_bfloat16*)x, (int)S, C, groups, rows_per_chunk, tmp);
     const int rows_per_cta = rows_per_chunk;
     launch_gn_apply(do_silu, dim3((unsigned)nchunks, F), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups,
-                    nchunks, rows_per_cta, eps, S);
+                    nchunks, rows_per_cta, eps, S, stats_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl: ") + cudaGetErrorString(e); return 1; }
     return 0;

@@ -131,8 +131,9 @@ def groupnorm(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
 
 
 def groupnorm_with_stats(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
-    """`groupnorm` through the split entry points, returning (y, stats[F, groups, 2] = (sum x, sum x^2)) so the guided
-    sampler's backward does not have to read x a second time for the statistics (vc_b200.grad.GroupNorm)."""
+    """`groupnorm` that also returns stats[F, groups, 2] = (sum x, sum x^2) (gvd_groupnorm_cl_keep_stats: two launches, the
+    same bits as the split entry points), so the guided sampler's backward does not have to read x a second time for the
+    statistics (vc_b200.grad.GroupNorm)."""
     lib = _n.nn()
     Cc = x.shape[-1]
     x = x.contiguous()
@@ -143,11 +144,9 @@ def groupnorm_with_stats(x, gamma, beta, F, S, groups=32, eps=1e-5, silu=False):
     if tmp is None:
         tmp = _gn_tmp[key] = torch.empty(nfl, dtype=torch.float32, device=x.device)
     stats = torch.empty(F * groups * 2, dtype=torch.float32, device=x.device)
-    _check(lib.gvd_groupnorm_cl_stats(x.data_ptr(), stats.data_ptr(), int(F), int(S), int(Cc), int(groups), tmp.data_ptr(), nfl,
-                                      _stream()), lib, "gvd_groupnorm_cl_stats")
-    _check(lib.gvd_groupnorm_cl_apply(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), int(F),
-                                      int(S), int(S), int(Cc), int(groups), float(eps), int(silu), _stream()), lib,
-           "gvd_groupnorm_cl_apply")
+    _check(lib.gvd_groupnorm_cl_keep_stats(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), int(F), int(S),
+                                           int(Cc), int(groups), float(eps), int(silu), tmp.data_ptr(), nfl, _stream()), lib,
+           "gvd_groupnorm_cl_keep_stats")
     return y, stats
 
 

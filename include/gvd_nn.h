@@ -109,6 +109,13 @@ GVD_NN_API int gvd_groupnorm_cl_apply(const void* x, void* y, const float* gamma
                                       long long S, long long stat_rows, int C, int groups, float eps, int do_silu,
                                       gvd_nn_stream_t stream);
 
+/* gvd_groupnorm_cl that also hands back the statistics it normalised with -- stats[F, groups, 2], bit-identical to what
+ * gvd_groupnorm_cl_stats writes for the same x -- so a caller that needs them for the backward (the guided sampler's
+ * tape) does not pay a separate fold launch per layer. */
+GVD_NN_API int gvd_groupnorm_cl_keep_stats(const void* x, void* y, const float* gamma, const float* beta, float* stats, int F,
+                                           long long S, int C, int groups, float eps, int do_silu, float* tmp, size_t tmp_floats,
+                                           gvd_nn_stream_t stream);
+
 /* LayerNorm over the last dimension of x[rows, C] (bf16 in/out) -- BasicTransformerBlock.norm1/2/3 (attention.py:236-238). */
 GVD_NN_API int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
                              gvd_nn_stream_t stream);

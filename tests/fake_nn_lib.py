@@ -170,6 +170,11 @@ class FakeNN:
         self._a(y, F, S, C).copy_(out.to(self.act))
         return 0
 
+    def gvd_groupnorm_cl_keep_stats(self, x, y, gamma, beta, stats, F, S, C, groups, eps, silu, tmp, tmp_floats, stream):
+        assert tmp_floats >= 1 and _addr(tmp)
+        self.gvd_groupnorm_cl_stats(x, stats, F, S, C, groups, tmp, tmp_floats, stream)
+        return self.gvd_groupnorm_cl_apply(x, y, gamma, beta, stats, F, S, S, C, groups, eps, silu, stream)
+
     def gvd_groupnorm_cl_stats(self, x, stats, F, S, C, groups, tmp, tmp_floats, stream):
         self._count("groupnorm_stats")
         xg = self._a(x, F, S, groups, C // groups).double()

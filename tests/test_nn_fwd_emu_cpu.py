@@ -22,7 +22,8 @@ from test_unet_grad_cpu import _rel, install_fake  # noqa: E402
 
 BF = torch.bfloat16
 FWD = ("gvd_groupnorm_tmp_floats", "gvd_groupnorm_cl", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply", "gvd_layernorm", "gvd_geglu",
-       "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention", "gvd_ddim_step")
+       "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention", "gvd_ddim_step",
+       "gvd_groupnorm_cl_keep_stats")
 
 
 @pytest.fixture(scope="module")
@@ -61,6 +62,30 @@ def test_groupnorm_kernels(monkeypatch, emu_lib, F, S, C, silu):
     z = torch.nn.functional.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
     ref = torch.nn.functional.silu(z.to(BF).float() if silu == 1 else z) if silu else z
     assert _rel(emu, closed) < 4e-3 and _rel(emu, ref) < 6e-3   # bf16 output rounding (and the extra rounding of mode 1)
+
+
+@pytest.mark.parametrize("F,S,C", [(2, 200, 64), (1, 70, 320)])
+def test_groupnorm_keep_stats_equals_fused_and_split(monkeypatch, emu_lib, F, S, C):
+    """gvd_groupnorm_cl_keep_stats: the output bits of the fused call and the statistic bits of the split one (the guided
+    tape's forward must not differ from the plain sampler's, and its backward reads exactly these sums)."""
+    import gvd_native
+    from vc_b200 import ops
+
+    x = _bf(F, S, C, seed=7, scale=2.0) + 0.25
+    g = torch.Generator().manual_seed(8)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    fake = install_fake(monkeypatch, BF)
+    for name in FWD:
+        setattr(fake, name, getattr(emu_lib, name))
+    monkeypatch.setattr(gvd_native, "nn", lambda: fake)
+    y_fused = ops.groupnorm(x, gamma, beta, F, S, 32, 1e-5, 1)
+    y_keep, stats = ops.groupnorm_with_stats(x, gamma, beta, F, S, 32, 1e-5, 1)
+    nfl = int(emu_lib.gvd_groupnorm_tmp_floats(F, S, 32))
+    tmp, st2 = torch.empty(nfl), torch.empty(F * 32 * 2)
+    assert emu_lib.gvd_groupnorm_cl_stats(x.data_ptr(), st2.data_ptr(), F, S, C, 32, tmp.data_ptr(), nfl, None) == 0
+    assert torch.equal(y_fused, y_keep) and torch.equal(stats, st2)
+    xs = x.float().view(F, S, 32, C // 32)
+    assert torch.allclose(stats.view(F, 32, 2)[..., 0], xs.sum(dim=(1, 3)), rtol=1e-5, atol=1e-3)
 
 
 def test_groupnorm_sharded_split(monkeypatch, emu_lib):
