@@ -348,6 +348,32 @@ void launch_gn_bwd_apply(int do_silu, dim3 grid, cudaStream_t s, const __nv_bflo
     else gn_bwd_apply_kernel<2><<<grid, 256, sm, s>>>(x, dy, dx, gamma, beta, stats, partial, S, C, groups, nchunks, rows_per_cta, eps, stat_rows);
 }
 
+// ---------------- adjoint of the nearest-neighbour 2x upsampling: dx[h, w] = sum of the 2 x 2 block of dy ----------------
+// fp32 sum of the four bf16 gradients, one rounding (what autograd's upsample_nearest2d_backward does under autocast)
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int F,
+                                                             int H, int W, int C) {
+    const int vec = C / 8;
+    const long long total = (long long)F * H * W * vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec);
+        long long t = i / vec;
+        const int ix = (int)(t % W);
+        t /= W;
+        const int iy = (int)(t % H);
+        const int f = (int)(t / H);
+        const uint4* in = reinterpret_cast<const uint4*>(dy) + ((((size_t)f * 2 * H + 2 * iy) * 2 * W + 2 * ix) * vec + v);
+        const uint4 u0 = __ldg(in), u1 = __ldg(in + vec), u2 = __ldg(in + (size_t)2 * W * vec), u3 = __ldg(in + (size_t)2 * W * vec + vec);
+        float a[8], b[8], c[8], d[8], o[8];
+        unpack8(u0, a);
+        unpack8(u1, b);
+        unpack8(u2, c);
+        unpack8(u3, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (a[e] + b[e]) + (c[e] + d[e]);
+        reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+    }
+}
+
 // ---------------- LayerNorm backward over the last dim (one warp per row) ----------------
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
@@ -799,6 +825,16 @@ int gvd_col2im3x3_cl(const void* dcol, void* dx, int F, int H, int W, int C, int
     const long long total = (long long)F * H * W * (C / 8);
     if (total <= 0) return 0;
     col2im3x3_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, F, H, W, C, Ho, Wo, stride, upsample ? 1 : 0);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_upsample2x_bwd_cl(const void* dy, void* dx, int F, int H, int W, int C, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (!dy || !dx) { g_nn_err_ext = "gvd_upsample2x_bwd_cl: null pointer"; return 2; }
+    if (C % 8) { g_nn_err_ext = "gvd_upsample2x_bwd_cl: C must be a multiple of 8"; return 2; }
+    const long long total = (long long)F * H * W * (C / 8);
+    if (total <= 0) return 0;
+    upsample2x_bwd_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, F, H, W, C);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

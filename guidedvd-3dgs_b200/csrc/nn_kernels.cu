@@ -424,6 +424,31 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
     }
 }
 
+// ---------------- nearest-neighbour 2x upsampling of [F, H, W, C] -> [F, 2H, 2W, C] ----------------
+// (Upsample.forward, openaimodel3d.py / ae_modules.py: F.interpolate(scale_factor=2, mode="nearest") in front of a 3x3
+// convolution.)  Materialising the 4x tensor and running the implicit-GEMM convolution over it moves 4 units + the
+// convolution's own reads; the fused im2col it replaces wrote and re-read a 36x matrix (3.8 GB for the VAE decoder's
+// last Upsample at 5 x 320 x 512 x 256).  One thread reads one 16-byte vector and writes it four times.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int F, int H,
+                                                         int W, int C) {
+    const int vec = C / 8;
+    const long long total = (long long)F * H * W * vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec);
+        long long t = i / vec;
+        const int ix = (int)(t % W);
+        t /= W;
+        const int iy = (int)(t % H);
+        const int f = (int)(t / H);
+        const uint4 val = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        uint4* out = reinterpret_cast<uint4*>(y) + ((((size_t)f * 2 * H + 2 * iy) * 2 * W + 2 * ix) * vec + v);
+        out[0] = val;
+        out[vec] = val;
+        out[(size_t)2 * W * vec] = val;
+        out[(size_t)2 * W * vec + vec] = val;
+    }
+}
+
 // ---------------- im2col for (3,1,1) temporal convs on [B, T, S, C]; K order = (kt, c) ----------------
 __global__ void __launch_bounds__(256) im2col_t3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col,
                                                         int B, int T, long long S, int C) {
@@ -775,6 +800,16 @@ int gvd_im2col3x3_cl(const void* x, void* col, int F, int H, int W, int C, int s
     if (total <= 0) return 0;
     if (nn_fast_enabled() && gvd_fast_im2col3x3(x, col, F, H, W, C, Ho, Wo, stride, upsample, s)) return cudaGetLastError() == cudaSuccess ? 0 : 1;
     im2col3x3_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, F, H, W, C, Ho, Wo, stride, upsample);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int gvd_upsample2x_cl(const void* x, void* y, int F, int H, int W, int C, gvd_nn_stream_t stream_) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !y) { g_nn_err_ext = "gvd_upsample2x_cl: null pointer"; return 2; }
+    if (C % 8) { g_nn_err_ext = "gvd_upsample2x_cl: C must be a multiple of 8"; return 2; }
+    const long long total = (long long)F * H * W * (C / 8);
+    if (total <= 0) return 0;
+    upsample2x_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, F, H, W, C);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

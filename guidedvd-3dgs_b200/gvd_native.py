@@ -289,7 +289,8 @@ NN_SYMBOLS = ("gvd_gemm_bf16", "gvd_nn_last_error", "gvd_groupnorm_tmp_floats", 
               "gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_groupnorm_cl_bwd_sums", "gvd_groupnorm_cl_bwd_apply", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
               "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp",
               "gvd_im2col3x3_down_cl", "gvd_nn_set_fast", "gvd_conv_bf16", "gvd_conv_bf16_supported",
-              "gvd_flash_attention_lse", "gvd_flash_attention_bwd", "gvd_groupnorm_cl_keep_stats")
+              "gvd_flash_attention_lse", "gvd_flash_attention_bwd", "gvd_groupnorm_cl_keep_stats",
+              "gvd_upsample2x_cl", "gvd_upsample2x_bwd_cl")
 _nn = None
 
 
@@ -313,6 +314,8 @@ def _nn_signatures():
         "gvd_im2col3x3_cl": (I, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "gvd_im2col3x3_down_cl": (I, [vp, vp, i32, i32, i32, i32, vp]),
         "gvd_im2col_t3_cl": (I, [vp, vp, i32, i32, ll, i32, vp]),
+        "gvd_upsample2x_cl": (I, [vp, vp, i32, i32, i32, i32, vp]),
+        "gvd_upsample2x_bwd_cl": (I, [vp, vp, i32, i32, i32, i32, vp]),
         "gvd_temporal_attention": (I, [vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]),
         "gvd_flash_attention": (I, [vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]),
         "gvd_flash_attention_lse": (I, [vp, vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]),

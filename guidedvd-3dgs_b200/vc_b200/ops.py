@@ -283,11 +283,38 @@ def conv3x3(x, F, H, W, weight, bias=None, stride=1, upsample=False, bias2=None,
     if stride == 1 and not upsample and _implicit_ok(1, H, W, Cin, weight.shape[0], x):
         y = _conv_implicit(1, x, weight, (F, H, W), bias, bias2, residual, act)
         return y.view(F, Ho * Wo, -1), Ho, Wo
+    if stride == 1 and upsample and _implicit_ok(1, 2 * H, 2 * W, Cin, weight.shape[0], x):
+        # Upsample + conv: the 4x tensor is materialised (4 units written) and convolved implicitly, instead of a 36x im2col matrix
+        y = _conv_implicit(1, upsample2x(x, F, H, W), weight, (F, 2 * H, 2 * W), bias, bias2, residual, act)
+        return y.view(F, Ho * Wo, -1), Ho, Wo
     col = torch.empty(F * Ho * Wo, 9 * Cin, dtype=BF16, device=x.device)
     _check(lib.gvd_im2col3x3_cl(x.data_ptr(), col.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),
                                 _stream()), lib, "gvd_im2col3x3_cl")
     y = linear(col, weight, bias=bias, bias2=bias2, residual=residual, act=act)
     return y.view(F, Ho * Wo, -1), Ho, Wo
+
+
+def upsample2x(x, F, H, W):
+    """Nearest-neighbour 2x upsampling of channels-last x[F, H*W, C] -> [F, 4*H*W, C] (gvd_upsample2x_cl)."""
+    lib = _n.nn()
+    Cc = x.shape[-1]
+    x = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty(F, 4 * H * W, Cc, dtype=x.dtype, device=x.device)
+    with _on_device(x.device):
+        _check(lib.gvd_upsample2x_cl(x.data_ptr(), y.data_ptr(), int(F), int(H), int(W), int(Cc), _stream()), lib, "gvd_upsample2x_cl")
+    return y
+
+
+def upsample2x_bwd(dy, F, H, W):
+    """Adjoint of `upsample2x`: dy[F, 4*H*W, C] -> dx[F, H*W, C], each the sum of its 2 x 2 block (gvd_upsample2x_bwd_cl)."""
+    lib = _n.nn()
+    Cc = dy.shape[-1]
+    dy = dy if dy.is_contiguous() else dy.contiguous()
+    dx = torch.empty(F, H * W, Cc, dtype=dy.dtype, device=dy.device)
+    with _on_device(dy.device):
+        _check(lib.gvd_upsample2x_bwd_cl(dy.data_ptr(), dx.data_ptr(), int(F), int(H), int(W), int(Cc), _stream()), lib,
+               "gvd_upsample2x_bwd_cl")
+    return dx
 
 
 def conv3x3_down(x, F, H, W, weight, bias=None):
@@ -596,6 +623,9 @@ def conv3x3_dx(dy, F, H, W, Cin, weight, stride=1, upsample=False):
     Cout = dy.shape[-1]
     if stride == 1 and not upsample and _implicit_ok(1, H, W, Cout, Cin, dy):
         return _conv_implicit(1, dy.reshape(F, H * W, Cout), _dgrad_weight(weight, 9), (F, H, W)).view(F, H * W, Cin)
+    if stride == 1 and upsample and _implicit_ok(1, 2 * H, 2 * W, Cout, Cin, dy):
+        dxu = _conv_implicit(1, dy.reshape(F, 4 * H * W, Cout), _dgrad_weight(weight, 9), (F, 2 * H, 2 * W))
+        return upsample2x_bwd(dxu.view(F, 4 * H * W, Cin), F, H, W)
     dcol = linear_dx(dy.reshape(-1, dy.shape[-1]), weight)  # [F*Ho*Wo, 9*Cin]
     dx = torch.empty(F, H * W, Cin, dtype=dy.dtype, device=dy.device)
     _check(lib.gvd_col2im3x3_cl(dcol.data_ptr(), dx.data_ptr(), int(F), int(H), int(W), int(Cin), int(stride), int(upsample),

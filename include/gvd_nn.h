@@ -138,6 +138,13 @@ GVD_NN_API int gvd_im2col3x3_cl(const void* x, void* col, int F, int H, int W, i
  * bottom only, stride 2, no further padding -- x[F, H, W, C] -> col[F, Ho, Wo, 9*C] with Ho = (H - 2) / 2 + 1. */
 GVD_NN_API int gvd_im2col3x3_down_cl(const void* x, void* col, int F, int H, int W, int C, gvd_nn_stream_t stream);
 
+/* Nearest-neighbour 2x upsampling of channels-last x[F, H, W, C] -> y[F, 2H, 2W, C] (Upsample.forward:
+ * F.interpolate(scale_factor=2, mode="nearest"), openaimodel3d.py / ae_modules.py) and its adjoint, dx[h, w] = the fp32
+ * sum of dy's 2 x 2 block rounded once.  They put the Upsample convolutions on the implicit-GEMM route
+ * (gvd_conv_bf16 over the 4x tensor) instead of a 36x im2col matrix.  C % 8 == 0. */
+GVD_NN_API int gvd_upsample2x_cl(const void* x, void* y, int F, int H, int W, int C, gvd_nn_stream_t stream);
+GVD_NN_API int gvd_upsample2x_bwd_cl(const void* dy, void* dx, int F, int H, int W, int C, gvd_nn_stream_t stream);
+
 /* im2col for the (3,1,1) / pad (1,0,0) temporal convolutions on x[B, T, S, C] -> col[B, T, S, 3*C], K order (kt, c)
  * (TemporalConvBlock, openaimodel3d.py:246-266). */
 GVD_NN_API int gvd_im2col_t3_cl(const void* x, void* col, int B, int T, long long S, int C, gvd_nn_stream_t stream);

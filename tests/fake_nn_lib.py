@@ -423,6 +423,18 @@ class FakeNN:
         view(out, Nq, qs).copy_(o.to(self.act))
         return 0
 
+    def gvd_upsample2x_cl(self, x, y, F, H, W, C, stream):
+        self._count("upsample2x")
+        xx = self._a(x, F, H, W, C)
+        self._a(y, F, 2 * H, 2 * W, C).copy_(xx.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+        return 0
+
+    def gvd_upsample2x_bwd_cl(self, dy, dx, F, H, W, C, stream):
+        self._count("upsample2x_bwd")
+        d = self._a(dy, F, H, 2, W, 2, C).float()
+        self._a(dx, F, H, W, C).copy_(d.sum(dim=(2, 4)).to(self.act))
+        return 0
+
     def gvd_flash_attention_lse(self, q, k, v, out, lse, B, Nq, Nk, H, qs, ks, scale, stream):
         self._count("flash_attention_lse")
         HD = H * 64

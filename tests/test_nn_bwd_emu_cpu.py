@@ -23,7 +23,7 @@ from test_unet_grad_cpu import _rel, install_fake  # noqa: E402
 
 BF = torch.bfloat16
 EMU_FUNCS = ("gvd_groupnorm_bwd_tmp_bytes", "gvd_groupnorm_cl_bwd", "gvd_layernorm_bwd", "gvd_geglu_bwd", "gvd_softmax_bwd_rows",
-             "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp")
+             "gvd_col2im3x3_cl", "gvd_col2im_t3_cl", "gvd_temporal_attention_bwd", "gvd_ddim_pred_x0_vjp", "gvd_upsample2x_bwd_cl")
 
 
 @pytest.fixture(scope="module")
@@ -41,6 +41,7 @@ def emu_lib():
     lib.gvd_softmax_bwd_rows.argtypes = [vp, vp, vp, ll, ll, i32, vp]
     lib.gvd_col2im3x3_cl.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gvd_col2im_t3_cl.argtypes = [vp, vp, i32, i32, ll, i32, vp]
+    lib.gvd_upsample2x_bwd_cl.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.gvd_temporal_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, ll, i32, f32, vp]
     lib.gvd_ddim_pred_x0_vjp.argtypes = [C.POINTER(gvd_native.DdimVjpArgs), vp]
     return lib
@@ -142,6 +143,16 @@ def test_col2im3x3_kernel(monkeypatch, emu_lib, stride, up, H, W):
     emu, closed = _both(monkeypatch, emu_lib, lambda: ops.conv3x3_dx(dy, F_, H, W, Cin, w, stride, up))
     assert _rel(emu, closed) < 1e-3          # same bf16 dcol, fp32 sums of <= 36 taps in a different order
     assert _rel(emu, xf.grad) < 1.5e-2
+
+
+def test_upsample2x_bwd_kernel(monkeypatch, emu_lib):
+    from vc_b200 import ops
+
+    F_, H, W, Cc = 2, 5, 7, 24
+    dy = _bf(F_, 4 * H * W, Cc, seed=17)
+    emu, closed = _both(monkeypatch, emu_lib, lambda: ops.upsample2x_bwd(dy, F_, H, W))
+    want = dy.float().view(F_, H, 2, W, 2, Cc).sum(dim=(2, 4)).reshape(F_, H * W, Cc)
+    assert _rel(emu, closed) < 4e-3 and _rel(emu, want) < 4e-3  # bf16 output rounding; the order of the four adds differs
 
 
 def test_col2im_t3_kernel(monkeypatch, emu_lib):

@@ -23,7 +23,7 @@ from test_unet_grad_cpu import _rel, install_fake  # noqa: E402
 BF = torch.bfloat16
 FWD = ("gvd_groupnorm_tmp_floats", "gvd_groupnorm_cl", "gvd_groupnorm_cl_stats", "gvd_groupnorm_cl_apply", "gvd_layernorm", "gvd_geglu",
        "gvd_softmax_rows", "gvd_im2col3x3_cl", "gvd_im2col_t3_cl", "gvd_temporal_attention", "gvd_ddim_step",
-       "gvd_groupnorm_cl_keep_stats")
+       "gvd_groupnorm_cl_keep_stats", "gvd_upsample2x_cl")
 
 
 @pytest.fixture(scope="module")
@@ -86,6 +86,16 @@ def test_groupnorm_keep_stats_equals_fused_and_split(monkeypatch, emu_lib, F, S,
     assert torch.equal(y_fused, y_keep) and torch.equal(stats, st2)
     xs = x.float().view(F, S, 32, C // 32)
     assert torch.allclose(stats.view(F, 32, 2)[..., 0], xs.sum(dim=(1, 3)), rtol=1e-5, atol=1e-3)
+
+
+def test_upsample2x_kernel(monkeypatch, emu_lib):
+    from vc_b200 import ops
+
+    F, H, W, C = 2, 5, 7, 24
+    x = _bf(F, H * W, C, seed=9)
+    emu, closed = _both(monkeypatch, emu_lib, lambda: ops.upsample2x(x, F, H, W))
+    assert torch.equal(emu, closed)
+    assert torch.equal(emu.view(F, 2 * H, 2 * W, C), x.view(F, H, W, C).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
 
 
 def test_groupnorm_sharded_split(monkeypatch, emu_lib):

@@ -139,6 +139,39 @@ def test_conv3x3_implicit_gemm(F, H, W, C, Cout, monkeypatch):
         _close(dx_col, want, tol=1.0 / 64)  # the col2im route rounds the nine partial products to bf16 first
 
 
+@pytest.mark.parametrize("F,H,W,C,Cout", [(2, 8, 16, 64, 64), (3, 20, 32, 128, 320), (1, 5, 64, 256, 128)])
+def test_upsample_conv_on_the_implicit_route(F, H, W, C, Cout, monkeypatch):
+    """Upsample + 3x3 convolution (openaimodel3d.py / ae_modules.py Upsample.forward): the materialised 4x tensor through
+    gvd_conv_bf16 is bit-identical to the fused-upsampling im2col + GEMM route; its data gradient (implicit dgrad over the
+    4x grid, then the 2 x 2 block sum) matches autograd of interpolate + conv2d within the bf16 bar."""
+    from vc_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(H * W + C)
+    x = torch.randn(F, C, H, W, device="cuda", generator=g).to(BF)
+    w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (3 * C ** 0.5)).to(BF)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    x_cl = x.permute(0, 2, 3, 1).reshape(F, H * W, C).contiguous()
+    w_cl = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    assert ops._implicit_ok(1, 2 * H, 2 * W, C, Cout, x_cl)
+    xu = ops.upsample2x(x_cl, F, H, W).view(F, 2 * H, 2 * W, C)
+    assert torch.equal(xu, x_cl.view(F, H, W, C).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    y, Ho, Wo = ops.conv3x3(x_cl, F, H, W, w_cl, b, upsample=True)
+    assert (Ho, Wo) == (2 * H, 2 * W)
+    dy = torch.randn(F, Ho * Wo, Cout, device="cuda", generator=g).to(BF)
+    dx = ops.conv3x3_dx(dy, F, H, W, C, w_cl, 1, True)
+    monkeypatch.setattr(ops, "IMPLICIT_CONV", False)
+    y_col, _, _ = ops.conv3x3(x_cl, F, H, W, w_cl, b, upsample=True)
+    dx_col = ops.conv3x3_dx(dy, F, H, W, C, w_cl, 1, True)
+    assert torch.equal(y, y_col)
+    xr = x.float().requires_grad_(True)
+    ref = Fn.conv2d(Fn.interpolate(xr, scale_factor=2, mode="nearest"), w.float(), b, padding=1)
+    _close(y.view(F, Ho, Wo, Cout).permute(0, 3, 1, 2), ref)
+    ref.backward(dy.float().view(F, Ho, Wo, Cout).permute(0, 3, 1, 2))
+    want = xr.grad.permute(0, 2, 3, 1).reshape(F, H * W, C)
+    _close(dx, want, tol=1.0 / 64)      # two bf16 roundings: per upsampled pixel, then the block sum (as autograd under autocast)
+    _close(dx_col, want, tol=1.0 / 64)
+
+
 @pytest.mark.parametrize("B,T,S,C,Cout", [(1, 7, 50, 64, 128), (2, 1, 129, 128, 64), (1, 25, 300, 320, 320)])
 def test_conv_t3_implicit_gemm(B, T, S, C, Cout, monkeypatch):
     from vc_b200 import ops
