@@ -136,6 +136,46 @@ def test_nn_header_symbols_exported():
     assert lib.gvd_ddim_step(None, None) != 0
 
 
+def test_nn_struct_sizes_and_late_entry_points_validate():
+    """ctypes mirrors of the include/gvd_nn.h argument structs have the C sizes, and the entry points added with the fused
+    attention adjoint / GroupNorm / upsample route reject bad arguments before any CUDA call."""
+    import subprocess
+    import tempfile
+
+    import gvd_native
+
+    src = '#include "gvd_nn.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(GvdGemmArgs), sizeof(GvdConvArgs), ' \
+          'sizeof(GvdFlashBwdArgs), sizeof(GvdDdimArgs));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "p")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(gvd_native.GemmArgs), C.sizeof(gvd_native.ConvArgs), C.sizeof(gvd_native.FlashBwdArgs),
+                     C.sizeof(gvd_native.DdimArgs)]
+    lib = gvd_native.nn()
+    assert lib.gvd_flash_attention_bwd(None, None) == 2 and b"null" in lib.gvd_nn_last_error()
+    a = gvd_native.FlashBwdArgs()
+    assert lib.gvd_flash_attention_bwd(C.byref(a), None) == 2            # null tensors
+    buf = (C.c_char * 4096)()
+    ptr = C.addressof(buf) // 16 * 16 + 16
+    for f in ("q", "k", "v", "out", "dout", "lse", "delta", "dq", "dk"):
+        setattr(a, f, ptr)
+    a.B, a.Nq, a.Nk, a.H, a.q_batch_stride, a.kv_batch_stride = 1, 8, 8, 1, 512, 512
+    assert lib.gvd_flash_attention_bwd(C.byref(a), None) == 2 and b"go together" in lib.gvd_nn_last_error()   # dk without dv
+    a.dv, a.Nk = ptr, 0
+    assert lib.gvd_flash_attention_bwd(C.byref(a), None) == 2 and b"Nk" in lib.gvd_nn_last_error()
+    a.Nk, a.q_batch_stride = 8, 513
+    assert lib.gvd_flash_attention_bwd(C.byref(a), None) == 2 and b"strides" in lib.gvd_nn_last_error()
+    a.q_batch_stride, a.B = 512, 0
+    assert lib.gvd_flash_attention_bwd(C.byref(a), None) == 0            # empty batch: nothing to do
+    assert lib.gvd_flash_attention_lse(ptr, ptr, ptr, ptr, None, 1, 8, 8, 1, 512, 512, 0.125, None) == 2
+    assert lib.gvd_upsample2x_cl(ptr, ptr, 1, 2, 2, 12, None) == 2 and lib.gvd_upsample2x_cl(None, ptr, 1, 2, 2, 8, None) == 2
+    assert lib.gvd_upsample2x_bwd_cl(ptr, ptr, 1, 2, 2, 12, None) == 2 and lib.gvd_upsample2x_cl(ptr, ptr, 0, 2, 2, 8, None) == 0
+    assert lib.gvd_groupnorm_cl_keep_stats(ptr, ptr, ptr, ptr, None, 1, 8, 64, 32, 1e-5, 0, ptr, 1024, None) == 2
+
+
 def _declared_symbols_api(header, macro):
     txt = open(os.path.join(ROOT, "include", header)).read()
     return sorted(set(re.findall(macro + r"\s+[\w\s\*]+?\b(gvd_\w+)\s*\(", txt)))
