@@ -23,9 +23,12 @@
 // the maximum exchange -- attn_tc.cu generation 8).
 //
 // One CTA per SM (all 512 TMEM columns), 10 warps: warp 0 TMA, warp 1 MMA issue, warps 2-9 softmax.  The streamed
-// operand arrives as 128-row tiles (2-stage ring) and is consumed as two 64-row sub-blocks; S, dP, P and dS are double
-// buffered and the S / dP products of sub-block i + 1 are issued BEFORE the wait for sub-block i's dS -- the software
-// pipeline of the forward's generation 7.
+// operand arrives as 128-row tiles (3-stage ring) and is consumed as two 64-row sub-blocks; S, dP, P and dS are double
+// buffered; as soon as the softmax of sub-block i is done, the S / dP products of sub-block i + 2 go into the tensor pipe
+// AHEAD of sub-block i's accumulating MMAs (the first version issued them one ahead and behind the accumulators: ncu
+// showed 19-30 % of the warp samples on the softmax warps' wait for S / dP, tensor pipe 24 %), so a separate barrier
+// tells the softmax when P / dS of sub-block i - 2 have been consumed.  The streamed ring has three stages for the same
+// reason: the next tile is needed one sub-block earlier.
 //   TMEM: S 0,64 | dP 128,192 | P 256,288 | dS 320,352 | acc0 (dV) 384 | acc1 (dQ or dK) 448
 // Rounding points: P and dS enter their MMAs as bf16 (as in the materialised backward); everything else fp32.
 #include <cuda.h>
@@ -42,7 +45,7 @@ bool gvd_fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long
 namespace {
 
 constexpr int FB_TILE = 128 * 64 * 2;  // 16 KB: one 128-row tile of Q, K, V or dO
-constexpr int FB_STAGES = 2;
+constexpr int FB_STAGES = 3;
 constexpr int FB_THREADS = 64 + 8 * 32;
 constexpr int FB_SMEM = FB_TILE * (2 + 2 * FB_STAGES) + 1024 + 256;
 constexpr uint32_t FB_S = 0, FB_DP = 128, FB_P = 256, FB_DS = 320, FB_ACC0 = 384, FB_ACC1 = 448;
@@ -102,12 +105,13 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
     uint8_t* sy1 = smem + (2 + FB_STAGES) * FB_TILE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * FB_STAGES) * FB_TILE);
     uint64_t* x_full = bars;
-    uint64_t* y_full = bars + 1;     // [2]
-    uint64_t* y_empty = bars + 3;    // [2]
-    uint64_t* sdp_full = bars + 5;   // [2]  S and dP of a sub-block are in TMEM
-    uint64_t* pds_full = bars + 7;   // [2]  P and dS of a sub-block are in TMEM (8 arrivals)
-    uint64_t* acc_done = bars + 9;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* y_full = bars + 1;     // [3]
+    uint64_t* y_empty = bars + 4;    // [3]
+    uint64_t* sdp_full = bars + 7;   // [2]  S and dP of a sub-block are in TMEM
+    uint64_t* pds_full = bars + 9;   // [2]  P and dS of a sub-block are in TMEM (8 arrivals)
+    uint64_t* pds_free = bars + 11;  // [2]  the accumulating MMAs have consumed P / dS of a sub-block
+    uint64_t* acc_done = bars + 13;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -127,6 +131,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&sdp_full[s], 1);
             tc::mbar_init(&pds_full[s], 8);  // one arrival per softmax warp
+            tc::mbar_init(&pds_free[s], 1);
         }
         tc::mbar_init(acc_done, 1);
         tc::fence_barrier_init();
@@ -176,12 +181,13 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
             tc::mbar_wait(x_full, 0);
             tc::fence_after_sync();
             issue_sdp(0);
+            if (nsub > 1) issue_sdp(1);
             for (int i = 0; i < nsub; ++i) {
-                // S / dP[(i+1)&1] were last read by the softmax of sub-block i-1, which finished before pds_full(i-1)
-                // completed -- waited on in the previous iteration
-                if (i + 1 < nsub) issue_sdp(i + 1);
-                tc::mbar_wait(&pds_full[i & 1], (uint32_t)((i >> 1) & 1));
+                tc::mbar_wait(&pds_full[i & 1], (uint32_t)((i >> 1) & 1));  // softmax(i) is done: it has read S / dP[i & 1] and written P / dS[i & 1]
                 tc::fence_after_sync();
+                // S / dP two sub-blocks ahead go into the pipe FIRST: the softmax warps need them one softmax time from now,
+                // the accumulators only at the end (issued after them, the profile showed the softmax warps waiting here)
+                if (i + 2 < nsub) issue_sdp(i + 2);
                 const int j = i >> 1, s = j % FB_STAGES;
                 const uint32_t y0 = tc::smem_u32(sy0 + s * FB_TILE) + (uint32_t)(i & 1) * 64 * 128;
                 const uint32_t y1 = tc::smem_u32(sy1 + s * FB_TILE) + (uint32_t)(i & 1) * 64 * 128;
@@ -195,6 +201,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
                 for (int k = 0; k < 4; ++k)
                     umma_bf16_ts(tmem_base + FB_ACC1, tmem_base + FB_DS + (uint32_t)(i & 1) * 32 + k * 8,
                                  tc::make_desc_kmajor_sw128(y0 + k * 16 * 128), idesc_ts, (i | k) != 0);
+                tc::umma_commit(&pds_free[i & 1]);  // softmax(i + 2) may overwrite P / dS[i & 1] once this completes
                 if ((i & 1) || i + 1 == nsub) tc::umma_commit(&y_empty[s]);  // the tile's last sub-block
             }
             tc::umma_commit(acc_done);
@@ -229,9 +236,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
             tc::tmem_ld32(tmem_base + lane_off + FB_DP + (uint32_t)(i & 1) * 64 + 32 * hf, dv);
             tc::tmem_ld_wait();
             uint32_t pk[16], dk[16];
-            const bool ragged = col0 + 32 > p.ncol;  // only the last sub-block(s) can hold out-of-range columns
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
+            auto element_pair = [&](int e, float& p0, float& p1, float& s0, float& s1) {
                 float nl0 = nl_row, nl1 = nl_row, dd0 = d_row, dd1 = d_row;
                 if constexpr (KV) {
                     const float4 a = l4[e >> 2], c = d4[e >> 2];
@@ -240,16 +245,33 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
                     dd0 = (e & 2) ? c.z : c.x;
                     dd1 = (e & 2) ? c.w : c.y;
                 }
-                float p0 = ex2(fmaf(__uint_as_float(sv[e]), sl2, nl0));
-                float p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), sl2, nl1));
-                float s0 = p0 * (__uint_as_float(dv[e]) - dd0);
-                float s1 = p1 * (__uint_as_float(dv[e + 1]) - dd1);
-                if (ragged) {
+                p0 = ex2(fmaf(__uint_as_float(sv[e]), sl2, nl0));
+                p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), sl2, nl1));
+                s0 = p0 * (__uint_as_float(dv[e]) - dd0);
+                s1 = p1 * (__uint_as_float(dv[e + 1]) - dd1);
+            };
+            if (col0 + 32 <= p.ncol) {  // the common case carries no masking instructions at all
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float p0, p1, s0, s1;
+                    element_pair(e, p0, p1, s0, s1);
+                    if (KV) pk[e / 2] = pack_bf16(p0, p1);
+                    dk[e / 2] = pack_bf16(s0, s1);
+                }
+            } else {  // only the last sub-block(s) can hold out-of-range columns
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float p0, p1, s0, s1;
+                    element_pair(e, p0, p1, s0, s1);
                     if (col0 + e >= p.ncol) p0 = s0 = 0.f;
                     if (col0 + e + 1 >= p.ncol) p1 = s1 = 0.f;
+                    if (KV) pk[e / 2] = pack_bf16(p0, p1);
+                    dk[e / 2] = pack_bf16(s0, s1);
                 }
-                if (KV) pk[e / 2] = pack_bf16(p0, p1);
-                dk[e / 2] = pack_bf16(s0, s1);
+            }
+            if (i >= 2) {  // the accumulating MMAs of sub-block i - 2 have read P / dS[i & 1]
+                tc::mbar_wait(&pds_free[i & 1], (uint32_t)(((i >> 1) - 1) & 1));
+                tc::fence_after_sync();
             }
             if (KV) tmem_st16(tmem_base + lane_off + FB_P + (uint32_t)(i & 1) * 32 + 16 * hf, pk);
             tmem_st16(tmem_base + lane_off + FB_DS + (uint32_t)(i & 1) * 32 + 16 * hf, dk);
