@@ -22,6 +22,7 @@
 // owning 32 of the 64 columns, with no exchange between them (unlike the forward, where two threads per row lose to
 // the maximum exchange -- attn_tc.cu generation 8).
 //
+// FIRST FORM (GVD_FLASH_BWD_CTAS=1; the default is the second form further down, 1.24 vs 1.29 ms at 25 x 5 x 2560 x 2560).
 // One CTA per SM (all 512 TMEM columns), 10 warps: warp 0 TMA, warp 1 MMA issue, warps 2-9 softmax.  The streamed
 // operand arrives as 128-row tiles (3-stage ring) and is consumed as two 64-row sub-blocks; S, dP, P and dS are double
 // buffered; as soon as the softmax of sub-block i is done, the S / dP products of sub-block i + 2 go into the tensor pipe
@@ -33,6 +34,7 @@
 // Rounding points: P and dS enter their MMAs as bf16 (as in the materialised backward); everything else fp32.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/gvd_nn.h"
@@ -47,7 +49,7 @@ namespace {
 constexpr int FB_TILE = 128 * 64 * 2;  // 16 KB: one 128-row tile of Q, K, V or dO
 constexpr int FB_STAGES = 3;
 constexpr int FB_THREADS = 64 + 8 * 32;
-constexpr int FB_SMEM = FB_TILE * (2 + 2 * FB_STAGES) + 1024 + 256;
+constexpr int FB_SMEM = FB_TILE * (2 + 2 * FB_STAGES) + 1024 + 256 + FB_STAGES * 1024;  // + per-stage column statistics
 constexpr uint32_t FB_S = 0, FB_DP = 128, FB_P = 256, FB_DS = 320, FB_ACC0 = 384, FB_ACC1 = 448;
 
 __device__ __forceinline__ float ex2(float x) {
@@ -82,6 +84,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// global -> shared bulk copy (bytes % 16 == 0), completion counted on an mbarrier like the tensor-map loads
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
 struct FbParams {
     const float* lse;    // [B, H, ldl]  base-2 log-sum-exp of the scaled logits
     const float* delta;  // [B, H, ldl]  sum_d dO O
@@ -112,6 +121,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
     uint64_t* pds_free = bars + 11;  // [2]  the accumulating MMAs have consumed P / dS of a sub-block
     uint64_t* acc_done = bars + 13;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    // KV: lse | delta of the streamed tile's 128 queries, per stage (the statistics are per COLUMN there)
+    float* sstat = reinterpret_cast<float*>(smem + (2 + 2 * FB_STAGES) * FB_TILE + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -150,9 +161,14 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
             for (int j = 0; j < nblk; ++j) {
                 const int s = j % FB_STAGES;
                 tc::mbar_wait(&y_empty[s], (uint32_t)(((j / FB_STAGES) & 1) ^ 1));
-                tc::mbar_expect_tx(&y_full[s], 2 * FB_TILE);
+                tc::mbar_expect_tx(&y_full[s], 2 * FB_TILE + (KV ? 1024 : 0));
                 tc::tma_load_4d(sy0 + s * FB_TILE, &tmap_y0, &y_full[s], 0, j * 128, h, b);
                 tc::tma_load_4d(sy1 + s * FB_TILE, &tmap_y1, &y_full[s], 0, j * 128, h, b);
+                if (KV) {
+                    const long long so = ((long long)b * p.H + h) * p.ldl + (long long)j * 128;
+                    bulk_g2s(sstat + s * 256, p.lse + so, 512, &y_full[s]);
+                    bulk_g2s(sstat + s * 256 + 128, p.delta + so, 512, &y_full[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -221,14 +237,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
         }
         for (int i = 0; i < nsub; ++i) {
             const int col0 = i * 64 + 32 * hf;
-            float4 l4[8], d4[8];
-            if constexpr (KV) {  // columns are queries: all lanes read the same addresses (one broadcast transaction each)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    l4[e] = __ldg(reinterpret_cast<const float4*>(lse + col0) + e);
-                    d4[e] = __ldg(reinterpret_cast<const float4*>(delta + col0) + e);
-                }
-            }
+            const float* st = sstat + ((i >> 1) % FB_STAGES) * 256 + (i & 1) * 64 + 32 * hf;  // KV: this thread's 32 columns
+            if (KV && (i & 1) == 0) tc::mbar_wait(&y_full[(i >> 1) % FB_STAGES], (uint32_t)(((i >> 1) / FB_STAGES) & 1));  // the bulk copies have landed
             tc::mbar_wait(&sdp_full[i & 1], (uint32_t)((i >> 1) & 1));
             tc::fence_after_sync();
             uint32_t sv[32], dv[32];
@@ -238,8 +248,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
             uint32_t pk[16], dk[16];
             auto element_pair = [&](int e, float& p0, float& p1, float& s0, float& s1) {
                 float nl0 = nl_row, nl1 = nl_row, dd0 = d_row, dd1 = d_row;
-                if constexpr (KV) {
-                    const float4 a = l4[e >> 2], c = d4[e >> 2];
+                if constexpr (KV) {  // all lanes read the same shared address: a broadcast
+                    const float4 a = *reinterpret_cast<const float4*>(st + (e & ~3)), c = *reinterpret_cast<const float4*>(st + 128 + (e & ~3));
                     nl0 = (e & 2) ? -a.z : -a.x;
                     nl1 = (e & 2) ? -a.w : -a.y;
                     dd0 = (e & 2) ? c.z : c.x;
@@ -309,6 +319,223 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_const
     if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// ---- second form: TWO CTAs per SM, 256 TMEM columns each -------------------------------------------------------------------
+// The kernel above is bound by its per-sub-block round trip (profiles/r02_ncu_flash_bwd.txt: tensor pipe 25 %, MUFU 30 %),
+// which a second, independent CTA on the same SM hides -- the way the forward runs.  To fit 256 columns the sub-blocks are
+// single-buffered and the bf16 operands overwrite the fp32 products they came from: P goes into S's columns and dS into
+// dP's (a thread overwrites only columns it has already read: keys 32 c .. 32 c + 31 -> packed columns 32 c .. 32 c + 15).
+// The next S / dP MMAs are issued right behind the accumulating MMAs that still read P / dS from those columns; tcgen05.mma
+// instructions of one CTA execute in issue order, so the reads are over before the overwrite.
+//   TMEM: S | P 0 | dP | dS 64 | acc0 (dV) 128 | acc1 (dQ or dK) 192 ; 6 warps: TMA, MMA, 4 softmax (thread = row, all 64 columns)
+constexpr int FB2_STAGES = 2;
+constexpr int FB2_THREADS = 192;
+constexpr int FB2_SMEM = FB_TILE * (2 + 2 * FB2_STAGES) + 1024 + 256 + FB2_STAGES * 1024;
+constexpr uint32_t FB2_S = 0, FB2_DP = 64, FB2_ACC0 = 128, FB2_ACC1 = 192;
+
+template <bool KV>
+__global__ void __launch_bounds__(FB2_THREADS, 2)
+flash_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_x1,
+                  const __grid_constant__ CUtensorMap tmap_y0, const __grid_constant__ CUtensorMap tmap_y1, FbParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sx0 = smem;
+    uint8_t* sx1 = smem + FB_TILE;
+    uint8_t* sy0 = smem + 2 * FB_TILE;
+    uint8_t* sy1 = smem + (2 + FB2_STAGES) * FB_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * FB2_STAGES) * FB_TILE);
+    uint64_t* x_full = bars;
+    uint64_t* y_full = bars + 1;    // [2]
+    uint64_t* y_empty = bars + 3;   // [2]
+    uint64_t* sdp_full = bars + 5;
+    uint64_t* pds_full = bars + 6;  // 4 arrivals
+    uint64_t* acc_done = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    float* sstat = reinterpret_cast<float*>(smem + (2 + 2 * FB2_STAGES) * FB_TILE + 256);  // KV: lse | delta of the streamed tile, per stage
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.ncol + 127) / 128;
+    const int nsub = (p.ncol + 63) / 64;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_x0);
+        tc::prefetch_tmap(&tmap_x1);
+        tc::prefetch_tmap(&tmap_y0);
+        tc::prefetch_tmap(&tmap_y1);
+        tc::mbar_init(x_full, 1);
+        for (int s = 0; s < FB2_STAGES; ++s) {
+            tc::mbar_init(&y_full[s], 1);
+            tc::mbar_init(&y_empty[s], 1);
+        }
+        tc::mbar_init(sdp_full, 1);
+        tc::mbar_init(pds_full, 4);
+        tc::mbar_init(acc_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, 256);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(x_full, 2 * FB_TILE);
+            tc::tma_load_4d(sx0, &tmap_x0, x_full, 0, m0, h, b);
+            tc::tma_load_4d(sx1, &tmap_x1, x_full, 0, m0, h, b);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % FB2_STAGES;
+                tc::mbar_wait(&y_empty[s], (uint32_t)(((j / FB2_STAGES) & 1) ^ 1));
+                tc::mbar_expect_tx(&y_full[s], 2 * FB_TILE + (KV ? 1024 : 0));
+                tc::tma_load_4d(sy0 + s * FB_TILE, &tmap_y0, &y_full[s], 0, j * 128, h, b);
+                tc::tma_load_4d(sy1 + s * FB_TILE, &tmap_y1, &y_full[s], 0, j * 128, h, b);
+                if (KV) {
+                    const long long so = ((long long)b * p.H + h) * p.ldl + (long long)j * 128;
+                    bulk_g2s(sstat + s * 256, p.lse + so, 512, &y_full[s]);
+                    bulk_g2s(sstat + s * 256 + 128, p.delta + so, 512, &y_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_ss = tc::make_idesc_bf16(128, 64);
+            const uint32_t idesc_ts = idesc_ts_mn();
+            const uint32_t x0_addr = tc::smem_u32(sx0), x1_addr = tc::smem_u32(sx1);
+            tc::mbar_wait(x_full, 0);
+            tc::fence_after_sync();
+            for (int i = 0; i < nsub; ++i) {
+                const int j = i >> 1, s = j % FB2_STAGES;
+                if ((i & 1) == 0) {
+                    tc::mbar_wait(&y_full[s], (uint32_t)((j / FB2_STAGES) & 1));
+                    tc::fence_after_sync();
+                }
+                const uint32_t y0 = tc::smem_u32(sy0 + s * FB_TILE) + (uint32_t)(i & 1) * 64 * 128;
+                const uint32_t y1 = tc::smem_u32(sy1 + s * FB_TILE) + (uint32_t)(i & 1) * 64 * 128;
+                // (the softmax of sub-block i - 1 has read S / dP: pds_full(i - 1) was waited on below; the MMAs of sub-block
+                // i - 1 that read P / dS from these columns were issued before these and execute before them)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_bf16(tmem_base + FB2_S, tc::make_desc_kmajor_sw128(x0_addr + k * 32), tc::make_desc_kmajor_sw128(y0 + k * 32),
+                                  idesc_ss, k != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_bf16(tmem_base + FB2_DP, tc::make_desc_kmajor_sw128(x1_addr + k * 32), tc::make_desc_kmajor_sw128(y1 + k * 32),
+                                  idesc_ss, k != 0);
+                tc::umma_commit(sdp_full);
+                tc::mbar_wait(pds_full, (uint32_t)(i & 1));
+                tc::fence_after_sync();
+                if (KV) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)  // keys 16 k .. + 15 of the sub-block: packed columns 32 (k / 2) + 8 (k % 2)
+                        umma_bf16_ts(tmem_base + FB2_ACC0, tmem_base + FB2_S + (uint32_t)((k >> 1) * 32 + (k & 1) * 8),
+                                     tc::make_desc_kmajor_sw128(y1 + k * 16 * 128), idesc_ts, (i | k) != 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ts(tmem_base + FB2_ACC1, tmem_base + FB2_DP + (uint32_t)((k >> 1) * 32 + (k & 1) * 8),
+                                 tc::make_desc_kmajor_sw128(y0 + k * 16 * 128), idesc_ts, (i | k) != 0);
+                if ((i & 1) || i + 1 == nsub) tc::umma_commit(&y_empty[s]);
+            }
+            tc::umma_commit(acc_done);
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int row = m0 + q * 32 + lane;
+        const float sl2 = p.scale * 1.4426950408889634f;
+        const float* lse = p.lse + ((long long)b * p.H + h) * p.ldl;
+        const float* delta = p.delta + ((long long)b * p.H + h) * p.ldl;
+        float nl_row = 0.f, d_row = 0.f;
+        if (!KV) {
+            nl_row = -lse[row];
+            d_row = delta[row];
+        }
+        for (int i = 0; i < nsub; ++i) {
+            if (KV && (i & 1) == 0) tc::mbar_wait(&y_full[(i >> 1) % FB2_STAGES], (uint32_t)(((i >> 1) / FB2_STAGES) & 1));  // the bulk copies have landed
+            tc::mbar_wait(sdp_full, (uint32_t)(i & 1));
+            tc::fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col0 = i * 64 + 32 * c;
+                const float* st = sstat + ((i >> 1) % FB2_STAGES) * 256 + (i & 1) * 64 + 32 * c;
+                uint32_t sv[32], dv[32];
+                tc::tmem_ld32(tmem_base + lane_off + FB2_S + 32 * c, sv);
+                tc::tmem_ld32(tmem_base + lane_off + FB2_DP + 32 * c, dv);
+                tc::tmem_ld_wait();
+                uint32_t pk[16], dk[16];
+                auto element_pair = [&](int e, float& p0, float& p1, float& s0, float& s1) {
+                    float nl0 = nl_row, nl1 = nl_row, dd0 = d_row, dd1 = d_row;
+                    if constexpr (KV) {  // all lanes read the same shared address: a broadcast
+                        const float4 a = *reinterpret_cast<const float4*>(st + (e & ~3)), cc = *reinterpret_cast<const float4*>(st + 128 + (e & ~3));
+                        nl0 = (e & 2) ? -a.z : -a.x;
+                        nl1 = (e & 2) ? -a.w : -a.y;
+                        dd0 = (e & 2) ? cc.z : cc.x;
+                        dd1 = (e & 2) ? cc.w : cc.y;
+                    }
+                    p0 = ex2(fmaf(__uint_as_float(sv[e]), sl2, nl0));
+                    p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), sl2, nl1));
+                    s0 = p0 * (__uint_as_float(dv[e]) - dd0);
+                    s1 = p1 * (__uint_as_float(dv[e + 1]) - dd1);
+                };
+                if (col0 + 32 <= p.ncol) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0, p1, s0, s1;
+                        element_pair(e, p0, p1, s0, s1);
+                        if (KV) pk[e / 2] = pack_bf16(p0, p1);
+                        dk[e / 2] = pack_bf16(s0, s1);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0, p1, s0, s1;
+                        element_pair(e, p0, p1, s0, s1);
+                        if (col0 + e >= p.ncol) p0 = s0 = 0.f;
+                        if (col0 + e + 1 >= p.ncol) p1 = s1 = 0.f;
+                        if (KV) pk[e / 2] = pack_bf16(p0, p1);
+                        dk[e / 2] = pack_bf16(s0, s1);
+                    }
+                }
+                // in place: these 16 packed columns lie inside the 32 fp32 columns just read
+                if (KV) tmem_st16(tmem_base + lane_off + FB2_S + 32 * c, pk);
+                tmem_st16(tmem_base + lane_off + FB2_DP + 32 * c, dk);
+            }
+            tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(pds_full);
+        }
+        tc::mbar_wait(acc_done, 0);
+        tc::fence_after_sync();
+        const long long off = (long long)b * p.stride_b + (long long)h * 64 + (long long)row * p.ld;
+#pragma unroll
+        for (int which = KV ? 0 : 1; which < 2; ++which) {
+            const float f = which ? p.scale : 1.0f;
+            __nv_bfloat16* dst = (which ? p.out1 : p.out0) + off;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t o[32];
+                tc::tmem_ld32(tmem_base + lane_off + (which ? FB2_ACC1 : FB2_ACC0) + c, o);
+                tc::tmem_ld_wait();
+                if (row < p.nrow) {
+#pragma unroll
+                    for (int e8 = 0; e8 < 32; e8 += 8) {
+                        uint4 u;
+                        u.x = pack_bf16(__uint_as_float(o[e8]) * f, __uint_as_float(o[e8 + 1]) * f);
+                        u.y = pack_bf16(__uint_as_float(o[e8 + 2]) * f, __uint_as_float(o[e8 + 3]) * f);
+                        u.z = pack_bf16(__uint_as_float(o[e8 + 4]) * f, __uint_as_float(o[e8 + 5]) * f);
+                        u.w = pack_bf16(__uint_as_float(o[e8 + 6]) * f, __uint_as_float(o[e8 + 7]) * f);
+                        *reinterpret_cast<uint4*>(dst + c + e8) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+}
+
 // D[b, h, i] = sum_d dO[b, i, h, d] O[b, i, h, d]; 8 lanes per (b, i, h), 16 bytes of each operand per lane.  Rows
 // i in [Nq, ldl) get 0.
 __global__ void flash_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, float* __restrict__ delta,
@@ -368,12 +595,17 @@ extern "C" int gvd_flash_attention_bwd(const GvdFlashBwdArgs* a, gvd_nn_stream_t
         g_nn_err_ext = "gvd_flash_attention_bwd: cuTensorMapEncodeTiled failed";
         return 1;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    // GVD_FLASH_BWD_CTAS=1: the first form (one CTA per SM, double-buffered sub-blocks); default 2: two CTAs per SM
+    static int form = 0;
+    if (!form) {
+        const char* ev = getenv("GVD_FLASH_BWD_CTAS");
+        const int want = (ev && ev[0] == '1') ? 1 : 2;
         cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB2_SMEM);
         if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention_bwd attr: ") + cudaGetErrorString(e); return 1; }
-        attr_done = true;
+        form = want;
     }
     {
         const long long threads = (long long)a->B * a->H * ldl * 8;
@@ -384,13 +616,15 @@ extern "C" int gvd_flash_attention_bwd(const GvdFlashBwdArgs* a, gvd_nn_stream_t
     {
         FbParams p{a->lse, a->delta, nullptr, reinterpret_cast<__nv_bfloat16*>(a->dq), ld, a->q_batch_stride, a->Nq, a->Nk, a->H, ldl, a->scale};
         dim3 grid((a->Nq + 127) / 128, a->H, a->B);
-        flash_bwd_kernel<false><<<grid, FB_THREADS, FB_SMEM, s>>>(tq, td, tk, tv, p);
+        if (form == 2) flash_bwd2_kernel<false><<<grid, FB2_THREADS, FB2_SMEM, s>>>(tq, td, tk, tv, p);
+        else flash_bwd_kernel<false><<<grid, FB_THREADS, FB_SMEM, s>>>(tq, td, tk, tv, p);
     }
     if (a->dk) {
         FbParams p{a->lse, a->delta, reinterpret_cast<__nv_bfloat16*>(a->dv), reinterpret_cast<__nv_bfloat16*>(a->dk), ld, a->kv_batch_stride,
                    a->Nk, a->Nq, a->H, ldl, a->scale};
         dim3 grid((a->Nk + 127) / 128, a->H, a->B);
-        flash_bwd_kernel<true><<<grid, FB_THREADS, FB_SMEM, s>>>(tk, tv, tq, td, p);
+        if (form == 2) flash_bwd2_kernel<true><<<grid, FB2_THREADS, FB2_SMEM, s>>>(tk, tv, tq, td, p);
+        else flash_bwd_kernel<true><<<grid, FB_THREADS, FB_SMEM, s>>>(tk, tv, tq, td, p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_flash_attention_bwd launch: ") + cudaGetErrorString(e); return 1; }
