@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/gvd_nn.h"
@@ -66,6 +67,24 @@ int grid_for(long long n, int block = 256, int cap = 148 * 16) {
 // One wave of CTAs: the backward kernels are resident two per SM (launch bounds below), so floor(296 / F) chunks per frame
 // keeps every CTA on the machine at once -- the rule it replaces (~592 CTAs) ran 2.03 waves at 25 frames.  16..4096 rows
 // per CTA.
+// frames per launch pair, as in the forward (nn_kernels.cu::gn_group_frames): x and dy of a group stay in the L2 between
+// the sums pass and the dx pass.  GVD_GN_GROUP_MB bounds 3 tensors x frames x S x C x 2 bytes; default 0 = one group (measured
+// slower with groups, see nn_kernels.cu).
+int gn_bwd_group_frames(int F, long long S, int C) {
+    static long long budget = -1;
+    if (budget < 0) {
+        const char* e = getenv("GVD_GN_GROUP_MB");
+        budget = (e ? atoll(e) : 0) << 20;
+    }
+    if (budget <= 0 || F <= 1) return F;
+    const long long per_frame = 3ll * S * C * 2;
+    long long fmax = budget / (per_frame > 0 ? per_frame : 1);
+    if (fmax < 1) fmax = 1;
+    if (fmax >= F) return F;
+    const long long ngroups = (F + fmax - 1) / fmax;
+    return (int)((F + ngroups - 1) / ngroups);
+}
+
 int gn_bwd_chunks(int F, long long S) {
     long long want = 296 / (F > 0 ? F : 1);
     long long maxc = (S + 15) / 16;
@@ -706,7 +725,13 @@ __global__ void __launch_bounds__(256) ddim_vjp_apply_kernel(const float* __rest
 extern "C" {
 
 size_t gvd_groupnorm_bwd_tmp_bytes(int F, long long S, int groups) {
-    return (size_t)F * (gn_bwd_chunks(F, S) + 1) * groups * 2 * sizeof(double);
+    // the frames may run in groups (gn_bwd_group_frames), each with its own chunking: the largest of them all
+    size_t most = (size_t)F * (gn_bwd_chunks(F, S) + 1);
+    for (int fg = 1; fg < F; ++fg) {
+        const size_t n = (size_t)fg * (gn_bwd_chunks(fg, S) + 1);
+        if (n > most) most = n;
+    }
+    return most * groups * 2 * sizeof(double);
 }
 
 static int gn_bwd_check(const char* who, int C, int groups, int do_silu) {
@@ -725,15 +750,21 @@ int gvd_groupnorm_cl_bwd(const void* x, const void* dy, void* dx, const float* g
     if (!x || !dy || !dx || !gamma || !beta || !stats || !tmp) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: null pointer"; return 2; }
     if (gn_bwd_check("gvd_groupnorm_cl_bwd", C, groups, do_silu)) return 2;
     if (reinterpret_cast<uintptr_t>(tmp) & 7) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: scratch must be 8-byte aligned"; return 2; }
-    int nchunks = gn_bwd_chunks(F, S);
-    const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
-    nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
-    if (tmp_bytes < (size_t)F * nchunks * groups * 2 * sizeof(double)) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: scratch too small"; return 2; }
     double* partial = reinterpret_cast<double*>(tmp);
-    launch_gn_bwd_partial(do_silu, dim3(nchunks, F), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, gamma, beta, stats, (int)S, C, groups,
-                          rows_per_chunk, eps, S, partial);
-    launch_gn_bwd_apply(do_silu, dim3(nchunks, F), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, gamma, beta, stats,
-                        partial, (int)S, C, groups, nchunks, rows_per_chunk, eps, S);
+    const int fg = gn_bwd_group_frames(F, S, C);
+    for (int f0 = 0; f0 < F; f0 += fg) {
+        const int Fg = F - f0 < fg ? F - f0 : fg;
+        int nchunks = gn_bwd_chunks(Fg, S);
+        const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
+        nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
+        if (tmp_bytes < (size_t)Fg * nchunks * groups * 2 * sizeof(double)) { g_nn_err_ext = "gvd_groupnorm_cl_bwd: scratch too small"; return 2; }
+        const size_t off = (size_t)f0 * S * C;
+        const float* st = stats + (size_t)f0 * groups * 2;
+        launch_gn_bwd_partial(do_silu, dim3(nchunks, Fg), s, (const __nv_bfloat16*)x + off, (const __nv_bfloat16*)dy + off, gamma, beta, st, (int)S, C,
+                              groups, rows_per_chunk, eps, S, partial);
+        launch_gn_bwd_apply(do_silu, dim3(nchunks, Fg), s, (const __nv_bfloat16*)x + off, (const __nv_bfloat16*)dy + off, (__nv_bfloat16*)dx + off, gamma,
+                            beta, st, partial, (int)S, C, groups, nchunks, rows_per_chunk, eps, S);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl_bwd: ") + cudaGetErrorString(e); return 1; }
     return 0;

@@ -635,6 +635,27 @@ __global__ void __launch_bounds__(256) ddim_update_kernel(const float* __restric
     }
 }
 
+// Frames per launch pair: both passes of a GroupNorm read x, so a group of frames whose tensors fit the L2 (126 MB) is
+// normalised before the next group is touched -- the second pass then finds its input on chip instead of in HBM.
+// `units` = tensors of S x C bf16 a frame moves through the two passes (forward: x, y; backward: x, dy, dx).
+// GVD_GN_GROUP_MB bounds units x frames x S x C x 2 bytes; DEFAULT 0 = one group, because it does not pay: graph-timed on B200
+// (profiles/r02_gn_groups.txt) 25 x 2560 x 320 runs forward / backward in 34 / 53 us ungrouped and 45 / 73 us with 48 MB groups
+// (71 / 99 us with 24 MB) -- the extra launches' ramps and tails cost more than the L2 hits return.  Kept as an A/B knob.
+int gn_group_frames(int F, long long S, int C, int units) {
+    static long long budget = -1;
+    if (budget < 0) {
+        const char* e = getenv("GVD_GN_GROUP_MB");
+        budget = (e ? atoll(e) : 0) << 20;
+    }
+    if (budget <= 0 || F <= 1) return F;
+    const long long per_frame = (long long)units * S * C * 2;
+    long long fmax = budget / (per_frame > 0 ? per_frame : 1);
+    if (fmax < 1) fmax = 1;
+    if (fmax >= F) return F;
+    const long long ngroups = (F + fmax - 1) / fmax;
+    return (int)((F + ngroups - 1) / ngroups);
+}
+
 int gn_chunks(int F, long long S) {
     long long want = 592 / (F > 0 ? F : 1);        // one wave: the kernels are resident four per SM (148 x 4 slots), never more CTAs than slots
     long long maxc = (S + 15) / 16;                // at least 16 rows per CTA
@@ -695,15 +716,18 @@ static int groupnorm_fused(const void* x, void* y, const float* gamma, const flo
         g_nn_err_ext = "gvd_groupnorm_cl: needs C % groups == 0, C % 8 == 0, groups <= 128";
         return 2;
     }
-    // enough CTAs to fill the chip even for small feature maps: >= ~2 waves of 148 SMs, >= 16 rows per CTA
-    int nchunks = gn_chunks(F, S);
-    const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
-    nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
-    if (tmp_floats < (size_t)F * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
-    gn_partial_kernel<<<dim3(nchunks, F), 256, gn_partial_smem(groups), s>>>((const __nv_bfloat16*)x, (int)S, C, groups, rows_per_chunk, tmp);
-    const int rows_per_cta = rows_per_chunk;
-    launch_gn_apply(do_silu, dim3((unsigned)nchunks, F), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, tmp, (int)S, C, groups,
-                    nchunks, rows_per_cta, eps, S, stats_out);
+    const int fg = gn_group_frames(F, S, C, 2);
+    for (int f0 = 0; f0 < F; f0 += fg) {
+        const int Fg = F - f0 < fg ? F - f0 : fg;
+        int nchunks = gn_chunks(Fg, S);  // one wave of CTAs per launch, >= 16 rows per CTA
+        const int rows_per_chunk = (int)((S + nchunks - 1) / nchunks);
+        nchunks = (int)((S + rows_per_chunk - 1) / rows_per_chunk);
+        if (tmp_floats < (size_t)Fg * nchunks * groups * 2) { g_nn_err_ext = "gvd_groupnorm_cl: scratch too small"; return 2; }
+        const __nv_bfloat16* xg = (const __nv_bfloat16*)x + (size_t)f0 * S * C;
+        gn_partial_kernel<<<dim3(nchunks, Fg), 256, gn_partial_smem(groups), s>>>(xg, (int)S, C, groups, rows_per_chunk, tmp);
+        launch_gn_apply(do_silu, dim3((unsigned)nchunks, Fg), s, xg, (__nv_bfloat16*)y + (size_t)f0 * S * C, gamma, beta, tmp, (int)S, C, groups,
+                        nchunks, rows_per_chunk, eps, S, stats_out ? stats_out + (size_t)f0 * groups * 2 : nullptr);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_nn_err_ext = std::string("gvd_groupnorm_cl: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -748,7 +772,13 @@ int gvd_groupnorm_cl_apply(const void* x, void* y, const float* gamma, const flo
 }
 
 size_t gvd_groupnorm_tmp_floats(int F, long long S, int groups) {
-    return (size_t)F * (gn_chunks(F, S) + 1) * groups * 2;
+    // the fused call may run the frames in groups (gn_group_frames), each with its own chunking: the largest of them all
+    size_t most = (size_t)F * (gn_chunks(F, S) + 1);
+    for (int fg = 1; fg < F; ++fg) {
+        const size_t n = (size_t)fg * (gn_chunks(fg, S) + 1);
+        if (n > most) most = n;
+    }
+    return most * groups * 2;
 }
 
 int gvd_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,

@@ -80,7 +80,7 @@ def _bf(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("silu", [0, 1, 2])
-@pytest.mark.parametrize("F,S,C", [(2, 40, 64), (1, 70, 320), (1, 19, 2560)])
+@pytest.mark.parametrize("F,S,C", [(2, 40, 64), (1, 70, 320), (1, 19, 2560), (3, 700, 320)])
 def test_groupnorm_bwd_kernels(monkeypatch, emu_lib, F, S, C, silu):
     from vc_b200 import ops
 
@@ -143,6 +143,21 @@ def test_col2im3x3_kernel(monkeypatch, emu_lib, stride, up, H, W):
     emu, closed = _both(monkeypatch, emu_lib, lambda: ops.conv3x3_dx(dy, F_, H, W, Cin, w, stride, up))
     assert _rel(emu, closed) < 1e-3          # same bf16 dcol, fp32 sums of <= 36 taps in a different order
     assert _rel(emu, xf.grad) < 1.5e-2
+
+
+def test_groupnorm_frame_groups_in_a_subprocess():
+    """GVD_GN_GROUP_MB (read once per process) splits the frames of one GroupNorm call into L2-sized launch pairs; with a 1 MB
+    budget the (3, 700, 320) cases above run as three groups, each with its own chunking, scratch window and statistics
+    offset -- forward (fused + kept statistics) and backward, same tolerances."""
+    import subprocess
+
+    env = dict(os.environ, GVD_GN_GROUP_MB="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_nn_fwd_emu_cpu.py"), os.path.join(here, "test_nn_bwd_emu_cpu.py"),
+                        "-k", "(test_groupnorm_kernels or test_groupnorm_bwd_kernels or keep_stats) and not subprocess"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_upsample2x_bwd_kernel(monkeypatch, emu_lib):

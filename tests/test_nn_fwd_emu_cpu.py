@@ -51,7 +51,7 @@ def _bf(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("silu", [0, 1, 2])
-@pytest.mark.parametrize("F,S,C", [(2, 40, 64), (1, 70, 320), (1, 19, 2560)])
+@pytest.mark.parametrize("F,S,C", [(2, 40, 64), (1, 70, 320), (1, 19, 2560), (3, 700, 320)])
 def test_groupnorm_kernels(monkeypatch, emu_lib, F, S, C, silu):
     from vc_b200 import ops
 
