@@ -613,7 +613,8 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* s_full = bars + 5;     // [2]
     uint64_t* p_full = bars + 7;     // [2]
     uint64_t* o_done = bars + 9;     // one completion per PV_i
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* o_final = bars + 10;   // completes once, after the last PV
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -634,6 +635,7 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             tc::mbar_init(&p_full[s], 4);  // one arrival per softmax warp
         }
         tc::mbar_init(o_done, 1);
+        tc::mbar_init(o_final, 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
@@ -687,6 +689,7 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     umma_bf16_ts(tmem_base + FA7_O_COL, tmem_base + FA7_P_COL + (uint32_t)(i & 1) * 32 + k * 8,
                                  tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (i | k) != 0);
                 tc::umma_commit(o_done);
+                if (i + 1 == nsub) tc::umma_commit(o_final);
                 if ((i & 1) || i + 1 == nsub) tc::umma_commit(&kv_empty[s]);  // the tile's last sub-block: K_j, V_j have no reader left
             }
         }
@@ -767,7 +770,12 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             l_run += l0 + l1;
             m_run = m_new;
         }
-        tc::mbar_wait(o_done, (uint32_t)((nsub - 1) & 1));
+        // The end of the accumulation has its own single-use barrier.  o_done completes once per sub-block, and a parity
+        // wait on it is only meaningful when the waiter is at most one phase behind: the last thing this thread waited on,
+        // s_full(nsub - 1), certifies PV up to nsub - 3 only, so "parity of phase nsub - 1" could be answered by phase
+        // nsub - 3 while PV_{nsub-2} was still in flight.  (It never showed in a timed run -- the softmax of the last
+        // sub-block outlasts that MMA -- but a compute-sanitizer run, with its different timing, produced one wrong tile.)
+        tc::mbar_wait(o_final, 0);
         tc::fence_after_sync();
         const float inv = 1.0f / l_run;
         // the statistic the backward needs (attn_bwd_tc.cu); m_run may be a stale maximum, m_run + log2 l_run is exact either way
@@ -823,7 +831,8 @@ flash_attn8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* s_full = bars + 5;     // [2]
     uint64_t* p_full = bars + 7;     // [2]
     uint64_t* o_done = bars + 9;     // one completion per PV_i
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* o_final = bars + 10;   // completes once, after the last PV
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
     float* xchg = reinterpret_cast<float*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256);  // [2][2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -845,6 +854,7 @@ flash_attn8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             tc::mbar_init(&p_full[s], 8);  // one arrival per softmax warp
         }
         tc::mbar_init(o_done, 1);
+        tc::mbar_init(o_final, 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_ptr, FA_TMEM_COLS);
@@ -898,6 +908,7 @@ flash_attn8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     umma_bf16_ts(tmem_base + FA7_O_COL, tmem_base + FA7_P_COL + (uint32_t)(i & 1) * 32 + k * 8,
                                  tc::make_desc_kmajor_sw128(v_addr + k * 16 * 128), idesc_pv, (i | k) != 0);
                 tc::umma_commit(o_done);
+                if (i + 1 == nsub) tc::umma_commit(o_final);
                 if ((i & 1) || i + 1 == nsub) tc::umma_commit(&kv_empty[s]);  // the tile's last sub-block: K_j, V_j have no reader left
             }
         }
@@ -983,7 +994,12 @@ flash_attn8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         xb[hf * 128 + rloc] = l_run;
         pair_bar(q);
         const float inv = 1.0f / (l_run + xb[(hf ^ 1) * 128 + rloc]);
-        tc::mbar_wait(o_done, (uint32_t)((nsub - 1) & 1));
+        // The end of the accumulation has its own single-use barrier.  o_done completes once per sub-block, and a parity
+        // wait on it is only meaningful when the waiter is at most one phase behind: the last thing this thread waited on,
+        // s_full(nsub - 1), certifies PV up to nsub - 3 only, so "parity of phase nsub - 1" could be answered by phase
+        // nsub - 3 while PV_{nsub-2} was still in flight.  (It never showed in a timed run -- the softmax of the last
+        // sub-block outlasts that MMA -- but a compute-sanitizer run, with its different timing, produced one wrong tile.)
+        tc::mbar_wait(o_final, 0);
         tc::fence_after_sync();
         __nv_bfloat16* dst = p.out + (long long)b * p.o_stride_b + (long long)h * p.o_stride_h + (long long)row * p.ldo + 32 * hf;
         uint32_t o[32];
