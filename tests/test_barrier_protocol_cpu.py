@@ -1,5 +1,5 @@
-"""Model check of the mbarrier / tcgen05.commit protocols of the attention kernels (csrc/attn_tc.cu generation 7,
-csrc/attn_bwd_tc.cu both forms) under random schedules.
+"""Model check of the mbarrier / tcgen05.commit protocols of the tensor-core kernels (csrc/attn_tc.cu generation 7,
+csrc/attn_bwd_tc.cu both forms, csrc/gemm_tc.cu one-CTA persistent kernel) under random schedules.
 
 What this is: a hand transcription of each kernel's SYNCHRONISATION -- which agent waits on which barrier with which
 parity expression, which MMAs it issues, when it commits -- run under a randomised scheduler in which the tensor pipe and
@@ -361,3 +361,72 @@ def backward_form2(nsub, seed, lag, kv=True, softmax_warps=4, stages=2):
 def test_backward_second_form_protocol(nsub, kv):
     for seed in range(60):
         backward_form2(nsub, seed, lag=(seed % 6) * 0.17, kv=kv)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GEMM, one-CTA persistent kernel (gemm_tc.cu::gemm_bf16_persistent_kernel): ST-stage operand ring fed in bursts of G
+# k blocks, accumulator double-buffered in TMEM, eight epilogue warps that hand a buffer back as soon as they have read it
+# ------------------------------------------------------------------------------------------------------------------
+def gemm_persistent(tiles, num_kb, stages, group, seed, lag, epi_warps=8):
+    m = Machine(seed, lag)
+    full, empty = [Barrier(f"full{s}") for s in range(stages)], [Barrier(f"empty{s}") for s in range(stages)]
+    tmem_full, tmem_empty = [Barrier(f"tmem_full{b}") for b in range(2)], [Barrier(f"tmem_empty{b}", epi_warps) for b in range(2)]
+    st = {"stage": [None] * stages, "acc": [None, None], "kdone": [0, 0], "read": [[None] * epi_warps for _ in range(2)]}
+
+    def producer():
+        kc = 0
+        for t in range(tiles):
+            kb = 0
+            while kb < num_kb:
+                g_n = min(group, num_kb - kb)
+                for g in range(g_n):  # the whole burst's slots are awaited first, then requested
+                    yield ("wait", empty[(kc + g) % stages], (((kc + g) // stages) & 1) ^ 1)
+                for g in range(g_n):
+                    s = kc % stages
+                    yield ("tma", (lambda s=s, t=t, k=kb + g: st["stage"].__setitem__(s, (t, k))), full[s])
+                    kc += 1
+                kb += g_n
+
+    def mma():
+        kc = 0
+        for it in range(tiles):
+            buf = it & 1
+            yield ("wait", tmem_empty[buf], ((it >> 1) & 1) ^ 1)
+
+            def check_drained(it=it, buf=buf):
+                need(it < 2 or all(v == it - 2 for v in st["read"][buf]), f"tile {it} overwrote buffer {buf} read by {st['read'][buf]}")
+            yield ("do", check_drained)
+            for kb in range(num_kb):
+                s = kc % stages
+                yield ("wait", full[s], (kc // stages) & 1)
+
+                def run(it=it, kb=kb, s=s, buf=buf):
+                    need(st["stage"][s] == (it, kb), f"MMA (tile {it}, k {kb}) read stage holding {st['stage'][s]}")
+                    st["acc"][buf] = it
+                    st["kdone"][buf] = kb + 1
+                yield ("mma", run)
+                yield ("commit", empty[s])
+                kc += 1
+            yield ("commit", tmem_full[buf])
+
+    def epilogue(w):
+        for it in range(tiles):
+            buf = it & 1
+            yield ("wait", tmem_full[buf], (it >> 1) & 1)
+            yield ("do", lambda it=it, buf=buf: need(st["acc"][buf] == it and st["kdone"][buf] == num_kb,
+                                                     f"epilogue of tile {it} read tile {st['acc'][buf]} after {st['kdone'][buf]} k blocks"))
+            yield ("do", lambda it=it, buf=buf: st["read"][buf].__setitem__(w, it))
+            yield ("arrive", tmem_empty[buf])
+
+    m.add("producer", producer())
+    m.add("mma", mma())
+    for w in range(epi_warps):
+        m.add(f"epi{w}", epilogue(w))
+    m.run()
+
+
+@pytest.mark.parametrize("stages,group", [(3, 1), (6, 2), (6, 3), (8, 2)])
+@pytest.mark.parametrize("tiles,num_kb", [(1, 1), (2, 5), (5, 3), (7, 20)])
+def test_gemm_persistent_protocol(tiles, num_kb, stages, group):
+    for seed in range(30):
+        gemm_persistent(tiles, num_kb, stages, group, seed, lag=(seed % 6) * 0.17)
