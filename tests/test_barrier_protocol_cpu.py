@@ -1,5 +1,5 @@
 """Model check of the mbarrier / tcgen05.commit protocols of the tensor-core kernels (csrc/attn_tc.cu generation 7,
-csrc/attn_bwd_tc.cu both forms, csrc/gemm_tc.cu one-CTA persistent kernel) under random schedules.
+csrc/attn_bwd_tc.cu both forms, csrc/gemm_tc.cu one-CTA persistent and CTA-pair kernels) under random schedules.
 
 What this is: a hand transcription of each kernel's SYNCHRONISATION -- which agent waits on which barrier with which
 parity expression, which MMAs it issues, when it commits -- run under a randomised scheduler in which the tensor pipe and
@@ -75,7 +75,11 @@ class Machine:
                 continue  # engines exist but chose to lag this tick
             if choice == "<pipe>":
                 kind, arg = self.pipe.pop(0)
-                arg() if kind == "mma" else arg.arrive()
+                if kind == "mma":
+                    arg()
+                else:  # a commit; a list is a multicast commit (cta_group::2: the same barrier in both CTAs of the pair)
+                    for bar in (arg if isinstance(arg, list) else [arg]):
+                        bar.arrive()
             elif choice == "<tma>":
                 fn, bar = self.tma.pop(self.rng.randrange(len(self.tma)))
                 fn()
@@ -430,3 +434,77 @@ def gemm_persistent(tiles, num_kb, stages, group, seed, lag, epi_warps=8):
 def test_gemm_persistent_protocol(tiles, num_kb, stages, group):
     for seed in range(30):
         gemm_persistent(tiles, num_kb, stages, group, seed, lag=(seed % 6) * 0.17)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GEMM, CTA-pair kernel (gemm_tc.cu::gemm_bf16_pair_kernel, cta_group::2): both CTAs' producers signal the LEADER's full[s]
+# (one expect_tx arrival by the leader + the bytes of both CTAs' loads), the leader's MMA thread multicasts its commits to
+# both CTAs' empty[s] / tmem_full[buf], and the sixteen epilogue warps of the pair arrive on the leader's tmem_empty[buf]
+# ------------------------------------------------------------------------------------------------------------------
+def gemm_pair(tiles, num_kb, stages, group, seed, lag, epi_warps=8):
+    m = Machine(seed, lag)
+    full = [Barrier(f"full{s}", 3) for s in range(stages)]  # leader only: its arrive.expect_tx + the two CTAs' transfers
+    empty = [[Barrier(f"empty{r}_{s}") for s in range(stages)] for r in range(2)]
+    tmem_full = [[Barrier(f"tmem_full{r}_{b}") for b in range(2)] for r in range(2)]
+    tmem_empty = [Barrier(f"tmem_empty{b}", 2 * epi_warps) for b in range(2)]  # leader only
+    st = {"stage": [[None] * stages for _ in range(2)], "acc": [None, None], "kdone": [0, 0],
+          "read": [[None] * (2 * epi_warps) for _ in range(2)]}
+
+    def producer(rank):
+        kc = 0
+        for t in range(tiles):
+            kb = 0
+            while kb < num_kb:
+                g_n = min(group, num_kb - kb)
+                for g in range(g_n):
+                    yield ("wait", empty[rank][(kc + g) % stages], (((kc + g) // stages) & 1) ^ 1)
+                for g in range(g_n):
+                    s = kc % stages
+                    if rank == 0:
+                        yield ("arrive", full[s])  # arrive.expect_tx(2 x stage bytes)
+                    yield ("tma", (lambda s=s, t=t, k=kb + g: st["stage"][rank].__setitem__(s, (t, k))), full[s])
+                    kc += 1
+                kb += g_n
+
+    def mma():  # the leader's warp 1
+        kc = 0
+        for it in range(tiles):
+            buf = it & 1
+            yield ("wait", tmem_empty[buf], ((it >> 1) & 1) ^ 1)
+            yield ("do", lambda it=it, buf=buf: need(it < 2 or all(v == it - 2 for v in st["read"][buf]),
+                                                     f"tile {it} overwrote buffer {buf} read by {st['read'][buf]}"))
+            for kb in range(num_kb):
+                s = kc % stages
+                yield ("wait", full[s], (kc // stages) & 1)
+
+                def run(it=it, kb=kb, s=s, buf=buf):
+                    need(st["stage"][0][s] == (it, kb) and st["stage"][1][s] == (it, kb),
+                         f"MMA (tile {it}, k {kb}) read stages holding {st['stage'][0][s]} / {st['stage'][1][s]}")
+                    st["acc"][buf], st["kdone"][buf] = it, kb + 1
+                yield ("mma", run)
+                yield ("commit", [empty[0][s], empty[1][s]])
+                kc += 1
+            yield ("commit", [tmem_full[0][buf], tmem_full[1][buf]])
+
+    def epilogue(rank, w):
+        for it in range(tiles):
+            buf = it & 1
+            yield ("wait", tmem_full[rank][buf], (it >> 1) & 1)
+            yield ("do", lambda it=it, buf=buf: need(st["acc"][buf] == it and st["kdone"][buf] == num_kb,
+                                                     f"epilogue of tile {it} read tile {st['acc'][buf]} after {st['kdone'][buf]} k blocks"))
+            yield ("do", lambda it=it, buf=buf: st["read"][buf].__setitem__(rank * epi_warps + w, it))
+            yield ("arrive", tmem_empty[buf])
+
+    for r in range(2):
+        m.add(f"producer{r}", producer(r))
+        for w in range(epi_warps):
+            m.add(f"epi{r}_{w}", epilogue(r, w))
+    m.add("mma", mma())
+    m.run()
+
+
+@pytest.mark.parametrize("stages,group", [(5, 1), (7, 2)])
+@pytest.mark.parametrize("tiles,num_kb", [(1, 1), (2, 5), (5, 3), (6, 12)])
+def test_gemm_pair_protocol(tiles, num_kb, stages, group):
+    for seed in range(20):
+        gemm_pair(tiles, num_kb, stages, group, seed, lag=(seed % 6) * 0.17)
