@@ -115,7 +115,7 @@ def need(cond, msg):
 # ------------------------------------------------------------------------------------------------------------------
 # forward, generation 7 (attn_tc.cu::flash_attn7_kernel): 64-key sub-blocks, S / P double-buffered, QK one ahead
 # ------------------------------------------------------------------------------------------------------------------
-def forward_gen7(nsub, seed, lag, rescale_prob=0.3, first_epilogue=False, softmax_warps=4):
+def forward_gen7(nsub, seed, lag, rescale_prob=0.3, first_epilogue=False, two_waits=False, softmax_warps=4):
     m = Machine(seed, lag)
     rng = random.Random(seed * 7 + 1)
     nblk = (nsub + 1) // 2
@@ -178,7 +178,11 @@ def forward_gen7(nsub, seed, lag, rescale_prob=0.3, first_epilogue=False, softma
                 yield ("do", lambda i=i: need(st["pv_done"] == i, f"rescale({i}) with {st['pv_done']} PVs executed"))
             yield ("do", lambda i=i: st["P"][i & 1].__setitem__(w, i))
             yield ("arrive", p_full[i & 1])
-        if first_epilogue:
+        if two_waits:  # the first attempted fix: phase nsub - 2, then nsub - 1, on the per-sub-block barrier
+            if nsub >= 2:
+                yield ("wait", o_done, (nsub - 2) & 1)
+            yield ("wait", o_done, (nsub - 1) & 1)
+        elif first_epilogue:
             yield ("wait", o_done, (nsub - 1) & 1)
         else:
             yield ("wait", o_final, 0)
@@ -205,6 +209,19 @@ def test_checker_finds_the_epilogue_wait_the_forward_used_to_have():
             forward_gen7(4, seed, lag=0.9, first_epilogue=True)
         except Violation as e:
             assert "epilogue read O" in str(e), e
+            found += 1
+    assert found > 0
+
+
+def test_checker_finds_the_deadlock_of_the_first_attempted_fix():
+    """Waiting for phase nsub - 2 and then nsub - 1 on the same barrier hangs whenever both are already over (a parity wait
+    two phases AHEAD never passes) -- which is the normal case at speed; on hardware it cost the round's last GPU minutes."""
+    found = 0
+    for seed in range(100):
+        try:
+            forward_gen7(4, seed, lag=0.0, two_waits=True)
+        except Violation as e:
+            assert "deadlock" in str(e), e
             found += 1
     assert found > 0
 
