@@ -20,6 +20,7 @@
 
 namespace {
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
     asm volatile(
@@ -32,6 +33,12 @@ __device__ __forceinline__ uint32_t movm_trans(uint32_t x) {
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
+#else  // tests/cuda_emu: the two warp-collective tile instructions with the PTX fragment layouts spelled out
+inline void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    emu_mma_m16n8k16_bf16(d, a0, a1, a2, a3, b0, b1);
+}
+inline uint32_t movm_trans(uint32_t x) { return emu_movmatrix_trans_b16(x); }
+#endif
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -390,3 +397,16 @@ bool gvd_mma_temporal_attention(const void* q, const void* k, const void* v, voi
                                                                    (__nv_bfloat16*)out, B, T, S, H, scale);
     return true;
 }
+
+#ifdef GVD_HOST_EMU
+// C entry points of the host build (tests/test_tattn_mma_emu_cpu.py); on the GPU the two functions above are reached through
+// gvd_temporal_attention / gvd_temporal_attention_bwd
+extern "C" int gvd_emu_mma_temporal_attention(const void* q, const void* k, const void* v, void* out, int B, int T, long long S, int H,
+                                              float scale) {
+    return gvd_mma_temporal_attention(q, k, v, out, B, T, S, H, scale, nullptr) ? 0 : 2;
+}
+extern "C" int gvd_emu_mma_temporal_attention_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
+                                                  int B, int T, long long S, int H, float scale) {
+    return gvd_mma_temporal_attention_bwd(q, k, v, dout, dq, dk, dv, B, T, S, H, scale, nullptr) ? 0 : 2;
+}
+#endif

@@ -226,6 +226,59 @@ template <class T> inline unsigned __match_any_sync(unsigned, T v) {
 }
 inline unsigned __activemask() { return 0xffffffffu; }
 
+// ---- warp-level tensor-core tiles (csrc/tattn_mma.cu), fragment layouts of the PTX ISA ----
+// mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32: lane (g = lane / 4, c = lane % 4) holds
+//   A (16 x 16, row):  a0 = (row g, k 2c..2c+1)  a1 = (row g + 8, same k)  a2 = (row g, k 2c + 8..)  a3 = (row g + 8, k 2c + 8..)
+//   B (16 x 8, col):   b0 = (k 2c..2c+1, n g)    b1 = (k 2c + 8.., n g)
+//   C / D (16 x 8):    d0 = (row g, n 2c)  d1 = (row g, n 2c + 1)  d2 = (row g + 8, n 2c)  d3 = (row g + 8, n 2c + 1)
+// All 32 lanes of the warp must call it (it is built on the warp exchange above); fp32 accumulation in k order.
+inline float emu_bf16_bits(uint32_t pair, int hi) { uint32_t b = (hi ? pair >> 16 : pair & 0xffffu) << 16; float f; std::memcpy(&f, &b, 4); return f; }
+inline void emu_mma_m16n8k16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    const int lane = emu_tid & 31, g = lane >> 2, c = lane & 3;
+    float arow[2][16], bcol[2][16];  // rows g, g + 8 of A; columns 2c, 2c + 1 of B
+    emu_warp_exchange((uint64_t)a0 | ((uint64_t)a1 << 32), [&](auto get, int) {
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t r = get(g * 4 + k / 2);
+            arow[0][k] = emu_bf16_bits((uint32_t)r, k & 1);
+            arow[1][k] = emu_bf16_bits((uint32_t)(r >> 32), k & 1);
+        }
+        return 0;
+    });
+    emu_warp_exchange((uint64_t)a2 | ((uint64_t)a3 << 32), [&](auto get, int) {
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t r = get(g * 4 + k / 2);
+            arow[0][8 + k] = emu_bf16_bits((uint32_t)r, k & 1);
+            arow[1][8 + k] = emu_bf16_bits((uint32_t)(r >> 32), k & 1);
+        }
+        return 0;
+    });
+    emu_warp_exchange((uint64_t)b0 | ((uint64_t)b1 << 32), [&](auto get, int) {
+        for (int e = 0; e < 2; ++e)
+            for (int k = 0; k < 8; ++k) {
+                const uint64_t r = get((2 * c + e) * 4 + k / 2);
+                bcol[e][k] = emu_bf16_bits((uint32_t)r, k & 1);
+                bcol[e][8 + k] = emu_bf16_bits((uint32_t)(r >> 32), k & 1);
+            }
+        return 0;
+    });
+    for (int m = 0; m < 2; ++m)
+        for (int e = 0; e < 2; ++e) {
+            float acc = d[2 * m + e];
+            for (int k = 0; k < 16; ++k) acc += arow[m][k] * bcol[e][k];
+            d[2 * m + e] = acc;
+        }
+}
+// movmatrix.sync.aligned.m8n8.trans.b16: lane (g, c) holds row g, columns 2c..2c+1 of an 8 x 8 matrix of 16-bit elements
+// and receives the same positions of its transpose, i.e. M[2c][g] and M[2c + 1][g]
+inline uint32_t emu_movmatrix_trans_b16(uint32_t x) {
+    const int lane = emu_tid & 31, g = lane >> 2, c = lane & 3;
+    return emu_warp_exchange(x, [&](auto get, int) {
+        const uint32_t lo = get((2 * c) * 4 + (g >> 1)), hi = get((2 * c + 1) * 4 + (g >> 1));
+        const uint32_t e0 = (g & 1) ? lo >> 16 : lo & 0xffffu, e1 = (g & 1) ? hi >> 16 : hi & 0xffffu;
+        return e0 | (e1 << 16);
+    });
+}
+
 inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
     const int nthreads = (int)(block.x * block.y * block.z);
     for (unsigned bz = 0; bz < grid.z; ++bz)
