@@ -42,7 +42,18 @@
 
 extern thread_local std::string g_nn_err_ext;
 // attn_tc.cu: [B, N, H*64] bf16 as a (64, N, H, B) tensor map with 64 x 128 boxes, 128-byte swizzle
+#ifndef GVD_HOST_EMU
 bool gvd_fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long H, long long B, long long ld, long long sb);
+#else  // the host build (tests/cuda_emu) holds this file alone: the same map, recorded by the driver-API stand-in
+static bool gvd_fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long H, long long B, long long ld, long long sb) {
+    cuuint64_t dims[4] = {64, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, 64 * 2, (cuuint64_t)(B > 1 ? sb : ld) * 2};
+    cuuint32_t box[4] = {64, 128, 1, 1}, estr[4] = {1, 1, 1, 1};
+    return emu_cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
 
 namespace {
 
@@ -52,6 +63,7 @@ constexpr int FB_THREADS = 64 + 8 * 32;
 constexpr int FB_SMEM = FB_TILE * (2 + 2 * FB_STAGES) + 1024 + 256 + FB_STAGES * 1024;  // + per-stage column statistics
 constexpr uint32_t FB_S = 0, FB_DP = 128, FB_P = 256, FB_DS = 320, FB_ACC0 = 384, FB_ACC1 = 448;
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -79,17 +91,30 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else  // tests/cuda_emu/tc_emu.h
+inline float ex2(float x) { return exp2f(x); }
+inline uint32_t idesc_ts_mn() { return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
+inline void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    tc::emu_umma_bf16_ts(tmem_d, tmem_a, bdesc, idesc, accumulate);
+}
+inline void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) { tc::emu_tmem_st16(taddr, v); }
+inline void tmem_st_wait() {}
+#endif
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // global -> shared bulk copy (bytes % 16 == 0), completion counted on an mbarrier like the tensor-map loads
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar))
                  : "memory");
 }
+#else
+inline void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) { tc::emu_bulk_g2s(smem_dst, gmem_src, bytes, bar); }
+#endif
 
 struct FbParams {
     const float* lse;    // [B, H, ldl]  base-2 log-sum-exp of the scaled logits

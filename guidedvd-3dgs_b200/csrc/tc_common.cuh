@@ -2,6 +2,13 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptors" (same fields CUTLASS names in
 // cute/arch/mma_sm100_desc.hpp); nothing here depends on CUTLASS.
 #pragma once
+#ifdef GVD_HOST_EMU
+// tests/cuda_emu: the same namespace on the host (tensor memory, swizzled tensor-map loads, tcgen05.mma, mbarrier phases)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tc_emu.h"
+#else
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -180,3 +187,4 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 }
 
 }  // namespace tc
+#endif  // GVD_HOST_EMU

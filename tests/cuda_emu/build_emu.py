@@ -37,7 +37,11 @@ def rewrite(src):
     dyn = []
 
     def hoist(m):
-        dyn.append(f"alignas(16) {m.group(2)} {m.group(3)}[1 << 17];")
+        # one array per NAME (kernels of a file may share it: blocks never overlap); 256 KB-aligned so that the low 18 bits
+        # of a shared-memory pointer are its offset in the block's window (tc_emu.h::smem_u32, descriptor start addresses)
+        decl = f"alignas(262144) {m.group(2)} {m.group(3)}[1 << 18];"
+        if decl not in dyn:
+            dyn.append(decl)
         return f"/* dynamic shared memory: file-scope array {m.group(3)} */"
     src = DYN_SHARED.sub(hoist, src)
     src = re.sub(r'#include "\.\./\.\./include/(\w+\.h)"', lambda m: f'#include "{os.path.join(ROOT, "include", m.group(1))}"', src)

@@ -26,6 +26,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
