@@ -38,11 +38,15 @@ constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 1024 + 256;
 constexpr int FA_THREADS = 192;
 constexpr uint32_t FA_TMEM_COLS = 256, FA_S_COL = 0, FA_P_COL = 128, FA_O_COL = 192;
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#else  // tests/cuda_emu/tc_emu.h
+inline float ex2(float x) { return exp2f(x); }
+#endif
 
 // MN-major B operand tile (V_j: 128 keys x 64 d, rows of 128 bytes, 128-byte swizzle): same geometry as the K-major
 // tile (8-row atoms of 1024 bytes); the "major" bit lives in the instruction descriptor.
@@ -51,6 +55,7 @@ __device__ __forceinline__ uint32_t make_idesc_pv() {
            ((uint32_t)(FA_BM >> 4) << 24);
 }
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
     asm volatile(
         "{\n"
@@ -70,6 +75,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+inline void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    tc::emu_umma_bf16_ts(tmem_d, tmem_a, bdesc, idesc, accumulate);
+}
+inline void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) { tc::emu_tmem_st16(taddr, v); }
+inline void tmem_st_wait() {}
+#endif
 
 struct FaParams {
     __nv_bfloat16* out;
@@ -814,7 +826,11 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 constexpr int FA8_THREADS = 64 + 8 * 32;
 constexpr int FA8_SMEM = FA_SMEM + 2 * 2 * 128 * 4;  // + pair exchange: [parity][half][row] floats
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+#else
+inline void pair_bar(int) { std::abort(); }  // named barriers have no host stand-in: generations 5 and 8 are not run there
+#endif
 
 __global__ void __launch_bounds__(FA8_THREADS, 2)
 flash_attn8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -1044,7 +1060,11 @@ constexpr int FA5_BAR_OFF = FA_TILE_BYTES * (2 + 2 * FA5_STAGES);
 constexpr int FA5_XCHG_OFF = FA5_BAR_OFF + 256;
 constexpr int FA5_SMEM = FA5_XCHG_OFF + 2 * 2 * 2 * 128 * 4 + 1024;  // exchange: [tile][parity][half][row]
 
+#ifndef GVD_HOST_EMU
 __device__ __forceinline__ void pair_sync_id(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+#else
+inline void pair_sync_id(int) { std::abort(); }
+#endif
 
 __global__ void __launch_bounds__(FA5_THREADS, 1)  // 18 warps are allocated as 20: 96 registers per thread
 flash_attn5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -1269,6 +1289,7 @@ flash_attn5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
+#ifndef GVD_HOST_EMU
 PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -1280,6 +1301,9 @@ PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() {
     }
     return fn;
 }
+#else
+PFN_cuTensorMapEncodeTiled_v12000 fa_get_encode() { return emu_cuTensorMapEncodeTiled; }
+#endif
 
 // [B, N, H*64] bf16 viewed as (d=64, rows=N with stride ld, heads with stride 64, batch with stride sb)
 bool fa_make_tmap(CUtensorMap* map, const void* base, long long N, long long H, long long B, long long ld, long long sb) {

@@ -116,6 +116,7 @@ inline int atomicMax(int* p, int v) { std::atomic_ref<int> a(*p); int o = a.load
 inline unsigned atomicOr(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_or(v); }
 inline unsigned atomicExch(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).exchange(v); }
 inline float __expf(float x) { return expf(x); }
+inline float __log2f(float x) { return log2f(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
