@@ -715,6 +715,9 @@ cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiP
 
 // GVD_GEMM_PAIR: 1 (default) = CTA-pair kernel where it applies, 0 = one-CTA kernels only (A/B timing)
 bool pair_enabled() {
+#ifdef GVD_HOST_EMU
+    return false;  // tests/cuda_emu runs one block at a time: no CTA pairs there
+#endif
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("GVD_GEMM_PAIR");
@@ -748,6 +751,9 @@ cudaError_t launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, cons
 
 // ---- host side: tensor maps ----
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+#ifdef GVD_HOST_EMU
+    return emu_cuTensorMapEncodeTiled;
+#else
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -757,6 +763,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
             fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
     }
     return fn;
+#endif
 }
 
 // 4-D bf16 view: (K contiguous, rows with stride ld, h with stride sh, b with stride sb), all in elements

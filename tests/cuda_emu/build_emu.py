@@ -30,7 +30,7 @@ def rewrite(src):
             i += 1
         args = src[m.end():i - 1]
         out.append(src[pos:m.start()])
-        out.append(f"EMU_LAUNCH({m.group(1)}, {m.group(2)}, {args})")
+        out.append(f"EMU_LAUNCH(({m.group(1)}), {m.group(2)}, {args})")  # parenthesised: template arguments may hold commas
         pos = i
     out.append(src[pos:])
     src = "".join(out)

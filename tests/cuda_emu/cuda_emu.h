@@ -27,6 +27,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __grid_constant__
+#define __cluster_dims__(...)
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))

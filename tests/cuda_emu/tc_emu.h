@@ -164,6 +164,17 @@ inline void emu_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
 }
 inline void tmem_ld_wait() {}
 
+// ---- CTA pairs (cta_group::2, clusters): not emulated -- one block runs at a time; the callers keep the pair kernels off ----
+inline uint32_t cluster_ctarank() { return 0; }
+inline void cluster_sync_all() { std::abort(); }
+inline uint32_t mapa(uint32_t local, uint32_t) { return local; }
+inline void mbar_arrive_cluster(uint32_t) { std::abort(); }
+inline void tma_load_4d_2cta(void*, const CUtensorMap*, uint32_t, int, int, int, int) { std::abort(); }
+inline void tmem_alloc_2cta(uint32_t*, uint32_t) { std::abort(); }
+inline void tmem_dealloc_2cta(uint32_t, uint32_t) { std::abort(); }
+inline void umma_bf16_2cta(uint32_t, uint64_t, uint64_t, uint32_t, bool) { std::abort(); }
+inline void umma_commit_2cta(uint64_t*) { std::abort(); }
+
 // global -> shared bulk copy counted on an mbarrier (no swizzle)
 inline void emu_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     std::memcpy(smem_dst, gmem_src, bytes);
