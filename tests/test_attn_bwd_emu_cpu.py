@@ -82,3 +82,32 @@ def test_fused_attention_adjoint_on_the_host_first_form():
             "for c in t.CASES[:4]: t.run_case(*c)\nprint('ok')" % HERE)
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GVD_FLASH_BWD_CTAS="1"), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_forward_statistic_feeds_the_adjoint_on_the_host():
+    """The two kernels together, as vc_b200.grad.FlashAttention chains them: out and lse from the emulated forward
+    (attn_tc.cu, generation 7) go into the emulated adjoint; gradients against autograd over fp32 attention."""
+    import build_emu
+
+    Lb, gvd_native = _lib()
+    Lf = C.CDLL(build_emu.build("attn_tc"))
+    vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+    Lf.gvd_flash_attention_lse.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, ll, ll, f32, vp]
+    B, Nq, Nk, H, scale = 1, 190, 140, 2, 0.125
+    g = torch.Generator().manual_seed(5)
+    q, do = (torch.randn(B, Nq, H * 64, generator=g).to(BF) for _ in range(2))
+    k = (torch.randn(B, Nk, H * 64, generator=g) * 2.5).to(BF)
+    v = torch.randn(B, Nk, H * 64, generator=g).to(BF)
+    out = torch.empty_like(q)
+    ldl = (Nq + 127) // 128 * 128
+    lse, delta = torch.empty(B, H, ldl), torch.empty(B, H, ldl)
+    assert Lf.gvd_flash_attention_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, Nq, Nk, H, Nq * H * 64,
+                                      Nk * H * 64, scale, None) == 0
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    a = gvd_native.FlashBwdArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, Nq, Nk, H, Nq * H * 64, Nk * H * 64, scale)
+    assert Lb.gvd_flash_attention_bwd(C.byref(a), None) == 0
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bihd,bjhd->bhij", qf.view(B, Nq, H, 64), kf.view(B, Nk, H, 64)) * scale
+    torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vf.view(B, Nk, H, 64)).reshape(B, Nq, H * 64).backward(do.float())
+    assert _rel(dq, qf.grad) < 2e-2 and _rel(dk, kf.grad) < 2e-2 and _rel(dv, vf.grad) < 2e-2
