@@ -282,29 +282,38 @@ inline uint32_t emu_movmatrix_trans_b16(uint32_t x) {
     });
 }
 
+// One set of OS threads per LAUNCH, walking the blocks in order (a thread per (block, CUDA thread) cost more in thread
+// creation than in kernel work: the tiny U-Net of tests/test_unet_emu_cpu.py makes ~5 000 blocks of 192-320 threads).
+// Every block gets a fresh EmuBlock -- a thread that returned early has dropped out of that block's barriers for good --
+// put in place by thread 0 between two launch-wide barriers, so no thread ever sees another block's state.
 inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
     const int nthreads = (int)(block.x * block.y * block.z);
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                EmuBlock blk(nthreads);
-                std::vector<std::thread> ts;
-                ts.reserve(nthreads);
-                for (int t = 0; t < nthreads; ++t)
-                    ts.emplace_back([&, t]() {
-                        emu_blk = &blk;
-                        emu_tid = t;
-                        emu_votes = 0;
-                        threadIdx = uint3_emu{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
-                        blockIdx = uint3_emu{bx, by, bz};
-                        blockDim = block;
-                        gridDim = grid;
-                        body();
-                        blk.warp_bars[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in barriers
-                        blk.block_bar.arrive_and_drop();
-                    });
-                for (auto& th : ts) th.join();
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    if (nblocks == 0 || nthreads == 0) return;
+    std::unique_ptr<EmuBlock> cur(new EmuBlock(nthreads));
+    std::barrier<> launch_bar(nthreads);
+    std::vector<std::thread> ts;
+    ts.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t)
+        ts.emplace_back([&, t]() {
+            for (unsigned long long b = 0; b < nblocks; ++b) {
+                EmuBlock& blk = *cur;
+                emu_blk = &blk;
+                emu_tid = t;
+                emu_votes = 0;
+                threadIdx = uint3_emu{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+                blockIdx = uint3_emu{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
+                blockDim = block;
+                gridDim = grid;
+                body();
+                blk.warp_bars[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in barriers
+                blk.block_bar.arrive_and_drop();
+                launch_bar.arrive_and_wait();              // everyone has left block b
+                if (t == 0 && b + 1 < nblocks) cur.reset(new EmuBlock(nthreads));
+                launch_bar.arrive_and_wait();              // block b + 1's barriers and slots are in place
             }
+        });
+    for (auto& th : ts) th.join();
 }
 #define EMU_LAUNCH(kernel, g, b, smem, stream, ...) emu_launch(dim3(g), dim3(b), [=]() { kernel(__VA_ARGS__); })
 
