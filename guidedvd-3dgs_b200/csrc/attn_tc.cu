@@ -787,7 +787,11 @@ flash_attn7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // s_full(nsub - 1), certifies PV up to nsub - 3 only, so "parity of phase nsub - 1" could be answered by phase
         // nsub - 3 while PV_{nsub-2} was still in flight.  (It never showed in a timed run -- the softmax of the last
         // sub-block outlasts that MMA -- but a compute-sanitizer run, with its different timing, produced one wrong tile.)
+#ifdef GVD_EMU_OLD_EPILOGUE_WAIT  // host tests only (tests/test_attn_fwd_emu_cpu.py): the former wait, to show the checker sees it
+        tc::mbar_wait(o_done, (uint32_t)((nsub - 1) & 1));
+#else
         tc::mbar_wait(o_final, 0);
+#endif
         tc::fence_after_sync();
         const float inv = 1.0f / l_run;
         // the statistic the backward needs (attn_bwd_tc.cu); m_run may be a stale maximum, m_run + log2 l_run is exact either way

@@ -8,14 +8,76 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <random>
 #include <thread>
+#include <vector>
 
 #include "cuda.h"
 #include "cuda_emu.h"
 
 inline char* emu_smem_window = nullptr;          // 256 KB-aligned window holding the block's shared memory
 inline uint32_t emu_tmem[128][512];             // lanes x 32-bit columns
+
+// ---- optional asynchrony (GVD_EMU_ASYNC=<lag 0..99>): MMAs / commits go into an in-order queue, tensor-map and bulk copies
+// into an unordered one, and are executed LATER -- by whichever thread is spinning in an mbarrier wait, with probability
+// (100 - lag) % per spin.  The kernel then sees operands consumed and barriers completed at arbitrary later times, in the
+// order the hardware guarantees and no other: an ordering that only holds "because the MMA is fast" breaks here.
+struct EmuEngine {
+    std::mutex mu;
+    std::deque<std::function<void()>> pipe;      // tcgen05.mma / tcgen05.commit: executed in issue order
+    std::vector<std::function<void()>> copies;   // TMA: any order
+    std::mt19937 rng{12345};
+    int lag = -1;                                // -1: synchronous (default)
+};
+inline EmuEngine emu_engine;
+inline bool emu_async() {
+    static int on = -2;
+    if (on == -2) {
+        const char* e = getenv("GVD_EMU_ASYNC");
+        on = e ? atoi(e) : -1;
+        emu_engine.lag = on;
+    }
+    return on >= 0;
+}
+inline void emu_engine_step(bool force) {  // execute one pending operation (maybe)
+    std::lock_guard<std::mutex> g(emu_engine.mu);
+    if (!force && (int)(emu_engine.rng() % 100) < emu_engine.lag) return;
+    const bool take_copy = !emu_engine.copies.empty() && (emu_engine.pipe.empty() || (emu_engine.rng() & 1));
+    if (take_copy) {
+        const size_t i = emu_engine.rng() % emu_engine.copies.size();
+        auto op = std::move(emu_engine.copies[i]);
+        emu_engine.copies.erase(emu_engine.copies.begin() + (long)i);
+        op();
+    } else if (!emu_engine.pipe.empty()) {
+        auto op = std::move(emu_engine.pipe.front());
+        emu_engine.pipe.pop_front();
+        op();
+    }
+}
+inline void emu_engine_drain() {
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> g(emu_engine.mu);
+            if (emu_engine.pipe.empty() && emu_engine.copies.empty()) return;
+        }
+        emu_engine_step(true);
+    }
+}
+template <class F> inline void emu_issue_pipe(F&& f) {
+    if (!emu_async()) { f(); return; }
+    std::lock_guard<std::mutex> g(emu_engine.mu);
+    emu_engine.pipe.emplace_back(std::forward<F>(f));
+}
+template <class F> inline void emu_issue_copy(F&& f) {
+    if (!emu_async()) { f(); return; }
+    std::lock_guard<std::mutex> g(emu_engine.mu);
+    emu_engine.copies.emplace_back(std::forward<F>(f));
+}
 
 namespace tc {
 
@@ -46,14 +108,23 @@ inline void mbar_arrive(uint64_t* bar) { emu_bar_update(bar, 1, 0); }
 inline void emu_complete_tx(uint64_t* bar, uint32_t bytes) { emu_bar_update(bar, 0, -(int)bytes); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {  // the phase of this parity has completed <=> the current phase's parity differs
     std::atomic_ref<uint64_t> a(*bar);
-    while ((uint32_t)(a.load() & 1) == parity) std::this_thread::yield();
+    while ((uint32_t)(a.load() & 1) == parity) {
+        if (emu_async()) emu_engine_step(false);
+        std::this_thread::yield();
+    }
 }
 
 // ---- TMA ----
 inline void prefetch_tmap(const CUtensorMap*) {}
 inline uint32_t emu_swz(uint32_t off) { return off ^ (((off >> 7) & 7) << 4); }
+inline void emu_tma_box_now(uint32_t dst, const CUtensorMap* m, uint64_t* bar, const int (&c)[5]);
 inline void emu_tma_box(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int (&c)[5]) {
     const uint32_t dst = smem_u32(smem_dst);
+    const CUtensorMap map = *m;  // the kernel parameter outlives the copy, but a by-value capture costs nothing
+    const int c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+    emu_issue_copy([=]() { const int cc[5] = {c0, c1, c2, c3, c4}; emu_tma_box_now(dst, &map, bar, cc); });
+}
+inline void emu_tma_box_now(uint32_t dst, const CUtensorMap* m, uint64_t* bar, const int (&c)[5]) {
     const uint32_t row_bytes = m->box[0] * 2;  // the innermost box dimension is one swizzle row (128 bytes in every use here)
     uint32_t r = 0;
     for (uint32_t i4 = 0; i4 < m->box[4]; ++i4)
@@ -84,7 +155,7 @@ inline void tma_load_4d(void* d, const CUtensorMap* m, uint64_t* bar, int c0, in
 
 // ---- tensor memory ----
 inline void tmem_alloc(uint32_t* smem_result, uint32_t) { *smem_result = 0; }
-inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void tmem_dealloc(uint32_t, uint32_t) { if (emu_async()) emu_engine_drain(); }  // the block is over: nothing may stay in flight
 inline void fence_before_sync() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void fence_after_sync() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
@@ -119,7 +190,11 @@ inline void emu_mma_store(uint32_t tmem_d, int m, int n, float sum, bool accumul
     std::memcpy(&cell, &v, 4);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, K = 16 per instruction; M x N from the instruction descriptor, bit 16: B is MN-major
+inline void emu_umma_ss_now(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate);
 inline void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    emu_issue_pipe([=]() { emu_umma_ss_now(tmem_d, adesc, bdesc, idesc, accumulate); });
+}
+inline void emu_umma_ss_now(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
     const uint32_t a_start = (uint32_t)(adesc & 0x3FFF) << 4, b_start = (uint32_t)(bdesc & 0x3FFF) << 4;
     const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
     const bool mn = (idesc >> 16) & 1;
@@ -132,7 +207,11 @@ inline void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t 
         }
 }
 // the same with A read from tensor memory: row m = lane m, K = 16 bf16 packed in 8 consecutive 32-bit columns
+inline void emu_umma_ts_now(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate);
 inline void emu_umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    emu_issue_pipe([=]() { emu_umma_ts_now(tmem_d, tmem_a, bdesc, idesc, accumulate); });
+}
+inline void emu_umma_ts_now(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
     const uint32_t b_start = (uint32_t)(bdesc & 0x3FFF) << 4;
     const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
     const bool mn = (idesc >> 16) & 1;
@@ -149,7 +228,7 @@ inline void emu_umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, u
         }
     }
 }
-inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }  // the MMAs above have completed by the time this is called
+inline void umma_commit(uint64_t* bar) { emu_issue_pipe([=]() { mbar_arrive(bar); }); }  // arrives once everything issued before it has executed
 
 template <int NCOL>
 inline void emu_tmem_ld(uint32_t taddr, uint32_t (&v)[NCOL]) {
@@ -177,8 +256,10 @@ inline void umma_commit_2cta(uint64_t*) { std::abort(); }
 
 // global -> shared bulk copy counted on an mbarrier (no swizzle)
 inline void emu_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    std::memcpy(smem_dst, gmem_src, bytes);
-    emu_complete_tx(bar, bytes);
+    emu_issue_copy([=]() {
+        std::memcpy(smem_dst, gmem_src, bytes);
+        emu_complete_tx(bar, bytes);
+    });
 }
 
 }  // namespace tc
