@@ -64,7 +64,8 @@ def build(name="nn_backward", sources=None, extra_flags=()):
     if asan:
         extra_flags = tuple(extra_flags) + ("-fsanitize=address", "-fno-omit-frame-pointer")
     so = os.path.join(OUT, f"lib{name}_emu{'_asan' if asan else ''}.so")
-    deps = [os.path.join(CSRC, s) for s in sources] + [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cub", "cub.cuh"), __file__]
+    deps = [os.path.join(CSRC, s) for s in sources] + [os.path.join(HERE, h) for h in ("cuda_emu.h", "tc_emu.h", "cuda.h", "cudaTypedefs.h")]
+    deps += [os.path.join(HERE, "cub", "cub.cuh"), __file__]
     deps += [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
     if os.path.exists(so) and os.path.getmtime(so) > max(os.path.getmtime(d) for d in deps):
         return so
