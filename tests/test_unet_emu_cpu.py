@@ -1,4 +1,4 @@
-"""The whole tiny denoiser (reference architecture, model_channels 64, 1 - 2 frames, 8 x 8 latent) with every forward operator
+"""The whole tiny denoiser (reference architecture, model_channels 64, one frame, 8 x 8 latent) with every forward operator
 executed by the product's CUDA SOURCES on the host: tensor-core GEMMs / im2col convolutions (gemm_tc.cu), the tcgen05
 flash attention (attn_tc.cu), GroupNorm / LayerNorm / GEGLU / temporal attention / im2col (nn_kernels.cu) -- through
 tests/cuda_emu and tc_emu.h, bound under the same ctypes layer the GPU library sits behind.  Compared with the same network
@@ -39,7 +39,7 @@ def test_tiny_unet_forward_through_the_emulated_kernels(monkeypatch, emu_libs):
     nn, gemm, attn = emu_libs
     torch.manual_seed(0)
     ref, cfg = unet_ref.build_reference_unet(model_channels=64, device="cpu")
-    x, cc, ctx, _ = unet_ref.synth_inputs(1, 8, 8, device="cpu")  # one frame here; the gradient test below runs two
+    x, cc, ctx, _ = unet_ref.synth_inputs(1, 8, 8, device="cpu")
     xin = torch.cat([x, cc], 1)
     ts, fs = torch.tensor([481]), torch.tensor([10])
     with torch.no_grad():
@@ -85,7 +85,7 @@ def test_tiny_unet_input_gradient_through_the_emulated_kernels(monkeypatch, emu_
     abwd = gvd_native.bind_nn(C.CDLL(build_emu.build("attn_bwd_tc")), partial=True)
     torch.manual_seed(0)
     ref, cfg = unet_ref.build_reference_unet(model_channels=64, device="cpu")
-    x, cc, ctx, _ = unet_ref.synth_inputs(2, 8, 8, device="cpu")
+    x, cc, ctx, _ = unet_ref.synth_inputs(1, 8, 8, device="cpu")  # one frame: T > 1 is the business of the operator-level emulation tests
     xin = torch.cat([x, cc], 1)
     ts, fs = torch.tensor([300]), torch.tensor([10])
     g = torch.randn(1, 4, *xin.shape[2:], generator=torch.Generator().manual_seed(1))
